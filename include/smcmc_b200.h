@@ -1,0 +1,203 @@
+/* smcmc_b200.h -- C ABI of libsmcmc_b200.so, the B200 (sm_100a) ensemble
+ * Metropolis engine that sits behind the root-simple-mcmc header API.
+ *
+ * One engine handle owns, on one GPU, the device state of `chains`
+ * independent Markov chains of dimension `dim`:  the state that ONE
+ * sMCMC::TSimpleMCMC<L, TProposeAdaptiveStep> object holds on the host in the
+ * reference (TSimpleMCMC.H:543-589 and :1833-1976), replicated per chain.
+ * Every entry point below names the reference interface it replaces.  All
+ * pointers are HOST pointers unless a name ends in _dev; all functions return
+ * 0 on success and a negative smcmc_status otherwise, with a message
+ * available from smcmc_last_error().  A handle is not thread-safe; use one
+ * host thread per handle.  There is no CPU fallback: creating an engine
+ * without a CUDA device fails.
+ *
+ * Random draws: chain c (global index chain_offset + c) at step s uses slots
+ * 0..dim of the counter-based stream defined in smcmc_rng.h.
+ */
+#ifndef SMCMC_B200_H_SEEN
+#define SMCMC_B200_H_SEEN
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMCMC_B200_ABI_VERSION 1
+
+typedef struct smcmc_engine smcmc_engine;
+
+typedef enum smcmc_status {
+    SMCMC_OK = 0,
+    SMCMC_ERR_INVALID_ARGUMENT = -1, /* std::invalid_argument in the reference */
+    SMCMC_ERR_LOGIC = -2,            /* std::logic_error                      */
+    SMCMC_ERR_RUNTIME = -3,          /* std::runtime_error                    */
+    SMCMC_ERR_CUDA = -4,             /* CUDA runtime failure                  */
+    SMCMC_ERR_NO_DEVICE = -5         /* no usable sm_100 device               */
+} smcmc_status;
+
+/* Built-in device likelihood functors. */
+typedef enum smcmc_likelihood {
+    SMCMC_LLH_UNIT_GAUSS = 0, /* -1/2 sum x^2        TSimpleMCMC.H:111-120        */
+    SMCMC_LLH_DUMMY = 1,      /* -1/2 x^T E x        TDummyLogLikelihood.H:21-31  */
+    SMCMC_LLH_HORRIFIC = 2,   /* box + ridge         THorrificLogLikelihood.H:26-38 */
+    SMCMC_LLH_ASYM = 3,       /* piecewise linear    TAsymLogLikelihood.H:20-31   */
+    SMCMC_LLH_FAKE = 4        /* event reweighting + binned Poisson,
+                                 example/FakeLikelihood.H:47-81,188-216          */
+} smcmc_likelihood;
+
+typedef struct smcmc_config {
+    uint32_t struct_size;   /* sizeof(smcmc_config), for ABI growth            */
+    int32_t device;         /* CUDA device ordinal                             */
+    int32_t dim;            /* parameters per chain                            */
+    int32_t chains;         /* chains owned by this engine (this GPU's shard)  */
+    uint32_t chain_offset;  /* global index of local chain 0 (RNG addressing)  */
+    int32_t likelihood;     /* smcmc_likelihood                                */
+    uint64_t seed;          /* run seed (Philox key)                           */
+} smcmc_config;
+
+/* The reference's MC event record, example/Simulated.H:7-14, 48 bytes. */
+typedef struct smcmc_event {
+    double Mass;
+    int32_t Type;           /* 0 signal, >0 background, <0 data                */
+    int32_t pad0_;
+    double Separation;
+    int32_t MuDk;
+    int32_t pad1_;
+    double TrueMass;
+    double TrueMassSigma;
+} smcmc_event;
+
+/* Scalar settings of the adaptive proposal; each names the
+ * TProposeAdaptiveStep setter (TSimpleMCMC.H line) it stands for.  Settings
+ * apply to every chain of the engine. */
+typedef enum smcmc_prop_field {
+    SMCMC_PROP_SIGMA = 0,                /* SetSigma                       :775  */
+    SMCMC_PROP_TARGET_ACCEPTANCE = 1,    /* SetTargetAcceptance            :977  */
+    SMCMC_PROP_ACCEPTANCE_WINDOW = 2,    /* SetAcceptanceWindow            :982  */
+    SMCMC_PROP_ACCEPTANCE_RIGIDITY = 3,  /* SetAcceptanceRigidity          :1002 */
+    SMCMC_PROP_ACCEPTANCE_DEWEIGHT = 4,  /* SetAcceptanceUpdateDeweighting :987  */
+    SMCMC_PROP_COVARIANCE_WINDOW = 5,    /* SetCovarianceWindow            :914  */
+    SMCMC_PROP_COVARIANCE_DEWEIGHT = 6,  /* SetCovarianceUpdateDeweighting :927  */
+    SMCMC_PROP_COVARIANCE_FROZEN = 7,    /* SetCovarianceFrozen            :937  */
+    SMCMC_PROP_COVARIANCE_TRIALS = 8,    /* SetCovarianceTrials            :947  */
+    SMCMC_PROP_CENTER_TRIALS = 9,        /* SetEstimatedCenterTrials       :747  */
+    SMCMC_PROP_NEXT_UPDATE = 10,         /* SetNextUpdate                  :992  */
+    SMCMC_PROP_MAX_CORRELATION = 11,     /* SetMaximumCorrelation          :909  */
+    SMCMC_PROP_STEP_RMS_WINDOW = 12      /* TSimpleMCMC::SetStepRMSWindow  :511  */
+} smcmc_prop_field;
+
+/* Per-chain quantities readable with smcmc_get().  Arrays are chain-major:
+ * element (c, i) at [c*dim + i]; packed covariance is lower-triangular
+ * row-major exactly as the AdaptiveCovariance branch (TSimpleMCMC.H:1645-1649).
+ */
+typedef enum smcmc_field {
+    SMCMC_F_ACCEPTED = 0,        /* double[chains*dim]   GetAccepted              :502 */
+    SMCMC_F_PROPOSED = 1,        /* double[chains*dim]   GetProposed              :514 */
+    SMCMC_F_ACCEPTED_LLH = 2,    /* double[chains]       GetAcceptedLogLikelihood :499 */
+    SMCMC_F_PROPOSED_LLH = 3,    /* double[chains]       GetProposedLogLikelihood :505 */
+    SMCMC_F_STEP_RMS = 4,        /* double[chains]       GetStepRMS               :508 */
+    SMCMC_F_SIGMA = 5,           /* double[chains]       GetSigma                 :770 */
+    SMCMC_F_ACCEPTANCE = 6,      /* double[chains]       GetAcceptance            :781 */
+    SMCMC_F_ACCEPTANCE_TRIALS = 7, /* double[chains]     GetAcceptanceTrials      :782 */
+    SMCMC_F_ACCEPTANCE_RIGIDITY = 8, /* double[chains]   GetAcceptanceRigidity    :1003 */
+    SMCMC_F_TRIALS = 9,          /* int32[chains]        GetTrials                :762 */
+    SMCMC_F_SUCCESSES = 10,      /* int32[chains]        GetSuccesses             :765 */
+    SMCMC_F_NEXT_UPDATE = 11,    /* int32[chains]        GetNextUpdate            :993 */
+    SMCMC_F_COVARIANCE_TRIALS = 12, /* double[chains]    GetCovarianceTrials      :942 */
+    SMCMC_F_CENTER_TRIALS = 13,  /* double[chains]       GetEstimatedCenterTrials :741 */
+    SMCMC_F_CENTER = 14,         /* double[chains*dim]   GetEstimatedCenter       :732 */
+    SMCMC_F_COVARIANCE = 15,     /* double[chains*dim*(dim+1)/2] packed           */
+    SMCMC_F_COVARIANCE_TRACE = 16, /* double[chains]     GetCovarianceTrace       :961 */
+    SMCMC_F_DECOMPOSITION = 17,  /* double[chains*dim*dim] row-major U, fDecomposition :1893 */
+    SMCMC_F_TOTAL_STEPS = 18,    /* int32[chains]        fTotalSteps              :554 */
+    SMCMC_F_LLH_CALLS = 19,      /* int32[chains]        GetLogLikelihoodCount    :242 */
+    SMCMC_F_STATUS = 20,         /* int32[chains]        0 ok, else smcmc_status of the
+                                    exception the reference would have thrown    */
+    SMCMC_F_SIGMA_TRACE = 21,    /* double[chains]       fSigmaTrace              :1960 */
+    SMCMC_F_COVARIANCE_WINDOW = 22, /* double[1]         GetCovarianceWindow      :915 */
+    SMCMC_F_ACCEPTANCE_WINDOW = 23, /* double[1]         GetAcceptanceWindow      :983 */
+    SMCMC_F_TARGET_ACCEPTANCE = 24  /* double[1]         GetTargetAcceptance      :978 */
+} smcmc_field;
+
+/* Optional per-step trace of smcmc_step_trace(); any pointer may be NULL.
+ * Step-major: entry (s, c) at [s*chains + c], points at [(s*chains+c)*dim]. */
+typedef struct smcmc_trace {
+    int32_t* accepted;      /* return value of TSimpleMCMC::Step  :370 */
+    double* llh_accepted;   /* LogLikelihood branch               :208 */
+    double* llh_proposed;
+    double* points;         /* Accepted branch                    :210 */
+    double* sigma;          /* AdaptiveSigma branch               :1621 */
+    double* step_rms;       /* StepRMS branch                     :211 */
+} smcmc_trace;
+
+int smcmc_abi_version(void);
+
+/* Global (handle-less) error text of the last failed smcmc_create. */
+const char* smcmc_last_error(const smcmc_engine* e);
+
+/* TSimpleMCMC(TTree*, bool) constructor, TSimpleMCMC.H:203-224, for `chains`
+ * chains at once.  Allocates all device state. */
+int smcmc_create(const smcmc_config* cfg, smcmc_engine** out);
+int smcmc_destroy(smcmc_engine* e);
+
+/* Launch on the caller's CUDA stream (a cudaStream_t); NULL = default. */
+int smcmc_set_stream(smcmc_engine* e, void* cuda_stream);
+/* Block until all queued work is done; reports asynchronous errors. */
+int smcmc_sync(smcmc_engine* e);
+
+/* ---- proposal configuration: TProposeAdaptiveStep setters ---------------- */
+int smcmc_prop_set(smcmc_engine* e, int field, double value);
+int smcmc_prop_set_gaussian(smcmc_engine* e, int dim, double sigma);      /* :855 */
+int smcmc_prop_set_uniform(smcmc_engine* e, int dim, double lo, double hi); /* :833 */
+int smcmc_prop_set_correlation(smcmc_engine* e, int d1, int d2, double c);  /* :883 */
+int smcmc_prop_reset_correlations(smcmc_engine* e);                       /* :874 */
+int smcmc_prop_update(smcmc_engine* e);   /* UpdateProposal() on every chain :1009 */
+int smcmc_prop_reset(smcmc_engine* e);    /* ResetProposal()  on every chain :1396 */
+
+/* ---- likelihood inputs --------------------------------------------------- */
+/* FakeLikelihood::SimulatedSample (example/FakeLikelihood.H:30); events are
+ * copied to the device and re-laid-out there.  Replaces the sample. */
+int smcmc_fake_set_events(smcmc_engine* e, const smcmc_event* events, int64_t n);
+/* The three 50-bin data histograms in the order Close, Separated, DecayTag
+ * (FakeLikelihood.H:24-26, bins 1..50) and Corrections.ExposureRatio (:107). */
+int smcmc_fake_set_data(smcmc_engine* e, const double* data150, double exposure);
+/* FakeLikelihood::FillHistograms (:188-216) at m points: out[m*150] simulated
+ * bin contents, same order as data150. */
+int smcmc_fake_histograms(smcmc_engine* e, const double* x, int m, double* out);
+/* TDummyLogLikelihood::Error (TDummyLogLikelihood.H:147), n x n row-major. */
+int smcmc_dummy_set_error(smcmc_engine* e, const double* error, int n);
+
+/* ---- sampler ------------------------------------------------------------- */
+/* UserLikelihood::operator() at m arbitrary points (x[m*dim]) -> llh[m]. */
+int smcmc_eval(smcmc_engine* e, const double* x, int m, double* llh);
+/* TSimpleMCMC::Start (:246-276): x0[chains*dim]; ok[chains] (may be NULL)
+ * receives the per-chain return value. */
+int smcmc_start(smcmc_engine* e, const double* x0, int32_t* ok);
+/* nsteps calls of TSimpleMCMC::Step(false, metropolis) (:370-496) on every
+ * chain.  Asynchronous: returns after queueing the launches. */
+int smcmc_step(smcmc_engine* e, int nsteps, int metropolis);
+/* nsteps calls of Step(true, metropolis): as smcmc_step, then copies the
+ * per-step quantities a TTree::Fill would have recorded to host memory.
+ * Synchronous. */
+int smcmc_step_trace(smcmc_engine* e, int nsteps, int metropolis,
+                     const smcmc_trace* trace);
+/* Read a per-chain quantity (synchronous). */
+int smcmc_get(smcmc_engine* e, int field, void* dst, size_t bytes);
+
+/* ---- instrumentation ------------------------------------------------------ */
+/* Kernel launches issued by this engine so far. */
+int64_t smcmc_launch_count(const smcmc_engine* e);
+/* Device time (ms, CUDA events on the engine's stream) and launch count
+ * accumulated by the dominant event-pair kernel since the last reset. */
+int smcmc_pair_kernel_stats(smcmc_engine* e, double* total_ms, int64_t* launches,
+                            int reset);
+/* Enable (1) / disable (0) CUDA-event timing of the dominant kernel. */
+int smcmc_enable_kernel_timing(smcmc_engine* e, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

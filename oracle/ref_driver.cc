@@ -1,0 +1,392 @@
+// oracle/ref_driver.cc -- builds oracle/_ref/libsmcmc_ref.so.
+//
+// This translation unit #includes the reference's OWN headers, unmodified,
+// from where they lie under /root/reference (never copied into this repo)
+// and exposes them through the single-chain C interface of chain_api.h.
+// ROOT is replaced by oracle/rootshim.  The reference's global gRandom is
+// pointed at an injected generator that serves the counter-based stream of
+// include/smcmc_rng.h, so the reference consumes exactly the draws the device
+// consumes.  TEST INFRASTRUCTURE ONLY (see chain_api.h).
+//
+// Build: oracle/Makefile target `ref` (needs /root/reference).
+
+// Standard and shim headers first, so that the access-specifier override
+// below only touches the reference's own classes.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <iomanip>
+#include <iostream>
+#include <limits>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <TDecompChol.h>
+#include <TFile.h>
+#include <TH1D.h>
+#include <TMatrixD.h>
+#include <TMatrixDSymEigen.h>
+#include <TRandom.h>
+#include <TRandom3.h>
+#include <TTree.h>
+#include <TVectorD.h>
+
+#include "chain_api.h"
+#include "smcmc_rng.h"
+
+// Read-only test access to the proposal's covariance and decomposition.
+#define private public
+#define protected public
+#include "TSimpleMCMC.H"
+using namespace sMCMC;  // example/ predates the namespace
+#include "TDummyLogLikelihood.H"
+#include "THorrificLogLikelihood.H"
+#include "TAsymLogLikelihood.H"
+#include "example/FakeLikelihood.H"
+#undef private
+#undef protected
+
+namespace {
+
+std::string gLastError;
+
+// gRandom replacement: call k of step s of chain c returns slot k.
+class InjectedRandom : public TRandom {
+public:
+    InjectedRandom(uint64_t seed, uint32_t chain)
+        : fSeed(seed), fChain(chain), fStep(0), fSlot(0) {}
+    void Begin(uint32_t step) { fStep = step; fSlot = 0; }
+    virtual double Rndm() {
+        return smcmc_uniform(fSeed, fChain, fStep, fSlot++, SMCMC_STREAM_STEP);
+    }
+    virtual double UnitGaus() {
+        return smcmc_normal(fSeed, fChain, fStep, fSlot++, SMCMC_STREAM_STEP);
+    }
+private:
+    uint64_t fSeed;
+    uint32_t fChain, fStep, fSlot;
+};
+
+// The documentation example likelihood, TSimpleMCMC.H:111-120.
+class UnitGaussLikelihood {
+public:
+    double operator()(const Vector& point) const {
+        double logLikelihood = 0.0;
+        for (std::size_t i = 0; i < point.size(); ++i) {
+            logLikelihood += -0.5 * point[i] * point[i];
+        }
+        return logLikelihood;
+    }
+};
+
+struct ChainBase {
+    InjectedRandom rng;
+    uint32_t step;
+    int dim;
+    ChainBase(uint64_t seed, uint32_t chain, int d)
+        : rng(seed, chain), step(0), dim(d) {}
+    virtual ~ChainBase() {}
+    virtual TProposeAdaptiveStep& Prop() = 0;
+    virtual bool Start(const Vector& x) = 0;
+    virtual bool Step(int metropolis) = 0;
+    virtual double Llh(const Vector& x) = 0;
+    virtual const Vector& Accepted() = 0;
+    virtual double AcceptedLlh() = 0;
+    virtual double ProposedLlh() = 0;
+    virtual double StepRMS() = 0;
+    virtual int TotalSteps() = 0;
+    virtual int LlhCalls() = 0;
+    virtual void SetStepRMSWindow(int n) = 0;
+    virtual FakeLikelihood* Fake() { return 0; }
+};
+
+template <class L>
+struct Chain : public ChainBase {
+    TSimpleMCMC<L> mcmc;
+    Chain(uint64_t seed, uint32_t chain, int d)
+        : ChainBase(seed, chain, d), mcmc(NULL, false) {}
+    TProposeAdaptiveStep& Prop() { return mcmc.GetProposeStep(); }
+    bool Start(const Vector& x) { return mcmc.Start(x, false); }
+    bool Step(int metropolis) { return mcmc.Step(false, metropolis); }
+    double Llh(const Vector& x) { return mcmc.GetLogLikelihood()(x); }
+    const Vector& Accepted() { return mcmc.GetAccepted(); }
+    double AcceptedLlh() { return mcmc.GetAcceptedLogLikelihood(); }
+    double ProposedLlh() { return mcmc.GetProposedLogLikelihood(); }
+    double StepRMS() { return mcmc.GetStepRMS(); }
+    int TotalSteps() { return mcmc.fTotalSteps; }
+    int LlhCalls() { return mcmc.GetLogLikelihoodCount(); }
+    void SetStepRMSWindow(int n) { mcmc.SetStepRMSWindow(n); }
+};
+
+struct FakeChain : public Chain<FakeLikelihood> {
+    FakeChain(uint64_t seed, uint32_t chain, int d)
+        : Chain<FakeLikelihood>(seed, chain, d) {
+        FakeLikelihood& like = mcmc.GetLogLikelihood();
+        like.DataClose = like.DataSeparated = like.DataDecayTag = 0;
+        like.SimulatedClose = like.SimulatedSeparated = like.SimulatedDecayTag = 0;
+    }
+    FakeLikelihood* Fake() { return &mcmc.GetLogLikelihood(); }
+};
+
+ChainBase* H(void* h) { return static_cast<ChainBase*>(h); }
+
+template <class F>
+int Guard(F f) {
+    try {
+        return f();
+    } catch (std::exception& e) {
+        gLastError = e.what();
+        return -1;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ref_last_error(void) { return gLastError.c_str(); }
+
+void* ref_chain_create(int kind, int dim, uint64_t seed, uint32_t chain) {
+    ChainBase* c = 0;
+    switch (kind) {
+    case ORC_LLH_UNIT_GAUSS:
+        c = new Chain<UnitGaussLikelihood>(seed, chain, dim);
+        break;
+    case ORC_LLH_DUMMY: {
+        // As shipped: dim 100, VERY_CORRELATED (TDummyLogLikelihood.H:16,78).
+        Chain<TDummyLogLikelihood>* d = new Chain<TDummyLogLikelihood>(seed, chain, 100);
+        if (dim != 100) { delete d; gLastError = "reference TDummyLogLikelihood is 100-dim"; return 0; }
+        std::streambuf* old = std::cout.rdbuf(0);
+        d->mcmc.GetLogLikelihood().Init();
+        std::cout.rdbuf(old);
+        c = d;
+        break;
+    }
+    case ORC_LLH_HORRIFIC:
+        if (dim != 75) { gLastError = "reference THorrificLogLikelihood is 75-dim"; return 0; }
+        c = new Chain<THorrificLogLikelihood>(seed, chain, 75);
+        break;
+    case ORC_LLH_ASYM:
+        if (dim != 100) { gLastError = "reference TASymLogLikelihood is 100-dim"; return 0; }
+        c = new Chain<TASymLogLikelihood>(seed, chain, 100);
+        break;
+    case ORC_LLH_FAKE:
+        if (dim != (int)SystematicCorrection::kParamSize) { gLastError = "FakeLikelihood is 9-dim"; return 0; }
+        c = new FakeChain(seed, chain, dim);
+        break;
+    default:
+        gLastError = "unknown likelihood kind";
+        return 0;
+    }
+    c->Prop().SetDim(c->dim);
+    return c;
+}
+
+void ref_chain_destroy(void* h) { delete H(h); }
+
+int ref_chain_set_fake(void* h, const orc_event* ev, long n,
+                       const double* data150, double exposure) {
+    FakeLikelihood* like = H(h)->Fake();
+    if (!like) { gLastError = "not a FakeLikelihood chain"; return -1; }
+    static_assert(sizeof(Simulated::Event) == sizeof(orc_event), "event layout");
+    like->SimulatedSample.resize(n);
+    std::memcpy((void*)like->SimulatedSample.data(), ev, sizeof(orc_event) * n);
+    // Same histogram geometry as FakeData::FillData (example/FakeData.H:94-104).
+    TH1D* close = new TH1D("DataClose", "", 50, 0.0, 500.0);
+    TH1D* separated = new TH1D("DataSeparated", "", 50, 0.0, 500.0);
+    TH1D* tag = new TH1D("DataDecayTag", "", 50, 0.0, 500.0);
+    for (int b = 0; b < 50; ++b) {
+        close->SetBinContent(b + 1, data150[b]);
+        separated->SetBinContent(b + 1, data150[50 + b]);
+        tag->SetBinContent(b + 1, data150[100 + b]);
+    }
+    like->DataClose = close;
+    like->DataSeparated = separated;
+    like->DataDecayTag = tag;
+    like->SimulatedSeparated = (TH1D*)separated->Clone("simSeparated");
+    like->SimulatedClose = (TH1D*)close->Clone("simClose");
+    like->SimulatedDecayTag = (TH1D*)tag->Clone("simDecayTag");
+    like->Corrections.ExposureRatio = exposure;
+    return 0;
+}
+
+int ref_chain_set_error_matrix(void*, const double*, int) {
+    gLastError = "the reference builds its own error matrix in Init()";
+    return -1;
+}
+
+int ref_chain_set(void* h, int field, double v) {
+    TProposeAdaptiveStep& p = H(h)->Prop();
+    switch (field) {
+    case ORC_SET_SIGMA: p.SetSigma(v); break;
+    case ORC_SET_TARGET_ACCEPTANCE: p.SetTargetAcceptance(v); break;
+    case ORC_SET_ACCEPTANCE_WINDOW: p.SetAcceptanceWindow(v); break;
+    case ORC_SET_ACCEPTANCE_RIGIDITY: p.SetAcceptanceRigidity(v); break;
+    case ORC_SET_ACCEPTANCE_DEWEIGHT: p.SetAcceptanceUpdateDeweighting(v); break;
+    case ORC_SET_COVARIANCE_WINDOW: p.SetCovarianceWindow((int)v); break;
+    case ORC_SET_COVARIANCE_DEWEIGHT: p.SetCovarianceUpdateDeweighting(v); break;
+    case ORC_SET_COVARIANCE_FROZEN: p.SetCovarianceFrozen(v != 0.0); break;
+    case ORC_SET_COVARIANCE_TRIALS: p.SetCovarianceTrials(v); break;
+    case ORC_SET_CENTER_TRIALS: p.SetEstimatedCenterTrials(v); break;
+    case ORC_SET_NEXT_UPDATE: p.SetNextUpdate(v); break;
+    case ORC_SET_MAX_CORRELATION: p.SetMaximumCorrelation(v); break;
+    case ORC_SET_STEP_RMS_WINDOW: H(h)->SetStepRMSWindow((int)v); break;
+    default: gLastError = "unknown field"; return -1;
+    }
+    return 0;
+}
+
+int ref_chain_set_gaussian(void* h, int d, double sigma) {
+    H(h)->Prop().SetGaussian(d, sigma);
+    return 0;
+}
+
+int ref_chain_set_uniform(void* h, int d, double lo, double hi) {
+    H(h)->Prop().SetUniform(d, lo, hi);
+    return 0;
+}
+
+int ref_chain_set_correlation(void* h, int d1, int d2, double c) {
+    H(h)->Prop().SetCorrelation(d1, d2, c);
+    return 0;
+}
+
+int ref_chain_start(void* h, const double* x0) {
+    ChainBase* c = H(h);
+    return Guard([&]() {
+        gRandom = &c->rng;
+        Vector x(x0, x0 + c->dim);
+        return c->Start(x) ? 1 : 0;
+    });
+}
+
+int ref_chain_step(void* h, int nsteps, int metropolis, int32_t* accepted,
+                   double* llhAccepted, double* llhProposed, double* x,
+                   double* sigma) {
+    ChainBase* c = H(h);
+    return Guard([&]() {
+        gRandom = &c->rng;
+        for (int s = 0; s < nsteps; ++s) {
+            c->rng.Begin(c->step++);
+            bool ok = c->Step(metropolis);
+            if (accepted) accepted[s] = ok ? 1 : 0;
+            if (llhAccepted) llhAccepted[s] = c->AcceptedLlh();
+            if (llhProposed) llhProposed[s] = c->ProposedLlh();
+            if (sigma) sigma[s] = c->Prop().GetSigma();
+            if (x) std::copy(c->Accepted().begin(), c->Accepted().end(),
+                             x + (size_t)s * c->dim);
+        }
+        return 0;
+    });
+}
+
+int ref_chain_update_proposal(void* h) {
+    return Guard([&]() { H(h)->Prop().UpdateProposal(); return 0; });
+}
+
+int ref_chain_reset_proposal(void* h) {
+    return Guard([&]() { H(h)->Prop().ResetProposal(); return 0; });
+}
+
+int ref_chain_get_state(void* h, double* s, double* accepted, double* center,
+                        double* cov, double* decomp) {
+    ChainBase* c = H(h);
+    TProposeAdaptiveStep& p = c->Prop();
+    const int n = c->dim;
+    if (s) {
+        s[ORC_ST_SIGMA] = p.GetSigma();
+        s[ORC_ST_ACCEPTANCE] = p.GetAcceptance();
+        s[ORC_ST_ACCEPTANCE_TRIALS] = p.GetAcceptanceTrials();
+        s[ORC_ST_ACCEPTANCE_WINDOW] = p.GetAcceptanceWindow();
+        s[ORC_ST_ACCEPTANCE_RIGIDITY] = p.GetAcceptanceRigidity();
+        s[ORC_ST_TARGET_ACCEPTANCE] = p.GetTargetAcceptance();
+        s[ORC_ST_TRIALS] = p.GetTrials();
+        s[ORC_ST_SUCCESSES] = p.GetSuccesses();
+        s[ORC_ST_NEXT_UPDATE] = p.GetNextUpdate();
+        s[ORC_ST_COVARIANCE_TRIALS] = p.GetCovarianceTrials();
+        s[ORC_ST_COVARIANCE_WINDOW] = p.GetCovarianceWindow();
+        s[ORC_ST_CENTER_TRIALS] = p.GetEstimatedCenterTrials();
+        s[ORC_ST_COVARIANCE_TRACE] =
+            p.fCurrentCov.GetNrows() == n ? p.GetCovarianceTrace() : 0.0;
+        s[ORC_ST_SIGMA_TRACE] = p.fSigmaTrace;
+        s[ORC_ST_STEP_RMS] = c->StepRMS();
+        s[ORC_ST_ACCEPTED_LLH] = c->AcceptedLlh();
+        s[ORC_ST_PROPOSED_LLH] = c->ProposedLlh();
+        s[ORC_ST_TOTAL_STEPS] = c->TotalSteps();
+        s[ORC_ST_LLH_CALLS] = c->LlhCalls();
+    }
+    if (accepted) std::copy(c->Accepted().begin(), c->Accepted().end(), accepted);
+    if (center) std::copy(p.GetEstimatedCenter().begin(), p.GetEstimatedCenter().end(), center);
+    if (cov && p.fCurrentCov.GetNrows() == n)
+        std::copy(p.fCurrentCov.GetMatrixArray(), p.fCurrentCov.GetMatrixArray() + (size_t)n * n, cov);
+    if (decomp && p.fDecomposition.GetNrows() == n)
+        std::copy(p.fDecomposition.GetMatrixArray(), p.fDecomposition.GetMatrixArray() + (size_t)n * n, decomp);
+    return 0;
+}
+
+double ref_chain_llh(void* h, const double* x) {
+    ChainBase* c = H(h);
+    Vector p(x, x + c->dim);
+    return c->Llh(p);
+}
+
+int ref_chain_fake_hist(void* h, const double* x, double* out150) {
+    FakeLikelihood* like = H(h)->Fake();
+    if (!like) { gLastError = "not a FakeLikelihood chain"; return -1; }
+    std::vector<double> p(x, x + H(h)->dim);
+    like->FillHistograms(p);
+    for (int b = 0; b < 50; ++b) {
+        out150[b] = like->SimulatedClose->GetBinContent(b + 1);
+        out150[50 + b] = like->SimulatedSeparated->GetBinContent(b + 1);
+        out150[100 + b] = like->SimulatedDecayTag->GetBinContent(b + 1);
+    }
+    return 0;
+}
+
+// TDummyLogLikelihood::Covariance / Error as built by the reference's Init()
+// (TDummyLogLikelihood.H:44-142); both are 100 x 100, row-major.
+int ref_dummy_matrices(double* covariance, double* error) {
+    if (TDummyLogLikelihood::Error.GetNrows() != 100) {
+        TDummyLogLikelihood like;
+        std::streambuf* old = std::cout.rdbuf(0);
+        like.Init();
+        std::cout.rdbuf(old);
+    }
+    if (covariance) std::copy(TDummyLogLikelihood::Covariance.GetMatrixArray(),
+                              TDummyLogLikelihood::Covariance.GetMatrixArray() + 10000, covariance);
+    if (error) std::copy(TDummyLogLikelihood::Error.GetMatrixArray(),
+                         TDummyLogLikelihood::Error.GetMatrixArray() + 10000, error);
+    return 0;
+}
+
+// The reference's own toy-input generators (example/Simulated.H:17-53 and
+// example/FakeData.H:32-117) run under a seeded shim generator; used to check
+// that the product's synthetic-input builder follows the same distributions.
+long ref_fake_generate(unsigned long seed, int dataSignal, int dataBackground,
+                       double oversample, orc_event* outEvents, long capacity,
+                       double* outData150, double* outExposure) {
+    TRandom* saved = gRandom;
+    TRandom3 local(seed);
+    gRandom = &local;
+    FakeLikelihood like;
+    std::streambuf* old = std::cout.rdbuf(0);
+    like.Init(dataSignal, dataBackground, oversample);
+    std::cout.rdbuf(old);
+    gRandom = saved;
+    long n = (long)like.SimulatedSample.size();
+    if (n > capacity) n = capacity;
+    if (outEvents) std::memcpy((void*)outEvents, like.SimulatedSample.data(), sizeof(orc_event) * n);
+    if (outData150) {
+        for (int b = 0; b < 50; ++b) {
+            outData150[b] = like.DataClose->GetBinContent(b + 1);
+            outData150[50 + b] = like.DataSeparated->GetBinContent(b + 1);
+            outData150[100 + b] = like.DataDecayTag->GetBinContent(b + 1);
+        }
+    }
+    if (outExposure) *outExposure = like.Corrections.ExposureRatio;
+    return (long)like.SimulatedSample.size();
+}
+
+}  // extern "C"

@@ -1,0 +1,755 @@
+// oracle/smcmc_oracle.cc -- the CPU restatement ("port") of the hot path.
+//
+// TEST INFRASTRUCTURE ONLY.  This file restates, in plain C++ over flat
+// arrays and with NO dependency on ROOT or on the reference tree, the
+// algorithm of the path BASELINE.json names: the Metropolis step
+// (TSimpleMCMC.H:370-496), the adaptive proposal (TSimpleMCMC.H:640-1831) and
+// the likelihood functors of SURVEY.md section 8a.  Each function cites the
+// reference lines it follows.  It is pinned by tests/test_oracle_vs_ref.py,
+// which runs it side by side with oracle/_ref/libsmcmc_ref.so (the
+// reference's own headers compiled unmodified) on identical injected draws
+// and requires bit-identical chains, and by the golden vectors in
+// tests/golden/ that were produced by that reference build.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference legs may load the resulting library.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "chain_api.h"
+#include "smcmc_rng.h"
+
+namespace {
+
+std::string gLastError;
+
+// ---------------------------------------------------------------------------
+// Third-party (ROOT) primitives, restated [SURVEY.md A.6].
+// ---------------------------------------------------------------------------
+
+// TDecompChol::Decompose: a = U^T U, column ordered, upper triangle only.
+// Returns false on a non-positive pivot.  `a` and `u` are n x n row-major.
+bool CholeskyUpper(const std::vector<double>& a, std::vector<double>& u, int n) {
+    u = a;
+    for (int c = 0; c < n; ++c) {
+        double pivot = u[(size_t)c * n + c];
+        for (int r = 0; r < c; ++r) pivot -= u[(size_t)r * n + c] * u[(size_t)r * n + c];
+        if (pivot <= 0.0) return false;
+        pivot = std::sqrt(pivot);
+        u[(size_t)c * n + c] = pivot;
+        for (int j = c + 1; j < n; ++j) {
+            double v = u[(size_t)c * n + j];
+            for (int r = 0; r < c; ++r) v -= u[(size_t)r * n + j] * u[(size_t)r * n + c];
+            u[(size_t)c * n + j] = v / pivot;
+        }
+    }
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < i; ++j) u[(size_t)i * n + j] = 0.0;
+    return true;
+}
+
+// TMatrixDSymEigen: eigenvalues descending, eigenvectors in columns.  Cyclic
+// Jacobi, the same procedure as oracle/rootshim/TMatrixD.h (the true ROOT
+// routine is tridiagonalisation + QL; eigenvectors are only defined up to
+// sign/order, so this stage is property-tested).
+void SymEigen(const std::vector<double>& in, int n, std::vector<double>& vec,
+              std::vector<double>& val) {
+    std::vector<double> a(in);
+    std::vector<double> v((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i) v[(size_t)i * n + i] = 1.0;
+    for (int sweep = 0; sweep < 100; ++sweep) {
+        double off = 0.0;
+        for (int p = 0; p < n; ++p)
+            for (int q = p + 1; q < n; ++q) off += a[(size_t)p * n + q] * a[(size_t)p * n + q];
+        if (!(off > 1e-300)) break;
+        for (int p = 0; p < n; ++p) {
+            for (int q = p + 1; q < n; ++q) {
+                double apq = a[(size_t)p * n + q];
+                if (apq == 0.0) continue;
+                double theta = (a[(size_t)q * n + q] - a[(size_t)p * n + p]) / (2.0 * apq);
+                double t = (theta >= 0 ? 1.0 : -1.0) / (std::abs(theta) + std::sqrt(theta * theta + 1.0));
+                double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < n; ++k) {
+                    double akp = a[(size_t)k * n + p], akq = a[(size_t)k * n + q];
+                    a[(size_t)k * n + p] = c * akp - s * akq;
+                    a[(size_t)k * n + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < n; ++k) {
+                    double apk = a[(size_t)p * n + k], aqk = a[(size_t)q * n + k];
+                    a[(size_t)p * n + k] = c * apk - s * aqk;
+                    a[(size_t)q * n + k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < n; ++k) {
+                    double vkp = v[(size_t)k * n + p], vkq = v[(size_t)k * n + q];
+                    v[(size_t)k * n + p] = c * vkp - s * vkq;
+                    v[(size_t)k * n + q] = s * vkp + c * vkq;
+                }
+            }
+        }
+    }
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+        return a[(size_t)x * n + x] > a[(size_t)y * n + y];
+    });
+    val.assign(n, 0.0);
+    vec.assign((size_t)n * n, 0.0);
+    for (int c = 0; c < n; ++c) {
+        val[c] = a[(size_t)order[c] * n + order[c]];
+        for (int r = 0; r < n; ++r) vec[(size_t)r * n + c] = v[(size_t)r * n + order[c]];
+    }
+}
+
+// TAxis::FindBin for the example's 50 bins on [0,500).
+inline int FindBin50(double x) {
+    if (x < 0.0) return 0;
+    if (!(x < 500.0)) return 51;
+    return 1 + int(50 * (x - 0.0) / (500.0 - 0.0));
+}
+
+// ---------------------------------------------------------------------------
+// Likelihoods.
+// ---------------------------------------------------------------------------
+struct Likelihood {
+    int kind = ORC_LLH_UNIT_GAUSS;
+    int dim = 0;
+    std::vector<double> error;          // ORC_LLH_DUMMY: n x n row-major
+    std::vector<orc_event> events;      // ORC_LLH_FAKE
+    double data[150];                   // close, separated, decay-tag
+    double exposure = 1.0;
+    double sim[3][52];                  // filled by FillFake
+
+    // example/SystematicCorrection.H:50-79
+    static double InvariantMass(const orc_event& e, const double* p) {
+        double mass = e.Mass;
+        if (e.Type < 0) return mass;
+        double nomLogMass = std::log(e.TrueMass);
+        double nomLogSigma = std::log(e.TrueMass + e.TrueMassSigma);
+        nomLogSigma = nomLogSigma - nomLogMass;
+        double logMass = std::log(mass);
+        double logSigma = (logMass - nomLogMass) / nomLogSigma;
+        double scale = p[2] / 10.0;
+        double width = std::exp(p[3] / 10.0);
+        double skew = 0.3 * std::erf(p[4] / 10.0);
+        skew = std::exp(logSigma * skew);
+        logMass = nomLogMass + (logMass - nomLogMass) * skew;
+        logMass = nomLogMass + (logMass - nomLogMass) * width;
+        logMass = logMass + scale;
+        return std::exp(logMass);
+    }
+    // example/SystematicCorrection.H:35-48
+    static double Separation(const orc_event& e, const double* p) {
+        if (e.Type < 0) return e.Separation;
+        double scale = 0.0;
+        if (e.Type == 0) scale += p[5];
+        if (e.Type > 0) scale += p[6];
+        scale = std::exp(scale / 10.0);
+        return e.Separation * scale;
+    }
+    // example/SystematicCorrection.H:81-117
+    double EventWeight(const orc_event& e, const double* p) const {
+        double weight = 1.0;
+        if (e.Type < 0) return weight;
+        if (e.Type == 0) weight *= std::exp(p[0] / 10.0);
+        else weight *= std::exp(p[1] / 10.0);
+        const double trueFakes = 0.05;
+        double fakes = std::tan(M_PI * (trueFakes - 0.5));
+        fakes += p[7];
+        fakes = std::atan(fakes) / M_PI + 0.5;
+        if (e.Type == 0) {
+            if (e.MuDk > 0) weight *= fakes / trueFakes;
+            else weight *= (1.0 - fakes) / (1.0 - trueFakes);
+        }
+        const double trueEff = 0.5;
+        double eff = std::tan(M_PI * (trueEff - 0.5));
+        eff += p[8];
+        eff = std::atan(eff) / M_PI + 0.5;
+        if (e.Type > 0) {
+            if (e.MuDk > 0) weight *= eff / trueEff;
+            else weight *= (1.0 - eff) / (1.0 - trueEff);
+        }
+        weight *= exposure;
+        return weight;
+    }
+    // example/FakeLikelihood.H:188-216
+    void FillFake(const double* p) {
+        std::memset(sim, 0, sizeof(sim));
+        for (size_t i = 0; i < events.size(); ++i) {
+            const orc_event& e = events[i];
+            double mass = InvariantMass(e, p);
+            double sep = Separation(e, p);
+            double w = EventWeight(e, p);
+            if (mass > 500.0) continue;
+            if (mass < 0.0) continue;
+            if (sep < 0.0) continue;
+            int h = 1;                       // separated
+            if (e.MuDk > 0) h = 2;           // decay tag
+            else if (sep < 100.0) h = 0;     // close
+            sim[h][FindBin50(mass)] += w;
+        }
+    }
+    // example/FakeLikelihood.H:47-81
+    double EvalFake(const double* p) {
+        FillFake(p);
+        double logLikelihood = 0.0;
+        for (int h = 0; h < 3; ++h) {
+            for (int b = 1; b <= 50; ++b) {
+                double d = data[h * 50 + b - 1];
+                double mc = sim[h][b];
+                if (mc < 0.001) mc = 0.001;
+                double v = d - mc;
+                if (d > 0.0) v += d * std::log(mc / d);
+                logLikelihood += v;
+            }
+        }
+        return logLikelihood;
+    }
+
+    double operator()(const double* x) {
+        switch (kind) {
+        case ORC_LLH_UNIT_GAUSS: {           // TSimpleMCMC.H:113-119
+            double s = 0.0;
+            for (int i = 0; i < dim; ++i) s += -0.5 * x[i] * x[i];
+            return s;
+        }
+        case ORC_LLH_DUMMY: {                // TDummyLogLikelihood.H:21-31
+            double s = 0.0;
+            for (int i = 0; i < dim; ++i)
+                for (int j = 0; j < dim; ++j)
+                    s -= 0.5 * x[i] * error[(size_t)j * dim + i] * x[j];
+            return s;
+        }
+        case ORC_LLH_HORRIFIC: {             // THorrificLogLikelihood.H:26-38
+            const double sigma = 0.01;
+            double s = 0.0;
+            for (int i = 0; i < dim; ++i) {
+                if (std::abs(x[i]) > 1.0) return -1E+30;
+                s += x[i];
+            }
+            double naturalSigma = std::sqrt(dim * 4.0 / 12.0);
+            s /= naturalSigma;
+            s = -0.5 * s * s / sigma / sigma;
+            return s;
+        }
+        case ORC_LLH_ASYM: {                 // TAsymLogLikelihood.H:20-31
+            double s = 0.0;
+            for (int i = 0; i < dim; ++i) {
+                double a = x[i];
+                if (a < 0.0) a *= 100.0;
+                else a *= -1.0;
+                s += a;
+            }
+            return s;
+        }
+        case ORC_LLH_FAKE:
+            return EvalFake(x);
+        }
+        return std::numeric_limits<double>::quiet_NaN();
+    }
+};
+
+// ---------------------------------------------------------------------------
+// TProposeAdaptiveStep (TSimpleMCMC.H:640-1977), flat-array restatement.
+// ---------------------------------------------------------------------------
+struct Proposal {
+    int n = 0;
+    uint64_t seed = 0;
+    uint32_t chain = 0;
+    std::vector<double> lastPoint, center, centerChange, cov, decomp;
+    std::vector<int> type;
+    std::vector<double> param1, param2;
+    struct Corr { int d1, d2; double c; };
+    std::vector<Corr> corr;
+    double lastValue = 0.0;
+    double centerTrials = 0.0, covTrials = 0.0, covDeweight = 0.5;
+    bool covFrozen = false;
+    double covWindow = -1;
+    int trials = 0, successes = 0, nextUpdate = -1;
+    double acceptance = 0.0, acceptanceTrials = 0.0, acceptanceDeweight = 0.5;
+    double acceptanceWindow = -1, rigidity = 2.0, target = -1;
+    double sigma = 0.0, sigmaTrace = 0.0;
+    double maxCorrelation = 1.0 - std::sqrt(std::numeric_limits<double>::epsilon());
+    bool initialized = false;
+    bool failed = false;
+
+    void SetDim(int d) {                      // :786-795
+        if (!lastPoint.empty()) return;
+        n = d;
+        lastPoint.assign(d, 0.0);
+        type.assign(d, 0);
+        param1.assign(d, 0.0);
+        param2.assign(d, 0.0);
+    }
+    double Trace() const {                    // :961-967
+        double t = 0.0;
+        for (int i = 0; i < n; ++i) t += cov[(size_t)i * n + i];
+        return t;
+    }
+    void SetCorrelation(int d1, int d2, double c) {   // :883-904
+        if (d1 == d2) return;
+        if (c < -maxCorrelation) c = -maxCorrelation;
+        if (c > maxCorrelation) c = maxCorrelation;
+        corr.push_back(Corr{d1, d2, c});
+    }
+
+    // :1009-1390.  Returns false when the reference would throw.
+    bool UpdateProposal(bool fromReset) {
+        double trace = Trace();
+        if (trace <= 0) { gLastError = "Invalid trace"; return false; }      // :1024-1028
+        sigma = sigma * std::sqrt(sigmaTrace / trace);                       // :1042
+        sigmaTrace = trace;
+        double maxUp = (double)((size_t)n * (size_t)n);                      // :1050-1052
+        double up = 0.5 * successes;
+        nextUpdate = (int)(acceptanceWindow + maxUp - maxUp / (up + 1.0));
+        if (covDeweight > 0.0) {                                             // :1056-1067
+            if (covDeweight > 1.0) covDeweight = 1.0;
+            double w = 1.0 - covDeweight;
+            covTrials = std::max(1.0, w * covTrials);
+            covTrials = std::min(covTrials, w * covWindow);
+            centerTrials = std::max(1.0, w * centerTrials);
+            centerTrials = std::min(centerTrials, w * covWindow);
+        }
+        if (acceptanceDeweight > 0.0) {                                      // :1081-1086
+            if (acceptanceDeweight > 1.0) acceptanceDeweight = 1.0;
+            double w = 1.0 - acceptanceDeweight;
+            acceptanceTrials = std::max(1.0, w * acceptanceTrials);
+            acceptanceTrials = std::min(acceptanceTrials, w * acceptanceWindow);
+        }
+        const double minVar = std::numeric_limits<double>::epsilon();
+        std::vector<double> u;
+        if (CholeskyUpper(cov, u, n)) { decomp = u; return true; }           // :1103-1120
+        // Condition the variances, :1134-1183.
+        for (int i = 0; i < n; ++i) {
+            double expected = 1.0;
+            if (type[i] == 0) {
+                if (param1[i] > 0) expected = param1[i];
+            } else {
+                expected = param2[i];
+                expected -= param1[i];
+                expected = expected * expected / 12.0;
+            }
+            double& v = cov[(size_t)i * n + i];
+            if (!std::isfinite(v)) v = expected;
+            if (v < 0.0) v = minVar * expected;
+            if (v < minVar * expected) v = minVar * expected;
+            if (v < minVar) v = minVar;
+        }
+        // Condition the correlations, :1187-1217.
+        for (int i = 0; i < n; ++i) {
+            for (int j = i + 1; j < n; ++j) {
+                double c = cov[(size_t)i * n + j];
+                c /= std::sqrt(cov[(size_t)i * n + i]);
+                c /= std::sqrt(cov[(size_t)j * n + j]);
+                if (!std::isfinite(c)) c = 0.0;
+                if (std::abs(c) > maxCorrelation) c = (c > 0.0) ? maxCorrelation : -maxCorrelation;
+                double v = c;
+                v *= std::sqrt(cov[(size_t)i * n + i]);
+                v *= std::sqrt(cov[(size_t)j * n + j]);
+                cov[(size_t)i * n + j] = v;
+                cov[(size_t)j * n + i] = v;
+            }
+        }
+        if (CholeskyUpper(cov, u, n)) { decomp = u; return true; }           // :1220-1239
+        // Eigen-decomposition fallback, :1252-1321.
+        {
+            std::vector<double> sym((size_t)n * n), vec, val;
+            for (int i = 0; i < n; ++i)
+                for (int j = i; j < n; ++j)
+                    sym[(size_t)j * n + i] = sym[(size_t)i * n + j] = cov[(size_t)i * n + j];
+            SymEigen(sym, n, vec, val);
+            double eigenSum = 0.0;
+            for (int i = 0; i < n; ++i) {
+                if (val[i] < 0.0) continue;
+                eigenSum += val[i];
+            }
+            double minAxis = 1.0 - maxCorrelation;
+            if (minAxis < minVar) minAxis = minVar;
+            minAxis = minAxis * val[0];
+            for (int i = 0; i < n; ++i) {
+                double rms = std::sqrt(std::max(minAxis, val[i]));
+                for (int j = 0; j < n; ++j) decomp[(size_t)i * n + j] = rms * vec[(size_t)j * n + i];
+            }
+            if (eigenSum > 1E-6) return true;
+        }
+        // Emergency shrink, :1335-1377.
+        double step = std::numeric_limits<double>::epsilon();
+        for (int i = 0; i < n; ++i) step = std::max(step, cov[(size_t)i * n + i]);
+        step *= 1E-4;
+        double dec = 1.0;
+        for (int trial = 0; trial < 10; ++trial) {
+            dec *= 0.84;
+            for (int i = 0; i < n; ++i) {
+                cov[(size_t)i * n + i] += step;
+                for (int j = i + 1; j < n; ++j) {
+                    double v = dec * cov[(size_t)i * n + j];
+                    cov[(size_t)j * n + i] = v;
+                    cov[(size_t)i * n + j] = v;
+                }
+            }
+            if (CholeskyUpper(cov, u, n)) { decomp = u; return true; }
+        }
+        if (fromReset) { gLastError = "Decomposition of user correlations failed"; return false; }
+        return ResetProposal();                                             // :1389
+    }
+
+    // :1396-1494
+    bool ResetProposal() {
+        trials = 0;
+        successes = 0;
+        if (sigma < 0.01 * std::sqrt(1.0 / n)) sigma = std::sqrt(1.0 / n);
+        decomp.resize((size_t)n * n, 0.0);
+        cov.resize((size_t)n * n, 0.0);
+        for (int i = 0; i < n; ++i) {
+            for (int j = i; j < n; ++j) {
+                if (i == j && type[i] == 0 && param1[i] > 0) cov[(size_t)i * n + i] = param1[i];
+                else if (i == j && type[i] == 1) {
+                    double delta = param1[i];
+                    delta -= param2[i];
+                    cov[(size_t)i * n + i] = delta * delta / 12.0;
+                } else if (i == j) cov[(size_t)i * n + i] = 1.0;
+                else cov[(size_t)i * n + j] = cov[(size_t)j * n + i] = 0.0;
+            }
+        }
+        for (size_t k = 0; k < corr.size(); ++k) {                           // :1445-1457
+            const Corr& c = corr[k];
+            if (c.d1 == c.d2) continue;
+            double v1 = cov[(size_t)c.d1 * n + c.d1];
+            double v2 = cov[(size_t)c.d2 * n + c.d2];
+            double v = c.c * std::sqrt(v1) * std::sqrt(v2);
+            cov[(size_t)c.d1 * n + c.d2] = v;
+            cov[(size_t)c.d2 * n + c.d1] = v;
+        }
+        sigmaTrace = Trace();                                                // :1460
+        int minWindow = 100 + 4 * n;                                         // :1468-1476
+        if (covWindow < minWindow) {
+            covWindow = n;
+            covWindow *= n;
+            covWindow *= n;
+            covWindow += minWindow;
+            double r = std::numeric_limits<double>::epsilon();
+            covWindow = std::min(covWindow, std::sqrt(1.0 / r));
+        }
+        if (target < 0.0) { gLastError = "Target acceptance not initialized"; return false; }
+        acceptance = target;                                                 // :1481-1482
+        acceptanceTrials = std::min(10.0, 0.5 * acceptanceWindow);
+        center = lastPoint;                                                  // :1484-1491
+        centerChange.assign(n, 0.0);
+        centerTrials = std::max(centerTrials, 1.0);
+        return UpdateProposal(true);
+    }
+
+    // :1679-1714
+    bool InitializeState(const double* current, double value) {
+        if (initialized) return true;
+        initialized = true;
+        if (lastPoint.empty()) SetDim(n);
+        lastValue = value;
+        std::copy(current, current + n, lastPoint.begin());
+        if (acceptanceWindow < 0) acceptanceWindow = std::pow(1.0 * n, 1.5) + 1000;
+        nextUpdate = (int)acceptanceWindow;
+        if (target < 1E-4) {
+            if (n > 4) target = 0.234;
+            else target = 0.44;
+        }
+        return ResetProposal();
+    }
+
+    // :1721-1831
+    bool UpdateState(const double* current, double value) {
+        if (!InitializeState(current, value)) return false;
+        ++trials;
+        bool accepted = false;
+        if (value != lastValue || current[0] != lastPoint[0]) accepted = true;
+        if (accepted) ++successes;
+        acceptance *= acceptanceTrials;
+        if (accepted) acceptance = acceptance + 1.0;
+        acceptance /= acceptanceTrials + 1.0;
+        acceptanceTrials = std::min(acceptanceWindow, acceptanceTrials + 1.0);
+        if (rigidity < 500.0 && rigidity > 0.0) {                            // :1745-1762
+            double accSigma = target * (1.0 - target);
+            accSigma = std::sqrt(accSigma / acceptanceWindow);
+            if (std::abs(acceptance - target) < accSigma) {
+                rigidity += 0.5 * rigidity / acceptanceWindow;
+                rigidity = std::min(200.0, rigidity);
+            }
+            if (std::abs(acceptance - target) > 4.0 * accSigma) {
+                rigidity -= 1.618 * 0.5 * rigidity / acceptanceWindow;
+                rigidity = std::max(2.0, rigidity);
+            }
+        }
+        if (rigidity > 0 && rigidity < 100.0) {                              // :1771-1776
+            sigma *= std::pow(acceptance / target,
+                              std::min(1.0 / 500.0, 1.0 / (rigidity * acceptanceWindow)));
+        }
+        for (int i = 0; i < n; ++i) {                                        // :1780-1788
+            centerChange[i] = center[i];
+            center[i] *= centerTrials;
+            center[i] += current[i];
+            center[i] /= centerTrials + 1;
+            centerChange[i] = center[i] - centerChange[i];
+        }
+        centerTrials = std::min(covWindow, centerTrials + 1.0);
+        if (!covFrozen) {                                                    // :1795-1820
+            for (int i = 0; i < n; ++i) {
+                for (int j = 0; j < i + 1; ++j) {
+                    double v = cov[(size_t)i * n + j];
+                    double r = (current[i] - center[i]) * (current[j] - center[j]);
+                    v *= covTrials;
+                    v += r;
+                    v /= covTrials + 1.0;
+                    cov[(size_t)i * n + j] = v;
+                    cov[(size_t)j * n + i] = v;
+                }
+            }
+            covTrials = std::min(covWindow, covTrials + 1.0);
+        }
+        if (accepted && (--nextUpdate) < 1) {                                // :1824-1826
+            if (!UpdateProposal(false)) return false;
+        }
+        lastValue = value;
+        std::copy(current, current + n, lastPoint.begin());
+        return true;
+    }
+
+    // operator(), :659-725 (forced-step and scan debug modes not restated)
+    bool Propose(double* proposal, const double* current, double value, uint32_t step) {
+        if (!UpdateState(current, value)) return false;
+        std::copy(current, current + n, proposal);
+        for (int i = 0; i < n; ++i) {
+            if (type[i] == 1) {
+                double u = smcmc_uniform(seed, chain, step, (uint32_t)i, SMCMC_STREAM_STEP);
+                proposal[i] = param1[i] + (param2[i] - param1[i]) * u;       // TRandom::Uniform(a,b)
+                continue;
+            }
+            double g = smcmc_normal(seed, chain, step, (uint32_t)i, SMCMC_STREAM_STEP);
+            double r = 0.0 + 1.0 * g;                                        // TRandom::Gaus(0,1)
+            for (int j = 0; j < n; ++j) {
+                if (type[j] == 1) continue;
+                proposal[j] += sigma * r * decomp[(size_t)i * n + j];
+            }
+        }
+        return true;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// TSimpleMCMC (TSimpleMCMC.H:185-590)
+// ---------------------------------------------------------------------------
+struct OrcChain {
+    Likelihood like;
+    Proposal prop;
+    int n = 0;
+    uint32_t step = 0;
+    std::vector<double> accepted, proposed, trial;
+    double acceptedLlh = 0.0, proposedLlh = 0.0;
+    double stepRMS = 0.0;
+    int stepRMSTrials = 0, stepRMSWindow = 1000;
+    int totalSteps = 0, llhCalls = 0;
+
+    double Eval(const double* x) { ++llhCalls; return like(x); }       // :538-541
+
+    int Start(const double* x0) {                                      // :246-276
+        proposed.assign(x0, x0 + n);
+        accepted.assign(x0, x0 + n);
+        trial.assign(x0, x0 + n);
+        proposedLlh = Eval(proposed.data());
+        if (!std::isfinite(proposedLlh) || proposedLlh < -0.999999E+10) return 0;
+        acceptedLlh = proposedLlh;
+        if (!prop.InitializeState(accepted.data(), acceptedLlh)) return -1;
+        return 1;
+    }
+
+    // :370-496.  Returns 1 accepted, 0 rejected, -1 error.
+    int Step(int metropolis) {
+        if (proposed.empty() || accepted.empty()) { gLastError = "Uninitialized starting point"; return -1; }
+        ++totalSteps;
+        if (!prop.Propose(proposed.data(), accepted.data(), acceptedLlh, step++)) return -1;
+        if (stepRMSWindow > 0) {                                       // :391-406
+            double sqr = 0.0;
+            for (int i = 0; i < n; ++i) {
+                trial[i] = proposed[i] - accepted[i];
+                sqr += trial[i] * trial[i];
+            }
+            double ms = stepRMS * stepRMS;
+            ms *= stepRMSTrials;
+            ms += sqr;
+            ms /= stepRMSTrials + 1.0;
+            stepRMSTrials = std::min(stepRMSWindow, stepRMSTrials + 1);
+            stepRMS = std::sqrt(ms);
+        }
+        proposedLlh = Eval(proposed.data());                           // :410
+        if (metropolis == 2) {                                         // :414-426
+            accepted = proposed;
+            acceptedLlh = proposedLlh;
+            return 1;
+        }
+        if (!std::isfinite(proposedLlh) || proposedLlh < -0.999999E+30) return 0;   // :432-436
+        double delta = proposedLlh - acceptedLlh;                      // :441-463
+        if (delta < 0.0) {
+            if (metropolis == 1) return 0;
+            double u = 1.0 * smcmc_uniform(prop.seed, prop.chain, step - 1, (uint32_t)n, SMCMC_STREAM_STEP);
+            double t = std::log(u);
+            if (delta < t) return 0;
+        }
+        acceptedLlh = proposedLlh;                                     // :484-491
+        accepted = proposed;
+        return 1;
+    }
+};
+
+OrcChain* H(void* h) { return static_cast<OrcChain*>(h); }
+
+}  // namespace
+
+extern "C" {
+
+const char* orc_last_error(void) { return gLastError.c_str(); }
+
+void* orc_chain_create(int kind, int dim, uint64_t seed, uint32_t chain) {
+    if (kind < ORC_LLH_UNIT_GAUSS || kind > ORC_LLH_FAKE || dim < 1) {
+        gLastError = "bad likelihood kind or dimension";
+        return 0;
+    }
+    if (kind == ORC_LLH_FAKE && dim != 9) { gLastError = "FakeLikelihood is 9-dim"; return 0; }
+    OrcChain* c = new OrcChain;
+    c->n = dim;
+    c->like.kind = kind;
+    c->like.dim = dim;
+    c->prop.seed = seed;
+    c->prop.chain = chain;
+    c->prop.n = dim;
+    c->prop.SetDim(dim);
+    return c;
+}
+
+void orc_chain_destroy(void* h) { delete H(h); }
+
+int orc_chain_set_fake(void* h, const orc_event* ev, long n, const double* data150, double exposure) {
+    Likelihood& l = H(h)->like;
+    if (l.kind != ORC_LLH_FAKE) { gLastError = "not a FakeLikelihood chain"; return -1; }
+    l.events.assign(ev, ev + n);
+    std::copy(data150, data150 + 150, l.data);
+    l.exposure = exposure;
+    return 0;
+}
+
+int orc_chain_set_error_matrix(void* h, const double* e, int n) {
+    Likelihood& l = H(h)->like;
+    if (l.kind != ORC_LLH_DUMMY || n != l.dim) { gLastError = "error matrix shape"; return -1; }
+    l.error.assign(e, e + (size_t)n * n);
+    return 0;
+}
+
+int orc_chain_set(void* h, int field, double v) {
+    Proposal& p = H(h)->prop;
+    switch (field) {
+    case ORC_SET_SIGMA: p.sigma = v; break;
+    case ORC_SET_TARGET_ACCEPTANCE: p.target = v; break;
+    case ORC_SET_ACCEPTANCE_WINDOW: p.acceptanceWindow = v; break;
+    case ORC_SET_ACCEPTANCE_RIGIDITY: p.rigidity = v; break;
+    case ORC_SET_ACCEPTANCE_DEWEIGHT: p.acceptanceDeweight = v; break;
+    case ORC_SET_COVARIANCE_WINDOW: p.covWindow = (int)v; break;      // SetCovarianceWindow(int) :914
+    case ORC_SET_COVARIANCE_DEWEIGHT: p.covDeweight = v; break;
+    case ORC_SET_COVARIANCE_FROZEN: p.covFrozen = (v != 0.0); break;
+    case ORC_SET_COVARIANCE_TRIALS: p.covTrials = v; break;
+    case ORC_SET_CENTER_TRIALS: p.centerTrials = v; break;
+    case ORC_SET_NEXT_UPDATE: p.nextUpdate = (int)v; break;           // int member :1930
+    case ORC_SET_MAX_CORRELATION: p.maxCorrelation = v; break;
+    case ORC_SET_STEP_RMS_WINDOW: H(h)->stepRMSWindow = (int)v; break;
+    default: gLastError = "unknown field"; return -1;
+    }
+    return 0;
+}
+
+int orc_chain_set_gaussian(void* h, int d, double sigma) {            // :855-867
+    Proposal& p = H(h)->prop;
+    if (d < 0 || d >= p.n) return -1;
+    p.type[d] = 0;
+    p.param1[d] = sigma * sigma;
+    return 0;
+}
+
+int orc_chain_set_uniform(void* h, int d, double lo, double hi) {     // :833-848
+    Proposal& p = H(h)->prop;
+    if (d < 0 || d >= p.n) return -1;
+    p.type[d] = 1;
+    p.param1[d] = lo;
+    p.param2[d] = hi;
+    return 0;
+}
+
+int orc_chain_set_correlation(void* h, int d1, int d2, double c) {
+    H(h)->prop.SetCorrelation(d1, d2, c);
+    return 0;
+}
+
+int orc_chain_start(void* h, const double* x0) { return H(h)->Start(x0); }
+
+int orc_chain_step(void* h, int nsteps, int metropolis, int32_t* accepted,
+                   double* llhAccepted, double* llhProposed, double* x, double* sigma) {
+    OrcChain* c = H(h);
+    for (int s = 0; s < nsteps; ++s) {
+        int r = c->Step(metropolis);
+        if (r < 0) return -1;
+        if (accepted) accepted[s] = r;
+        if (llhAccepted) llhAccepted[s] = c->acceptedLlh;
+        if (llhProposed) llhProposed[s] = c->proposedLlh;
+        if (sigma) sigma[s] = c->prop.sigma;
+        if (x) std::copy(c->accepted.begin(), c->accepted.end(), x + (size_t)s * c->n);
+    }
+    return 0;
+}
+
+int orc_chain_update_proposal(void* h) { return H(h)->prop.UpdateProposal(false) ? 0 : -1; }
+int orc_chain_reset_proposal(void* h) { return H(h)->prop.ResetProposal() ? 0 : -1; }
+
+int orc_chain_get_state(void* h, double* s, double* accepted, double* center,
+                        double* cov, double* decomp) {
+    OrcChain* c = H(h);
+    Proposal& p = c->prop;
+    const size_t nn = (size_t)c->n * c->n;
+    if (s) {
+        s[ORC_ST_SIGMA] = p.sigma;
+        s[ORC_ST_ACCEPTANCE] = p.acceptance;
+        s[ORC_ST_ACCEPTANCE_TRIALS] = p.acceptanceTrials;
+        s[ORC_ST_ACCEPTANCE_WINDOW] = p.acceptanceWindow;
+        s[ORC_ST_ACCEPTANCE_RIGIDITY] = p.rigidity;
+        s[ORC_ST_TARGET_ACCEPTANCE] = p.target;
+        s[ORC_ST_TRIALS] = p.trials;
+        s[ORC_ST_SUCCESSES] = p.successes;
+        s[ORC_ST_NEXT_UPDATE] = p.nextUpdate;
+        s[ORC_ST_COVARIANCE_TRIALS] = p.covTrials;
+        s[ORC_ST_COVARIANCE_WINDOW] = p.covWindow;
+        s[ORC_ST_CENTER_TRIALS] = p.centerTrials;
+        s[ORC_ST_COVARIANCE_TRACE] = p.cov.size() == nn ? p.Trace() : 0.0;
+        s[ORC_ST_SIGMA_TRACE] = p.sigmaTrace;
+        s[ORC_ST_STEP_RMS] = c->stepRMS;
+        s[ORC_ST_ACCEPTED_LLH] = c->acceptedLlh;
+        s[ORC_ST_PROPOSED_LLH] = c->proposedLlh;
+        s[ORC_ST_TOTAL_STEPS] = c->totalSteps;
+        s[ORC_ST_LLH_CALLS] = c->llhCalls;
+    }
+    if (accepted) std::copy(c->accepted.begin(), c->accepted.end(), accepted);
+    if (center && p.center.size() == (size_t)c->n) std::copy(p.center.begin(), p.center.end(), center);
+    if (cov && p.cov.size() == nn) std::copy(p.cov.begin(), p.cov.end(), cov);
+    if (decomp && p.decomp.size() == nn) std::copy(p.decomp.begin(), p.decomp.end(), decomp);
+    return 0;
+}
+
+double orc_chain_llh(void* h, const double* x) { return H(h)->like(x); }
+
+int orc_chain_fake_hist(void* h, const double* x, double* out150) {
+    Likelihood& l = H(h)->like;
+    if (l.kind != ORC_LLH_FAKE) { gLastError = "not a FakeLikelihood chain"; return -1; }
+    l.FillFake(x);
+    for (int hh = 0; hh < 3; ++hh)
+        for (int b = 0; b < 50; ++b) out150[hh * 50 + b] = l.sim[hh][b + 1];
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,754 @@
+// engine.cu -- libsmcmc_b200.so: the engine object behind the C ABI of
+// include/smcmc_b200.h.  Host code here only owns device memory, resolves the
+// few n-dependent defaults the reference computes once, and queues kernels;
+// all per-chain and per-event arithmetic is in the .cuh kernels.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "fake_likelihood.cuh"
+#include "proposal.cuh"
+#include "simple_likelihoods.cuh"
+
+namespace smcmc {
+
+static thread_local std::string gCreateError;
+
+// Smallest double l with pred(exp(l)) true, for a predicate monotone in l:
+// bisection on the ordered bit patterns of positive doubles.
+template <class Pred>
+static double firstLogWhere(Pred pred, double lo, double hi) {
+    // invariant: !pred(exp(lo)), pred(exp(hi)), 0 < lo < hi
+    uint64_t a, b;
+    std::memcpy(&a, &lo, 8);
+    std::memcpy(&b, &hi, 8);
+    while (b - a > 1) {
+        uint64_t mid = a + (b - a) / 2;
+        double m;
+        std::memcpy(&m, &mid, 8);
+        if (pred(std::exp(m))) b = mid;
+        else a = mid;
+    }
+    double r;
+    std::memcpy(&r, &b, 8);
+    return r;
+}
+
+}  // namespace smcmc
+
+using namespace smcmc;
+
+struct smcmc_engine {
+    smcmc_config cfg;
+    cudaStream_t stream = nullptr;
+    std::string lastError;
+    int64_t launches = 0;
+    uint32_t stepIndex = 0;
+    bool started = false;
+
+    // ---- proposal settings (host mirror of the reference's members) -------
+    std::vector<int> type;
+    std::vector<double> param1, param2;
+    std::vector<int> corrDim1, corrDim2;
+    std::vector<double> corrValue;
+    double covWindow = -1, accWindow = -1, target = -1;
+    double covDeweight = 0.5, accDeweight = 0.5;
+    double maxCorr = 1.0 - std::sqrt(std::numeric_limits<double>::epsilon());
+    int covFrozen = 0, stepRMSWindow = 1000;
+    bool settingsDirty = true;
+    DeviceBuffer<int> dType, dCorr1, dCorr2;
+    DeviceBuffer<double> dParam1, dParam2, dCorrValue;
+
+    // ---- per-chain state ---------------------------------------------------
+    DeviceBuffer<double> xAcc, xProp, lastPoint, center, cov, decomp, llhProp;
+    DeviceBuffer<ChainScalars> sc;
+    DeviceBuffer<int32_t> okDev;
+
+    // ---- likelihood data ---------------------------------------------------
+    DeviceBuffer<double> errMatrix;                 // DUMMY
+    int errDim = 0;
+    DeviceBuffer<PreparedEvent> fakeEvents;         // FAKE
+    DeviceBuffer<smcmc_event> fakeIrregular;
+    int64_t fakeClassBase[kFakeClasses] = {0, 0, 0, 0};
+    int64_t fakeClassCount[kFakeClasses] = {0, 0, 0, 0};
+    int64_t fakeIrregularCount = 0;
+    int64_t fakeEventCount = -1;
+    DeviceBuffer<double> fakeData;
+    bool fakeDataSet = false;
+    double fakeExposure = 1.0;
+    DeviceBuffer<FakeChainParams> fakeChains;
+    DeviceBuffer<uint32_t> fakeCounts;
+    int fakeCountStride = 0;
+    bool forceGeneric = false;
+
+    // ---- scratch for smcmc_eval / smcmc_fake_histograms ---------------------
+    DeviceBuffer<double> evalX, evalOut, evalHist;
+
+    // ---- instrumentation ----------------------------------------------------
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pairEvents;
+    double pairMs = 0.0;
+    int64_t pairLaunches = 0;
+
+    int n() const { return cfg.dim; }
+    int E() const { return cfg.chains; }
+    int tri() const { return cfg.dim * (cfg.dim + 1) / 2; }
+
+    void launched() {
+        ++launches;
+        CUDA_CHECK(cudaGetLastError());
+    }
+
+    ChainArrays arrays() {
+        ChainArrays a;
+        a.xAcc = xAcc.get();
+        a.xProp = xProp.get();
+        a.lastPoint = lastPoint.get();
+        a.center = center.get();
+        a.cov = cov.get();
+        a.decomp = decomp.get();
+        a.sc = sc.get();
+        return a;
+    }
+
+    PropSettings settings() {
+        if (settingsDirty) {
+            const int nn = n();
+            dType.reserve(nn);
+            dParam1.reserve(nn);
+            dParam2.reserve(nn);
+            CUDA_CHECK(cudaMemcpyAsync(dType.get(), type.data(), nn * sizeof(int), cudaMemcpyHostToDevice, stream));
+            CUDA_CHECK(cudaMemcpyAsync(dParam1.get(), param1.data(), nn * sizeof(double), cudaMemcpyHostToDevice, stream));
+            CUDA_CHECK(cudaMemcpyAsync(dParam2.get(), param2.data(), nn * sizeof(double), cudaMemcpyHostToDevice, stream));
+            const size_t nc = corrValue.size();
+            if (nc) {
+                dCorr1.reserve(nc);
+                dCorr2.reserve(nc);
+                dCorrValue.reserve(nc);
+                CUDA_CHECK(cudaMemcpyAsync(dCorr1.get(), corrDim1.data(), nc * sizeof(int), cudaMemcpyHostToDevice, stream));
+                CUDA_CHECK(cudaMemcpyAsync(dCorr2.get(), corrDim2.data(), nc * sizeof(int), cudaMemcpyHostToDevice, stream));
+                CUDA_CHECK(cudaMemcpyAsync(dCorrValue.get(), corrValue.data(), nc * sizeof(double), cudaMemcpyHostToDevice, stream));
+            }
+            // the host vectors may change before the copies run
+            CUDA_CHECK(cudaStreamSynchronize(stream));
+            settingsDirty = false;
+        }
+        PropSettings ps;
+        ps.n = n();
+        ps.tri = tri();
+        ps.covFrozen = covFrozen;
+        ps.stepRMSWindow = stepRMSWindow;
+        ps.ncorr = (int)corrValue.size();
+        ps.covWindow = covWindow;
+        ps.accWindow = accWindow;
+        ps.target = target;
+        ps.covDeweight = covDeweight;
+        ps.accDeweight = accDeweight;
+        ps.maxCorr = maxCorr;
+        ps.type = dType.get();
+        ps.param1 = dParam1.get();
+        ps.param2 = dParam2.get();
+        ps.corrDim1 = dCorr1.get();
+        ps.corrDim2 = dCorr2.get();
+        ps.corrValue = dCorrValue.get();
+        return ps;
+    }
+
+    // The n-dependent defaults of InitializeState (TSimpleMCMC.H:1693-1711).
+    void resolveInitDefaults() {
+        const int nn = n();
+        if (accWindow < 0) accWindow = std::pow(1.0 * nn, 1.5) + 1000;     // :1693-1695
+        if (target < 1E-4) target = (nn > 4) ? 0.234 : 0.44;               // :1699-1711
+    }
+    // ... and of ResetProposal (:1468-1480).
+    void resolveResetDefaults() {
+        const int nn = n();
+        int minWindow = 100 + 4 * nn;
+        if (covWindow < minWindow) {
+            covWindow = nn;
+            covWindow *= nn;
+            covWindow *= nn;
+            covWindow += minWindow;
+            double r = std::numeric_limits<double>::epsilon();
+            covWindow = std::min(covWindow, std::sqrt(1.0 / r));
+        }
+        if (target < 0.0) throw Error(SMCMC_ERR_RUNTIME, "Target acceptance not initialized");
+    }
+
+    // ---- likelihood evaluation on device arrays ----------------------------
+    void evaluate(const double* xDev, int m, double* llhDev, double* histDev) {
+        switch (cfg.likelihood) {
+        case SMCMC_LLH_FAKE:
+            evaluateFake(xDev, m, llhDev, histDev);
+            break;
+        case SMCMC_LLH_DUMMY:
+            if (errDim != n()) throw Error(SMCMC_ERR_LOGIC, "error matrix not set (smcmc_dummy_set_error)");
+            // fall through
+        default:
+            kSimpleLikelihood<<<ceilDiv(m, 128), 128, 0, stream>>>(cfg.likelihood, xDev, m, n(),
+                                                                  errMatrix.get(), llhDev);
+            launched();
+        }
+    }
+
+    void evaluateFake(const double* xDev, int m, double* llhDev, double* histDev) {
+        if (fakeEventCount < 0) throw Error(SMCMC_ERR_LOGIC, "events not set (smcmc_fake_set_events)");
+        if (!fakeDataSet) throw Error(SMCMC_ERR_LOGIC, "data histograms not set (smcmc_fake_set_data)");
+        const int stride = (m + 31) / 32 * 32;
+        fakeChains.reserve(stride);
+        fakeCounts.reserve((size_t)kFakeSlots * stride);
+        fakeCountStride = stride;
+        CUDA_CHECK(cudaMemsetAsync(fakeCounts.get(), 0, (size_t)kFakeSlots * stride * sizeof(uint32_t), stream));
+        kFakePrepareChains<<<ceilDiv(m, 128), 128, 0, stream>>>(xDev, m, n(), fakeExposure, fakeChains.get());
+        launched();
+
+        PairLaunch L;
+        L.events = fakeEvents.get();
+        int chunks = 0;
+        for (int c = 0; c < kFakeClasses; ++c) {
+            L.classBase[c] = fakeClassBase[c];
+            L.classCount[c] = fakeClassCount[c];
+            L.chunkBase[c] = chunks;
+            chunks += (int)((fakeClassCount[c] + kPairChunk - 1) / kPairChunk);
+        }
+        L.chunkBase[kFakeClasses] = chunks;
+        L.chains = fakeChains.get();
+        L.numPoints = m;
+        L.pointStride = stride;
+        L.counts = fakeCounts.get();
+        if (chunks > 0) {
+            const int pointTiles = ceilDiv(m, kPairThreads);
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (timing) {
+                CUDA_CHECK(cudaEventCreate(&e0));
+                CUDA_CHECK(cudaEventCreate(&e1));
+                CUDA_CHECK(cudaEventRecord(e0, stream));
+            }
+            kFakePairs<<<(unsigned)chunks * (unsigned)pointTiles, kPairThreads, kPairSmemBytes, stream>>>(L);
+            launched();
+            if (timing) {
+                CUDA_CHECK(cudaEventRecord(e1, stream));
+                pairEvents.emplace_back(e0, e1);
+            }
+            ++pairLaunches;
+        }
+        if (fakeIrregularCount > 0) {
+            long long pairs = (long long)fakeIrregularCount * m;
+            kFakePairsGeneric<<<ceilDiv(pairs, 256), 256, 0, stream>>>(fakeIrregular.get(), fakeIrregularCount,
+                                                                       xDev, m, n(), fakeCounts.get(), stride);
+            launched();
+        }
+        kFakeFinish<<<ceilDiv(m, 32), 32 * kFinishWarps, 0, stream>>>(fakeCounts.get(), stride, m, fakeChains.get(),
+                                                                      fakeData.get(), llhDev, histDev);
+        launched();
+    }
+
+    void collectPairTimings() {
+        for (auto& pr : pairEvents) {
+            CUDA_CHECK(cudaEventSynchronize(pr.second));
+            float ms = 0.f;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+            pairMs += ms;
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
+        pairEvents.clear();
+    }
+
+    void checkChainStatus() {
+        // surfaces what the reference would have thrown inside Step()
+        std::vector<ChainScalars> h(E());
+        CUDA_CHECK(cudaMemcpyAsync(h.data(), sc.get(), sizeof(ChainScalars) * E(), cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        for (int c = 0; c < E(); ++c) {
+            if (h[c].status != 0) {
+                throw Error(h[c].status, "chain " + std::to_string(c) +
+                                             ": proposal update failed (invalid covariance trace or "
+                                             "decomposition of user correlations failed)");
+            }
+        }
+    }
+
+    void stepOnce(int metropolis, const TraceDev& tr, int traceStep) {
+        PropSettings ps = settings();
+        ChainArrays a = arrays();
+        const int blocks = ceilDiv(E(), kWarpsPerBlock);
+        const size_t smem = (size_t)kWarpsPerBlock * 3 * n() * sizeof(double);
+        kPropose<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a, ps, E(), cfg.seed, cfg.chain_offset, stepIndex);
+        launched();
+        evaluate(xProp.get(), E(), llhProp.get(), nullptr);
+        kAccept<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(a, ps, E(), llhProp.get(), cfg.seed, cfg.chain_offset,
+                                                            stepIndex, metropolis, tr, traceStep);
+        launched();
+        ++stepIndex;
+    }
+};
+
+namespace {
+
+template <class F>
+int guarded(smcmc_engine* e, F f) {
+    try {
+        f();
+        return SMCMC_OK;
+    } catch (const Error& err) {
+        if (e) e->lastError = err.what();
+        else gCreateError = err.what();
+        return err.status;
+    } catch (const std::exception& err) {
+        if (e) e->lastError = err.what();
+        else gCreateError = err.what();
+        return SMCMC_ERR_RUNTIME;
+    }
+}
+
+void requireStarted(smcmc_engine* e) {
+    if (!e->started) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "Uninitialized starting point");   // TSimpleMCMC.H:371-374
+}
+
+}  // namespace
+
+extern "C" {
+
+int smcmc_abi_version(void) { return SMCMC_B200_ABI_VERSION; }
+
+const char* smcmc_last_error(const smcmc_engine* e) {
+    return e ? e->lastError.c_str() : gCreateError.c_str();
+}
+
+int smcmc_create(const smcmc_config* cfg, smcmc_engine** out) {
+    if (out) *out = nullptr;
+    smcmc_engine* e = nullptr;
+    int rc = guarded(nullptr, [&]() {
+        if (!cfg || !out) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null argument");
+        if (cfg->struct_size != sizeof(smcmc_config)) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "smcmc_config size mismatch");
+        if (cfg->dim < 1 || cfg->chains < 1) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "dim and chains must be positive");
+        if (cfg->likelihood < SMCMC_LLH_UNIT_GAUSS || cfg->likelihood > SMCMC_LLH_FAKE)
+            throw Error(SMCMC_ERR_INVALID_ARGUMENT, "unknown likelihood");
+        if (cfg->likelihood == SMCMC_LLH_FAKE && cfg->dim != 9)
+            throw Error(SMCMC_ERR_INVALID_ARGUMENT, "the FakeLikelihood functor has 9 parameters");
+        int count = 0;
+        cudaError_t ce = cudaGetDeviceCount(&count);
+        if (ce != cudaSuccess || count < 1) {
+            cudaGetLastError();
+            throw Error(SMCMC_ERR_NO_DEVICE, "no CUDA device: libsmcmc_b200 has no CPU fallback");
+        }
+        if (cfg->device < 0 || cfg->device >= count) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "bad device ordinal");
+        CUDA_CHECK(cudaSetDevice(cfg->device));
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
+        if (prop.major < 10) throw Error(SMCMC_ERR_NO_DEVICE, "libsmcmc_b200 is built for sm_100a only");
+
+        e = new smcmc_engine;
+        e->cfg = *cfg;
+        const size_t E = cfg->chains, n = cfg->dim;
+        e->type.assign(n, 0);
+        e->param1.assign(n, 0.0);
+        e->param2.assign(n, 0.0);
+        e->xAcc.reserve(E * n);
+        e->xProp.reserve(E * n);
+        e->lastPoint.reserve(E * n);
+        e->center.reserve(E * n);
+        e->cov.reserve(E * (n * (n + 1) / 2));
+        e->decomp.reserve(E * n * n);
+        e->llhProp.reserve(E);
+        e->sc.reserve(E);
+        e->okDev.reserve(E);
+        CUDA_CHECK(cudaMemset(e->sc.get(), 0, e->sc.bytes()));
+        CUDA_CHECK(cudaMemset(e->cov.get(), 0, e->cov.bytes()));
+        CUDA_CHECK(cudaMemset(e->decomp.get(), 0, e->decomp.bytes()));
+        CUDA_CHECK(cudaMemset(e->center.get(), 0, e->center.bytes()));
+        CUDA_CHECK(cudaMemset(e->lastPoint.get(), 0, e->lastPoint.bytes()));
+        // TProposeAdaptiveStep constructor defaults, TSimpleMCMC.H:642-655
+        std::vector<ChainScalars> init(E);
+        std::memset(init.data(), 0, sizeof(ChainScalars) * E);
+        for (size_t c = 0; c < E; ++c) {
+            init[c].rigidity = 2.0;
+            init[c].nextUpdate = -1;
+        }
+        CUDA_CHECK(cudaMemcpy(e->sc.get(), init.data(), sizeof(ChainScalars) * E, cudaMemcpyHostToDevice));
+        e->forceGeneric = std::getenv("SMCMC_FAKE_FORCE_GENERIC") != nullptr;
+
+        if (cfg->likelihood == SMCMC_LLH_FAKE) {
+            // Pre-images of the TH1 bin edges under this host's exp: bin(exp(l)).
+            double edges[52];
+            edges[0] = -std::numeric_limits<double>::infinity();
+            for (int k = 1; k <= 49; ++k) {
+                edges[k] = firstLogWhere(
+                    [k](double mass) { return 1 + int(50 * (mass - 0.0) / (500.0 - 0.0)) >= k + 1; },
+                    std::log(10.0 * k) - 0.01, std::log(10.0 * k) + 0.01);
+            }
+            // dropped when Mass > 500 (FakeLikelihood.H:203) or in the overflow bin (!(x<500))
+            edges[50] = firstLogWhere([](double mass) { return !(mass < 500.0); }, std::log(500.0) - 0.01,
+                                      std::log(500.0) + 0.01);
+            edges[51] = std::numeric_limits<double>::infinity();
+            CUDA_CHECK(cudaMemcpyToSymbol(gEdges, edges, sizeof(edges)));
+            double consts[4] = {std::tan(M_PI * (0.05 - 0.5)), std::tan(M_PI * (0.5 - 0.5)), M_PI, 0.0};
+            CUDA_CHECK(cudaMemcpyToSymbol(gFakeConst, consts, sizeof(consts)));
+            CUDA_CHECK(cudaFuncSetAttribute(kFakePairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes));
+            e->fakeData.reserve(150);
+        }
+        if ((size_t)kWarpsPerBlock * 3 * n * sizeof(double) > 48 * 1024)
+            CUDA_CHECK(cudaFuncSetAttribute(kPropose, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)((size_t)kWarpsPerBlock * 3 * n * sizeof(double))));
+        *out = e;
+    });
+    if (rc != SMCMC_OK && e) delete e;
+    return rc;
+}
+
+int smcmc_destroy(smcmc_engine* e) {
+    if (!e) return SMCMC_OK;
+    cudaSetDevice(e->cfg.device);
+    cudaDeviceSynchronize();
+    for (auto& pr : e->pairEvents) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    delete e;
+    return SMCMC_OK;
+}
+
+int smcmc_set_stream(smcmc_engine* e, void* s) {
+    return guarded(e, [&]() {
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        e->stream = (cudaStream_t)s;
+    });
+}
+
+int smcmc_sync(smcmc_engine* e) {
+    return guarded(e, [&]() {
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        if (e->started) e->checkChainStatus();
+    });
+}
+
+int smcmc_prop_set(smcmc_engine* e, int field, double v) {
+    return guarded(e, [&]() {
+        bool perChain = false;
+        switch (field) {
+        case SMCMC_PROP_SIGMA: perChain = true; break;
+        case SMCMC_PROP_TARGET_ACCEPTANCE: e->target = v; break;
+        case SMCMC_PROP_ACCEPTANCE_WINDOW: e->accWindow = v; break;
+        case SMCMC_PROP_ACCEPTANCE_RIGIDITY: perChain = true; break;
+        case SMCMC_PROP_ACCEPTANCE_DEWEIGHT: e->accDeweight = v; break;
+        case SMCMC_PROP_COVARIANCE_WINDOW: e->covWindow = (int)v; break;      // SetCovarianceWindow(int)
+        case SMCMC_PROP_COVARIANCE_DEWEIGHT: e->covDeweight = v; break;
+        case SMCMC_PROP_COVARIANCE_FROZEN: e->covFrozen = (v != 0.0); break;
+        case SMCMC_PROP_COVARIANCE_TRIALS: perChain = true; break;
+        case SMCMC_PROP_CENTER_TRIALS: perChain = true; break;
+        case SMCMC_PROP_NEXT_UPDATE: perChain = true; break;
+        case SMCMC_PROP_MAX_CORRELATION: e->maxCorr = v; break;
+        case SMCMC_PROP_STEP_RMS_WINDOW: e->stepRMSWindow = (int)v; break;
+        default: throw Error(SMCMC_ERR_INVALID_ARGUMENT, "unknown proposal field");
+        }
+        if (perChain) {
+            kSetScalar<<<ceilDiv(e->E(), 128), 128, 0, e->stream>>>(e->sc.get(), e->E(), field, v);
+            e->launched();
+        }
+    });
+}
+
+int smcmc_prop_set_gaussian(smcmc_engine* e, int d, double sigma) {
+    return guarded(e, [&]() {
+        if (d < 0 || d >= e->n()) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "dimension out of range");   // :856-860
+        e->type[d] = 0;
+        e->param1[d] = sigma * sigma;                                                                  // :865-866
+        e->settingsDirty = true;
+    });
+}
+
+int smcmc_prop_set_uniform(smcmc_engine* e, int d, double lo, double hi) {
+    return guarded(e, [&]() {
+        if (d < 0 || d >= e->n()) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "dimension out of range");   // :834-839
+        e->type[d] = 1;
+        e->param1[d] = lo;
+        e->param2[d] = hi;
+        e->settingsDirty = true;
+    });
+}
+
+int smcmc_prop_set_correlation(smcmc_engine* e, int d1, int d2, double c) {
+    return guarded(e, [&]() {
+        if (d1 < 0 || d1 >= e->n() || d2 < 0 || d2 >= e->n())
+            throw Error(SMCMC_ERR_INVALID_ARGUMENT, "dimension out of range");
+        if (d1 == d2) return;                                                                          // :884-890
+        if (c < -e->maxCorr) c = -e->maxCorr;                                                          // :891-902
+        if (c > e->maxCorr) c = e->maxCorr;
+        e->corrDim1.push_back(d1);
+        e->corrDim2.push_back(d2);
+        e->corrValue.push_back(c);
+        e->settingsDirty = true;
+    });
+}
+
+int smcmc_prop_reset_correlations(smcmc_engine* e) {
+    return guarded(e, [&]() {
+        e->corrDim1.clear();
+        e->corrDim2.clear();
+        e->corrValue.clear();
+        e->settingsDirty = true;
+    });
+}
+
+static void userUpdate(smcmc_engine* e, int reset) {
+    requireStarted(e);
+    if (reset) e->resolveResetDefaults();
+    PropSettings ps = e->settings();
+    kUserUpdate<<<ceilDiv(e->E(), kWarpsPerBlock), kWarpsPerBlock * 32, 0, e->stream>>>(e->arrays(), ps, e->E(), reset);
+    e->launched();
+    e->checkChainStatus();
+}
+
+int smcmc_prop_update(smcmc_engine* e) {
+    return guarded(e, [&]() { userUpdate(e, 0); });
+}
+
+int smcmc_prop_reset(smcmc_engine* e) {
+    return guarded(e, [&]() { userUpdate(e, 1); });
+}
+
+int smcmc_fake_set_events(smcmc_engine* e, const smcmc_event* events, int64_t count) {
+    return guarded(e, [&]() {
+        if (e->cfg.likelihood != SMCMC_LLH_FAKE) throw Error(SMCMC_ERR_LOGIC, "engine was not created with SMCMC_LLH_FAKE");
+        if (count < 0 || (count > 0 && !events)) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "bad event array");
+        DeviceBuffer<smcmc_event> raw;
+        DeviceBuffer<unsigned long long> counters;
+        DeviceBuffer<int64_t> baseDev;
+        counters.reserve(16);
+        baseDev.reserve(8);
+        CUDA_CHECK(cudaMemsetAsync(counters.get(), 0, 16 * sizeof(unsigned long long), e->stream));
+        unsigned long long hostCount[8] = {0};
+        if (count > 0) {
+            raw.reserve(count);
+            CUDA_CHECK(cudaMemcpyAsync(raw.get(), events, sizeof(smcmc_event) * count, cudaMemcpyHostToDevice, e->stream));
+            kFakeCountClasses<<<ceilDiv(count, 256), 256, 0, e->stream>>>(raw.get(), count, counters.get(), e->forceGeneric);
+            e->launched();
+            CUDA_CHECK(cudaMemcpyAsync(hostCount, counters.get(), 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+            CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        }
+        int64_t base[8] = {0};
+        int64_t total = 0;
+        for (int c = 0; c < kFakeClasses; ++c) {
+            base[c] = total;
+            e->fakeClassBase[c] = total;
+            e->fakeClassCount[c] = (int64_t)hostCount[c];
+            total += (int64_t)hostCount[c];
+        }
+        e->fakeIrregularCount = (int64_t)hostCount[kIrregularClass];
+        e->fakeEvents.reserve(total > 0 ? total : 1);
+        e->fakeIrregular.reserve(e->fakeIrregularCount > 0 ? e->fakeIrregularCount : 1);
+        if (count > 0) {
+            CUDA_CHECK(cudaMemcpyAsync(baseDev.get(), base, sizeof(base), cudaMemcpyHostToDevice, e->stream));
+            kFakeScatter<<<ceilDiv(count, 256), 256, 0, e->stream>>>(raw.get(), count, e->fakeEvents.get(), baseDev.get(),
+                                                                   counters.get() + 8, e->fakeIrregular.get(), e->forceGeneric);
+            e->launched();
+            CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        }
+        e->fakeEventCount = count;
+    });
+}
+
+int smcmc_fake_set_data(smcmc_engine* e, const double* data150, double exposure) {
+    return guarded(e, [&]() {
+        if (e->cfg.likelihood != SMCMC_LLH_FAKE) throw Error(SMCMC_ERR_LOGIC, "engine was not created with SMCMC_LLH_FAKE");
+        if (!data150) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null data histograms");
+        CUDA_CHECK(cudaMemcpyAsync(e->fakeData.get(), data150, 150 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        e->fakeExposure = exposure;
+        e->fakeDataSet = true;
+    });
+}
+
+int smcmc_dummy_set_error(smcmc_engine* e, const double* err, int nn) {
+    return guarded(e, [&]() {
+        if (e->cfg.likelihood != SMCMC_LLH_DUMMY) throw Error(SMCMC_ERR_LOGIC, "engine was not created with SMCMC_LLH_DUMMY");
+        if (!err || nn != e->n()) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "error matrix must be dim x dim");
+        e->errMatrix.reserve((size_t)nn * nn);
+        CUDA_CHECK(cudaMemcpyAsync(e->errMatrix.get(), err, sizeof(double) * nn * nn, cudaMemcpyHostToDevice, e->stream));
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        e->errDim = nn;
+    });
+}
+
+static void evalHost(smcmc_engine* e, const double* x, int m, double* llh, double* hist) {
+    if (m < 1 || !x) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "bad point array");
+    const size_t n = e->n();
+    e->evalX.reserve((size_t)m * n);
+    e->evalOut.reserve(m);
+    if (hist) e->evalHist.reserve((size_t)m * 150);
+    CUDA_CHECK(cudaMemcpyAsync(e->evalX.get(), x, sizeof(double) * m * n, cudaMemcpyHostToDevice, e->stream));
+    e->evaluate(e->evalX.get(), m, e->evalOut.get(), hist ? e->evalHist.get() : nullptr);
+    if (llh) CUDA_CHECK(cudaMemcpyAsync(llh, e->evalOut.get(), sizeof(double) * m, cudaMemcpyDeviceToHost, e->stream));
+    if (hist) CUDA_CHECK(cudaMemcpyAsync(hist, e->evalHist.get(), sizeof(double) * m * 150, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+}
+
+int smcmc_fake_histograms(smcmc_engine* e, const double* x, int m, double* out) {
+    return guarded(e, [&]() {
+        if (e->cfg.likelihood != SMCMC_LLH_FAKE) throw Error(SMCMC_ERR_LOGIC, "engine was not created with SMCMC_LLH_FAKE");
+        if (!out) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null output");
+        evalHost(e, x, m, nullptr, out);
+    });
+}
+
+int smcmc_eval(smcmc_engine* e, const double* x, int m, double* llh) {
+    return guarded(e, [&]() {
+        if (!llh) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null output");
+        evalHost(e, x, m, llh, nullptr);
+    });
+}
+
+int smcmc_start(smcmc_engine* e, const double* x0, int32_t* ok) {
+    return guarded(e, [&]() {
+        if (!x0) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null starting points");
+        const size_t bytes = sizeof(double) * e->E() * e->n();
+        CUDA_CHECK(cudaMemcpyAsync(e->xAcc.get(), x0, bytes, cudaMemcpyHostToDevice, e->stream));   // :247-256
+        CUDA_CHECK(cudaMemcpyAsync(e->xProp.get(), e->xAcc.get(), bytes, cudaMemcpyDeviceToDevice, e->stream));
+        e->evaluate(e->xProp.get(), e->E(), e->llhProp.get(), nullptr);                             // :258
+        e->resolveInitDefaults();
+        e->resolveResetDefaults();
+        PropSettings ps = e->settings();
+        // stash the start likelihood in the chain records
+        kStoreStartLlh<<<ceilDiv(e->E(), 128), 128, 0, e->stream>>>(e->sc.get(), e->llhProp.get(), e->E());
+        e->launched();
+        kInitState<<<ceilDiv(e->E(), kWarpsPerBlock), kWarpsPerBlock * 32, 0, e->stream>>>(e->arrays(), ps, e->E(), e->okDev.get());
+        e->launched();
+        std::vector<int32_t> okHost(e->E());
+        CUDA_CHECK(cudaMemcpyAsync(okHost.data(), e->okDev.get(), sizeof(int32_t) * e->E(), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        if (ok) std::memcpy(ok, okHost.data(), sizeof(int32_t) * e->E());
+        e->started = true;
+        e->checkChainStatus();
+    });
+}
+
+int smcmc_step(smcmc_engine* e, int nsteps, int metropolis) {
+    return guarded(e, [&]() {
+        requireStarted(e);
+        TraceDev none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        for (int s = 0; s < nsteps; ++s) e->stepOnce(metropolis, none, -1);
+    });
+}
+
+int smcmc_step_trace(smcmc_engine* e, int nsteps, int metropolis, const smcmc_trace* trace) {
+    return guarded(e, [&]() {
+        requireStarted(e);
+        if (nsteps < 1) return;
+        const size_t rows = (size_t)nsteps * e->E();
+        DeviceBuffer<int32_t> acc;
+        DeviceBuffer<double> la, lp, pts, sg, rms;
+        TraceDev tr = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        if (trace) {
+            if (trace->accepted) { acc.reserve(rows); tr.accepted = acc.get(); }
+            if (trace->llh_accepted) { la.reserve(rows); tr.llhAccepted = la.get(); }
+            if (trace->llh_proposed) { lp.reserve(rows); tr.llhProposed = lp.get(); }
+            if (trace->points) { pts.reserve(rows * e->n()); tr.points = pts.get(); }
+            if (trace->sigma) { sg.reserve(rows); tr.sigma = sg.get(); }
+            if (trace->step_rms) { rms.reserve(rows); tr.stepRMS = rms.get(); }
+        }
+        for (int s = 0; s < nsteps; ++s) e->stepOnce(metropolis, tr, s);
+        if (trace) {
+            if (trace->accepted) CUDA_CHECK(cudaMemcpyAsync(trace->accepted, acc.get(), rows * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+            if (trace->llh_accepted) CUDA_CHECK(cudaMemcpyAsync(trace->llh_accepted, la.get(), rows * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+            if (trace->llh_proposed) CUDA_CHECK(cudaMemcpyAsync(trace->llh_proposed, lp.get(), rows * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+            if (trace->points) CUDA_CHECK(cudaMemcpyAsync(trace->points, pts.get(), rows * e->n() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+            if (trace->sigma) CUDA_CHECK(cudaMemcpyAsync(trace->sigma, sg.get(), rows * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+            if (trace->step_rms) CUDA_CHECK(cudaMemcpyAsync(trace->step_rms, rms.get(), rows * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        }
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        e->checkChainStatus();
+    });
+}
+
+int smcmc_get(smcmc_engine* e, int field, void* dst, size_t bytes) {
+    return guarded(e, [&]() {
+        if (!dst) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null destination");
+        const size_t E = e->E(), n = e->n();
+        auto need = [&](size_t want) {
+            if (bytes < want) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "destination too small");
+        };
+        auto copyArray = [&](const void* src, size_t want) {
+            need(want);
+            CUDA_CHECK(cudaMemcpyAsync(dst, src, want, cudaMemcpyDeviceToHost, e->stream));
+            CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        };
+        switch (field) {
+        case SMCMC_F_ACCEPTED: copyArray(e->xAcc.get(), E * n * 8); return;
+        case SMCMC_F_PROPOSED: copyArray(e->xProp.get(), E * n * 8); return;
+        case SMCMC_F_CENTER: copyArray(e->center.get(), E * n * 8); return;
+        case SMCMC_F_COVARIANCE: copyArray(e->cov.get(), E * e->tri() * 8); return;
+        case SMCMC_F_DECOMPOSITION: copyArray(e->decomp.get(), E * n * n * 8); return;
+        case SMCMC_F_COVARIANCE_WINDOW: need(8); *(double*)dst = e->covWindow; return;
+        case SMCMC_F_ACCEPTANCE_WINDOW: need(8); *(double*)dst = e->accWindow; return;
+        case SMCMC_F_TARGET_ACCEPTANCE: need(8); *(double*)dst = e->target; return;
+        default: break;
+        }
+        std::vector<ChainScalars> h(E);
+        CUDA_CHECK(cudaMemcpyAsync(h.data(), e->sc.get(), sizeof(ChainScalars) * E, cudaMemcpyDeviceToHost, e->stream));
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        auto putD = [&](double ChainScalars::*m) {
+            need(E * 8);
+            for (size_t c = 0; c < E; ++c) ((double*)dst)[c] = h[c].*m;
+        };
+        auto putI = [&](int ChainScalars::*m) {
+            need(E * 4);
+            for (size_t c = 0; c < E; ++c) ((int32_t*)dst)[c] = h[c].*m;
+        };
+        switch (field) {
+        case SMCMC_F_ACCEPTED_LLH: putD(&ChainScalars::accLlh); break;
+        case SMCMC_F_PROPOSED_LLH: putD(&ChainScalars::propLlh); break;
+        case SMCMC_F_STEP_RMS: putD(&ChainScalars::stepRMS); break;
+        case SMCMC_F_SIGMA: putD(&ChainScalars::sigma); break;
+        case SMCMC_F_SIGMA_TRACE: putD(&ChainScalars::sigmaTrace); break;
+        case SMCMC_F_ACCEPTANCE: putD(&ChainScalars::acceptance); break;
+        case SMCMC_F_ACCEPTANCE_TRIALS: putD(&ChainScalars::acceptanceTrials); break;
+        case SMCMC_F_ACCEPTANCE_RIGIDITY: putD(&ChainScalars::rigidity); break;
+        case SMCMC_F_COVARIANCE_TRIALS: putD(&ChainScalars::covTrials); break;
+        case SMCMC_F_CENTER_TRIALS: putD(&ChainScalars::centerTrials); break;
+        case SMCMC_F_TRIALS: putI(&ChainScalars::trials); break;
+        case SMCMC_F_SUCCESSES: putI(&ChainScalars::successes); break;
+        case SMCMC_F_NEXT_UPDATE: putI(&ChainScalars::nextUpdate); break;
+        case SMCMC_F_TOTAL_STEPS: putI(&ChainScalars::totalSteps); break;
+        case SMCMC_F_LLH_CALLS: putI(&ChainScalars::llhCalls); break;
+        case SMCMC_F_STATUS: putI(&ChainScalars::status); break;
+        case SMCMC_F_COVARIANCE_TRACE: {
+            need(E * 8);
+            std::vector<double> covHost(E * e->tri());
+            CUDA_CHECK(cudaMemcpyAsync(covHost.data(), e->cov.get(), covHost.size() * 8, cudaMemcpyDeviceToHost, e->stream));
+            CUDA_CHECK(cudaStreamSynchronize(e->stream));
+            for (size_t c = 0; c < E; ++c) {
+                double t = 0.0;                                             // :961-967
+                for (size_t i = 0; i < n; ++i) t += covHost[c * e->tri() + i * (i + 1) / 2 + i];
+                ((double*)dst)[c] = t;
+            }
+            break;
+        }
+        default: throw Error(SMCMC_ERR_INVALID_ARGUMENT, "unknown field");
+        }
+    });
+}
+
+int64_t smcmc_launch_count(const smcmc_engine* e) { return e ? e->launches : 0; }
+
+int smcmc_enable_kernel_timing(smcmc_engine* e, int on) {
+    return guarded(e, [&]() { e->timing = on != 0; });
+}
+
+int smcmc_pair_kernel_stats(smcmc_engine* e, double* totalMs, int64_t* launches, int reset) {
+    return guarded(e, [&]() {
+        e->collectPairTimings();
+        if (totalMs) *totalMs = e->pairMs;
+        if (launches) *launches = e->pairLaunches;
+        if (reset) {
+            e->pairMs = 0.0;
+            e->pairLaunches = 0;
+        }
+    });
+}
+
+}  // extern "C"

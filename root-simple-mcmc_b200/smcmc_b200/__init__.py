@@ -1,0 +1,15 @@
+"""smcmc_b200 -- Python binding of libsmcmc_b200.so (include/smcmc_b200.h).
+
+The binding is ctypes over the C ABI; it adds no computation of its own.  The
+hot path lives in the CUDA library, and importing :class:`Engine` without the
+built library, or creating one without a GPU, fails loudly: there is no CPU
+fallback.
+"""
+from .binding import (Engine, EVENT_DTYPE, LLH_ASYM, LLH_DUMMY, LLH_FAKE,
+                      LLH_HORRIFIC, LLH_UNIT_GAUSS, SmcmcError, build_library,
+                      library_path, load_library)
+from . import synth
+
+__all__ = ["Engine", "EVENT_DTYPE", "SmcmcError", "build_library",
+           "library_path", "load_library", "synth", "LLH_UNIT_GAUSS",
+           "LLH_DUMMY", "LLH_HORRIFIC", "LLH_ASYM", "LLH_FAKE"]

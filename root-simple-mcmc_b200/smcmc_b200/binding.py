@@ -1,0 +1,273 @@
+"""ctypes binding of the C ABI declared in include/smcmc_b200.h."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(os.path.dirname(HERE), "csrc")
+
+LLH_UNIT_GAUSS, LLH_DUMMY, LLH_HORRIFIC, LLH_ASYM, LLH_FAKE = range(5)
+
+# smcmc_prop_field
+(PROP_SIGMA, PROP_TARGET_ACCEPTANCE, PROP_ACCEPTANCE_WINDOW,
+ PROP_ACCEPTANCE_RIGIDITY, PROP_ACCEPTANCE_DEWEIGHT, PROP_COVARIANCE_WINDOW,
+ PROP_COVARIANCE_DEWEIGHT, PROP_COVARIANCE_FROZEN, PROP_COVARIANCE_TRIALS,
+ PROP_CENTER_TRIALS, PROP_NEXT_UPDATE, PROP_MAX_CORRELATION,
+ PROP_STEP_RMS_WINDOW) = range(13)
+
+# smcmc_field: name -> (id, dtype, shape code)
+_FIELDS = {
+    "accepted": (0, np.float64, "En"), "proposed": (1, np.float64, "En"),
+    "accepted_llh": (2, np.float64, "E"), "proposed_llh": (3, np.float64, "E"),
+    "step_rms": (4, np.float64, "E"), "sigma": (5, np.float64, "E"),
+    "acceptance": (6, np.float64, "E"), "acceptance_trials": (7, np.float64, "E"),
+    "acceptance_rigidity": (8, np.float64, "E"), "trials": (9, np.int32, "E"),
+    "successes": (10, np.int32, "E"), "next_update": (11, np.int32, "E"),
+    "covariance_trials": (12, np.float64, "E"), "center_trials": (13, np.float64, "E"),
+    "center": (14, np.float64, "En"), "covariance": (15, np.float64, "Et"),
+    "covariance_trace": (16, np.float64, "E"), "decomposition": (17, np.float64, "Enn"),
+    "total_steps": (18, np.int32, "E"), "llh_calls": (19, np.int32, "E"),
+    "status": (20, np.int32, "E"), "sigma_trace": (21, np.float64, "E"),
+    "covariance_window": (22, np.float64, "1"), "acceptance_window": (23, np.float64, "1"),
+    "target_acceptance": (24, np.float64, "1"),
+}
+
+# The reference's MC event record (example/Simulated.H:7-14), 48 bytes.
+EVENT_DTYPE = np.dtype([
+    ("Mass", "<f8"), ("Type", "<i4"), ("pad0", "<i4"),
+    ("Separation", "<f8"), ("MuDk", "<i4"), ("pad1", "<i4"),
+    ("TrueMass", "<f8"), ("TrueMassSigma", "<f8"),
+])
+assert EVENT_DTYPE.itemsize == 48
+
+
+class SmcmcError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("smcmc status %d: %s" % (status, message))
+        self.status = status
+
+
+class _Config(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_uint32), ("device", ctypes.c_int32),
+                ("dim", ctypes.c_int32), ("chains", ctypes.c_int32),
+                ("chain_offset", ctypes.c_uint32), ("likelihood", ctypes.c_int32),
+                ("seed", ctypes.c_uint64)]
+
+
+class _Trace(ctypes.Structure):
+    _fields_ = [("accepted", ctypes.c_void_p), ("llh_accepted", ctypes.c_void_p),
+                ("llh_proposed", ctypes.c_void_p), ("points", ctypes.c_void_p),
+                ("sigma", ctypes.c_void_p), ("step_rms", ctypes.c_void_p)]
+
+
+def library_path():
+    return os.path.join(HERE, "libsmcmc_b200.so")
+
+
+def build_library(verbose=False):
+    """Compile libsmcmc_b200.so for sm_100a with nvcc (csrc/Makefile)."""
+    subprocess.run(["make", "-C", CSRC], check=True,
+                   stdout=None if verbose else subprocess.DEVNULL)
+
+
+_LIB = None
+
+
+def load_library():
+    """Load the CUDA library.  Raises if it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise ImportError("%s is missing: run __graft_entry__.build() (there is no "
+                          "CPU fallback for the MCMC step path)" % path)
+    lib = ctypes.CDLL(path)
+    vp, ci, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+    sig = {
+        "smcmc_abi_version": (ci, []),
+        "smcmc_last_error": (ctypes.c_char_p, [vp]),
+        "smcmc_create": (ci, [ctypes.POINTER(_Config), ctypes.POINTER(vp)]),
+        "smcmc_destroy": (ci, [vp]),
+        "smcmc_set_stream": (ci, [vp, vp]),
+        "smcmc_sync": (ci, [vp]),
+        "smcmc_prop_set": (ci, [vp, ci, cd]),
+        "smcmc_prop_set_gaussian": (ci, [vp, ci, cd]),
+        "smcmc_prop_set_uniform": (ci, [vp, ci, cd, cd]),
+        "smcmc_prop_set_correlation": (ci, [vp, ci, ci, cd]),
+        "smcmc_prop_reset_correlations": (ci, [vp]),
+        "smcmc_prop_update": (ci, [vp]),
+        "smcmc_prop_reset": (ci, [vp]),
+        "smcmc_fake_set_events": (ci, [vp, vp, ctypes.c_int64]),
+        "smcmc_fake_set_data": (ci, [vp, vp, cd]),
+        "smcmc_fake_histograms": (ci, [vp, vp, ci, vp]),
+        "smcmc_dummy_set_error": (ci, [vp, vp, ci]),
+        "smcmc_eval": (ci, [vp, vp, ci, vp]),
+        "smcmc_start": (ci, [vp, vp, vp]),
+        "smcmc_step": (ci, [vp, ci, ci]),
+        "smcmc_step_trace": (ci, [vp, ci, ci, ctypes.POINTER(_Trace)]),
+        "smcmc_get": (ci, [vp, ci, vp, ctypes.c_size_t]),
+        "smcmc_launch_count": (ctypes.c_int64, [vp]),
+        "smcmc_pair_kernel_stats": (ci, [vp, ctypes.POINTER(cd), ctypes.POINTER(ctypes.c_int64), ci]),
+        "smcmc_enable_kernel_timing": (ci, [vp, ci]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = [
+    "smcmc_abi_version", "smcmc_last_error", "smcmc_create", "smcmc_destroy",
+    "smcmc_set_stream", "smcmc_sync", "smcmc_prop_set", "smcmc_prop_set_gaussian",
+    "smcmc_prop_set_uniform", "smcmc_prop_set_correlation",
+    "smcmc_prop_reset_correlations", "smcmc_prop_update", "smcmc_prop_reset",
+    "smcmc_fake_set_events", "smcmc_fake_set_data", "smcmc_fake_histograms",
+    "smcmc_dummy_set_error", "smcmc_eval", "smcmc_start", "smcmc_step",
+    "smcmc_step_trace", "smcmc_get", "smcmc_launch_count",
+    "smcmc_pair_kernel_stats", "smcmc_enable_kernel_timing",
+]
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Engine:
+    """E chains of an n-dimensional adaptive Metropolis sampler on one GPU.
+
+    Mirrors sMCMC::TSimpleMCMC<L, TProposeAdaptiveStep> (TSimpleMCMC.H:185):
+    Start / Step / GetProposeStep().Set* keep their names and meaning, applied
+    to every chain of the ensemble.
+    """
+
+    def __init__(self, likelihood, dim, chains, seed=1, device=0, chain_offset=0):
+        self.lib = load_library()
+        self.dim, self.chains = int(dim), int(chains)
+        cfg = _Config(ctypes.sizeof(_Config), device, dim, chains, chain_offset,
+                      likelihood, seed)
+        h = ctypes.c_void_p()
+        rc = self.lib.smcmc_create(ctypes.byref(cfg), ctypes.byref(h))
+        if rc != 0:
+            raise SmcmcError(rc, self.lib.smcmc_last_error(None).decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.smcmc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SmcmcError(rc, self.lib.smcmc_last_error(self.h).decode())
+
+    # -- plumbing ---------------------------------------------------------
+    def set_stream(self, cuda_stream):
+        self._check(self.lib.smcmc_set_stream(self.h, ctypes.c_void_p(cuda_stream)))
+
+    def sync(self):
+        self._check(self.lib.smcmc_sync(self.h))
+
+    # -- GetProposeStep().Set*  (TSimpleMCMC.H:733-1003) ---------------------
+    def prop_set(self, field, value):
+        self._check(self.lib.smcmc_prop_set(self.h, field, float(value)))
+
+    def set_gaussian(self, d, sigma):
+        self._check(self.lib.smcmc_prop_set_gaussian(self.h, d, float(sigma)))
+
+    def set_uniform(self, d, lo, hi):
+        self._check(self.lib.smcmc_prop_set_uniform(self.h, d, float(lo), float(hi)))
+
+    def set_correlation(self, d1, d2, c):
+        self._check(self.lib.smcmc_prop_set_correlation(self.h, d1, d2, float(c)))
+
+    def reset_correlations(self):
+        self._check(self.lib.smcmc_prop_reset_correlations(self.h))
+
+    def update_proposal(self):
+        self._check(self.lib.smcmc_prop_update(self.h))
+
+    def reset_proposal(self):
+        self._check(self.lib.smcmc_prop_reset(self.h))
+
+    # -- likelihood inputs ---------------------------------------------------
+    def set_fake_events(self, events):
+        ev = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+        self._check(self.lib.smcmc_fake_set_events(self.h, _ptr(ev), len(ev)))
+
+    def set_fake_data(self, data150, exposure):
+        d = np.ascontiguousarray(data150, dtype=np.float64).reshape(150)
+        self._check(self.lib.smcmc_fake_set_data(self.h, _ptr(d), float(exposure)))
+
+    def fake_histograms(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, self.dim)
+        out = np.zeros((x.shape[0], 150))
+        self._check(self.lib.smcmc_fake_histograms(self.h, _ptr(x), x.shape[0], _ptr(out)))
+        return out
+
+    def set_error_matrix(self, e):
+        e = np.ascontiguousarray(e, dtype=np.float64)
+        self._check(self.lib.smcmc_dummy_set_error(self.h, _ptr(e), e.shape[0]))
+
+    # -- sampler -----------------------------------------------------------------
+    def eval(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, self.dim)
+        out = np.zeros(x.shape[0])
+        self._check(self.lib.smcmc_eval(self.h, _ptr(x), x.shape[0], _ptr(out)))
+        return out
+
+    def start(self, x0):
+        x0 = np.ascontiguousarray(np.broadcast_to(np.asarray(x0, dtype=np.float64),
+                                                  (self.chains, self.dim)))
+        ok = np.zeros(self.chains, np.int32)
+        self._check(self.lib.smcmc_start(self.h, _ptr(x0), _ptr(ok)))
+        return ok
+
+    def step(self, nsteps=1, metropolis=0):
+        self._check(self.lib.smcmc_step(self.h, nsteps, metropolis))
+
+    def step_trace(self, nsteps, metropolis=0, want=("accepted", "llh_accepted", "llh_proposed",
+                                                      "points", "sigma", "step_rms"), out=None):
+        """Step(save=true): returns the per-step record a TTree::Fill would hold."""
+        E, n = self.chains, self.dim
+        shapes = {"accepted": ((nsteps, E), np.int32), "llh_accepted": ((nsteps, E), np.float64),
+                  "llh_proposed": ((nsteps, E), np.float64), "points": ((nsteps, E, n), np.float64),
+                  "sigma": ((nsteps, E), np.float64), "step_rms": ((nsteps, E), np.float64)}
+        out = {} if out is None else out
+        tr = _Trace()
+        for name in want:
+            shape, dt = shapes[name]
+            if name not in out:
+                out[name] = np.zeros(shape, dt)
+            setattr(tr, name, out[name].ctypes.data)
+        self._check(self.lib.smcmc_step_trace(self.h, nsteps, metropolis, ctypes.byref(tr)))
+        return out
+
+    def get(self, name):
+        fid, dt, code = _FIELDS[name]
+        E, n = self.chains, self.dim
+        shape = {"E": (E,), "En": (E, n), "Et": (E, n * (n + 1) // 2), "Enn": (E, n, n), "1": (1,)}[code]
+        out = np.zeros(shape, dt)
+        self._check(self.lib.smcmc_get(self.h, fid, _ptr(out), out.nbytes))
+        return out
+
+    # -- instrumentation -----------------------------------------------------------
+    def launch_count(self):
+        return int(self.lib.smcmc_launch_count(self.h))
+
+    def enable_kernel_timing(self, on=True):
+        self._check(self.lib.smcmc_enable_kernel_timing(self.h, 1 if on else 0))
+
+    def pair_kernel_stats(self, reset=False):
+        ms = ctypes.c_double()
+        n = ctypes.c_int64()
+        self._check(self.lib.smcmc_pair_kernel_stats(self.h, ctypes.byref(ms), ctypes.byref(n),
+                                                     1 if reset else 0))
+        return ms.value, n.value
