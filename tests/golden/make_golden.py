@@ -1,0 +1,147 @@
+"""Generate the golden vectors under tests/golden/ by running the REFERENCE's
+own code (oracle/_ref/libsmcmc_ref.so = /root/reference headers compiled
+unmodified against oracle/rootshim) on seeded inputs.
+
+Run in the build container (needs /root/reference):
+    python tests/golden/make_golden.py
+The reference ships no golden vectors of its own, so these
+files are how its behaviour is pinned for the machines where the reference
+tree is absent.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "root-simple-mcmc_b200"))
+sys.path.insert(0, ROOT)
+
+from oracle import cpu_checkers as cc  # noqa: E402
+import smcmc_b200.synth as synth       # noqa: E402
+
+# The parameter excursions of example/TestLikelihood.C:36-207 (nominal, then
+# each of the 9 parameters at +delta and -delta).
+GRID_DELTAS = [1.0, 1.0, 1.0, 1.0, 5.0, 5.0, 5.0, 10.0, 10.0]
+
+
+def likelihood_grid():
+    pts = [np.zeros(9)]
+    for i, d in enumerate(GRID_DELTAS):
+        for s in (+1.0, -1.0):
+            p = np.zeros(9)
+            p[i] = s * d
+            pts.append(p)
+    return np.array(pts)
+
+
+def make_fake():
+    events, data = synth.fake_inputs(200, 200, 10, seed=17)      # 6000 events
+    # a few irregular records: data-typed, negative separation, zero mass
+    extra = np.zeros(4, cc.EVENT_DTYPE)
+    extra["Mass"] = [120.0, 80.0, 0.0, 250.0]
+    extra["Type"] = [-1, 0, 1, -2]
+    extra["Separation"] = [30.0, -5.0, 20.0, 150.0]
+    extra["MuDk"] = [0, 0, 1, 1]
+    extra["TrueMass"] = [135.0, 135.0, 300.0, 200.0]
+    extra["TrueMassSigma"] = [40.5, 40.5, 90.0, 60.0]
+    events_irregular = np.concatenate([events, extra])
+    c = cc.CpuChain("ref", cc.LLH_FAKE, 9, 1, 0)
+    c.set_fake(events, data, 1.0)
+    sim0 = c.fake_hist(np.zeros(9))
+    exposure = float(sum(data)) / float(sum(sim0))
+    rng = np.random.default_rng(23)
+    points = np.concatenate([likelihood_grid(), rng.uniform(-3, 3, (13, 9)),
+                             rng.normal(0, 8, (6, 9))])
+    out = {"events": events, "events_irregular": events_irregular, "data": data,
+           "exposure": exposure, "points": points}
+    for tag, ev in (("", events), ("_irregular", events_irregular)):
+        c = cc.CpuChain("ref", cc.LLH_FAKE, 9, 1, 0)
+        c.set_fake(ev, data, exposure)
+        out["llh" + tag] = np.array([c.llh(p) for p in points])
+        out["hist" + tag] = np.array([c.fake_hist(p) for p in points])
+    # the FakeMCMC.C schedule (:93-165) in miniature, two chains
+    for chain in (0, 7):
+        x0 = np.random.default_rng(100 + chain).uniform(-1, 1, 9)
+        c = cc.CpuChain("ref", cc.LLH_FAKE, 9, 4242, chain)
+        c.set_fake(events, data, exposure)
+        c.start(x0)
+        parts = [c.step(60)]
+        c.reset_proposal()
+        parts.append(c.step(60))
+        c.update_proposal()
+        parts.append(c.step(120))
+        for k in ("accepted", "llh_accepted", "llh_proposed", "x", "sigma"):
+            out["chain%d_%s" % (chain, k)] = np.concatenate([p[k] for p in parts])
+        out["chain%d_x0" % chain] = x0
+        st = c.state()
+        out["chain%d_cov" % chain] = st["cov"]
+        out["chain%d_decomp" % chain] = st["decomp"]
+        out["chain%d_center" % chain] = st["center"]
+    np.savez_compressed(os.path.join(HERE, "fake_likelihood.npz"), **out)
+    print("fake_likelihood.npz: %d events, %d points" % (len(events), len(points)))
+
+
+def run_chain(kind, dim, seed, chain, nsteps, configure=None, x0=None):
+    c = cc.CpuChain("ref", kind, dim, seed, chain)
+    if configure:
+        configure(c)
+    x0 = np.zeros(dim) if x0 is None else x0
+    ok = c.start(x0)
+    tr = c.step(nsteps)
+    st = c.state()
+    rec = {k: tr[k] for k in ("accepted", "llh_accepted", "llh_proposed", "x", "sigma")}
+    rec["ok"] = np.array([ok])
+    for k in ("cov", "decomp", "center", "accepted"):
+        rec["final_" + k] = st[k]
+    rec["final_scalars"] = np.array([st[k] for k in cc.STATE_FIELDS])
+    return rec
+
+
+def make_chains():
+    out = {}
+
+    def put(name, rec):
+        for k, v in rec.items():
+            out[name + "__" + k] = v
+
+    # C1: the documentation example (TSimpleMCMC.H:111-157), 5 dimensions,
+    # with its proposal hints, default adaptive proposal.
+    def readme(c):
+        c.set_gaussian(3, 2.0)
+        c.set_uniform(4, -5, 5)
+        c.set_correlation(3, 4, 0.3)
+    put("unit5_hints", run_chain(cc.LLH_UNIT_GAUSS, 5, 1, 0, 4000, readme))
+    put("unit5_plain", run_chain(cc.LLH_UNIT_GAUSS, 5, 1, 2, 4000))
+    put("unit9", run_chain(cc.LLH_UNIT_GAUSS, 9, 5, 1, 2500))
+    # step size frozen (SetAcceptanceRigidity(-1), TSimpleMCMC.H:995-1002):
+    # no pow() in the loop, so every device must reproduce this bit for bit.
+    def frozen(c):
+        c.set(cc.SET_ACCEPTANCE_RIGIDITY, -1.0)
+        c.set(cc.SET_SIGMA, 0.4)
+    put("unit9_frozen_sigma", run_chain(cc.LLH_UNIT_GAUSS, 9, 5, 3, 2500, frozen))
+    # as-shipped test likelihoods
+    put("horrific75", run_chain(cc.LLH_HORRIFIC, 75, 4, 11, 2500))
+    put("asym100", run_chain(cc.LLH_ASYM, 100, 4, 12, 1500, x0=np.full(100, 0.01)))
+    cov, err = cc.ref_dummy_matrices()
+    out["dummy100_error"] = err
+    out["dummy100_covariance"] = cov
+    put("dummy100", run_chain(cc.LLH_DUMMY, 100, 9, 0, 1200))
+    # correlation hints that are out of range / nearly singular: drives the
+    # conditioning ladder (SimpleMCMC.C:107-115, TSimpleMCMC.H:1124-1239)
+    def nasty(c):
+        rng = np.random.default_rng(8)
+        for i in range(6):
+            for j in range(i + 1, 6):
+                c.set_correlation(i, j, float(rng.uniform(-0.2, 0.2)))
+        c.set_correlation(2, 3, 2.0)     # clamped to the maximum correlation
+    put("unit6_clamped", run_chain(cc.LLH_UNIT_GAUSS, 6, 3, 4, 1500, nasty))
+    np.savez_compressed(os.path.join(HERE, "chains.npz"), **out)
+    print("chains.npz: %d arrays" % len(out))
+
+
+if __name__ == "__main__":
+    cc.build()
+    make_fake()
+    make_chains()

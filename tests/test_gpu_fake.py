@@ -1,0 +1,157 @@
+"""Parity of the device event likelihood (libsmcmc_b200.so, called through the
+C ABI) with the oracle: example/FakeLikelihood.H:47-81,188-216.
+
+Tolerances: histogram bin contents must be BIT-IDENTICAL (integer counts plus
+the exact sequential-sum emulation); the log-likelihood must agree to 1e-12
+relative, the bound BASELINE.json states for FP64 (the only difference left is
+the last ulp of log/exp/atan between CUDA's and the host's libm).
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+def make_engine(events, data, exposure, chains=32, seed=1):
+    import smcmc_b200
+    eng = smcmc_b200.Engine(smcmc_b200.LLH_FAKE, 9, chains, seed=seed)
+    eng.set_fake_events(events)
+    eng.set_fake_data(data, exposure)
+    return eng
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+@pytest.mark.parametrize("tag", ["", "_irregular"])
+def test_golden_grid(tag):
+    """The 19-point parameter grid of example/TestLikelihood.C plus random
+    points, values produced by the reference build."""
+    assert torch.cuda.is_available()
+    g = golden("fake_likelihood.npz")
+    eng = make_engine(g["events" + tag], g["data"], float(g["exposure"]))
+    llh = eng.eval(g["points"])
+    hist = eng.fake_histograms(g["points"])
+    assert np.array_equal(hist, g["hist" + tag])
+    assert rel(llh, g["llh" + tag]) < RTOL
+
+
+def test_against_oracle_on_seeded_inputs(checkers):
+    import smcmc_b200
+    events, data = smcmc_b200.synth.fake_inputs(3000, 3000, 10, seed=31)      # 90 000 events
+    eng = make_engine(events, data, 1.0, chains=300)
+    expo = smcmc_b200.synth.exposure_ratio(eng, data)
+    eng.set_fake_data(data, expo)
+    orc = checkers.CpuChain("orc", checkers.LLH_FAKE, 9, 1, 0)
+    orc.set_fake(events, data, 1.0)
+    sim0 = orc.fake_hist(np.zeros(9))
+    total = 0.0
+    for h in range(3):
+        part = 0.0
+        for v in sim0[h * 50:(h + 1) * 50]:
+            part += v
+        total += part
+    assert expo == float(sum(data[:50]) + sum(data[50:100]) + sum(data[100:])) / total
+    orc.set_fake(events, data, expo)
+    rng = np.random.default_rng(7)
+    pts = np.concatenate([rng.uniform(-1, 1, (200, 9)), rng.normal(0, 6, (100, 9))])
+    llh = eng.eval(pts)                      # 300 points: not a multiple of the 256-chain tile
+    hist = eng.fake_histograms(pts[:40])
+    for i in range(40):
+        assert np.array_equal(hist[i], orc.fake_hist(pts[i])), i
+    want = np.array([orc.llh(p) for p in pts])
+    assert rel(llh, want) < RTOL
+
+
+def test_generic_path_equals_fast_path(monkeypatch):
+    """Every event through the straight per-pair transcription (the path the
+    irregular events take) gives the same integer counts as the fast path."""
+    import smcmc_b200
+    g = golden("fake_likelihood.npz")
+    fast = make_engine(g["events"], g["data"], float(g["exposure"]))
+    monkeypatch.setenv("SMCMC_FAKE_FORCE_GENERIC", "1")
+    slow = make_engine(g["events"], g["data"], float(g["exposure"]))
+    monkeypatch.delenv("SMCMC_FAKE_FORCE_GENERIC")
+    pts = g["points"]
+    assert np.array_equal(fast.fake_histograms(pts), slow.fake_histograms(pts))
+    assert np.array_equal(fast.eval(pts), slow.eval(pts))
+
+
+def test_event_order_does_not_matter():
+    """Integer counting: any permutation inside the signal block and inside
+    the background block leaves every bit of the result unchanged."""
+    g = golden("fake_likelihood.npz")
+    ev = g["events"]
+    rng = np.random.default_rng(0)
+    sig = ev[ev["Type"] == 0]
+    bkg = ev[ev["Type"] != 0]
+    shuffled = np.concatenate([rng.permutation(sig), rng.permutation(bkg)])
+    a = make_engine(ev, g["data"], float(g["exposure"]))
+    b = make_engine(shuffled, g["data"], float(g["exposure"]))
+    assert np.array_equal(a.eval(g["points"]), b.eval(g["points"]))
+    assert np.array_equal(a.fake_histograms(g["points"]), b.fake_histograms(g["points"]))
+
+
+@pytest.mark.parametrize("nev", [0, 1, 2, 127, 128, 129, 8191, 8192, 8193, 20001])
+def test_ragged_event_counts(checkers, nev):
+    """Empty sample, one event, tile (128) and chunk (8192) boundaries."""
+    import smcmc_b200
+    events = smcmc_b200.synth.make_mc_sample(nev // 3, nev - nev // 3, seed=nev + 1)
+    data = smcmc_b200.synth.make_data_histograms(300, 300, seed=2)
+    eng = make_engine(events, data, 0.37, chains=5)
+    orc = checkers.CpuChain("orc", checkers.LLH_FAKE, 9, 1, 0)
+    orc.set_fake(events, data, 0.37)
+    pts = np.random.default_rng(nev).uniform(-2, 2, (5, 9))
+    hist = eng.fake_histograms(pts)
+    llh = eng.eval(pts)
+    for i in range(5):
+        assert np.array_equal(hist[i], orc.fake_hist(pts[i]))
+    assert rel(llh, np.array([orc.llh(p) for p in pts])) < RTOL
+
+
+def test_extreme_parameters(checkers):
+    """Parameter points that push masses out of range, collapse the width, or
+    are not finite: the cut / overflow handling must follow the reference
+    (FakeLikelihood.H:203-205 and TH1's under/overflow bins)."""
+    g = golden("fake_likelihood.npz")
+    eng = make_engine(g["events"], g["data"], float(g["exposure"]))
+    orc = checkers.CpuChain("orc", checkers.LLH_FAKE, 9, 1, 0)
+    orc.set_fake(g["events"], g["data"], float(g["exposure"]))
+    pts = np.zeros((12, 9))
+    pts[0, 2] = 40.0          # mass scale e^4: everything above 500
+    pts[1, 2] = -60.0         # everything in the first bin
+    pts[2, 3] = -400.0        # width -> 0: all events at the nominal mass
+    pts[3, 3] = 60.0          # width e^6
+    pts[4, 4] = 500.0         # skew saturates at 0.3
+    pts[5, 4] = -500.0
+    pts[6, 5] = 7000.0        # separation scale overflows to inf
+    pts[7, 6] = -8000.0       # separation scale underflows to 0
+    pts[8, 7] = 1e6
+    pts[9, 8] = -1e6
+    pts[10, 2] = np.nan
+    pts[11, 3] = np.inf
+    hist = eng.fake_histograms(pts)
+    llh = eng.eval(pts)
+    for i in range(len(pts)):
+        assert np.array_equal(hist[i], orc.fake_hist(pts[i])), i
+        want = orc.llh(pts[i])
+        if np.isfinite(want):
+            assert abs(llh[i] - want) <= RTOL * abs(want), i
+        else:
+            assert np.isnan(llh[i]) == np.isnan(want) and (np.isnan(want) or llh[i] == want), i
+
+
+def test_missing_inputs_fail_loudly():
+    import smcmc_b200
+    eng = smcmc_b200.Engine(smcmc_b200.LLH_FAKE, 9, 4)
+    with pytest.raises(smcmc_b200.SmcmcError) as err:
+        eng.eval(np.zeros((1, 9)))
+    assert err.value.status == -2
+    with pytest.raises(smcmc_b200.SmcmcError) as err:
+        eng.step(1)
+    assert err.value.status == -1          # Step before Start: std::invalid_argument (:371-374)

@@ -1,0 +1,125 @@
+"""The CPU checkers against the golden vectors that the reference build
+produced (tests/golden/make_golden.py), and against each other.
+
+The oracle port (oracle/smcmc_oracle.cc) must reproduce the reference's own
+code BIT FOR BIT on identical injected draws: same accept/reject sequence,
+same points, same adaptive state.  Where the reference-backed library is
+present (build container; or prebuilt on the GPU box) it is re-checked too.
+"""
+import numpy as np
+import pytest
+
+from helpers import GOLDEN_CHAINS, configure_golden, golden, golden_chain
+
+
+def _set_field(c, name, value):
+    from oracle import cpu_checkers as cc
+    c.set({"acceptance_rigidity": cc.SET_ACCEPTANCE_RIGIDITY, "sigma": cc.SET_SIGMA}[name], value)
+
+
+def _run(cc, which, name, err=None):
+    kind, dim, seed, chain, nsteps, start = GOLDEN_CHAINS[name]
+    c = cc.CpuChain(which, kind, dim, seed, chain)
+    if kind == cc.LLH_DUMMY and which == "orc":
+        c.set_error_matrix(err)
+    configure_golden(name, c, _set_field)
+    x0 = np.zeros(dim) if start is None else np.full(dim, start)
+    ok = c.start(x0)
+    tr = c.step(nsteps)
+    return ok, tr, c.state()
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_CHAINS))
+@pytest.mark.parametrize("which", ["orc", "ref"])
+def test_chain_matches_golden_bit_for_bit(checkers, have_ref, which, name):
+    if which == "ref" and not have_ref:
+        pytest.skip("reference-backed checker not built here")
+    g = golden("chains.npz")
+    want = golden_chain(g, name)
+    ok, tr, st = _run(checkers, which, name, g["dummy100_error"])
+    assert ok == int(want["ok"][0])
+    for k in ("accepted", "llh_accepted", "llh_proposed", "x", "sigma"):
+        assert np.array_equal(tr[k], want[k]), k
+    assert np.array_equal(st["cov"], want["final_cov"])
+    assert np.array_equal(st["decomp"], want["final_decomp"])
+    assert np.array_equal(st["center"], want["final_center"])
+    scal = np.array([st[k] for k in checkers.STATE_FIELDS])
+    assert np.array_equal(scal, want["final_scalars"])
+
+
+@pytest.mark.parametrize("which", ["orc", "ref"])
+def test_fake_likelihood_matches_golden(checkers, have_ref, which):
+    if which == "ref" and not have_ref:
+        pytest.skip("reference-backed checker not built here")
+    g = golden("fake_likelihood.npz")
+    for tag in ("", "_irregular"):
+        c = checkers.CpuChain(which, checkers.LLH_FAKE, 9, 1, 0)
+        c.set_fake(g["events" + tag], g["data"], float(g["exposure"]))
+        for p, llh, hist in zip(g["points"], g["llh" + tag], g["hist" + tag]):
+            assert c.llh(p) == llh
+            assert np.array_equal(c.fake_hist(p), hist)
+
+
+@pytest.mark.parametrize("which", ["orc", "ref"])
+def test_fake_schedule_matches_golden(checkers, have_ref, which):
+    """Burn-in, ResetProposal, burn-in, UpdateProposal, run: the call
+    sequence of example/FakeMCMC.C:93-165."""
+    if which == "ref" and not have_ref:
+        pytest.skip("reference-backed checker not built here")
+    g = golden("fake_likelihood.npz")
+    for chain in (0, 7):
+        c = checkers.CpuChain(which, checkers.LLH_FAKE, 9, 4242, chain)
+        c.set_fake(g["events"], g["data"], float(g["exposure"]))
+        c.start(g["chain%d_x0" % chain])
+        parts = [c.step(60)]
+        c.reset_proposal()
+        parts.append(c.step(60))
+        c.update_proposal()
+        parts.append(c.step(120))
+        for k in ("accepted", "llh_accepted", "llh_proposed", "x", "sigma"):
+            got = np.concatenate([p[k] for p in parts])
+            assert np.array_equal(got, g["chain%d_%s" % (chain, k)]), k
+        st = c.state()
+        assert np.array_equal(st["cov"], g["chain%d_cov" % chain])
+        assert np.array_equal(st["decomp"], g["chain%d_decomp" % chain])
+
+
+def test_port_equals_reference_on_fresh_inputs(checkers, have_ref):
+    """Not just the committed vectors: new seeds, every likelihood kind."""
+    if not have_ref:
+        pytest.skip("reference-backed checker not built here")
+    cc = checkers
+    for kind, dim, n in [(0, 5, 1500), (0, 3, 800), (2, 75, 1200), (3, 100, 800)]:
+        for chain in (1, 9):
+            a = cc.CpuChain("ref", kind, dim, 77, chain)
+            b = cc.CpuChain("orc", kind, dim, 77, chain)
+            x0 = np.random.default_rng(chain).uniform(-0.2, 0.2, dim)
+            assert a.start(x0) == b.start(x0)
+            ta, tb = a.step(n), b.step(n)
+            for k in ta:
+                assert np.array_equal(ta[k], tb[k]), (kind, k)
+
+
+def test_cholesky_identity(checkers):
+    """TDecompChol restated: U upper triangular with U^T U = covariance."""
+    c = checkers.CpuChain("orc", checkers.LLH_UNIT_GAUSS, 7, 3, 0)
+    c.start(np.zeros(7))
+    c.step(3000)
+    c.update_proposal()
+    st = c.state()
+    u = st["decomp"]
+    assert np.allclose(np.tril(u, -1), 0.0)
+    assert np.allclose(u.T @ u, st["cov"], rtol=1e-12, atol=1e-14)
+
+
+def test_gaussian_target_statistics(checkers):
+    """Analytic known-answer test: the chain of the unit Gaussian target has
+    mean 0 and unit variance (MakeCovariance.C:63-89 formulas)."""
+    c = checkers.CpuChain("orc", checkers.LLH_UNIT_GAUSS, 4, 12, 0)
+    c.start(np.zeros(4))
+    c.step(3000)
+    x = c.step(40000)["x"]
+    assert np.all(np.abs(x.mean(0)) < 0.08)
+    cov = np.cov(x.T)
+    assert np.all(np.abs(np.diag(cov) - 1.0) < 0.1)
+    assert np.all(np.abs(cov - np.diag(np.diag(cov))) < 0.08)

@@ -1,0 +1,95 @@
+"""The counter-based stream of include/smcmc_rng.h (host side)."""
+import ctypes
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "root-simple-mcmc_b200")
+
+
+@pytest.fixture(scope="module")
+def kat():
+    subprocess.run(["make", "-C", os.path.join(PKG, "csrc"), "../smcmc_b200/libsmcmc_hostkat.so"],
+                   check=True, stdout=subprocess.DEVNULL)
+    lib = ctypes.CDLL(os.path.join(PKG, "smcmc_b200", "libsmcmc_hostkat.so"))
+    d, u32, u64 = ctypes.c_double, ctypes.c_uint32, ctypes.c_uint64
+    lib.smcmc_kat_uniform.restype = d
+    lib.smcmc_kat_uniform.argtypes = [u64, u32, u32, u32, u32]
+    lib.smcmc_kat_normal.restype = d
+    lib.smcmc_kat_normal.argtypes = [u64, u32, u32, u32, u32]
+    lib.smcmc_kat_normals.argtypes = [u64, u32, u32, u32, u32, ctypes.c_void_p]
+    lib.smcmc_kat_det_log.restype = d
+    lib.smcmc_kat_det_log.argtypes = [d]
+    lib.smcmc_kat_det_cos2pi.restype = d
+    lib.smcmc_kat_det_cos2pi.argtypes = [d]
+    lib.smcmc_kat_seq_add.restype = d
+    lib.smcmc_kat_seq_add.argtypes = [d, d, u32]
+    lib.smcmc_kat_seq_add_naive.restype = d
+    lib.smcmc_kat_seq_add_naive.argtypes = [d, d, u32]
+    return lib
+
+
+def philox(lib, ctr, key):
+    out = (ctypes.c_uint32 * 4)()
+    lib.smcmc_kat_philox((ctypes.c_uint32 * 4)(*ctr), (ctypes.c_uint32 * 2)(*key), out)
+    return list(out)
+
+
+def test_philox_known_answers(kat):
+    # Random123 kat_vectors, philox4x32 with 10 rounds
+    assert philox(kat, [0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert philox(kat, [0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert philox(kat, [0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_uniform_open_interval_and_addressing(kat):
+    u = [kat.smcmc_kat_uniform(7, c, s, k, 0) for c in range(4) for s in range(50) for k in range(10)]
+    assert min(u) > 0.0 and max(u) < 1.0
+    assert len(set(u)) == len(u)                       # distinct counters -> distinct draws
+    assert abs(np.mean(u) - 0.5) < 0.02
+    assert kat.smcmc_kat_uniform(7, 1, 2, 3, 0) == kat.smcmc_kat_uniform(7, 1, 2, 3, 0)
+    assert kat.smcmc_kat_uniform(7, 1, 2, 3, 0) != kat.smcmc_kat_uniform(8, 1, 2, 3, 0)
+    assert kat.smcmc_kat_uniform(7, 1, 2, 3, 0) != kat.smcmc_kat_uniform(7, 1, 2, 3, 1)
+
+
+def test_normal_moments(kat):
+    n_steps, n_slots = 4000, 50
+    g = np.zeros(n_steps * n_slots)
+    kat.smcmc_kat_normals(123, 5, 0, n_steps, n_slots, g.ctypes.data)
+    assert abs(g.mean()) < 0.01
+    assert abs(g.var() - 1.0) < 0.01
+    assert abs(np.mean(g ** 3)) < 0.03
+    assert abs(np.mean(g ** 4) - 3.0) < 0.06
+    assert np.abs(g).max() < 7.0
+    # tail fractions of a unit normal
+    assert abs(np.mean(np.abs(g) > 1.959964) - 0.05) < 0.003
+
+
+def test_deterministic_log_and_cos_accuracy(kat):
+    rng = np.random.default_rng(2)
+    for x in rng.uniform(0, 1, 20000):
+        assert abs(kat.smcmc_kat_det_log(float(x)) - math.log(x)) <= 4e-16 * abs(math.log(x)) + 1e-18
+    for x in [1e-300, 5e-324, 2.0 ** -53 * 0.5, 0.5, 0.9999999999999999]:
+        assert abs(kat.smcmc_kat_det_log(x) - math.log(x)) <= 4e-16 * abs(math.log(x))
+    for x in rng.uniform(0, 1, 20000):
+        assert abs(kat.smcmc_kat_det_cos2pi(float(x)) - math.cos(2 * math.pi * x)) < 1.5e-15
+
+
+def test_sequential_sum_emulation_is_exact(kat):
+    rng = np.random.default_rng(1)
+    for t in range(4000):
+        w = float(np.exp(rng.uniform(-6, 3)))
+        if t % 3 == 0:                                  # tie-heavy: few significant bits
+            w = float(2.0 ** int(rng.integers(-6, 3)) * int(rng.integers(1, 16)))
+        s = 0.0 if t % 2 else float(rng.uniform(0, 100))
+        n = int(rng.integers(0, 100000))
+        assert kat.smcmc_kat_seq_add(s, w, n) == kat.smcmc_kat_seq_add_naive(s, w, n)
+    for s, w, n in [(0.0, 0.0, 10), (1.0, 1e-30, 1000), (0.0, 0.1, 0), (0.0, 0.1, 1), (0.0, 0.1, 3),
+                    (0.0, float("inf"), 5), (0.0, -0.5, 7), (3.0, 0.09582700887723655, 1000020)]:
+        a, b = kat.smcmc_kat_seq_add(s, w, n), kat.smcmc_kat_seq_add_naive(s, w, n)
+        assert a == b or (math.isnan(a) and math.isnan(b))
