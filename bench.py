@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on the reference's headline
+config, on N B200s of one node.
+
+Metric  : MH steps/s = chains x steps / time              (BASELINE.json)
+Workload: example/FakeMCMC.C -- binned Poisson likelihood with
+          SystematicCorrection reweighting, 4096 chains x 1 000 000 synthetic
+          events PER GPU (BASELINE.json configs[1]); chains shard over GPUs
+          with no data-path collective, so scaling is "weak".
+A step  : one TSimpleMCMC::Step() of every chain = adaptive proposal, one
+          likelihood evaluation over all events, Metropolis accept/reject.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's own CPU code
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "root-simple-mcmc_b200"))
+sys.path.insert(0, ROOT)
+
+CHAINS_PER_GPU = 4096
+EVENTS = 1_000_000
+DIM = 9
+SEED = 3
+# algorithmic work of one (chain, event) pair and bytes of one
+# ensemble step of the event likelihood.
+FLOP_PER_PAIR = 120.0
+BYTES_PER_EVENT = 32.0            # PreparedEvent, the record the pair kernel streams
+BYTES_PER_CHAIN = (9 + 150) * 8.0 # parameters in, 150 bin contents out
+
+
+def workload_inputs(events_n):
+    """SURVEY.md 8(d) C2 inputs: 1:2 signal:background MC sample, the toy
+    data of FakeData::FillData(33334, 33334); generator seed 2."""
+    from smcmc_b200 import synth
+    signal = events_n // 3 + (1 if events_n % 3 else 0)
+    events = synth.make_mc_sample(signal, events_n - signal, seed=2)
+    data = synth.make_data_histograms(33334, 33334, seed=2)
+    return events, data
+
+
+def start_points(chains, offset):
+    """FakeMCMC.C:67: every parameter ~ U(-1, 1); chain seed 3."""
+    x0 = np.zeros((chains, DIM))
+    for c in range(chains):
+        x0[c] = np.random.default_rng([SEED, offset + c]).uniform(-1.0, 1.0, DIM)
+    return x0
+
+
+# --------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (NVML,
+    the same counters as the nvidia-smi line of B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {
+                pynvml.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                pynvml.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                pynvml.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                pynvml.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            }
+            while not self._stop_evt.is_set():
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.02)
+        except Exception as exc:                      # NVML missing: report that
+            self.reasons.add("nvml_unavailable:%s" % type(exc).__name__)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# --------------------------------------------------------------------------
+# CPU arms (the reference's own code on the host cores)
+# --------------------------------------------------------------------------
+_worker = {}
+
+
+def _cpu_worker_init(which, events, data, exposure, seed):
+    from oracle import cpu_checkers as cc
+    _worker["cc"] = cc
+    _worker["which"] = which
+    _worker["inputs"] = (events, data, exposure)
+    _worker["seed"] = seed
+
+
+def _cpu_worker_start(chain):
+    cc = _worker["cc"]
+    c = cc.CpuChain(_worker["which"], cc.LLH_FAKE, DIM, _worker["seed"], chain)
+    c.set_fake(*_worker["inputs"])
+    c.start(start_points(1, chain)[0])
+    _worker["chain"] = c
+    return chain
+
+
+def _cpu_worker_step(nsteps):
+    t = time.perf_counter()
+    _worker["chain"].step(nsteps, want_x=False)
+    return time.perf_counter() - t
+
+
+def cpu_arm(events, data, exposure, steps, warmup, cores=None):
+    """`cores` independent single-chain processes (the reference is single
+    threaded and non-reentrant; independent processes are its own scale-out
+    model, continue-chain.sh) each doing `steps` Metropolis steps over ALL
+    events.  Returns (MH steps/s, description)."""
+    from oracle import cpu_checkers as cc
+    which = "ref" if cc.available("ref") else "orc"
+    if which == "orc":
+        cc.build(("orc",))
+    cores = cores or len(os.sched_getaffinity(0))
+    ctx = mp.get_context("fork")
+    pools = [ctx.Pool(1, _cpu_worker_init, (which, events, data, exposure, SEED)) for _ in range(cores)]
+    try:
+        for r in [p.apply_async(_cpu_worker_start, (i,)) for i, p in enumerate(pools)]:
+            r.get()
+        if warmup:
+            for r in [p.apply_async(_cpu_worker_step, (warmup,)) for p in pools]:
+                r.get()
+        t0 = time.perf_counter()
+        for r in [p.apply_async(_cpu_worker_step, (steps,)) for p in pools]:
+            r.get()
+        wall = time.perf_counter() - t0
+    finally:
+        for p in pools:
+            p.terminate()
+    kind = "reference" if which == "ref" else "port"
+    sample = ("%d chains (one process per host core) x %d steps x %d events of the same workload; "
+              "per-chain rate is independent of the ensemble size" % (cores, steps, len(events)))
+    return cores * steps / wall, {"kind": kind, "cores": cores, "sample": sample}
+
+
+# --------------------------------------------------------------------------
+# main arms
+# --------------------------------------------------------------------------
+def dist_setup(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def run_reference(args):
+    rank, world, local = dist_setup(args)
+    if rank != 0:
+        return
+    events, data = workload_inputs(args.events)
+    # exposure ratio (FakeLikelihood.H:107-138) computed by the CPU code itself
+    from oracle import cpu_checkers as cc
+    which = "ref" if cc.available("ref") else "orc"
+    if which == "orc":
+        cc.build(("orc",))
+    c = cc.CpuChain(which, cc.LLH_FAKE, DIM, SEED, 0)
+    c.set_fake(events, data, 1.0)
+    sim = c.fake_hist(np.zeros(DIM))
+    exposure = float(data.sum()) / float(sim.sum())
+    c.close()
+    steps = max(1, args.steps)
+    value, desc = cpu_arm(events, data, exposure, steps, min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "MH steps/sec (chains x steps)", "value": value,
+        "unit": "steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": 1e3 * desc["cores"] / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "example/FakeMCMC.C binned Poisson likelihood, %d events; CPU arm runs %d "
+                               "chains (one per core) instead of %d" % (args.events, desc["cores"], args.chains),
+                   "events": args.events, "chains": desc["cores"], "dim": DIM},
+        "cpu_baseline": dict(desc, value=value, unit="steps/s"),
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import smcmc_b200
+    from smcmc_b200 import binding, synth
+
+    rank, world, local = dist_setup(args)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the MCMC step path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    chains = args.chains
+    offset = rank * chains
+    events, data = workload_inputs(args.events)
+    x0 = start_points(chains, offset)
+
+    stream = torch.cuda.current_stream().cuda_stream
+    eng = smcmc_b200.Engine(smcmc_b200.LLH_FAKE, DIM, chains, seed=SEED, device=local, chain_offset=offset)
+    eng.set_stream(stream)
+    eng.set_fake_events(events)
+    exposure = synth.exposure_ratio(eng, data)
+    eng.set_fake_data(data, exposure)
+    ok = eng.start(x0)
+    assert ok.all()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def one_step():
+        flush.zero_()
+        eng.step(1)
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    eng.sync()
+    eng.enable_kernel_timing(True)
+    eng.pair_kernel_stats(reset=True)
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin.record()
+    for _ in range(args.steps):
+        one_step()
+    t_end.record()
+    barrier()
+    ms = t_begin.elapsed_time(t_end)
+    clocks = sampler.stop()
+    launches = eng.launch_count() - launches0 + args.steps            # + the L2 flush memsets
+    eng.sync()
+    pair_ms, pair_n = eng.pair_kernel_stats(reset=True)
+    eng.enable_kernel_timing(False)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * chains * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers -----------------
+    pinned_events = torch.empty(len(events) * 48, dtype=torch.uint8, pin_memory=True)
+    pinned_events.numpy()[:] = events.view(np.uint8)
+    ev_host = pinned_events.numpy().view(binding.EVENT_DTYPE)
+    e2e_steps = args.steps
+    out = {"points": torch.empty((1, chains, DIM), dtype=torch.float64, pin_memory=True).numpy(),
+           "llh_accepted": torch.empty((1, chains), dtype=torch.float64, pin_memory=True).numpy(),
+           "accepted": torch.empty((1, chains), dtype=torch.int32, pin_memory=True).numpy()}
+    eng2 = smcmc_b200.Engine(smcmc_b200.LLH_FAKE, DIM, chains, seed=SEED, device=local, chain_offset=offset)
+    eng2.set_stream(stream)
+    barrier()
+    t0 = time.perf_counter()
+    eng2.set_fake_events(ev_host)                       # H2D 48 B/event
+    eng2.set_fake_data(data, exposure)
+    eng2.start(x0)                                      # H2D chains*dim*8
+    for _ in range(e2e_steps):
+        eng2.step_trace(1, want=("points", "llh_accepted", "accepted"), out=out)   # D2H every step
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    h2d = (len(events) * 48 + 150 * 8 + chains * DIM * 8) / e2e_steps
+    d2h = chains * (DIM * 8 + 8 + 4) + chains * 4 / e2e_steps
+    e2e = {"value": world * chains * e2e_steps / e2e_s, "unit": "steps/s",
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "includes": "event upload + re-layout, Start, %d x Step(save=true) with the accepted points, "
+                       "likelihoods and accept flags copied to pinned host memory every step" % e2e_steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ------------------------------------------
+    pairs_per_launch = float(chains) * float(len(events))
+    pair_s = (pair_ms / max(pair_n, 1)) * 1e-3
+    fp64_peak = binding.measure_fp64_peak(local)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    alg_bytes = len(events) * BYTES_PER_EVENT + chains * BYTES_PER_CHAIN
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "pair_kernel_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    achieved_tf = FLOP_PER_PAIR * pairs_per_launch / pair_s / 1e12
+    roofline = {
+        "kernel": "kFakePairs (event x chain pair kernel)",
+        "bound": "fp64",
+        "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
+        "peak_source": "measured in this run: DFMA chain micro-benchmark (smcmc_measure_fp64_peak); "
+                       "MEASURED_PEAKS.json has no FP64 entry",
+        "algorithmic": "120 flop per (chain,event) pair (SURVEY.md 8d) x %.4g pairs per launch" % pairs_per_launch,
+        "launch_ms": pair_ms / max(pair_n, 1), "launches_timed": int(pair_n),
+        "kernel_share_of_step": (pair_ms / max(pair_n, 1)) / (ms / args.steps),
+        "pairs_per_s": pairs_per_launch / pair_s,
+        "traffic": traffic,
+        "hbm": {"achieved": alg_bytes / pair_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": alg_bytes / pair_s / 1e9 / hbm_peak, "peak_source": hbm_src,
+                "algorithmic_bytes": alg_bytes,
+                "note": "every event is re-used by all %d chains: %.0f pair evaluations per byte, "
+                        "the kernel is FP64/issue bound, not HBM bound" % (chains, pairs_per_launch / alg_bytes)},
+    }
+
+    cpu_value, cpu_desc = (None, None)
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_value, cpu_desc = cpu_arm(events, data, exposure, args.cpu_steps, 1)
+
+    line = {
+        "metric": "MH steps/sec (chains x steps)", "value": value, "unit": "steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "example/FakeMCMC.C: binned Poisson likelihood with SystematicCorrection "
+                               "reweighting, %d chains x %d events per GPU (BASELINE.json configs[1])"
+                               % (chains, len(events)),
+                   "chains_per_gpu": chains, "events": len(events), "dim": DIM, "parallelism": "chains/%d" % world,
+                   "l2": "256 MiB memset between steps (inside the timed region) flushes the 126 MB L2"},
+        "likelihood_evals_per_s": value,
+        "event_pair_evals_per_s": value * len(events),
+        "roofline": roofline,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if cpu_desc:
+        line["cpu_baseline"] = dict(cpu_desc, value=cpu_value, unit="steps/s")
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
+    ap.add_argument("--events", type=int, default=EVENTS)
+    ap.add_argument("--cpu-steps", type=int, default=12, help="steps of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

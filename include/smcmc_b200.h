@@ -167,6 +167,10 @@ int smcmc_fake_set_data(smcmc_engine* e, const double* data150, double exposure)
 /* FakeLikelihood::FillHistograms (:188-216) at m points: out[m*150] simulated
  * bin contents, same order as data150. */
 int smcmc_fake_histograms(smcmc_engine* e, const double* x, int m, double* out);
+/* The exact integer event counts behind those histograms, per weight class:
+ * out[m*450], slot layout of DESIGN.md section 3 (signal/background x decay tag
+ * x histogram x bin).  Test and diagnostics access. */
+int smcmc_fake_counts(smcmc_engine* e, const double* x, int m, uint32_t* out);
 /* TDummyLogLikelihood::Error (TDummyLogLikelihood.H:147), n x n row-major. */
 int smcmc_dummy_set_error(smcmc_engine* e, const double* error, int n);
 
@@ -196,6 +200,11 @@ int smcmc_pair_kernel_stats(smcmc_engine* e, double* total_ms, int64_t* launches
                             int reset);
 /* Enable (1) / disable (0) CUDA-event timing of the dominant kernel. */
 int smcmc_enable_kernel_timing(smcmc_engine* e, int on);
+
+/* Measured FP64 FMA throughput of `device` in TFLOP/s (2 flop per DFMA): a
+ * register-resident chain of independent DFMAs on every SM, timed with CUDA
+ * events.  The roofline denominator for the FP64-bound pair kernel. */
+int smcmc_measure_fp64_peak(int device, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -91,6 +91,9 @@ def load(which):
         fn = getattr(lib, p + name)
         fn.restype = res
         fn.argtypes = args
+    if which == "orc":
+        lib.orc_chain_fake_counts.restype = ci
+        lib.orc_chain_fake_counts.argtypes = [vp, vp, vp]
     if which == "ref":
         lib.ref_fake_generate.restype = ctypes.c_long
         lib.ref_fake_generate.argtypes = [ctypes.c_ulong, ci, ci, cd, vp,
@@ -195,6 +198,13 @@ class CpuChain:
         x = np.ascontiguousarray(x, dtype=np.float64)
         out = np.zeros(150)
         self._check(self._f("chain_fake_hist")(self.h, _ptr(x), _ptr(out)))
+        return out
+
+    def fake_counts(self, x):
+        """Oracle port only: exact event counts per (class, histogram, bin)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.zeros(450, np.uint32)
+        self._check(self.lib.orc_chain_fake_counts(self.h, _ptr(x), _ptr(out)))
         return out
 
 

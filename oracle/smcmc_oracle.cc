@@ -193,6 +193,33 @@ struct Likelihood {
             sim[h][FindBin50(mass)] += w;
         }
     }
+    // The same loop, but counting events per weight class instead of summing
+    // weights: slot layout of the device count table (signal untagged 0-99,
+    // signal tagged 100-149, background untagged 150-249, background tagged
+    // 250-299, data-typed 300-449; inside a block: Close bins, Separated bins).
+    void CountFake(const double* p, uint32_t* out450) {
+        std::memset(out450, 0, 450 * sizeof(uint32_t));
+        for (size_t i = 0; i < events.size(); ++i) {
+            const orc_event& e = events[i];
+            double mass = InvariantMass(e, p);
+            double sep = Separation(e, p);
+            if (mass > 500.0) continue;
+            if (mass < 0.0) continue;
+            if (sep < 0.0) continue;
+            int bin = FindBin50(mass);
+            if (bin < 1 || bin > 50) continue;
+            int h = 1;
+            if (e.MuDk > 0) h = 2;
+            else if (sep < 100.0) h = 0;
+            int slot;
+            if (e.Type < 0) slot = 300 + h * 50;
+            else {
+                int base = (e.Type == 0) ? 0 : 150;
+                slot = (h == 2) ? base + 100 : base + h * 50;
+            }
+            out450[slot + bin - 1] += 1;
+        }
+    }
     // example/FakeLikelihood.H:47-81
     double EvalFake(const double* p) {
         FillFake(p);
@@ -749,6 +776,13 @@ int orc_chain_fake_hist(void* h, const double* x, double* out150) {
     l.FillFake(x);
     for (int hh = 0; hh < 3; ++hh)
         for (int b = 0; b < 50; ++b) out150[hh * 50 + b] = l.sim[hh][b + 1];
+    return 0;
+}
+
+int orc_chain_fake_counts(void* h, const double* x, uint32_t* out450) {
+    Likelihood& l = H(h)->like;
+    if (l.kind != ORC_LLH_FAKE) { gLastError = "not a FakeLikelihood chain"; return -1; }
+    l.CountFake(x, out450);
     return 0;
 }
 

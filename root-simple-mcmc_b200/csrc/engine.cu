@@ -596,6 +596,20 @@ int smcmc_fake_histograms(smcmc_engine* e, const double* x, int m, double* out) 
     });
 }
 
+int smcmc_fake_counts(smcmc_engine* e, const double* x, int m, uint32_t* out) {
+    return guarded(e, [&]() {
+        if (e->cfg.likelihood != SMCMC_LLH_FAKE) throw Error(SMCMC_ERR_LOGIC, "engine was not created with SMCMC_LLH_FAKE");
+        if (!out) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null output");
+        evalHost(e, x, m, nullptr, nullptr);
+        const int stride = e->fakeCountStride;
+        std::vector<uint32_t> host((size_t)kFakeSlots * stride);
+        CUDA_CHECK(cudaMemcpyAsync(host.data(), e->fakeCounts.get(), host.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        for (int p = 0; p < m; ++p)
+            for (int s = 0; s < kFakeSlots; ++s) out[(size_t)p * kFakeSlots + s] = host[(size_t)s * stride + p];
+    });
+}
+
 int smcmc_eval(smcmc_engine* e, const double* x, int m, double* llh) {
     return guarded(e, [&]() {
         if (!llh) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null output");
@@ -730,6 +744,57 @@ int smcmc_get(smcmc_engine* e, int field, void* dst, size_t bytes) {
         }
         default: throw Error(SMCMC_ERR_INVALID_ARGUMENT, "unknown field");
         }
+    });
+}
+
+namespace smcmc {
+// 8 independent DFMA chains per thread, 4096 iterations.
+__global__ void __launch_bounds__(256) kFp64Peak(double* out, double a, double b, int iters) {
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (double)(threadIdx.x + k);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = __fma_rn(v[k], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
+    if (s == 12345.678) out[0] = s;      // never true: keeps the chain alive
+}
+}  // namespace smcmc
+
+int smcmc_measure_fp64_peak(int device, double* tflops) {
+    return guarded(nullptr, [&]() {
+        if (!tflops) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null output");
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+            cudaGetLastError();
+            throw Error(SMCMC_ERR_NO_DEVICE, "no CUDA device");
+        }
+        CUDA_CHECK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        DeviceBuffer<double> out;
+        out.reserve(1);
+        const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+        cudaEvent_t e0, e1;
+        CUDA_CHECK(cudaEventCreate(&e0));
+        CUDA_CHECK(cudaEventCreate(&e1));
+        double best = 0.0;
+        for (int rep = 0; rep < 6; ++rep) {
+            CUDA_CHECK(cudaEventRecord(e0));
+            kFp64Peak<<<blocks, threads>>>(out.get(), 0.999999, 1e-7, iters);
+            CUDA_CHECK(cudaEventRecord(e1));
+            CUDA_CHECK(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+            double flops = 2.0 * 8.0 * iters * (double)blocks * threads;
+            if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *tflops = best;
     });
 }
 

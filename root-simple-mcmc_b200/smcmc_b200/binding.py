@@ -103,6 +103,7 @@ def load_library():
         "smcmc_fake_set_events": (ci, [vp, vp, ctypes.c_int64]),
         "smcmc_fake_set_data": (ci, [vp, vp, cd]),
         "smcmc_fake_histograms": (ci, [vp, vp, ci, vp]),
+        "smcmc_fake_counts": (ci, [vp, vp, ci, vp]),
         "smcmc_dummy_set_error": (ci, [vp, vp, ci]),
         "smcmc_eval": (ci, [vp, vp, ci, vp]),
         "smcmc_start": (ci, [vp, vp, vp]),
@@ -112,6 +113,7 @@ def load_library():
         "smcmc_launch_count": (ctypes.c_int64, [vp]),
         "smcmc_pair_kernel_stats": (ci, [vp, ctypes.POINTER(cd), ctypes.POINTER(ctypes.c_int64), ci]),
         "smcmc_enable_kernel_timing": (ci, [vp, ci]),
+        "smcmc_measure_fp64_peak": (ci, [ci, ctypes.POINTER(cd)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -127,10 +129,22 @@ EXPORTED_SYMBOLS = [
     "smcmc_prop_set_uniform", "smcmc_prop_set_correlation",
     "smcmc_prop_reset_correlations", "smcmc_prop_update", "smcmc_prop_reset",
     "smcmc_fake_set_events", "smcmc_fake_set_data", "smcmc_fake_histograms",
+    "smcmc_fake_counts",
     "smcmc_dummy_set_error", "smcmc_eval", "smcmc_start", "smcmc_step",
     "smcmc_step_trace", "smcmc_get", "smcmc_launch_count",
     "smcmc_pair_kernel_stats", "smcmc_enable_kernel_timing",
+    "smcmc_measure_fp64_peak",
 ]
+
+
+def measure_fp64_peak(device=0):
+    """Measured DFMA throughput of the device, TFLOP/s."""
+    lib = load_library()
+    out = ctypes.c_double()
+    rc = lib.smcmc_measure_fp64_peak(device, ctypes.byref(out))
+    if rc != 0:
+        raise SmcmcError(rc, lib.smcmc_last_error(None).decode())
+    return out.value
 
 
 def _ptr(a):
@@ -210,6 +224,13 @@ class Engine:
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, self.dim)
         out = np.zeros((x.shape[0], 150))
         self._check(self.lib.smcmc_fake_histograms(self.h, _ptr(x), x.shape[0], _ptr(out)))
+        return out
+
+    def fake_counts(self, x):
+        """Exact event counts per (weight class, histogram, bin): (m, 450) uint32."""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, self.dim)
+        out = np.zeros((x.shape[0], 450), np.uint32)
+        self._check(self.lib.smcmc_fake_counts(self.h, _ptr(x), x.shape[0], _ptr(out)))
         return out
 
     def set_error_matrix(self, e):
