@@ -171,6 +171,11 @@ int smcmc_fake_histograms(smcmc_engine* e, const double* x, int m, double* out);
  * out[m*450], slot layout of DESIGN.md section 3 (signal/background x decay tag
  * x histogram x bin).  Test and diagnostics access. */
 int smcmc_fake_counts(smcmc_engine* e, const double* x, int m, uint32_t* out);
+/* Diagnostic for the pair kernel's FP32 interval filter:
+ * evaluates EVERY (point, event) pair both ways and returns out3 = {pairs,
+ * pairs the filter left to FP64, pairs where a filter decision differs from
+ * the FP64 decision}.  The last number must be 0. */
+int smcmc_fake_filter_check(smcmc_engine* e, const double* x, int m, uint64_t* out3);
 /* TDummyLogLikelihood::Error (TDummyLogLikelihood.H:147), n x n row-major. */
 int smcmc_dummy_set_error(smcmc_engine* e, const double* error, int n);
 

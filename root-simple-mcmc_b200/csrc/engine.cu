@@ -72,6 +72,10 @@ struct smcmc_engine {
     DeviceBuffer<double> errMatrix;                 // DUMMY
     int errDim = 0;
     DeviceBuffer<PreparedEvent> fakeEvents;         // FAKE
+    DeviceBuffer<FilterEvent> fakeFilterEvents;
+    DeviceBuffer<FilterChain> fakeFilterChains;
+    DeviceBuffer<unsigned long long> fakeStats;
+    bool exactOnly = false;
     DeviceBuffer<smcmc_event> fakeIrregular;
     int64_t fakeClassBase[kFakeClasses] = {0, 0, 0, 0};
     int64_t fakeClassCount[kFakeClasses] = {0, 0, 0, 0};
@@ -195,19 +199,10 @@ struct smcmc_engine {
         }
     }
 
-    void evaluateFake(const double* xDev, int m, double* llhDev, double* histDev) {
-        if (fakeEventCount < 0) throw Error(SMCMC_ERR_LOGIC, "events not set (smcmc_fake_set_events)");
-        if (!fakeDataSet) throw Error(SMCMC_ERR_LOGIC, "data histograms not set (smcmc_fake_set_data)");
-        const int stride = (m + 31) / 32 * 32;
-        fakeChains.reserve(stride);
-        fakeCounts.reserve((size_t)kFakeSlots * stride);
-        fakeCountStride = stride;
-        CUDA_CHECK(cudaMemsetAsync(fakeCounts.get(), 0, (size_t)kFakeSlots * stride * sizeof(uint32_t), stream));
-        kFakePrepareChains<<<ceilDiv(m, 128), 128, 0, stream>>>(xDev, m, n(), fakeExposure, fakeChains.get());
-        launched();
-
+    PairLaunch pairLaunch(int m, int stride) {
         PairLaunch L;
         L.events = fakeEvents.get();
+        L.filterEvents = fakeFilterEvents.get();
         int chunks = 0;
         for (int c = 0; c < kFakeClasses; ++c) {
             L.classBase[c] = fakeClassBase[c];
@@ -217,9 +212,30 @@ struct smcmc_engine {
         }
         L.chunkBase[kFakeClasses] = chunks;
         L.chains = fakeChains.get();
+        L.filterChains = fakeFilterChains.get();
         L.numPoints = m;
         L.pointStride = stride;
         L.counts = fakeCounts.get();
+        L.stats = collectStats ? fakeStats.get() : nullptr;
+        return L;
+    }
+    bool collectStats = false;
+
+    void evaluateFake(const double* xDev, int m, double* llhDev, double* histDev) {
+        if (fakeEventCount < 0) throw Error(SMCMC_ERR_LOGIC, "events not set (smcmc_fake_set_events)");
+        if (!fakeDataSet) throw Error(SMCMC_ERR_LOGIC, "data histograms not set (smcmc_fake_set_data)");
+        const int stride = (m + 31) / 32 * 32;
+        fakeChains.reserve(stride);
+        fakeFilterChains.reserve(stride);
+        fakeCounts.reserve((size_t)kFakeSlots * stride);
+        fakeCountStride = stride;
+        CUDA_CHECK(cudaMemsetAsync(fakeCounts.get(), 0, (size_t)kFakeSlots * stride * sizeof(uint32_t), stream));
+        kFakePrepareChains<<<ceilDiv(m, 128), 128, 0, stream>>>(xDev, m, n(), fakeExposure, fakeChains.get(),
+                                                                fakeFilterChains.get(), exactOnly ? 1 : 0);
+        launched();
+
+        PairLaunch L = pairLaunch(m, stride);
+        const int chunks = L.chunkBase[kFakeClasses];
         if (chunks > 0) {
             const int pointTiles = ceilDiv(m, kPairThreads);
             cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -372,6 +388,9 @@ int smcmc_create(const smcmc_config* cfg, smcmc_engine** out) {
         }
         CUDA_CHECK(cudaMemcpy(e->sc.get(), init.data(), sizeof(ChainScalars) * E, cudaMemcpyHostToDevice));
         e->forceGeneric = std::getenv("SMCMC_FAKE_FORCE_GENERIC") != nullptr;
+        e->exactOnly = std::getenv("SMCMC_FAKE_EXACT") != nullptr;
+        e->fakeStats.reserve(4);
+        CUDA_CHECK(cudaMemset(e->fakeStats.get(), 0, 4 * sizeof(unsigned long long)));
 
         if (cfg->likelihood == SMCMC_LLH_FAKE) {
             // Pre-images of the TH1 bin edges under this host's exp: bin(exp(l)).
@@ -541,10 +560,12 @@ int smcmc_fake_set_events(smcmc_engine* e, const smcmc_event* events, int64_t co
         }
         e->fakeIrregularCount = (int64_t)hostCount[kIrregularClass];
         e->fakeEvents.reserve(total > 0 ? total : 1);
+        e->fakeFilterEvents.reserve(total > 0 ? total : 1);
         e->fakeIrregular.reserve(e->fakeIrregularCount > 0 ? e->fakeIrregularCount : 1);
         if (count > 0) {
             CUDA_CHECK(cudaMemcpyAsync(baseDev.get(), base, sizeof(base), cudaMemcpyHostToDevice, e->stream));
-            kFakeScatter<<<ceilDiv(count, 256), 256, 0, e->stream>>>(raw.get(), count, e->fakeEvents.get(), baseDev.get(),
+            kFakeScatter<<<ceilDiv(count, 256), 256, 0, e->stream>>>(raw.get(), count, e->fakeEvents.get(),
+                                                                   e->fakeFilterEvents.get(), baseDev.get(),
                                                                    counters.get() + 8, e->fakeIrregular.get(), e->forceGeneric);
             e->launched();
             CUDA_CHECK(cudaStreamSynchronize(e->stream));
@@ -607,6 +628,23 @@ int smcmc_fake_counts(smcmc_engine* e, const double* x, int m, uint32_t* out) {
         CUDA_CHECK(cudaStreamSynchronize(e->stream));
         for (int p = 0; p < m; ++p)
             for (int s = 0; s < kFakeSlots; ++s) out[(size_t)p * kFakeSlots + s] = host[(size_t)s * stride + p];
+    });
+}
+
+int smcmc_fake_filter_check(smcmc_engine* e, const double* x, int m, uint64_t* out3) {
+    return guarded(e, [&]() {
+        if (e->cfg.likelihood != SMCMC_LLH_FAKE) throw Error(SMCMC_ERR_LOGIC, "engine was not created with SMCMC_LLH_FAKE");
+        if (!out3) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null output");
+        evalHost(e, x, m, nullptr, nullptr);         // fills the per-chain constants for these points
+        PairLaunch L = e->pairLaunch(m, e->fakeCountStride);
+        CUDA_CHECK(cudaMemsetAsync(e->fakeStats.get(), 0, 4 * sizeof(unsigned long long), e->stream));
+        dim3 grid(512, ceilDiv(m, 128));
+        kFakeVerifyFilter<<<grid, 128, 0, e->stream>>>(L, e->fakeStats.get());
+        e->launched();
+        unsigned long long host[4];
+        CUDA_CHECK(cudaMemcpyAsync(host, e->fakeStats.get(), sizeof(host), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        for (int i = 0; i < 3; ++i) out3[i] = host[i];
     });
 }
 

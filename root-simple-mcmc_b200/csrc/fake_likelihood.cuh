@@ -93,7 +93,8 @@ __device__ __forceinline__ int classifyEvent(const smcmc_event& e, PreparedEvent
     p.nomLog = nomLog;
     p.sep = e.Separation;
     bool regular = e.Type >= 0 && isfinite(p.dLog) && isfinite(p.logSigma) &&
-                   isfinite(p.nomLog) && isfinite(p.sep) && p.sep >= 0.0;
+                   isfinite(p.nomLog) && isfinite(p.sep) && p.sep >= 0.0 &&
+                   fabs(p.nomLog) <= 11.0;      // |nomLog*log2(e)| <= 16: filter guard
     if (!regular) return kIrregularClass;
     return (e.Type == 0 ? 0 : 2) + (e.MuDk > 0 ? 1 : 0);
 }
@@ -116,8 +117,11 @@ __global__ void kFakeCountClasses(const smcmc_event* __restrict__ ev, int64_t n,
 
 // Scatter events into their class segment.  Order inside a segment is
 // arbitrary (integer counting does not depend on it).
+struct FilterEvent;
+__device__ __forceinline__ void storeFilterEvent(FilterEvent* dst, int64_t idx, const PreparedEvent& p);
+
 __global__ void kFakeScatter(const smcmc_event* __restrict__ ev, int64_t n,
-                             PreparedEvent* prepared, const int64_t* classBase,
+                             PreparedEvent* prepared, FilterEvent* filter, const int64_t* classBase,
                              unsigned long long* cursor, smcmc_event* irregular,
                              int forceGeneric) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -127,14 +131,21 @@ __global__ void kFakeScatter(const smcmc_event* __restrict__ ev, int64_t n,
     int cls = forceGeneric ? kIrregularClass : classifyEvent(e, p);
     unsigned long long pos = atomicAdd(&cursor[cls], 1ull);
     if (cls == kIrregularClass) irregular[pos] = e;
-    else prepared[classBase[cls] + (int64_t)pos] = p;
+    else {
+        prepared[classBase[cls] + (int64_t)pos] = p;
+        storeFilterEvent(filter, classBase[cls] + (int64_t)pos, p);
+    }
 }
 
 // ---------------------------------------------------------------------------
 // Per-evaluation chain constants.
 // ---------------------------------------------------------------------------
+struct FilterChain;
+__device__ __forceinline__ void storeFilterChain(FilterChain* dst, int c, const FakeChainParams& cp, int exactOnly);
+
 __global__ void kFakePrepareChains(const double* __restrict__ x, int m, int dim,
-                                   double exposure, FakeChainParams* out) {
+                                   double exposure, FakeChainParams* out, FilterChain* fout,
+                                   int exactOnly) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= m) return;
     const double* p = x + (size_t)c * dim;
@@ -162,14 +173,15 @@ __global__ void kFakePrepareChains(const double* __restrict__ x, int m, int dim,
     cp.weight[2] = __dmul_rn(bkgNo, exposure);
     cp.weight[3] = __dmul_rn(bkgTag, exposure);
     out[c] = cp;
+    storeFilterChain(fout, c, cp, exactOnly);
 }
 
 // ---------------------------------------------------------------------------
-// Bin lookup.
+// Bin lookup (exact).
 // ---------------------------------------------------------------------------
-// Exact: 0-based bin of a corrected log-mass, or 50 when the event is cut
+// 0-based bin of a corrected log-mass, or 50 when the event is cut
 // (FakeLikelihood.H:203-204 and the TH1 overflow bin).  NaN is cut.
-__device__ __noinline__ int exactBin(double lm, int guess) {
+__device__ __forceinline__ int exactBin(double lm, int guess) {
     if (!(lm < gEdges[50])) return 50;
     int k = min(max(guess, 0), 49);
     while (k > 0 && lm < gEdges[k]) --k;
@@ -177,36 +189,156 @@ __device__ __noinline__ int exactBin(double lm, int guess) {
     return k;
 }
 
-// double -> float by bit manipulation (truncation), without touching the
-// FP64 pipe's conversion unit.  Only used for the bin guess.
-__device__ __forceinline__ float truncToFloat(double v) {
-    const unsigned hi = (unsigned)__double2hiint(v);
-    const unsigned lo = (unsigned)__double2loint(v);
-    const int e = (int)((hi >> 20) & 0x7ff) - 1023;
-    unsigned bits;
-    if (e < -60) bits = 0u;                         // |v| tiny: exp(v) == 1 to float precision
-    else if (e > 7) bits = 0x43800000u;             // |v| >= 256 (also inf/NaN): saturate
-    else bits = ((unsigned)(e + 127) << 23) | ((hi & 0xfffffu) << 3) | (lo >> 29);
-    return __uint_as_float(bits | (hi & 0x80000000u));
+// The reference's arithmetic for one (chain, event) pair in FP64, operation
+// for operation (SystematicCorrection.H:69-74, :45-47; FakeLikelihood.H:
+// 203-214).  Returns the counter row (bin, +50 for the Separated histogram of
+// untagged events) or -1 when the event is cut.
+__device__ __forceinline__ int exactDecide(const PreparedEvent& ev, const FakeChainParams& cp,
+                                           int cls) {
+    double skew = exp(__dmul_rn(ev.logSigma, cp.skewc));
+    double lm = __dadd_rn(ev.nomLog, __dmul_rn(ev.dLog, skew));
+    lm = __dadd_rn(ev.nomLog, __dmul_rn(__dsub_rn(lm, ev.nomLog), cp.width));
+    lm = __dadd_rn(lm, cp.scale);
+    int guess = (int)(__expf((float)lm) * 0.1f);      // any guess is corrected below
+    int bin = exactBin(lm, guess);                    // mass = exp(lm); TH1 bin of mass
+    if (bin >= 50) return -1;
+    if (!(cls & 1)) {
+        double sep = __dmul_rn(ev.sep, cp.sepScale[cls >> 1]);
+        if (!(sep < 100.0)) bin += 50;
+    }
+    return bin;
 }
 
-// The common case costs FP32/SFU/integer work only: an approximate mass gives
-// a candidate bin, accepted when it is farther than the approximation error
-// from a bin edge.  Everything else goes through exactBin.
-__device__ __forceinline__ int fastBin(double lm) {
-    float mf = __expf(truncToFloat(lm));            // relative error < 2e-6
-    float q = mf * 0.1f;                            // bins are 10 wide
-    float qc = fminf(q, 60.0f);
-    // nearest integer to qc-0.5 by the 1.5*2^23 trick (FP32 pipe, no F2I)
-    float shifted = (qc - 0.5f) + 12582912.0f;
-    float kf = shifted - 12582912.0f;
-    float frac = qc - kf;
-    int k = __float_as_int(shifted) - 0x4b400000;
-    bool sure = (frac > 4e-4f) && (frac < 1.0f - 4e-4f) && (q < 49.9f) && (k >= 0);
-    bool surelyOut = (q > 50.1f) && (q < 1e30f);
-    if (sure) return k;
-    if (surelyOut) return 50;
-    return exactBin(lm, k);
+// ---------------------------------------------------------------------------
+// The FP32 interval filter.
+//
+// Only a DISCRETE decision is needed per pair: which counter row, or none.
+// The filter evaluates q = mass/10 in FP32 together with a rigorous bound mq
+// on |q_fp32 - q_exact| and accepts the FP32 decision only when q is farther
+// than mq from the two neighbouring bin edges (and from the cut at 500, and
+// the scaled separation farther than its bound from 100).  Everything else is
+// "unsure" and is re-evaluated with exactDecide.  The filter therefore never
+// changes a count; it only decides which pairs need FP64.
+//
+// Error bound (u = 2^-24; inputs are correctly rounded to FP32):
+//   x2 = ls*scl2             rel. error <= 3u
+//   skew = ex2.approx(x2)    rel. error <= 4u + ln2*3u|x2|          (2 ulp unit)
+//   t = d*skew               rel. error <= (6 + 2.08|x2|)u
+//   z = t*w2 + nl2 + c2      abs. error <= u[(9+2.08|x2|)|t w2| + 4|nl2| + 4|c2|]
+//   q = ex2.approx(z)        rel. error <= 4u + ln2*abs.err(z)
+// With the guards |x2| <= 16 (checked per pair) and |nl2| <= 16 (checked per
+// event at upload) this is  <= u[48.4 + 2.78|c2| + 30.5|t w2|];  the code
+// uses twice that.
+// ---------------------------------------------------------------------------
+struct __align__(16) FilterEvent {
+    float ls;      // logSigma
+    float d;       // dLog
+    float nl2;     // nomLog * log2(e)
+    float sep;
+};
+struct __align__(16) FilterChain {
+    float scl2;    // skewc * log2(e)
+    float w2;      // width * log2(e)
+    float c2;      // scale * log2(e) - log2(10)
+    float m0;      // constant part of the relative error bound of q
+    float ss[2];   // separation scale: signal, background
+    float pad_[2];
+};
+__device__ __forceinline__ void storeFilterEvent(FilterEvent* dst, int64_t idx, const PreparedEvent& p) {
+    FilterEvent f;
+    f.ls = __double2float_rn(p.logSigma);
+    f.d = __double2float_rn(p.dLog);
+    f.nl2 = __double2float_rn(p.nomLog * 1.4426950408889634);
+    f.sep = __double2float_rn(p.sep);
+    dst[idx] = f;
+}
+constexpr float kFilterU = 5.9604645e-8f;
+constexpr float kFilterSlope = 2.0f * kFilterU * 30.5f;
+
+
+// exactOnly (SMCMC_FAKE_EXACT=1): an infinite error bound makes every pair
+// "unsure", i.e. the whole evaluation runs through the FP64 arithmetic.
+__device__ __forceinline__ void storeFilterChain(FilterChain* dst, int c, const FakeChainParams& cp, int exactOnly) {
+    const double log2e = 1.4426950408889634, log2ten = 3.3219280948873623;
+    FilterChain f;
+    f.scl2 = __double2float_rn(cp.skewc * log2e);
+    f.w2 = __double2float_rn(cp.width * log2e);
+    const double c2 = cp.scale * log2e - log2ten;
+    f.c2 = __double2float_rn(c2);
+    f.m0 = __double2float_ru(2.0 * 5.9604645e-8 * (48.4 + 2.78 * fabs(c2)));
+    if (exactOnly) f.m0 = __int_as_float(0x7f800000);
+    f.ss[0] = __double2float_rn(cp.sepScale[0]);
+    f.ss[1] = __double2float_rn(cp.sepScale[1]);
+    f.pad_[0] = f.pad_[1] = 0.f;
+    dst[c] = f;
+}
+
+__device__ __forceinline__ float fastEx2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// One decision.  `sure` is false when the pair must go to FP64.  A sure pair
+// with row >= kFilterCutRow is cut (mass >= 500); q beyond the float grid of
+// the floor trick only occurs far above 50, where any row value means "cut".
+constexpr int kFilterCutRow = 50;
+template <bool TAGGED>
+__device__ __forceinline__ void filterDecide(const FilterEvent& ev, float scl2, float w2, float c2,
+                                             float m0, float ss, bool& sure, int& row) {
+    const float x2 = ev.ls * scl2;
+    const float tw = (ev.d * fastEx2(x2)) * w2;
+    const float q = fastEx2((tw + ev.nl2) + c2);
+    const float mq = q * fmaf(fabsf(tw), kFilterSlope, m0);
+    const float shifted = __fadd_rz(q, 12582912.0f);          // 1.5*2^23 + floor(q)
+    const float frac = q - (shifted - 12582912.0f);
+    const int k = __float_as_int(shifted) - 0x4b400000;       // floor(q)
+    // away from both neighbouring edges by more than the error bound
+    bool ok = (fabsf(x2) <= 16.0f) & (fabsf(frac - 0.5f) < 0.5f - mq);
+    row = k;
+    if (!TAGGED) {
+        const float sp = ev.sep * ss;
+        ok = ok & (fabsf(sp - 100.0f) > 1.0e-4f);
+        row = (sp > 100.0f) ? k + 50 : k;
+        if (k >= kFilterCutRow) row = kFilterCutRow + 50;     // stays "cut"
+    }
+    sure = ok;
+}
+
+// The same decision for kPairIlp consecutive events, written stage by stage
+// (identical arithmetic to filterDecide).
+constexpr int kPairIlp = 4;
+template <bool TAGGED>
+__device__ __forceinline__ void filterDecideMany(const FilterEvent* ev, float scl2, float w2, float c2,
+                                                 float m0, float ss, bool (&sure)[kPairIlp],
+                                                 int (&row)[kPairIlp]) {
+    FilterEvent e[kPairIlp];
+    float x2[kPairIlp], tw[kPairIlp], q[kPairIlp];
+#pragma unroll
+    for (int g = 0; g < kPairIlp; ++g) e[g] = ev[g];
+#pragma unroll
+    for (int g = 0; g < kPairIlp; ++g) x2[g] = e[g].ls * scl2;
+#pragma unroll
+    for (int g = 0; g < kPairIlp; ++g) tw[g] = (e[g].d * fastEx2(x2[g])) * w2;
+#pragma unroll
+    for (int g = 0; g < kPairIlp; ++g) q[g] = fastEx2((tw[g] + e[g].nl2) + c2);
+#pragma unroll
+    for (int g = 0; g < kPairIlp; ++g) {
+        const float mq = q[g] * fmaf(fabsf(tw[g]), kFilterSlope, m0);
+        const float shifted = __fadd_rz(q[g], 12582912.0f);
+        const float frac = q[g] - (shifted - 12582912.0f);
+        const int k = __float_as_int(shifted) - 0x4b400000;
+        bool ok = (fabsf(x2[g]) <= 16.0f) & (fabsf(frac - 0.5f) < 0.5f - mq);
+        int r = k;
+        if (!TAGGED) {
+            const float sp = e[g].sep * ss;
+            ok = ok & (fabsf(sp - 100.0f) > 1.0e-4f);
+            r = (sp > 100.0f) ? k + 50 : k;
+            if (k >= kFilterCutRow) r = kFilterCutRow + 50;
+        }
+        sure[g] = ok;
+        row[g] = r;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -249,75 +381,99 @@ __device__ __forceinline__ void tmaLoad1D(void* dstSmem, const void* srcGlobal, 
 // The pair kernel.
 // ---------------------------------------------------------------------------
 struct PairLaunch {
-    const PreparedEvent* events;     // all classes, class segments contiguous
+    const PreparedEvent* events;     // FP64 records, class segments contiguous
+    const FilterEvent* filterEvents; // FP32 records, same order
     int64_t classBase[kFakeClasses]; // first event of each class
     int64_t classCount[kFakeClasses];
     int chunkBase[kFakeClasses + 1]; // prefix sum of chunks per class
     const FakeChainParams* chains;
+    const FilterChain* filterChains;
     int numPoints;                   // chains (parameter points) to evaluate
     int pointStride;                 // row length of the count table
     uint32_t* counts;                // [kFakeSlots][pointStride]
+    unsigned long long* stats;       // optional: [0] unsure pairs
 };
 
-template <bool TAGGED>
-__device__ __forceinline__ void pairOne(const PreparedEvent& ev, double skewc, double width,
-                                        double scale, double sepScale, uint32_t* myCounters) {
-    // example/SystematicCorrection.H:69-74, in the reference's order
-    double skew = exp(__dmul_rn(ev.logSigma, skewc));
-    double lm = __dadd_rn(ev.nomLog, __dmul_rn(ev.dLog, skew));
-    lm = __dadd_rn(ev.nomLog, __dmul_rn(__dsub_rn(lm, ev.nomLog), width));
-    lm = __dadd_rn(lm, scale);
-    int bin = fastBin(lm);                        // mass = exp(lm); TH1 bin of mass
-    if (bin >= 50) return;                        // FakeLikelihood.H:203-204 / overflow
-    int row = bin;
-    if (!TAGGED) {
-        double sep = __dmul_rn(ev.sep, sepScale); // SystematicCorrection.H:45-47
-        if (!(sep < 100.0)) row += 50;            // FakeLikelihood.H:210-214
-    }
-    myCounters[row * kPairThreads] += 1;
+// FP64 evaluation of one undecided pair (out of line: it is the rare path).
+__device__ __noinline__ unsigned int exactCount(const PreparedEvent* ev, const FakeChainParams* cp,
+                                                int cls, uint32_t* mine, bool live) {
+    if (!live) return 0;
+    const int row = exactDecide(*ev, *cp, cls);
+    if (row >= 0) mine[row * kPairThreads] += 1;
+    return 1;
 }
 
 template <bool TAGGED>
 __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t first, int count,
-                                          int pointBase, PreparedEvent (*tiles)[kPairTile],
+                                          int pointBase, FilterEvent (*tiles)[kPairTile],
                                           uint64_t* bars, uint32_t* counters) {
     const int tid = threadIdx.x;
     const int point = pointBase + tid;
     const bool live = point < L.numPoints;
-    FakeChainParams cp;
-    if (live) cp = L.chains[point];
-    else { cp.skewc = 0; cp.width = 1; cp.scale = 0; cp.sepScale[0] = cp.sepScale[1] = 1; }
-    const double sepScale = cp.sepScale[cls >> 1];
+    FilterChain fc;
+    if (live) fc = L.filterChains[point];
+    else { fc.scl2 = 0.f; fc.w2 = 1.f; fc.c2 = 0.f; fc.m0 = 1e-4f; fc.ss[0] = fc.ss[1] = 1.f; }
+    const float ss = (cls >> 1) ? fc.ss[1] : fc.ss[0];
     constexpr int rows = TAGGED ? 50 : 100;
     for (int r = 0; r < rows; ++r) counters[r * kPairThreads + tid] = 0;
     uint32_t* mine = counters + tid;
+    unsigned int unsureTotal = 0;
 
-    const PreparedEvent* src = L.events + L.classBase[cls] + first;
+    const int64_t classFirst = L.classBase[cls] + first;
+    const FilterEvent* src = L.filterEvents + classFirst;
     const int numTiles = (count + kPairTile - 1) / kPairTile;
     if (tid == 0) {
         int len = min(kPairTile, count);
-        mbarExpectTx(&bars[0], (uint32_t)len * sizeof(PreparedEvent));
-        tmaLoad1D(tiles[0], src, (uint32_t)len * sizeof(PreparedEvent), &bars[0]);
+        mbarExpectTx(&bars[0], (uint32_t)len * sizeof(FilterEvent));
+        tmaLoad1D(tiles[0], src, (uint32_t)len * sizeof(FilterEvent), &bars[0]);
     }
     for (int t = 0; t < numTiles; ++t) {
         const int buf = t & 1;
         if (tid == 0 && t + 1 < numTiles) {
             // buffer buf^1 was released by the __syncthreads at the end of tile t-1
             int len = min(kPairTile, count - (t + 1) * kPairTile);
-            mbarExpectTx(&bars[buf ^ 1], (uint32_t)len * sizeof(PreparedEvent));
+            mbarExpectTx(&bars[buf ^ 1], (uint32_t)len * sizeof(FilterEvent));
             tmaLoad1D(tiles[buf ^ 1], src + (size_t)(t + 1) * kPairTile,
-                      (uint32_t)len * sizeof(PreparedEvent), &bars[buf ^ 1]);
+                      (uint32_t)len * sizeof(FilterEvent), &bars[buf ^ 1]);
         }
         mbarWait(&bars[buf], (uint32_t)(t >> 1) & 1u);
         const int len = min(kPairTile, count - t * kPairTile);
-        const PreparedEvent* tile = tiles[buf];
-        int e = 0;
-        for (; e + 1 < len; e += 2) {
-            PreparedEvent a = tile[e], b = tile[e + 1];
-            pairOne<TAGGED>(a, cp.skewc, cp.width, cp.scale, sepScale, mine);
-            pairOne<TAGGED>(b, cp.skewc, cp.width, cp.scale, sepScale, mine);
+        const FilterEvent* tile = tiles[buf];
+        for (int base = 0; base < len; base += 32) {
+            const int nb = min(32, len - base);
+            constexpr int cutRow = TAGGED ? kFilterCutRow : 2 * kFilterCutRow;
+            const PreparedEvent* exact = L.events + classFirst + (size_t)t * kPairTile + base;
+            if (nb == 32) {
+                // four events at a time, stage by stage, so that the four
+                // dependency chains (LDS -> MUFU -> MUFU -> LDS/STS) overlap
+#pragma unroll 1
+                for (int e = 0; e < 32; e += kPairIlp) {
+                    bool sure[kPairIlp];
+                    int row[kPairIlp];
+                    filterDecideMany<TAGGED>(tile + base + e, fc.scl2, fc.w2, fc.c2, fc.m0, ss, sure, row);
+                    bool allSure = true;
+#pragma unroll
+                    for (int g = 0; g < kPairIlp; ++g) {
+                        if (sure[g] & (row[g] < cutRow)) mine[row[g] * kPairThreads] += 1;
+                        allSure = allSure & sure[g];
+                    }
+                    if (!allSure) {          // rare: FP64 for the undecided pairs
+#pragma unroll
+                        for (int g = 0; g < kPairIlp; ++g) {
+                            if (!sure[g]) unsureTotal += exactCount(exact + e + g, L.chains + point, cls, mine, live);
+                        }
+                    }
+                }
+            } else {
+                for (int e = 0; e < nb; ++e) {
+                    bool sure;
+                    int row;
+                    filterDecide<TAGGED>(tile[base + e], fc.scl2, fc.w2, fc.c2, fc.m0, ss, sure, row);
+                    if (sure & (row < cutRow)) mine[row * kPairThreads] += 1;
+                    if (!sure) unsureTotal += exactCount(exact + e, L.chains + point, cls, mine, live);
+                }
+            }
         }
-        if (e < len) pairOne<TAGGED>(tile[e], cp.skewc, cp.width, cp.scale, sepScale, mine);
         __syncthreads();
     }
     if (live) {
@@ -326,6 +482,7 @@ __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t 
             uint32_t v = counters[r * kPairThreads + tid];
             if (v) atomicAdd(&L.counts[(size_t)(slotBase + r) * L.pointStride + point], v);
         }
+        if (L.stats && unsureTotal) atomicAdd(&L.stats[0], (unsigned long long)unsureTotal);
     }
 }
 
@@ -335,9 +492,9 @@ __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t 
 __global__ void __launch_bounds__(kPairThreads, 2)
 kFakePairs(const __grid_constant__ PairLaunch L) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
-    PreparedEvent(*tiles)[kPairTile] = reinterpret_cast<PreparedEvent(*)[kPairTile]>(smemRaw);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smemRaw + 2 * kPairTile * sizeof(PreparedEvent));
-    uint32_t* counters = reinterpret_cast<uint32_t*>(smemRaw + 2 * kPairTile * sizeof(PreparedEvent) + 64);
+    FilterEvent(*tiles)[kPairTile] = reinterpret_cast<FilterEvent(*)[kPairTile]>(smemRaw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smemRaw + 2 * kPairTile * sizeof(FilterEvent));
+    uint32_t* counters = reinterpret_cast<uint32_t*>(smemRaw + 2 * kPairTile * sizeof(FilterEvent) + 64);
 
     const int pointTiles = (L.numPoints + kPairThreads - 1) / kPairThreads;
     const int chunk = blockIdx.x / pointTiles;
@@ -358,7 +515,38 @@ kFakePairs(const __grid_constant__ PairLaunch L) {
 }
 
 constexpr size_t kPairSmemBytes =
-    2 * kPairTile * sizeof(PreparedEvent) + 64 + (size_t)kPairCounterRows * kPairThreads * sizeof(uint32_t);
+    2 * kPairTile * sizeof(FilterEvent) + 64 + (size_t)kPairCounterRows * kPairThreads * sizeof(uint32_t);
+
+// Test kernel: run the filter AND the FP64 arithmetic on every pair and count
+// the pairs where a filter decision differs from the FP64 decision (must be
+// zero).  stats[0] = pairs, [1] = unsure, [2] = mismatches.
+__global__ void kFakeVerifyFilter(const PairLaunch L, unsigned long long* stats) {
+    const int point = blockIdx.y * blockDim.x + threadIdx.x;
+    if (point >= L.numPoints) return;
+    const FakeChainParams cp = L.chains[point];
+    const FilterChain fc = L.filterChains[point];
+    unsigned long long pairs = 0, unsure = 0, bad = 0;
+    for (int cls = 0; cls < kFakeClasses; ++cls) {
+        const float ss = (cls >> 1) ? fc.ss[1] : fc.ss[0];
+        for (int64_t i = blockIdx.x; i < L.classCount[cls]; i += gridDim.x) {
+            const int64_t idx = L.classBase[cls] + i;
+            const FilterEvent fe = L.filterEvents[idx];
+            bool sure;
+            int row;
+            if (cls & 1) filterDecide<true>(fe, fc.scl2, fc.w2, fc.c2, fc.m0, ss, sure, row);
+            else filterDecide<false>(fe, fc.scl2, fc.w2, fc.c2, fc.m0, ss, sure, row);
+            const int cutRow = (cls & 1) ? kFilterCutRow : 2 * kFilterCutRow;
+            const int f = (row < cutRow) ? row : -1;
+            const int x = exactDecide(L.events[idx], cp, cls);
+            ++pairs;
+            if (!sure) ++unsure;
+            else if (f != x) ++bad;
+        }
+    }
+    atomicAdd(&stats[0], pairs);
+    atomicAdd(&stats[1], unsure);
+    atomicAdd(&stats[2], bad);
+}
 
 // Straight transcription of the per-event formula for the events the fast
 // path cannot take (data-typed, negative separation, non-finite fields):

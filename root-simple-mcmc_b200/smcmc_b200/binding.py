@@ -104,6 +104,7 @@ def load_library():
         "smcmc_fake_set_data": (ci, [vp, vp, cd]),
         "smcmc_fake_histograms": (ci, [vp, vp, ci, vp]),
         "smcmc_fake_counts": (ci, [vp, vp, ci, vp]),
+        "smcmc_fake_filter_check": (ci, [vp, vp, ci, vp]),
         "smcmc_dummy_set_error": (ci, [vp, vp, ci]),
         "smcmc_eval": (ci, [vp, vp, ci, vp]),
         "smcmc_start": (ci, [vp, vp, vp]),
@@ -129,7 +130,7 @@ EXPORTED_SYMBOLS = [
     "smcmc_prop_set_uniform", "smcmc_prop_set_correlation",
     "smcmc_prop_reset_correlations", "smcmc_prop_update", "smcmc_prop_reset",
     "smcmc_fake_set_events", "smcmc_fake_set_data", "smcmc_fake_histograms",
-    "smcmc_fake_counts",
+    "smcmc_fake_counts", "smcmc_fake_filter_check",
     "smcmc_dummy_set_error", "smcmc_eval", "smcmc_start", "smcmc_step",
     "smcmc_step_trace", "smcmc_get", "smcmc_launch_count",
     "smcmc_pair_kernel_stats", "smcmc_enable_kernel_timing",
@@ -232,6 +233,13 @@ class Engine:
         out = np.zeros((x.shape[0], 450), np.uint32)
         self._check(self.lib.smcmc_fake_counts(self.h, _ptr(x), x.shape[0], _ptr(out)))
         return out
+
+    def fake_filter_check(self, x):
+        """(pairs, pairs left to FP64, filter decisions that differ from FP64)."""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, self.dim)
+        out = np.zeros(3, np.uint64)
+        self._check(self.lib.smcmc_fake_filter_check(self.h, _ptr(x), x.shape[0], _ptr(out)))
+        return int(out[0]), int(out[1]), int(out[2])
 
     def set_error_matrix(self, e):
         e = np.ascontiguousarray(e, dtype=np.float64)
