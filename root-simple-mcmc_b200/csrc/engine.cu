@@ -47,6 +47,7 @@ struct smcmc_engine {
     cudaStream_t stream = nullptr;
     std::string lastError;
     int64_t launches = 0;
+    int smCount = 148;
     uint32_t stepIndex = 0;
     bool started = false;
 
@@ -203,12 +204,26 @@ struct smcmc_engine {
         PairLaunch L;
         L.events = fakeEvents.get();
         L.filterEvents = fakeFilterEvents.get();
+        // Work items = (chunk of one class) x (tile of 256 points).  Pick the
+        // chunk length so that the grid is close to a whole number of waves of
+        // (SMs x resident CTAs): equal-cost items, no ragged last wave.
+        const int pointTiles = ceilDiv(m, kPairThreads);
+        int64_t total = 0;
+        for (int c = 0; c < kFakeClasses; ++c) total += fakeClassCount[c];
+        const int64_t slots = (int64_t)smCount * kPairCtasPerSm;
+        int64_t waves = (total * pointTiles + slots * kPairChunk - 1) / (slots * kPairChunk);
+        if (waves < 1) waves = 1;
+        int64_t chunkEvents = (total * pointTiles + slots * waves - 1) / (slots * waves);
+        chunkEvents = (chunkEvents + kPairTile - 1) / kPairTile * kPairTile;
+        if (chunkEvents > kPairChunk) chunkEvents = kPairChunk;
+        if (chunkEvents < kPairTile) chunkEvents = kPairTile;
+        L.chunkEvents = (int)chunkEvents;
         int chunks = 0;
         for (int c = 0; c < kFakeClasses; ++c) {
             L.classBase[c] = fakeClassBase[c];
             L.classCount[c] = fakeClassCount[c];
             L.chunkBase[c] = chunks;
-            chunks += (int)((fakeClassCount[c] + kPairChunk - 1) / kPairChunk);
+            chunks += (int)((fakeClassCount[c] + chunkEvents - 1) / chunkEvents);
         }
         L.chunkBase[kFakeClasses] = chunks;
         L.chains = fakeChains.get();
@@ -361,6 +376,7 @@ int smcmc_create(const smcmc_config* cfg, smcmc_engine** out) {
 
         e = new smcmc_engine;
         e->cfg = *cfg;
+        e->smCount = prop.multiProcessorCount;
         const size_t E = cfg->chains, n = cfg->dim;
         e->type.assign(n, 0);
         e->param1.assign(n, 0.0);

@@ -69,8 +69,21 @@ constexpr int kIrregularClass = 5;   // events the fast path cannot take
 
 constexpr int kPairThreads = 256;    // chains per CTA
 constexpr int kPairTile = 128;       // events per shared-memory tile
-constexpr int kPairChunk = 8192;     // events per CTA work item
+constexpr int kPairChunk = 8192;     // most events per CTA work item
 constexpr int kPairCounterRows = 100;
+// Private shared-memory counters: 16 bits are enough for one chunk
+// (kPairChunk < 65536) and let four CTAs share an SM instead of two.
+#ifndef SMCMC_PAIR_COUNTER_BITS
+#define SMCMC_PAIR_COUNTER_BITS 16
+#endif
+#if SMCMC_PAIR_COUNTER_BITS == 16
+typedef uint16_t PairCounter;
+constexpr int kPairCtasPerSm = 4;
+#else
+typedef uint32_t PairCounter;
+constexpr int kPairCtasPerSm = 2;
+#endif
+static_assert(kPairChunk < (1 << SMCMC_PAIR_COUNTER_BITS), "a chunk must not overflow a counter");
 
 // Pre-images of the 50 bin edges under the host's exp, and of the cut at 500:
 //   bin (1-based) of exp(l) is 1 + #{k in 1..49 : l >= gEdges[k]},
@@ -386,6 +399,7 @@ struct PairLaunch {
     int64_t classBase[kFakeClasses]; // first event of each class
     int64_t classCount[kFakeClasses];
     int chunkBase[kFakeClasses + 1]; // prefix sum of chunks per class
+    int chunkEvents;                 // events per work item (multiple of kPairTile, <= kPairChunk)
     const FakeChainParams* chains;
     const FilterChain* filterChains;
     int numPoints;                   // chains (parameter points) to evaluate
@@ -396,7 +410,7 @@ struct PairLaunch {
 
 // FP64 evaluation of one undecided pair (out of line: it is the rare path).
 __device__ __noinline__ unsigned int exactCount(const PreparedEvent* ev, const FakeChainParams* cp,
-                                                int cls, uint32_t* mine, bool live) {
+                                                int cls, PairCounter* mine, bool live) {
     if (!live) return 0;
     const int row = exactDecide(*ev, *cp, cls);
     if (row >= 0) mine[row * kPairThreads] += 1;
@@ -406,7 +420,7 @@ __device__ __noinline__ unsigned int exactCount(const PreparedEvent* ev, const F
 template <bool TAGGED>
 __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t first, int count,
                                           int pointBase, FilterEvent (*tiles)[kPairTile],
-                                          uint64_t* bars, uint32_t* counters) {
+                                          uint64_t* bars, PairCounter* counters) {
     const int tid = threadIdx.x;
     const int point = pointBase + tid;
     const bool live = point < L.numPoints;
@@ -416,7 +430,7 @@ __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t 
     const float ss = (cls >> 1) ? fc.ss[1] : fc.ss[0];
     constexpr int rows = TAGGED ? 50 : 100;
     for (int r = 0; r < rows; ++r) counters[r * kPairThreads + tid] = 0;
-    uint32_t* mine = counters + tid;
+    PairCounter* mine = counters + tid;
     unsigned int unsureTotal = 0;
 
     const int64_t classFirst = L.classBase[cls] + first;
@@ -489,20 +503,20 @@ __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t 
 // grid.x = (#chunks over all classes) * (#point tiles); consecutive CTAs take
 // the point tiles of the same chunk, so a chunk is fetched from HBM once and
 // re-read from L2 by the other tiles.
-__global__ void __launch_bounds__(kPairThreads, 2)
+__global__ void __launch_bounds__(kPairThreads, kPairCtasPerSm)
 kFakePairs(const __grid_constant__ PairLaunch L) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     FilterEvent(*tiles)[kPairTile] = reinterpret_cast<FilterEvent(*)[kPairTile]>(smemRaw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smemRaw + 2 * kPairTile * sizeof(FilterEvent));
-    uint32_t* counters = reinterpret_cast<uint32_t*>(smemRaw + 2 * kPairTile * sizeof(FilterEvent) + 64);
+    PairCounter* counters = reinterpret_cast<PairCounter*>(smemRaw + 2 * kPairTile * sizeof(FilterEvent) + 64);
 
     const int pointTiles = (L.numPoints + kPairThreads - 1) / kPairThreads;
     const int chunk = blockIdx.x / pointTiles;
     const int pointBase = (blockIdx.x - chunk * pointTiles) * kPairThreads;
     int cls = 0;
     while (cls + 1 < kFakeClasses && chunk >= L.chunkBase[cls + 1]) ++cls;
-    const int64_t first = (int64_t)(chunk - L.chunkBase[cls]) * kPairChunk;
-    const int count = (int)min((int64_t)kPairChunk, L.classCount[cls] - first);
+    const int64_t first = (int64_t)(chunk - L.chunkBase[cls]) * L.chunkEvents;
+    const int count = (int)min((int64_t)L.chunkEvents, L.classCount[cls] - first);
 
     if (threadIdx.x == 0) {
         mbarInit(&bars[0], 1);
@@ -515,7 +529,7 @@ kFakePairs(const __grid_constant__ PairLaunch L) {
 }
 
 constexpr size_t kPairSmemBytes =
-    2 * kPairTile * sizeof(FilterEvent) + 64 + (size_t)kPairCounterRows * kPairThreads * sizeof(uint32_t);
+    2 * kPairTile * sizeof(FilterEvent) + 64 + (size_t)kPairCounterRows * kPairThreads * sizeof(PairCounter);
 
 // Test kernel: run the filter AND the FP64 arithmetic on every pair and count
 // the pairs where a filter decision differs from the FP64 decision (must be
