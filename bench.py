@@ -306,39 +306,66 @@ def run_b200(args):
         return
 
     # ---- roofline of the dominant kernel ------------------------------------------
+    # kFakePairs is neither HBM- nor tensor-bound: every event is re-used by all
+    # chains (hundreds of pair evaluations per byte) and the per-pair work is a
+    # short FP32/integer/SFU sequence, so the binding resource is the SM's
+    # instruction issue rate (1 warp-instruction / clock / SM sub-partition).
+    # DESIGN.md section 4 derives the algorithmic instruction count per pair.
     pairs_per_launch = float(chains) * float(len(events))
+    pair_warps = pairs_per_launch / 32.0
     pair_s = (pair_ms / max(pair_n, 1)) * 1e-3
-    fp64_peak = binding.measure_fp64_peak(local)
-    peaks = {}
+    peaks, prof = {}, {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "pair_kernel_profile.json")))
+    except Exception:
+        pass
+    props = torch.cuda.get_device_properties(local)
+    sm_hz = (clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)) * 1e6
+    issue_peak = props.multi_processor_count * 4 * sm_hz / 1e9                  # G warp-inst/s
+    # tagged events need 20 instructions per pair, untagged ones 24
+    tagged = float((events["MuDk"] > 0).mean())
+    alg_inst = 20.0 * tagged + 24.0 * (1.0 - tagged)
+    achieved = alg_inst * pair_warps / pair_s / 1e9
+    executed = None
+    if prof.get("warp_instructions_per_pair_warp"):
+        executed = prof["warp_instructions_per_pair_warp"] * pair_warps / pair_s / 1e9
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     alg_bytes = len(events) * BYTES_PER_EVENT + chains * BYTES_PER_CHAIN
     traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "pair_kernel_traffic.json")))["dram_bytes_per_launch"]
-    except Exception:
-        pass
-    achieved_tf = FLOP_PER_PAIR * pairs_per_launch / pair_s / 1e12
+    if prof.get("dram_bytes_per_launch") and prof.get("workload", {}).get("chains") == chains \
+            and prof.get("workload", {}).get("events") == len(events):
+        traffic = prof["dram_bytes_per_launch"]
+    fp64_peak = binding.measure_fp64_peak(local)
     roofline = {
-        "kernel": "kFakePairs (event x chain pair kernel)",
-        "bound": "fp64",
-        "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
-        "peak_source": "measured in this run: DFMA chain micro-benchmark (smcmc_measure_fp64_peak); "
-                       "MEASURED_PEAKS.json has no FP64 entry",
-        "algorithmic": "120 flop per (chain,event) pair (SURVEY.md 8d) x %.4g pairs per launch" % pairs_per_launch,
+        "kernel": "smcmc::kFakePairs (event x chain pair kernel)",
+        "bound": "issue",
+        "bound_note": "compute-bound on instruction issue, not hbm/tensor: %.0f pair evaluations per HBM byte"
+                      % (pairs_per_launch / alg_bytes),
+        "achieved": achieved, "peak": issue_peak, "unit": "G warp-inst/s", "frac": achieved / issue_peak,
+        "algorithmic": "%.1f warp-instructions per 32 (chain,event) pairs (20 tagged / 24 untagged events, "
+                       "DESIGN.md section 4) x %.4g pairs per launch" % (alg_inst, pairs_per_launch),
+        "peak_source": "%d SMs x 4 sub-partitions x %.0f MHz (median SM clock sampled during the timed region) "
+                       "x 1 warp-instruction/clock" % (props.multi_processor_count, sm_hz / 1e6),
+        "issue_utilisation_executed": (executed / issue_peak) if executed else None,
+        "executed_source": "profiles/pair_kernel_profile.json (ncu smsp__inst_executed.sum per launch)",
         "launch_ms": pair_ms / max(pair_n, 1), "launches_timed": int(pair_n),
         "kernel_share_of_step": (pair_ms / max(pair_n, 1)) / (ms / args.steps),
         "pairs_per_s": pairs_per_launch / pair_s,
         "traffic": traffic,
         "hbm": {"achieved": alg_bytes / pair_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / pair_s / 1e9 / hbm_peak, "peak_source": hbm_src,
-                "algorithmic_bytes": alg_bytes,
-                "note": "every event is re-used by all %d chains: %.0f pair evaluations per byte, "
-                        "the kernel is FP64/issue bound, not HBM bound" % (chains, pairs_per_launch / alg_bytes)},
+                "algorithmic_bytes": alg_bytes},
+        "fp64_of_unfiltered_algorithm": {
+            "note": "the FP64 work the same counts cost WITHOUT the FP32 interval filter: 25 FP64 instructions "
+                    "(50 flop) per pair, first version of this kernel; above 1.0 = faster than that roofline allows",
+            "achieved": 50.0 * pairs_per_launch / pair_s / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": 50.0 * pairs_per_launch / pair_s / 1e12 / fp64_peak,
+            "peak_source": "measured in this run (DFMA chain micro-benchmark)"},
     }
 
     cpu_value, cpu_desc = (None, None)

@@ -215,8 +215,16 @@ struct smcmc_engine {
         if (waves < 1) waves = 1;
         int64_t chunkEvents = (total * pointTiles + slots * waves - 1) / (slots * waves);
         chunkEvents = (chunkEvents + kPairTile - 1) / kPairTile * kPairTile;
-        if (chunkEvents > kPairChunk) chunkEvents = kPairChunk;
         if (chunkEvents < kPairTile) chunkEvents = kPairTile;
+        // the per-class round-up can spill a few items into one more wave:
+        // lengthen the chunk until the grid fits in `waves` waves
+        auto items = [&](int64_t ce) {
+            int64_t n = 0;
+            for (int c = 0; c < kFakeClasses; ++c) n += (fakeClassCount[c] + ce - 1) / ce;
+            return n * pointTiles;
+        };
+        while (chunkEvents < kPairChunk && items(chunkEvents) > slots * waves) chunkEvents += kPairTile;
+        if (chunkEvents > kPairChunk) chunkEvents = kPairChunk;
         L.chunkEvents = (int)chunkEvents;
         int chunks = 0;
         for (int c = 0; c < kFakeClasses; ++c) {

@@ -250,13 +250,17 @@ struct __align__(16) FilterEvent {
     float sep;
 };
 struct __align__(16) FilterChain {
-    float scl2;    // skewc * log2(e)
-    float w2;      // width * log2(e)
-    float c2;      // scale * log2(e) - log2(10)
-    float m0;      // constant part of the relative error bound of q
-    float ss[2];   // separation scale: signal, background
-    float pad_[2];
+    float scl2;      // skewc * log2(e)
+    float w2;        // width * log2(e)
+    float c2;        // scale * log2(e) - log2(10)
+    float m0;        // relative error bound of q: constant part ...
+    float slopeT;    // ... plus slopeT * |d*skew|
+    float thr[2];    // 100 / separation scale: signal, background
+    float thrEps[2]; // error bound of the comparison  sep <> thr
+    float pad_[3];
 };
+static_assert(sizeof(FilterChain) == 48, "FilterChain is 48 bytes");
+
 __device__ __forceinline__ void storeFilterEvent(FilterEvent* dst, int64_t idx, const PreparedEvent& p) {
     FilterEvent f;
     f.ls = __double2float_rn(p.logSigma);
@@ -265,24 +269,26 @@ __device__ __forceinline__ void storeFilterEvent(FilterEvent* dst, int64_t idx, 
     f.sep = __double2float_rn(p.sep);
     dst[idx] = f;
 }
-constexpr float kFilterU = 5.9604645e-8f;
-constexpr float kFilterSlope = 2.0f * kFilterU * 30.5f;
-
 
 // exactOnly (SMCMC_FAKE_EXACT=1): an infinite error bound makes every pair
 // "unsure", i.e. the whole evaluation runs through the FP64 arithmetic.
 __device__ __forceinline__ void storeFilterChain(FilterChain* dst, int c, const FakeChainParams& cp, int exactOnly) {
     const double log2e = 1.4426950408889634, log2ten = 3.3219280948873623;
+    const double u = 5.9604645e-8;
     FilterChain f;
     f.scl2 = __double2float_rn(cp.skewc * log2e);
     f.w2 = __double2float_rn(cp.width * log2e);
     const double c2 = cp.scale * log2e - log2ten;
     f.c2 = __double2float_rn(c2);
-    f.m0 = __double2float_ru(2.0 * 5.9604645e-8 * (48.4 + 2.78 * fabs(c2)));
+    f.m0 = __double2float_ru(2.0 * u * (48.4 + 2.78 * fabs(c2)));
+    f.slopeT = __double2float_ru(2.0 * u * 30.5 * fabs(cp.width * log2e));
     if (exactOnly) f.m0 = __int_as_float(0x7f800000);
-    f.ss[0] = __double2float_rn(cp.sepScale[0]);
-    f.ss[1] = __double2float_rn(cp.sepScale[1]);
-    f.pad_[0] = f.pad_[1] = 0.f;
+    for (int k = 0; k < 2; ++k) {
+        const double thr = 100.0 / cp.sepScale[k];
+        f.thr[k] = __double2float_rn(thr);
+        f.thrEps[k] = __double2float_ru(8.0 * u * fabs(thr));
+    }
+    f.pad_[0] = f.pad_[1] = f.pad_[2] = 0.f;
     dst[c] = f;
 }
 
@@ -292,65 +298,65 @@ __device__ __forceinline__ float fastEx2(float x) {
     return y;
 }
 
-// One decision.  `sure` is false when the pair must go to FP64.  A sure pair
-// with row >= kFilterCutRow is cut (mass >= 500); q beyond the float grid of
-// the floor trick only occurs far above 50, where any row value means "cut".
+__device__ __forceinline__ uint32_t smemAddr(const void* p);
+
+// One decision: `sure` is false when the pair must go to FP64; otherwise the
+// pair is counted when `inRange` (mass < 500), in row floor(q) = bits -
+// 0x4b400000 (+50 for the Separated histogram when `far`).  q = mass/10 is
+// accepted when q(1-m) and q(1+m) have the same integer part (m = relative
+// error bound): both are pushed onto the integer grid by a round-toward-zero
+// add of 1.5*2^23 and compared as bit patterns.
+constexpr unsigned kFloorMagicBits = 0x4b400000u;
 constexpr int kFilterCutRow = 50;
+constexpr int kPairIlp = 4;
+
+struct FilterResult {
+    bool sure;       // the FP32 decision is provably the FP64 decision
+    bool inRange;    // bin 0..49
+    bool far;        // separation >= 100 (untagged classes only)
+    unsigned bits;   // 0x4b400000 + floor(q)
+};
+
 template <bool TAGGED>
-__device__ __forceinline__ void filterDecide(const FilterEvent& ev, float scl2, float w2, float c2,
-                                             float m0, float ss, bool& sure, int& row) {
-    const float x2 = ev.ls * scl2;
-    const float tw = (ev.d * fastEx2(x2)) * w2;
-    const float q = fastEx2((tw + ev.nl2) + c2);
-    const float mq = q * fmaf(fabsf(tw), kFilterSlope, m0);
-    const float shifted = __fadd_rz(q, 12582912.0f);          // 1.5*2^23 + floor(q)
-    const float frac = q - (shifted - 12582912.0f);
-    const int k = __float_as_int(shifted) - 0x4b400000;       // floor(q)
-    // away from both neighbouring edges by more than the error bound
-    bool ok = (fabsf(x2) <= 16.0f) & (fabsf(frac - 0.5f) < 0.5f - mq);
-    row = k;
+__device__ __forceinline__ FilterResult filterCore(float ls, float d, float nl2, float sep,
+                                                   const FilterChain& fc, float thr, float thrEps) {
+    const float x2 = ls * fc.scl2;
+    const float t = d * fastEx2(x2);
+    const float q = fastEx2(fmaf(t, fc.w2, nl2) + fc.c2);
+    const float m = fmaf(fabsf(t), fc.slopeT, fc.m0);
+    const unsigned lo = __float_as_uint(__fadd_rz(fmaf(-q, m, q), 12582912.0f));
+    const unsigned hi = __float_as_uint(__fadd_rz(fmaf(q, m, q), 12582912.0f));
+    FilterResult r;
+    // hi below 2^24 also rejects NaN and infinities (their patterns are larger)
+    r.sure = (lo == hi) & (hi < 0x4b800000u) & (fabsf(x2) <= 16.0f);
+    r.far = false;
     if (!TAGGED) {
-        const float sp = ev.sep * ss;
-        ok = ok & (fabsf(sp - 100.0f) > 1.0e-4f);
-        row = (sp > 100.0f) ? k + 50 : k;
-        if (k >= kFilterCutRow) row = kFilterCutRow + 50;     // stays "cut"
+        const float ds = sep - thr;               // sep*scale <> 100  <=>  sep <> 100/scale
+        r.sure = r.sure & (fabsf(ds) > thrEps);
+        r.far = ds > 0.0f;
     }
-    sure = ok;
+    r.inRange = lo < kFloorMagicBits + kFilterCutRow;
+    r.bits = lo;
+    return r;
 }
 
-// The same decision for kPairIlp consecutive events, written stage by stage
-// (identical arithmetic to filterDecide).
-constexpr int kPairIlp = 4;
-template <bool TAGGED>
-__device__ __forceinline__ void filterDecideMany(const FilterEvent* ev, float scl2, float w2, float c2,
-                                                 float m0, float ss, bool (&sure)[kPairIlp],
-                                                 int (&row)[kPairIlp]) {
-    FilterEvent e[kPairIlp];
-    float x2[kPairIlp], tw[kPairIlp], q[kPairIlp];
-#pragma unroll
-    for (int g = 0; g < kPairIlp; ++g) e[g] = ev[g];
-#pragma unroll
-    for (int g = 0; g < kPairIlp; ++g) x2[g] = e[g].ls * scl2;
-#pragma unroll
-    for (int g = 0; g < kPairIlp; ++g) tw[g] = (e[g].d * fastEx2(x2[g])) * w2;
-#pragma unroll
-    for (int g = 0; g < kPairIlp; ++g) q[g] = fastEx2((tw[g] + e[g].nl2) + c2);
-#pragma unroll
-    for (int g = 0; g < kPairIlp; ++g) {
-        const float mq = q[g] * fmaf(fabsf(tw[g]), kFilterSlope, m0);
-        const float shifted = __fadd_rz(q[g], 12582912.0f);
-        const float frac = q[g] - (shifted - 12582912.0f);
-        const int k = __float_as_int(shifted) - 0x4b400000;
-        bool ok = (fabsf(x2[g]) <= 16.0f) & (fabsf(frac - 0.5f) < 0.5f - mq);
-        int r = k;
-        if (!TAGGED) {
-            const float sp = e[g].sep * ss;
-            ok = ok & (fabsf(sp - 100.0f) > 1.0e-4f);
-            r = (sp > 100.0f) ? k + 50 : k;
-            if (k >= kFilterCutRow) r = kFilterCutRow + 50;
-        }
-        sure[g] = ok;
-        row[g] = r;
+// Private counter update through a shared-memory byte address:
+// counter(row) lives at (address of row 0) + row * kPairRowBytes.
+constexpr unsigned kPairRowBytes = kPairThreads * sizeof(PairCounter);
+__device__ __forceinline__ void bumpCounter(unsigned addr) {
+#if SMCMC_PAIR_COUNTER_BITS == 16
+    asm volatile("{\n.reg .u16 c;\nld.shared.u16 c, [%0];\nadd.u16 c, c, 1;\nst.shared.u16 [%0], c;\n}" ::"r"(addr) : "memory");
+#else
+    asm volatile("{\n.reg .u32 c;\nld.shared.u32 c, [%0];\nadd.u32 c, c, 1;\nst.shared.u32 [%0], c;\n}" ::"r"(addr) : "memory");
+#endif
+}
+// mineAdj = (shared address of this thread's row-0 counter) - 0x4b400000*rowBytes,
+// so that bits*rowBytes + mineAdj addresses counter(floor(q)).
+__device__ __forceinline__ void countResult(const FilterResult& r, unsigned mineAdj) {
+    if (r.sure & r.inRange) {
+        unsigned addr = r.bits * kPairRowBytes + mineAdj;
+        if (r.far) addr += kFilterCutRow * kPairRowBytes;
+        bumpCounter(addr);
     }
 }
 
@@ -426,11 +432,16 @@ __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t 
     const bool live = point < L.numPoints;
     FilterChain fc;
     if (live) fc = L.filterChains[point];
-    else { fc.scl2 = 0.f; fc.w2 = 1.f; fc.c2 = 0.f; fc.m0 = 1e-4f; fc.ss[0] = fc.ss[1] = 1.f; }
-    const float ss = (cls >> 1) ? fc.ss[1] : fc.ss[0];
+    else {
+        fc.scl2 = 0.f; fc.w2 = 1.f; fc.c2 = 0.f; fc.m0 = 1e-4f; fc.slopeT = 0.f;
+        fc.thr[0] = fc.thr[1] = 100.f; fc.thrEps[0] = fc.thrEps[1] = 1e-3f;
+    }
+    const float thr = (cls >> 1) ? fc.thr[1] : fc.thr[0];
+    const float thrEps = (cls >> 1) ? fc.thrEps[1] : fc.thrEps[0];
     constexpr int rows = TAGGED ? 50 : 100;
     for (int r = 0; r < rows; ++r) counters[r * kPairThreads + tid] = 0;
     PairCounter* mine = counters + tid;
+    const unsigned mineAdj = smemAddr(mine) - kFloorMagicBits * kPairRowBytes;
     unsigned int unsureTotal = 0;
 
     const int64_t classFirst = L.classBase[cls] + first;
@@ -455,36 +466,38 @@ __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t 
         const FilterEvent* tile = tiles[buf];
         for (int base = 0; base < len; base += 32) {
             const int nb = min(32, len - base);
-            constexpr int cutRow = TAGGED ? kFilterCutRow : 2 * kFilterCutRow;
             const PreparedEvent* exact = L.events + classFirst + (size_t)t * kPairTile + base;
             if (nb == 32) {
                 // four events at a time, stage by stage, so that the four
                 // dependency chains (LDS -> MUFU -> MUFU -> LDS/STS) overlap
 #pragma unroll 1
                 for (int e = 0; e < 32; e += kPairIlp) {
-                    bool sure[kPairIlp];
-                    int row[kPairIlp];
-                    filterDecideMany<TAGGED>(tile + base + e, fc.scl2, fc.w2, fc.c2, fc.m0, ss, sure, row);
+                    FilterEvent ev[kPairIlp];
+                    FilterResult r[kPairIlp];
+#pragma unroll
+                    for (int g = 0; g < kPairIlp; ++g) ev[g] = tile[base + e + g];
+#pragma unroll
+                    for (int g = 0; g < kPairIlp; ++g)
+                        r[g] = filterCore<TAGGED>(ev[g].ls, ev[g].d, ev[g].nl2, ev[g].sep, fc, thr, thrEps);
                     bool allSure = true;
 #pragma unroll
                     for (int g = 0; g < kPairIlp; ++g) {
-                        if (sure[g] & (row[g] < cutRow)) mine[row[g] * kPairThreads] += 1;
-                        allSure = allSure & sure[g];
+                        countResult(r[g], mineAdj);
+                        allSure = allSure & r[g].sure;
                     }
                     if (!allSure) {          // rare: FP64 for the undecided pairs
 #pragma unroll
                         for (int g = 0; g < kPairIlp; ++g) {
-                            if (!sure[g]) unsureTotal += exactCount(exact + e + g, L.chains + point, cls, mine, live);
+                            if (!r[g].sure) unsureTotal += exactCount(exact + e + g, L.chains + point, cls, mine, live);
                         }
                     }
                 }
             } else {
                 for (int e = 0; e < nb; ++e) {
-                    bool sure;
-                    int row;
-                    filterDecide<TAGGED>(tile[base + e], fc.scl2, fc.w2, fc.c2, fc.m0, ss, sure, row);
-                    if (sure & (row < cutRow)) mine[row * kPairThreads] += 1;
-                    if (!sure) unsureTotal += exactCount(exact + e, L.chains + point, cls, mine, live);
+                    const FilterEvent ev = tile[base + e];
+                    const FilterResult r = filterCore<TAGGED>(ev.ls, ev.d, ev.nl2, ev.sep, fc, thr, thrEps);
+                    countResult(r, mineAdj);
+                    if (!r.sure) unsureTotal += exactCount(exact + e, L.chains + point, cls, mine, live);
                 }
             }
         }
@@ -541,16 +554,15 @@ __global__ void kFakeVerifyFilter(const PairLaunch L, unsigned long long* stats)
     const FilterChain fc = L.filterChains[point];
     unsigned long long pairs = 0, unsure = 0, bad = 0;
     for (int cls = 0; cls < kFakeClasses; ++cls) {
-        const float ss = (cls >> 1) ? fc.ss[1] : fc.ss[0];
+        const float thr = (cls >> 1) ? fc.thr[1] : fc.thr[0];
+        const float thrEps = (cls >> 1) ? fc.thrEps[1] : fc.thrEps[0];
         for (int64_t i = blockIdx.x; i < L.classCount[cls]; i += gridDim.x) {
             const int64_t idx = L.classBase[cls] + i;
             const FilterEvent fe = L.filterEvents[idx];
-            bool sure;
-            int row;
-            if (cls & 1) filterDecide<true>(fe, fc.scl2, fc.w2, fc.c2, fc.m0, ss, sure, row);
-            else filterDecide<false>(fe, fc.scl2, fc.w2, fc.c2, fc.m0, ss, sure, row);
-            const int cutRow = (cls & 1) ? kFilterCutRow : 2 * kFilterCutRow;
-            const int f = (row < cutRow) ? row : -1;
+            const FilterResult r = (cls & 1) ? filterCore<true>(fe.ls, fe.d, fe.nl2, fe.sep, fc, thr, thrEps)
+                                             : filterCore<false>(fe.ls, fe.d, fe.nl2, fe.sep, fc, thr, thrEps);
+            const bool sure = r.sure;
+            const int f = r.inRange ? (int)(r.bits - kFloorMagicBits) + (r.far ? kFilterCutRow : 0) : -1;
             const int x = exactDecide(L.events[idx], cp, cls);
             ++pairs;
             if (!sure) ++unsure;
