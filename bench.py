@@ -224,8 +224,8 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    chains = args.chains
-    offset = rank * chains
+    from smcmc_b200 import shard
+    offset, chains = shard.chain_shard(world * args.chains, world, rank)     # weak scaling: args.chains per GPU
     events, data = workload_inputs(args.events)
     x0 = start_points(chains, offset)
 

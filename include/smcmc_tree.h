@@ -1,0 +1,62 @@
+// smcmc_tree.h -- the TTree the sampler writes to.
+//
+// With ROOT available (<TTree.h> on the include path) this header is just
+// `#include <TTree.h>`.  Without ROOT it provides a minimal in-memory TTree
+// with the calls the sampler header makes (TSimpleMCMC.H:208-216, :300-349,
+// :1517-1596, :1616-1626): Branch() binds the address of a double, an int or
+// a std::vector<double>; Fill() snapshots every bound object.
+#ifndef SMCMC_TREE_H_SEEN
+#define SMCMC_TREE_H_SEEN
+
+#if defined(__has_include)
+#if __has_include(<TTree.h>)
+#define SMCMC_HAVE_ROOT_TTREE 1
+#endif
+#endif
+
+#ifdef SMCMC_HAVE_ROOT_TTREE
+#include <TTree.h>
+#else
+#include <map>
+#include <string>
+#include <vector>
+
+#ifndef NULL
+#define NULL 0
+#endif
+
+class TTree {
+public:
+    TTree(const char* name = "", const char* title = "") : fName(name), fTitle(title), fEntries(0) {}
+    const char* GetName() const { return fName.c_str(); }
+    void Branch(const char* n, double* a) { fD[n].src = a; }
+    void Branch(const char* n, int* a) { fI[n].src = a; }
+    void Branch(const char* n, std::vector<double>* a) { fV[n].src = a; }
+    int Fill() {
+        for (auto& c : fD) c.second.rows.push_back(*c.second.src);
+        for (auto& c : fI) c.second.rows.push_back(*c.second.src);
+        for (auto& c : fV) c.second.rows.push_back(*c.second.src);
+        return (int)++fEntries;
+    }
+    long GetEntries() const { return fEntries; }
+    int Write(const char* = 0) { return 0; }
+    // Reading back (tests, Restore): column access by name.
+    const std::vector<double>& DoubleColumn(const std::string& n) const { return fD.at(n).rows; }
+    const std::vector<int>& IntColumn(const std::string& n) const { return fI.at(n).rows; }
+    const std::vector<std::vector<double> >& VectorColumn(const std::string& n) const { return fV.at(n).rows; }
+    bool HasBranch(const std::string& n) const { return fD.count(n) || fI.count(n) || fV.count(n); }
+
+private:
+    template <class T>
+    struct Column {
+        const T* src;
+        std::vector<T> rows;
+    };
+    std::string fName, fTitle;
+    long fEntries;
+    std::map<std::string, Column<double> > fD;
+    std::map<std::string, Column<int> > fI;
+    std::map<std::string, Column<std::vector<double> > > fV;
+};
+#endif
+#endif

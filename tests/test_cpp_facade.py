@@ -1,0 +1,65 @@
+"""The C++ mirror of the reference API (include/TSimpleMCMC.H +
+include/smcmc_likelihoods.H): a program written like the reference's
+documentation example (reference TSimpleMCMC.H:122-156) compiles against it,
+links libsmcmc_b200, and -- on a GPU -- reproduces the reference chain."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden, golden_chain
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIBDIR = os.path.join(ROOT, "root-simple-mcmc_b200", "smcmc_b200")
+
+
+@pytest.fixture(scope="module")
+def program(tmp_path_factory):
+    import smcmc_b200
+    if not os.path.exists(smcmc_b200.library_path()):
+        smcmc_b200.build_library()
+    exe = str(tmp_path_factory.mktemp("cpp") / "simple_mcmc")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    "-o", exe, os.path.join(ROOT, "tests", "cpp", "simple_mcmc.cc"),
+                    "-L", LIBDIR, "-lsmcmc_b200", "-Wl,-rpath," + LIBDIR], check=True)
+    return exe
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_compiles_and_refuses_to_run_without_gpu(program):
+    r = subprocess.run([program, "unit", "1", "3"], capture_output=True, text=True)
+    assert r.returncode != 0
+    assert "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_documentation_example_reproduces_reference_chain(program):
+    r = subprocess.run([program, "unit", "1", "300"], capture_output=True, text=True, check=True)
+    want = golden_chain(golden("chains.npz"), "unit5_hints")
+    rows = re.findall(r"step (\d+) acc (\d) llh (\S+) x0 (\S+) sigma (\S+)", r.stdout)
+    assert len(rows) == 300
+    acc = np.array([int(x[1]) for x in rows])
+    llh = np.array([float(x[2]) for x in rows])
+    x0 = np.array([float(x[3]) for x in rows])
+    assert np.array_equal(acc, want["accepted"][:300])
+    assert np.allclose(llh, want["llh_accepted"][:300], rtol=1e-12, atol=1e-13)
+    assert np.allclose(x0, want["x"][:300, 0], rtol=1e-12, atol=1e-13)
+    m = re.search(r"entries (\d+) expected (\d+) accepted (\d+) calls (\d+)", r.stdout)
+    assert m and m.group(1) == m.group(2) == "301"
+    assert int(m.group(4)) == 301                       # Start + 300 steps
+    assert int(m.group(3)) == int(want["accepted"][:300].sum())
+    assert "last covariance size 15 first covariance size 0" in r.stdout   # full state only on SaveStep()
+    assert "caught invalid_argument: Uninitialized starting point" in r.stdout
+    assert "start llh 0 direct 0" in r.stdout
+
+
+@pytest.mark.gpu
+def test_fake_likelihood_ensemble_through_the_cpp_api(program):
+    r = subprocess.run([program, "fake", "8", "40"], capture_output=True, text=True, check=True)
+    m = re.search(r"entries (\d+) expected (\d+) accepted (\d+) calls (\d+)", r.stdout)
+    assert m and m.group(1) == m.group(2) == str(8 * 41)
+    s = re.search(r"start llh (\S+) direct (\S+)", r.stdout)
+    assert s and s.group(1) == s.group(2) and np.isfinite(float(s.group(1)))
