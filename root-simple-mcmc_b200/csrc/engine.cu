@@ -68,6 +68,9 @@ struct smcmc_engine {
     DeviceBuffer<double> xAcc, xProp, lastPoint, center, cov, decomp, llhProp;
     DeviceBuffer<ChainScalars> sc;
     DeviceBuffer<int32_t> okDev;
+    DeviceBuffer<double> eigScratch;
+    DeviceBuffer<int> eigLocks;
+    int eigSlots = 0;
 
     // ---- likelihood data ---------------------------------------------------
     DeviceBuffer<double> errMatrix;                 // DUMMY
@@ -117,6 +120,9 @@ struct smcmc_engine {
         a.cov = cov.get();
         a.decomp = decomp.get();
         a.sc = sc.get();
+        a.eigScratch = eigScratch.get();
+        a.eigLocks = eigLocks.get();
+        a.eigSlots = eigSlots;
         return a;
     }
 
@@ -398,6 +404,11 @@ int smcmc_create(const smcmc_config* cfg, smcmc_engine** out) {
         e->llhProp.reserve(E);
         e->sc.reserve(E);
         e->okDev.reserve(E);
+        // scratch pool for the eigen-decomposition fallback: at most 64 slots, <= 256 MB
+        e->eigSlots = (int)std::min<size_t>(std::min<size_t>(E, 64), std::max<size_t>(1, (256u << 20) / (2 * n * n * 8)));
+        e->eigScratch.reserve((size_t)e->eigSlots * 2 * n * n);
+        e->eigLocks.reserve(e->eigSlots);
+        CUDA_CHECK(cudaMemset(e->eigLocks.get(), 0, e->eigSlots * sizeof(int)));
         CUDA_CHECK(cudaMemset(e->sc.get(), 0, e->sc.bytes()));
         CUDA_CHECK(cudaMemset(e->cov.get(), 0, e->cov.bytes()));
         CUDA_CHECK(cudaMemset(e->decomp.get(), 0, e->decomp.bytes()));

@@ -37,10 +37,6 @@ def test_golden_chain(name):
     reference for that chain id, whatever its neighbours do."""
     import smcmc_b200
     assert torch.cuda.is_available()
-    if name == "unit6_clamped":
-        pytest.skip("needs the eigen-decomposition stage of UpdateProposal (TSimpleMCMC.H:1252-1321); the "
-                    "device implements the MCMC_SKIP_EIGENVALUE_DECOMPOSITION configuration -- see "
-                    "test_conditioning_ladder_keeps_chains_alive")
     kind, dim, seed, chain, nsteps, start = GOLDEN_CHAINS[name]
     g = golden("chains.npz")
     want = golden_chain(g, name)
@@ -178,18 +174,25 @@ def test_bad_start_is_reported():
 
 
 def test_conditioning_ladder_keeps_chains_alive():
-    """Out-of-range correlation hints (SimpleMCMC.C:107-115): the first
-    Cholesky fails, the conditioning / emergency stages (TSimpleMCMC.H:1134-1239,
-    :1335-1377) must leave every chain with a usable upper-triangular factor of
-    a positive-definite matrix, and the chains must keep sampling the target."""
+    """Out-of-range correlation hints (SimpleMCMC.C:107-115): both Cholesky
+    attempts fail and the eigen-decomposition stage (TSimpleMCMC.H:1252-1321)
+    must leave every chain with a decomposition U whose U^T U is positive
+    definite and reproduces the conditioned covariance up to the clamped
+    eigenvalues; the chains must keep sampling the target."""
     import smcmc_b200
     E, dim = 32, 6
     eng = smcmc_b200.Engine(smcmc_b200.LLH_UNIT_GAUSS, dim, E, seed=3)
     configure_golden("unit6_clamped", eng, _set_field)
     assert eng.start(np.zeros(dim)).all()
     u = eng.get("decomposition")
-    assert np.all(np.isfinite(u)) and np.all(np.abs(np.tril(u[0], -1)) == 0)
-    assert np.all(np.linalg.eigvalsh(u[0].T @ u[0]) > 0)
+    assert np.all(np.isfinite(u))
+    packed = eng.get("covariance")[0]
+    cov = np.zeros((dim, dim))
+    cov[np.tril_indices(dim)] = packed
+    cov = cov + np.tril(cov, -1).T
+    rebuilt = u[0].T @ u[0]
+    assert np.all(np.linalg.eigvalsh(rebuilt) > 0)
+    assert np.allclose(rebuilt, cov, atol=1e-6)        # eigenvalues are clamped from below at ~1.5e-8
     tr = eng.step_trace(4000, want=("accepted", "points"))
     assert 0.05 < tr["accepted"].mean() < 0.6
     pts = tr["points"][1500:].reshape(-1, dim)
