@@ -86,7 +86,10 @@ typedef enum smcmc_prop_field {
     SMCMC_PROP_CENTER_TRIALS = 9,        /* SetEstimatedCenterTrials       :747  */
     SMCMC_PROP_NEXT_UPDATE = 10,         /* SetNextUpdate                  :992  */
     SMCMC_PROP_MAX_CORRELATION = 11,     /* SetMaximumCorrelation          :909  */
-    SMCMC_PROP_STEP_RMS_WINDOW = 12      /* TSimpleMCMC::SetStepRMSWindow  :511  */
+    SMCMC_PROP_STEP_RMS_WINDOW = 12,     /* TSimpleMCMC::SetStepRMSWindow  :511  */
+    SMCMC_PROP_POOLED_EVERY = 13         /* NEW (not in the reference): K > 0 pools the
+                                            covariance adaptation over all chains and
+                                            GPUs, exchanging statistics every K steps   */
 } smcmc_prop_field;
 
 /* Per-chain quantities readable with smcmc_get().  Arrays are chain-major:
@@ -119,7 +122,11 @@ typedef enum smcmc_field {
     SMCMC_F_SIGMA_TRACE = 21,    /* double[chains]       fSigmaTrace              :1960 */
     SMCMC_F_COVARIANCE_WINDOW = 22, /* double[1]         GetCovarianceWindow      :915 */
     SMCMC_F_ACCEPTANCE_WINDOW = 23, /* double[1]         GetAcceptanceWindow      :983 */
-    SMCMC_F_TARGET_ACCEPTANCE = 24  /* double[1]         GetTargetAcceptance      :978 */
+    SMCMC_F_TARGET_ACCEPTANCE = 24, /* double[1]         GetTargetAcceptance      :978 */
+    SMCMC_F_POOLED_MEAN = 25,       /* double[dim]       pooled mode: ensemble mean        */
+    SMCMC_F_POOLED_COVARIANCE = 26, /* double[dim*(dim+1)/2] pooled mode: packed covariance */
+    SMCMC_F_POOLED_DECOMPOSITION = 27, /* double[dim*dim] pooled mode: the shared U         */
+    SMCMC_F_POOLED_COUNT = 28       /* double[1]         points behind the pooled estimate */
 } smcmc_field;
 
 /* Optional per-step trace of smcmc_step_trace(); any pointer may be NULL.
@@ -147,6 +154,19 @@ int smcmc_destroy(smcmc_engine* e);
 int smcmc_set_stream(smcmc_engine* e, void* cuda_stream);
 /* Block until all queued work is done; reports asynchronous errors. */
 int smcmc_sync(smcmc_engine* e);
+
+/* ---- multi-GPU: NCCL over NVLink (one engine = one rank = one GPU) --------- */
+/* Rank 0 creates the 128-byte NCCL unique id and distributes it out of band. */
+int smcmc_comm_unique_id(char* out, size_t bytes);
+/* Join `world` ranks.  Ranks [k*event_group, (k+1)*event_group) form an EVENT
+ * GROUP: they must be created with the same chains / chain_offset / seed, each
+ * uploads its own slice of the events, and every likelihood evaluation
+ * all-reduces the integer event counts inside the group.  The world
+ * communicator all-reduces the pooled adaptation statistics
+ * (SMCMC_PROP_POOLED_EVERY).  Chain-sharded ensembles with per-chain adaptation
+ * need no communicator at all. */
+int smcmc_comm_init(smcmc_engine* e, const char* unique_id, size_t bytes, int world, int rank,
+                    int event_group);
 
 /* ---- proposal configuration: TProposeAdaptiveStep setters ---------------- */
 int smcmc_prop_set(smcmc_engine* e, int field, double value);

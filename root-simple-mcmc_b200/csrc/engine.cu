@@ -11,6 +11,8 @@
 
 #include "common.cuh"
 #include "fake_likelihood.cuh"
+#include "nccl_dyn.h"
+#include "pooled.cuh"
 #include "proposal.cuh"
 #include "simple_likelihoods.cuh"
 
@@ -92,6 +94,55 @@ struct smcmc_engine {
     DeviceBuffer<uint32_t> fakeCounts;
     int fakeCountStride = 0;
     bool forceGeneric = false;
+
+    // ---- pooled adaptation (pooled.cuh) -----------------------------------------
+    int pooledEvery = 0;                            // 0 = per-chain adaptation (the reference)
+    DeviceBuffer<double> poolStats, poolStatsAll, poolCov, poolDecomp, poolMean, poolTrace;
+    DeviceBuffer<int> poolOk;
+    int64_t poolExchanges = 0;
+
+    // ---- multi-GPU (NCCL over NVLink) ---------------------------------------------
+    ncclComm_t worldComm = nullptr;                 // pooled-statistics all-reduce
+    ncclComm_t eventComm = nullptr;                 // ranks that share chains and split the events
+    int worldSize = 1, worldRank = 0, eventGroup = 1;
+
+    PooledState pooled() {
+        PooledState p;
+        p.stats = poolStats.get();
+        p.statsAll = poolStatsAll.get();
+        p.cov = poolCov.get();
+        p.decomp = poolDecomp.get();
+        p.mean = poolMean.get();
+        p.trace = poolTrace.get();
+        return p;
+    }
+    int poolStatCount() const { return 1 + n() + tri(); }
+    void poolInit() {
+        const size_t nn = (size_t)n() * n();
+        poolStats.reserve(poolStatCount());
+        poolStatsAll.reserve(poolStatCount());
+        poolCov.reserve(tri());
+        poolDecomp.reserve(2 * nn);
+        poolMean.reserve(n());
+        poolTrace.reserve(1);
+        poolOk.reserve(1);
+        CUDA_CHECK(cudaMemsetAsync(poolStats.get(), 0, poolStatCount() * sizeof(double), stream));
+        // every chain starts from the same U and trace (same settings): adopt chain 0's
+        CUDA_CHECK(cudaMemcpyAsync(poolDecomp.get(), decomp.get(), nn * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+        CUDA_CHECK(cudaMemcpyAsync(poolTrace.get(), &sc.get()->sigmaTrace, sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    }
+    void poolExchange() {
+        CUDA_CHECK(cudaMemcpyAsync(poolStatsAll.get(), poolStats.get(), poolStatCount() * sizeof(double),
+                                   cudaMemcpyDeviceToDevice, stream));
+        if (worldComm) {
+            NcclApi& nccl = NcclApi::get();
+            nccl.check(nccl.AllReduce(poolStatsAll.get(), poolStatsAll.get(), poolStatCount(), ncclDouble, ncclSum,
+                                      worldComm, stream), "all-reduce of pooled statistics");
+        }
+        kPoolFactor<<<1, 32, 0, stream>>>(pooled(), n(), poolOk.get());
+        launched();
+        ++poolExchanges;
+    }
 
     // ---- scratch for smcmc_eval / smcmc_fake_histograms ---------------------
     DeviceBuffer<double> evalX, evalOut, evalHist;
@@ -287,6 +338,13 @@ struct smcmc_engine {
                                                                        xDev, m, n(), fakeCounts.get(), stride);
             launched();
         }
+        if (eventComm) {
+            // events are split over the ranks of the event group: the integer
+            // counts add exactly, so the result does not depend on the split
+            NcclApi& nccl = NcclApi::get();
+            nccl.check(nccl.AllReduce(fakeCounts.get(), fakeCounts.get(), (size_t)kFakeSlots * stride, ncclUint32,
+                                      ncclSum, eventComm, stream), "all-reduce of event counts");
+        }
         kFakeFinish<<<ceilDiv(m, 32), 32 * kFinishWarps, 0, stream>>>(fakeCounts.get(), stride, m, fakeChains.get(),
                                                                       fakeData.get(), llhDev, histDev);
         launched();
@@ -323,13 +381,24 @@ struct smcmc_engine {
         ChainArrays a = arrays();
         const int blocks = ceilDiv(E(), kWarpsPerBlock);
         const size_t smem = (size_t)kWarpsPerBlock * 3 * n() * sizeof(double);
-        kPropose<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a, ps, E(), cfg.seed, cfg.chain_offset, stepIndex);
+        if (pooledEvery > 0)
+            kProposePooled<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a, ps, pooled(), E(), cfg.seed,
+                                                                          cfg.chain_offset, stepIndex);
+        else
+            kPropose<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a, ps, E(), cfg.seed, cfg.chain_offset, stepIndex);
         launched();
         evaluate(xProp.get(), E(), llhProp.get(), nullptr);
         kAccept<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(a, ps, E(), llhProp.get(), cfg.seed, cfg.chain_offset,
                                                             stepIndex, metropolis, tr, traceStep);
         launched();
         ++stepIndex;
+        if (pooledEvery > 0) {
+            const int poolBlocks = std::min(smCount * 2, ceilDiv(E(), 32));
+            kPoolAccumulate<<<poolBlocks, 256, 32 * n() * sizeof(double), stream>>>(xAcc.get(), sc.get(), E(), n(),
+                                                                                    poolStats.get());
+            launched();
+            if (stepIndex % (uint32_t)pooledEvery == 0) poolExchange();
+        }
     }
 };
 
@@ -446,19 +515,54 @@ int smcmc_create(const smcmc_config* cfg, smcmc_engine** out) {
             CUDA_CHECK(cudaFuncSetAttribute(kFakePairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes));
             e->fakeData.reserve(150);
         }
-        if ((size_t)kWarpsPerBlock * 3 * n * sizeof(double) > 48 * 1024)
+        if ((size_t)kWarpsPerBlock * 3 * n * sizeof(double) > 48 * 1024) {
             CUDA_CHECK(cudaFuncSetAttribute(kPropose, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)((size_t)kWarpsPerBlock * 3 * n * sizeof(double))));
+            CUDA_CHECK(cudaFuncSetAttribute(kProposePooled, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)((size_t)kWarpsPerBlock * 3 * n * sizeof(double))));
+        }
         *out = e;
     });
     if (rc != SMCMC_OK && e) delete e;
     return rc;
 }
 
+int smcmc_comm_unique_id(char* out, size_t bytes) {
+    return guarded(nullptr, [&]() {
+        if (!out || bytes < sizeof(ncclUniqueId)) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "need 128 bytes");
+        NcclApi& nccl = NcclApi::get();
+        ncclUniqueId id;
+        nccl.check(nccl.GetUniqueId(&id), "ncclGetUniqueId");
+        std::memcpy(out, &id, sizeof id);
+    });
+}
+
+int smcmc_comm_init(smcmc_engine* e, const char* idBytes, size_t bytes, int world, int rank, int eventGroup) {
+    return guarded(e, [&]() {
+        if (!idBytes || bytes < sizeof(ncclUniqueId)) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "need the 128-byte unique id");
+        if (world < 1 || rank < 0 || rank >= world || eventGroup < 1 || world % eventGroup)
+            throw Error(SMCMC_ERR_INVALID_ARGUMENT, "bad world / rank / event group");
+        if (e->worldComm) throw Error(SMCMC_ERR_LOGIC, "communicator already initialised");
+        NcclApi& nccl = NcclApi::get();
+        ncclUniqueId id;
+        std::memcpy(&id, idBytes, sizeof id);
+        CUDA_CHECK(cudaSetDevice(e->cfg.device));
+        nccl.check(nccl.CommInitRank(&e->worldComm, world, id, rank), "ncclCommInitRank");
+        e->worldSize = world;
+        e->worldRank = rank;
+        e->eventGroup = eventGroup;
+        if (eventGroup > 1)
+            nccl.check(nccl.CommSplit(e->worldComm, rank / eventGroup, rank % eventGroup, &e->eventComm, nullptr),
+                       "ncclCommSplit");
+    });
+}
+
 int smcmc_destroy(smcmc_engine* e) {
     if (!e) return SMCMC_OK;
     cudaSetDevice(e->cfg.device);
     cudaDeviceSynchronize();
+    if (e->eventComm) NcclApi::get().CommDestroy(e->eventComm);
+    if (e->worldComm) NcclApi::get().CommDestroy(e->worldComm);
     for (auto& pr : e->pairEvents) {
         cudaEventDestroy(pr.first);
         cudaEventDestroy(pr.second);
@@ -498,6 +602,11 @@ int smcmc_prop_set(smcmc_engine* e, int field, double v) {
         case SMCMC_PROP_NEXT_UPDATE: perChain = true; break;
         case SMCMC_PROP_MAX_CORRELATION: e->maxCorr = v; break;
         case SMCMC_PROP_STEP_RMS_WINDOW: e->stepRMSWindow = (int)v; break;
+        case SMCMC_PROP_POOLED_EVERY:
+            if (v < 0) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "pooled exchange period must be >= 0");
+            e->pooledEvery = (int)v;
+            if (e->started && e->pooledEvery > 0 && e->poolStats.count() == 0) e->poolInit();
+            break;
         default: throw Error(SMCMC_ERR_INVALID_ARGUMENT, "unknown proposal field");
         }
         if (perChain) {
@@ -551,6 +660,14 @@ int smcmc_prop_reset_correlations(smcmc_engine* e) {
 
 static void userUpdate(smcmc_engine* e, int reset) {
     requireStarted(e);
+    if (e->pooledEvery > 0) {
+        // pooled mode: UpdateProposal = exchange + refactor now; ResetProposal
+        // additionally forgets the accumulated statistics afterwards
+        e->poolExchange();
+        if (reset) CUDA_CHECK(cudaMemsetAsync(e->poolStats.get(), 0, e->poolStatCount() * sizeof(double), e->stream));
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        return;
+    }
     if (reset) e->resolveResetDefaults();
     PropSettings ps = e->settings();
     kUserUpdate<<<ceilDiv(e->E(), kWarpsPerBlock), kWarpsPerBlock * 32, 0, e->stream>>>(e->arrays(), ps, e->E(), reset);
@@ -711,6 +828,7 @@ int smcmc_start(smcmc_engine* e, const double* x0, int32_t* ok) {
         if (ok) std::memcpy(ok, okHost.data(), sizeof(int32_t) * e->E());
         e->started = true;
         e->checkChainStatus();
+        if (e->pooledEvery > 0) e->poolInit();
     });
 }
 
@@ -773,6 +891,18 @@ int smcmc_get(smcmc_engine* e, int field, void* dst, size_t bytes) {
         case SMCMC_F_COVARIANCE_WINDOW: need(8); *(double*)dst = e->covWindow; return;
         case SMCMC_F_ACCEPTANCE_WINDOW: need(8); *(double*)dst = e->accWindow; return;
         case SMCMC_F_TARGET_ACCEPTANCE: need(8); *(double*)dst = e->target; return;
+        case SMCMC_F_POOLED_MEAN:
+            if (!e->poolMean.count()) throw Error(SMCMC_ERR_LOGIC, "pooled adaptation is off");
+            copyArray(e->poolMean.get(), n * 8); return;
+        case SMCMC_F_POOLED_COVARIANCE:
+            if (!e->poolCov.count()) throw Error(SMCMC_ERR_LOGIC, "pooled adaptation is off");
+            copyArray(e->poolCov.get(), e->tri() * 8); return;
+        case SMCMC_F_POOLED_DECOMPOSITION:
+            if (!e->poolDecomp.count()) throw Error(SMCMC_ERR_LOGIC, "pooled adaptation is off");
+            copyArray(e->poolDecomp.get(), n * n * 8); return;
+        case SMCMC_F_POOLED_COUNT:
+            if (!e->poolStatsAll.count()) throw Error(SMCMC_ERR_LOGIC, "pooled adaptation is off");
+            copyArray(e->poolStatsAll.get(), 8); return;
         default: break;
         }
         std::vector<ChainScalars> h(E);

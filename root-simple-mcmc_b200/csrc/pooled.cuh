@@ -1,0 +1,219 @@
+// pooled.cuh -- ensemble-pooled adaptation (BASELINE.json config 3: "adaptive
+// covariance pooled across chains").  NOT in the reference, where every
+// TProposeAdaptiveStep is private to its chain (TSimpleMCMC.H:547): a new
+// mode, off by default, for ensembles where per-chain covariance state
+// (n(n+1)/2 + n^2 doubles per chain, read and written every step) is the
+// bottleneck.
+//
+// All chains share ONE proposal decomposition U, estimated from the pooled
+// sufficient statistics of every accepted point of every chain on every GPU:
+//     S = (count, sum x, sum x x^T)       [1 + n + n(n+1)/2 doubles]
+//   * kPoolAccumulate adds the current accepted points of the local chains;
+//   * every K steps S is all-reduced over the GPUs (NCCL, one small message);
+//   * kPoolFactor turns S into mean / covariance / U = chol(covariance) with
+//     the same warp Cholesky as the per-chain path, on every rank redundantly.
+// Each chain keeps its own step size sigma with the reference's acceptance
+// driven adaptation (TSimpleMCMC.H:1734-1776) and rescales it by the trace
+// ratio when the shared covariance changes (as UpdateProposal does, :1042).
+#pragma once
+#include "proposal.cuh"
+
+namespace smcmc {
+
+struct PooledState {
+    double* stats;      // accumulated S, this rank (all-reduced copy in statsAll)
+    double* statsAll;   // S summed over ranks at the last exchange
+    double* cov;        // packed lower triangle of the pooled covariance
+    double* decomp;     // n x n row-major shared U
+    double* mean;       // n
+    double* trace;      // [0] trace of the pooled covariance behind `decomp`
+};
+
+// S += sum over local chains.  Block = 256 threads; thread t owns packed
+// entries t, t+256, ...; a block walks a slice of the chains with the points
+// staged through shared memory.
+__global__ void __launch_bounds__(256)
+kPoolAccumulate(const double* __restrict__ xAcc, const ChainScalars* __restrict__ sc, int chains, int n,
+                double* stats) {
+    extern __shared__ double tile[];          // 32 chains x n
+    const int tri = n * (n + 1) / 2;
+    const int nstat = 1 + n + tri;
+    constexpr int kMaxOwn = 8;                // entries per thread handled per pass
+    const int perBlock = (chains + gridDim.x - 1) / gridDim.x;
+    const int first = blockIdx.x * perBlock;
+    const int last = min(chains, first + perBlock);
+    for (int pass = 0; pass * 256 * kMaxOwn < nstat; ++pass) {
+        double acc[kMaxOwn];
+        int ei[kMaxOwn], ej[kMaxOwn];
+#pragma unroll
+        for (int o = 0; o < kMaxOwn; ++o) {
+            acc[o] = 0.0;
+            const int k = (pass * kMaxOwn + o) * 256 + threadIdx.x;      // 0: count, 1..n: sum x, then packed x x^T
+            ei[o] = -2; ej[o] = 0;
+            if (k == 0) ei[o] = -1;
+            else if (k <= n) { ei[o] = k - 1; ej[o] = -1; }
+            else if (k < nstat) {
+                const int p = k - 1 - n;
+                int i = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+                while (i * (i + 1) / 2 > p) --i;
+                while ((i + 1) * (i + 2) / 2 <= p) ++i;
+                ei[o] = i; ej[o] = p - i * (i + 1) / 2;
+            }
+        }
+        for (int c0 = first; c0 < last; c0 += 32) {
+            const int nc = min(32, last - c0);
+            __syncthreads();
+            for (int k = threadIdx.x; k < nc * n; k += 256) {
+                const int c = k / n;
+                tile[k] = sc[c0 + c].started ? xAcc[(size_t)(c0 + c) * n + (k - c * n)] : nan("");
+            }
+            __syncthreads();
+            for (int c = 0; c < nc; ++c) {
+                const double* x = tile + c * n;
+                if (isnan(x[0])) continue;               // chain not started
+#pragma unroll
+                for (int o = 0; o < kMaxOwn; ++o) {
+                    if (ei[o] == -1) acc[o] += 1.0;
+                    else if (ei[o] >= 0 && ej[o] < 0) acc[o] += x[ei[o]];
+                    else if (ei[o] >= 0) acc[o] += x[ei[o]] * x[ej[o]];
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < kMaxOwn; ++o) {
+            const int k = (pass * kMaxOwn + o) * 256 + threadIdx.x;
+            if (k < nstat && acc[o] != 0.0) atomicAdd(&stats[k], acc[o]);
+        }
+    }
+}
+
+// One warp: S -> mean, covariance, trace, U.  Keeps the previous U when the
+// pooled covariance is not (yet) positive definite.  ok[0] = 1 on success.
+__global__ void kPoolFactor(PooledState ps, int n, int* ok) {
+    const int lane = threadIdx.x;
+    const int tri = n * (n + 1) / 2;
+    const double count = ps.statsAll[0];
+    if (!(count > (double)(n + 1))) { if (lane == 0) ok[0] = 0; return; }
+    for (int i = lane; i < n; i += 32) ps.mean[i] = ps.statsAll[1 + i] / count;
+    __syncwarp();
+    for (int p = lane; p < tri; p += 32) {
+        int i = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+        while (i * (i + 1) / 2 > p) --i;
+        while ((i + 1) * (i + 2) / 2 <= p) ++i;
+        const int j = p - i * (i + 1) / 2;
+        ps.cov[p] = ps.statsAll[1 + n + p] / count - ps.mean[i] * ps.mean[j];
+    }
+    __syncwarp();
+    // factor into the second half of the U buffer, publish on success
+    double* work = ps.decomp + (size_t)n * n;
+    const bool good = warpCholesky(ps.cov, work, n, lane);
+    if (good) {
+        for (int k = lane; k < n * n; k += 32) ps.decomp[k] = work[k];
+        double t = 0.0;
+        for (int i = 0; i < n; ++i) t += ps.cov[triIndex(i, i)];
+        if (lane == 0) ps.trace[0] = t;
+    }
+    if (lane == 0) ok[0] = good ? 1 : 0;
+}
+
+// The head of Step() in pooled mode: the scalar part of UpdateState
+// (:1723-1776) per chain, then the draw (:709-724) with the SHARED U.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 8)
+kProposePooled(ChainArrays a, PropSettings ps, PooledState pool, int chains, uint64_t seed,
+               uint32_t chainOffset, uint32_t step) {
+    extern __shared__ double smemD[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * kWarpsPerBlock + warp;
+    if (c >= chains) return;
+    const int n = ps.n;
+    double* cur = smemD + (size_t)warp * 3 * n;
+    double* prop = cur + n;
+    double* zr = prop + n;
+    ChainScalars s = a.sc[c];
+    if (!s.started || s.status != 0) return;
+    double* xAcc = a.xAcc + (size_t)c * n;
+    double* xProp = a.xProp + (size_t)c * n;
+    double* last = a.lastPoint + (size_t)c * n;
+    s.totalSteps += 1;
+    const double value = s.accLlh;
+    for (int i = lane; i < n; i += 32) cur[i] = xAcc[i];
+    __syncwarp();
+    s.trials += 1;
+    const bool accepted = (value != s.lastValue) || (cur[0] != last[0]);
+    if (accepted) s.successes += 1;
+    s.acceptance = __dmul_rn(s.acceptance, s.acceptanceTrials);
+    if (accepted) s.acceptance = __dadd_rn(s.acceptance, 1.0);
+    s.acceptance = __ddiv_rn(s.acceptance, __dadd_rn(s.acceptanceTrials, 1.0));
+    s.acceptanceTrials = fmin(ps.accWindow, __dadd_rn(s.acceptanceTrials, 1.0));
+    if (s.rigidity < 500.0 && s.rigidity > 0.0) {
+        double accSigma = __dmul_rn(ps.target, __dsub_rn(1.0, ps.target));
+        accSigma = __dsqrt_rn(__ddiv_rn(accSigma, ps.accWindow));
+        const double dist = fabs(__dsub_rn(s.acceptance, ps.target));
+        if (dist < accSigma) {
+            s.rigidity = __dadd_rn(s.rigidity, __ddiv_rn(__dmul_rn(0.5, s.rigidity), ps.accWindow));
+            s.rigidity = fmin(200.0, s.rigidity);
+        }
+        if (dist > __dmul_rn(4.0, accSigma)) {
+            s.rigidity = __dsub_rn(s.rigidity, __ddiv_rn(__dmul_rn(__dmul_rn(1.618, 0.5), s.rigidity), ps.accWindow));
+            s.rigidity = fmax(2.0, s.rigidity);
+        }
+    }
+    if (s.rigidity > 0 && s.rigidity < 100.0) {
+        const double ex = fmin(__ddiv_rn(1.0, 500.0), __ddiv_rn(1.0, __dmul_rn(s.rigidity, ps.accWindow)));
+        s.sigma = __dmul_rn(s.sigma, pow(__ddiv_rn(s.acceptance, ps.target), ex));
+    }
+    // the shared covariance changed since this chain last looked: keep the
+    // step length in units of the new trace (UpdateProposal :1042-1043)
+    const double poolTrace = pool.trace[0];
+    if (poolTrace > 0.0 && poolTrace != s.sigmaTrace) {
+        s.sigma = __dmul_rn(s.sigma, __dsqrt_rn(__ddiv_rn(s.sigmaTrace, poolTrace)));
+        s.sigmaTrace = poolTrace;
+    }
+    s.lastValue = value;
+    for (int i = lane; i < n; i += 32) last[i] = cur[i];
+
+    const uint32_t gchain = chainOffset + (uint32_t)c;
+    for (int i = lane; i < n; i += 32) {
+        if (ps.type[i] == 1) {
+            const double uu = smcmc_uniform(seed, gchain, step, (uint32_t)i, SMCMC_STREAM_STEP);
+            zr[i] = __dadd_rn(ps.param1[i], __dmul_rn(__dsub_rn(ps.param2[i], ps.param1[i]), uu));
+        } else {
+            const double g = smcmc_normal(seed, gchain, step, (uint32_t)i, SMCMC_STREAM_STEP);
+            zr[i] = __dmul_rn(s.sigma, __dadd_rn(0.0, __dmul_rn(1.0, g)));
+        }
+    }
+    __syncwarp();
+    const double* u = pool.decomp;
+    for (int j = lane; j < n; j += 32) {
+        double p;
+        if (ps.type[j] == 1) p = zr[j];
+        else {
+            p = cur[j];
+#pragma unroll 8
+            for (int i = 0; i <= j; ++i) {
+                if (ps.type[i] == 1) continue;
+                p = __dadd_rn(p, __dmul_rn(zr[i], u[(size_t)i * n + j]));
+            }
+        }
+        xProp[j] = p;
+        prop[j] = p;
+    }
+    __syncwarp();
+    if (ps.stepRMSWindow > 0) {
+        double sqr = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double d = __dsub_rn(prop[i], cur[i]);
+            sqr = __dadd_rn(sqr, __dmul_rn(d, d));
+        }
+        double ms = __dmul_rn(s.stepRMS, s.stepRMS);
+        ms = __dmul_rn(ms, (double)s.stepRMSTrials);
+        ms = __dadd_rn(ms, sqr);
+        ms = __ddiv_rn(ms, __dadd_rn((double)s.stepRMSTrials, 1.0));
+        s.stepRMSTrials = min(ps.stepRMSWindow, s.stepRMSTrials + 1);
+        s.stepRMS = __dsqrt_rn(ms);
+    }
+    if (lane == 0) a.sc[c] = s;
+}
+
+}  // namespace smcmc

@@ -15,7 +15,7 @@ LLH_UNIT_GAUSS, LLH_DUMMY, LLH_HORRIFIC, LLH_ASYM, LLH_FAKE = range(5)
  PROP_ACCEPTANCE_RIGIDITY, PROP_ACCEPTANCE_DEWEIGHT, PROP_COVARIANCE_WINDOW,
  PROP_COVARIANCE_DEWEIGHT, PROP_COVARIANCE_FROZEN, PROP_COVARIANCE_TRIALS,
  PROP_CENTER_TRIALS, PROP_NEXT_UPDATE, PROP_MAX_CORRELATION,
- PROP_STEP_RMS_WINDOW) = range(13)
+ PROP_STEP_RMS_WINDOW, PROP_POOLED_EVERY) = range(14)
 
 # smcmc_field: name -> (id, dtype, shape code)
 _FIELDS = {
@@ -32,6 +32,8 @@ _FIELDS = {
     "status": (20, np.int32, "E"), "sigma_trace": (21, np.float64, "E"),
     "covariance_window": (22, np.float64, "1"), "acceptance_window": (23, np.float64, "1"),
     "target_acceptance": (24, np.float64, "1"),
+    "pooled_mean": (25, np.float64, "n"), "pooled_covariance": (26, np.float64, "t"),
+    "pooled_decomposition": (27, np.float64, "nn"), "pooled_count": (28, np.float64, "1"),
 }
 
 # The reference's MC event record (example/Simulated.H:7-14), 48 bytes.
@@ -92,6 +94,8 @@ def load_library():
         "smcmc_create": (ci, [ctypes.POINTER(_Config), ctypes.POINTER(vp)]),
         "smcmc_destroy": (ci, [vp]),
         "smcmc_set_stream": (ci, [vp, vp]),
+        "smcmc_comm_unique_id": (ci, [ctypes.c_char_p, ctypes.c_size_t]),
+        "smcmc_comm_init": (ci, [vp, ctypes.c_char_p, ctypes.c_size_t, ci, ci, ci]),
         "smcmc_sync": (ci, [vp]),
         "smcmc_prop_set": (ci, [vp, ci, cd]),
         "smcmc_prop_set_gaussian": (ci, [vp, ci, cd]),
@@ -126,7 +130,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     "smcmc_abi_version", "smcmc_last_error", "smcmc_create", "smcmc_destroy",
-    "smcmc_set_stream", "smcmc_sync", "smcmc_prop_set", "smcmc_prop_set_gaussian",
+    "smcmc_set_stream", "smcmc_sync", "smcmc_comm_unique_id", "smcmc_comm_init", "smcmc_prop_set", "smcmc_prop_set_gaussian",
     "smcmc_prop_set_uniform", "smcmc_prop_set_correlation",
     "smcmc_prop_reset_correlations", "smcmc_prop_update", "smcmc_prop_reset",
     "smcmc_fake_set_events", "smcmc_fake_set_data", "smcmc_fake_histograms",
@@ -136,6 +140,16 @@ EXPORTED_SYMBOLS = [
     "smcmc_pair_kernel_stats", "smcmc_enable_kernel_timing",
     "smcmc_measure_fp64_peak",
 ]
+
+
+def comm_unique_id():
+    """A fresh 128-byte NCCL unique id (create on rank 0, broadcast, pass to Engine.comm_init)."""
+    lib = load_library()
+    buf = ctypes.create_string_buffer(128)
+    rc = lib.smcmc_comm_unique_id(buf, 128)
+    if rc != 0:
+        raise SmcmcError(rc, lib.smcmc_last_error(None).decode())
+    return buf.raw
 
 
 def measure_fp64_peak(device=0):
@@ -186,6 +200,10 @@ class Engine:
     # -- plumbing ---------------------------------------------------------
     def set_stream(self, cuda_stream):
         self._check(self.lib.smcmc_set_stream(self.h, ctypes.c_void_p(cuda_stream)))
+
+    def comm_init(self, unique_id, world, rank, event_group=1):
+        """Join the NCCL communicator(s); see smcmc_comm_init."""
+        self._check(self.lib.smcmc_comm_init(self.h, unique_id, len(unique_id), world, rank, event_group))
 
     def sync(self):
         self._check(self.lib.smcmc_sync(self.h))
@@ -282,7 +300,8 @@ class Engine:
     def get(self, name):
         fid, dt, code = _FIELDS[name]
         E, n = self.chains, self.dim
-        shape = {"E": (E,), "En": (E, n), "Et": (E, n * (n + 1) // 2), "Enn": (E, n, n), "1": (1,)}[code]
+        shape = {"E": (E,), "En": (E, n), "Et": (E, n * (n + 1) // 2), "Enn": (E, n, n), "1": (1,),
+                 "n": (n,), "t": (n * (n + 1) // 2,), "nn": (n, n)}[code]
         out = np.zeros(shape, dt)
         self._check(self.lib.smcmc_get(self.h, fid, _ptr(out), out.nbytes))
         return out
