@@ -216,6 +216,42 @@ int smcmc_step_trace(smcmc_engine* e, int nsteps, int metropolis,
 /* Read a per-chain quantity (synchronous). */
 int smcmc_get(smcmc_engine* e, int field, void* dst, size_t bytes);
 
+/* ---- checkpoint / resume ----------------------------------------------------- */
+/* What the reference keeps in its output tree to continue a chain
+ * (TSimpleMCMC.H:208-216 and the Adaptive* branches :1616-1626, filled by
+ * SaveStep(true) :528-532,1631-1652), for every chain of the engine.  Arrays
+ * are chain-major; covariance packed lower-triangular as the
+ * AdaptiveCovariance branch. */
+typedef struct smcmc_saved_state {
+    double* accepted;            /* [chains*dim]  Accepted                    */
+    double* log_likelihood;      /* [chains]      LogLikelihood               */
+    int32_t* total_steps;        /* [chains]      TotalSteps                  */
+    double* step_rms;            /* [chains]      StepRMS                     */
+    int32_t* trials;             /* [chains]      AdaptiveTrials              */
+    int32_t* successes;          /* [chains]      AdaptiveSuccesses           */
+    int32_t* next_update;        /* [chains]      AdaptiveNextUpdate          */
+    double* acceptance;          /* [chains]      AdaptiveAcceptance          */
+    double* acceptance_trials;   /* [chains]      AdaptiveAcceptanceTrials    */
+    double* sigma;               /* [chains]      AdaptiveSigma               */
+    double* central_point;       /* [chains*dim]  AdaptiveCentralPoint        */
+    double* central_point_trials;/* [chains]      AdaptiveCentralPointTrials  */
+    double* covariance;          /* [chains*dim*(dim+1)/2] AdaptiveCovariance */
+    double* covariance_trials;   /* [chains]      AdaptiveCovarianceTrials    */
+} smcmc_saved_state;
+/* SaveStep(true): copy the state of every chain into the caller's arrays. */
+int smcmc_save_state(smcmc_engine* e, const smcmc_saved_state* out);
+/* TSimpleMCMC::Restore (:282-352) + TProposeAdaptiveStep::RestoreState
+ * (:1501-1610) on every chain, after Start(): adopt the saved point and
+ * proposal state, re-evaluate the likelihood at the restored point (the
+ * calculated value replaces the saved one when they differ by more than 1e-4,
+ * :335-345; mismatch[c] receives 1 in that case, may be NULL), set the sigma
+ * trace to the trace of the restored covariance and run UpdateProposal(). */
+int smcmc_restore_state(smcmc_engine* e, const smcmc_saved_state* in, int32_t* mismatch);
+/* The step counter that addresses the random stream: a resumed run continues
+ * the stream where the saved run stopped when this is carried over. */
+int smcmc_get_step_index(smcmc_engine* e, uint32_t* step);
+int smcmc_set_step_index(smcmc_engine* e, uint32_t step);
+
 /* ---- instrumentation ------------------------------------------------------ */
 /* Kernel launches issued by this engine so far. */
 int64_t smcmc_launch_count(const smcmc_engine* e);

@@ -86,6 +86,9 @@ def load(which):
         "chain_llh": (cd, [vp, vp]),
         "chain_fake_hist": (ci, [vp, vp, vp]),
         "last_error": (ctypes.c_char_p, []),
+        "chain_step_saved": (ci, [vp, ci, vp]),
+        "chain_save_step": (ci, [vp]),
+        "chain_restore": (ci, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, p + name)
@@ -171,6 +174,20 @@ class CpuChain:
                                           _ptr(la), _ptr(lp), _ptr(x), _ptr(sg)))
         return {"accepted": acc, "llh_accepted": la, "llh_proposed": lp,
                 "x": x, "sigma": sg}
+
+    def step_saved(self, nsteps):
+        """Step(true): every step is written to the chain's tree."""
+        acc = np.zeros(nsteps, np.int32)
+        self._check(self._f("chain_step_saved")(self.h, nsteps, _ptr(acc)))
+        return acc
+
+    def save_step(self):
+        """SaveStep(): the full proposal state goes to the tree."""
+        self._check(self._f("chain_save_step")(self.h))
+
+    def restore(self, source):
+        """Restore() from the tree of `source` (call after start())."""
+        self._check(self._f("chain_restore")(self.h, source.h))
 
     def update_proposal(self):
         self._check(self._f("chain_update_proposal")(self.h))

@@ -91,6 +91,7 @@ struct ChainBase {
     virtual TProposeAdaptiveStep& Prop() = 0;
     virtual bool Start(const Vector& x) = 0;
     virtual bool Step(int metropolis) = 0;
+    virtual bool StepSaved(int metropolis) = 0;
     virtual double Llh(const Vector& x) = 0;
     virtual const Vector& Accepted() = 0;
     virtual double AcceptedLlh() = 0;
@@ -99,14 +100,20 @@ struct ChainBase {
     virtual int TotalSteps() = 0;
     virtual int LlhCalls() = 0;
     virtual void SetStepRMSWindow(int n) = 0;
+    virtual void SaveStep() = 0;
+    virtual void Restore(TTree* tree) = 0;
     virtual FakeLikelihood* Fake() { return 0; }
+    TTree tree;      // every chain writes to its own in-memory tree
 };
 
 template <class L>
 struct Chain : public ChainBase {
     TSimpleMCMC<L> mcmc;
     Chain(uint64_t seed, uint32_t chain, int d)
-        : ChainBase(seed, chain, d), mcmc(NULL, false) {}
+        : ChainBase(seed, chain, d), mcmc(&tree, false) {}
+    void SaveStep() { mcmc.SaveStep(); }
+    void Restore(TTree* t) { mcmc.Restore(t); }
+    bool StepSaved(int metropolis) { return mcmc.Step(true, metropolis); }
     TProposeAdaptiveStep& Prop() { return mcmc.GetProposeStep(); }
     bool Start(const Vector& x) { return mcmc.Start(x, false); }
     bool Step(int metropolis) { return mcmc.Step(false, metropolis); }
@@ -278,6 +285,38 @@ int ref_chain_step(void* h, int nsteps, int metropolis, int32_t* accepted,
             if (x) std::copy(c->Accepted().begin(), c->Accepted().end(),
                              x + (size_t)s * c->dim);
         }
+        return 0;
+    });
+}
+
+// Step(true): as ref_chain_step but every step is written to the chain's tree.
+int ref_chain_step_saved(void* h, int nsteps, int32_t* accepted) {
+    ChainBase* c = H(h);
+    return Guard([&]() {
+        gRandom = &c->rng;
+        for (int s = 0; s < nsteps; ++s) {
+            c->rng.Begin(c->step++);
+            bool ok = c->StepSaved(0);
+            if (accepted) accepted[s] = ok ? 1 : 0;
+        }
+        return 0;
+    });
+}
+
+// SaveStep(): the full proposal state goes to the tree (TSimpleMCMC.H:528-532).
+int ref_chain_save_step(void* h) {
+    return Guard([&]() { H(h)->SaveStep(); return 0; });
+}
+
+// Restore(tree) from the tree of another chain (TSimpleMCMC.H:282-352); the
+// random stream continues at the source chain's step counter.
+int ref_chain_restore(void* h, void* source) {
+    ChainBase* c = H(h);
+    ChainBase* src = H(source);
+    return Guard([&]() {
+        gRandom = &c->rng;
+        c->Restore(&src->tree);
+        c->step = src->step;
         return 0;
     });
 }

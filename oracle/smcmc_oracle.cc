@@ -629,6 +629,70 @@ struct OrcChain {
     }
 };
 
+// What SaveStep(true) leaves in the last tree entry (TSimpleMCMC.H:208-216,
+// :1631-1652), and Restore()/RestoreState() (:282-352, :1501-1610) from it.
+struct SavedState {
+    std::vector<double> accepted, center, covPacked;
+    double llh, stepRMS, acceptance, acceptanceTrials, sigma, centerTrials, covTrials;
+    int totalSteps, trials, successes, nextUpdate;
+};
+
+SavedState SaveFull(const OrcChain& c) {
+    SavedState s;
+    const Proposal& p = c.prop;
+    s.accepted = c.accepted;
+    s.llh = c.acceptedLlh;
+    s.totalSteps = c.totalSteps;
+    s.stepRMS = c.stepRMS;
+    s.trials = p.trials;
+    s.successes = p.successes;
+    s.nextUpdate = p.nextUpdate;
+    s.acceptance = p.acceptance;
+    s.acceptanceTrials = p.acceptanceTrials;
+    s.sigma = p.sigma;
+    s.center = p.center;
+    s.centerTrials = p.centerTrials;
+    s.covTrials = p.covTrials;
+    for (int i = 0; i < c.n; ++i)
+        for (int j = 0; j < i + 1; ++j) s.covPacked.push_back(p.cov[(size_t)i * c.n + j]);
+    return s;
+}
+
+bool RestoreFrom(OrcChain& c, const SavedState& s) {
+    const int n = c.n;
+    c.totalSteps = s.totalSteps;                                     // :320-331
+    c.acceptedLlh = s.llh;
+    c.stepRMS = s.stepRMS;
+    c.accepted = s.accepted;
+    c.proposed = s.accepted;
+    c.trial = s.accepted;
+    c.proposedLlh = c.Eval(c.proposed.data());                       // :335-345
+    if (std::abs(c.proposedLlh - c.acceptedLlh) > 1E-4) c.acceptedLlh = c.proposedLlh;
+    Proposal& p = c.prop;                                            // RestoreState :1501-1610
+    p.initialized = true;
+    p.lastValue = c.acceptedLlh;
+    p.lastPoint = c.accepted;
+    p.trials = s.trials;
+    p.successes = s.successes;
+    p.nextUpdate = s.nextUpdate;
+    p.acceptance = s.acceptance;
+    p.acceptanceTrials = s.acceptanceTrials;
+    p.sigma = s.sigma;
+    p.center = s.center;
+    p.centerTrials = s.centerTrials;
+    if (s.covPacked.size() != (size_t)n * (n + 1) / 2) { gLastError = "Past the end of the covariance"; return false; }
+    size_t k = 0;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < i + 1; ++j) {
+            p.cov[(size_t)i * n + j] = s.covPacked[k];
+            p.cov[(size_t)j * n + i] = s.covPacked[k];
+            ++k;
+        }
+    p.sigmaTrace = p.Trace();
+    p.covTrials = s.covTrials;
+    return p.UpdateProposal(false);                                  // :1607
+}
+
 OrcChain* H(void* h) { return static_cast<OrcChain*>(h); }
 
 }  // namespace
@@ -777,6 +841,21 @@ int orc_chain_fake_hist(void* h, const double* x, double* out150) {
     for (int hh = 0; hh < 3; ++hh)
         for (int b = 0; b < 50; ++b) out150[hh * 50 + b] = l.sim[hh][b + 1];
     return 0;
+}
+
+int orc_chain_restore(void* h, void* source) {
+    OrcChain* c = H(h);
+    OrcChain* src = H(source);
+    if (!RestoreFrom(*c, SaveFull(*src))) return -1;
+    c->step = src->step;
+    return 0;
+}
+
+// For symmetry with the reference-backed checker: saving is a no-op here, the
+// full state is read from the source chain at restore time.
+int orc_chain_save_step(void*) { return 0; }
+int orc_chain_step_saved(void* h, int nsteps, int32_t* accepted) {
+    return orc_chain_step(h, nsteps, 0, accepted, 0, 0, 0, 0);
 }
 
 int orc_chain_fake_counts(void* h, const double* x, uint32_t* out450) {

@@ -870,6 +870,93 @@ int smcmc_step_trace(smcmc_engine* e, int nsteps, int metropolis, const smcmc_tr
     });
 }
 
+int smcmc_save_state(smcmc_engine* e, const smcmc_saved_state* out) {
+    return guarded(e, [&]() {
+        requireStarted(e);
+        if (!out) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null state");
+        const size_t E = e->E(), n = e->n(), tri = e->tri();
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        std::vector<ChainScalars> h(E);
+        CUDA_CHECK(cudaMemcpy(h.data(), e->sc.get(), sizeof(ChainScalars) * E, cudaMemcpyDeviceToHost));
+        if (out->accepted) CUDA_CHECK(cudaMemcpy(out->accepted, e->xAcc.get(), E * n * 8, cudaMemcpyDeviceToHost));
+        if (out->central_point) CUDA_CHECK(cudaMemcpy(out->central_point, e->center.get(), E * n * 8, cudaMemcpyDeviceToHost));
+        if (out->covariance) CUDA_CHECK(cudaMemcpy(out->covariance, e->cov.get(), E * tri * 8, cudaMemcpyDeviceToHost));
+        for (size_t c = 0; c < E; ++c) {
+            if (out->log_likelihood) out->log_likelihood[c] = h[c].accLlh;
+            if (out->total_steps) out->total_steps[c] = h[c].totalSteps;
+            if (out->step_rms) out->step_rms[c] = h[c].stepRMS;
+            if (out->trials) out->trials[c] = h[c].trials;
+            if (out->successes) out->successes[c] = h[c].successes;
+            if (out->next_update) out->next_update[c] = h[c].nextUpdate;
+            if (out->acceptance) out->acceptance[c] = h[c].acceptance;
+            if (out->acceptance_trials) out->acceptance_trials[c] = h[c].acceptanceTrials;
+            if (out->sigma) out->sigma[c] = h[c].sigma;
+            if (out->central_point_trials) out->central_point_trials[c] = h[c].centerTrials;
+            if (out->covariance_trials) out->covariance_trials[c] = h[c].covTrials;
+        }
+    });
+}
+
+int smcmc_restore_state(smcmc_engine* e, const smcmc_saved_state* in, int32_t* mismatch) {
+    return guarded(e, [&]() {
+        requireStarted(e);
+        if (!in || !in->accepted || !in->log_likelihood || !in->total_steps || !in->step_rms || !in->trials ||
+            !in->successes || !in->next_update || !in->acceptance || !in->acceptance_trials || !in->sigma ||
+            !in->central_point || !in->central_point_trials || !in->covariance || !in->covariance_trials)
+            throw Error(SMCMC_ERR_LOGIC, "Past the end of the covariance");      // incomplete saved state (:1572-1576)
+        if (e->pooledEvery > 0) throw Error(SMCMC_ERR_LOGIC, "restore is defined for per-chain adaptation");
+        const size_t E = e->E(), n = e->n(), tri = e->tri();
+        DeviceBuffer<double> d[7];
+        DeviceBuffer<int> i4[4];
+        DeviceBuffer<int32_t> mm;
+        auto upD = [&](DeviceBuffer<double>& b, const double* src) {
+            b.reserve(E);
+            CUDA_CHECK(cudaMemcpyAsync(b.get(), src, E * 8, cudaMemcpyHostToDevice, e->stream));
+            return b.get();
+        };
+        auto upI = [&](DeviceBuffer<int>& b, const int32_t* src) {
+            b.reserve(E);
+            CUDA_CHECK(cudaMemcpyAsync(b.get(), src, E * 4, cudaMemcpyHostToDevice, e->stream));
+            return b.get();
+        };
+        CUDA_CHECK(cudaMemcpyAsync(e->xAcc.get(), in->accepted, E * n * 8, cudaMemcpyHostToDevice, e->stream));
+        CUDA_CHECK(cudaMemcpyAsync(e->center.get(), in->central_point, E * n * 8, cudaMemcpyHostToDevice, e->stream));
+        CUDA_CHECK(cudaMemcpyAsync(e->cov.get(), in->covariance, E * tri * 8, cudaMemcpyHostToDevice, e->stream));
+        RestoreScalars r;
+        r.savedLlh = upD(d[0], in->log_likelihood);
+        r.stepRMS = upD(d[1], in->step_rms);
+        r.acceptance = upD(d[2], in->acceptance);
+        r.acceptanceTrials = upD(d[3], in->acceptance_trials);
+        r.sigma = upD(d[4], in->sigma);
+        r.centerTrials = upD(d[5], in->central_point_trials);
+        r.covTrials = upD(d[6], in->covariance_trials);
+        r.totalSteps = upI(i4[0], in->total_steps);
+        r.trials = upI(i4[1], in->trials);
+        r.successes = upI(i4[2], in->successes);
+        r.nextUpdate = upI(i4[3], in->next_update);
+        e->evaluate(e->xAcc.get(), e->E(), e->llhProp.get(), nullptr);                    // :335
+        mm.reserve(E);
+        PropSettings ps = e->settings();
+        kRestore<<<ceilDiv(e->E(), kWarpsPerBlock), kWarpsPerBlock * 32, 0, e->stream>>>(e->arrays(), ps, e->E(), r,
+                                                                                         e->llhProp.get(), mm.get());
+        e->launched();
+        if (mismatch) CUDA_CHECK(cudaMemcpyAsync(mismatch, mm.get(), E * 4, cudaMemcpyDeviceToHost, e->stream));
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        e->checkChainStatus();
+    });
+}
+
+int smcmc_get_step_index(smcmc_engine* e, uint32_t* step) {
+    return guarded(e, [&]() {
+        if (!step) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null output");
+        *step = e->stepIndex;
+    });
+}
+
+int smcmc_set_step_index(smcmc_engine* e, uint32_t step) {
+    return guarded(e, [&]() { e->stepIndex = step; });
+}
+
 int smcmc_get(smcmc_engine* e, int field, void* dst, size_t bytes) {
     return guarded(e, [&]() {
         if (!dst) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null destination");

@@ -58,6 +58,18 @@ class _Config(ctypes.Structure):
                 ("seed", ctypes.c_uint64)]
 
 
+_SAVED_FIELDS = [("accepted", np.float64, "En"), ("log_likelihood", np.float64, "E"), ("total_steps", np.int32, "E"),
+                 ("step_rms", np.float64, "E"), ("trials", np.int32, "E"), ("successes", np.int32, "E"),
+                 ("next_update", np.int32, "E"), ("acceptance", np.float64, "E"),
+                 ("acceptance_trials", np.float64, "E"), ("sigma", np.float64, "E"),
+                 ("central_point", np.float64, "En"), ("central_point_trials", np.float64, "E"),
+                 ("covariance", np.float64, "Et"), ("covariance_trials", np.float64, "E")]
+
+
+class _SavedState(ctypes.Structure):
+    _fields_ = [(name, ctypes.c_void_p) for name, _, _ in _SAVED_FIELDS]
+
+
 class _Trace(ctypes.Structure):
     _fields_ = [("accepted", ctypes.c_void_p), ("llh_accepted", ctypes.c_void_p),
                 ("llh_proposed", ctypes.c_void_p), ("points", ctypes.c_void_p),
@@ -115,6 +127,10 @@ def load_library():
         "smcmc_step": (ci, [vp, ci, ci]),
         "smcmc_step_trace": (ci, [vp, ci, ci, ctypes.POINTER(_Trace)]),
         "smcmc_get": (ci, [vp, ci, vp, ctypes.c_size_t]),
+        "smcmc_save_state": (ci, [vp, ctypes.POINTER(_SavedState)]),
+        "smcmc_restore_state": (ci, [vp, ctypes.POINTER(_SavedState), vp]),
+        "smcmc_get_step_index": (ci, [vp, ctypes.POINTER(ctypes.c_uint32)]),
+        "smcmc_set_step_index": (ci, [vp, ctypes.c_uint32]),
         "smcmc_launch_count": (ctypes.c_int64, [vp]),
         "smcmc_pair_kernel_stats": (ci, [vp, ctypes.POINTER(cd), ctypes.POINTER(ctypes.c_int64), ci]),
         "smcmc_enable_kernel_timing": (ci, [vp, ci]),
@@ -136,7 +152,8 @@ EXPORTED_SYMBOLS = [
     "smcmc_fake_set_events", "smcmc_fake_set_data", "smcmc_fake_histograms",
     "smcmc_fake_counts", "smcmc_fake_filter_check",
     "smcmc_dummy_set_error", "smcmc_eval", "smcmc_start", "smcmc_step",
-    "smcmc_step_trace", "smcmc_get", "smcmc_launch_count",
+    "smcmc_step_trace", "smcmc_get", "smcmc_save_state", "smcmc_restore_state",
+    "smcmc_get_step_index", "smcmc_set_step_index", "smcmc_launch_count",
     "smcmc_pair_kernel_stats", "smcmc_enable_kernel_timing",
     "smcmc_measure_fp64_peak",
 ]
@@ -305,6 +322,35 @@ class Engine:
         out = np.zeros(shape, dt)
         self._check(self.lib.smcmc_get(self.h, fid, _ptr(out), out.nbytes))
         return out
+
+    # -- checkpoint / resume --------------------------------------------------------
+    def _saved_arrays(self):
+        E, n = self.chains, self.dim
+        shapes = {"E": (E,), "En": (E, n), "Et": (E, n * (n + 1) // 2)}
+        return {name: np.zeros(shapes[code], dt) for name, dt, code in _SAVED_FIELDS}
+
+    def save_state(self):
+        """SaveStep(true) for every chain: dict of the tree-branch values, plus
+        the stream position ("step_index")."""
+        arrays = self._saved_arrays()
+        st = _SavedState(**{k: v.ctypes.data for k, v in arrays.items()})
+        self._check(self.lib.smcmc_save_state(self.h, ctypes.byref(st)))
+        step = ctypes.c_uint32()
+        self._check(self.lib.smcmc_get_step_index(self.h, ctypes.byref(step)))
+        arrays["step_index"] = np.array([step.value], np.uint32)
+        return arrays
+
+    def restore_state(self, saved):
+        """Restore() + RestoreState() for every chain (call after start())."""
+        arrays = self._saved_arrays()
+        for k in arrays:
+            arrays[k][...] = np.asarray(saved[k]).reshape(arrays[k].shape)
+        st = _SavedState(**{k: v.ctypes.data for k, v in arrays.items()})
+        mismatch = np.zeros(self.chains, np.int32)
+        self._check(self.lib.smcmc_restore_state(self.h, ctypes.byref(st), _ptr(mismatch)))
+        if "step_index" in saved:
+            self._check(self.lib.smcmc_set_step_index(self.h, int(np.asarray(saved["step_index"]).reshape(-1)[0])))
+        return mismatch
 
     # -- instrumentation -----------------------------------------------------------
     def launch_count(self):

@@ -137,6 +137,21 @@ def make_chains():
                 c.set_correlation(i, j, float(rng.uniform(-0.2, 0.2)))
         c.set_correlation(2, 3, 2.0)     # clamped to the maximum correlation
     put("unit6_clamped", run_chain(cc.LLH_UNIT_GAUSS, 6, 3, 4, 1500, nasty))
+    # checkpoint / resume: 250 unsaved + 50 saved steps, SaveStep(), then a NEW
+    # sampler is started, Restore()d from that tree and run on (TSimpleMCMC.H:282-352)
+    a = cc.CpuChain("ref", cc.LLH_UNIT_GAUSS, 7, 31, 2)
+    a.start(np.full(7, 0.1))
+    first = a.step(250)
+    a.step_saved(50)
+    a.save_step()
+    sa = a.state()
+    b = cc.CpuChain("ref", cc.LLH_UNIT_GAUSS, 7, 31, 2)
+    b.start(np.zeros(7))
+    b.restore(a)
+    put("restore7", dict(b.step(200), before_accepted=first["accepted"],
+                         saved_scalars=np.array([sa[k] for k in cc.STATE_FIELDS]), saved_accepted=sa["accepted"],
+                         saved_center=sa["center"], saved_cov=sa["cov"],
+                         final_scalars=np.array([b.state()[k] for k in cc.STATE_FIELDS])))
     np.savez_compressed(os.path.join(HERE, "chains.npz"), **out)
     print("chains.npz: %d arrays" % len(out))
 

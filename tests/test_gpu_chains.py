@@ -199,3 +199,66 @@ def test_conditioning_ladder_keeps_chains_alive():
     assert np.all(np.abs(pts.mean(0)) < 0.15)
     assert np.all(np.abs(pts.var(0) - 1.0) < 0.25)
     assert np.all(eng.get("status") == 0)
+
+
+def test_restore_continues_the_reference_chain():
+    """smcmc_restore_state == Restore() + RestoreState(): a fresh engine that
+    adopts the state the reference saved after 300 steps continues with the
+    reference's accept/reject sequence (TSimpleMCMC.H:282-352, :1501-1610)."""
+    import smcmc_b200
+    from oracle import cpu_checkers as cc
+    want = golden_chain(golden("chains.npz"), "restore7")
+    sc = dict(zip(cc.STATE_FIELDS, want["saved_scalars"]))
+    n, E = 7, 3
+    cov = want["saved_cov"]
+    saved = {
+        "accepted": np.tile(want["saved_accepted"], (E, 1)), "log_likelihood": np.full(E, sc["accepted_llh"]),
+        "total_steps": np.full(E, sc["total_steps"]), "step_rms": np.full(E, sc["step_rms"]),
+        "trials": np.full(E, sc["trials"]), "successes": np.full(E, sc["successes"]),
+        "next_update": np.full(E, sc["next_update"]), "acceptance": np.full(E, sc["acceptance"]),
+        "acceptance_trials": np.full(E, sc["acceptance_trials"]), "sigma": np.full(E, sc["sigma"]),
+        "central_point": np.tile(want["saved_center"], (E, 1)), "central_point_trials": np.full(E, sc["center_trials"]),
+        "covariance": np.tile(np.array([cov[i, j] for i in range(n) for j in range(i + 1)]), (E, 1)),
+        "covariance_trials": np.full(E, sc["covariance_trials"]), "step_index": np.array([300]),
+    }
+    eng = smcmc_b200.Engine(smcmc_b200.LLH_UNIT_GAUSS, n, E, seed=31, chain_offset=0)
+    eng.start(np.zeros(n))
+    mismatch = eng.restore_state(saved)
+    assert not mismatch.any()
+    tr = eng.step_trace(200)
+    c = 2                                              # the golden chain id
+    assert np.array_equal(tr["accepted"][:, c], want["accepted"])
+    assert close(tr["points"][:, c], want["x"])
+    assert close(tr["sigma"][:, c], want["sigma"])
+    fin = dict(zip(cc.STATE_FIELDS, want["final_scalars"]))
+    assert eng.get("total_steps")[c] == fin["total_steps"] == 500
+    assert eng.get("llh_calls")[c] == fin["llh_calls"]
+    assert eng.get("trials")[c] == fin["trials"] and eng.get("next_update")[c] == fin["next_update"]
+
+
+def test_save_then_restore_round_trip():
+    """Engine state saved after 150 steps and restored into a new engine gives
+    the same continuation as the uninterrupted run (frozen step size: bit for bit)."""
+    import smcmc_b200
+    from smcmc_b200 import binding
+    n, E = 6, 40
+
+    def fresh():
+        e = smcmc_b200.Engine(smcmc_b200.LLH_UNIT_GAUSS, n, E, seed=8)
+        e.prop_set(binding.PROP_ACCEPTANCE_RIGIDITY, -1.0)
+        e.prop_set(binding.PROP_SIGMA, 0.6)
+        e.prop_set(binding.PROP_COVARIANCE_DEWEIGHT, 0.0)      # UpdateProposal at restore must not deweight
+        e.prop_set(binding.PROP_ACCEPTANCE_DEWEIGHT, 0.0)
+        e.start(np.zeros(n))
+        return e
+    a = fresh()
+    a.step(150)
+    saved = a.save_state()
+    assert saved["step_index"][0] == 150 and np.all(saved["total_steps"] == 150)
+    a.update_proposal()                                         # what Restore() does on the other side
+    cont = a.step_trace(100, want=("accepted", "points"))
+    b = fresh()
+    b.restore_state(saved)
+    again = b.step_trace(100, want=("accepted", "points"))
+    assert np.array_equal(cont["accepted"], again["accepted"])
+    assert np.array_equal(cont["points"], again["points"])

@@ -47,7 +47,7 @@ def _worker(rank, world, uid, out_dir):
     # --- pooled adaptation over chain shards: rank r owns chains [r*256, (r+1)*256)
     n = 6
     pe = smcmc_b200.Engine(smcmc_b200.LLH_UNIT_GAUSS, n, 256, seed=9, device=rank, chain_offset=rank * 256)
-    uid2 = uid[:]          # a second communicator needs its own id: reuse via split is not exposed, so
+    # a second engine needs its own communicator, hence its own unique id
     pe.prop_set(binding.PROP_POOLED_EVERY, 4)
     pe.comm_init(_SECOND_ID[0], world, rank, event_group=1)
     pe.start(np.zeros(n))

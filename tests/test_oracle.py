@@ -123,3 +123,25 @@ def test_gaussian_target_statistics(checkers):
     cov = np.cov(x.T)
     assert np.all(np.abs(np.diag(cov) - 1.0) < 0.1)
     assert np.all(np.abs(cov - np.diag(np.diag(cov))) < 0.08)
+
+
+@pytest.mark.parametrize("which", ["orc", "ref"])
+def test_restore_matches_golden(checkers, have_ref, which):
+    """Restore() into a fresh sampler continues the chain exactly as the
+    reference build did (TSimpleMCMC.H:282-352, :1501-1610)."""
+    if which == "ref" and not have_ref:
+        pytest.skip("reference-backed checker not built here")
+    want = golden_chain(golden("chains.npz"), "restore7")
+    cc = checkers
+    a = cc.CpuChain(which, cc.LLH_UNIT_GAUSS, 7, 31, 2)
+    a.start(np.full(7, 0.1))
+    assert np.array_equal(a.step(250)["accepted"], want["before_accepted"])
+    a.step_saved(50)
+    a.save_step()
+    b = cc.CpuChain(which, cc.LLH_UNIT_GAUSS, 7, 31, 2)
+    b.start(np.zeros(7))
+    b.restore(a)
+    tr = b.step(200)
+    for k in ("accepted", "llh_accepted", "llh_proposed", "x", "sigma"):
+        assert np.array_equal(tr[k], want[k]), k
+    assert np.array_equal(np.array([b.state()[k] for k in cc.STATE_FIELDS]), want["final_scalars"])
