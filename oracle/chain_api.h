@@ -94,6 +94,36 @@ typedef struct orc_event {
 ORC_DECLARE(ref_)
 ORC_DECLARE(orc_)
 
+/* sMCMC::TSimpleHMC<L, G> (TSimpleHMC.H:119-973), one chain per handle, same
+ * injected stream: step s consumes slots 0..n-1 (momentum refresh), n (epsilon
+ * jitter) and n+1 (accept) in the order the reference calls gRandom
+ * (TSimpleHMC.H:568, :297, :347).  with_gradient selects
+ * TSimpleHMC<L, L> (user gradient) or TSimpleHMC<L> (finite differences). */
+enum {
+    ORC_HMC_ALPHA = 0,          /* SetAlpha        :175 */
+    ORC_HMC_MEAN_EPSILON = 1,   /* SetMeanEpsilon  :181 */
+    ORC_HMC_LEAPFROG = 2        /* SetLeapFrog     :190 */
+};
+enum {
+    ORC_HS_ACCEPTANCE = 0, ORC_HS_MEAN_EPSILON, ORC_HS_LEAPFROG, ORC_HS_REVERSAL_LEN,
+    ORC_HS_ACCEPTED_POTENTIAL, ORC_HS_PROPOSED_POTENTIAL, ORC_HS_CENTRAL_POTENTIAL,
+    ORC_HS_POTENTIAL_COUNT, ORC_HS_GRADIENT_COUNT, ORC_HS_STEP_COUNT, ORC_HS_COV_TRIALS,
+    ORC_HS_AVERAGE_TRIALS, ORC_HS_EST_COV_TRACE, ORC_HS_CUR_COV_TRACE, ORC_HS_ORBIT_LENGTH,
+    ORC_HS_STEPS_REMAINING, ORC_HS_STEPS_SINCE_UPDATE, ORC_HS_COUNT
+};
+#define ORC_DECLARE_HMC(P)                                                            \
+    void* P##hmc_create(int kind, int dim, int with_gradient, uint64_t seed, uint32_t chain); \
+    void P##hmc_destroy(void* h);                                                     \
+    int P##hmc_set_error_matrix(void* h, const double* e, int n);                     \
+    int P##hmc_set(void* h, int field, double value);                                 \
+    int P##hmc_start(void* h, const double* x0);                                      \
+    int P##hmc_step(void* h, int nsteps, int gradient_type, double* potential,        \
+                    double* x, double* epsilon, int32_t* leapfrog);                   \
+    int P##hmc_get_state(void* h, double* scalars, double* accepted, double* momentum, \
+                         double* central, double* average, double* covariance, double* error);
+ORC_DECLARE_HMC(ref_)
+ORC_DECLARE_HMC(orc_)
+
 #ifdef __cplusplus
 }
 #endif

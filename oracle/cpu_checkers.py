@@ -94,6 +94,19 @@ def load(which):
         fn = getattr(lib, p + name)
         fn.restype = res
         fn.argtypes = args
+    hsig = {
+        "hmc_create": (vp, [ci, ci, ci, ctypes.c_uint64, ctypes.c_uint32]),
+        "hmc_destroy": (None, [vp]),
+        "hmc_set_error_matrix": (ci, [vp, vp, ci]),
+        "hmc_set": (ci, [vp, ci, cd]),
+        "hmc_start": (ci, [vp, vp]),
+        "hmc_step": (ci, [vp, ci, ci, vp, vp, vp, vp]),
+        "hmc_get_state": (ci, [vp] * 8),
+    }
+    for name, (res, args) in hsig.items():
+        fn = getattr(lib, p + name)
+        fn.restype = res
+        fn.argtypes = args
     if which == "orc":
         lib.orc_chain_fake_counts.restype = ci
         lib.orc_chain_fake_counts.argtypes = [vp, vp, vp]
@@ -222,6 +235,70 @@ class CpuChain:
         x = np.ascontiguousarray(x, dtype=np.float64)
         out = np.zeros(450, np.uint32)
         self._check(self.lib.orc_chain_fake_counts(self.h, _ptr(x), _ptr(out)))
+        return out
+
+
+HMC_ALPHA, HMC_MEAN_EPSILON, HMC_LEAPFROG = range(3)
+HMC_STATE_FIELDS = ["acceptance", "mean_epsilon", "leapfrog", "reversal_len", "accepted_potential",
+                    "proposed_potential", "central_potential", "potential_count", "gradient_count",
+                    "step_count", "cov_trials", "average_trials", "est_cov_trace", "cur_cov_trace",
+                    "orbit_length", "steps_remaining", "steps_since_update"]
+
+
+class CpuHmc:
+    """One TSimpleHMC chain of one checker."""
+
+    def __init__(self, which, kind, dim, with_gradient, seed, chain):
+        self.lib = load(which)
+        self.p = which + "_"
+        self.dim = dim
+        self.h = self._f("hmc_create")(kind, dim, 1 if with_gradient else 0, seed, chain)
+        if not self.h:
+            raise RuntimeError(self._f("last_error")().decode())
+
+    def _f(self, name):
+        return getattr(self.lib, self.p + name)
+
+    def _check(self, rc):
+        if rc < 0:
+            raise RuntimeError(self._f("last_error")().decode())
+        return rc
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._f("hmc_destroy")(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def set_error_matrix(self, e):
+        e = np.ascontiguousarray(e, dtype=np.float64)
+        self._check(self._f("hmc_set_error_matrix")(self.h, _ptr(e), e.shape[0]))
+
+    def set(self, field, value):
+        self._check(self._f("hmc_set")(self.h, field, float(value)))
+
+    def start(self, x0):
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        return self._check(self._f("hmc_start")(self.h, _ptr(x0)))
+
+    def step(self, nsteps, gradient_type=0):
+        pot = np.zeros(nsteps)
+        x = np.zeros((nsteps, self.dim))
+        eps = np.zeros(nsteps)
+        lf = np.zeros(nsteps, np.int32)
+        self._check(self._f("hmc_step")(self.h, nsteps, gradient_type, _ptr(pot), _ptr(x), _ptr(eps), _ptr(lf)))
+        return {"potential": pot, "x": x, "epsilon": eps, "leapfrog": lf}
+
+    def state(self):
+        n = self.dim
+        s = np.zeros(len(HMC_STATE_FIELDS))
+        acc, mom, cen, avg = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n)
+        cov, err = np.zeros((n, n)), np.zeros((n, n))
+        self._f("hmc_get_state")(self.h, _ptr(s), _ptr(acc), _ptr(mom), _ptr(cen), _ptr(avg), _ptr(cov), _ptr(err))
+        out = dict(zip(HMC_STATE_FIELDS, s))
+        out.update(accepted=acc, momentum=mom, central=cen, average=avg, covariance=cov, error=err)
         return out
 
 

@@ -45,6 +45,8 @@ using namespace sMCMC;  // example/ predates the namespace
 #include "THorrificLogLikelihood.H"
 #include "TAsymLogLikelihood.H"
 #include "example/FakeLikelihood.H"
+#define HMC_DEBUG_LEVEL -1
+#include "TSimpleHMC.H"
 #undef private
 #undef protected
 
@@ -426,6 +428,120 @@ long ref_fake_generate(unsigned long seed, int dataSignal, int dataBackground,
     }
     if (outExposure) *outExposure = like.Corrections.ExposureRatio;
     return (long)like.SimulatedSample.size();
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// TSimpleHMC
+// ---------------------------------------------------------------------------
+namespace {
+struct HmcBase {
+    InjectedRandom rng;
+    uint32_t step;
+    int dim;
+    HmcBase(uint64_t seed, uint32_t chain, int d) : rng(seed, chain), step(0), dim(d) {}
+    virtual ~HmcBase() {}
+    virtual void Set(int field, double v) = 0;
+    virtual void Start(const Vector& x) = 0;
+    virtual void Step(int type) = 0;
+    virtual void State(double* s, double* acc, double* mom, double* cen, double* avg, double* cov, double* err) = 0;
+    virtual double AcceptedPotential() = 0;
+    virtual const Vector& Accepted() = 0;
+    virtual double MeanEpsilon() = 0;
+    virtual int LeapFrog() = 0;
+};
+template <class L, class G>
+struct Hmc : public HmcBase {
+    sMCMC::TSimpleHMC<L, G> hmc;
+    Hmc(uint64_t seed, uint32_t chain, int d) : HmcBase(seed, chain, d), hmc(NULL) {}
+    void Set(int field, double v) {
+        if (field == ORC_HMC_ALPHA) hmc.SetAlpha(v);
+        else if (field == ORC_HMC_MEAN_EPSILON) hmc.SetMeanEpsilon(v);
+        else if (field == ORC_HMC_LEAPFROG) hmc.SetLeapFrog((int)v);
+    }
+    void Start(const Vector& x) { hmc.Start(x, false); }
+    void Step(int type) { hmc.Step(false, type); }
+    double AcceptedPotential() { return hmc.fAcceptedPotential; }
+    const Vector& Accepted() { return hmc.fAccepted; }
+    double MeanEpsilon() { return hmc.fMeanEpsilon; }
+    int LeapFrog() { return hmc.fLeapFrogSteps; }
+    void State(double* s, double* acc, double* mom, double* cen, double* avg, double* cov, double* err) {
+        const int n = dim;
+        if (s) {
+            s[ORC_HS_ACCEPTANCE] = hmc.fCurrentAcceptance;
+            s[ORC_HS_MEAN_EPSILON] = hmc.fMeanEpsilon;
+            s[ORC_HS_LEAPFROG] = hmc.fLeapFrogSteps;
+            s[ORC_HS_REVERSAL_LEN] = hmc.fReversalLen;
+            s[ORC_HS_ACCEPTED_POTENTIAL] = hmc.fAcceptedPotential;
+            s[ORC_HS_PROPOSED_POTENTIAL] = hmc.fProposedPotential;
+            s[ORC_HS_CENTRAL_POTENTIAL] = hmc.fCentralPotential;
+            s[ORC_HS_POTENTIAL_COUNT] = hmc.fPotentialCount;
+            s[ORC_HS_GRADIENT_COUNT] = hmc.fPotentialGradientCount;
+            s[ORC_HS_STEP_COUNT] = hmc.fStepCount;
+            s[ORC_HS_COV_TRIALS] = hmc.fCovarianceTrials;
+            s[ORC_HS_AVERAGE_TRIALS] = hmc.fAveragePointTrials;
+            s[ORC_HS_EST_COV_TRACE] = hmc.fEstimatedCovarianceTrace;
+            s[ORC_HS_CUR_COV_TRACE] = hmc.fCurrentCovarianceTrace;
+            s[ORC_HS_ORBIT_LENGTH] = hmc.fEstimatedOrbitLength;
+            s[ORC_HS_STEPS_REMAINING] = hmc.fStepsRemaining;
+            s[ORC_HS_STEPS_SINCE_UPDATE] = hmc.fStepsSinceUpdate;
+        }
+        if (acc) std::copy(hmc.fAccepted.begin(), hmc.fAccepted.end(), acc);
+        if (mom) std::copy(hmc.fAcceptedMomentum.begin(), hmc.fAcceptedMomentum.end(), mom);
+        if (cen) std::copy(hmc.fCentralPoint.begin(), hmc.fCentralPoint.end(), cen);
+        if (avg) std::copy(hmc.fAveragePoint.begin(), hmc.fAveragePoint.end(), avg);
+        if (cov) std::copy(hmc.fEstimatedCovariance.GetMatrixArray(), hmc.fEstimatedCovariance.GetMatrixArray() + (size_t)n * n, cov);
+        if (err) std::copy(hmc.fEstimatedError.GetMatrixArray(), hmc.fEstimatedError.GetMatrixArray() + (size_t)n * n, err);
+    }
+};
+HmcBase* HH(void* h) { return static_cast<HmcBase*>(h); }
+}  // namespace
+
+extern "C" {
+
+void* ref_hmc_create(int kind, int dim, int withGradient, uint64_t seed, uint32_t chain) {
+    if (kind == ORC_LLH_DUMMY) {
+        if (dim != 100) { gLastError = "reference TDummyLogLikelihood is 100-dim"; return 0; }
+        if (TDummyLogLikelihood::Error.GetNrows() != 100) ref_dummy_matrices(0, 0);
+        if (withGradient) return new Hmc<TDummyLogLikelihood, TDummyLogLikelihood>(seed, chain, 100);
+        return new Hmc<TDummyLogLikelihood, SimpleHMCInvalidGradient>(seed, chain, 100);
+    }
+    if (kind == ORC_LLH_UNIT_GAUSS) return new Hmc<UnitGaussLikelihood, SimpleHMCInvalidGradient>(seed, chain, dim);
+    if (kind == ORC_LLH_HORRIFIC && dim == 75) return new Hmc<THorrificLogLikelihood, THorrificLogLikelihood>(seed, chain, 75);
+    gLastError = "unsupported HMC likelihood";
+    return 0;
+}
+void ref_hmc_destroy(void* h) { delete HH(h); }
+int ref_hmc_set_error_matrix(void*, const double*, int) { gLastError = "the reference builds its own error matrix"; return -1; }
+int ref_hmc_set(void* h, int field, double v) { HH(h)->Set(field, v); return 0; }
+int ref_hmc_start(void* h, const double* x0) {
+    HmcBase* c = HH(h);
+    return Guard([&]() {
+        gRandom = &c->rng;
+        Vector x(x0, x0 + c->dim);
+        c->Start(x);
+        return 1;
+    });
+}
+int ref_hmc_step(void* h, int nsteps, int type, double* potential, double* x, double* epsilon, int32_t* leapfrog) {
+    HmcBase* c = HH(h);
+    return Guard([&]() {
+        gRandom = &c->rng;
+        for (int s = 0; s < nsteps; ++s) {
+            c->rng.Begin(c->step++);
+            c->Step(type);
+            if (potential) potential[s] = c->AcceptedPotential();
+            if (epsilon) epsilon[s] = c->MeanEpsilon();
+            if (leapfrog) leapfrog[s] = c->LeapFrog();
+            if (x) std::copy(c->Accepted().begin(), c->Accepted().end(), x + (size_t)s * c->dim);
+        }
+        return 0;
+    });
+}
+int ref_hmc_get_state(void* h, double* s, double* acc, double* mom, double* cen, double* avg, double* cov, double* err) {
+    HH(h)->State(s, acc, mom, cen, avg, cov, err);
+    return 0;
 }
 
 }  // extern "C"

@@ -866,3 +866,401 @@ int orc_chain_fake_counts(void* h, const double* x, uint32_t* out450) {
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// TSimpleHMC (TSimpleHMC.H:119-973), flat-array restatement.
+// ---------------------------------------------------------------------------
+namespace {
+
+// TMatrixD::Invert as restated by the shim (Gauss-Jordan, partial pivoting).
+void InvertInPlace(std::vector<double>& m, int n) {
+    std::vector<double> a(m), inv((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i) inv[(size_t)i * n + i] = 1.0;
+    for (int k = 0; k < n; ++k) {
+        int piv = k;
+        double best = std::abs(a[(size_t)k * n + k]);
+        for (int i = k + 1; i < n; ++i) {
+            double v = std::abs(a[(size_t)i * n + k]);
+            if (v > best) { best = v; piv = i; }
+        }
+        if (piv != k) {
+            for (int j = 0; j < n; ++j) {
+                std::swap(a[(size_t)k * n + j], a[(size_t)piv * n + j]);
+                std::swap(inv[(size_t)k * n + j], inv[(size_t)piv * n + j]);
+            }
+        }
+        double p = a[(size_t)k * n + k];
+        for (int j = 0; j < n; ++j) {
+            a[(size_t)k * n + j] /= p;
+            inv[(size_t)k * n + j] /= p;
+        }
+        for (int i = 0; i < n; ++i) {
+            if (i == k) continue;
+            double f = a[(size_t)i * n + k];
+            if (f == 0.0) continue;
+            for (int j = 0; j < n; ++j) {
+                a[(size_t)i * n + j] -= f * a[(size_t)k * n + j];
+                inv[(size_t)i * n + j] -= f * inv[(size_t)k * n + j];
+            }
+        }
+    }
+    m.swap(inv);
+}
+
+struct OrcHmc {
+    Likelihood like;
+    bool withGradient = false;
+    int n = 0;
+    uint64_t seed = 0;
+    uint32_t chain = 0, step = 0, slot = 0;
+    // TSimpleHMC members
+    int stepCount = 0, potentialCount = 0, gradientCount = 0, leapFrogSteps = 10;
+    double alpha = 0.0, covWindow = 1000000;
+    double currentAcceptance = 0, targetAcceptance = 0, meanEpsilon = 0, reversalLen = 0;
+    std::vector<double> accepted, acceptedMomentum, proposed, proposedMomentum, central, average;
+    double acceptedPotential = 0, proposedPotential = 0, centralPotential = 0;
+    double averageTrials = 0, covTrials = 0, orbitLength = 0, estCovTrace = 0, curCovTrace = 0;
+    std::vector<double> estCov, exxt, estErr;
+    int stepsRemaining = 0, stepsSinceUpdate = 0;
+
+    double Rndm() { return smcmc_uniform(seed, chain, step, slot++, SMCMC_STREAM_STEP); }
+    double Gaus() { return 0.0 + 1.0 * smcmc_normal(seed, chain, step, slot++, SMCMC_STREAM_STEP); }
+
+    double Potential(const std::vector<double>& x) {                  // :411-414
+        ++potentialCount;
+        return -like(x.data());
+    }
+    // user gradient of log(likelihood): TDummyLogLikelihood.H:34-42
+    bool UserGradient(std::vector<double>& g, const std::vector<double>& p) {
+        if (!withGradient || like.kind != ORC_LLH_DUMMY) return false;
+        for (int i = 0; i < n; ++i) {
+            g[i] = 0.0;
+            for (int j = 0; j < n; ++j) g[i] -= like.error[(size_t)i * n + j] * p[j];
+        }
+        return true;
+    }
+    void FiniteDifference(std::vector<double>& grad, const std::vector<double>& point) {   // :417-444
+        std::vector<double> work(n);
+        for (int i = 0; i < n; ++i) {
+            for (int j = 0; j < n; ++j) work[j] = point[j];
+            double du = 0.01;
+            work[i] -= du;
+            double u1 = Potential(work);
+            work[i] += 2.0 * du;
+            double u2 = Potential(work);
+            grad[i] = 0.5 * (u2 - u1) / du;
+        }
+    }
+    void Covariant(std::vector<double>& grad, const std::vector<double>& point) {          // :447-454
+        for (int i = 0; i < n; ++i) {
+            grad[i] = 0.0;
+            for (int j = 0; j < n; ++j) grad[i] += estErr[(size_t)i * n + j] * (point[j] - average[j]);
+        }
+    }
+    bool PotentialGradient(std::vector<double>& grad, const std::vector<double>& point, int type) {   // :467-532
+        ++gradientCount;
+        switch (type) {
+        default:
+        case 0:
+        case 1:
+            if (UserGradient(grad, point)) {
+                for (int i = 0; i < n; ++i) grad[i] = -grad[i];
+                return true;
+            }
+            FiniteDifference(grad, point);
+            return true;
+        case 2: Covariant(grad, point); return true;
+        case 3: FiniteDifference(grad, point); return true;
+        case 4:
+            if (!UserGradient(grad, point)) { gLastError = "user gradient required"; return false; }
+            for (int i = 0; i < n; ++i) grad[i] = -grad[i];
+            return true;
+        case 5:
+            for (int i = 0; i < n; ++i) grad[i] = 0.0;
+            return true;
+        }
+    }
+    double Kinetic(const std::vector<double>& m) {                    // :535-542
+        double ke = 0.0;
+        for (int i = 0; i < n; ++i) { double p = m[i]; ke += p * p / 2.0; }
+        return ke;
+    }
+    void ProposeMomentum(std::vector<double>& pNew, const std::vector<double>& m) {   // :554-570
+        if (alpha >= 1.0) {
+            alpha = std::max(1.0, alpha);
+            for (int i = 0; i < n; ++i) pNew[i] = m[i] / alpha;
+            return;
+        }
+        if (alpha < 0.0) alpha = 0.0;
+        for (int i = 0; i < n; ++i) pNew[i] = alpha * m[i] + std::sqrt(1.0 - alpha * alpha) * Gaus();
+    }
+    int LeapFrog(std::vector<double>& qNew, std::vector<double>& pNew, const std::vector<double>& position,
+                 double epsilon, int steps, int type) {               // :582-651
+        qNew = position;
+        std::vector<double> momentum = pNew, grad(n);
+        int status = 1;
+        if (steps < 1) {
+            for (int j = 0; j < n; ++j) qNew[j] = qNew[j] + epsilon * (momentum[j] + pNew[j]) / 2.0;
+            return status;
+        }
+        if (!PotentialGradient(grad, qNew, type)) return -1;
+        for (int j = 0; j < n; ++j) pNew[j] = pNew[j] - epsilon * grad[j] / 2.0;
+        for (int i = 0; i < steps - 1; ++i) {
+            for (int j = 0; j < n; ++j) qNew[j] = qNew[j] + epsilon * pNew[j];
+            if (!PotentialGradient(grad, qNew, type)) return -1;
+            for (int j = 0; j < n; ++j) pNew[j] = pNew[j] - epsilon * grad[j];
+            double inner = 0.0;
+            for (int j = 0; j < n; ++j) inner += pNew[j] * momentum[j];
+            if (inner >= 0.0) continue;
+            status = 2;
+        }
+        for (int j = 0; j < n; ++j) qNew[j] = qNew[j] + epsilon * pNew[j];
+        if (!PotentialGradient(grad, qNew, type)) return -1;
+        for (int j = 0; j < n; ++j) pNew[j] = pNew[j] - epsilon * grad[j] / 2.0;
+        return status;
+    }
+    void UpdateCovariance() {                                         // :665-695
+        ++stepsSinceUpdate;
+        --stepsRemaining;
+        for (int i = 0; i < n; ++i) {
+            double v = average[i];
+            v *= averageTrials;
+            v += accepted[i];
+            v /= averageTrials + 1.0;
+            average[i] = v;
+        }
+        averageTrials = std::min(covWindow, averageTrials + 1.0);
+        for (int i = 0; i < n; ++i) {
+            for (int j = 0; j < i + 1; ++j) {
+                double v = exxt[(size_t)i * n + j];
+                v *= covTrials;
+                v += accepted[i] * accepted[j];
+                v /= covTrials + 1.0;
+                exxt[(size_t)i * n + j] = exxt[(size_t)j * n + i] = v;
+                double c = v - average[i] * average[j];
+                estCov[(size_t)i * n + j] = estCov[(size_t)j * n + i] = c;
+            }
+        }
+        covTrials = std::min(covWindow, covTrials + 1.0);
+    }
+    void UpdateErrorMatrix() {                                        // :703-858
+        if (!leapFrogSteps) return;
+        if (covTrials < 2 * n) return;
+        curCovTrace = 0.0;
+        for (int i = 0; i < n; ++i) curCovTrace += std::abs(estCov[(size_t)i * n + i]);
+        double change = std::abs(curCovTrace - estCovTrace);
+        bool doIt = false;
+        if (stepsRemaining < 0) doIt = true;
+        if (stepsSinceUpdate > 2.0 * n && change > 0.01 * estCovTrace) doIt = true;
+        if (!doIt) return;
+        double aPot = Potential(average);                             // :729-738
+        if (aPot < centralPotential) { central = average; centralPotential = aPot; }
+        stepsRemaining = 2 * n + stepCount;                           // :758-759
+        stepsSinceUpdate = 0;
+        double maxScale = 0.0, minScale = 1E+20;                      // :762-807
+        do {
+            std::vector<double> vec, val;
+            SymEigen(estCov, n, vec, val);
+            bool positiveDefinite = true;
+            for (int i = 0; i < n; ++i) {
+                double eigen = val[i];
+                if (maxScale < std::abs(eigen)) maxScale = std::abs(eigen);
+                if (minScale > std::abs(eigen)) minScale = std::abs(eigen);
+                if (eigen < 0) positiveDefinite = false;
+            }
+            if (positiveDefinite) break;
+            for (int i = 0; i < n; ++i) {
+                double r = estCovTrace * 1E-6;
+                r /= n;
+                r = std::abs(r);
+                if (estCov[(size_t)i * n + i] < r) estCov[(size_t)i * n + i] = r;
+                for (int j = i + 1; j < n; ++j) {
+                    estCov[(size_t)i * n + j] = 0.0;
+                    estCov[(size_t)j * n + i] = 0.0;
+                }
+            }
+        } while (true);
+        curCovTrace = 0.0;                                            // :813-817
+        for (int i = 0; i < n; ++i) curCovTrace += std::abs(estCov[(size_t)i * n + i]);
+        estCovTrace = curCovTrace;
+        maxScale = std::sqrt(maxScale);                               // :820-825
+        if (maxScale < 0.1) maxScale = 0.1;
+        minScale = std::sqrt(minScale);
+        if (minScale < 0.01) minScale = 0.01;
+        orbitLength = 2.0 * 3.14 * maxScale;                          // :828
+        if (meanEpsilon > 0) {                                        // :833-837
+            meanEpsilon = 0.2 * maxScale;
+            if (meanEpsilon > 0.5 * minScale) meanEpsilon = 0.5 * minScale;
+            if (meanEpsilon < 0.05 * maxScale) meanEpsilon = 0.05 * maxScale;
+        }
+        if (leapFrogSteps > 0) {                                      // :839-847
+            double targetLength = 0.4 * orbitLength;
+            leapFrogSteps = (int)(targetLength / std::abs(meanEpsilon));
+            leapFrogSteps = 2 * (leapFrogSteps / 2 + 1);
+            if (leapFrogSteps > 3 * n) leapFrogSteps = 3 * n;
+            if (meanEpsilon > 0) meanEpsilon = targetLength / leapFrogSteps;
+        }
+        estErr = estCov;                                              // :849-850
+        InvertInPlace(estErr, n);
+    }
+    void Start(const double* x0) {                                    // :210-269
+        stepCount = 0;
+        proposed.assign(n, 0.0);
+        proposedMomentum.assign(n, 0.0);
+        accepted.assign(x0, x0 + n);
+        acceptedMomentum.assign(n, 0.0);
+        central.assign(n, 0.0);
+        average.assign(n, 0.0);
+        acceptedPotential = Potential(accepted);
+        proposed = accepted;
+        proposedPotential = acceptedPotential;
+        meanEpsilon = 0.05;
+        reversalLen = 0.0;
+        targetAcceptance = 0.65;
+        currentAcceptance = targetAcceptance;
+        central = accepted;
+        centralPotential = acceptedPotential;
+        average = accepted;
+        averageTrials = 0.0;
+        estCov.assign((size_t)n * n, 0.0);
+        exxt.assign((size_t)n * n, 0.0);
+        covTrials = 0;
+        for (int i = 0; i < n; ++i) estCov[(size_t)i * n + i] = 1.0;
+        estErr = estCov;
+        InvertInPlace(estErr, n);
+        estCovTrace = n;
+        stepsRemaining = 0;
+        stepsSinceUpdate = 0;
+    }
+    int Step(int type) {                                              // :279-401
+        slot = 0;
+        ++stepCount;
+        ProposeMomentum(proposedMomentum, acceptedMomentum);
+        double initialKinetic = Kinetic(proposedMomentum);
+        double lo = 0.9 * std::abs(meanEpsilon), hi = 1.1 * std::abs(meanEpsilon);
+        double epsilon = lo + (hi - lo) * Rndm();
+        int okLeap = LeapFrog(proposed, proposedMomentum, accepted, epsilon, std::abs(leapFrogSteps), type);
+        if (okLeap < 0) return -1;
+        if (leapFrogSteps > 0) {                                      // :302-323
+            if (okLeap != 2) {
+                if (meanEpsilon > 0 && reversalLen > meanEpsilon) {
+                    double targetEpsilon = reversalLen / 8.0;
+                    double deltaEpsilon = targetEpsilon - meanEpsilon;
+                    if (deltaEpsilon > 0.0) meanEpsilon += 0.1 * deltaEpsilon;
+                }
+                if (leapFrogSteps < 50) leapFrogSteps += 1;
+            } else {
+                if (reversalLen < meanEpsilon) reversalLen = std::abs(leapFrogSteps * epsilon);
+                else {
+                    reversalLen = 0.95 * reversalLen;
+                    reversalLen += 0.05 * std::abs(leapFrogSteps * epsilon);
+                }
+                if (leapFrogSteps > 3) leapFrogSteps -= 1;
+                if (meanEpsilon > 0) meanEpsilon *= 0.99;
+            }
+        }
+        double proposedKinetic = Kinetic(proposedMomentum);           // :326-334
+        proposedPotential = Potential(proposed);
+        double proposedH = proposedPotential + proposedKinetic;
+        double acceptedH = acceptedPotential + initialKinetic;
+        if (okLeap && std::isfinite(proposedPotential)) {             // :336-344
+            UpdateCovariance();
+            UpdateErrorMatrix();
+        } else {
+            if (meanEpsilon > 0) meanEpsilon = 0.3 * meanEpsilon;
+        }
+        double delta = proposedH - acceptedH;                         // :346-387
+        double trial = -std::log(1.0 * Rndm());
+        if (delta > trial || !std::isfinite(delta)) {
+            for (int i = 0; i < n; ++i) acceptedMomentum[i] = -acceptedMomentum[i];
+            currentAcceptance = (currentAcceptance * 4999.0) / 5000.0;
+        } else {
+            for (int i = 0; i < n; ++i) {
+                accepted[i] = proposed[i];
+                acceptedMomentum[i] = proposedMomentum[i];
+            }
+            acceptedPotential = proposedPotential;
+            currentAcceptance = (currentAcceptance * 4999.0 + 1.0) / 5000.0;
+        }
+        if (acceptedPotential < centralPotential) {                   // :393-395
+            central = accepted;
+            centralPotential = acceptedPotential;
+        }
+        ++step;
+        return 0;
+    }
+};
+OrcHmc* HH(void* h) { return static_cast<OrcHmc*>(h); }
+}  // namespace
+
+extern "C" {
+
+void* orc_hmc_create(int kind, int dim, int withGradient, uint64_t seed, uint32_t chain) {
+    if (kind < ORC_LLH_UNIT_GAUSS || kind > ORC_LLH_ASYM || dim < 1) { gLastError = "unsupported HMC likelihood"; return 0; }
+    OrcHmc* c = new OrcHmc;
+    c->n = dim;
+    c->like.kind = kind;
+    c->like.dim = dim;
+    c->withGradient = withGradient != 0;
+    c->seed = seed;
+    c->chain = chain;
+    return c;
+}
+void orc_hmc_destroy(void* h) { delete HH(h); }
+int orc_hmc_set_error_matrix(void* h, const double* e, int n) {
+    OrcHmc* c = HH(h);
+    if (c->like.kind != ORC_LLH_DUMMY || n != c->n) { gLastError = "error matrix shape"; return -1; }
+    c->like.error.assign(e, e + (size_t)n * n);
+    return 0;
+}
+int orc_hmc_set(void* h, int field, double v) {
+    OrcHmc* c = HH(h);
+    if (field == ORC_HMC_ALPHA) c->alpha = v;
+    else if (field == ORC_HMC_MEAN_EPSILON) c->meanEpsilon = v;
+    else if (field == ORC_HMC_LEAPFROG) c->leapFrogSteps = -(int)v;      // SetLeapFrog stores -i (:190)
+    else { gLastError = "unknown field"; return -1; }
+    return 0;
+}
+int orc_hmc_start(void* h, const double* x0) { HH(h)->Start(x0); return 1; }
+int orc_hmc_step(void* h, int nsteps, int type, double* potential, double* x, double* epsilon, int32_t* leapfrog) {
+    OrcHmc* c = HH(h);
+    for (int s = 0; s < nsteps; ++s) {
+        if (c->Step(type) < 0) return -1;
+        if (potential) potential[s] = c->acceptedPotential;
+        if (epsilon) epsilon[s] = c->meanEpsilon;
+        if (leapfrog) leapfrog[s] = c->leapFrogSteps;
+        if (x) std::copy(c->accepted.begin(), c->accepted.end(), x + (size_t)s * c->n);
+    }
+    return 0;
+}
+int orc_hmc_get_state(void* h, double* s, double* acc, double* mom, double* cen, double* avg, double* cov, double* err) {
+    OrcHmc* c = HH(h);
+    if (s) {
+        s[ORC_HS_ACCEPTANCE] = c->currentAcceptance;
+        s[ORC_HS_MEAN_EPSILON] = c->meanEpsilon;
+        s[ORC_HS_LEAPFROG] = c->leapFrogSteps;
+        s[ORC_HS_REVERSAL_LEN] = c->reversalLen;
+        s[ORC_HS_ACCEPTED_POTENTIAL] = c->acceptedPotential;
+        s[ORC_HS_PROPOSED_POTENTIAL] = c->proposedPotential;
+        s[ORC_HS_CENTRAL_POTENTIAL] = c->centralPotential;
+        s[ORC_HS_POTENTIAL_COUNT] = c->potentialCount;
+        s[ORC_HS_GRADIENT_COUNT] = c->gradientCount;
+        s[ORC_HS_STEP_COUNT] = c->stepCount;
+        s[ORC_HS_COV_TRIALS] = c->covTrials;
+        s[ORC_HS_AVERAGE_TRIALS] = c->averageTrials;
+        s[ORC_HS_EST_COV_TRACE] = c->estCovTrace;
+        s[ORC_HS_CUR_COV_TRACE] = c->curCovTrace;
+        s[ORC_HS_ORBIT_LENGTH] = c->orbitLength;
+        s[ORC_HS_STEPS_REMAINING] = c->stepsRemaining;
+        s[ORC_HS_STEPS_SINCE_UPDATE] = c->stepsSinceUpdate;
+    }
+    if (acc) std::copy(c->accepted.begin(), c->accepted.end(), acc);
+    if (mom) std::copy(c->acceptedMomentum.begin(), c->acceptedMomentum.end(), mom);
+    if (cen) std::copy(c->central.begin(), c->central.end(), cen);
+    if (avg) std::copy(c->average.begin(), c->average.end(), avg);
+    if (cov) std::copy(c->estCov.begin(), c->estCov.end(), cov);
+    if (err) std::copy(c->estErr.begin(), c->estErr.end(), err);
+    return 0;
+}
+
+}  // extern "C"
