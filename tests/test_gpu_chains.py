@@ -199,7 +199,14 @@ def test_conditioning_ladder_keeps_chains_alive():
     assert 0.05 < tr["accepted"].mean() < 0.6
     pts = tr["points"][1500:].reshape(-1, dim)
     assert np.all(np.abs(pts.mean(0)) < 0.15)
-    assert np.all(np.abs(pts.var(0) - 1.0) < 0.25)
+    # The clamped hint (2,3) leaves the proposal (almost) no width along x2-x3,
+    # and the first covariance update needs ~1000 ACCEPTED steps
+    # (TSimpleMCMC.H:1693-1697), more than this run has: as in the reference,
+    # x2-x3 stays frozen near the start while x2+x3 samples N(0,2).
+    free = [0, 1, 4, 5]
+    assert np.all(np.abs(pts[:, free].var(0) - 1.0) < 0.25)
+    assert abs(((pts[:, 2] + pts[:, 3]) / np.sqrt(2.0)).var() - 1.0) < 0.25
+    assert (pts[:, 2] - pts[:, 3]).var() < 0.25
     assert np.all(eng.get("status") == 0)
 
 
