@@ -252,6 +252,78 @@ int smcmc_restore_state(smcmc_engine* e, const smcmc_saved_state* in, int32_t* m
 int smcmc_get_step_index(smcmc_engine* e, uint32_t* step);
 int smcmc_set_step_index(smcmc_engine* e, uint32_t step);
 
+/* ---- Hamiltonian Monte Carlo: sMCMC::TSimpleHMC<L, G> (TSimpleHMC.H:119-973) ---- */
+/* The same engine handle (likelihood, dim, chains, seed, likelihood inputs) can
+ * be driven as an ensemble of TSimpleHMC chains instead of TSimpleMCMC chains.
+ * Random draws of chain c at step s: slots 0..dim-1 the momentum refresh (:568,
+ * only when alpha < 1), the next slot the step-size jitter (:297), the next one
+ * the accept test (:347). */
+typedef enum smcmc_hmc_setting {
+    SMCMC_HMC_ALPHA = 0,            /* SetAlpha        :175                                  */
+    SMCMC_HMC_MEAN_EPSILON = 1,     /* SetMeanEpsilon  :181 (Start() resets it to 0.05, :229) */
+    SMCMC_HMC_LEAPFROG = 2,         /* SetLeapFrog     :190 (stored negated = fixed)          */
+    SMCMC_HMC_USER_GRADIENT = 3,    /* 1: TSimpleHMC<L, L> (the likelihood's own gradient functor,
+                                       TDummyLogLikelihood.H:34-42); 0: TSimpleHMC<L>, finite
+                                       differences (:417-444).  Set before smcmc_hmc_start.   */
+    SMCMC_HMC_KEEP_ERROR_MATRIX = 4 /* 1: keep fEstimatedError per chain (dim*dim doubles), which
+                                       gradient type 2 (:447-454) reads.  Set before start.   */
+} smcmc_hmc_setting;
+
+/* Per-chain quantities readable with smcmc_hmc_get(); arrays chain-major. */
+typedef enum smcmc_hmc_field {
+    SMCMC_HMC_F_ACCEPTED = 0,      /* double[chains*dim]      fAccepted                      */
+    SMCMC_HMC_F_MOMENTUM = 1,      /* double[chains*dim]      fAcceptedMomentum              */
+    SMCMC_HMC_F_PROPOSED = 2,      /* double[chains*dim]      fProposed                      */
+    SMCMC_HMC_F_CENTRAL = 3,       /* double[chains*dim]      GetCentralPoint        :193    */
+    SMCMC_HMC_F_AVERAGE = 4,       /* double[chains*dim]      fAveragePoint                  */
+    SMCMC_HMC_F_COVARIANCE = 5,    /* double[chains*dim*dim]  GetEstimatedCovariance :197    */
+    SMCMC_HMC_F_ERROR_MATRIX = 6,  /* double[chains*dim*dim]  fEstimatedError                */
+    SMCMC_HMC_F_SCALARS = 7        /* double[chains*SMCMC_HMC_SCALAR_COUNT], columns below   */
+} smcmc_hmc_field;
+enum {
+    SMCMC_HMC_S_ACCEPTANCE = 0,      /* GetAcceptanceRate :160 */
+    SMCMC_HMC_S_MEAN_EPSILON,        /* GetMeanEpsilon    :184 */
+    SMCMC_HMC_S_LEAPFROG,            /* fLeapFrogSteps         */
+    SMCMC_HMC_S_REVERSAL_LEN,
+    SMCMC_HMC_S_ACCEPTED_POTENTIAL,
+    SMCMC_HMC_S_PROPOSED_POTENTIAL,
+    SMCMC_HMC_S_CENTRAL_POTENTIAL,   /* GetCentralPotential :194 */
+    SMCMC_HMC_S_POTENTIAL_COUNT,     /* GetPotentialCount :163 */
+    SMCMC_HMC_S_GRADIENT_COUNT,      /* GetGradientCount  :168 */
+    SMCMC_HMC_S_STEP_COUNT,
+    SMCMC_HMC_S_COV_TRIALS,
+    SMCMC_HMC_S_AVERAGE_TRIALS,
+    SMCMC_HMC_S_EST_COV_TRACE,
+    SMCMC_HMC_S_CUR_COV_TRACE,
+    SMCMC_HMC_S_ORBIT_LENGTH,
+    SMCMC_HMC_S_STEPS_REMAINING,
+    SMCMC_HMC_S_STEPS_SINCE_UPDATE,
+    SMCMC_HMC_SCALAR_COUNT
+};
+
+/* Optional per-step record of smcmc_hmc_step_trace(): what SaveStep() (:861)
+ * writes to the tree (:139-147).  Step-major, any pointer may be NULL. */
+typedef struct smcmc_hmc_trace {
+    double* potential;      /* [nsteps*chains]      "LogLikelihood" = fAcceptedPotential */
+    double* points;         /* [nsteps*chains*dim]  "Accepted"                           */
+    double* mean_epsilon;   /* [nsteps*chains]      "MeanEpsilon"                        */
+    int32_t* leapfrog;      /* [nsteps*chains]      "Leapfrog"                           */
+    int32_t* accepted;      /* [nsteps*chains]      1 when the proposed point was taken  */
+} smcmc_hmc_trace;
+
+int smcmc_hmc_set(smcmc_engine* e, int setting, double value);
+/* TSimpleHMC::Start (:210-269): x0[chains*dim]. */
+int smcmc_hmc_start(smcmc_engine* e, const double* x0);
+/* TSimpleHMC::SetPosition (:202-205): x[chains*dim]. */
+int smcmc_hmc_set_position(smcmc_engine* e, const double* x);
+/* nsteps calls of TSimpleHMC::Step(false, gradient_type) (:279-401) on every
+ * chain.  gradient_type as PotentialGradient (:467-532): 0/1 user gradient when
+ * there is one, else finite differences; 2 covariant; 3 finite differences;
+ * 4 user gradient or SMCMC_ERR_LOGIC; 5 zero. */
+int smcmc_hmc_step(smcmc_engine* e, int nsteps, int gradient_type);
+int smcmc_hmc_step_trace(smcmc_engine* e, int nsteps, int gradient_type, const smcmc_hmc_trace* trace);
+int smcmc_hmc_get(smcmc_engine* e, int field, void* dst, size_t bytes);
+
 /* ---- instrumentation ------------------------------------------------------ */
 /* Kernel launches issued by this engine so far. */
 int64_t smcmc_launch_count(const smcmc_engine* e);

@@ -11,6 +11,7 @@
 
 #include "common.cuh"
 #include "fake_likelihood.cuh"
+#include "hmc.cuh"
 #include "nccl_dyn.h"
 #include "pooled.cuh"
 #include "proposal.cuh"
@@ -43,6 +44,22 @@ static double firstLogWhere(Pred pred, double lo, double hi) {
 }  // namespace smcmc
 
 using namespace smcmc;
+
+// Device state of the TSimpleHMC ensemble (hmc.cuh), allocated on first use.
+struct HmcHost {
+    bool allocated = false, started = false, firstStart = true;
+    double alpha = 0.0;              // fAlpha                 TSimpleHMC.H:133
+    int userGradient = 0;            // TSimpleHMC<L, L> instead of TSimpleHMC<L>
+    int keepError = 0;               // keep fEstimatedError per chain
+    DeviceBuffer<double> qAcc, pAcc, qProp, pProp, p0, grad, central, average, exxt, estErr, repairedDiag;
+    DeviceBuffer<double> llh, fdWork, fdLlh, avgPts, avgLlh;
+    DeviceBuffer<HmcScalars> sc;
+    DeviceBuffer<int> leapSteps, counters, updateList;
+    int* hostCounters = nullptr;     // pinned
+    ~HmcHost() {
+        if (hostCounters) cudaFreeHost(hostCounters);
+    }
+};
 
 struct smcmc_engine {
     smcmc_config cfg;
@@ -143,6 +160,9 @@ struct smcmc_engine {
         launched();
         ++poolExchanges;
     }
+
+    // ---- TSimpleHMC ---------------------------------------------------------------
+    HmcHost hmc;
 
     // ---- scratch for smcmc_eval / smcmc_fake_histograms ---------------------
     DeviceBuffer<double> evalX, evalOut, evalHist;
@@ -1107,3 +1127,5 @@ int smcmc_pair_kernel_stats(smcmc_engine* e, double* totalMs, int64_t* launches,
 }
 
 }  // extern "C"
+
+#include "engine_hmc.inl"

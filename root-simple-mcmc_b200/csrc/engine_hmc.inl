@@ -1,0 +1,368 @@
+// engine_hmc.inl -- host side of the TSimpleHMC entry points (included by
+// engine.cu after the engine struct).  Queues the kernels of hmc.cuh.
+
+namespace {
+
+constexpr size_t kHmcFdWorkBytes = 512u << 20;     // finite-difference work points per pass
+
+void hmcAllocate(smcmc_engine* e) {
+    HmcHost& h = e->hmc;
+    if (h.allocated) return;
+    const size_t E = e->E(), n = e->n(), tri = e->tri();
+    h.qAcc.reserve(E * n);
+    h.pAcc.reserve(E * n);
+    h.qProp.reserve(E * n);
+    h.pProp.reserve(E * n);
+    h.p0.reserve(E * n);
+    h.grad.reserve(E * n);
+    h.central.reserve(E * n);
+    h.average.reserve(E * n);
+    h.repairedDiag.reserve(E * n);
+    h.exxt.reserve(E * tri);
+    h.llh.reserve(E);
+    h.sc.reserve(E);
+    h.leapSteps.reserve(E);
+    h.updateList.reserve(E);
+    h.counters.reserve(2);
+    CUDA_CHECK(cudaMallocHost((void**)&h.hostCounters, 2 * sizeof(int)));
+    std::vector<HmcScalars> init(E);
+    std::memset(init.data(), 0, sizeof(HmcScalars) * E);
+    for (size_t c = 0; c < E; ++c) init[c].leapFrogSteps = 10;            // TSimpleHMC.H:133
+    CUDA_CHECK(cudaMemcpy(h.sc.get(), init.data(), sizeof(HmcScalars) * E, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemset(h.pAcc.get(), 0, h.pAcc.bytes()));
+    CUDA_CHECK(cudaMemset(h.pProp.get(), 0, h.pProp.bytes()));
+    CUDA_CHECK(cudaMemset(h.grad.get(), 0, h.grad.bytes()));
+    CUDA_CHECK(cudaMemset(h.leapSteps.get(), 0, h.leapSteps.bytes()));
+    h.allocated = true;
+}
+
+HmcArrays hmcArrays(smcmc_engine* e) {
+    HmcHost& h = e->hmc;
+    HmcArrays a;
+    a.qAcc = h.qAcc.get();
+    a.pAcc = h.pAcc.get();
+    a.qProp = h.qProp.get();
+    a.pProp = h.pProp.get();
+    a.p0 = h.p0.get();
+    a.grad = h.grad.get();
+    a.central = h.central.get();
+    a.average = h.average.get();
+    a.exxt = h.exxt.get();
+    a.estErr = h.keepError ? h.estErr.get() : nullptr;
+    a.repairedDiag = h.repairedDiag.get();
+    a.sc = h.sc.get();
+    a.leapSteps = h.leapSteps.get();
+    a.counters = h.counters.get();
+    a.updateList = h.updateList.get();
+    a.eigScratch = e->eigScratch.get();
+    a.eigLocks = e->eigLocks.get();
+    a.eigSlots = e->eigSlots;
+    return a;
+}
+
+void requireHmcStarted(smcmc_engine* e) {
+    if (!e->hmc.started) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "Must initialize starting point");   // TSimpleHMC.H:280-284
+}
+
+// Which gradient PotentialGradient(type) ends up computing (:467-532).
+enum HmcGradientMode { kGradUser, kGradFinite, kGradCovariant, kGradZero };
+
+HmcGradientMode hmcResolveGradient(smcmc_engine* e, int type) {
+    const bool haveUser = e->hmc.userGradient && e->cfg.likelihood == SMCMC_LLH_DUMMY;
+    switch (type) {
+    case 2:
+        if (!e->hmc.keepError)
+            throw Error(SMCMC_ERR_LOGIC, "gradient type 2 needs SMCMC_HMC_KEEP_ERROR_MATRIX set before smcmc_hmc_start");
+        return kGradCovariant;
+    case 3: return kGradFinite;
+    case 4:
+        if (!haveUser) throw Error(SMCMC_ERR_LOGIC, "gradient type 4 needs a user gradient");        // :521
+        return kGradUser;
+    case 5: return kGradZero;
+    default: return haveUser ? kGradUser : kGradFinite;                                           // :472-507
+    }
+}
+
+void hmcGradient(smcmc_engine* e, HmcGradientMode mode, int k) {
+    HmcHost& h = e->hmc;
+    HmcArrays a = hmcArrays(e);
+    const int E = e->E(), n = e->n();
+    switch (mode) {
+    case kGradUser: {
+        if (e->errDim != n) throw Error(SMCMC_ERR_LOGIC, "error matrix not set (smcmc_dummy_set_error)");
+        dim3 grid(ceilDiv(n, kGemmBN), ceilDiv(E, kGemmBM));
+        kDummyGradient<<<grid, 256, 0, e->stream>>>(h.qProp.get(), e->errMatrix.get(), h.grad.get(),
+                                                    h.leapSteps.get(), k, E, n);
+        e->launched();
+        break;
+    }
+    case kGradFinite: {
+        const size_t perChain = (size_t)2 * n * n * sizeof(double);
+        int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)E, kHmcFdWorkBytes / perChain));
+        h.fdWork.reserve((size_t)chunk * 2 * n * n);
+        h.fdLlh.reserve((size_t)chunk * 2 * n);
+        for (int base = 0; base < E; base += chunk) {
+            const int cc = std::min(chunk, E - base);
+            const size_t total = (size_t)cc * 2 * n * n;
+            kHmcFdPoints<<<ceilDiv((long long)total, 256), 256, 0, e->stream>>>(h.qProp.get(), h.fdWork.get(), base, cc, n);
+            e->launched();
+            e->evaluate(h.fdWork.get(), cc * 2 * n, h.fdLlh.get(), nullptr);
+            kHmcFdGradient<<<ceilDiv((long long)cc * n, 256), 256, 0, e->stream>>>(h.fdLlh.get(), h.grad.get(),
+                                                                                  h.leapSteps.get(), k, base, cc, n);
+            e->launched();
+        }
+        break;
+    }
+    case kGradCovariant:
+        kHmcCovariantGradient<<<ceilDiv(E, kWarpsPerBlock), kWarpsPerBlock * 32,
+                                (size_t)kWarpsPerBlock * n * sizeof(double), e->stream>>>(a, n, E, k);
+        e->launched();
+        break;
+    case kGradZero:
+        if (k == 0) {
+            kHmcZeroGradient<<<ceilDiv((long long)E * n, 256), 256, 0, e->stream>>>(a, n, E);
+            e->launched();
+        }
+        break;
+    }
+}
+
+int hmcReadCounter(smcmc_engine* e, int which) {
+    HmcHost& h = e->hmc;
+    CUDA_CHECK(cudaMemcpyAsync(h.hostCounters + which, h.counters.get() + which, sizeof(int),
+                               cudaMemcpyDeviceToHost, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    return h.hostCounters[which];
+}
+
+void hmcStepOnce(smcmc_engine* e, int type, const HmcTraceDev& tr, int traceStep) {
+    HmcHost& h = e->hmc;
+    const HmcGradientMode mode = hmcResolveGradient(e, type);
+    HmcArrays a = hmcArrays(e);
+    const int E = e->E(), n = e->n();
+    const int blocks = ceilDiv(E, kWarpsPerBlock), threads = kWarpsPerBlock * 32;
+    const size_t smem = (size_t)kWarpsPerBlock * n * sizeof(double);
+    if (h.alpha < 0.0) h.alpha = 0.0;                                     // :565
+    CUDA_CHECK(cudaMemsetAsync(h.counters.get(), 0, 2 * sizeof(int), e->stream));
+    kHmcBegin<<<blocks, threads, smem, e->stream>>>(a, n, E, h.alpha, e->cfg.seed, e->cfg.chain_offset, e->stepIndex);
+    e->launched();
+    const int maxSteps = hmcReadCounter(e, 0);
+    const int countPotentials = (mode == kGradFinite) ? 2 * n : 0;
+    if (maxSteps >= 1) {
+        for (int k = 0; k <= maxSteps; ++k) {
+            hmcGradient(e, mode, k);
+            kHmcKickDrift<<<blocks, threads, smem, e->stream>>>(a, n, E, k, countPotentials);
+            e->launched();
+        }
+    }
+    e->evaluate(h.qProp.get(), E, h.llh.get(), nullptr);                  // :327
+    kHmcPost<<<blocks, threads, smem, e->stream>>>(a, n, E, h.llh.get(), 1000000.0 /* fCovarianceWindow :134 */);
+    e->launched();
+    const int updates = hmcReadCounter(e, 1);
+    if (updates > 0) {
+        h.avgPts.reserve((size_t)updates * n);
+        h.avgLlh.reserve(updates);
+        kHmcGatherAverage<<<ceilDiv((long long)updates * n, 256), 256, 0, e->stream>>>(a, n, updates, h.avgPts.get());
+        e->launched();
+        e->evaluate(h.avgPts.get(), updates, h.avgLlh.get(), nullptr);    // :729
+        kHmcErrorMatrix<<<ceilDiv(updates, kWarpsPerBlock), threads, 0, e->stream>>>(a, n, updates, h.avgLlh.get());
+        e->launched();
+    }
+    const uint32_t acceptSlot = (h.alpha >= 1.0 ? 0u : (uint32_t)n) + 1u;
+    kHmcAccept<<<blocks, threads, 0, e->stream>>>(a, n, E, e->cfg.seed, e->cfg.chain_offset, e->stepIndex,
+                                                  acceptSlot, tr, traceStep);
+    e->launched();
+    ++e->stepIndex;
+}
+
+}  // namespace
+
+extern "C" {
+
+int smcmc_hmc_set(smcmc_engine* e, int setting, double v) {
+    return guarded(e, [&]() {
+        HmcHost& h = e->hmc;
+        switch (setting) {
+        case SMCMC_HMC_ALPHA: h.alpha = v; return;
+        case SMCMC_HMC_USER_GRADIENT:
+            if (v != 0.0 && e->cfg.likelihood != SMCMC_LLH_DUMMY)
+                throw Error(SMCMC_ERR_INVALID_ARGUMENT, "only TDummyLogLikelihood provides a gradient functor");
+            h.userGradient = (v != 0.0);
+            return;
+        case SMCMC_HMC_KEEP_ERROR_MATRIX:
+            if (h.started) throw Error(SMCMC_ERR_LOGIC, "set SMCMC_HMC_KEEP_ERROR_MATRIX before smcmc_hmc_start");
+            h.keepError = (v != 0.0);
+            return;
+        case SMCMC_HMC_MEAN_EPSILON:
+        case SMCMC_HMC_LEAPFROG:
+            hmcAllocate(e);
+            kHmcSetScalar<<<ceilDiv(e->E(), 128), 128, 0, e->stream>>>(h.sc.get(), e->E(), setting, v);
+            e->launched();
+            return;
+        default: throw Error(SMCMC_ERR_INVALID_ARGUMENT, "unknown HMC setting");
+        }
+    });
+}
+
+int smcmc_hmc_start(smcmc_engine* e, const double* x0) {
+    return guarded(e, [&]() {
+        if (!x0) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null starting points");
+        HmcHost& h = e->hmc;
+        hmcAllocate(e);
+        const size_t E = e->E(), n = e->n();
+        if (h.keepError) h.estErr.reserve(E * n * n);
+        // scratch for UpdateErrorMatrix: eigenvalues and the inverse share the engine's slots
+        CUDA_CHECK(cudaMemcpyAsync(h.qAcc.get(), x0, E * n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        e->evaluate(h.qAcc.get(), (int)E, h.llh.get(), nullptr);           // SetPosition, :221
+        kHmcStart<<<ceilDiv((long long)E, kWarpsPerBlock), kWarpsPerBlock * 32, 0, e->stream>>>(
+            hmcArrays(e), (int)n, (int)E, h.llh.get(), h.firstStart ? 1 : 0);
+        e->launched();
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        h.firstStart = false;
+        h.started = true;
+        if ((size_t)kWarpsPerBlock * n * sizeof(double) > 48 * 1024) {
+            const int bytes = (int)((size_t)kWarpsPerBlock * n * sizeof(double));
+            CUDA_CHECK(cudaFuncSetAttribute(kHmcBegin, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            CUDA_CHECK(cudaFuncSetAttribute(kHmcKickDrift, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            CUDA_CHECK(cudaFuncSetAttribute(kHmcPost, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            CUDA_CHECK(cudaFuncSetAttribute(kHmcCovariantGradient, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        }
+    });
+}
+
+int smcmc_hmc_set_position(smcmc_engine* e, const double* x) {
+    return guarded(e, [&]() {
+        requireHmcStarted(e);
+        if (!x) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null points");
+        HmcHost& h = e->hmc;
+        const size_t E = e->E(), n = e->n();
+        CUDA_CHECK(cudaMemcpyAsync(h.qAcc.get(), x, E * n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        e->evaluate(h.qAcc.get(), (int)E, h.llh.get(), nullptr);
+        kHmcSetPosition<<<ceilDiv((long long)E, 128), 128, 0, e->stream>>>(hmcArrays(e), (int)E, h.llh.get());
+        e->launched();
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    });
+}
+
+int smcmc_hmc_step(smcmc_engine* e, int nsteps, int type) {
+    return guarded(e, [&]() {
+        requireHmcStarted(e);
+        HmcTraceDev none = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        for (int s = 0; s < nsteps; ++s) hmcStepOnce(e, type, none, -1);
+    });
+}
+
+int smcmc_hmc_step_trace(smcmc_engine* e, int nsteps, int type, const smcmc_hmc_trace* trace) {
+    return guarded(e, [&]() {
+        requireHmcStarted(e);
+        if (nsteps < 1) return;
+        const size_t rows = (size_t)nsteps * e->E();
+        DeviceBuffer<double> pot, pts, eps;
+        DeviceBuffer<int32_t> lf, acc;
+        HmcTraceDev tr = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        if (trace) {
+            if (trace->potential) { pot.reserve(rows); tr.potential = pot.get(); }
+            if (trace->points) { pts.reserve(rows * e->n()); tr.points = pts.get(); }
+            if (trace->mean_epsilon) { eps.reserve(rows); tr.meanEpsilon = eps.get(); }
+            if (trace->leapfrog) { lf.reserve(rows); tr.leapfrog = lf.get(); }
+            if (trace->accepted) { acc.reserve(rows); tr.accepted = acc.get(); }
+        }
+        for (int s = 0; s < nsteps; ++s) hmcStepOnce(e, type, tr, s);
+        if (trace) {
+            if (trace->potential) CUDA_CHECK(cudaMemcpyAsync(trace->potential, pot.get(), rows * 8, cudaMemcpyDeviceToHost, e->stream));
+            if (trace->points) CUDA_CHECK(cudaMemcpyAsync(trace->points, pts.get(), rows * e->n() * 8, cudaMemcpyDeviceToHost, e->stream));
+            if (trace->mean_epsilon) CUDA_CHECK(cudaMemcpyAsync(trace->mean_epsilon, eps.get(), rows * 8, cudaMemcpyDeviceToHost, e->stream));
+            if (trace->leapfrog) CUDA_CHECK(cudaMemcpyAsync(trace->leapfrog, lf.get(), rows * 4, cudaMemcpyDeviceToHost, e->stream));
+            if (trace->accepted) CUDA_CHECK(cudaMemcpyAsync(trace->accepted, acc.get(), rows * 4, cudaMemcpyDeviceToHost, e->stream));
+        }
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    });
+}
+
+int smcmc_hmc_get(smcmc_engine* e, int field, void* dst, size_t bytes) {
+    return guarded(e, [&]() {
+        if (!dst) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null destination");
+        HmcHost& h = e->hmc;
+        if (!h.allocated) throw Error(SMCMC_ERR_LOGIC, "HMC state does not exist yet (smcmc_hmc_start)");
+        const size_t E = e->E(), n = e->n(), tri = e->tri();
+        auto need = [&](size_t want) {
+            if (bytes < want) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "destination too small");
+        };
+        auto copyArray = [&](const void* src, size_t want) {
+            need(want);
+            CUDA_CHECK(cudaMemcpyAsync(dst, src, want, cudaMemcpyDeviceToHost, e->stream));
+            CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        };
+        switch (field) {
+        case SMCMC_HMC_F_ACCEPTED: copyArray(h.qAcc.get(), E * n * 8); return;
+        case SMCMC_HMC_F_MOMENTUM: copyArray(h.pAcc.get(), E * n * 8); return;
+        case SMCMC_HMC_F_PROPOSED: copyArray(h.qProp.get(), E * n * 8); return;
+        case SMCMC_HMC_F_CENTRAL: copyArray(h.central.get(), E * n * 8); return;
+        case SMCMC_HMC_F_AVERAGE: copyArray(h.average.get(), E * n * 8); return;
+        case SMCMC_HMC_F_ERROR_MATRIX:
+            if (!h.keepError || !h.estErr.count()) throw Error(SMCMC_ERR_LOGIC, "the error matrix is not kept (SMCMC_HMC_KEEP_ERROR_MATRIX)");
+            copyArray(h.estErr.get(), E * n * n * 8);
+            return;
+        default: break;
+        }
+        std::vector<HmcScalars> sc(E);
+        CUDA_CHECK(cudaMemcpyAsync(sc.data(), h.sc.get(), sizeof(HmcScalars) * E, cudaMemcpyDeviceToHost, e->stream));
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        if (field == SMCMC_HMC_F_SCALARS) {
+            need(E * SMCMC_HMC_SCALAR_COUNT * 8);
+            double* out = (double*)dst;
+            for (size_t c = 0; c < E; ++c) {
+                double* o = out + c * SMCMC_HMC_SCALAR_COUNT;
+                const HmcScalars& s = sc[c];
+                o[SMCMC_HMC_S_ACCEPTANCE] = s.acceptance;
+                o[SMCMC_HMC_S_MEAN_EPSILON] = s.meanEpsilon;
+                o[SMCMC_HMC_S_LEAPFROG] = s.leapFrogSteps;
+                o[SMCMC_HMC_S_REVERSAL_LEN] = s.reversalLen;
+                o[SMCMC_HMC_S_ACCEPTED_POTENTIAL] = s.accPotential;
+                o[SMCMC_HMC_S_PROPOSED_POTENTIAL] = s.propPotential;
+                o[SMCMC_HMC_S_CENTRAL_POTENTIAL] = s.centralPotential;
+                o[SMCMC_HMC_S_POTENTIAL_COUNT] = s.potentialCount;
+                o[SMCMC_HMC_S_GRADIENT_COUNT] = s.gradientCount;
+                o[SMCMC_HMC_S_STEP_COUNT] = s.stepCount;
+                o[SMCMC_HMC_S_COV_TRIALS] = s.covTrials;
+                o[SMCMC_HMC_S_AVERAGE_TRIALS] = s.averageTrials;
+                o[SMCMC_HMC_S_EST_COV_TRACE] = s.estCovTrace;
+                o[SMCMC_HMC_S_CUR_COV_TRACE] = s.curCovTrace;
+                o[SMCMC_HMC_S_ORBIT_LENGTH] = s.orbitLength;
+                o[SMCMC_HMC_S_STEPS_REMAINING] = s.stepsRemaining;
+                o[SMCMC_HMC_S_STEPS_SINCE_UPDATE] = s.stepsSinceUpdate;
+            }
+            return;
+        }
+        if (field == SMCMC_HMC_F_COVARIANCE) {
+            // fEstimatedCovariance = fEXXT - mean mean^T (:688-689), or what a
+            // positive-definiteness repair left (:792-806); the identity before
+            // the first step (:254-260).
+            need(E * n * n * 8);
+            std::vector<double> ex(E * tri), avg(E * n), diag(E * n);
+            CUDA_CHECK(cudaMemcpy(ex.data(), h.exxt.get(), ex.size() * 8, cudaMemcpyDeviceToHost));
+            CUDA_CHECK(cudaMemcpy(avg.data(), h.average.get(), avg.size() * 8, cudaMemcpyDeviceToHost));
+            CUDA_CHECK(cudaMemcpy(diag.data(), h.repairedDiag.get(), diag.size() * 8, cudaMemcpyDeviceToHost));
+            double* out = (double*)dst;
+            for (size_t c = 0; c < E; ++c) {
+                double* o = out + c * n * n;
+                const bool fresh = sc[c].covTrials == 0.0 && sc[c].averageTrials == 0.0;
+                for (size_t i = 0; i < n; ++i)
+                    for (size_t j = 0; j <= i; ++j) {
+                        double v;
+                        if (fresh) v = (i == j) ? 1.0 : 0.0;
+                        else if (sc[c].repaired) v = (i == j) ? diag[c * n + i] : 0.0;
+                        else {
+                            volatile double prod = avg[c * n + i] * avg[c * n + j];     // no contraction
+                            v = ex[c * tri + i * (i + 1) / 2 + j] - prod;
+                        }
+                        o[i * n + j] = o[j * n + i] = v;
+                    }
+            }
+            return;
+        }
+        throw Error(SMCMC_ERR_INVALID_ARGUMENT, "unknown HMC field");
+    });
+}
+
+}  // extern "C"

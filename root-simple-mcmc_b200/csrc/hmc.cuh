@@ -1,0 +1,788 @@
+// hmc.cuh -- sMCMC::TSimpleHMC (TSimpleHMC.H:119-973) for E chains at once.
+//
+// One HMC transition of the ensemble is a short pipeline of kernels queued by
+// the host (engine.cu, hmcStepOnce):
+//
+//   kHmcBegin      ProposeMomentum (:554-570), initial kinetic energy (:292),
+//                  the jittered step size (:297), LeapFrog's set-up (:586-611)
+//   repeat k = 0 .. max_c |fLeapFrogSteps_c|:
+//     gradient     PotentialGradient (:467-532) at the current positions of all
+//                  chains: kDummyGradient (user gradient of TDummyLogLikelihood,
+//                  a batched X.E^T contraction), the finite-difference pipeline
+//                  (:417-444), kHmcCovariantGradient (:447-454) or zero
+//     kHmcKickDrift  the k-th momentum update of LeapFrog (:618-648), the
+//                  U-turn test (:633-638) and the next position update
+//   likelihood of the proposed points (the engine's ordinary evaluate())
+//   kHmcPost       leap-frog / step-size adaptation (:302-323), proposed kinetic
+//                  energy (:326), UpdateCovariance (:665-695) and the trigger
+//                  part of UpdateErrorMatrix (:703-719)
+//   kHmcErrorMatrix (rare, only the chains that triggered) the rest of
+//                  UpdateErrorMatrix (:727-858)
+//   kHmcAccept     the Metropolis test on the Hamiltonian (:346-395)
+//
+// Chains have their own number of leap-frog steps; a chain whose trajectory is
+// complete ignores the remaining iterations.  One warp owns one chain in the
+// elementwise kernels (lanes across the dimension).  Parity rules as in
+// proposal.cuh: the reference's operation order with __dXXX_rn intrinsics,
+// sequential sums stay sequential.
+//
+// HBM layout, chain-major: qAcc, pAcc, qProp, pProp, p0, grad, central, average
+// : double[E][n]; exxt : double[E][n(n+1)/2] packed lower triangle of fEXXT;
+// estErr : double[E][n*n] (fEstimatedError, only when the covariant gradient is
+// enabled); sc : HmcScalars[E].  fEstimatedCovariance is not stored: every entry
+// is fEXXT(i,j) - fAveragePoint[i]*fAveragePoint[j] (:688-689) and is rebuilt
+// where it is read; the diagonal that a positive-definiteness repair leaves
+// behind (:792-806) is kept in repairedDiag until the next step overwrites it.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "proposal.cuh"
+#include "simple_likelihoods.cuh"
+#include "smcmc_b200.h"
+#include "smcmc_rng.h"
+
+namespace smcmc {
+
+struct __align__(16) HmcScalars {
+    double meanEpsilon;       // fMeanEpsilon              :902
+    double reversalLen;       // fReversalLen
+    double acceptance;        // fCurrentAcceptance
+    double epsilon;           // the jittered step size of the step in flight :297
+    double accPotential;      // fAcceptedPotential
+    double propPotential;     // fProposedPotential
+    double centralPotential;  // fCentralPotential
+    double initialKinetic;    // :292
+    double deltaH;            // proposed - accepted Hamiltonian :346
+    double averageTrials;     // fAveragePointTrials
+    double covTrials;         // fCovarianceTrials
+    double orbitLength;       // fEstimatedOrbitLength
+    double estCovTrace;       // fEstimatedCovarianceTrace
+    double curCovTrace;       // fCurrentCovarianceTrace
+    int leapFrogSteps;        // fLeapFrogSteps (negative = fixed by the user, :190)
+    int steps;                // |fLeapFrogSteps| of the step in flight
+    int okLeap;               // LeapFrog's return value
+    int stepCount;            // fStepCount
+    int potentialCount;       // fPotentialCount
+    int gradientCount;        // fPotentialGradientCount
+    int stepsRemaining;       // fStepsRemaining
+    int stepsSinceUpdate;     // fStepsSinceUpdate
+    int needUpdate;           // UpdateErrorMatrix passed its trigger this step
+    int status;
+    int started;
+    int repaired;             // fEstimatedCovariance currently holds the repaired (diagonal) matrix
+};
+static_assert(sizeof(HmcScalars) == 160, "HmcScalars layout");
+
+struct HmcArrays {
+    double* qAcc;       // fAccepted
+    double* pAcc;       // fAcceptedMomentum
+    double* qProp;      // fProposed
+    double* pProp;      // fProposedMomentum
+    double* p0;         // LeapFrog's copy of the starting momentum (:587)
+    double* grad;
+    double* central;    // fCentralPoint
+    double* average;    // fAveragePoint
+    double* exxt;       // fEXXT, packed lower triangle
+    double* estErr;     // fEstimatedError or nullptr
+    double* repairedDiag;
+    HmcScalars* sc;
+    int* leapSteps;     // copy of sc.steps for the gradient kernels
+    int* counters;      // [0] max steps of this transition, [1] chains that need UpdateErrorMatrix
+    int* updateList;
+    double* eigScratch; // slots of 2*n*n doubles
+    int* eigLocks;
+    int eigSlots;
+};
+
+// Sum buf[0..n) in index order; every lane returns the same value.
+__device__ __forceinline__ double warpSeqSum(const double* buf, int n) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s = __dadd_rn(s, buf[i]);
+    return s;
+}
+
+// KineticEnergy (:535-542): ke += p*p/2.0 in index order.  `buf` is the warp's
+// shared scratch of n doubles.
+__device__ __forceinline__ double warpKinetic(const double* __restrict__ p, double* buf, int n, int lane) {
+    for (int i = lane; i < n; i += 32) buf[i] = __ddiv_rn(__dmul_rn(p[i], p[i]), 2.0);
+    __syncwarp();
+    const double ke = warpSeqSum(buf, n);
+    __syncwarp();
+    return ke;
+}
+
+// ---------------------------------------------------------------------------
+// Start (:210-269); the likelihood of the starting points is in llh[].
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+kHmcStart(HmcArrays a, int n, int chains, const double* __restrict__ llh, int firstStart) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (c >= chains) return;
+    const size_t row = (size_t)c * n;
+    const size_t tri = (size_t)n * (n + 1) / 2;
+    HmcScalars s = a.sc[c];
+    s.stepCount = 0;                                          // :211
+    s.potentialCount += 1;                                    // SetPosition -> Potential :204
+    s.accPotential = -llh[c];
+    s.propPotential = s.accPotential;                         // :225
+    s.meanEpsilon = 0.05;                                     // :229
+    s.reversalLen = 0.0;
+    s.acceptance = 0.65;                                      // :234-235
+    s.centralPotential = s.accPotential;                      // :240
+    s.averageTrials = 0.0;                                    // :244
+    s.covTrials = 0.0;                                        // :253
+    s.estCovTrace = (double)n;                                // :263
+    s.stepsRemaining = 0;                                     // :265-266
+    s.stepsSinceUpdate = 0;
+    s.needUpdate = 0;
+    s.status = 0;
+    s.started = 1;
+    s.repaired = 0;
+    for (int i = lane; i < n; i += 32) {
+        const double x = a.qAcc[row + i];
+        a.qProp[row + i] = x;                                 // :224
+        a.central[row + i] = x;                               // :239
+        a.average[row + i] = x;                               // :243
+        if (firstStart) {                                     // resize() zero-fills only new elements
+            a.pAcc[row + i] = 0.0;
+            a.pProp[row + i] = 0.0;
+        }
+    }
+    for (size_t k = lane; k < tri; k += 32) a.exxt[(size_t)c * tri + k] = 0.0;        // :258
+    if (a.estErr) {                                           // :261-262: the inverse of the identity
+        double* e = a.estErr + (size_t)c * n * n;
+        for (int k = lane; k < n * n; k += 32) e[k] = (k / n == k % n) ? 1.0 : 0.0;
+    }
+    if (lane == 0) a.sc[c] = s;
+}
+
+// SetPosition (:202-205).
+__global__ void kHmcSetPosition(HmcArrays a, int chains, const double* __restrict__ llh) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= chains) return;
+    a.sc[c].potentialCount += 1;
+    a.sc[c].accPotential = -llh[c];
+}
+
+// Broadcast a scalar setter to every chain (SetMeanEpsilon :181, SetLeapFrog :190).
+__global__ void kHmcSetScalar(HmcScalars* sc, int chains, int field, double value) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= chains) return;
+    if (field == SMCMC_HMC_MEAN_EPSILON) sc[c].meanEpsilon = value;
+    else if (field == SMCMC_HMC_LEAPFROG) sc[c].leapFrogSteps = -(int)value;
+}
+
+// ---------------------------------------------------------------------------
+// Head of Step (:286-300) and of LeapFrog (:586-611).
+// Dynamic shared memory: n doubles per warp.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+kHmcBegin(HmcArrays a, int n, int chains, double alpha, uint64_t seed, uint32_t chainOffset,
+          uint32_t step) {
+    extern __shared__ double smemD[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * kWarpsPerBlock + warp;
+    if (c >= chains) return;
+    double* buf = smemD + (size_t)warp * n;
+    HmcScalars s = a.sc[c];
+    if (!s.started || s.status != 0) {
+        if (lane == 0) a.leapSteps[c] = -1;
+        return;
+    }
+    const size_t row = (size_t)c * n;
+    const uint32_t gchain = chainOffset + (uint32_t)c;
+    s.stepCount += 1;                                                     // :286
+    // ProposeMomentum, :554-570.  alpha has been clamped on the host the way
+    // the reference clamps its member (:558, :565).
+    uint32_t slot = 0;
+    if (alpha >= 1.0) {
+        for (int i = lane; i < n; i += 32) {
+            const double p = __ddiv_rn(a.pAcc[row + i], alpha);
+            a.pProp[row + i] = p;
+            a.p0[row + i] = p;
+        }
+    } else {
+        const double w = __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(alpha, alpha)));
+        for (int i = lane; i < n; i += 32) {
+            const double g = __dadd_rn(0.0, __dmul_rn(1.0, smcmc_normal(seed, gchain, step, (uint32_t)i,
+                                                                       SMCMC_STREAM_STEP)));   // Gaus(0,1)
+            const double p = __dadd_rn(__dmul_rn(alpha, a.pAcc[row + i]), __dmul_rn(w, g));
+            a.pProp[row + i] = p;
+            a.p0[row + i] = p;                                            // :587
+        }
+        slot = (uint32_t)n;
+    }
+    __syncwarp();
+    s.initialKinetic = warpKinetic(a.pProp + row, buf, n, lane);          // :292
+    {                                                                     // :297-298
+        const double lo = __dmul_rn(0.9, fabs(s.meanEpsilon));
+        const double hi = __dmul_rn(1.1, fabs(s.meanEpsilon));
+        const double u = smcmc_uniform(seed, gchain, step, slot, SMCMC_STREAM_STEP);
+        s.epsilon = __dadd_rn(lo, __dmul_rn(__dsub_rn(hi, lo), u));       // TRandom::Uniform(a,b)
+    }
+    s.steps = abs(s.leapFrogSteps);                                       // :300
+    s.okLeap = 1;                                                         // :589
+    if (s.steps < 1) {                                                    // :598-611
+        for (int i = lane; i < n; i += 32) {
+            const double p = a.pProp[row + i];
+            const double mv = __ddiv_rn(__dmul_rn(s.epsilon, __dadd_rn(p, p)), 2.0);
+            a.qProp[row + i] = __dadd_rn(a.qAcc[row + i], mv);
+        }
+    } else {
+        for (int i = lane; i < n; i += 32) a.qProp[row + i] = a.qAcc[row + i];   // :586
+    }
+    if (lane == 0) {
+        a.sc[c] = s;
+        a.leapSteps[c] = s.steps;
+        atomicMax(&a.counters[0], s.steps);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// After gradient number k of a trajectory (k = 0 .. steps): the momentum update
+// that uses it (:618-620, :628-630, :646-648), the U-turn test (:633-638) and
+// the position update that precedes gradient k+1 (:624-626, :641-643).
+// countPotentials = calls of Potential() one gradient made (2n for finite
+// differences, :436-438).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+kHmcKickDrift(HmcArrays a, int n, int chains, int k, int countPotentials) {
+    extern __shared__ double smemD[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * kWarpsPerBlock + warp;
+    if (c >= chains) return;
+    const int steps = a.leapSteps[c];
+    if (steps < 1 || k > steps) return;
+    double* buf = smemD + (size_t)warp * n;
+    const size_t row = (size_t)c * n;
+    HmcScalars* sp = a.sc + c;
+    const double eps = sp->epsilon;
+    const bool half = (k == 0) || (k == steps);
+    for (int i = lane; i < n; i += 32) {
+        double kick = __dmul_rn(eps, a.grad[row + i]);
+        if (half) kick = __ddiv_rn(kick, 2.0);
+        const double p = __dsub_rn(a.pProp[row + i], kick);
+        a.pProp[row + i] = p;
+        if (!half) buf[i] = __dmul_rn(p, a.p0[row + i]);                  // :635
+        if (k < steps) a.qProp[row + i] = __dadd_rn(a.qProp[row + i], __dmul_rn(eps, p));
+    }
+    __syncwarp();
+    bool reversed = false;
+    if (!half) {
+        const double inner = warpSeqSum(buf, n);
+        reversed = !(inner >= 0.0);                                       // :637-638
+    }
+    if (lane == 0) {
+        sp->gradientCount += 1;                                           // :469
+        if (countPotentials) sp->potentialCount += countPotentials;
+        if (reversed) sp->okLeap = 2;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// User gradient of TDummyLogLikelihood (TDummyLogLikelihood.H:34-42) with the
+// sign flip of PotentialGradient (:478-487), for all chains at once:
+//   g = 0;  g -= Error(i,j)*p[j]  (j ascending);  grad[i] = -g.
+// A 64 x 64 x 8 shared-memory tiled contraction X[E x n] . Error^T with 4 x 4
+// outputs per thread.  Multiply and subtract are separate roundings and the j
+// order is the reference's, so every entry is bit-identical to the host loop.
+// ---------------------------------------------------------------------------
+constexpr int kGemmBM = 64, kGemmBN = 64, kGemmBK = 8;
+
+__global__ void __launch_bounds__(256)
+kDummyGradient(const double* __restrict__ x, const double* __restrict__ err, double* __restrict__ grad,
+               const int* __restrict__ leapSteps, int k, int chains, int n) {
+    __shared__ double As[kGemmBK][kGemmBM + 2];
+    __shared__ double Bs[kGemmBK][kGemmBN + 2];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int c0 = blockIdx.y * kGemmBM, i0 = blockIdx.x * kGemmBN;
+    double acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[r][q] = 0.0;
+    const int lr = threadIdx.x >> 2;          // 0..63: row of the tile this thread loads
+    const int lk = (threadIdx.x & 3) * 2;     // 0,2,4,6
+    for (int k0 = 0; k0 < n; k0 += kGemmBK) {
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+            const int kk = k0 + lk + d;
+            double av = 0.0, bv = 0.0;
+            if (kk < n) {
+                if (c0 + lr < chains) av = x[(size_t)(c0 + lr) * n + kk];
+                if (i0 + lr < n) bv = err[(size_t)(i0 + lr) * n + kk];
+            }
+            As[lk + d][lr] = av;
+            Bs[lk + d][lr] = bv;
+        }
+        __syncthreads();
+        const int kmax = min(kGemmBK, n - k0);
+        for (int kk = 0; kk < kmax; ++kk) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) av[r] = As[kk][ty * 4 + r];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) bv[q] = Bs[kk][tx * 4 + q];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[r][q] = __dsub_rn(acc[r][q], __dmul_rn(bv[q], av[r]));
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int c = c0 + ty * 4 + r;
+        if (c >= chains) continue;
+        const int steps = leapSteps[c];
+        if (steps < 1 || k > steps) continue;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = i0 + tx * 4 + q;
+            if (i < n) grad[(size_t)c * n + i] = -acc[r][q];
+        }
+    }
+}
+
+// CovariantGradient (:447-454): grad[i] = sum_j fEstimatedError(i,j)*(point[j]-fAveragePoint[j]).
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+kHmcCovariantGradient(HmcArrays a, int n, int chains, int k) {
+    extern __shared__ double smemD[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * kWarpsPerBlock + warp;
+    if (c >= chains) return;
+    const int steps = a.leapSteps[c];
+    if (steps < 1 || k > steps) return;
+    double* d = smemD + (size_t)warp * n;
+    const size_t row = (size_t)c * n;
+    for (int j = lane; j < n; j += 32) d[j] = __dsub_rn(a.qProp[row + j], a.average[row + j]);
+    __syncwarp();
+    const double* e = a.estErr + (size_t)c * n * n;
+    for (int i = lane; i < n; i += 32) {
+        double g = 0.0;
+        for (int j = 0; j < n; ++j) g = __dadd_rn(g, __dmul_rn(e[(size_t)i * n + j], d[j]));
+        a.grad[row + i] = g;
+    }
+}
+
+// Force a flat gradient (:525-529).
+__global__ void kHmcZeroGradient(HmcArrays a, int n, int chains) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < (size_t)chains * n) a.grad[idx] = 0.0;
+}
+
+// FiniteDifferenceGradient (:417-444), stage 1: the 2n displaced copies of each
+// chain's position.  work[((c*n + i)*2 + s)*n + j].
+__global__ void kHmcFdPoints(const double* __restrict__ q, double* __restrict__ work, int chainBase,
+                             int chainCount, int n) {
+    const size_t total = (size_t)chainCount * n * 2 * n;
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int j = (int)(idx % n);
+    size_t r = idx / n;
+    const int sgn = (int)(r & 1);
+    r >>= 1;
+    const int i = (int)(r % n);
+    const int c = (int)(r / n);
+    double v = q[(size_t)(chainBase + c) * n + j];
+    if (j == i) {
+        const double du = 0.01;                                           // :434
+        v = __dsub_rn(v, du);                                             // :435
+        if (sgn) v = __dadd_rn(v, __dmul_rn(2.0, du));                    // :437
+    }
+    work[idx] = v;
+}
+
+// ... stage 2: grad[i] = 0.5*(u2-u1)/du with u = -log(likelihood) (:439, :413).
+__global__ void kHmcFdGradient(const double* __restrict__ llh, double* __restrict__ grad,
+                               const int* __restrict__ leapSteps, int k, int chainBase, int chainCount, int n) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)chainCount * n) return;
+    const int c = chainBase + (int)(idx / n);
+    const int steps = leapSteps[c];
+    if (steps < 1 || k > steps) return;
+    const double u1 = -llh[idx * 2], u2 = -llh[idx * 2 + 1];
+    grad[(size_t)chainBase * n + idx] = __ddiv_rn(__dmul_rn(0.5, __dsub_rn(u2, u1)), 0.01);
+}
+
+// ---------------------------------------------------------------------------
+// After the trajectory and the likelihood of the proposed point: :302-344.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+kHmcPost(HmcArrays a, int n, int chains, const double* __restrict__ llhProp, double covWindow) {
+    extern __shared__ double smemD[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * kWarpsPerBlock + warp;
+    if (c >= chains) return;
+    double* buf = smemD + (size_t)warp * n;
+    HmcScalars s = a.sc[c];
+    if (!s.started || s.status != 0) return;
+    const size_t row = (size_t)c * n;
+    const size_t tri = (size_t)n * (n + 1) / 2;
+    s.needUpdate = 0;
+
+    if (s.leapFrogSteps > 0) {                                            // :302-323
+        if (s.okLeap != 2) {
+            if (s.meanEpsilon > 0 && s.reversalLen > s.meanEpsilon) {
+                const double targetEpsilon = __ddiv_rn(s.reversalLen, 8.0);
+                const double deltaEpsilon = __dsub_rn(targetEpsilon, s.meanEpsilon);
+                if (deltaEpsilon > 0.0) s.meanEpsilon = __dadd_rn(s.meanEpsilon, __dmul_rn(0.1, deltaEpsilon));
+            }
+            if (s.leapFrogSteps < 50) s.leapFrogSteps += 1;
+        } else {
+            const double len = fabs(__dmul_rn((double)s.leapFrogSteps, s.epsilon));
+            if (s.reversalLen < s.meanEpsilon) s.reversalLen = len;
+            else {
+                s.reversalLen = __dmul_rn(0.95, s.reversalLen);
+                s.reversalLen = __dadd_rn(s.reversalLen, __dmul_rn(0.05, len));
+            }
+            if (s.leapFrogSteps > 3) s.leapFrogSteps -= 1;
+            if (s.meanEpsilon > 0) s.meanEpsilon = __dmul_rn(s.meanEpsilon, 0.99);
+        }
+    }
+    const double proposedKinetic = warpKinetic(a.pProp + row, buf, n, lane);   // :326
+    s.potentialCount += 1;                                                // :327
+    s.propPotential = -llhProp[c];
+    const double proposedH = __dadd_rn(s.propPotential, proposedKinetic);  // :333-334
+    const double acceptedH = __dadd_rn(s.accPotential, s.initialKinetic);
+    s.deltaH = __dsub_rn(proposedH, acceptedH);                           // :346
+
+    if (s.okLeap && isfinite(s.propPotential)) {                          // :336
+        // ---- UpdateCovariance, :665-695 ----------------------------------
+        s.stepsSinceUpdate += 1;
+        s.stepsRemaining -= 1;
+        {
+            const double t = s.averageTrials, t1 = __dadd_rn(t, 1.0);
+            for (int i = lane; i < n; i += 32) {
+                double v = __dmul_rn(a.average[row + i], t);
+                v = __dadd_rn(v, a.qAcc[row + i]);
+                v = __ddiv_rn(v, t1);
+                a.average[row + i] = v;
+            }
+            s.averageTrials = fmin(covWindow, t1);
+        }
+        for (int i = lane; i < n; i += 32) buf[i] = a.qAcc[row + i];
+        __syncwarp();
+        {
+            const double t = s.covTrials, t1 = __dadd_rn(t, 1.0);
+            double* ex = a.exxt + (size_t)c * tri;
+            int i = 0, rowStart = 0;
+            for (size_t k0 = 0; k0 < tri; k0 += 32) {
+                const size_t kk = k0 + lane;
+                if (kk < tri) {
+                    int ii = i, rs = rowStart;
+                    while ((size_t)(rs + ii + 1) <= kk) { rs += ii + 1; ++ii; }
+                    const int j = (int)kk - rs;
+                    double v = __dmul_rn(ex[kk], t);
+                    v = __dadd_rn(v, __dmul_rn(buf[ii], buf[j]));
+                    v = __ddiv_rn(v, t1);
+                    ex[kk] = v;
+                }
+                const size_t nk = k0 + 32;
+                while ((size_t)(rowStart + i + 1) <= nk) { rowStart += i + 1; ++i; }
+            }
+            s.covTrials = fmin(covWindow, t1);
+        }
+        s.repaired = 0;          // fEstimatedCovariance is again fEXXT - mean mean^T
+        __syncwarp();
+        // ---- UpdateErrorMatrix up to its trigger, :703-719 ---------------
+        if (s.leapFrogSteps != 0 && !(s.covTrials < (double)(2 * n))) {
+            const double* ex = a.exxt + (size_t)c * tri;
+            for (int i = lane; i < n; i += 32) {
+                const double m = a.average[row + i];
+                buf[i] = fabs(__dsub_rn(ex[triIndex(i, i)], __dmul_rn(m, m)));
+            }
+            __syncwarp();
+            s.curCovTrace = warpSeqSum(buf, n);
+            const double change = fabs(__dsub_rn(s.curCovTrace, s.estCovTrace));
+            bool doIt = false;
+            if (s.stepsRemaining < 0) doIt = true;
+            if ((double)s.stepsSinceUpdate > __dmul_rn(2.0, (double)n) &&
+                change > __dmul_rn(0.01, s.estCovTrace)) doIt = true;
+            if (doIt) {
+                s.needUpdate = 1;
+                if (lane == 0) {
+                    const int slot = atomicAdd(&a.counters[1], 1);
+                    a.updateList[slot] = c;
+                }
+            }
+        }
+    } else {
+        if (s.meanEpsilon > 0) s.meanEpsilon = __dmul_rn(0.3, s.meanEpsilon);   // :343
+    }
+    if (lane == 0) a.sc[c] = s;
+}
+
+// Copy the average points of the chains in the update list to a dense array.
+__global__ void kHmcGatherAverage(HmcArrays a, int n, int count, double* __restrict__ out) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)count * n) return;
+    const int c = a.updateList[idx / n];
+    out[idx] = a.average[(size_t)c * n + idx % n];
+}
+
+// Eigenvalues only of the symmetric matrix in `m` (destroyed): the rotations of
+// warpSymEigen without the eigenvector accumulation.  On return the diagonal
+// of m holds the eigenvalues (unsorted).
+__device__ void warpSymEigenValues(double* m, int n, int lane) {
+    for (int sweep = 0; sweep < 100; ++sweep) {
+        double off = 0.0;
+        for (int p = 0; p < n; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = m[(size_t)p * n + q];
+                off = __dadd_rn(off, __dmul_rn(apq, apq));
+            }
+        if (!(off > 1e-300)) break;
+        for (int p = 0; p < n; ++p) {
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = m[(size_t)p * n + q];
+                if (apq == 0.0) continue;
+                const double theta = __ddiv_rn(__dsub_rn(m[(size_t)q * n + q], m[(size_t)p * n + p]),
+                                               __dmul_rn(2.0, apq));
+                const double t = __ddiv_rn(theta >= 0 ? 1.0 : -1.0,
+                                           __dadd_rn(fabs(theta), __dsqrt_rn(__dadd_rn(__dmul_rn(theta, theta), 1.0))));
+                const double cs = __ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(__dmul_rn(t, t), 1.0)));
+                const double sn = __dmul_rn(t, cs);
+                __syncwarp();
+                for (int k = lane; k < n; k += 32) {
+                    const double akp = m[(size_t)k * n + p], akq = m[(size_t)k * n + q];
+                    m[(size_t)k * n + p] = __dsub_rn(__dmul_rn(cs, akp), __dmul_rn(sn, akq));
+                    m[(size_t)k * n + q] = __dadd_rn(__dmul_rn(sn, akp), __dmul_rn(cs, akq));
+                }
+                __syncwarp();
+                for (int k = lane; k < n; k += 32) {
+                    const double apk = m[(size_t)p * n + k], aqk = m[(size_t)q * n + k];
+                    m[(size_t)p * n + k] = __dsub_rn(__dmul_rn(cs, apk), __dmul_rn(sn, aqk));
+                    m[(size_t)q * n + k] = __dadd_rn(__dmul_rn(sn, apk), __dmul_rn(cs, aqk));
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+// TMatrixD::Invert as restated by oracle/rootshim/TMatrixD.h (Gauss-Jordan with
+// partial pivoting), warp cooperative: m (destroyed) and inv are n x n; lanes
+// split the column index of every row operation, so each entry sees the scalar
+// routine's operations in the scalar routine's order.
+__device__ void warpInvert(double* m, double* inv, int n, int lane) {
+    for (int k = lane; k < n * n; k += 32) inv[k] = (k / n == k % n) ? 1.0 : 0.0;
+    __syncwarp();
+    for (int k = 0; k < n; ++k) {
+        int piv = k;
+        double best = fabs(m[(size_t)k * n + k]);
+        for (int i = k + 1; i < n; ++i) {
+            const double v = fabs(m[(size_t)i * n + k]);
+            if (v > best) { best = v; piv = i; }
+        }
+        if (piv != k) {
+            for (int j = lane; j < n; j += 32) {
+                double t = m[(size_t)k * n + j];
+                m[(size_t)k * n + j] = m[(size_t)piv * n + j];
+                m[(size_t)piv * n + j] = t;
+                t = inv[(size_t)k * n + j];
+                inv[(size_t)k * n + j] = inv[(size_t)piv * n + j];
+                inv[(size_t)piv * n + j] = t;
+            }
+            __syncwarp();
+        }
+        const double p = m[(size_t)k * n + k];
+        __syncwarp();
+        for (int j = lane; j < n; j += 32) {
+            m[(size_t)k * n + j] = __ddiv_rn(m[(size_t)k * n + j], p);
+            inv[(size_t)k * n + j] = __ddiv_rn(inv[(size_t)k * n + j], p);
+        }
+        __syncwarp();
+        for (int i = 0; i < n; ++i) {
+            if (i == k) continue;
+            const double f = m[(size_t)i * n + k];
+            __syncwarp();
+            if (f == 0.0) continue;
+            for (int j = lane; j < n; j += 32) {
+                m[(size_t)i * n + j] = __dsub_rn(m[(size_t)i * n + j], __dmul_rn(f, m[(size_t)k * n + j]));
+                inv[(size_t)i * n + j] = __dsub_rn(inv[(size_t)i * n + j], __dmul_rn(f, inv[(size_t)k * n + j]));
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// The body of UpdateErrorMatrix (:727-858) for the chains in the update list;
+// avgLlh[idx] is the likelihood at the chain's average point (:729).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+kHmcErrorMatrix(HmcArrays a, int n, int count, const double* __restrict__ avgLlh) {
+    const int lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (idx >= count) return;
+    const int c = a.updateList[idx];
+    HmcScalars s = a.sc[c];
+    const size_t row = (size_t)c * n;
+    const size_t tri = (size_t)n * (n + 1) / 2;
+    const double* ex = a.exxt + (size_t)c * tri;
+    const double* avg = a.average + row;
+
+    s.potentialCount += 1;                                                // :729
+    const double aPot = -avgLlh[idx];
+    if (aPot < s.centralPotential) {                                      // :734-738
+        for (int i = lane; i < n; i += 32) a.central[row + i] = avg[i];
+        s.centralPotential = aPot;
+    }
+    s.stepsRemaining = 2 * n + s.stepCount;                               // :758-759
+    s.stepsSinceUpdate = 0;
+
+    int slot = 0;
+    if (lane == 0) {
+        slot = (int)((blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) % a.eigSlots);
+        while (atomicCAS(&a.eigLocks[slot], 0, 1) != 0) slot = (slot + 1) % a.eigSlots;
+        __threadfence();
+    }
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    double* m = a.eigScratch + (size_t)slot * 2 * n * n;
+    double* inv = m + (size_t)n * n;
+    auto buildCov = [&]() {                                               // :688-689
+        for (int k = lane; k < n * n; k += 32) {
+            const int i = k / n, j = k - i * n;
+            const double e = (j <= i) ? ex[triIndex(i, j)] : ex[triIndex(j, i)];
+            m[k] = __dsub_rn(e, (j <= i) ? __dmul_rn(avg[i], avg[j]) : __dmul_rn(avg[j], avg[i]));
+        }
+        __syncwarp();
+    };
+    buildCov();
+    warpSymEigenValues(m, n, lane);
+    double maxScale = 0.0, minScale = 1E+20;                              // :763-781
+    bool positiveDefinite = true;
+    for (int i = 0; i < n; ++i) {
+        const double eigen = m[(size_t)i * n + i];
+        if (maxScale < fabs(eigen)) maxScale = fabs(eigen);
+        if (minScale > fabs(eigen)) minScale = fabs(eigen);
+        if (eigen < 0) positiveDefinite = false;
+    }
+    double* diag = a.repairedDiag + row;
+    if (!positiveDefinite) {                                              // :792-806
+        // floor the variances, drop every correlation: the matrix is diagonal
+        // from here on, its eigenvalues are its diagonal, and the second pass
+        // of the loop (:766-782) always ends it.
+        double r = __dmul_rn(s.estCovTrace, 1E-6);
+        r = __ddiv_rn(r, (double)n);
+        r = fabs(r);
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
+            double v = __dsub_rn(ex[triIndex(i, i)], __dmul_rn(avg[i], avg[i]));
+            if (v < r) v = r;
+            diag[i] = v;
+        }
+        __syncwarp();
+        __threadfence_block();
+        for (int i = 0; i < n; ++i) {
+            const double eigen = diag[i];
+            if (maxScale < fabs(eigen)) maxScale = fabs(eigen);
+            if (minScale > fabs(eigen)) minScale = fabs(eigen);
+        }
+        s.repaired = 1;
+    }
+    s.curCovTrace = 0.0;                                                  // :813-817
+    for (int i = 0; i < n; ++i) {
+        const double v = s.repaired ? diag[i] : __dsub_rn(ex[triIndex(i, i)], __dmul_rn(avg[i], avg[i]));
+        s.curCovTrace = __dadd_rn(s.curCovTrace, fabs(v));
+    }
+    s.estCovTrace = s.curCovTrace;
+    maxScale = __dsqrt_rn(maxScale);                                      // :820-825
+    if (maxScale < 0.1) maxScale = 0.1;
+    minScale = __dsqrt_rn(minScale);
+    if (minScale < 0.01) minScale = 0.01;
+    s.orbitLength = __dmul_rn(__dmul_rn(2.0, 3.14), maxScale);            // :828
+    if (s.meanEpsilon > 0) {                                              // :833-837
+        s.meanEpsilon = __dmul_rn(0.2, maxScale);
+        if (s.meanEpsilon > __dmul_rn(0.5, minScale)) s.meanEpsilon = __dmul_rn(0.5, minScale);
+        if (s.meanEpsilon < __dmul_rn(0.05, maxScale)) s.meanEpsilon = __dmul_rn(0.05, maxScale);
+    }
+    if (s.leapFrogSteps > 0) {                                            // :839-847
+        const double targetLength = __dmul_rn(0.4, s.orbitLength);
+        s.leapFrogSteps = (int)__ddiv_rn(targetLength, fabs(s.meanEpsilon));
+        s.leapFrogSteps = 2 * (s.leapFrogSteps / 2 + 1);
+        if (s.leapFrogSteps > 3 * n) s.leapFrogSteps = 3 * n;
+        if (s.meanEpsilon > 0) s.meanEpsilon = __ddiv_rn(targetLength, (double)s.leapFrogSteps);
+    }
+    if (a.estErr) {                                                       // :849-850
+        if (s.repaired) {
+            for (int k = lane; k < n * n; k += 32) {
+                const int i = k / n, j = k - i * n;
+                m[k] = (i == j) ? diag[i] : 0.0;
+            }
+            __syncwarp();
+        } else {
+            buildCov();
+        }
+        warpInvert(m, inv, n, lane);
+        double* e = a.estErr + (size_t)c * n * n;
+        for (int k = lane; k < n * n; k += 32) e[k] = inv[k];
+    }
+    __syncwarp();
+    __threadfence();
+    if (lane == 0) {
+        atomicExch(&a.eigLocks[slot], 0);
+        a.sc[c] = s;
+    }
+}
+
+struct HmcTraceDev {
+    double* potential;    // fAcceptedPotential after the step ("LogLikelihood" branch :139)
+    double* points;       // fAccepted                          ("Accepted" :140)
+    double* meanEpsilon;  // fMeanEpsilon                       ("MeanEpsilon" :145)
+    int32_t* leapfrog;    // fLeapFrogSteps                     ("Leapfrog" :147)
+    int32_t* accepted;    // 1 when the proposed point was taken
+};
+
+// The Metropolis test on the Hamiltonian and the commit, :346-395.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+kHmcAccept(HmcArrays a, int n, int chains, uint64_t seed, uint32_t chainOffset, uint32_t step,
+           uint32_t slot, HmcTraceDev tr, int traceStep) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (c >= chains) return;
+    HmcScalars s = a.sc[c];
+    if (!s.started || s.status != 0) return;
+    const size_t row = (size_t)c * n;
+    const double u = __dmul_rn(1.0, smcmc_uniform(seed, chainOffset + (uint32_t)c, step, slot, SMCMC_STREAM_STEP));
+    const double trial = -log(u);                                         // :347
+    const bool reject = (s.deltaH > trial) || !isfinite(s.deltaH);        // :348
+    if (reject) {
+        for (int i = lane; i < n; i += 32) a.pAcc[row + i] = -a.pAcc[row + i];            // :364-366
+        s.acceptance = __ddiv_rn(__dmul_rn(s.acceptance, 4999.0), 5000.0);               // :367
+    } else {
+        for (int i = lane; i < n; i += 32) {                              // :380-383
+            a.qAcc[row + i] = a.qProp[row + i];
+            a.pAcc[row + i] = a.pProp[row + i];
+        }
+        s.accPotential = s.propPotential;                                 // :384
+        s.acceptance = __ddiv_rn(__dadd_rn(__dmul_rn(s.acceptance, 4999.0), 1.0), 5000.0);   // :386
+    }
+    __syncwarp();
+    if (s.accPotential < s.centralPotential) {                            // :393-395
+        for (int i = lane; i < n; i += 32) a.central[row + i] = a.qAcc[row + i];
+        s.centralPotential = s.accPotential;
+    }
+    if (lane == 0) a.sc[c] = s;
+    if (traceStep >= 0) {
+        const size_t r = (size_t)traceStep * chains + c;
+        if (lane == 0) {
+            if (tr.potential) tr.potential[r] = s.accPotential;
+            if (tr.meanEpsilon) tr.meanEpsilon[r] = s.meanEpsilon;
+            if (tr.leapfrog) tr.leapfrog[r] = s.leapFrogSteps;
+            if (tr.accepted) tr.accepted[r] = reject ? 0 : 1;
+        }
+        if (tr.points)
+            for (int i = lane; i < n; i += 32) tr.points[r * n + i] = a.qAcc[row + i];
+    }
+}
+
+}  // namespace smcmc

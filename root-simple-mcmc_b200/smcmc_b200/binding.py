@@ -70,6 +70,21 @@ class _SavedState(ctypes.Structure):
     _fields_ = [(name, ctypes.c_void_p) for name, _, _ in _SAVED_FIELDS]
 
 
+# smcmc_hmc_setting / smcmc_hmc_field / scalar columns of SMCMC_HMC_F_SCALARS
+HMC_ALPHA, HMC_MEAN_EPSILON, HMC_LEAPFROG, HMC_USER_GRADIENT, HMC_KEEP_ERROR_MATRIX = range(5)
+_HMC_FIELDS = {"accepted": (0, "En"), "momentum": (1, "En"), "proposed": (2, "En"), "central": (3, "En"),
+               "average": (4, "En"), "covariance": (5, "Enn"), "error_matrix": (6, "Enn"), "scalars": (7, "Es")}
+HMC_SCALARS = ["acceptance", "mean_epsilon", "leapfrog", "reversal_len", "accepted_potential",
+               "proposed_potential", "central_potential", "potential_count", "gradient_count", "step_count",
+               "cov_trials", "average_trials", "est_cov_trace", "cur_cov_trace", "orbit_length",
+               "steps_remaining", "steps_since_update"]
+
+
+class _HmcTrace(ctypes.Structure):
+    _fields_ = [("potential", ctypes.c_void_p), ("points", ctypes.c_void_p), ("mean_epsilon", ctypes.c_void_p),
+                ("leapfrog", ctypes.c_void_p), ("accepted", ctypes.c_void_p)]
+
+
 class _Trace(ctypes.Structure):
     _fields_ = [("accepted", ctypes.c_void_p), ("llh_accepted", ctypes.c_void_p),
                 ("llh_proposed", ctypes.c_void_p), ("points", ctypes.c_void_p),
@@ -131,6 +146,12 @@ def load_library():
         "smcmc_restore_state": (ci, [vp, ctypes.POINTER(_SavedState), vp]),
         "smcmc_get_step_index": (ci, [vp, ctypes.POINTER(ctypes.c_uint32)]),
         "smcmc_set_step_index": (ci, [vp, ctypes.c_uint32]),
+        "smcmc_hmc_set": (ci, [vp, ci, cd]),
+        "smcmc_hmc_start": (ci, [vp, vp]),
+        "smcmc_hmc_set_position": (ci, [vp, vp]),
+        "smcmc_hmc_step": (ci, [vp, ci, ci]),
+        "smcmc_hmc_step_trace": (ci, [vp, ci, ci, ctypes.POINTER(_HmcTrace)]),
+        "smcmc_hmc_get": (ci, [vp, ci, vp, ctypes.c_size_t]),
         "smcmc_launch_count": (ctypes.c_int64, [vp]),
         "smcmc_pair_kernel_stats": (ci, [vp, ctypes.POINTER(cd), ctypes.POINTER(ctypes.c_int64), ci]),
         "smcmc_enable_kernel_timing": (ci, [vp, ci]),
@@ -154,6 +175,8 @@ EXPORTED_SYMBOLS = [
     "smcmc_dummy_set_error", "smcmc_eval", "smcmc_start", "smcmc_step",
     "smcmc_step_trace", "smcmc_get", "smcmc_save_state", "smcmc_restore_state",
     "smcmc_get_step_index", "smcmc_set_step_index", "smcmc_launch_count",
+    "smcmc_hmc_set", "smcmc_hmc_start", "smcmc_hmc_set_position", "smcmc_hmc_step",
+    "smcmc_hmc_step_trace", "smcmc_hmc_get",
     "smcmc_pair_kernel_stats", "smcmc_enable_kernel_timing",
     "smcmc_measure_fp64_peak",
 ]
@@ -351,6 +374,51 @@ class Engine:
         if "step_index" in saved:
             self._check(self.lib.smcmc_set_step_index(self.h, int(np.asarray(saved["step_index"]).reshape(-1)[0])))
         return mismatch
+
+    # -- sMCMC::TSimpleHMC (TSimpleHMC.H:119-973) -----------------------------------
+    def hmc_set(self, setting, value):
+        """SetAlpha / SetMeanEpsilon / SetLeapFrog, and the two template choices."""
+        self._check(self.lib.smcmc_hmc_set(self.h, setting, float(value)))
+
+    def hmc_start(self, x0):
+        x0 = np.ascontiguousarray(np.broadcast_to(np.asarray(x0, dtype=np.float64), (self.chains, self.dim)))
+        self._check(self.lib.smcmc_hmc_start(self.h, _ptr(x0)))
+
+    def hmc_set_position(self, x):
+        x = np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), (self.chains, self.dim)))
+        self._check(self.lib.smcmc_hmc_set_position(self.h, _ptr(x)))
+
+    def hmc_step(self, nsteps=1, gradient_type=0):
+        self._check(self.lib.smcmc_hmc_step(self.h, nsteps, gradient_type))
+
+    def hmc_step_trace(self, nsteps, gradient_type=0,
+                       want=("potential", "points", "mean_epsilon", "leapfrog", "accepted")):
+        """Step(save=true): the per-step record of the output tree (:139-147)."""
+        E, n = self.chains, self.dim
+        shapes = {"potential": ((nsteps, E), np.float64), "points": ((nsteps, E, n), np.float64),
+                  "mean_epsilon": ((nsteps, E), np.float64), "leapfrog": ((nsteps, E), np.int32),
+                  "accepted": ((nsteps, E), np.int32)}
+        out = {}
+        tr = _HmcTrace()
+        for name in want:
+            shape, dt = shapes[name]
+            out[name] = np.zeros(shape, dt)
+            setattr(tr, name, out[name].ctypes.data)
+        self._check(self.lib.smcmc_hmc_step_trace(self.h, nsteps, gradient_type, ctypes.byref(tr)))
+        return out
+
+    def hmc_get(self, name):
+        fid, code = _HMC_FIELDS[name]
+        E, n = self.chains, self.dim
+        shape = {"En": (E, n), "Enn": (E, n, n), "Es": (E, len(HMC_SCALARS))}[code]
+        out = np.zeros(shape)
+        self._check(self.lib.smcmc_hmc_get(self.h, fid, _ptr(out), out.nbytes))
+        return out
+
+    def hmc_scalars(self):
+        """dict name -> array[chains] of the scalar members (HMC_SCALARS)."""
+        s = self.hmc_get("scalars")
+        return {k: s[:, i] for i, k in enumerate(HMC_SCALARS)}
 
     # -- instrumentation -----------------------------------------------------------
     def launch_count(self):

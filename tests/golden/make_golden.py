@@ -156,7 +156,44 @@ def make_chains():
     print("chains.npz: %d arrays" % len(out))
 
 
+def make_hmc():
+    """TSimpleHMC chains of the reference build (TSimpleHMC.H:119-973)."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from helpers import HMC_GOLDEN, hmc_error_matrix
+    fields = {"alpha": cc.HMC_ALPHA, "mean_epsilon": cc.HMC_MEAN_EPSILON, "leapfrog": cc.HMC_LEAPFROG}
+    out = {}
+    _, err100 = cc.ref_dummy_matrices()
+    for name, cfg in HMC_GOLDEN.items():
+        c = cc.CpuHmc("ref", cfg["kind"], cfg["dim"], cfg["grad"], cfg["seed"], cfg["chain"])
+        if "error" in cfg:
+            key = "error_" + cfg["error"]
+            if key not in out:
+                out[key] = err100 if cfg["error"] == "dummy100" else hmc_error_matrix(cfg["error"])
+            # (the reference build keeps its own static matrix; the file carries it for the others)
+        for f, v in cfg.get("pre", ()):
+            c.set(fields[f], v)
+        c.start(np.full(cfg["dim"], cfg["x0"]))
+        for f, v in cfg.get("post", ()):
+            c.set(fields[f], v)
+        tr = c.step(cfg["nsteps"], cfg["gtype"])
+        st = c.state()
+        for k in ("potential", "x", "epsilon", "leapfrog"):
+            out[name + "__" + k] = tr[k]
+        out[name + "__final_scalars"] = np.array([st[k] for k in cc.HMC_STATE_FIELDS])
+        for k in ("accepted", "momentum", "central", "average", "covariance", "error"):
+            out[name + "__final_" + k] = st[k]
+        print("  %-20s acceptance %.3f  leapfrog %d  epsilon %.4g  gradients %d" % (
+            name, st["acceptance"], st["leapfrog"], st["mean_epsilon"], st["gradient_count"]))
+    np.savez_compressed(os.path.join(HERE, "hmc.npz"), **out)
+    print("hmc.npz: %d arrays" % len(out))
+
+
 if __name__ == "__main__":
     cc.build()
-    make_fake()
-    make_chains()
+    which = sys.argv[1:] or ["fake", "chains", "hmc"]
+    if "fake" in which:
+        make_fake()
+    if "chains" in which:
+        make_chains()
+    if "hmc" in which:
+        make_hmc()

@@ -45,3 +45,70 @@ GOLDEN_CHAINS = {
     "dummy100": (1, 100, 9, 0, 1200, None),
     "unit6_clamped": (0, 6, 3, 4, 1500, None),
 }
+
+
+# ---------------------------------------------------------------------------
+# TSimpleHMC golden chains (tests/golden/hmc.npz, made by make_golden.py with
+# the reference build).  name -> settings; "error" names the matrix stored in
+# the file for TDummyLogLikelihood chains.
+#   pre / post: (setting name, value) applied before / after Start()
+#   (Start() resets the mean epsilon, TSimpleHMC.H:229, so a fixed step size
+#   has to be set afterwards, as SimpleAHMC.C does).
+# ---------------------------------------------------------------------------
+HMC_GOLDEN = {
+    # SimpleHMC.C: the as-shipped 100-dimensional TDummyLogLikelihood with its own
+    # gradient functor, automatic step size and trajectory length; long enough
+    # for UpdateErrorMatrix (covariance trials >= 2 dim, :705) to fire
+    "dummy100_user": dict(kind=1, dim=100, grad=True, seed=28, chain=0, nsteps=260, gtype=0, x0=1.0, error="dummy100"),
+    # SimpleAHMC.C: the covariant approximate gradient (type 2, :447-454)
+    "dummy100_covariant": dict(kind=1, dim=100, grad=True, seed=23, chain=5, nsteps=260, gtype=2, x0=0.3, error="dummy100"),
+    # fixed trajectory (SetLeapFrog), fixed step size (negative mean epsilon),
+    # partial momentum refresh (SetAlpha), forced user gradient (type 4)
+    "dummy100_fixed": dict(kind=1, dim=100, grad=True, seed=24, chain=1, nsteps=200, gtype=4, x0=0.2, error="dummy100",
+                           pre=(("leapfrog", 7), ("alpha", 0.3)), post=(("mean_epsilon", -0.11),)),
+    # TSimpleHMC<L>: finite-difference gradient (:417-444)
+    "dummy100_finite": dict(kind=1, dim=100, grad=False, seed=29, chain=2, nsteps=40, gtype=0, x0=0.4, error="dummy100"),
+    "unit6_finite": dict(kind=0, dim=6, grad=False, seed=22, chain=0, nsteps=300, gtype=0, x0=0.5),
+    # a box-constrained target whose gradient functor declines (THorrificLogLikelihood.H:41-43):
+    # finite differences, proposals that leave the box see -1e30
+    "horrific75_finite": dict(kind=2, dim=75, grad=True, seed=25, chain=2, nsteps=120, gtype=0, x0=0.0),
+    # zero gradient (type 5), and the single-approximate-step mode SetLeapFrog(0) (:598-611)
+    "unit5_flat": dict(kind=0, dim=5, grad=False, seed=26, chain=4, nsteps=200, gtype=5, x0=0.1),
+    "unit5_forced": dict(kind=0, dim=5, grad=False, seed=27, chain=6, nsteps=200, gtype=0, x0=0.1,
+                         pre=(("leapfrog", 0),)),
+}
+
+# Chains the reference build cannot run (its TDummyLogLikelihood is hard-wired to
+# 100 dimensions): the device is compared with the oracle port, which the golden
+# chains above pin to the reference.
+HMC_PORT_ONLY = {
+    "dummy16_user": dict(kind=1, dim=16, grad=True, seed=31, chain=3, nsteps=400, gtype=0, x0=1.0, error="spd16"),
+    "dummy10_covariant": dict(kind=1, dim=10, grad=True, seed=33, chain=5, nsteps=400, gtype=2, x0=0.3, error="spd10"),
+    "dummy37_user": dict(kind=1, dim=37, grad=True, seed=34, chain=9, nsteps=300, gtype=0, x0=-0.6, error="spd37"),
+    "asym7_finite": dict(kind=3, dim=7, grad=False, seed=35, chain=1, nsteps=200, gtype=0, x0=0.05),
+}
+
+
+def hmc_error_matrix(name):
+    """Deterministic SPD precision matrices for the TDummyLogLikelihood chains."""
+    n = int(name[3:])
+    rng = np.random.default_rng(1000 + n)
+    a = rng.normal(size=(n, n))
+    m = a @ a.T / n + np.diag(rng.uniform(0.5, 2.0, n))
+    return 0.5 * (m + m.T)
+
+
+def hmc_scalar_mask(scalars, dim):
+    """The reference never initialises fCurrentCovarianceTrace and
+    fEstimatedOrbitLength (TSimpleHMC.H:130-134, :210-269): they hold garbage
+    until UpdateErrorMatrix assigns them (:708, :828).  True where a scalar of
+    the HMC_STATE_FIELDS block is defined."""
+    names = ["acceptance", "mean_epsilon", "leapfrog", "reversal_len", "accepted_potential",
+             "proposed_potential", "central_potential", "potential_count", "gradient_count",
+             "step_count", "cov_trials", "average_trials", "est_cov_trace", "cur_cov_trace",
+             "orbit_length", "steps_remaining", "steps_since_update"]
+    s = dict(zip(names, scalars))
+    mask = np.ones(len(names), bool)
+    mask[names.index("cur_cov_trace")] = s["leapfrog"] != 0 and s["cov_trials"] >= 2 * dim
+    mask[names.index("orbit_length")] = s["steps_remaining"] > 0
+    return mask

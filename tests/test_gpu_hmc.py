@@ -1,0 +1,134 @@
+"""Step-for-step parity of the device TSimpleHMC ensemble with the reference:
+TSimpleHMC::Step (TSimpleHMC.H:279-401), LeapFrog (:582-651), the gradient
+variants (:417-532), UpdateCovariance / UpdateErrorMatrix (:665-858), driven by
+identical draws (include/smcmc_rng.h).
+
+Required: the accepted position and potential after every step, the adapted
+mean step size and the trajectory length are those of the reference -- bit for
+bit except for the one libm call in the loop (log of the accept draw, :347;
+CUDA's log and glibc's can differ in the last ulp, which only matters at a
+knife edge) -- and the final adaptive state (running mean, covariance estimate,
+error matrix, counters) is identical.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import HMC_GOLDEN, HMC_PORT_ONLY, golden, golden_chain, hmc_error_matrix, hmc_scalar_mask
+
+pytestmark = pytest.mark.gpu
+
+
+def device_hmc(cfg, error, chains=4):
+    import smcmc_b200
+    from smcmc_b200 import binding as b
+    assert torch.cuda.is_available()
+    lo = max(0, cfg["chain"] - 1)
+    eng = smcmc_b200.Engine(cfg["kind"], cfg["dim"], chains, seed=cfg["seed"], chain_offset=lo)
+    if error is not None:
+        eng.set_error_matrix(error)
+    # THorrificLogLikelihood's gradient functor exists but declines (:41-43):
+    # the same as having none
+    eng.hmc_set(b.HMC_USER_GRADIENT, 1 if (cfg["grad"] and cfg["kind"] == 1) else 0)
+    if cfg["gtype"] == 2:
+        eng.hmc_set(b.HMC_KEEP_ERROR_MATRIX, 1)
+    fields = {"alpha": b.HMC_ALPHA, "mean_epsilon": b.HMC_MEAN_EPSILON, "leapfrog": b.HMC_LEAPFROG}
+    for f, v in cfg.get("pre", ()):
+        eng.hmc_set(fields[f], v)
+    eng.hmc_start(np.full(cfg["dim"], cfg["x0"]))
+    for f, v in cfg.get("post", ()):
+        eng.hmc_set(fields[f], v)
+    tr = eng.hmc_step_trace(cfg["nsteps"], cfg["gtype"])
+    return eng, tr, cfg["chain"] - lo
+
+
+def check_against(eng, tr, c, want_tr, want_scalars, want_arrays, keep_error):
+    from smcmc_b200 import binding as b
+    assert np.array_equal(tr["leapfrog"][:, c], want_tr["leapfrog"])
+    assert np.array_equal(tr["mean_epsilon"][:, c], want_tr["epsilon"])
+    assert np.array_equal(tr["potential"][:, c], want_tr["potential"])
+    assert np.array_equal(tr["points"][:, c], want_tr["x"])
+    sc = eng.hmc_get("scalars")[c]
+    mask = hmc_scalar_mask(want_scalars, eng.dim)
+    assert np.array_equal(sc[mask], want_scalars[mask]), list(zip(b.HMC_SCALARS, sc, want_scalars))
+    for dev, ref in (("accepted", "accepted"), ("momentum", "momentum"), ("central", "central"),
+                     ("average", "average"), ("covariance", "covariance")):
+        assert np.array_equal(eng.hmc_get(dev)[c], want_arrays[ref], equal_nan=True), dev
+    if keep_error:
+        assert np.array_equal(eng.hmc_get("error_matrix")[c], want_arrays["error"], equal_nan=True)
+
+
+@pytest.mark.parametrize("name", sorted(HMC_GOLDEN))
+def test_hmc_golden_chain(name):
+    """Chain `id` of a 4-chain ensemble equals the golden run of the reference
+    build for that chain id."""
+    g = golden("hmc.npz")
+    want = golden_chain(g, name)
+    cfg = HMC_GOLDEN[name]
+    err = g["error_" + cfg["error"]] if "error" in cfg else None
+    eng, tr, c = device_hmc(cfg, err)
+    arrays = {k: want["final_" + k] for k in ("accepted", "momentum", "central", "average", "covariance", "error")}
+    check_against(eng, tr, c, want, want["final_scalars"], arrays, cfg["gtype"] == 2)
+
+
+@pytest.mark.parametrize("name", sorted(HMC_PORT_ONLY))
+def test_hmc_against_the_port(name):
+    """Dimensions the reference build cannot run: every chain of an 8-chain
+    ensemble equals the oracle port's chain with the same id."""
+    from oracle import cpu_checkers as cc
+    from test_oracle import run_cpu_hmc
+    cfg = dict(HMC_PORT_ONLY[name])
+    err = hmc_error_matrix(cfg["error"]) if "error" in cfg else None
+    eng, tr, _ = device_hmc(cfg, err, chains=8)
+    lo = max(0, cfg["chain"] - 1)
+    for c in range(8):
+        one = dict(cfg, chain=lo + c)
+        otr, st = run_cpu_hmc(cc, "orc", one, err)
+        scal = np.array([st[k] for k in cc.HMC_STATE_FIELDS])
+        check_against(eng, tr, c, otr, scal, st, cfg["gtype"] == 2)
+
+
+def test_hmc_ensemble_samples_the_target():
+    """2048 chains on a correlated 24-dimensional Gaussian: ensemble mean and
+    covariance after burn-in agree with the target (posterior mean 0,
+    covariance = inverse of the precision matrix)."""
+    import smcmc_b200
+    from smcmc_b200 import binding as b
+    n, E = 24, 2048
+    prec = hmc_error_matrix("spd24")
+    eng = smcmc_b200.Engine(smcmc_b200.LLH_DUMMY, n, E, seed=5)
+    eng.set_error_matrix(prec)
+    eng.hmc_set(b.HMC_USER_GRADIENT, 1)
+    eng.hmc_start(np.zeros(n))
+    eng.hmc_step(150)
+    pts = []
+    for _ in range(10):
+        eng.hmc_step(10)
+        pts.append(eng.hmc_get("accepted"))
+    x = np.concatenate(pts)
+    cov = np.linalg.inv(prec)
+    assert np.all(np.abs(x.mean(0)) < 0.05)
+    got = np.cov(x.T)
+    assert np.max(np.abs(got - cov)) < 0.08 * np.max(np.diag(cov))
+    sc = eng.hmc_scalars()
+    assert np.all(sc["step_count"] == 250)
+    assert 0.3 < np.mean(sc["acceptance"]) < 1.0
+
+
+def test_hmc_errors():
+    import smcmc_b200
+    from smcmc_b200 import binding as b
+    eng = smcmc_b200.Engine(smcmc_b200.LLH_UNIT_GAUSS, 4, 2, seed=1)
+    with pytest.raises(smcmc_b200.SmcmcError) as ei:
+        eng.hmc_step(1)                       # "Must initialize starting point", TSimpleHMC.H:280-284
+    assert ei.value.status == -1
+    with pytest.raises(smcmc_b200.SmcmcError):
+        eng.hmc_set(b.HMC_USER_GRADIENT, 1)   # the documentation likelihood has no gradient functor
+    eng.hmc_start(np.zeros(4))
+    with pytest.raises(smcmc_b200.SmcmcError) as ei:
+        eng.hmc_step(1, 4)                    # type 4 without a user gradient: the reference's bare throw (:521)
+    assert ei.value.status == -2
+    with pytest.raises(smcmc_b200.SmcmcError):
+        eng.hmc_step(1, 2)                    # covariant gradient needs the error matrix
+    eng.hmc_step(3)
+    assert np.all(eng.hmc_scalars()["step_count"] == 3)

@@ -145,3 +145,61 @@ def test_restore_matches_golden(checkers, have_ref, which):
     for k in ("accepted", "llh_accepted", "llh_proposed", "x", "sigma"):
         assert np.array_equal(tr[k], want[k]), k
     assert np.array_equal(np.array([b.state()[k] for k in cc.STATE_FIELDS]), want["final_scalars"])
+
+
+# ---------------------------------------------------------------------------
+# TSimpleHMC (TSimpleHMC.H:119-973)
+# ---------------------------------------------------------------------------
+from helpers import HMC_GOLDEN, HMC_PORT_ONLY, hmc_error_matrix, hmc_scalar_mask  # noqa: E402
+
+
+def run_cpu_hmc(cc, which, cfg, error):
+    fields = {"alpha": cc.HMC_ALPHA, "mean_epsilon": cc.HMC_MEAN_EPSILON, "leapfrog": cc.HMC_LEAPFROG}
+    c = cc.CpuHmc(which, cfg["kind"], cfg["dim"], cfg["grad"], cfg["seed"], cfg["chain"])
+    if error is not None and which == "orc":
+        c.set_error_matrix(error)
+    for f, v in cfg.get("pre", ()):
+        c.set(fields[f], v)
+    c.start(np.full(cfg["dim"], cfg["x0"]))
+    for f, v in cfg.get("post", ()):
+        c.set(fields[f], v)
+    tr = c.step(cfg["nsteps"], cfg["gtype"])
+    return tr, c.state()
+
+
+@pytest.mark.parametrize("name", sorted(HMC_GOLDEN))
+@pytest.mark.parametrize("which", ["orc", "ref"])
+def test_hmc_chain_matches_golden_bit_for_bit(checkers, have_ref, which, name):
+    """Positions, potentials, the adapted step size and trajectory length of
+    every step, and the final state (covariance estimate, its inverse, the
+    counters) equal what the reference build produced."""
+    if which == "ref" and not have_ref:
+        pytest.skip("reference-backed checker not built here")
+    g = golden("hmc.npz")
+    want = golden_chain(g, name)
+    cfg = HMC_GOLDEN[name]
+    err = g["error_" + cfg["error"]] if "error" in cfg else None
+    tr, st = run_cpu_hmc(checkers, which, cfg, err)
+    for k in ("potential", "x", "epsilon", "leapfrog"):
+        assert np.array_equal(tr[k], want[k]), k
+    scal = np.array([st[k] for k in checkers.HMC_STATE_FIELDS])
+    mask = hmc_scalar_mask(want["final_scalars"], cfg["dim"])
+    assert np.array_equal(scal[mask], want["final_scalars"][mask])
+    for k in ("accepted", "momentum", "central", "average", "covariance", "error"):
+        assert np.array_equal(st[k], want["final_" + k], equal_nan=True), k
+
+
+def test_hmc_samples_the_target(checkers):
+    """Known-answer check of the restated sampler itself: the marginal
+    variances of a correlated Gaussian target (precision matrix P) are the
+    diagonal of P^-1."""
+    n = 6
+    prec = hmc_error_matrix("spd6")
+    c = checkers.CpuHmc("orc", checkers.LLH_DUMMY, n, True, 77, 0)
+    c.set_error_matrix(prec)
+    c.start(np.zeros(n))
+    c.step(500)
+    x = c.step(6000)["x"]
+    var = np.diag(np.linalg.inv(prec))
+    assert np.all(np.abs(x.mean(0)) < 0.15)
+    assert np.all(np.abs(x.var(0) / var - 1.0) < 0.2)
