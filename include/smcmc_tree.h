@@ -40,6 +40,24 @@ public:
     }
     long GetEntries() const { return fEntries; }
     int Write(const char* = 0) { return 0; }
+    // Reading the way the reference does (TSimpleMCMC.H:300-349, :1517-1596):
+    // SetBranchAddress binds a destination (for vectors: the address of a
+    // pointer to the vector, as ROOT wants it), GetEntry(i) fills every bound
+    // destination, SetBranchAddress(name, NULL) detaches.
+    template <class T>
+    void SetBranchAddress(const char* n, T* a) { BindRead(n, a); }
+    void SetBranchAddress(const char* n, void*) {
+        if (fD.count(n)) fD[n].dst = 0;
+        if (fI.count(n)) fI[n].dst = 0;
+        if (fV.count(n)) fV[n].dst = 0;
+    }
+    int GetEntry(long i) {
+        if (i < 0 || i >= fEntries) return 0;
+        for (auto& c : fD) if (c.second.dst) *c.second.dst = c.second.rows[i];
+        for (auto& c : fI) if (c.second.dst) *c.second.dst = c.second.rows[i];
+        for (auto& c : fV) if (c.second.dst && *c.second.dst) **c.second.dst = c.second.rows[i];
+        return 1;
+    }
     // Reading back (tests, Restore): column access by name.
     const std::vector<double>& DoubleColumn(const std::string& n) const { return fD.at(n).rows; }
     const std::vector<int>& IntColumn(const std::string& n) const { return fI.at(n).rows; }
@@ -47,16 +65,20 @@ public:
     bool HasBranch(const std::string& n) const { return fD.count(n) || fI.count(n) || fV.count(n); }
 
 private:
-    template <class T>
+    template <class T, class Dst = T*>
     struct Column {
-        const T* src;
+        const T* src = 0;
+        Dst dst = 0;
         std::vector<T> rows;
     };
+    void BindRead(const char* n, double* a) { if (fD.count(n)) fD[n].dst = a; }
+    void BindRead(const char* n, int* a) { if (fI.count(n)) fI[n].dst = a; }
+    void BindRead(const char* n, std::vector<double>** a) { if (fV.count(n)) fV[n].dst = a; }
     std::string fName, fTitle;
     long fEntries;
     std::map<std::string, Column<double> > fD;
     std::map<std::string, Column<int> > fI;
-    std::map<std::string, Column<std::vector<double> > > fV;
+    std::map<std::string, Column<std::vector<double>, std::vector<double>**> > fV;
 };
 #endif
 #endif

@@ -28,6 +28,62 @@ def program(tmp_path_factory):
     return exe
 
 
+@pytest.fixture(scope="module")
+def hmc_program(tmp_path_factory):
+    import smcmc_b200
+    if not os.path.exists(smcmc_b200.library_path()):
+        smcmc_b200.build_library()
+    exe = str(tmp_path_factory.mktemp("cpp") / "simple_hmc")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    "-o", exe, os.path.join(ROOT, "tests", "cpp", "simple_hmc.cc"),
+                    "-L", LIBDIR, "-lsmcmc_b200", "-Wl,-rpath," + LIBDIR], check=True)
+    return exe
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_hmc_program_compiles_and_refuses_to_run_without_gpu(hmc_program):
+    r = subprocess.run([hmc_program, "hmc", "1", "3"], capture_output=True, text=True)
+    assert r.returncode != 0
+    assert "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_simple_hmc_program_reproduces_reference_chain(hmc_program):
+    """SimpleHMC.C through include/TSimpleHMC.H against the golden chain of the
+    reference build.  The header builds the as-shipped error matrix itself
+    (its own inversion routine), so values agree to rounding, not bit for bit."""
+    r = subprocess.run([hmc_program, "hmc", "2", "60"], capture_output=True, text=True, check=True)
+    want = golden_chain(golden("hmc.npz"), "dummy100_user")
+    rows = re.findall(r"step (\d+) potential (\S+) x0 (\S+) eps (\S+) leap (-?\d+)", r.stdout)
+    assert len(rows) == 60
+    pot = np.array([float(x[1]) for x in rows])
+    x0 = np.array([float(x[2]) for x in rows])
+    eps = np.array([float(x[3]) for x in rows])
+    assert np.allclose(pot, want["potential"][:60], rtol=1e-7)
+    assert np.allclose(x0, want["x"][:60, 0], rtol=1e-7, atol=1e-9)
+    assert np.allclose(eps, want["epsilon"][:60], rtol=1e-9)
+    m = re.search(r"entries (\d+) expected (\d+) calls (\d+) gradients (\d+)", r.stdout)
+    assert m and m.group(1) == m.group(2) == str(2 * 61)
+    assert int(m.group(3)) == 61                        # Start + one potential per step
+    assert "caught invalid_argument: Must initialize starting point" in r.stdout
+
+
+@pytest.mark.gpu
+def test_restore_through_the_cpp_api(hmc_program):
+    """Save 300 steps + the full state to a tree, Restore() a NEW sampler from
+    it: it continues with the accept/reject sequence of the reference's own
+    restore run (reference TSimpleMCMC.H:282-352, golden chain restore7)."""
+    r = subprocess.run([hmc_program, "restore", "3", "300"], capture_output=True, text=True, check=True)
+    want = golden_chain(golden("chains.npz"), "restore7")
+    m = re.search(r"restored llh (\S+) saved (\S+) x0 (\S+) sigma (\S+) trials (\d+)", r.stdout)
+    assert m and float(m.group(1)) == float(m.group(2))
+    assert float(m.group(3)) == want["saved_accepted"][0]
+    rows = re.findall(r"step (\d+) acc (\d) llh (\S+)", r.stdout)
+    assert len(rows) == 50
+    assert np.array_equal(np.array([int(x[1]) for x in rows]), want["accepted"][:50])
+    assert np.allclose(np.array([float(x[2]) for x in rows]), want["llh_accepted"][:50], rtol=1e-12, atol=1e-13)
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_compiles_and_refuses_to_run_without_gpu(program):
     r = subprocess.run([program, "unit", "1", "3"], capture_output=True, text=True)
