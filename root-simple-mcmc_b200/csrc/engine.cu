@@ -95,13 +95,14 @@ struct smcmc_engine {
     DeviceBuffer<double> errMatrix;                 // DUMMY
     int errDim = 0;
     DeviceBuffer<PreparedEvent> fakeEvents;         // FAKE
-    DeviceBuffer<FilterEvent> fakeFilterEvents;
+    DeviceBuffer<FilterTile> fakeFilterTiles;
     DeviceBuffer<FilterChain> fakeFilterChains;
     DeviceBuffer<unsigned long long> fakeStats;
     bool exactOnly = false;
     DeviceBuffer<smcmc_event> fakeIrregular;
-    int64_t fakeClassBase[kFakeClasses] = {0, 0, 0, 0};
-    int64_t fakeClassCount[kFakeClasses] = {0, 0, 0, 0};
+    int64_t fakeClassBase[kFakeClasses] = {0, 0, 0, 0};    // padded event index, multiple of kPairTile
+    int64_t fakeClassCount[kFakeClasses] = {0, 0, 0, 0};   // events of the class, padding included
+    int64_t fakeClassReal[kFakeClasses] = {0, 0, 0, 0};
     int64_t fakeIrregularCount = 0;
     int64_t fakeEventCount = -1;
     DeviceBuffer<double> fakeData;
@@ -280,7 +281,7 @@ struct smcmc_engine {
     PairLaunch pairLaunch(int m, int stride) {
         PairLaunch L;
         L.events = fakeEvents.get();
-        L.filterEvents = fakeFilterEvents.get();
+        L.filterTiles = fakeFilterTiles.get();
         // Work items = (chunk of one class) x (tile of 256 points).  Pick the
         // chunk length so that the grid is close to a whole number of waves of
         // (SMs x resident CTAs): equal-cost items, no ragged last wave.
@@ -307,6 +308,7 @@ struct smcmc_engine {
         for (int c = 0; c < kFakeClasses; ++c) {
             L.classBase[c] = fakeClassBase[c];
             L.classCount[c] = fakeClassCount[c];
+            L.classReal[c] = fakeClassReal[c];
             L.chunkBase[c] = chunks;
             chunks += (int)((fakeClassCount[c] + chunkEvents - 1) / chunkEvents);
         }
@@ -722,22 +724,28 @@ int smcmc_fake_set_events(smcmc_engine* e, const smcmc_event* events, int64_t co
             CUDA_CHECK(cudaMemcpyAsync(hostCount, counters.get(), 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
             CUDA_CHECK(cudaStreamSynchronize(e->stream));
         }
+        // class segments are padded to whole tiles of kPairTile events
         int64_t base[8] = {0};
         int64_t total = 0;
         for (int c = 0; c < kFakeClasses; ++c) {
             base[c] = total;
             e->fakeClassBase[c] = total;
-            e->fakeClassCount[c] = (int64_t)hostCount[c];
-            total += (int64_t)hostCount[c];
+            e->fakeClassReal[c] = (int64_t)hostCount[c];
+            e->fakeClassCount[c] = ((int64_t)hostCount[c] + kPairTile - 1) / kPairTile * kPairTile;
+            total += e->fakeClassCount[c];
         }
         e->fakeIrregularCount = (int64_t)hostCount[kIrregularClass];
         e->fakeEvents.reserve(total > 0 ? total : 1);
-        e->fakeFilterEvents.reserve(total > 0 ? total : 1);
+        e->fakeFilterTiles.reserve(total > 0 ? total / kPairTile : 1);
         e->fakeIrregular.reserve(e->fakeIrregularCount > 0 ? e->fakeIrregularCount : 1);
+        if (total > 0) {
+            kFakePadEvents<<<ceilDiv(total, 256), 256, 0, e->stream>>>(e->fakeEvents.get(), e->fakeFilterTiles.get(), total);
+            e->launched();
+        }
         if (count > 0) {
             CUDA_CHECK(cudaMemcpyAsync(baseDev.get(), base, sizeof(base), cudaMemcpyHostToDevice, e->stream));
             kFakeScatter<<<ceilDiv(count, 256), 256, 0, e->stream>>>(raw.get(), count, e->fakeEvents.get(),
-                                                                   e->fakeFilterEvents.get(), baseDev.get(),
+                                                                   e->fakeFilterTiles.get(), baseDev.get(),
                                                                    counters.get() + 8, e->fakeIrregular.get(), e->forceGeneric);
             e->launched();
             CUDA_CHECK(cudaStreamSynchronize(e->stream));

@@ -71,19 +71,10 @@ constexpr int kPairThreads = 256;    // chains per CTA
 constexpr int kPairTile = 128;       // events per shared-memory tile
 constexpr int kPairChunk = 8192;     // most events per CTA work item
 constexpr int kPairCounterRows = 100;
-// Private shared-memory counters: 16 bits are enough for one chunk
-// (kPairChunk < 65536) and let four CTAs share an SM instead of two.
-#ifndef SMCMC_PAIR_COUNTER_BITS
-#define SMCMC_PAIR_COUNTER_BITS 16
-#endif
-#if SMCMC_PAIR_COUNTER_BITS == 16
-typedef uint16_t PairCounter;
+// Private shared-memory counters are 16 bits wide (a chunk has fewer than 65536
+// events), two chains per 32-bit word: four CTAs fit one SM.
 constexpr int kPairCtasPerSm = 4;
-#else
-typedef uint32_t PairCounter;
-constexpr int kPairCtasPerSm = 2;
-#endif
-static_assert(kPairChunk < (1 << SMCMC_PAIR_COUNTER_BITS), "a chunk must not overflow a counter");
+static_assert(kPairChunk < (1 << 16), "a chunk must not overflow a counter");
 
 // Pre-images of the 50 bin edges under the host's exp, and of the cut at 500:
 //   bin (1-based) of exp(l) is 1 + #{k in 1..49 : l >= gEdges[k]},
@@ -107,7 +98,8 @@ __device__ __forceinline__ int classifyEvent(const smcmc_event& e, PreparedEvent
     p.sep = e.Separation;
     bool regular = e.Type >= 0 && isfinite(p.dLog) && isfinite(p.logSigma) &&
                    isfinite(p.nomLog) && isfinite(p.sep) && p.sep >= 0.0 &&
-                   fabs(p.nomLog) <= 11.0;      // |nomLog*log2(e)| <= 16: filter guard
+                   fabs(p.nomLog) <= 11.0 &&    // |nomLog*log2(e)| <= 16: filter guard
+                   fabs(p.logSigma) <= 36.0;    // |logSigma*scl2| <= 16 for every chain: filter guard
     if (!regular) return kIrregularClass;
     return (e.Type == 0 ? 0 : 2) + (e.MuDk > 0 ? 1 : 0);
 }
@@ -130,11 +122,11 @@ __global__ void kFakeCountClasses(const smcmc_event* __restrict__ ev, int64_t n,
 
 // Scatter events into their class segment.  Order inside a segment is
 // arbitrary (integer counting does not depend on it).
-struct FilterEvent;
-__device__ __forceinline__ void storeFilterEvent(FilterEvent* dst, int64_t idx, const PreparedEvent& p);
+struct FilterTile;
+__device__ __forceinline__ void storeFilterEvent(FilterTile* tiles, int64_t idx, const PreparedEvent& p);
 
 __global__ void kFakeScatter(const smcmc_event* __restrict__ ev, int64_t n,
-                             PreparedEvent* prepared, FilterEvent* filter, const int64_t* classBase,
+                             PreparedEvent* prepared, FilterTile* filter, const int64_t* classBase,
                              unsigned long long* cursor, smcmc_event* irregular,
                              int forceGeneric) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -226,12 +218,12 @@ __device__ __forceinline__ int exactDecide(const PreparedEvent& ev, const FakeCh
 // The FP32 interval filter.
 //
 // Only a DISCRETE decision is needed per pair: which counter row, or none.
-// The filter evaluates q = mass/10 in FP32 together with a rigorous bound mq
-// on |q_fp32 - q_exact| and accepts the FP32 decision only when q is farther
-// than mq from the two neighbouring bin edges (and from the cut at 500, and
-// the scaled separation farther than its bound from 100).  Everything else is
-// "unsure" and is re-evaluated with exactDecide.  The filter therefore never
-// changes a count; it only decides which pairs need FP64.
+// The filter evaluates q = mass/10 in FP32 together with a rigorous bound m on
+// its relative error and accepts the FP32 decision only when q(1-m) and q(1+m)
+// have the same integer part (and the scaled separation is farther than its
+// bound from 100).  Everything else is "unsure" and is re-evaluated with
+// exactDecide.  The filter therefore never changes a count; it only decides
+// which pairs need FP64.
 //
 // Error bound (u = 2^-24; inputs are correctly rounded to FP32):
 //   x2 = ls*scl2             rel. error <= 3u
@@ -239,16 +231,27 @@ __device__ __forceinline__ int exactDecide(const PreparedEvent& ev, const FakeCh
 //   t = d*skew               rel. error <= (6 + 2.08|x2|)u
 //   z = t*w2 + nl2 + c2      abs. error <= u[(9+2.08|x2|)|t w2| + 4|nl2| + 4|c2|]
 //   q = ex2.approx(z)        rel. error <= 4u + ln2*abs.err(z)
-// With the guards |x2| <= 16 (checked per pair) and |nl2| <= 16 (checked per
-// event at upload) this is  <= u[48.4 + 2.78|c2| + 30.5|t w2|];  the code
-// uses twice that.
+// |x2| <= 16 holds for every pair because |scl2| = |0.3 erf(.) log2 e| <= 0.4329
+// and events with |logSigma| > 36 are kept out of the fast path at upload;
+// |nl2| <= 16 is checked per event at upload as well.  With those guards the
+// bound is  <= u[48.4 + 2.78|c2| + 30.5|t w2|];  the code uses twice that.
+//
+// Data layout.  Events of a class are stored in TILES of 128, structure of
+// arrays inside a tile (FilterTile, 2 KB, one TMA bulk copy), and every class
+// segment is padded to a whole number of tiles with records that can never be
+// counted (nl2 = +inf).  A thread therefore reads four events' worth of one
+// field with a single broadcast LDS.128, and the arithmetic runs on PAIRS of
+// events with the packed FP32x2 instructions of sm_100 (FMUL2 / FFMA2 / FADD2:
+// two roundings per issue slot, identical results to the scalar instructions).
 // ---------------------------------------------------------------------------
-struct __align__(16) FilterEvent {
-    float ls;      // logSigma
-    float d;       // dLog
-    float nl2;     // nomLog * log2(e)
-    float sep;
+struct __align__(16) FilterTile {
+    float ls[kPairTile];     // logSigma
+    float d[kPairTile];      // dLog
+    float nl2[kPairTile];    // nomLog * log2(e)
+    float sep[kPairTile];
 };
+static_assert(sizeof(FilterTile) == 16 * kPairTile, "FilterTile is 16 bytes per event");
+
 struct __align__(16) FilterChain {
     float scl2;      // skewc * log2(e)
     float w2;        // width * log2(e)
@@ -261,13 +264,32 @@ struct __align__(16) FilterChain {
 };
 static_assert(sizeof(FilterChain) == 48, "FilterChain is 48 bytes");
 
-__device__ __forceinline__ void storeFilterEvent(FilterEvent* dst, int64_t idx, const PreparedEvent& p) {
-    FilterEvent f;
-    f.ls = __double2float_rn(p.logSigma);
-    f.d = __double2float_rn(p.dLog);
-    f.nl2 = __double2float_rn(p.nomLog * 1.4426950408889634);
-    f.sep = __double2float_rn(p.sep);
-    dst[idx] = f;
+__device__ __forceinline__ void storeFilterEvent(FilterTile* tiles, int64_t idx, const PreparedEvent& p) {
+    FilterTile& t = tiles[idx / kPairTile];
+    const int k = (int)(idx % kPairTile);
+    t.ls[k] = __double2float_rn(p.logSigma);
+    t.d[k] = __double2float_rn(p.dLog);
+    t.nl2[k] = __double2float_rn(p.nomLog * 1.4426950408889634);
+    t.sep[k] = __double2float_rn(p.sep);
+}
+
+// Padding records: q = 2^(+inf) is cut in FP32, nomLog = +inf is cut in FP64.
+__global__ void kFakePadEvents(PreparedEvent* prepared, FilterTile* tiles, int64_t total) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float inf = __int_as_float(0x7f800000);
+    FilterTile& t = tiles[i / kPairTile];
+    const int k = (int)(i % kPairTile);
+    t.ls[k] = 0.f;
+    t.d[k] = 0.f;
+    t.nl2[k] = inf;
+    t.sep[k] = inf;
+    PreparedEvent p;
+    p.logSigma = 0.0;
+    p.dLog = 0.0;
+    p.nomLog = (double)inf;
+    p.sep = 0.0;
+    prepared[i] = p;
 }
 
 // exactOnly (SMCMC_FAKE_EXACT=1): an infinite error bound makes every pair
@@ -300,64 +322,66 @@ __device__ __forceinline__ float fastEx2(float x) {
 
 __device__ __forceinline__ uint32_t smemAddr(const void* p);
 
-// One decision: `sure` is false when the pair must go to FP64; otherwise the
-// pair is counted when `inRange` (mass < 500), in row floor(q) = bits -
-// 0x4b400000 (+50 for the Separated histogram when `far`).  q = mass/10 is
-// accepted when q(1-m) and q(1+m) have the same integer part (m = relative
-// error bound): both are pushed onto the integer grid by a round-toward-zero
-// add of 1.5*2^23 and compared as bit patterns.
+// The filter on two events at once.  For each half: lo = RZ(q(1-m) + 1.5*2^23)
+// and hi = RZ(q(1+m) + 1.5*2^23) sit on the integer grid, so the pair is
+// decided ("sure") when lo == hi as FLOATS (NaN is never sure; +inf is, and is
+// cut), and then counted in row floor(q) = bits(lo) - 0x4b400000 when that is
+// below 50 (mass < 500).  ds = sep - 100/scale for the separation test.
 constexpr unsigned kFloorMagicBits = 0x4b400000u;
 constexpr int kFilterCutRow = 50;
-constexpr int kPairIlp = 4;
 
-struct FilterResult {
-    bool sure;       // the FP32 decision is provably the FP64 decision
-    bool inRange;    // bin 0..49
-    bool far;        // separation >= 100 (untagged classes only)
-    unsigned bits;   // 0x4b400000 + floor(q)
+struct FilterPair {
+    float2 lo, hi, ds;
 };
 
 template <bool TAGGED>
-__device__ __forceinline__ FilterResult filterCore(float ls, float d, float nl2, float sep,
-                                                   const FilterChain& fc, float thr, float thrEps) {
-    const float x2 = ls * fc.scl2;
-    const float t = d * fastEx2(x2);
-    const float q = fastEx2(fmaf(t, fc.w2, nl2) + fc.c2);
-    const float m = fmaf(fabsf(t), fc.slopeT, fc.m0);
-    const unsigned lo = __float_as_uint(__fadd_rz(fmaf(-q, m, q), 12582912.0f));
-    const unsigned hi = __float_as_uint(__fadd_rz(fmaf(q, m, q), 12582912.0f));
-    FilterResult r;
-    // hi below 2^24 also rejects NaN and infinities (their patterns are larger)
-    r.sure = (lo == hi) & (hi < 0x4b800000u) & (fabsf(x2) <= 16.0f);
-    r.far = false;
-    if (!TAGGED) {
-        const float ds = sep - thr;               // sep*scale <> 100  <=>  sep <> 100/scale
-        r.sure = r.sure & (fabsf(ds) > thrEps);
-        r.far = ds > 0.0f;
-    }
-    r.inRange = lo < kFloorMagicBits + kFilterCutRow;
-    r.bits = lo;
+__device__ __forceinline__ FilterPair filterCore2(float2 ls, float2 d, float2 nl2, float2 sep,
+                                                  const FilterChain& fc, float thr) {
+    const float2 x2 = __fmul2_rn(ls, make_float2(fc.scl2, fc.scl2));
+    const float2 t = __fmul2_rn(d, make_float2(fastEx2(x2.x), fastEx2(x2.y)));
+    const float2 z = __fadd2_rn(__ffma2_rn(t, make_float2(fc.w2, fc.w2), nl2), make_float2(fc.c2, fc.c2));
+    const float2 q = make_float2(fastEx2(z.x), fastEx2(z.y));
+    const float2 m = make_float2(fmaf(fabsf(t.x), fc.slopeT, fc.m0), fmaf(fabsf(t.y), fc.slopeT, fc.m0));
+    const float2 magic = make_float2(12582912.0f, 12582912.0f);
+    FilterPair r;
+    r.hi = __fadd2_rz(__ffma2_rn(q, m, q), magic);
+    r.lo = __fadd2_rz(__ffma2_rn(q, make_float2(-m.x, -m.y), q), magic);
+    r.ds = TAGGED ? make_float2(0.f, 0.f) : __fadd2_rn(sep, make_float2(-thr, -thr));
     return r;
 }
 
-// Private counter update through a shared-memory byte address:
-// counter(row) lives at (address of row 0) + row * kPairRowBytes.
-constexpr unsigned kPairRowBytes = kPairThreads * sizeof(PairCounter);
-__device__ __forceinline__ void bumpCounter(unsigned addr) {
-#if SMCMC_PAIR_COUNTER_BITS == 16
-    asm volatile("{\n.reg .u16 c;\nld.shared.u16 c, [%0];\nadd.u16 c, c, 1;\nst.shared.u16 [%0], c;\n}" ::"r"(addr) : "memory");
-#else
-    asm volatile("{\n.reg .u32 c;\nld.shared.u32 c, [%0];\nadd.u32 c, c, 1;\nst.shared.u32 [%0], c;\n}" ::"r"(addr) : "memory");
-#endif
-}
-// mineAdj = (shared address of this thread's row-0 counter) - 0x4b400000*rowBytes,
-// so that bits*rowBytes + mineAdj addresses counter(floor(q)).
-__device__ __forceinline__ void countResult(const FilterResult& r, unsigned mineAdj) {
-    if (r.sure & r.inRange) {
-        unsigned addr = r.bits * kPairRowBytes + mineAdj;
-        if (r.far) addr += kFilterCutRow * kPairRowBytes;
-        bumpCounter(addr);
+// The discrete decision of one half.
+struct FilterDecision {
+    bool sure;       // the FP32 decision is provably the FP64 decision
+    bool counted;    // sure, and the event falls in a histogram bin
+    unsigned bits;   // 0x4b400000 + floor(q)
+    bool far;        // separation >= 100 (untagged classes only)
+};
+template <bool TAGGED>
+__device__ __forceinline__ FilterDecision filterDecide(float lo, float hi, float ds, float thrEps) {
+    FilterDecision r;
+    r.sure = (lo == hi);
+    r.far = false;
+    if (!TAGGED) {
+        r.sure = r.sure & (fabsf(ds) > thrEps);
+        r.far = ds > 0.0f;
     }
+    r.bits = __float_as_uint(lo);
+    r.counted = r.sure & (r.bits < kFloorMagicBits + kFilterCutRow);
+    return r;
+}
+
+// Counters.  A CTA holds 100 rows x 256 chains of 16-bit counters, packed two
+// per 32-bit word (chains c and c+128 -> word c), and EVERY update is a shared-memory
+// atomic add without a return value (RED): one instruction instead of a
+// load/add/store chain, and the deferred FP64 pass may update any chain's
+// column.  16 bits cannot overflow within a chunk (kPairChunk < 65536), so the
+// low half never carries into the high half.
+constexpr unsigned kPairRowBytes = (kPairThreads / 2) * sizeof(uint32_t);
+static_assert(kPairRowBytes == 512, "row stride of the counter table");
+
+__device__ __forceinline__ void redShared(unsigned addr, unsigned value) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(value) : "memory");
 }
 
 // ---------------------------------------------------------------------------
@@ -400,10 +424,11 @@ __device__ __forceinline__ void tmaLoad1D(void* dstSmem, const void* srcGlobal, 
 // The pair kernel.
 // ---------------------------------------------------------------------------
 struct PairLaunch {
-    const PreparedEvent* events;     // FP64 records, class segments contiguous
-    const FilterEvent* filterEvents; // FP32 records, same order
-    int64_t classBase[kFakeClasses]; // first event of each class
-    int64_t classCount[kFakeClasses];
+    const PreparedEvent* events;     // FP64 records; class segments contiguous, padded to whole tiles
+    const FilterTile* filterTiles;   // FP32 records, same order, 128 per tile
+    int64_t classBase[kFakeClasses]; // first (padded) event index of each class, a multiple of kPairTile
+    int64_t classCount[kFakeClasses];// events of the class INCLUDING the padding of its last tile
+    int64_t classReal[kFakeClasses]; // events of the class without the padding
     int chunkBase[kFakeClasses + 1]; // prefix sum of chunks per class
     int chunkEvents;                 // events per work item (multiple of kPairTile, <= kPairChunk)
     const FakeChainParams* chains;
@@ -414,19 +439,116 @@ struct PairLaunch {
     unsigned long long* stats;       // optional: [0] unsure pairs
 };
 
-// FP64 evaluation of one undecided pair (out of line: it is the rare path).
-__device__ __noinline__ unsigned int exactCount(const PreparedEvent* ev, const FakeChainParams* cp,
-                                                int cls, PairCounter* mine, bool live) {
-    if (!live) return 0;
+// Undecided pairs are not evaluated where they are found (one lane in FP64
+// while 31 wait): they are appended to a small shared-memory queue and the
+// whole CTA works the queue off at the end of the tile, one pair per thread.
+constexpr int kPairQueueCap = 240;
+struct PairQueue {
+    unsigned count[2];               // by tile parity
+    unsigned pad_[2];
+    unsigned entry[kPairQueueCap];   // (event index in tile) << 8 | chain index in CTA
+};
+
+constexpr size_t kPairSmemTiles = 2 * sizeof(FilterTile);
+// one more row than the histograms need: the row that takes the updates of pairs
+// that are not counted (cut or undecided), so that the update itself is
+// unconditional (no branch around the atomic)
+constexpr int kPairDummyRow = kPairCounterRows;
+constexpr size_t kPairSmemCounters = (size_t)(kPairCounterRows + 1) * kPairRowBytes;
+constexpr size_t kPairSmemBytes = kPairSmemTiles + 64 + kPairSmemCounters + sizeof(PairQueue);
+static_assert(4 * (kPairSmemBytes + 1024) <= 232448, "four CTAs per SM");
+
+// FP64 evaluation of one undecided pair and its count.
+__device__ __noinline__ void exactCount(const PreparedEvent* ev, const FakeChainParams* cp, int cls,
+                                        unsigned countersAddr, int chain) {
     const int row = exactDecide(*ev, *cp, cls);
-    if (row >= 0) mine[row * kPairThreads] += 1;
-    return 1;
+    if (row >= 0)
+        redShared(countersAddr + (unsigned)row * kPairRowBytes + (unsigned)(chain & (kPairThreads / 2 - 1)) * 4u,
+                  (chain >= kPairThreads / 2) ? 65536u : 1u);
+}
+
+// Decide and count one event: one unconditional shared-memory RED whose target
+// is the event's counter when the decision is sure and in range, and the
+// thread's dummy row otherwise; an undecided event sets the group's bit in
+// `mask`.  Written in PTX so that the sequence stays
+//   FSETP.EQ  [FSETP.GT.AND]  ISETP.LT.AND  SEL  ATOMS  @!p LOP3
+// (the compiler otherwise splits the select in two and re-evaluates compares).
+//   lo, hi, ds : from filterCore2;  rowAdj = (address of the thread's word in
+//   row 0) - 0x4b400000 * row bytes, so that bits(lo) * row bytes + rowAdj is
+//   the counter of floor(q).
+template <bool TAGGED>
+__device__ __forceinline__ void countOne(float lo, float hi, float ds, float thrEps, unsigned rowAdj,
+                                         unsigned dummyAddr, unsigned addValue, unsigned& mask, unsigned groupBit) {
+    const unsigned bits = __float_as_uint(lo);
+    unsigned addr = bits * kPairRowBytes + rowAdj;
+    if (TAGGED) {
+        asm volatile(
+            "{\n.reg .pred p, q;\n.reg .u32 a;\n"
+            "setp.eq.f32 p, %1, %2;\n"
+            "setp.lt.and.u32 q, %3, %4, p;\n"
+            "selp.u32 a, %5, %6, q;\n"
+            "red.shared.add.u32 [a], %7;\n"
+            "@!p or.b32 %0, %0, %8;\n}"
+            : "+r"(mask)
+            : "f"(lo), "f"(hi), "r"(bits), "r"(kFloorMagicBits + kFilterCutRow), "r"(addr), "r"(dummyAddr),
+              "r"(addValue), "r"(groupBit)
+            : "memory");
+    } else {
+        if (ds > 0.0f) addr += kFilterCutRow * kPairRowBytes;
+        asm volatile(
+            "{\n.reg .pred p, q;\n.reg .u32 a;\n.reg .f32 t;\n"
+            "setp.eq.f32 p, %1, %2;\n"
+            "abs.f32 t, %9;\n"
+            "setp.gt.and.f32 p, t, %10, p;\n"
+            "setp.lt.and.u32 q, %3, %4, p;\n"
+            "selp.u32 a, %5, %6, q;\n"
+            "red.shared.add.u32 [a], %7;\n"
+            "@!p or.b32 %0, %0, %8;\n}"
+            : "+r"(mask)
+            : "f"(lo), "f"(hi), "r"(bits), "r"(kFloorMagicBits + kFilterCutRow), "r"(addr), "r"(dummyAddr),
+              "r"(addValue), "r"(groupBit), "f"(ds), "f"(thrEps)
+            : "memory");
+    }
+}
+
+// The rare path: group g of the tile (four events) held at least one undecided
+// pair of this thread.  Find them again (the filter is cheap) and queue them
+// for the FP64 pass at the end of the tile.  Out of line.
+template <bool TAGGED>
+__device__ __noinline__ unsigned queueUnsure(const FilterTile* tile, int g, const FilterChain* fcp, float thr,
+                                             float thrEps, PairQueue* queue, int buf, const PreparedEvent* tileEvents,
+                                             const FakeChainParams* chain, int cls, unsigned countersAddr) {
+    const FilterChain fc = *fcp;
+    const float4 ls = reinterpret_cast<const float4*>(tile->ls)[g], d = reinterpret_cast<const float4*>(tile->d)[g];
+    const float4 nl = reinterpret_cast<const float4*>(tile->nl2)[g], sp = reinterpret_cast<const float4*>(tile->sep)[g];
+    const FilterPair a = filterCore2<TAGGED>(make_float2(ls.x, ls.y), make_float2(d.x, d.y), make_float2(nl.x, nl.y),
+                                             make_float2(sp.x, sp.y), fc, thr);
+    const FilterPair b = filterCore2<TAGGED>(make_float2(ls.z, ls.w), make_float2(d.z, d.w), make_float2(nl.z, nl.w),
+                                             make_float2(sp.z, sp.w), fc, thr);
+    bool sure[4];
+    sure[0] = filterDecide<TAGGED>(a.lo.x, a.hi.x, a.ds.x, thrEps).sure;
+    sure[1] = filterDecide<TAGGED>(a.lo.y, a.hi.y, a.ds.y, thrEps).sure;
+    sure[2] = filterDecide<TAGGED>(b.lo.x, b.hi.x, b.ds.x, thrEps).sure;
+    sure[3] = filterDecide<TAGGED>(b.lo.y, b.hi.y, b.ds.y, thrEps).sure;
+    unsigned inPlace = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (sure[k]) continue;
+        const int e = g * 4 + k;
+        const unsigned slot = atomicAdd(&queue->count[buf], 1u);
+        if (slot < (unsigned)kPairQueueCap) queue->entry[slot] = ((unsigned)e << 8) | threadIdx.x;
+        else {                            // queue full: evaluate in place
+            exactCount(tileEvents + e, chain, cls, countersAddr, (int)threadIdx.x);
+            ++inPlace;
+        }
+    }
+    return inPlace;
 }
 
 template <bool TAGGED>
 __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t first, int count,
-                                          int pointBase, FilterEvent (*tiles)[kPairTile],
-                                          uint64_t* bars, PairCounter* counters) {
+                                          int pointBase, FilterTile* tiles, uint64_t* bars,
+                                          uint32_t* counters, PairQueue* queue) {
     const int tid = threadIdx.x;
     const int point = pointBase + tid;
     const bool live = point < L.numPoints;
@@ -439,78 +561,91 @@ __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t 
     const float thr = (cls >> 1) ? fc.thr[1] : fc.thr[0];
     const float thrEps = (cls >> 1) ? fc.thrEps[1] : fc.thrEps[0];
     constexpr int rows = TAGGED ? 50 : 100;
-    for (int r = 0; r < rows; ++r) counters[r * kPairThreads + tid] = 0;
-    PairCounter* mine = counters + tid;
-    const unsigned mineAdj = smemAddr(mine) - kFloorMagicBits * kPairRowBytes;
+    for (int w = tid; w < rows * (kPairThreads / 2); w += kPairThreads) counters[w] = 0;
+    if (tid < 2) queue->count[tid] = 0;
+    const unsigned countersAddr = smemAddr(counters);
+    // chains c and c+128 share a word: the 32 lanes of a warp always address 32
+    // consecutive words, i.e. 32 different banks, whatever rows they hit
+    const unsigned mineWord = (unsigned)(tid & (kPairThreads / 2 - 1));
+    const unsigned mineAdj = countersAddr + mineWord * 4u - kFloorMagicBits * kPairRowBytes;
+    const unsigned mineDummy = countersAddr + mineWord * 4u + kPairDummyRow * kPairRowBytes;
+    const unsigned mineAdd = (tid >= kPairThreads / 2) ? 65536u : 1u;
     unsigned int unsureTotal = 0;
+    __syncthreads();
 
-    const int64_t classFirst = L.classBase[cls] + first;
-    const FilterEvent* src = L.filterEvents + classFirst;
-    const int numTiles = (count + kPairTile - 1) / kPairTile;
+    const int64_t classFirst = L.classBase[cls] + first;          // a multiple of kPairTile
+    const FilterTile* src = L.filterTiles + classFirst / kPairTile;
+    const int numTiles = count / kPairTile;
     if (tid == 0) {
-        int len = min(kPairTile, count);
-        mbarExpectTx(&bars[0], (uint32_t)len * sizeof(FilterEvent));
-        tmaLoad1D(tiles[0], src, (uint32_t)len * sizeof(FilterEvent), &bars[0]);
+        mbarExpectTx(&bars[0], (uint32_t)sizeof(FilterTile));
+        tmaLoad1D(&tiles[0], src, (uint32_t)sizeof(FilterTile), &bars[0]);
     }
     for (int t = 0; t < numTiles; ++t) {
         const int buf = t & 1;
         if (tid == 0 && t + 1 < numTiles) {
             // buffer buf^1 was released by the __syncthreads at the end of tile t-1
-            int len = min(kPairTile, count - (t + 1) * kPairTile);
-            mbarExpectTx(&bars[buf ^ 1], (uint32_t)len * sizeof(FilterEvent));
-            tmaLoad1D(tiles[buf ^ 1], src + (size_t)(t + 1) * kPairTile,
-                      (uint32_t)len * sizeof(FilterEvent), &bars[buf ^ 1]);
+            mbarExpectTx(&bars[buf ^ 1], (uint32_t)sizeof(FilterTile));
+            tmaLoad1D(&tiles[buf ^ 1], src + (t + 1), (uint32_t)sizeof(FilterTile), &bars[buf ^ 1]);
         }
         mbarWait(&bars[buf], (uint32_t)(t >> 1) & 1u);
-        const int len = min(kPairTile, count - t * kPairTile);
-        const FilterEvent* tile = tiles[buf];
-        for (int base = 0; base < len; base += 32) {
-            const int nb = min(32, len - base);
-            const PreparedEvent* exact = L.events + classFirst + (size_t)t * kPairTile + base;
-            if (nb == 32) {
-                // four events at a time, stage by stage, so that the four
-                // dependency chains (LDS -> MUFU -> MUFU -> LDS/STS) overlap
-#pragma unroll 1
-                for (int e = 0; e < 32; e += kPairIlp) {
-                    FilterEvent ev[kPairIlp];
-                    FilterResult r[kPairIlp];
-#pragma unroll
-                    for (int g = 0; g < kPairIlp; ++g) ev[g] = tile[base + e + g];
-#pragma unroll
-                    for (int g = 0; g < kPairIlp; ++g)
-                        r[g] = filterCore<TAGGED>(ev[g].ls, ev[g].d, ev[g].nl2, ev[g].sep, fc, thr, thrEps);
-                    bool allSure = true;
-#pragma unroll
-                    for (int g = 0; g < kPairIlp; ++g) {
-                        countResult(r[g], mineAdj);
-                        allSure = allSure & r[g].sure;
-                    }
-                    if (!allSure) {          // rare: FP64 for the undecided pairs
-#pragma unroll
-                        for (int g = 0; g < kPairIlp; ++g) {
-                            if (!r[g].sure) unsureTotal += exactCount(exact + e + g, L.chains + point, cls, mine, live);
-                        }
-                    }
-                }
-            } else {
-                for (int e = 0; e < nb; ++e) {
-                    const FilterEvent ev = tile[base + e];
-                    const FilterResult r = filterCore<TAGGED>(ev.ls, ev.d, ev.nl2, ev.sep, fc, thr, thrEps);
-                    countResult(r, mineAdj);
-                    if (!r.sure) unsureTotal += exactCount(exact + e, L.chains + point, cls, mine, live);
-                }
-            }
+        const FilterTile* tile = &tiles[buf];
+        const float4* ls4 = reinterpret_cast<const float4*>(tile->ls);
+        const float4* d4 = reinterpret_cast<const float4*>(tile->d);
+        const float4* nl4 = reinterpret_cast<const float4*>(tile->nl2);
+        const float4* sp4 = reinterpret_cast<const float4*>(tile->sep);
+        // four events per iteration: two packed pairs whose dependency chains
+        // (LDS -> MUFU -> MUFU -> RED) overlap; bit g of `mask` remembers that
+        // group g held an undecided pair
+        unsigned mask = 0;
+#pragma unroll 2
+        for (int g = 0; g < kPairTile / 4; ++g) {
+            const float4 ls = ls4[g], d = d4[g], nl = nl4[g];
+            float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!TAGGED) sp = sp4[g];
+            const FilterPair a = filterCore2<TAGGED>(make_float2(ls.x, ls.y), make_float2(d.x, d.y),
+                                                     make_float2(nl.x, nl.y), make_float2(sp.x, sp.y), fc, thr);
+            const FilterPair b = filterCore2<TAGGED>(make_float2(ls.z, ls.w), make_float2(d.z, d.w),
+                                                     make_float2(nl.z, nl.w), make_float2(sp.z, sp.w), fc, thr);
+            const unsigned bit = 1u << g;
+            countOne<TAGGED>(a.lo.x, a.hi.x, a.ds.x, thrEps, mineAdj, mineDummy, mineAdd, mask, bit);
+            countOne<TAGGED>(a.lo.y, a.hi.y, a.ds.y, thrEps, mineAdj, mineDummy, mineAdd, mask, bit);
+            countOne<TAGGED>(b.lo.x, b.hi.x, b.ds.x, thrEps, mineAdj, mineDummy, mineAdd, mask, bit);
+            countOne<TAGGED>(b.lo.y, b.hi.y, b.ds.y, thrEps, mineAdj, mineDummy, mineAdd, mask, bit);
+        }
+        if (!live) mask = 0;
+        while (mask) {                            // rare: queue the undecided pairs for FP64
+            const int g = __ffs(mask) - 1;
+            mask &= mask - 1;
+            unsureTotal += queueUnsure<TAGGED>(tile, g, L.filterChains + point, thr, thrEps, queue, buf,
+                                               L.events + classFirst + (size_t)t * kPairTile, L.chains + point, cls,
+                                               countersAddr);
         }
         __syncthreads();
+        unsigned queued = queue->count[buf];
+        if (queued) {                             // uniform over the CTA
+            if (queued > (unsigned)kPairQueueCap) queued = kPairQueueCap;
+            for (unsigned i = tid; i < queued; i += kPairThreads) {
+                const unsigned e = queue->entry[i];
+                const int chain = (int)(e & 255u);
+                if (pointBase + chain < L.numPoints) {
+                    exactCount(L.events + classFirst + (size_t)t * kPairTile + (e >> 8), L.chains + pointBase + chain,
+                               cls, countersAddr, chain);
+                    ++unsureTotal;
+                }
+            }
+            __syncthreads();
+            if (tid == 0) queue->count[buf] = 0;  // next used by tile t+2, after the barrier of tile t+1
+        }
     }
     if (live) {
         const int slotBase = fakeClassSlotBase(cls);
+        const int word = tid & (kPairThreads / 2 - 1), shift = (tid >= kPairThreads / 2) ? 16 : 0;
         for (int r = 0; r < rows; ++r) {
-            uint32_t v = counters[r * kPairThreads + tid];
+            const uint32_t v = (counters[r * (kPairThreads / 2) + word] >> shift) & 0xffffu;
             if (v) atomicAdd(&L.counts[(size_t)(slotBase + r) * L.pointStride + point], v);
         }
-        if (L.stats && unsureTotal) atomicAdd(&L.stats[0], (unsigned long long)unsureTotal);
     }
+    if (L.stats && unsureTotal) atomicAdd(&L.stats[0], (unsigned long long)unsureTotal);
 }
 
 // grid.x = (#chunks over all classes) * (#point tiles); consecutive CTAs take
@@ -519,9 +654,10 @@ __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t 
 __global__ void __launch_bounds__(kPairThreads, kPairCtasPerSm)
 kFakePairs(const __grid_constant__ PairLaunch L) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
-    FilterEvent(*tiles)[kPairTile] = reinterpret_cast<FilterEvent(*)[kPairTile]>(smemRaw);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smemRaw + 2 * kPairTile * sizeof(FilterEvent));
-    PairCounter* counters = reinterpret_cast<PairCounter*>(smemRaw + 2 * kPairTile * sizeof(FilterEvent) + 64);
+    FilterTile* tiles = reinterpret_cast<FilterTile*>(smemRaw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smemRaw + kPairSmemTiles);
+    uint32_t* counters = reinterpret_cast<uint32_t*>(smemRaw + kPairSmemTiles + 64);
+    PairQueue* queue = reinterpret_cast<PairQueue*>(smemRaw + kPairSmemTiles + 64 + kPairSmemCounters);
 
     const int pointTiles = (L.numPoints + kPairThreads - 1) / kPairThreads;
     const int chunk = blockIdx.x / pointTiles;
@@ -537,12 +673,9 @@ kFakePairs(const __grid_constant__ PairLaunch L) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (cls & 1) pairChunk<true>(L, cls, first, count, pointBase, tiles, bars, counters);
-    else pairChunk<false>(L, cls, first, count, pointBase, tiles, bars, counters);
+    if (cls & 1) pairChunk<true>(L, cls, first, count, pointBase, tiles, bars, counters, queue);
+    else pairChunk<false>(L, cls, first, count, pointBase, tiles, bars, counters, queue);
 }
-
-constexpr size_t kPairSmemBytes =
-    2 * kPairTile * sizeof(FilterEvent) + 64 + (size_t)kPairCounterRows * kPairThreads * sizeof(PairCounter);
 
 // Test kernel: run the filter AND the FP64 arithmetic on every pair and count
 // the pairs where a filter decision differs from the FP64 decision (must be
@@ -556,16 +689,24 @@ __global__ void kFakeVerifyFilter(const PairLaunch L, unsigned long long* stats)
     for (int cls = 0; cls < kFakeClasses; ++cls) {
         const float thr = (cls >> 1) ? fc.thr[1] : fc.thr[0];
         const float thrEps = (cls >> 1) ? fc.thrEps[1] : fc.thrEps[0];
-        for (int64_t i = blockIdx.x; i < L.classCount[cls]; i += gridDim.x) {
+        for (int64_t i = blockIdx.x; i < L.classReal[cls]; i += gridDim.x) {
             const int64_t idx = L.classBase[cls] + i;
-            const FilterEvent fe = L.filterEvents[idx];
-            const FilterResult r = (cls & 1) ? filterCore<true>(fe.ls, fe.d, fe.nl2, fe.sep, fc, thr, thrEps)
-                                             : filterCore<false>(fe.ls, fe.d, fe.nl2, fe.sep, fc, thr, thrEps);
-            const bool sure = r.sure;
-            const int f = r.inRange ? (int)(r.bits - kFloorMagicBits) + (r.far ? kFilterCutRow : 0) : -1;
+            const FilterTile& tile = L.filterTiles[idx / kPairTile];
+            const int k = (int)(idx % kPairTile);
+            const float2 ls = make_float2(tile.ls[k], tile.ls[k]), d = make_float2(tile.d[k], tile.d[k]);
+            const float2 nl = make_float2(tile.nl2[k], tile.nl2[k]), sp = make_float2(tile.sep[k], tile.sep[k]);
+            FilterDecision r;
+            if (cls & 1) {
+                const FilterPair fp = filterCore2<true>(ls, d, nl, sp, fc, thr);
+                r = filterDecide<true>(fp.lo.y, fp.hi.y, fp.ds.y, thrEps);
+            } else {
+                const FilterPair fp = filterCore2<false>(ls, d, nl, sp, fc, thr);
+                r = filterDecide<false>(fp.lo.y, fp.hi.y, fp.ds.y, thrEps);
+            }
+            const int f = r.counted ? (int)(r.bits - kFloorMagicBits) + (r.far ? kFilterCutRow : 0) : -1;
             const int x = exactDecide(L.events[idx], cp, cls);
             ++pairs;
-            if (!sure) ++unsure;
+            if (!r.sure) ++unsure;
             else if (f != x) ++bad;
         }
     }

@@ -27,7 +27,9 @@ def setup():
 def test_filter_against_fp64_on_every_pair(setup):
     eng, events, data, expo, x = setup
     pairs, unsure, bad = eng.fake_filter_check(x)
-    assert pairs == CHAINS * EVENTS
+    # a handful of events (|logSigma| > 36, i.e. reconstructed masses of a few
+    # keV) are kept out of the FP32 path at upload and always evaluated in FP64
+    assert CHAINS * (EVENTS - 20) <= pairs <= CHAINS * EVENTS
     assert bad == 0
     assert unsure < 0.005 * pairs
 
