@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "common.cuh"
 #include "fake_likelihood.cuh"
 #include "hmc.cuh"
@@ -725,31 +727,61 @@ int smcmc_fake_set_events(smcmc_engine* e, const smcmc_event* events, int64_t co
             CUDA_CHECK(cudaStreamSynchronize(e->stream));
         }
         // class segments are padded to whole tiles of kPairTile events
-        int64_t base[8] = {0};
-        int64_t total = 0;
+        int64_t base[8] = {0}, sortedStart[8] = {0};
+        int64_t total = 0, seen = 0;
         for (int c = 0; c < kFakeClasses; ++c) {
             base[c] = total;
+            sortedStart[c] = seen;
+            seen += (int64_t)hostCount[c];
             e->fakeClassBase[c] = total;
             e->fakeClassReal[c] = (int64_t)hostCount[c];
             e->fakeClassCount[c] = ((int64_t)hostCount[c] + kPairTile - 1) / kPairTile * kPairTile;
             total += e->fakeClassCount[c];
         }
+        sortedStart[kIrregularClass] = seen;
         e->fakeIrregularCount = (int64_t)hostCount[kIrregularClass];
         e->fakeEvents.reserve(total > 0 ? total : 1);
         e->fakeFilterTiles.reserve(total > 0 ? total / kPairTile : 1);
         e->fakeIrregular.reserve(e->fakeIrregularCount > 0 ? e->fakeIrregularCount : 1);
-        if (total > 0) {
-            kFakePadEvents<<<ceilDiv(total, 256), 256, 0, e->stream>>>(e->fakeEvents.get(), e->fakeFilterTiles.get(), total);
-            e->launched();
-        }
         if (count > 0) {
-            CUDA_CHECK(cudaMemcpyAsync(baseDev.get(), base, sizeof(base), cudaMemcpyHostToDevice, e->stream));
-            kFakeScatter<<<ceilDiv(count, 256), 256, 0, e->stream>>>(raw.get(), count, e->fakeEvents.get(),
-                                                                   e->fakeFilterTiles.get(), baseDev.get(),
-                                                                   counters.get() + 8, e->fakeIrregular.get(), e->forceGeneric);
+            if (count > 0xffffffffLL) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "more than 2^32 events per engine");
+            // order by (class, separation): device radix sort of (key, index)
+            DeviceBuffer<unsigned long long> keysIn, keysOut;
+            DeviceBuffer<unsigned int> indexIn, indexOut;
+            DeviceBuffer<int64_t> startDev;
+            DeviceBuffer<unsigned char> temp;
+            keysIn.reserve(count);
+            keysOut.reserve(count);
+            indexIn.reserve(count);
+            indexOut.reserve(count);
+            startDev.reserve(8);
+            kFakeSortKeys<<<ceilDiv(count, 256), 256, 0, e->stream>>>(raw.get(), count, keysIn.get(), indexIn.get(), e->forceGeneric);
             e->launched();
-            CUDA_CHECK(cudaStreamSynchronize(e->stream));
+            size_t tempBytes = 0;
+            CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, keysIn.get(), keysOut.get(), indexIn.get(),
+                                                       indexOut.get(), (int)count, 0, 35, e->stream));
+            temp.reserve(tempBytes > 0 ? tempBytes : 1);
+            CUDA_CHECK(cub::DeviceRadixSort::SortPairs(temp.get(), tempBytes, keysIn.get(), keysOut.get(), indexIn.get(),
+                                                       indexOut.get(), (int)count, 0, 35, e->stream));
+            e->launched();
+            CUDA_CHECK(cudaMemcpyAsync(baseDev.get(), base, sizeof(base), cudaMemcpyHostToDevice, e->stream));
+            CUDA_CHECK(cudaMemcpyAsync(startDev.get(), sortedStart, sizeof(sortedStart), cudaMemcpyHostToDevice, e->stream));
+            kFakeGather<<<ceilDiv(count, 256), 256, 0, e->stream>>>(raw.get(), count, keysOut.get(), indexOut.get(),
+                                                                  startDev.get(), baseDev.get(), e->fakeEvents.get(),
+                                                                  e->fakeFilterTiles.get(), e->fakeIrregular.get());
+            e->launched();
+            CUDA_CHECK(cudaStreamSynchronize(e->stream));      // the sort buffers go out of scope
         }
+        for (int c = 0; c < kFakeClasses; ++c) {
+            const int64_t pad = e->fakeClassCount[c] - e->fakeClassReal[c];
+            if (pad > 0) {
+                kFakePadEvents<<<ceilDiv(pad, 128), 128, 0, e->stream>>>(e->fakeEvents.get(), e->fakeFilterTiles.get(),
+                                                                       e->fakeClassBase[c], e->fakeClassReal[c],
+                                                                       e->fakeClassCount[c]);
+                e->launched();
+            }
+        }
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
         e->fakeEventCount = count;
     });
 }

@@ -120,26 +120,45 @@ __global__ void kFakeCountClasses(const smcmc_event* __restrict__ ev, int64_t n,
         atomicAdd(&classCount[threadIdx.x], (unsigned long long)local[threadIdx.x]);
 }
 
-// Scatter events into their class segment.  Order inside a segment is
-// arbitrary (integer counting does not depend on it).
+// Re-layout at upload.  Events are ordered by (class, separation): inside a
+// class the order does not matter for the counts, and ascending separation
+// makes most tiles of the untagged classes lie entirely on one side of every
+// chain's separation cut, so that the pair kernel can skip the per-pair test
+// there (pairChunk).  kFakeSortKeys writes the 64-bit sort keys, the host sorts
+// (key, index) with a device radix sort, kFakeGather fills the class segments.
 struct FilterTile;
 __device__ __forceinline__ void storeFilterEvent(FilterTile* tiles, int64_t idx, const PreparedEvent& p);
 
-__global__ void kFakeScatter(const smcmc_event* __restrict__ ev, int64_t n,
-                             PreparedEvent* prepared, FilterTile* filter, const int64_t* classBase,
-                             unsigned long long* cursor, smcmc_event* irregular,
-                             int forceGeneric) {
+__global__ void kFakeSortKeys(const smcmc_event* __restrict__ ev, int64_t n, unsigned long long* keys,
+                              unsigned int* index, int forceGeneric) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     PreparedEvent p;
-    smcmc_event e = ev[i];
-    int cls = forceGeneric ? kIrregularClass : classifyEvent(e, p);
-    unsigned long long pos = atomicAdd(&cursor[cls], 1ull);
-    if (cls == kIrregularClass) irregular[pos] = e;
-    else {
-        prepared[classBase[cls] + (int64_t)pos] = p;
-        storeFilterEvent(filter, classBase[cls] + (int64_t)pos, p);
+    const int cls = forceGeneric ? kIrregularClass : classifyEvent(ev[i], p);
+    unsigned int low = 0;
+    if (cls == 0 || cls == 2) low = __float_as_uint(fabsf(__double2float_rn(p.sep)));   // >= 0: bit order = value order
+    keys[i] = ((unsigned long long)cls << 32) | low;
+    index[i] = (unsigned int)i;
+}
+
+// sortedStart[c] = position of the first event of class c in the sorted order.
+__global__ void kFakeGather(const smcmc_event* __restrict__ ev, int64_t n, const unsigned long long* __restrict__ keys,
+                            const unsigned int* __restrict__ index, const int64_t* __restrict__ sortedStart,
+                            const int64_t* __restrict__ classBase, PreparedEvent* prepared, FilterTile* filter,
+                            smcmc_event* irregular) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cls = (int)(keys[i] >> 32);
+    const int64_t rank = i - sortedStart[cls];
+    const smcmc_event e = ev[index[i]];
+    if (cls == kIrregularClass) {
+        irregular[rank] = e;
+        return;
     }
+    PreparedEvent p;
+    classifyEvent(e, p);
+    prepared[classBase[cls] + rank] = p;
+    storeFilterEvent(filter, classBase[cls] + rank, p);
 }
 
 // ---------------------------------------------------------------------------
@@ -273,17 +292,25 @@ __device__ __forceinline__ void storeFilterEvent(FilterTile* tiles, int64_t idx,
     t.sep[k] = __double2float_rn(p.sep);
 }
 
-// Padding records: q = 2^(+inf) is cut in FP32, nomLog = +inf is cut in FP64.
-__global__ void kFakePadEvents(PreparedEvent* prepared, FilterTile* tiles, int64_t total) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
+// Padding records of one class segment [base+real, base+padded): q = 2^(+inf) is
+// cut in FP32 and nomLog = +inf is cut in FP64, so they are never counted; their
+// separation repeats the last real one so that a tile's first and last
+// separation stay its minimum and maximum.
+__global__ void kFakePadEvents(PreparedEvent* prepared, FilterTile* tiles, int64_t base, int64_t real, int64_t padded) {
+    int64_t i = base + real + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= base + padded) return;
     const float inf = __int_as_float(0x7f800000);
+    float sep = 0.f;
+    if (real > 0) {
+        const int64_t last = base + real - 1;
+        sep = tiles[last / kPairTile].sep[last % kPairTile];
+    }
     FilterTile& t = tiles[i / kPairTile];
     const int k = (int)(i % kPairTile);
     t.ls[k] = 0.f;
     t.d[k] = 0.f;
     t.nl2[k] = inf;
-    t.sep[k] = inf;
+    t.sep[k] = sep;
     PreparedEvent p;
     p.logSigma = 0.0;
     p.dLog = 0.0;
@@ -545,6 +572,37 @@ __device__ __noinline__ unsigned queueUnsure(const FilterTile* tile, int g, cons
     return inPlace;
 }
 
+// One tile of 128 events for one chain: four events per iteration, two packed
+// pairs whose dependency chains (LDS -> MUFU -> MUFU -> RED) overlap.  Returns
+// the mask of the groups (of four events) that held an undecided pair.
+// NOSEP: no separation test (tagged classes, and tiles of the untagged classes
+// that lie on one side of the cut for every chain of the CTA).
+template <bool NOSEP>
+__device__ __forceinline__ unsigned tileLoop(const FilterTile* tile, const FilterChain& fc, float thr, float thrEps,
+                                             unsigned rowAdj, unsigned dummyAddr, unsigned addValue) {
+    const float4* ls4 = reinterpret_cast<const float4*>(tile->ls);
+    const float4* d4 = reinterpret_cast<const float4*>(tile->d);
+    const float4* nl4 = reinterpret_cast<const float4*>(tile->nl2);
+    const float4* sp4 = reinterpret_cast<const float4*>(tile->sep);
+    unsigned mask = 0;
+#pragma unroll 2
+    for (int g = 0; g < kPairTile / 4; ++g) {
+        const float4 ls = ls4[g], d = d4[g], nl = nl4[g];
+        float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!NOSEP) sp = sp4[g];
+        const FilterPair a = filterCore2<NOSEP>(make_float2(ls.x, ls.y), make_float2(d.x, d.y),
+                                                make_float2(nl.x, nl.y), make_float2(sp.x, sp.y), fc, thr);
+        const FilterPair b = filterCore2<NOSEP>(make_float2(ls.z, ls.w), make_float2(d.z, d.w),
+                                                make_float2(nl.z, nl.w), make_float2(sp.z, sp.w), fc, thr);
+        const unsigned bit = 1u << g;
+        countOne<NOSEP>(a.lo.x, a.hi.x, a.ds.x, thrEps, rowAdj, dummyAddr, addValue, mask, bit);
+        countOne<NOSEP>(a.lo.y, a.hi.y, a.ds.y, thrEps, rowAdj, dummyAddr, addValue, mask, bit);
+        countOne<NOSEP>(b.lo.x, b.hi.x, b.ds.x, thrEps, rowAdj, dummyAddr, addValue, mask, bit);
+        countOne<NOSEP>(b.lo.y, b.hi.y, b.ds.y, thrEps, rowAdj, dummyAddr, addValue, mask, bit);
+    }
+    return mask;
+}
+
 template <bool TAGGED>
 __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t first, int count,
                                           int pointBase, FilterTile* tiles, uint64_t* bars,
@@ -571,6 +629,34 @@ __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t 
     const unsigned mineDummy = countersAddr + mineWord * 4u + kPairDummyRow * kPairRowBytes;
     const unsigned mineAdd = (tid >= kPairThreads / 2) ? 65536u : 1u;
     unsigned int unsureTotal = 0;
+    // Range of the separation cut over the chains of the CTA, widened by the
+    // error bound of the FP32 comparison: a tile whose separations all lie below
+    // sepLow (above sepHigh) is near (far) for every chain, decided.
+    float sepLow = 0.f, sepHigh = 0.f;
+    if (!TAGGED) {
+        const float inf = __int_as_float(0x7f800000);
+        const bool usable = !(isnan(thr) || isnan(thrEps));
+        float lo = live ? (usable ? __fsub_rd(thr, thrEps) : -inf) : inf;
+        float hi = live ? (usable ? __fadd_ru(thr, thrEps) : inf) : -inf;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        float* red = reinterpret_cast<float*>(queue->entry);       // the queue is not in use yet
+        if ((tid & 31) == 0) {
+            red[(tid >> 5) * 2] = lo;
+            red[(tid >> 5) * 2 + 1] = hi;
+        }
+        __syncthreads();
+        sepLow = red[0];
+        sepHigh = red[1];
+#pragma unroll
+        for (int w = 1; w < kPairThreads / 32; ++w) {
+            sepLow = fminf(sepLow, red[2 * w]);
+            sepHigh = fmaxf(sepHigh, red[2 * w + 1]);
+        }
+    }
     __syncthreads();
 
     const int64_t classFirst = L.classBase[cls] + first;          // a multiple of kPairTile
@@ -589,33 +675,23 @@ __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t 
         }
         mbarWait(&bars[buf], (uint32_t)(t >> 1) & 1u);
         const FilterTile* tile = &tiles[buf];
-        const float4* ls4 = reinterpret_cast<const float4*>(tile->ls);
-        const float4* d4 = reinterpret_cast<const float4*>(tile->d);
-        const float4* nl4 = reinterpret_cast<const float4*>(tile->nl2);
-        const float4* sp4 = reinterpret_cast<const float4*>(tile->sep);
-        // four events per iteration: two packed pairs whose dependency chains
-        // (LDS -> MUFU -> MUFU -> RED) overlap; bit g of `mask` remembers that
-        // group g held an undecided pair
-        unsigned mask = 0;
-#pragma unroll 2
-        for (int g = 0; g < kPairTile / 4; ++g) {
-            const float4 ls = ls4[g], d = d4[g], nl = nl4[g];
-            float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!TAGGED) sp = sp4[g];
-            const FilterPair a = filterCore2<TAGGED>(make_float2(ls.x, ls.y), make_float2(d.x, d.y),
-                                                     make_float2(nl.x, nl.y), make_float2(sp.x, sp.y), fc, thr);
-            const FilterPair b = filterCore2<TAGGED>(make_float2(ls.z, ls.w), make_float2(d.z, d.w),
-                                                     make_float2(nl.z, nl.w), make_float2(sp.z, sp.w), fc, thr);
-            const unsigned bit = 1u << g;
-            countOne<TAGGED>(a.lo.x, a.hi.x, a.ds.x, thrEps, mineAdj, mineDummy, mineAdd, mask, bit);
-            countOne<TAGGED>(a.lo.y, a.hi.y, a.ds.y, thrEps, mineAdj, mineDummy, mineAdd, mask, bit);
-            countOne<TAGGED>(b.lo.x, b.hi.x, b.ds.x, thrEps, mineAdj, mineDummy, mineAdd, mask, bit);
-            countOne<TAGGED>(b.lo.y, b.hi.y, b.ds.y, thrEps, mineAdj, mineDummy, mineAdd, mask, bit);
-        }
+        // Untagged classes: the events are sorted by separation, so most tiles lie
+        // on one side of the cut for every chain of the CTA and the per-pair
+        // separation test (and the load of the separations) is skipped there.
+        unsigned mask;
+        int mode = 0;                             // 0: test every pair, 1: all near, 2: all far
+        if (TAGGED) mode = 1;
+        else if (tile->sep[kPairTile - 1] < sepLow) mode = 1;
+        else if (tile->sep[0] > sepHigh) mode = 2;
+        if (mode == 0) mask = tileLoop<false>(tile, fc, thr, thrEps, mineAdj, mineDummy, mineAdd);
+        else mask = tileLoop<true>(tile, fc, thr, thrEps, mode == 2 ? mineAdj + kFilterCutRow * kPairRowBytes : mineAdj,
+                                   mineDummy, mineAdd);
         if (!live) mask = 0;
         while (mask) {                            // rare: queue the undecided pairs for FP64
             const int g = __ffs(mask) - 1;
             mask &= mask - 1;
+            // (the general variant is right for every tile mode: where the test
+            // was skipped it is passed with room to spare)
             unsureTotal += queueUnsure<TAGGED>(tile, g, L.filterChains + point, thr, thrEps, queue, buf,
                                                L.events + classFirst + (size_t)t * kPairTile, L.chains + point, cls,
                                                countersAddr);

@@ -1,19 +1,44 @@
-"""Quick timing of the headline config (no CPU baseline)."""
-import sys, os, time
+"""Where the end-to-end time goes: engine creation, event upload + re-layout
+(first and second call), Start, single traced steps."""
+import os
+import sys
+import time
+
 import numpy as np
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "root-simple-mcmc_b200")); sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "root-simple-mcmc_b200"))
+sys.path.insert(0, ROOT)
+import torch
 import smcmc_b200
+from smcmc_b200 import binding, synth
+
 E, N = 4096, 1000000
-events = smcmc_b200.synth.make_mc_sample(N // 3 + 1, N - N // 3 - 1, 2)
-data = smcmc_b200.synth.make_data_histograms(33334, 33334, 2)
-eng = smcmc_b200.Engine(smcmc_b200.LLH_FAKE, 9, E, seed=3)
-eng.set_fake_events(events)
-expo = smcmc_b200.synth.exposure_ratio(eng, data); eng.set_fake_data(data, expo)
-eng.start(np.random.default_rng(0).uniform(-1, 1, (E, 9)))
-eng.enable_kernel_timing(True)
-eng.step(5); eng.sync(); eng.pair_kernel_stats(reset=True)
-t = time.time(); eng.step(20); eng.sync(); dt = time.time() - t
-ms, n = eng.pair_kernel_stats()
-print("20 steps wall %.3f s -> %.1f MH steps/s ; pair kernel %.3f ms/launch ; pairs/s %.3e" % (dt, E * 20 / dt, ms / n, E * N * n / (ms * 1e-3)))
-print("filter check (256 pts):", eng.fake_filter_check(np.random.default_rng(1).uniform(-1, 1, (256, 9))))
+events = synth.make_mc_sample(N // 3 + 1, N - N // 3 - 1, 2)
+data = synth.make_data_histograms(33334, 33334, 2)
+pinned = torch.empty(len(events) * 48, dtype=torch.uint8, pin_memory=True)
+pinned.numpy()[:] = events.view(np.uint8)
+ev = pinned.numpy().view(binding.EVENT_DTYPE)
+x0 = np.random.default_rng(0).uniform(-1, 1, (E, 9))
+
+
+def clock(label, fn):
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    r = fn()
+    torch.cuda.synchronize()
+    print("%-28s %8.2f ms" % (label, (time.perf_counter() - t) * 1e3), flush=True)
+    return r
+
+
+for rep in range(2):
+    eng = clock("create", lambda: smcmc_b200.Engine(smcmc_b200.LLH_FAKE, 9, E, seed=3))
+    clock("set_fake_events (1st)", lambda: eng.set_fake_events(ev))
+    clock("set_fake_events (2nd)", lambda: eng.set_fake_events(ev))
+    clock("set_fake_data", lambda: eng.set_fake_data(data, 0.1))
+    clock("start", lambda: eng.start(x0))
+    out = {}
+    clock("step_trace(1) first", lambda: eng.step_trace(1, want=("points", "llh_accepted", "accepted"), out=out))
+    clock("step_trace(1) x10", lambda: [eng.step_trace(1, want=("points", "llh_accepted", "accepted"), out=out) for _ in range(10)])
+    clock("step(10)+sync", lambda: (eng.step(10), eng.sync()))
+    eng.close()
