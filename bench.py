@@ -316,10 +316,12 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel ------------------------------------------
     # kFakePairs is neither HBM- nor tensor-bound: every event is re-used by all
-    # chains (hundreds of pair evaluations per byte) and the per-pair work is a
-    # short FP32/integer/SFU sequence, so the binding resource is the SM's
-    # instruction issue rate (1 warp-instruction / clock / SM sub-partition).
-    # DESIGN.md section 4 derives the algorithmic instruction count per pair.
+    # chains (hundreds of pair evaluations per byte of HBM traffic) and the
+    # per-pair work is two exponentials plus a dozen FP32 / integer
+    # instructions.  The binding resource is the special-function unit: the
+    # reference's formula needs TWO exponentials per (chain, event) pair
+    # (example/SystematicCorrection.H:68-74), MUFU.EX2
+    # issues 16 lanes per clock per SM, and every other pipe has headroom.
     pairs_per_launch = float(chains) * float(len(events))
     pair_warps = pairs_per_launch / 32.0
     pair_s = (pair_ms / max(pair_n, 1)) * 1e-3
@@ -334,11 +336,10 @@ def run_b200(args):
         pass
     props = torch.cuda.get_device_properties(local)
     sm_hz = (clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)) * 1e6
+    sfu_peak = binding.measure_sfu_peak(local)                                   # G ex2/s, measured now
+    sfu_nominal = props.multi_processor_count * 16 * sm_hz / 1e9                 # 16 lanes / clock / SM
+    achieved = 2.0 * pairs_per_launch / pair_s / 1e9
     issue_peak = props.multi_processor_count * 4 * sm_hz / 1e9                  # G warp-inst/s
-    # tagged events need 20 instructions per pair, untagged ones 24
-    tagged = float((events["MuDk"] > 0).mean())
-    alg_inst = 20.0 * tagged + 24.0 * (1.0 - tagged)
-    achieved = alg_inst * pair_warps / pair_s / 1e9
     executed = None
     if prof.get("warp_instructions_per_pair_warp"):
         executed = prof["warp_instructions_per_pair_warp"] * pair_warps / pair_s / 1e9
@@ -352,20 +353,24 @@ def run_b200(args):
     fp64_peak = binding.measure_fp64_peak(local)
     roofline = {
         "kernel": "smcmc::kFakePairs (event x chain pair kernel)",
-        "bound": "issue",
-        "bound_note": "compute-bound on instruction issue, not hbm/tensor: %.0f pair evaluations per HBM byte"
-                      % (pairs_per_launch / alg_bytes),
-        "achieved": achieved, "peak": issue_peak, "unit": "G warp-inst/s", "frac": achieved / issue_peak,
-        "algorithmic": "%.1f warp-instructions per 32 (chain,event) pairs (20 tagged / 24 untagged events, "
-                       "DESIGN.md section 4) x %.4g pairs per launch" % (alg_inst, pairs_per_launch),
-        "peak_source": "%d SMs x 4 sub-partitions x %.0f MHz (median SM clock sampled during the timed region) "
-                       "x 1 warp-instruction/clock" % (props.multi_processor_count, sm_hz / 1e6),
-        "issue_utilisation_executed": (executed / issue_peak) if executed else None,
-        "executed_source": "profiles/pair_kernel_profile.json (ncu smsp__inst_executed.sum per launch)",
+        "bound": "sfu",
+        "bound_note": "neither hbm nor tensor: %.0f pair evaluations per HBM byte; bound by the special-function "
+                      "unit (2 exponentials per pair, MUFU.EX2 = 16 lanes/clock/SM)" % (pairs_per_launch / alg_bytes),
+        "achieved": achieved, "peak": sfu_peak, "unit": "G ex2/s", "frac": achieved / sfu_peak,
+        "algorithmic": "2 exponentials per (chain,event) pair (SystematicCorrection.H:68-74) x %.4g pairs per launch"
+                       % pairs_per_launch,
+        "peak_source": "measured in this run: register-resident MUFU.EX2 chains on every SM "
+                       "(nominal %d SMs x 16 lanes x %.0f MHz = %.0f G/s)"
+                       % (props.multi_processor_count, sm_hz / 1e6, sfu_nominal),
         "launch_ms": pair_ms / max(pair_n, 1), "launches_timed": int(pair_n),
         "kernel_share_of_step": (pair_ms / max(pair_n, 1)) / (ms / args.steps),
         "pairs_per_s": pairs_per_launch / pair_s,
         "traffic": traffic,
+        "issue": {"note": "executed warp-instructions per 32 pairs from profiles/pair_kernel_profile.json "
+                          "(ncu smsp__inst_executed.sum) against 1 warp-instruction/clock/SM sub-partition",
+                  "executed_per_pair_warp": prof.get("warp_instructions_per_pair_warp"),
+                  "achieved": executed, "peak": issue_peak, "unit": "G warp-inst/s",
+                  "frac": (executed / issue_peak) if executed else None},
         "hbm": {"achieved": alg_bytes / pair_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / pair_s / 1e9 / hbm_peak, "peak_source": hbm_src,
                 "algorithmic_bytes": alg_bytes},

@@ -1148,6 +1148,57 @@ int smcmc_measure_fp64_peak(int device, double* tflops) {
     });
 }
 
+namespace smcmc {
+// 8 independent MUFU.EX2 chains per thread.
+__global__ void __launch_bounds__(256) kSfuPeak(float* out, float a, int iters) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = a * (float)(threadIdx.x + k);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(v[k]));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
+    if (s == 12345.678f) out[0] = s;     // never true: keeps the chains alive
+}
+}  // namespace smcmc
+
+int smcmc_measure_sfu_peak(int device, double* gops) {
+    return guarded(nullptr, [&]() {
+        if (!gops) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null output");
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+            cudaGetLastError();
+            throw Error(SMCMC_ERR_NO_DEVICE, "no CUDA device");
+        }
+        CUDA_CHECK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        DeviceBuffer<float> out;
+        out.reserve(1);
+        const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 2048;
+        cudaEvent_t e0, e1;
+        CUDA_CHECK(cudaEventCreate(&e0));
+        CUDA_CHECK(cudaEventCreate(&e1));
+        double best = 0.0;
+        for (int rep = 0; rep < 6; ++rep) {
+            CUDA_CHECK(cudaEventRecord(e0));
+            kSfuPeak<<<blocks, threads>>>(out.get(), 1e-3f, iters);
+            CUDA_CHECK(cudaEventRecord(e1));
+            CUDA_CHECK(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+            const double ops = 8.0 * iters * (double)blocks * threads;
+            if (rep > 0) best = std::max(best, ops / (ms * 1e-3) / 1e9);
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *gops = best;
+    });
+}
+
 int64_t smcmc_launch_count(const smcmc_engine* e) { return e ? e->launches : 0; }
 
 int smcmc_enable_kernel_timing(smcmc_engine* e, int on) {

@@ -468,12 +468,15 @@ struct PairLaunch {
 
 // Undecided pairs are not evaluated where they are found (one lane in FP64
 // while 31 wait): they are appended to a small shared-memory queue and the
-// whole CTA works the queue off at the end of the tile, one pair per thread.
+// whole CTA works the queue off, one pair per thread, every kPairDrainEvery
+// tiles (and at the end of the chunk); pairs that do not fit are evaluated in place.
 constexpr int kPairQueueCap = 240;
+constexpr int kPairDrainEvery = 8;       // tiles between two passes over the queue
 struct PairQueue {
-    unsigned count[2];               // by tile parity
-    unsigned pad_[2];
-    unsigned entry[kPairQueueCap];   // (event index in tile) << 8 | chain index in CTA
+    unsigned count;
+    unsigned done[2];                // warps that have finished the tile in each buffer
+    unsigned pad_;
+    unsigned entry[kPairQueueCap];   // (event index in chunk) << 8 | chain index in CTA
 };
 
 constexpr size_t kPairSmemTiles = 2 * sizeof(FilterTile);
@@ -543,7 +546,7 @@ __device__ __forceinline__ void countOne(float lo, float hi, float ds, float thr
 // for the FP64 pass at the end of the tile.  Out of line.
 template <bool TAGGED>
 __device__ __noinline__ unsigned queueUnsure(const FilterTile* tile, int g, const FilterChain* fcp, float thr,
-                                             float thrEps, PairQueue* queue, int buf, const PreparedEvent* tileEvents,
+                                             float thrEps, PairQueue* queue, int tileBase, const PreparedEvent* chunkEvents,
                                              const FakeChainParams* chain, int cls, unsigned countersAddr) {
     const FilterChain fc = *fcp;
     const float4 ls = reinterpret_cast<const float4*>(tile->ls)[g], d = reinterpret_cast<const float4*>(tile->d)[g];
@@ -561,11 +564,11 @@ __device__ __noinline__ unsigned queueUnsure(const FilterTile* tile, int g, cons
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         if (sure[k]) continue;
-        const int e = g * 4 + k;
-        const unsigned slot = atomicAdd(&queue->count[buf], 1u);
+        const int e = tileBase + g * 4 + k;
+        const unsigned slot = atomicAdd(&queue->count, 1u);
         if (slot < (unsigned)kPairQueueCap) queue->entry[slot] = ((unsigned)e << 8) | threadIdx.x;
         else {                            // queue full: evaluate in place
-            exactCount(tileEvents + e, chain, cls, countersAddr, (int)threadIdx.x);
+            exactCount(chunkEvents + e, chain, cls, countersAddr, (int)threadIdx.x);
             ++inPlace;
         }
     }
@@ -620,7 +623,10 @@ __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t 
     const float thrEps = (cls >> 1) ? fc.thrEps[1] : fc.thrEps[0];
     constexpr int rows = TAGGED ? 50 : 100;
     for (int w = tid; w < rows * (kPairThreads / 2); w += kPairThreads) counters[w] = 0;
-    if (tid < 2) queue->count[tid] = 0;
+    if (tid == 0) {
+        queue->count = 0;
+        queue->done[0] = queue->done[1] = 0;
+    }
     const unsigned countersAddr = smemAddr(counters);
     // chains c and c+128 share a word: the 32 lanes of a warp always address 32
     // consecutive words, i.e. 32 different banks, whatever rows they hit
@@ -662,17 +668,19 @@ __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t 
     const int64_t classFirst = L.classBase[cls] + first;          // a multiple of kPairTile
     const FilterTile* src = L.filterTiles + classFirst / kPairTile;
     const int numTiles = count / kPairTile;
+    // Two tile buffers.  There is no CTA-wide barrier per tile: a warp that has
+    // finished a tile says so with an atomic increment of done[buffer], and the
+    // warp that makes the count complete refills the buffer with the tile after
+    // next (TMA bulk copy, completion on the buffer's mbarrier).  Warps drift
+    // apart by up to one tile instead of meeting at every tile end.
     if (tid == 0) {
-        mbarExpectTx(&bars[0], (uint32_t)sizeof(FilterTile));
-        tmaLoad1D(&tiles[0], src, (uint32_t)sizeof(FilterTile), &bars[0]);
+        for (int b = 0; b < 2 && b < numTiles; ++b) {
+            mbarExpectTx(&bars[b], (uint32_t)sizeof(FilterTile));
+            tmaLoad1D(&tiles[b], src + b, (uint32_t)sizeof(FilterTile), &bars[b]);
+        }
     }
     for (int t = 0; t < numTiles; ++t) {
         const int buf = t & 1;
-        if (tid == 0 && t + 1 < numTiles) {
-            // buffer buf^1 was released by the __syncthreads at the end of tile t-1
-            mbarExpectTx(&bars[buf ^ 1], (uint32_t)sizeof(FilterTile));
-            tmaLoad1D(&tiles[buf ^ 1], src + (t + 1), (uint32_t)sizeof(FilterTile), &bars[buf ^ 1]);
-        }
         mbarWait(&bars[buf], (uint32_t)(t >> 1) & 1u);
         const FilterTile* tile = &tiles[buf];
         // Untagged classes: the events are sorted by separation, so most tiles lie
@@ -692,25 +700,41 @@ __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t 
             mask &= mask - 1;
             // (the general variant is right for every tile mode: where the test
             // was skipped it is passed with room to spare)
-            unsureTotal += queueUnsure<TAGGED>(tile, g, L.filterChains + point, thr, thrEps, queue, buf,
-                                               L.events + classFirst + (size_t)t * kPairTile, L.chains + point, cls,
-                                               countersAddr);
+            unsureTotal += queueUnsure<TAGGED>(tile, g, L.filterChains + point, thr, thrEps, queue, t * kPairTile,
+                                               L.events + classFirst, L.chains + point, cls, countersAddr);
         }
-        __syncthreads();
-        unsigned queued = queue->count[buf];
-        if (queued) {                             // uniform over the CTA
+        // end of tile for this warp: release the buffer
+        __syncwarp();
+        if ((tid & 31) == 0) {
+            __threadfence_block();
+            const unsigned before = atomicAdd(&queue->done[buf], 1u);
+            if (before == kPairThreads / 32 - 1) {            // the last warp of the CTA to finish tile t
+                __threadfence_block();
+                queue->done[buf] = 0;
+                if (t + 2 < numTiles) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbarExpectTx(&bars[buf], (uint32_t)sizeof(FilterTile));
+                    tmaLoad1D(&tiles[buf], src + (t + 2), (uint32_t)sizeof(FilterTile), &bars[buf]);
+                }
+            }
+        }
+        // every kPairDrainEvery tiles (and at the end of the chunk) the CTA meets
+        // and works the queue of undecided pairs off
+        if ((t % kPairDrainEvery) == kPairDrainEvery - 1 || t + 1 == numTiles) {
+            __syncthreads();
+            unsigned queued = queue->count;       // stable: nobody pushes before the next barrier
             if (queued > (unsigned)kPairQueueCap) queued = kPairQueueCap;
             for (unsigned i = tid; i < queued; i += kPairThreads) {
                 const unsigned e = queue->entry[i];
                 const int chain = (int)(e & 255u);
                 if (pointBase + chain < L.numPoints) {
-                    exactCount(L.events + classFirst + (size_t)t * kPairTile + (e >> 8), L.chains + pointBase + chain,
-                               cls, countersAddr, chain);
+                    exactCount(L.events + classFirst + (e >> 8), L.chains + pointBase + chain, cls, countersAddr, chain);
                     ++unsureTotal;
                 }
             }
             __syncthreads();
-            if (tid == 0) queue->count[buf] = 0;  // next used by tile t+2, after the barrier of tile t+1
+            if (tid == 0) queue->count = 0;
+            __syncthreads();
         }
     }
     if (live) {

@@ -156,6 +156,7 @@ def load_library():
         "smcmc_pair_kernel_stats": (ci, [vp, ctypes.POINTER(cd), ctypes.POINTER(ctypes.c_int64), ci]),
         "smcmc_enable_kernel_timing": (ci, [vp, ci]),
         "smcmc_measure_fp64_peak": (ci, [ci, ctypes.POINTER(cd)]),
+        "smcmc_measure_sfu_peak": (ci, [ci, ctypes.POINTER(cd)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -178,7 +179,7 @@ EXPORTED_SYMBOLS = [
     "smcmc_hmc_set", "smcmc_hmc_start", "smcmc_hmc_set_position", "smcmc_hmc_step",
     "smcmc_hmc_step_trace", "smcmc_hmc_get",
     "smcmc_pair_kernel_stats", "smcmc_enable_kernel_timing",
-    "smcmc_measure_fp64_peak",
+    "smcmc_measure_fp64_peak", "smcmc_measure_sfu_peak",
 ]
 
 
@@ -197,6 +198,16 @@ def measure_fp64_peak(device=0):
     lib = load_library()
     out = ctypes.c_double()
     rc = lib.smcmc_measure_fp64_peak(device, ctypes.byref(out))
+    if rc != 0:
+        raise SmcmcError(rc, lib.smcmc_last_error(None).decode())
+    return out.value
+
+
+def measure_sfu_peak(device=0):
+    """Measured MUFU.EX2 throughput of the device, 1e9 evaluations per second."""
+    lib = load_library()
+    out = ctypes.c_double()
+    rc = lib.smcmc_measure_sfu_peak(device, ctypes.byref(out))
     if rc != 0:
         raise SmcmcError(rc, lib.smcmc_last_error(None).decode())
     return out.value

@@ -53,6 +53,8 @@ def main(raw, out_prefix, chains, events):
             elif h.startswith(STALLS) and h.endswith("_per_warp_active.pct"):
                 rec.setdefault("stall_pct", {})[h[len(STALLS):-len("_per_warp_active.pct")]] = float(r[i])
         launches.append(rec)
+    # the dominant kernel only (the regex of the capture also matches kFakePairsGeneric)
+    launches = [l for l in launches if "kFakePairs(" in l["kernel"] or l["kernel"].endswith("kFakePairs")]
     n = len(launches)
     avg = lambda k: sum(l[k] for l in launches) / n
     pair_warps = chains * events / 32.0
