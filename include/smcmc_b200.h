@@ -198,6 +198,14 @@ int smcmc_fake_counts(smcmc_engine* e, const double* x, int m, uint32_t* out);
 int smcmc_fake_filter_check(smcmc_engine* e, const double* x, int m, uint64_t* out3);
 /* TDummyLogLikelihood::Error (TDummyLogLikelihood.H:147), n x n row-major. */
 int smcmc_dummy_set_error(smcmc_engine* e, const double* error, int n);
+/* How the dense contractions of TDummyLogLikelihood (likelihood :21-31, gradient
+ * :34-42) are evaluated.  EXACT (default): the reference's operation order,
+ * multiply and add rounded separately -- bit-identical to the host functor.
+ * TENSOR: X . Error^T on the FP64 tensor cores (DMMA), fused multiply-adds in the
+ * tensor core's summation order -- within 1e-12 relative, not bit for bit; meant
+ * for dimensions of a few hundred and thousands of chains. */
+typedef enum smcmc_dummy_mode { SMCMC_DUMMY_EXACT = 0, SMCMC_DUMMY_TENSOR = 1 } smcmc_dummy_mode;
+int smcmc_dummy_set_mode(smcmc_engine* e, int mode);
 
 /* ---- sampler ------------------------------------------------------------- */
 /* UserLikelihood::operator() at m arbitrary points (x[m*dim]) -> llh[m]. */

@@ -12,6 +12,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
+#include "contraction.cuh"
 #include "fake_likelihood.cuh"
 #include "hmc.cuh"
 #include "nccl_dyn.h"
@@ -94,8 +95,10 @@ struct smcmc_engine {
     int eigSlots = 0;
 
     // ---- likelihood data ---------------------------------------------------
-    DeviceBuffer<double> errMatrix;                 // DUMMY
+    DeviceBuffer<double> errMatrix, errMatrixT;     // DUMMY: Error(i,j) row-major, and its transpose
     int errDim = 0;
+    int dummyMode = SMCMC_DUMMY_EXACT;              // SMCMC_DUMMY_EXACT | SMCMC_DUMMY_TENSOR
+    DeviceBuffer<double> dummyPartials;
     DeviceBuffer<PreparedEvent> fakeEvents;         // FAKE
     DeviceBuffer<FilterTile> fakeFilterTiles;
     DeviceBuffer<FilterChain> fakeFilterChains;
@@ -270,9 +273,38 @@ struct smcmc_engine {
         case SMCMC_LLH_FAKE:
             evaluateFake(xDev, m, llhDev, histDev);
             break;
-        case SMCMC_LLH_DUMMY:
+        case SMCMC_LLH_DUMMY: {
             if (errDim != n()) throw Error(SMCMC_ERR_LOGIC, "error matrix not set (smcmc_dummy_set_error)");
-            // fall through
+            if (dummyMode == SMCMC_DUMMY_TENSOR) {
+                // L = -1/2 x . (Error^T x): the contraction on the FP64 tensor cores
+                dim3 grid(ceilDiv(n(), kDmmaBN), ceilDiv(m, kDmmaBM));
+                dummyPartials.reserve((size_t)m * grid.x);
+                kDummyContractDmma<<<grid, 128, 0, stream>>>(xDev, errMatrixT.get(), dummyPartials.get(), nullptr, 0, m, n(), 1);
+                launched();
+                kDummyLlhFromPartials<<<ceilDiv(m, 128), 128, 0, stream>>>(dummyPartials.get(), (int)grid.x, m, llhDev);
+                launched();
+                break;
+            }
+            // points per block: as many warps as fit the shared-memory tile, one
+            // warp when there are too few points to fill the SMs otherwise
+            int warps = (int)std::min<size_t>(4, ((200u << 10) - 2 * ((size_t)n() + 1) * 8) / ((size_t)n() * 8 * 32));
+            if (warps >= 1) {
+                if (m <= smCount * 32 * 2) warps = 1;
+                const int width = warps * 32;
+                const size_t smem = ((size_t)n() * width + 2 * (((size_t)n() + 1) & ~(size_t)1)) * sizeof(double);
+                if (smem > dummySmemSet) {
+                    CUDA_CHECK(cudaFuncSetAttribute(kDummyLikelihood, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    dummySmemSet = smem;
+                }
+                kDummyLikelihood<<<ceilDiv(m, width), width, smem, stream>>>(xDev, m, n(), errMatrixT.get(), llhDev);
+                launched();
+                break;
+            }
+            // dimension too large for the tile: the generic kernel
+            kSimpleLikelihood<<<ceilDiv(m, 128), 128, 0, stream>>>(cfg.likelihood, xDev, m, n(), errMatrix.get(), llhDev);
+            launched();
+            break;
+        }
         default:
             kSimpleLikelihood<<<ceilDiv(m, 128), 128, 0, stream>>>(cfg.likelihood, xDev, m, n(),
                                                                   errMatrix.get(), llhDev);
@@ -324,6 +356,7 @@ struct smcmc_engine {
         return L;
     }
     bool collectStats = false;
+    size_t dummySmemSet = 48 << 10;
 
     void evaluateFake(const double* xDev, int m, double* llhDev, double* histDev) {
         if (fakeEventCount < 0) throw Error(SMCMC_ERR_LOGIC, "events not set (smcmc_fake_set_events)");
@@ -797,12 +830,25 @@ int smcmc_fake_set_data(smcmc_engine* e, const double* data150, double exposure)
     });
 }
 
+int smcmc_dummy_set_mode(smcmc_engine* e, int mode) {
+    return guarded(e, [&]() {
+        if (e->cfg.likelihood != SMCMC_LLH_DUMMY) throw Error(SMCMC_ERR_LOGIC, "engine was not created with SMCMC_LLH_DUMMY");
+        if (mode != SMCMC_DUMMY_EXACT && mode != SMCMC_DUMMY_TENSOR) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "unknown mode");
+        e->dummyMode = mode;
+    });
+}
+
 int smcmc_dummy_set_error(smcmc_engine* e, const double* err, int nn) {
     return guarded(e, [&]() {
         if (e->cfg.likelihood != SMCMC_LLH_DUMMY) throw Error(SMCMC_ERR_LOGIC, "engine was not created with SMCMC_LLH_DUMMY");
         if (!err || nn != e->n()) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "error matrix must be dim x dim");
         e->errMatrix.reserve((size_t)nn * nn);
+        e->errMatrixT.reserve((size_t)nn * nn);
+        std::vector<double> t((size_t)nn * nn);
+        for (int i = 0; i < nn; ++i)
+            for (int j = 0; j < nn; ++j) t[(size_t)i * nn + j] = err[(size_t)j * nn + i];
         CUDA_CHECK(cudaMemcpyAsync(e->errMatrix.get(), err, sizeof(double) * nn * nn, cudaMemcpyHostToDevice, e->stream));
+        CUDA_CHECK(cudaMemcpyAsync(e->errMatrixT.get(), t.data(), sizeof(double) * nn * nn, cudaMemcpyHostToDevice, e->stream));
         CUDA_CHECK(cudaStreamSynchronize(e->stream));
         e->errDim = nn;
     });

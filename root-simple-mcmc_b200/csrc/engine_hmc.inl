@@ -90,9 +90,15 @@ void hmcGradient(smcmc_engine* e, HmcGradientMode mode, int k) {
     switch (mode) {
     case kGradUser: {
         if (e->errDim != n) throw Error(SMCMC_ERR_LOGIC, "error matrix not set (smcmc_dummy_set_error)");
-        dim3 grid(ceilDiv(n, kGemmBN), ceilDiv(E, kGemmBM));
-        kDummyGradient<<<grid, 256, 0, e->stream>>>(h.qProp.get(), e->errMatrix.get(), h.grad.get(),
-                                                    h.leapSteps.get(), k, E, n);
+        if (e->dummyMode == SMCMC_DUMMY_TENSOR) {
+            dim3 grid(ceilDiv(n, kDmmaBN), ceilDiv(E, kDmmaBM));
+            kDummyContractDmma<<<grid, 128, 0, e->stream>>>(h.qProp.get(), e->errMatrix.get(), h.grad.get(),
+                                                           h.leapSteps.get(), k, E, n, 0);
+        } else {
+            dim3 grid(ceilDiv(n, kGemmBN), ceilDiv(E, kGemmBM));
+            kDummyGradient<<<grid, 256, 0, e->stream>>>(h.qProp.get(), e->errMatrix.get(), h.grad.get(),
+                                                        h.leapSteps.get(), k, E, n);
+        }
         e->launched();
         break;
     }

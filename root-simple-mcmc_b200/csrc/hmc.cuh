@@ -473,20 +473,27 @@ kHmcPost(HmcArrays a, int n, int chains, const double* __restrict__ llhProp, dou
         {
             const double t = s.covTrials, t1 = __dadd_rn(t, 1.0);
             double* ex = a.exxt + (size_t)c * tri;
-            int i = 0, rowStart = 0;
-            for (size_t k0 = 0; k0 < tri; k0 += 32) {
-                const size_t kk = k0 + lane;
-                if (kk < tri) {
-                    int ii = i, rs = rowStart;
-                    while ((size_t)(rs + ii + 1) <= kk) { rs += ii + 1; ++ii; }
-                    const int j = (int)kk - rs;
-                    double v = __dmul_rn(ex[kk], t);
-                    v = __dadd_rn(v, __dmul_rn(buf[ii], buf[j]));
-                    v = __ddiv_rn(v, t1);
-                    ex[kk] = v;
+            for (int i = 0; i < n; ++i) {         // row i of the packed lower triangle: lanes across j <= i
+                double* exRow = ex + triIndex(i, 0);
+                const double xi = buf[i];
+                int j = lane;
+                for (; j + 96 <= i; j += 128) {   // four independent loads in flight per lane
+                    double v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) v[u] = exRow[j + 32 * u];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        double w = __dmul_rn(v[u], t);
+                        w = __dadd_rn(w, __dmul_rn(xi, buf[j + 32 * u]));
+                        exRow[j + 32 * u] = __ddiv_rn(w, t1);
+                    }
                 }
-                const size_t nk = k0 + 32;
-                while ((size_t)(rowStart + i + 1) <= nk) { rowStart += i + 1; ++i; }
+                for (; j <= i; j += 32) {
+                    double v = __dmul_rn(exRow[j], t);
+                    v = __dadd_rn(v, __dmul_rn(xi, buf[j]));
+                    v = __ddiv_rn(v, t1);
+                    exRow[j] = v;
+                }
             }
             s.covTrials = fmin(covWindow, t1);
         }

@@ -53,6 +53,60 @@ __device__ __forceinline__ double llhAsym(const double* x, int n) {
     return s;
 }
 
+// TDummyLogLikelihood for many points: one THREAD per point, the block's points
+// transposed into shared memory (xs[j][point], lane = point: conflict-free).  The
+// error matrix is read through its transpose errT[i][j] = Error(j,i), one row per
+// outer index i, copied into shared memory one row ahead with cp.async so that
+// the inner loop only touches shared memory.  The single running sum of the
+// reference (n^2 terms, i outer, j inner) stays a single sequential sum per
+// point; the two products of each term are independent work beside that chain.
+// Dynamic shared memory: n * blockDim.x + 2 * (n rounded up to 2) doubles.
+__device__ __forceinline__ void cpAsyncRow(double* dst, const double* src, int n, int tid, int nthreads) {
+    // 16-byte pieces where the row is 16-byte aligned, 8-byte pieces otherwise
+    const bool aligned = ((reinterpret_cast<size_t>(src) | reinterpret_cast<size_t>(dst)) & 15) == 0;
+    if (aligned) {
+        for (int k = tid * 2; k + 1 < n; k += nthreads * 2)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst + k)),
+                         "l"(src + k) : "memory");
+        if ((n & 1) && tid == 0)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst + n - 1)),
+                         "l"(src + n - 1) : "memory");
+    } else {
+        for (int k = tid; k < n; k += nthreads)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst + k)),
+                         "l"(src + k) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__global__ void kDummyLikelihood(const double* __restrict__ x, int m, int n, const double* __restrict__ errT,
+                                 double* __restrict__ out) {
+    extern __shared__ __align__(16) double xs[];
+    const int width = blockDim.x;
+    const int npad = (n + 1) & ~1;
+    double* rows = xs + (size_t)n * width;          // two row buffers of npad doubles
+    const int c0 = blockIdx.x * width;
+    cpAsyncRow(rows, errT, n, threadIdx.x, width);
+    for (int idx = threadIdx.x; idx < n * width; idx += width) {
+        const int j = idx / width, c = idx - j * width;
+        xs[idx] = (c0 + c < m) ? x[(size_t)(c0 + c) * n + j] : 0.0;
+    }
+    const int c = threadIdx.x;
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double* row = rows + (size_t)(i & 1) * npad;
+        if (i + 1 < n) cpAsyncRow(rows + (size_t)((i + 1) & 1) * npad, errT + (size_t)(i + 1) * n, n, threadIdx.x, width);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");     // row i has landed (row i+1 may be in flight)
+        __syncthreads();
+        const double hx = __dmul_rn(0.5, xs[i * width + c]);
+#pragma unroll 4
+        for (int j = 0; j < n; ++j) s = __dsub_rn(s, __dmul_rn(__dmul_rn(hx, row[j]), xs[j * width + c]));
+        __syncthreads();                                         // before row buffer (i & 1) is refilled
+    }
+    if (c0 + c < m) out[c0 + c] = s;
+}
+
 __global__ void kSimpleLikelihood(int kind, const double* __restrict__ x, int m, int n,
                                   const double* __restrict__ err, double* __restrict__ out) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;

@@ -9,6 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 
 LLH_UNIT_GAUSS, LLH_DUMMY, LLH_HORRIFIC, LLH_ASYM, LLH_FAKE = range(5)
+DUMMY_EXACT, DUMMY_TENSOR = 0, 1
 
 # smcmc_prop_field
 (PROP_SIGMA, PROP_TARGET_ACCEPTANCE, PROP_ACCEPTANCE_WINDOW,
@@ -137,6 +138,7 @@ def load_library():
         "smcmc_fake_counts": (ci, [vp, vp, ci, vp]),
         "smcmc_fake_filter_check": (ci, [vp, vp, ci, vp]),
         "smcmc_dummy_set_error": (ci, [vp, vp, ci]),
+        "smcmc_dummy_set_mode": (ci, [vp, ci]),
         "smcmc_eval": (ci, [vp, vp, ci, vp]),
         "smcmc_start": (ci, [vp, vp, vp]),
         "smcmc_step": (ci, [vp, ci, ci]),
@@ -173,7 +175,7 @@ EXPORTED_SYMBOLS = [
     "smcmc_prop_reset_correlations", "smcmc_prop_update", "smcmc_prop_reset",
     "smcmc_fake_set_events", "smcmc_fake_set_data", "smcmc_fake_histograms",
     "smcmc_fake_counts", "smcmc_fake_filter_check",
-    "smcmc_dummy_set_error", "smcmc_eval", "smcmc_start", "smcmc_step",
+    "smcmc_dummy_set_error", "smcmc_dummy_set_mode", "smcmc_eval", "smcmc_start", "smcmc_step",
     "smcmc_step_trace", "smcmc_get", "smcmc_save_state", "smcmc_restore_state",
     "smcmc_get_step_index", "smcmc_set_step_index", "smcmc_launch_count",
     "smcmc_hmc_set", "smcmc_hmc_start", "smcmc_hmc_set_position", "smcmc_hmc_step",
@@ -309,6 +311,10 @@ class Engine:
         out = np.zeros(3, np.uint64)
         self._check(self.lib.smcmc_fake_filter_check(self.h, _ptr(x), x.shape[0], _ptr(out)))
         return int(out[0]), int(out[1]), int(out[2])
+
+    def set_dummy_mode(self, mode):
+        """DUMMY_EXACT (reference operation order, default) or DUMMY_TENSOR (FP64 tensor cores)."""
+        self._check(self.lib.smcmc_dummy_set_mode(self.h, int(mode)))
 
     def set_error_matrix(self, e):
         e = np.ascontiguousarray(e, dtype=np.float64)

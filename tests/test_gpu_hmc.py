@@ -132,3 +132,37 @@ def test_hmc_errors():
         eng.hmc_step(1, 2)                    # covariant gradient needs the error matrix
     eng.hmc_step(3)
     assert np.all(eng.hmc_scalars()["step_count"] == 3)
+
+
+def test_tensor_mode_matches_exact_mode():
+    """SMCMC_DUMMY_TENSOR (X . Error^T on the FP64 tensor cores) against the
+    reference-ordered evaluation: likelihood values to 1e-12 relative (the
+    tolerance of the specification), and an HMC ensemble whose trajectories stay
+    on top of the exact ones (same trajectory lengths, potentials to 1e-9)."""
+    import smcmc_b200
+    from smcmc_b200 import binding as b
+    from oracle import cpu_checkers as cc
+    for n, E in ((37, 70), (200, 130)):
+        prec = hmc_error_matrix("spd%d" % n)
+        pts = np.random.default_rng(n).normal(size=(E, n))
+        eng = smcmc_b200.Engine(smcmc_b200.LLH_DUMMY, n, E, seed=2)
+        eng.set_error_matrix(prec)
+        exact = eng.eval(pts)
+        eng.set_dummy_mode(b.DUMMY_TENSOR)
+        tensor = eng.eval(pts)
+        o = cc.CpuChain("orc", cc.LLH_DUMMY, n, 2, 0)
+        o.set_error_matrix(prec)
+        ref = np.array([o.llh(p) for p in pts[:16]])
+        assert np.array_equal(exact[:16], ref)                       # exact mode: bit for bit
+        assert np.max(np.abs(tensor / exact - 1.0)) < 1e-12          # tensor mode: the specified tolerance
+        runs = {}
+        for mode in (b.DUMMY_EXACT, b.DUMMY_TENSOR):
+            h = smcmc_b200.Engine(smcmc_b200.LLH_DUMMY, n, E, seed=6)
+            h.set_error_matrix(prec)
+            h.set_dummy_mode(mode)
+            h.hmc_set(b.HMC_USER_GRADIENT, 1)
+            h.hmc_start(np.full(n, 0.5))
+            runs[mode] = h.hmc_step_trace(60, 0, want=("potential", "leapfrog", "accepted"))
+        assert np.array_equal(runs[0]["leapfrog"], runs[1]["leapfrog"])
+        assert np.array_equal(runs[0]["accepted"], runs[1]["accepted"])
+        assert np.allclose(runs[0]["potential"], runs[1]["potential"], rtol=1e-9)
