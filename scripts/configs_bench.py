@@ -1,0 +1,207 @@
+#!/usr/bin/env python
+"""Per-config figures of SURVEY.md 8(d) for the BASELINE.json configs other than
+the headline one (bench.py measures C2):
+
+  C1  1 chain, default adaptive proposal: steps/s (latency bound), next to the
+      reference's own code on one host core
+  C3  65 536 chains x 50 dimensions (THorrific / TASym), per-chain adaptation
+      (33 KB of state traffic per chain-step => HBM bound) and pooled adaptation
+  C4  TSimpleHMC, 500-dimensional Gaussian with the analytic gradient,
+      E in {1, 1024, 16384}: gradient + likelihood contractions per second
+      against the FP64 peak, EXACT and TENSOR (DMMA) modes
+  C5  ensemble sweep: chains x events of the event likelihood sharded over the
+      GPUs of the node (chain groups x event groups, integer counts all-reduced
+      inside an event group over NCCL)
+
+    python scripts/configs_bench.py c1 c3 c4            # one GPU
+    python -m torch.distributed.run --nproc-per-node G scripts/configs_bench.py c5 [--event-group K]
+
+Prints one JSON object per measurement; profiles/r01_configs.jsonl keeps a run."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "root-simple-mcmc_b200"))
+sys.path.insert(0, ROOT)
+import torch
+import smcmc_b200
+from smcmc_b200 import binding as b, synth
+
+PEAKS = {}
+try:
+    PEAKS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+except Exception:
+    pass
+HBM = PEAKS.get("hbm_gbs", 6650.0)
+
+
+def emit(rec):
+    print(json.dumps(rec), flush=True)
+
+
+def timed(fn, sync):
+    sync()
+    t = time.perf_counter()
+    fn()
+    sync()
+    return time.perf_counter() - t
+
+
+def c1():
+    from oracle import cpu_checkers as cc
+    have_ref = cc.available("ref")
+    err100 = None
+    if have_ref:
+        _, err100 = cc.ref_dummy_matrices()
+    for name, kind, dim in (("unit gauss 5-dim (README example)", 0, 5), ("TDummyLogLikelihood 100-dim as shipped", 1, 100)):
+        if kind == 1 and err100 is None:
+            continue
+        eng = smcmc_b200.Engine(kind, dim, 1, seed=1)
+        if kind == 1:
+            eng.set_error_matrix(err100)
+        eng.start(np.zeros(dim))
+        eng.step(500)
+        steps = 5000
+        dt = timed(lambda: eng.step(steps), eng.sync)
+        rec = {"config": "C1", "target": name, "chains": 1, "dim": dim, "steps_per_s": steps / dt,
+               "us_per_step": 1e6 * dt / steps, "bound": "latency (one chain)"}
+        which = "ref" if have_ref else "orc"
+        c = cc.CpuChain(which, kind, dim, 1, 0)
+        if kind == 1 and which == "orc":
+            c.set_error_matrix(err100)
+        c.start(np.zeros(dim))
+        c.step(500)
+        t = time.perf_counter()
+        c.step(steps)
+        rec["cpu_steps_per_s"] = steps / (time.perf_counter() - t)
+        rec["cpu_kind"] = "reference" if have_ref else "port"
+        emit(rec)
+
+
+def c3():
+    E, n, steps = 65536, 50, 100
+    tri = n * (n + 1) // 2
+    for name, kind in (("THorrificLogLikelihood", 2), ("TASymLogLikelihood", 3)):
+        for pooled in (0, 16):
+            eng = smcmc_b200.Engine(kind, n, E, seed=4)
+            if pooled:
+                eng.prop_set(b.PROP_POOLED_EVERY, pooled)
+            eng.start(np.zeros(n) if kind == 2 else np.full(n, 0.01))
+            eng.step(20)
+            dt = timed(lambda: eng.step(steps), eng.sync)
+            # per chain-step 3 n(n+1)/2 doubles (covariance read + write, U read)
+            # + 6n doubles; pooled mode (4n + 8) doubles
+            bytes_per = (3 * tri + 6 * n) * 8 if not pooled else (4 * n + 8) * 8
+            rate = E * steps / dt
+            emit({"config": "C3", "target": name, "chains": E, "dim": n, "mode": "pooled/%d" % pooled if pooled else "per-chain",
+                  "ms_per_step": 1e3 * dt / steps, "chain_steps_per_s": rate, "algorithmic_bytes_per_chain_step": bytes_per,
+                  "hbm_gbs": rate * bytes_per / 1e9, "hbm_peak_gbs": HBM, "frac": rate * bytes_per / 1e9 / HBM,
+                  "acceptance": float(eng.get("acceptance").mean())})
+            eng.close()
+
+
+def precision(n, seed=5):
+    rng = np.random.default_rng(seed)
+    a = rng.normal(size=(n, n))
+    m = a @ a.T / n + np.diag(rng.uniform(0.5, 2.0, n))
+    return 0.5 * (m + m.T)
+
+
+def c4():
+    n = 500
+    fp64 = b.measure_fp64_peak(0)
+    prec = precision(n)
+    for E, steps, burn in ((1, 20, 5), (1024, 20, 5), (16384, 10, 3)):
+        for mode in (b.DUMMY_EXACT, b.DUMMY_TENSOR):
+            eng = smcmc_b200.Engine(smcmc_b200.LLH_DUMMY, n, E, seed=5)
+            eng.set_error_matrix(prec)
+            eng.set_dummy_mode(mode)
+            eng.hmc_set(b.HMC_USER_GRADIENT, 1)
+            eng.hmc_start(np.ones(n))
+            eng.hmc_step(burn)
+            eng.sync()
+            s0 = eng.hmc_scalars()
+            dt = timed(lambda: eng.hmc_step(steps), eng.sync)
+            s1 = eng.hmc_scalars()
+            evals = float((s1["gradient_count"] - s0["gradient_count"]).sum() + (s1["potential_count"] - s0["potential_count"]).sum())
+            flops = evals * 2.0 * n * n / dt
+            emit({"config": "C4", "target": "TSimpleHMC, 500-dim dense Gaussian, analytic gradient", "chains": E, "dim": n,
+                  "mode": "tensor (DMMA)" if mode else "exact (reference order)", "ms_per_step": 1e3 * dt / steps,
+                  "chain_steps_per_s": E * steps / dt, "gradients_plus_likelihoods_per_s": evals / dt,
+                  "tflops_2n2_each": flops / 1e12, "fp64_peak_tflops_measured": fp64, "frac": flops / 1e12 / fp64,
+                  "mean_leapfrog": float(np.abs(s1["leapfrog"]).mean()), "acceptance": float(s1["acceptance"].mean())})
+            eng.close()
+
+
+def c5(args):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eg = args.event_group
+    assert world % eg == 0
+    chain_groups = world // eg
+    chains_total, events_total = args.chains, args.events
+    chains = chains_total // chain_groups                     # per chain group
+    offset = (rank // eg) * chains
+    signal = events_total // 3 + 1
+    events = synth.make_mc_sample(signal, events_total - signal, seed=2)
+    data = synth.make_data_histograms(33334, 33334, seed=2)
+    mine = events[(rank % eg)::eg]                            # this rank's slice of the events
+    eng = smcmc_b200.Engine(smcmc_b200.LLH_FAKE, 9, chains, seed=3, device=local, chain_offset=offset)
+    if world > 1 and eg > 1:
+        uid = [b.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.comm_init(uid[0], world, rank, event_group=eg)
+    eng.set_fake_events(mine)
+    eng.set_fake_data(data, 0.1)
+    x0 = np.zeros((chains, 9))
+    for c in range(chains):
+        x0[c] = np.random.default_rng([3, offset + c]).uniform(-1.0, 1.0, 9)
+    eng.start(x0)
+    eng.step(1)
+
+    def sync():
+        eng.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    dt = timed(lambda: eng.step(args.steps), sync)
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    if rank == 0:
+        pairs = float(chains_total) * float(events_total) * args.steps
+        emit({"config": "C5", "target": "ensemble sweep of the event likelihood (binned Poisson, example/FakeLikelihood.H)",
+              "chains": chains_total, "events": events_total, "gpus": world, "chain_groups": chain_groups, "event_group": eg,
+              "steps": args.steps, "s_per_step": dt / args.steps, "chain_steps_per_s": chains_total * args.steps / dt,
+              "pair_evals_per_s": pairs / dt, "pair_evals_per_s_per_gpu": pairs / dt / world,
+              "exchange": "all-reduce of %d x %d uint32 event counts per step inside each event group" % (450, chains) if eg > 1 else "none"})
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("which", nargs="+")
+    ap.add_argument("--event-group", type=int, default=1)
+    ap.add_argument("--chains", type=int, default=262144)
+    ap.add_argument("--events", type=int, default=16777216)
+    ap.add_argument("--steps", type=int, default=2)
+    a = ap.parse_args()
+    for w in a.which:
+        if w == "c5":
+            c5(a)
+        else:
+            {"c1": c1, "c3": c3, "c4": c4}[w]()
