@@ -231,6 +231,8 @@ struct smcmc_engine {
         ps.covFrozen = covFrozen;
         ps.stepRMSWindow = stepRMSWindow;
         ps.ncorr = (int)corrValue.size();
+        ps.anyUniform = 0;
+        for (int t : type) ps.anyUniform |= (t == 1);
         ps.covWindow = covWindow;
         ps.accWindow = accWindow;
         ps.target = target;
@@ -744,19 +746,48 @@ int smcmc_fake_set_events(smcmc_engine* e, const smcmc_event* events, int64_t co
     return guarded(e, [&]() {
         if (e->cfg.likelihood != SMCMC_LLH_FAKE) throw Error(SMCMC_ERR_LOGIC, "engine was not created with SMCMC_LLH_FAKE");
         if (count < 0 || (count > 0 && !events)) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "bad event array");
-        DeviceBuffer<smcmc_event> raw;
-        DeviceBuffer<unsigned long long> counters;
-        DeviceBuffer<int64_t> baseDev;
-        counters.reserve(16);
-        baseDev.reserve(8);
-        CUDA_CHECK(cudaMemsetAsync(counters.get(), 0, 16 * sizeof(unsigned long long), e->stream));
+        if (count > 0xffffffffLL) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "more than 2^32 events per engine");
+        // One arena for everything that only lives during the re-layout (raw
+        // records, sort keys and indices in and out, the sort's scratch, the
+        // small counters): one allocation and one release per upload.
+        size_t sortBytes = 0;
+        if (count > 0)
+            CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, sortBytes, (unsigned long long*)nullptr,
+                                                       (unsigned long long*)nullptr, (unsigned int*)nullptr,
+                                                       (unsigned int*)nullptr, (int)count, 0, 35, e->stream));
+        auto align = [](size_t b) { return (b + 255) / 256 * 256; };
+        const size_t n = (size_t)count;
+        const size_t offRaw = 0;
+        const size_t offKeysIn = offRaw + align(n * sizeof(smcmc_event));
+        const size_t offKeysOut = offKeysIn + align(n * 8);
+        const size_t offIndexIn = offKeysOut + align(n * 8);
+        const size_t offIndexOut = offIndexIn + align(n * 4);
+        const size_t offSort = offIndexOut + align(n * 4);
+        const size_t offSmall = offSort + align(sortBytes);
+        DeviceBuffer<unsigned char> arena;
+        arena.reserve(offSmall + 512);
+        unsigned char* base0 = arena.get();
+        smcmc_event* raw = (smcmc_event*)(base0 + offRaw);
+        unsigned long long* keysIn = (unsigned long long*)(base0 + offKeysIn);
+        unsigned long long* keysOut = (unsigned long long*)(base0 + offKeysOut);
+        unsigned int* indexIn = (unsigned int*)(base0 + offIndexIn);
+        unsigned int* indexOut = (unsigned int*)(base0 + offIndexOut);
+        unsigned long long* counters = (unsigned long long*)(base0 + offSmall);        // 16 x u64
+        int64_t* baseDev = (int64_t*)(base0 + offSmall + 128);                           // 8 x i64
+        int64_t* startDev = (int64_t*)(base0 + offSmall + 192);                          // 8 x i64
+        CUDA_CHECK(cudaMemsetAsync(counters, 0, 16 * sizeof(unsigned long long), e->stream));
         unsigned long long hostCount[8] = {0};
         if (count > 0) {
-            raw.reserve(count);
-            CUDA_CHECK(cudaMemcpyAsync(raw.get(), events, sizeof(smcmc_event) * count, cudaMemcpyHostToDevice, e->stream));
-            kFakeCountClasses<<<ceilDiv(count, 256), 256, 0, e->stream>>>(raw.get(), count, counters.get(), e->forceGeneric);
+            CUDA_CHECK(cudaMemcpyAsync(raw, events, sizeof(smcmc_event) * count, cudaMemcpyHostToDevice, e->stream));
+            kFakeCountClasses<<<ceilDiv(count, 256), 256, 0, e->stream>>>(raw, count, counters, e->forceGeneric);
             e->launched();
-            CUDA_CHECK(cudaMemcpyAsync(hostCount, counters.get(), 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+            // the keys do not depend on the counts: queue them before the read-back
+            kFakeSortKeys<<<ceilDiv(count, 256), 256, 0, e->stream>>>(raw, count, keysIn, indexIn, e->forceGeneric);
+            e->launched();
+            CUDA_CHECK(cub::DeviceRadixSort::SortPairs(base0 + offSort, sortBytes, keysIn, keysOut, indexIn, indexOut,
+                                                       (int)count, 0, 35, e->stream));
+            e->launched();
+            CUDA_CHECK(cudaMemcpyAsync(hostCount, counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
             CUDA_CHECK(cudaStreamSynchronize(e->stream));
         }
         // class segments are padded to whole tiles of kPairTile events
@@ -777,33 +808,12 @@ int smcmc_fake_set_events(smcmc_engine* e, const smcmc_event* events, int64_t co
         e->fakeFilterTiles.reserve(total > 0 ? total / kPairTile : 1);
         e->fakeIrregular.reserve(e->fakeIrregularCount > 0 ? e->fakeIrregularCount : 1);
         if (count > 0) {
-            if (count > 0xffffffffLL) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "more than 2^32 events per engine");
-            // order by (class, separation): device radix sort of (key, index)
-            DeviceBuffer<unsigned long long> keysIn, keysOut;
-            DeviceBuffer<unsigned int> indexIn, indexOut;
-            DeviceBuffer<int64_t> startDev;
-            DeviceBuffer<unsigned char> temp;
-            keysIn.reserve(count);
-            keysOut.reserve(count);
-            indexIn.reserve(count);
-            indexOut.reserve(count);
-            startDev.reserve(8);
-            kFakeSortKeys<<<ceilDiv(count, 256), 256, 0, e->stream>>>(raw.get(), count, keysIn.get(), indexIn.get(), e->forceGeneric);
+            CUDA_CHECK(cudaMemcpyAsync(baseDev, base, sizeof(base), cudaMemcpyHostToDevice, e->stream));
+            CUDA_CHECK(cudaMemcpyAsync(startDev, sortedStart, sizeof(sortedStart), cudaMemcpyHostToDevice, e->stream));
+            kFakeGather<<<ceilDiv(count, 256), 256, 0, e->stream>>>(raw, count, keysOut, indexOut, startDev, baseDev,
+                                                                  e->fakeEvents.get(), e->fakeFilterTiles.get(),
+                                                                  e->fakeIrregular.get());
             e->launched();
-            size_t tempBytes = 0;
-            CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, keysIn.get(), keysOut.get(), indexIn.get(),
-                                                       indexOut.get(), (int)count, 0, 35, e->stream));
-            temp.reserve(tempBytes > 0 ? tempBytes : 1);
-            CUDA_CHECK(cub::DeviceRadixSort::SortPairs(temp.get(), tempBytes, keysIn.get(), keysOut.get(), indexIn.get(),
-                                                       indexOut.get(), (int)count, 0, 35, e->stream));
-            e->launched();
-            CUDA_CHECK(cudaMemcpyAsync(baseDev.get(), base, sizeof(base), cudaMemcpyHostToDevice, e->stream));
-            CUDA_CHECK(cudaMemcpyAsync(startDev.get(), sortedStart, sizeof(sortedStart), cudaMemcpyHostToDevice, e->stream));
-            kFakeGather<<<ceilDiv(count, 256), 256, 0, e->stream>>>(raw.get(), count, keysOut.get(), indexOut.get(),
-                                                                  startDev.get(), baseDev.get(), e->fakeEvents.get(),
-                                                                  e->fakeFilterTiles.get(), e->fakeIrregular.get());
-            e->launched();
-            CUDA_CHECK(cudaStreamSynchronize(e->stream));      // the sort buffers go out of scope
         }
         for (int c = 0; c < kFakeClasses; ++c) {
             const int64_t pad = e->fakeClassCount[c] - e->fakeClassReal[c];
@@ -814,7 +824,7 @@ int smcmc_fake_set_events(smcmc_engine* e, const smcmc_event* events, int64_t co
                 e->launched();
             }
         }
-        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));          // the arena goes out of scope; host arrays were read
         e->fakeEventCount = count;
     });
 }

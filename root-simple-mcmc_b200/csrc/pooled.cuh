@@ -190,10 +190,15 @@ kProposePooled(ChainArrays a, PropSettings ps, PooledState pool, int chains, uin
         if (ps.type[j] == 1) p = zr[j];
         else {
             p = cur[j];
+            if (!ps.anyUniform) {
 #pragma unroll 8
-            for (int i = 0; i <= j; ++i) {
-                if (ps.type[i] == 1) continue;
-                p = __dadd_rn(p, __dmul_rn(zr[i], u[(size_t)i * n + j]));
+                for (int i = 0; i <= j; ++i) p = __dadd_rn(p, __dmul_rn(zr[i], u[(size_t)i * n + j]));
+            } else {
+#pragma unroll 4
+                for (int i = 0; i <= j; ++i) {
+                    if (ps.type[i] == 1) continue;
+                    p = __dadd_rn(p, __dmul_rn(zr[i], u[(size_t)i * n + j]));
+                }
             }
         }
         xProp[j] = p;
