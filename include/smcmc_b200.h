@@ -44,8 +44,11 @@ typedef enum smcmc_likelihood {
     SMCMC_LLH_DUMMY = 1,      /* -1/2 x^T E x        TDummyLogLikelihood.H:21-31  */
     SMCMC_LLH_HORRIFIC = 2,   /* box + ridge         THorrificLogLikelihood.H:26-38 */
     SMCMC_LLH_ASYM = 3,       /* piecewise linear    TAsymLogLikelihood.H:20-31   */
-    SMCMC_LLH_FAKE = 4        /* event reweighting + binned Poisson,
+    SMCMC_LLH_FAKE = 4,       /* event reweighting + binned Poisson,
                                  example/FakeLikelihood.H:47-81,188-216          */
+    SMCMC_LLH_UNBINNED = 5    /* NOT in the reference: unbinned mixture likelihood over
+                                 events (BASELINE.json configs[4]); see
+                                 smcmc_unbinned_set_events                        */
 } smcmc_likelihood;
 
 typedef struct smcmc_config {
@@ -196,6 +199,20 @@ int smcmc_fake_counts(smcmc_engine* e, const double* x, int m, uint32_t* out);
  * pairs the filter left to FP64, pairs where a filter decision differs from
  * the FP64 decision}.  The last number must be 0. */
 int smcmc_fake_filter_check(smcmc_engine* e, const double* x, int m, uint64_t* out3);
+/* SMCMC_LLH_UNBINNED, the unbinned counterpart of the event likelihood.  The
+ * reference has no such functor (its likelihood is binned); this one is DEFINED
+ * HERE on top of the reference's per-event corrections, with the same 9
+ * parameters (example/SystematicCorrection.H:11-22):
+ *   L(p) = sum over events of log( w_s phi_s(m') + w_b phi_b(m') )
+ *   log m' = corrected log-mass of InvariantMass (:50-79)
+ *   w_s, w_b = EventWeight (:81-117) of the signal / background hypothesis for
+ *              the event's MuDk flag (exposure ratio 1); the event's Type is not used
+ *   phi_s(m) = log-normal density, mean of log m = log 135, sigma = log 1.3
+ *   phi_b(m) = exp(-m/500)/500
+ * Its CPU checker is oracle/smcmc_oracle.cc (EvalUnbinned); parity is not pinned by
+ * the reference.  Events are copied to the device and kept in upload order inside
+ * the two MuDk classes. */
+int smcmc_unbinned_set_events(smcmc_engine* e, const smcmc_event* events, int64_t n);
 /* TDummyLogLikelihood::Error (TDummyLogLikelihood.H:147), n x n row-major. */
 int smcmc_dummy_set_error(smcmc_engine* e, const double* error, int n);
 /* How the dense contractions of TDummyLogLikelihood (likelihood :21-31, gradient

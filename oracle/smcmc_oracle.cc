@@ -275,8 +275,53 @@ struct Likelihood {
         }
         case ORC_LLH_FAKE:
             return EvalFake(x);
+        case ORC_LLH_UNBINNED:
+            return EvalUnbinned(x);
         }
         return std::numeric_limits<double>::quiet_NaN();
+    }
+
+    // The unbinned mixture likelihood of BASELINE.json configs[4].  It has no
+    // counterpart in the reference; the definition is in
+    // include/smcmc_b200.h (SMCMC_LLH_UNBINNED) and reuses the reference's
+    // per-event corrections: the corrected log-mass of
+    // SystematicCorrection::InvariantMass (example/SystematicCorrection.H:50-79)
+    // and the two hypothesis weights of EventWeight (:81-117).
+    double EvalUnbinned(const double* p) const {
+        const double scale = p[2] / 10.0;
+        const double width = std::exp(p[3] / 10.0);
+        const double skewc = 0.3 * std::erf(p[4] / 10.0);
+        double fakes = std::tan(M_PI * (0.05 - 0.5));
+        fakes += p[7];
+        fakes = std::atan(fakes) / M_PI + 0.5;
+        double eff = std::tan(M_PI * (0.5 - 0.5));
+        eff += p[8];
+        eff = std::atan(eff) / M_PI + 0.5;
+        const double wSig = 1.0 * std::exp(p[0] / 10.0), wBkg = 1.0 * std::exp(p[1] / 10.0);
+        // log weight of the signal / background hypothesis, untagged and tagged
+        const double lws[2] = {std::log(wSig * ((1.0 - fakes) / (1.0 - 0.05))), std::log(wSig * (fakes / 0.05))};
+        const double lwb[2] = {std::log(wBkg * ((1.0 - eff) / (1.0 - 0.5))), std::log(wBkg * (eff / 0.5))};
+        const double mu = std::log(135.0), sig = std::log(1.3), tau = 500.0;
+        const double ca = -std::log(sig * std::sqrt(2.0 * M_PI)), cb = -std::log(tau);
+        double sum = 0.0;
+        for (size_t i = 0; i < events.size(); ++i) {
+            const orc_event& e = events[i];
+            const double nomLog = std::log(e.TrueMass);
+            const double nomLogSigma = std::log(e.TrueMass + e.TrueMassSigma) - nomLog;
+            const double d = std::log(e.Mass) - nomLog;
+            const double logSigma = d / nomLogSigma;
+            const double skew = std::exp(logSigma * skewc);
+            double lm = nomLog + d * skew;
+            lm = nomLog + (lm - nomLog) * width;
+            lm = lm + scale;
+            const int tag = e.MuDk > 0 ? 1 : 0;
+            const double z = (lm - mu) / sig;
+            const double a = lws[tag] + ca - 0.5 * z * z - lm;         // log(w_s phi_s(m)), lognormal around 135
+            const double b = lwb[tag] + cb - std::exp(lm) / tau;       // log(w_b phi_b(m)), exponential, tau = 500
+            const double hi = a > b ? a : b, lo = a > b ? b : a;
+            sum += hi + std::log1p(std::exp(lo - hi));
+        }
+        return sum;
     }
 };
 
@@ -702,11 +747,11 @@ extern "C" {
 const char* orc_last_error(void) { return gLastError.c_str(); }
 
 void* orc_chain_create(int kind, int dim, uint64_t seed, uint32_t chain) {
-    if (kind < ORC_LLH_UNIT_GAUSS || kind > ORC_LLH_FAKE || dim < 1) {
+    if (kind < ORC_LLH_UNIT_GAUSS || kind > ORC_LLH_UNBINNED || dim < 1) {
         gLastError = "bad likelihood kind or dimension";
         return 0;
     }
-    if (kind == ORC_LLH_FAKE && dim != 9) { gLastError = "FakeLikelihood is 9-dim"; return 0; }
+    if ((kind == ORC_LLH_FAKE || kind == ORC_LLH_UNBINNED) && dim != 9) { gLastError = "FakeLikelihood is 9-dim"; return 0; }
     OrcChain* c = new OrcChain;
     c->n = dim;
     c->like.kind = kind;
@@ -722,9 +767,9 @@ void orc_chain_destroy(void* h) { delete H(h); }
 
 int orc_chain_set_fake(void* h, const orc_event* ev, long n, const double* data150, double exposure) {
     Likelihood& l = H(h)->like;
-    if (l.kind != ORC_LLH_FAKE) { gLastError = "not a FakeLikelihood chain"; return -1; }
+    if (l.kind != ORC_LLH_FAKE && l.kind != ORC_LLH_UNBINNED) { gLastError = "not a FakeLikelihood chain"; return -1; }
     l.events.assign(ev, ev + n);
-    std::copy(data150, data150 + 150, l.data);
+    if (data150) std::copy(data150, data150 + 150, l.data);
     l.exposure = exposure;
     return 0;
 }

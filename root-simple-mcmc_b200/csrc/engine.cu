@@ -19,6 +19,7 @@
 #include "pooled.cuh"
 #include "proposal.cuh"
 #include "simple_likelihoods.cuh"
+#include "unbinned_likelihood.cuh"
 
 namespace smcmc {
 
@@ -117,6 +118,13 @@ struct smcmc_engine {
     DeviceBuffer<uint32_t> fakeCounts;
     int fakeCountStride = 0;
     bool forceGeneric = false;
+
+    // ---- unbinned mixture likelihood (unbinned_likelihood.cuh) ---------------------
+    DeviceBuffer<PreparedEvent> unbEvents;
+    DeviceBuffer<UnbinnedChain> unbChains;
+    DeviceBuffer<double> unbPartial;
+    int64_t unbClassCount[2] = {0, 0};
+    int64_t unbEventCount = -1;
 
     // ---- pooled adaptation (pooled.cuh) -----------------------------------------
     int pooledEvery = 0;                            // 0 = per-chain adaptation (the reference)
@@ -275,6 +283,9 @@ struct smcmc_engine {
         case SMCMC_LLH_FAKE:
             evaluateFake(xDev, m, llhDev, histDev);
             break;
+        case SMCMC_LLH_UNBINNED:
+            evaluateUnbinned(xDev, m, llhDev);
+            break;
         case SMCMC_LLH_DUMMY: {
             if (errDim != n()) throw Error(SMCMC_ERR_LOGIC, "error matrix not set (smcmc_dummy_set_error)");
             if (dummyMode == SMCMC_DUMMY_TENSOR) {
@@ -409,6 +420,51 @@ struct smcmc_engine {
         launched();
     }
 
+    void evaluateUnbinned(const double* xDev, int m, double* llhDev) {
+        if (unbEventCount < 0) throw Error(SMCMC_ERR_LOGIC, "events not set (smcmc_unbinned_set_events)");
+        const int stride = (m + 31) / 32 * 32;
+        unbChains.reserve(stride);
+        kUnbinnedPrepareChains<<<ceilDiv(m, 128), 128, 0, stream>>>(xDev, m, n(), unbChains.get());
+        launched();
+        UnbinnedLaunch L;
+        L.events = unbEvents.get();
+        const int pointTiles = ceilDiv(m, kUnbThreads);
+        const int64_t total = unbClassCount[0] + unbClassCount[1];
+        // chunk length: about four waves of (SMs x 8 resident CTAs), at most kUnbMaxChunk events
+        const int64_t slots = (int64_t)smCount * 8;
+        int64_t waves = std::max<int64_t>(1, (total * pointTiles + slots * kUnbMaxChunk - 1) / (slots * kUnbMaxChunk));
+        waves = std::max<int64_t>(waves, std::min<int64_t>(4, (total * pointTiles) / (slots * kUnbTile) + 1));
+        int64_t chunkEvents = (total * pointTiles + slots * waves - 1) / (slots * waves);
+        chunkEvents = std::min<int64_t>(kUnbMaxChunk, std::max<int64_t>(kUnbTile, (chunkEvents + kUnbTile - 1) / kUnbTile * kUnbTile));
+        L.chunkEvents = (int)chunkEvents;
+        int chunks = 0;
+        for (int c = 0; c < 2; ++c) {
+            L.classBase[c] = c == 0 ? 0 : unbClassCount[0];
+            L.classCount[c] = unbClassCount[c];
+            L.chunkBase[c] = chunks;
+            chunks += (int)((unbClassCount[c] + chunkEvents - 1) / chunkEvents);
+        }
+        L.chunkBase[2] = chunks;
+        L.chains = unbChains.get();
+        L.numPoints = m;
+        L.stride = stride;
+        unbPartial.reserve((size_t)std::max(chunks, 1) * stride);
+        L.partial = unbPartial.get();
+        if (chunks > 0) {
+            kUnbinnedPairs<<<(unsigned)chunks * (unsigned)pointTiles, kUnbThreads, 0, stream>>>(L);
+            launched();
+        }
+        kUnbinnedFinish<<<ceilDiv(m, 128), 128, 0, stream>>>(unbPartial.get(), chunks, stride, m, llhDev);
+        launched();
+        if (eventComm) {
+            // events are split over the ranks of the event group: the partial
+            // log-likelihoods add (the likelihood is a sum over events)
+            NcclApi& nccl = NcclApi::get();
+            nccl.check(nccl.AllReduce(llhDev, llhDev, (size_t)m, ncclDouble, ncclSum, eventComm, stream),
+                       "all-reduce of partial log-likelihoods");
+        }
+    }
+
     void collectPairTimings() {
         for (auto& pr : pairEvents) {
             CUDA_CHECK(cudaEventSynchronize(pr.second));
@@ -500,10 +556,10 @@ int smcmc_create(const smcmc_config* cfg, smcmc_engine** out) {
         if (!cfg || !out) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null argument");
         if (cfg->struct_size != sizeof(smcmc_config)) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "smcmc_config size mismatch");
         if (cfg->dim < 1 || cfg->chains < 1) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "dim and chains must be positive");
-        if (cfg->likelihood < SMCMC_LLH_UNIT_GAUSS || cfg->likelihood > SMCMC_LLH_FAKE)
+        if (cfg->likelihood < SMCMC_LLH_UNIT_GAUSS || cfg->likelihood > SMCMC_LLH_UNBINNED)
             throw Error(SMCMC_ERR_INVALID_ARGUMENT, "unknown likelihood");
-        if (cfg->likelihood == SMCMC_LLH_FAKE && cfg->dim != 9)
-            throw Error(SMCMC_ERR_INVALID_ARGUMENT, "the FakeLikelihood functor has 9 parameters");
+        if ((cfg->likelihood == SMCMC_LLH_FAKE || cfg->likelihood == SMCMC_LLH_UNBINNED) && cfg->dim != 9)
+            throw Error(SMCMC_ERR_INVALID_ARGUMENT, "the event likelihood functors have 9 parameters");
         int count = 0;
         cudaError_t ce = cudaGetDeviceCount(&count);
         if (ce != cudaSuccess || count < 1) {
@@ -555,6 +611,10 @@ int smcmc_create(const smcmc_config* cfg, smcmc_engine** out) {
         e->fakeStats.reserve(4);
         CUDA_CHECK(cudaMemset(e->fakeStats.get(), 0, 4 * sizeof(unsigned long long)));
 
+        if (cfg->likelihood == SMCMC_LLH_UNBINNED) {
+            double consts[4] = {std::tan(M_PI * (0.05 - 0.5)), std::tan(M_PI * (0.5 - 0.5)), M_PI, 0.0};
+            CUDA_CHECK(cudaMemcpyToSymbol(gFakeConst, consts, sizeof(consts)));
+        }
         if (cfg->likelihood == SMCMC_LLH_FAKE) {
             // Pre-images of the TH1 bin edges under this host's exp: bin(exp(l)).
             double edges[52];
@@ -826,6 +886,50 @@ int smcmc_fake_set_events(smcmc_engine* e, const smcmc_event* events, int64_t co
         }
         CUDA_CHECK(cudaStreamSynchronize(e->stream));          // the arena goes out of scope; host arrays were read
         e->fakeEventCount = count;
+    });
+}
+
+int smcmc_unbinned_set_events(smcmc_engine* e, const smcmc_event* events, int64_t count) {
+    return guarded(e, [&]() {
+        if (e->cfg.likelihood != SMCMC_LLH_UNBINNED) throw Error(SMCMC_ERR_LOGIC, "engine was not created with SMCMC_LLH_UNBINNED");
+        if (count < 0 || (count > 0 && !events)) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "bad event array");
+        if (count > 0xffffffffLL) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "more than 2^32 events per engine");
+        e->unbEvents.reserve(count > 0 ? count : 1);
+        unsigned long long tagged = 0;
+        if (count > 0) {
+            size_t sortBytes = 0;
+            CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, sortBytes, (unsigned long long*)nullptr,
+                                                       (unsigned long long*)nullptr, (unsigned int*)nullptr,
+                                                       (unsigned int*)nullptr, (int)count, 0, 33, e->stream));
+            auto align = [](size_t b) { return (b + 255) / 256 * 256; };
+            const size_t n = (size_t)count;
+            const size_t offKeysIn = align(n * sizeof(smcmc_event)), offKeysOut = offKeysIn + align(n * 8);
+            const size_t offIndexIn = offKeysOut + align(n * 8), offIndexOut = offIndexIn + align(n * 4);
+            const size_t offSort = offIndexOut + align(n * 4), offSmall = offSort + align(sortBytes);
+            DeviceBuffer<unsigned char> arena;
+            arena.reserve(offSmall + 256);
+            unsigned char* b0 = arena.get();
+            smcmc_event* raw = (smcmc_event*)b0;
+            unsigned long long* keysIn = (unsigned long long*)(b0 + offKeysIn);
+            unsigned long long* keysOut = (unsigned long long*)(b0 + offKeysOut);
+            unsigned int* indexIn = (unsigned int*)(b0 + offIndexIn);
+            unsigned int* indexOut = (unsigned int*)(b0 + offIndexOut);
+            unsigned long long* counter = (unsigned long long*)(b0 + offSmall);
+            CUDA_CHECK(cudaMemsetAsync(counter, 0, 8, e->stream));
+            CUDA_CHECK(cudaMemcpyAsync(raw, events, sizeof(smcmc_event) * count, cudaMemcpyHostToDevice, e->stream));
+            kUnbinnedSortKeys<<<ceilDiv(count, 256), 256, 0, e->stream>>>(raw, count, keysIn, indexIn, counter);
+            e->launched();
+            CUDA_CHECK(cub::DeviceRadixSort::SortPairs(b0 + offSort, sortBytes, keysIn, keysOut, indexIn, indexOut,
+                                                       (int)count, 0, 33, e->stream));
+            e->launched();
+            kUnbinnedGather<<<ceilDiv(count, 256), 256, 0, e->stream>>>(raw, count, indexOut, e->unbEvents.get());
+            e->launched();
+            CUDA_CHECK(cudaMemcpyAsync(&tagged, counter, 8, cudaMemcpyDeviceToHost, e->stream));
+            CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        }
+        e->unbClassCount[0] = count - (int64_t)tagged;
+        e->unbClassCount[1] = (int64_t)tagged;
+        e->unbEventCount = count;
     });
 }
 

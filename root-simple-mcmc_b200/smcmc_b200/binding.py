@@ -8,7 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 
-LLH_UNIT_GAUSS, LLH_DUMMY, LLH_HORRIFIC, LLH_ASYM, LLH_FAKE = range(5)
+LLH_UNIT_GAUSS, LLH_DUMMY, LLH_HORRIFIC, LLH_ASYM, LLH_FAKE, LLH_UNBINNED = range(6)
 DUMMY_EXACT, DUMMY_TENSOR = 0, 1
 
 # smcmc_prop_field
@@ -134,6 +134,7 @@ def load_library():
         "smcmc_prop_reset": (ci, [vp]),
         "smcmc_fake_set_events": (ci, [vp, vp, ctypes.c_int64]),
         "smcmc_fake_set_data": (ci, [vp, vp, cd]),
+        "smcmc_unbinned_set_events": (ci, [vp, vp, ctypes.c_int64]),
         "smcmc_fake_histograms": (ci, [vp, vp, ci, vp]),
         "smcmc_fake_counts": (ci, [vp, vp, ci, vp]),
         "smcmc_fake_filter_check": (ci, [vp, vp, ci, vp]),
@@ -173,7 +174,7 @@ EXPORTED_SYMBOLS = [
     "smcmc_set_stream", "smcmc_sync", "smcmc_comm_unique_id", "smcmc_comm_init", "smcmc_prop_set", "smcmc_prop_set_gaussian",
     "smcmc_prop_set_uniform", "smcmc_prop_set_correlation",
     "smcmc_prop_reset_correlations", "smcmc_prop_update", "smcmc_prop_reset",
-    "smcmc_fake_set_events", "smcmc_fake_set_data", "smcmc_fake_histograms",
+    "smcmc_fake_set_events", "smcmc_fake_set_data", "smcmc_unbinned_set_events", "smcmc_fake_histograms",
     "smcmc_fake_counts", "smcmc_fake_filter_check",
     "smcmc_dummy_set_error", "smcmc_dummy_set_mode", "smcmc_eval", "smcmc_start", "smcmc_step",
     "smcmc_step_trace", "smcmc_get", "smcmc_save_state", "smcmc_restore_state",
@@ -287,6 +288,10 @@ class Engine:
     def set_fake_events(self, events):
         ev = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
         self._check(self.lib.smcmc_fake_set_events(self.h, _ptr(ev), len(ev)))
+
+    def set_unbinned_events(self, events):
+        ev = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+        self._check(self.lib.smcmc_unbinned_set_events(self.h, _ptr(ev), len(ev)))
 
     def set_fake_data(self, data150, exposure):
         d = np.ascontiguousarray(data150, dtype=np.float64).reshape(150)

@@ -203,3 +203,45 @@ def test_hmc_samples_the_target(checkers):
     var = np.diag(np.linalg.inv(prec))
     assert np.all(np.abs(x.mean(0)) < 0.15)
     assert np.all(np.abs(x.var(0) / var - 1.0) < 0.2)
+
+
+# ---------------------------------------------------------------------------
+# The unbinned mixture likelihood (not in the reference; defined in
+# include/smcmc_b200.h).  Its checker is the port only: pin the port against an
+# independent numpy statement of the definition.
+# ---------------------------------------------------------------------------
+def numpy_unbinned(events, p):
+    from math import erf, pi
+    scale, width, skewc = p[2] / 10.0, np.exp(p[3] / 10.0), 0.3 * erf(p[4] / 10.0)
+    fakes = np.arctan(np.tan(pi * (0.05 - 0.5)) + p[7]) / pi + 0.5
+    eff = np.arctan(np.tan(pi * (0.5 - 0.5)) + p[8]) / pi + 0.5
+    w_s, w_b = np.exp(p[0] / 10.0), np.exp(p[1] / 10.0)
+    tag = events["MuDk"] > 0
+    lws = np.where(tag, np.log(w_s * fakes / 0.05), np.log(w_s * (1 - fakes) / 0.95))
+    lwb = np.where(tag, np.log(w_b * eff / 0.5), np.log(w_b * (1 - eff) / 0.5))
+    nl = np.log(events["TrueMass"])
+    d = np.log(events["Mass"]) - nl
+    ls = d / (np.log(events["TrueMass"] + events["TrueMassSigma"]) - nl)
+    lm = nl + d * np.exp(ls * skewc) * width + scale
+    sig, tau = np.log(1.3), 500.0
+    a = lws - np.log(sig * np.sqrt(2 * pi)) - 0.5 * ((lm - np.log(135.0)) / sig) ** 2 - lm
+    b = lwb - np.log(tau) - np.exp(lm) / tau
+    return float(np.sum(np.logaddexp(a, b)))
+
+
+def test_unbinned_port_matches_its_definition(checkers):
+    import smcmc_b200.synth as synth
+    events = synth.make_mc_sample(700, 1300, seed=9)
+    c = checkers.CpuChain("orc", checkers.LLH_UNBINNED, 9, 1, 0)
+    c.set_fake(events, np.zeros(150), 1.0)
+    rng = np.random.default_rng(4)
+    for p in np.concatenate([np.zeros((1, 9)), rng.uniform(-2, 2, (12, 9))]):
+        want = numpy_unbinned(events, p)
+        assert abs(c.llh(p) / want - 1.0) < 1e-13
+    # a sum over events: additive over any split of the sample
+    a = checkers.CpuChain("orc", checkers.LLH_UNBINNED, 9, 1, 0)
+    b = checkers.CpuChain("orc", checkers.LLH_UNBINNED, 9, 1, 0)
+    a.set_fake(events[:900], np.zeros(150), 1.0)
+    b.set_fake(events[900:], np.zeros(150), 1.0)
+    p = rng.uniform(-1, 1, 9)
+    assert abs((a.llh(p) + b.llh(p)) / c.llh(p) - 1.0) < 1e-13
