@@ -157,13 +157,17 @@ def c5(args):
     events = synth.make_mc_sample(signal, events_total - signal, seed=2)
     data = synth.make_data_histograms(33334, 33334, seed=2)
     mine = events[(rank % eg)::eg]                            # this rank's slice of the events
-    eng = smcmc_b200.Engine(smcmc_b200.LLH_FAKE, 9, chains, seed=3, device=local, chain_offset=offset)
+    kind = smcmc_b200.LLH_UNBINNED if args.unbinned else smcmc_b200.LLH_FAKE
+    eng = smcmc_b200.Engine(kind, 9, chains, seed=3, device=local, chain_offset=offset)
     if world > 1 and eg > 1:
         uid = [b.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         eng.comm_init(uid[0], world, rank, event_group=eg)
-    eng.set_fake_events(mine)
-    eng.set_fake_data(data, 0.1)
+    if args.unbinned:
+        eng.set_unbinned_events(mine)
+    else:
+        eng.set_fake_events(mine)
+        eng.set_fake_data(data, 0.1)
     x0 = np.zeros((chains, 9))
     for c in range(chains):
         x0[c] = np.random.default_rng([3, offset + c]).uniform(-1.0, 1.0, 9)
@@ -183,11 +187,15 @@ def c5(args):
     dt = float(t.item())
     if rank == 0:
         pairs = float(chains_total) * float(events_total) * args.steps
-        emit({"config": "C5", "target": "ensemble sweep of the event likelihood (binned Poisson, example/FakeLikelihood.H)",
+        target = ("ensemble sweep of the unbinned mixture likelihood (defined in smcmc_b200.h; 3 exp + 1 log1p in FP64 per pair)"
+                  if args.unbinned else "ensemble sweep of the event likelihood (binned Poisson, example/FakeLikelihood.H)")
+        exchange = ("all-reduce of %d partial log-likelihoods (f64) per step inside each event group" % chains if args.unbinned
+                    else "all-reduce of %d x %d uint32 event counts per step inside each event group" % (450, chains))
+        emit({"config": "C5", "target": target,
               "chains": chains_total, "events": events_total, "gpus": world, "chain_groups": chain_groups, "event_group": eg,
               "steps": args.steps, "s_per_step": dt / args.steps, "chain_steps_per_s": chains_total * args.steps / dt,
               "pair_evals_per_s": pairs / dt, "pair_evals_per_s_per_gpu": pairs / dt / world,
-              "exchange": "all-reduce of %d x %d uint32 event counts per step inside each event group" % (450, chains) if eg > 1 else "none"})
+              "exchange": exchange if eg > 1 else "none"})
     if world > 1:
         dist.destroy_process_group()
 
@@ -199,6 +207,7 @@ if __name__ == "__main__":
     ap.add_argument("--chains", type=int, default=262144)
     ap.add_argument("--events", type=int, default=16777216)
     ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--unbinned", action="store_true")
     a = ap.parse_args()
     for w in a.which:
         if w == "c5":

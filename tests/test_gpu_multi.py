@@ -44,6 +44,23 @@ def _worker(rank, world, uid, out_dir):
         np.savez(os.path.join(out_dir, "full.npz"), llh=f_llh, counts=f_counts, acc=ftr["accepted"],
                  pts=ftr["points"], la=ftr["llh_accepted"])
     eng.close()
+    # --- the unbinned likelihood: partial log-likelihoods of the event slices add up
+    ub = smcmc_b200.Engine(smcmc_b200.LLH_UNBINNED, 9, 96, seed=7, device=rank, chain_offset=0)
+    ub.comm_init(_THIRD_ID[0], world, rank, event_group=world)
+    ub.set_unbinned_events(events[rank::world])
+    u_llh = ub.eval(pts)
+    ub.start(pts)
+    utr = ub.step_trace(20, want=("accepted", "llh_accepted"))
+    np.savez(os.path.join(out_dir, "unb%d.npz" % rank), llh=u_llh, acc=utr["accepted"], la=utr["llh_accepted"])
+    ub.close()
+    if rank == 0:
+        fu = smcmc_b200.Engine(smcmc_b200.LLH_UNBINNED, 9, 96, seed=7, device=rank, chain_offset=0)
+        fu.set_unbinned_events(events)
+        f_llh = fu.eval(pts)
+        fu.start(pts)
+        ftr = fu.step_trace(20, want=("accepted", "llh_accepted"))
+        np.savez(os.path.join(out_dir, "unbfull.npz"), llh=f_llh, acc=ftr["accepted"], la=ftr["llh_accepted"])
+        fu.close()
     # --- pooled adaptation over chain shards: rank r owns chains [r*256, (r+1)*256)
     n = 6
     pe = smcmc_b200.Engine(smcmc_b200.LLH_UNIT_GAUSS, n, 256, seed=9, device=rank, chain_offset=rank * 256)
@@ -58,10 +75,12 @@ def _worker(rank, world, uid, out_dir):
 
 
 _SECOND_ID = [None]
+_THIRD_ID = [None]
 
 
-def _entry(rank, world, uid, uid2, out_dir):
+def _entry(rank, world, uid, uid2, uid3, out_dir):
     _SECOND_ID[0] = uid2
+    _THIRD_ID[0] = uid3
     _worker(rank, world, uid, out_dir)
 
 
@@ -69,8 +88,8 @@ def _entry(rank, world, uid, uid2, out_dir):
 def test_event_sharding_and_pooled_statistics_over_two_gpus(tmp_path):
     sys.path.insert(0, PKG)
     from smcmc_b200 import binding
-    uid, uid2 = binding.comm_unique_id(), binding.comm_unique_id()
-    mp.spawn(_entry, args=(2, uid, uid2, str(tmp_path)), nprocs=2, join=True)
+    uid, uid2, uid3 = binding.comm_unique_id(), binding.comm_unique_id(), binding.comm_unique_id()
+    mp.spawn(_entry, args=(2, uid, uid2, uid3, str(tmp_path)), nprocs=2, join=True)
     full = np.load(tmp_path / "full.npz")
     for r in range(2):
         s = np.load(tmp_path / ("shard%d.npz" % r))
@@ -80,6 +99,14 @@ def test_event_sharding_and_pooled_statistics_over_two_gpus(tmp_path):
         assert np.array_equal(s["acc"], full["acc"])
         assert np.array_equal(s["pts"], full["pts"])
         assert np.array_equal(s["la"], full["la"])
+    # unbinned: a floating-point sum, so the split changes the last bits only; both ranks
+    # hold the same all-reduced value
+    uf = np.load(tmp_path / "unbfull.npz")
+    u0, u1 = np.load(tmp_path / "unb0.npz"), np.load(tmp_path / "unb1.npz")
+    assert np.array_equal(u0["llh"], u1["llh"]) and np.array_equal(u0["acc"], u1["acc"])
+    assert np.max(np.abs(u0["llh"] / uf["llh"] - 1.0)) < 1e-12
+    assert np.array_equal(u0["acc"], uf["acc"])
+    assert np.allclose(u0["la"], uf["la"], rtol=1e-11)
     p0, p1 = np.load(tmp_path / "pool0.npz"), np.load(tmp_path / "pool1.npz")
     assert p0["count"][0] == 2 * 256 * 40
     for k in ("count", "cov", "mean", "u"):
