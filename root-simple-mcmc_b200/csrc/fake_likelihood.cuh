@@ -73,7 +73,14 @@ constexpr int kPairChunk = 8192;     // most events per CTA work item
 constexpr int kPairCounterRows = 100;
 // Private shared-memory counters are 16 bits wide (a chunk has fewer than 65536
 // events), two chains per 32-bit word: four CTAs fit one SM.
-constexpr int kPairCtasPerSm = 4;
+#ifndef SMCMC_PAIR_CTAS
+#define SMCMC_PAIR_CTAS 4
+#endif
+#ifndef SMCMC_PAIR_UNROLL
+#define SMCMC_PAIR_UNROLL 2
+#endif
+constexpr int kPairCtasPerSm = SMCMC_PAIR_CTAS;
+constexpr int kPairUnroll = SMCMC_PAIR_UNROLL;    // groups of four events in flight per thread
 static_assert(kPairChunk < (1 << 16), "a chunk must not overflow a counter");
 
 // Pre-images of the 50 bin edges under the host's exp, and of the cut at 500:
@@ -486,7 +493,7 @@ constexpr size_t kPairSmemTiles = 2 * sizeof(FilterTile);
 constexpr int kPairDummyRow = kPairCounterRows;
 constexpr size_t kPairSmemCounters = (size_t)(kPairCounterRows + 1) * kPairRowBytes;
 constexpr size_t kPairSmemBytes = kPairSmemTiles + 64 + kPairSmemCounters + sizeof(PairQueue);
-static_assert(4 * (kPairSmemBytes + 1024) <= 232448, "four CTAs per SM");
+static_assert(kPairCtasPerSm * (kPairSmemBytes + 1024) <= 232448, "resident CTAs per SM");
 
 // FP64 evaluation of one undecided pair and its count.
 __device__ __noinline__ void exactCount(const PreparedEvent* ev, const FakeChainParams* cp, int cls,
@@ -588,7 +595,7 @@ __device__ __forceinline__ unsigned tileLoop(const FilterTile* tile, const Filte
     const float4* nl4 = reinterpret_cast<const float4*>(tile->nl2);
     const float4* sp4 = reinterpret_cast<const float4*>(tile->sep);
     unsigned mask = 0;
-#pragma unroll 2
+#pragma unroll kPairUnroll
     for (int g = 0; g < kPairTile / 4; ++g) {
         const float4 ls = ls4[g], d = d4[g], nl = nl4[g];
         float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);

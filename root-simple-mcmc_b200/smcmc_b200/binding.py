@@ -93,7 +93,8 @@ class _Trace(ctypes.Structure):
 
 
 def library_path():
-    return os.path.join(HERE, "libsmcmc_b200.so")
+    # SMCMC_B200_LIB: an alternative build of the same library (kernel tuning experiments)
+    return os.environ.get("SMCMC_B200_LIB") or os.path.join(HERE, "libsmcmc_b200.so")
 
 
 def build_library(verbose=False):
