@@ -90,9 +90,12 @@ typedef enum smcmc_prop_field {
     SMCMC_PROP_NEXT_UPDATE = 10,         /* SetNextUpdate                  :992  */
     SMCMC_PROP_MAX_CORRELATION = 11,     /* SetMaximumCorrelation          :909  */
     SMCMC_PROP_STEP_RMS_WINDOW = 12,     /* TSimpleMCMC::SetStepRMSWindow  :511  */
-    SMCMC_PROP_POOLED_EVERY = 13         /* NEW (not in the reference): K > 0 pools the
+    SMCMC_PROP_POOLED_EVERY = 13,        /* NEW (not in the reference): K > 0 pools the
                                             covariance adaptation over all chains and
                                             GPUs, exchanging statistics every K steps   */
+    SMCMC_PROP_POOLED_TENSOR = 14        /* pooled mode: evaluate x' = x + (sigma z).U of all
+                                            chains as one GEMM on the FP64 tensor cores;
+                                            -1 automatic (dim >= 128, default), 0 off, 1 on */
 } smcmc_prop_field;
 
 /* Per-chain quantities readable with smcmc_get().  Arrays are chain-major:

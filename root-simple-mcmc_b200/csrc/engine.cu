@@ -129,6 +129,16 @@ struct smcmc_engine {
     // ---- pooled adaptation (pooled.cuh) -----------------------------------------
     int pooledEvery = 0;                            // 0 = per-chain adaptation (the reference)
     DeviceBuffer<double> poolStats, poolStatsAll, poolCov, poolDecomp, poolMean, poolTrace;
+    DeviceBuffer<double> poolDecompT, poolZ, poolY;  // TENSOR path of the pooled proposal (n >= 128)
+    int pooledTensor = -1;                          // -1: automatic (dim >= 128), 0: off, 1: on
+    bool usePooledTensor() const { return pooledTensor < 0 ? n() >= 128 : pooledTensor != 0; }
+    void poolTranspose() {
+        if (!usePooledTensor()) return;
+        const size_t nn = (size_t)n() * n();
+        poolDecompT.reserve(nn);
+        kTransposeSquare<<<ceilDiv((long long)nn, 256), 256, 0, stream>>>(poolDecomp.get(), poolDecompT.get(), n());
+        launched();
+    }
     DeviceBuffer<int> poolOk;
     int64_t poolExchanges = 0;
 
@@ -150,6 +160,9 @@ struct smcmc_engine {
     int poolStatCount() const { return 1 + n() + tri(); }
     void poolInit() {
         const size_t nn = (size_t)n() * n();
+        if ((size_t)32 * n() * sizeof(double) > 48 * 1024)
+            CUDA_CHECK(cudaFuncSetAttribute(kPoolAccumulate, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)((size_t)32 * n() * sizeof(double))));
         poolStats.reserve(poolStatCount());
         poolStatsAll.reserve(poolStatCount());
         poolCov.reserve(tri());
@@ -161,6 +174,7 @@ struct smcmc_engine {
         // every chain starts from the same U and trace (same settings): adopt chain 0's
         CUDA_CHECK(cudaMemcpyAsync(poolDecomp.get(), decomp.get(), nn * sizeof(double), cudaMemcpyDeviceToDevice, stream));
         CUDA_CHECK(cudaMemcpyAsync(poolTrace.get(), &sc.get()->sigmaTrace, sizeof(double), cudaMemcpyDeviceToDevice, stream));
+        poolTranspose();
     }
     void poolExchange() {
         CUDA_CHECK(cudaMemcpyAsync(poolStatsAll.get(), poolStats.get(), poolStatCount() * sizeof(double),
@@ -172,6 +186,7 @@ struct smcmc_engine {
         }
         kPoolFactor<<<1, 32, 0, stream>>>(pooled(), n(), poolOk.get());
         launched();
+        poolTranspose();
         ++poolExchanges;
     }
 
@@ -496,9 +511,21 @@ struct smcmc_engine {
         ChainArrays a = arrays();
         const int blocks = ceilDiv(E(), kWarpsPerBlock);
         const size_t smem = (size_t)kWarpsPerBlock * 3 * n() * sizeof(double);
-        if (pooledEvery > 0)
+        if (pooledEvery > 0 && usePooledTensor()) {
+            // x' = x + (sigma z) . U for all chains as one GEMM on the FP64 tensor cores
+            poolZ.reserve((size_t)E() * n());
+            poolY.reserve((size_t)E() * n());
             kProposePooled<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a, ps, pooled(), E(), cfg.seed,
-                                                                          cfg.chain_offset, stepIndex);
+                                                                          cfg.chain_offset, stepIndex, poolZ.get());
+            launched();
+            dim3 grid(ceilDiv(n(), kDmmaBN), ceilDiv(E(), kDmmaBM));
+            kDummyContractDmma<<<grid, 128, 0, stream>>>(poolZ.get(), poolDecompT.get(), poolY.get(), nullptr, 0, E(), n(), 0);
+            launched();
+            kProposePooledFinish<<<blocks, kWarpsPerBlock * 32, (size_t)kWarpsPerBlock * n() * sizeof(double), stream>>>(
+                a, ps, E(), poolY.get());
+        } else if (pooledEvery > 0)
+            kProposePooled<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a, ps, pooled(), E(), cfg.seed,
+                                                                          cfg.chain_offset, stepIndex, nullptr);
         else
             kPropose<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a, ps, E(), cfg.seed, cfg.chain_offset, stepIndex);
         launched();
@@ -721,6 +748,10 @@ int smcmc_prop_set(smcmc_engine* e, int field, double v) {
         case SMCMC_PROP_NEXT_UPDATE: perChain = true; break;
         case SMCMC_PROP_MAX_CORRELATION: e->maxCorr = v; break;
         case SMCMC_PROP_STEP_RMS_WINDOW: e->stepRMSWindow = (int)v; break;
+        case SMCMC_PROP_POOLED_TENSOR:
+            e->pooledTensor = (v < 0) ? -1 : (v != 0.0);
+            if (e->started && e->pooledEvery > 0 && e->poolStats.count() != 0) e->poolTranspose();
+            break;
         case SMCMC_PROP_POOLED_EVERY:
             if (v < 0) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "pooled exchange period must be >= 0");
             e->pooledEvery = (int)v;

@@ -120,7 +120,7 @@ __global__ void kPoolFactor(PooledState ps, int n, int* ok) {
 // (:1723-1776) per chain, then the draw (:709-724) with the SHARED U.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 8)
 kProposePooled(ChainArrays a, PropSettings ps, PooledState pool, int chains, uint64_t seed,
-               uint32_t chainOffset, uint32_t step) {
+               uint32_t chainOffset, uint32_t step, double* zOut) {
     extern __shared__ double smemD[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -184,6 +184,17 @@ kProposePooled(ChainArrays a, PropSettings ps, PooledState pool, int chains, uin
         }
     }
     __syncwarp();
+    if (zOut) {
+        // TENSOR path (n >= 128): the contraction z . U of all chains runs as one
+        // DMMA GEMM (contraction.cuh) and kProposePooledFinish completes the step
+        for (int i = lane; i < n; i += 32) {
+            const bool uniform = ps.type[i] == 1;
+            zOut[(size_t)c * n + i] = uniform ? 0.0 : zr[i];
+            if (uniform) xProp[i] = zr[i];
+        }
+        if (lane == 0) a.sc[c] = s;
+        return;
+    }
     const double* u = pool.decomp;
     for (int j = lane; j < n; j += 32) {
         double p;
@@ -219,6 +230,54 @@ kProposePooled(ChainArrays a, PropSettings ps, PooledState pool, int chains, uin
         s.stepRMS = __dsqrt_rn(ms);
     }
     if (lane == 0) a.sc[c] = s;
+}
+
+// TENSOR path, after the GEMM y = (sigma z) . U: x' = x + y on the Gaussian
+// dimensions (uniform ones were written by kProposePooled) and the step-RMS
+// tracker (TSimpleMCMC.H:391-406).
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+kProposePooledFinish(ChainArrays a, PropSettings ps, int chains, const double* __restrict__ y) {
+    extern __shared__ double smemD[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * kWarpsPerBlock + warp;
+    if (c >= chains) return;
+    const int n = ps.n;
+    double* diff = smemD + (size_t)warp * n;
+    ChainScalars s = a.sc[c];
+    if (!s.started || s.status != 0) return;
+    const double* xAcc = a.xAcc + (size_t)c * n;
+    double* xProp = a.xProp + (size_t)c * n;
+    for (int j = lane; j < n; j += 32) {
+        const double cur = xAcc[j];
+        double p;
+        if (ps.type[j] == 1) p = xProp[j];
+        else {
+            p = __dadd_rn(cur, y[(size_t)c * n + j]);
+            xProp[j] = p;
+        }
+        diff[j] = __dsub_rn(p, cur);
+    }
+    __syncwarp();
+    if (ps.stepRMSWindow > 0) {
+        double sqr = 0.0;
+        for (int i = 0; i < n; ++i) sqr = __dadd_rn(sqr, __dmul_rn(diff[i], diff[i]));
+        double ms = __dmul_rn(s.stepRMS, s.stepRMS);
+        ms = __dmul_rn(ms, (double)s.stepRMSTrials);
+        ms = __dadd_rn(ms, sqr);
+        ms = __ddiv_rn(ms, __dadd_rn((double)s.stepRMSTrials, 1.0));
+        s.stepRMSTrials = min(ps.stepRMSWindow, s.stepRMSTrials + 1);
+        s.stepRMS = __dsqrt_rn(ms);
+        if (lane == 0) a.sc[c] = s;
+    }
+}
+
+// ut[j][i] = u[i][j]: the K-contiguous operand of the GEMM.
+__global__ void kTransposeSquare(const double* __restrict__ u, double* __restrict__ ut, int n) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * n) return;
+    const int j = idx / n, i = idx - j * n;
+    ut[idx] = u[(size_t)i * n + j];
 }
 
 }  // namespace smcmc

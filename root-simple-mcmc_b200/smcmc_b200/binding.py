@@ -16,7 +16,7 @@ DUMMY_EXACT, DUMMY_TENSOR = 0, 1
  PROP_ACCEPTANCE_RIGIDITY, PROP_ACCEPTANCE_DEWEIGHT, PROP_COVARIANCE_WINDOW,
  PROP_COVARIANCE_DEWEIGHT, PROP_COVARIANCE_FROZEN, PROP_COVARIANCE_TRIALS,
  PROP_CENTER_TRIALS, PROP_NEXT_UPDATE, PROP_MAX_CORRELATION,
- PROP_STEP_RMS_WINDOW, PROP_POOLED_EVERY) = range(14)
+ PROP_STEP_RMS_WINDOW, PROP_POOLED_EVERY, PROP_POOLED_TENSOR) = range(15)
 
 # smcmc_field: name -> (id, dtype, shape code)
 _FIELDS = {
