@@ -46,9 +46,11 @@ typedef enum smcmc_likelihood {
     SMCMC_LLH_ASYM = 3,       /* piecewise linear    TAsymLogLikelihood.H:20-31   */
     SMCMC_LLH_FAKE = 4,       /* event reweighting + binned Poisson,
                                  example/FakeLikelihood.H:47-81,188-216          */
-    SMCMC_LLH_UNBINNED = 5    /* NOT in the reference: unbinned mixture likelihood over
+    SMCMC_LLH_UNBINNED = 5,   /* NOT in the reference: unbinned mixture likelihood over
                                  events (BASELINE.json configs[4]); see
                                  smcmc_unbinned_set_events                        */
+    SMCMC_LLH_HARD = 6        /* Rosenbrock valley   THardLogLikelihood.H:57-91 (with its
+                                 gradient functor for TSimpleHMC), dim >= 2       */
 } smcmc_likelihood;
 
 typedef struct smcmc_config {

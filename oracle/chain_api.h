@@ -27,6 +27,7 @@ enum {
     ORC_LLH_HORRIFIC = 2,   /* THorrificLogLikelihood.H:26-38                   */
     ORC_LLH_ASYM = 3,       /* TAsymLogLikelihood.H:20-31                       */
     ORC_LLH_FAKE = 4,       /* example/FakeLikelihood.H:47-81                   */
+    ORC_LLH_HARD = 6,       /* THardLogLikelihood.H:57-91 (Rosenbrock, with gradient) */
     ORC_LLH_UNBINNED = 5    /* NOT in the reference: the unbinned
                                mixture likelihood of BASELINE.json configs[4], defined in
                                include/smcmc_b200.h; events set with *_chain_set_fake */

@@ -18,7 +18,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-LLH_UNIT_GAUSS, LLH_DUMMY, LLH_HORRIFIC, LLH_ASYM, LLH_FAKE, LLH_UNBINNED = range(6)
+LLH_UNIT_GAUSS, LLH_DUMMY, LLH_HORRIFIC, LLH_ASYM, LLH_FAKE, LLH_UNBINNED, LLH_HARD = range(7)
 
 (SET_SIGMA, SET_TARGET_ACCEPTANCE, SET_ACCEPTANCE_WINDOW,
  SET_ACCEPTANCE_RIGIDITY, SET_ACCEPTANCE_DEWEIGHT, SET_COVARIANCE_WINDOW,

@@ -44,6 +44,10 @@ using namespace sMCMC;  // example/ predates the namespace
 #include "TDummyLogLikelihood.H"
 #include "THorrificLogLikelihood.H"
 #include "TAsymLogLikelihood.H"
+// THorrificLogLikelihood.H reuses the include guard of THardLogLikelihood.H
+// (a copy-paste quirk of the reference): release it so that both can be used.
+#undef THardLogLikelihood_H_seen
+#include "THardLogLikelihood.H"
 #include "example/FakeLikelihood.H"
 #define HMC_DEBUG_LEVEL -1
 #include "TSimpleHMC.H"
@@ -180,6 +184,10 @@ void* ref_chain_create(int kind, int dim, uint64_t seed, uint32_t chain) {
     case ORC_LLH_ASYM:
         if (dim != 100) { gLastError = "reference TASymLogLikelihood is 100-dim"; return 0; }
         c = new Chain<TASymLogLikelihood>(seed, chain, 100);
+        break;
+    case ORC_LLH_HARD:
+        if (dim != 6) { gLastError = "reference THardLogLikelihood is 6-dim"; return 0; }
+        c = new Chain<THardLogLikelihood>(seed, chain, 6);
         break;
     case ORC_LLH_FAKE:
         if (dim != (int)SystematicCorrection::kParamSize) { gLastError = "FakeLikelihood is 9-dim"; return 0; }
@@ -509,6 +517,10 @@ void* ref_hmc_create(int kind, int dim, int withGradient, uint64_t seed, uint32_
     }
     if (kind == ORC_LLH_UNIT_GAUSS) return new Hmc<UnitGaussLikelihood, SimpleHMCInvalidGradient>(seed, chain, dim);
     if (kind == ORC_LLH_HORRIFIC && dim == 75) return new Hmc<THorrificLogLikelihood, THorrificLogLikelihood>(seed, chain, 75);
+    if (kind == ORC_LLH_HARD && dim == 6) {
+        if (withGradient) return new Hmc<THardLogLikelihood, THardLogLikelihood>(seed, chain, 6);
+        return new Hmc<THardLogLikelihood, SimpleHMCInvalidGradient>(seed, chain, 6);
+    }
     gLastError = "unsupported HMC likelihood";
     return 0;
 }

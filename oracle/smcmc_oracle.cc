@@ -277,6 +277,15 @@ struct Likelihood {
             return EvalFake(x);
         case ORC_LLH_UNBINNED:
             return EvalUnbinned(x);
+        case ORC_LLH_HARD: {                 // THardLogLikelihood.H:57-69
+            double s = 0.0;
+            for (int i = 0; i < dim - 1; ++i) {
+                double a = (1.0 - x[i]);
+                double b = x[i + 1] - x[i] * x[i];
+                s -= a * a + 100.0 * b * b;
+            }
+            return s;
+        }
         }
         return std::numeric_limits<double>::quiet_NaN();
     }
@@ -747,7 +756,7 @@ extern "C" {
 const char* orc_last_error(void) { return gLastError.c_str(); }
 
 void* orc_chain_create(int kind, int dim, uint64_t seed, uint32_t chain) {
-    if (kind < ORC_LLH_UNIT_GAUSS || kind > ORC_LLH_UNBINNED || dim < 1) {
+    if (kind < ORC_LLH_UNIT_GAUSS || kind > ORC_LLH_HARD || dim < 1 || (kind == ORC_LLH_HARD && dim < 2)) {
         gLastError = "bad likelihood kind or dimension";
         return 0;
     }
@@ -977,6 +986,18 @@ struct OrcHmc {
     }
     // user gradient of log(likelihood): TDummyLogLikelihood.H:34-42
     bool UserGradient(std::vector<double>& g, const std::vector<double>& p) {
+        if (withGradient && like.kind == ORC_LLH_HARD) {              // THardLogLikelihood.H:72-91
+            const double B = 100.0;
+            g[0] = -2.0 * (1.0 - p[0]) - 4.0 * B * p[0] * (p[1] - p[0] * p[0]);
+            for (int i = 1; i < n - 1; ++i) {
+                g[i] = 2.0 * B * (p[i] - p[i - 1] * p[i - 1]);
+                g[i] += -2.0 * (1.0 - p[i]);
+                g[i] += -4.0 * B * p[i] * (p[i + 1] - p[i] * p[i]);
+            }
+            g[n - 1] = +2.0 * B * (p[n - 1] - p[n - 2] * p[n - 2]);
+            for (int i = 0; i < n; ++i) g[i] = -g[i];
+            return true;
+        }
         if (!withGradient || like.kind != ORC_LLH_DUMMY) return false;
         for (int i = 0; i < n; ++i) {
             g[i] = 0.0;
@@ -1241,7 +1262,8 @@ OrcHmc* HH(void* h) { return static_cast<OrcHmc*>(h); }
 extern "C" {
 
 void* orc_hmc_create(int kind, int dim, int withGradient, uint64_t seed, uint32_t chain) {
-    if (kind < ORC_LLH_UNIT_GAUSS || kind > ORC_LLH_ASYM || dim < 1) { gLastError = "unsupported HMC likelihood"; return 0; }
+    if (!((kind >= ORC_LLH_UNIT_GAUSS && kind <= ORC_LLH_ASYM) || kind == ORC_LLH_HARD) || dim < 1 ||
+        (kind == ORC_LLH_HARD && dim < 2)) { gLastError = "unsupported HMC likelihood"; return 0; }
     OrcHmc* c = new OrcHmc;
     c->n = dim;
     c->like.kind = kind;

@@ -583,8 +583,10 @@ int smcmc_create(const smcmc_config* cfg, smcmc_engine** out) {
         if (!cfg || !out) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null argument");
         if (cfg->struct_size != sizeof(smcmc_config)) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "smcmc_config size mismatch");
         if (cfg->dim < 1 || cfg->chains < 1) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "dim and chains must be positive");
-        if (cfg->likelihood < SMCMC_LLH_UNIT_GAUSS || cfg->likelihood > SMCMC_LLH_UNBINNED)
+        if (cfg->likelihood < SMCMC_LLH_UNIT_GAUSS || cfg->likelihood > SMCMC_LLH_HARD)
             throw Error(SMCMC_ERR_INVALID_ARGUMENT, "unknown likelihood");
+        if (cfg->likelihood == SMCMC_LLH_HARD && cfg->dim < 2)
+            throw Error(SMCMC_ERR_INVALID_ARGUMENT, "THardLogLikelihood needs two or more dimensions");
         if ((cfg->likelihood == SMCMC_LLH_FAKE || cfg->likelihood == SMCMC_LLH_UNBINNED) && cfg->dim != 9)
             throw Error(SMCMC_ERR_INVALID_ARGUMENT, "the event likelihood functors have 9 parameters");
         int count = 0;

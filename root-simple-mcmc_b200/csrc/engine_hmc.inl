@@ -68,7 +68,8 @@ void requireHmcStarted(smcmc_engine* e) {
 enum HmcGradientMode { kGradUser, kGradFinite, kGradCovariant, kGradZero };
 
 HmcGradientMode hmcResolveGradient(smcmc_engine* e, int type) {
-    const bool haveUser = e->hmc.userGradient && e->cfg.likelihood == SMCMC_LLH_DUMMY;
+    const bool haveUser = e->hmc.userGradient &&
+                          (e->cfg.likelihood == SMCMC_LLH_DUMMY || e->cfg.likelihood == SMCMC_LLH_HARD);
     switch (type) {
     case 2:
         if (!e->hmc.keepError)
@@ -89,6 +90,12 @@ void hmcGradient(smcmc_engine* e, HmcGradientMode mode, int k) {
     const int E = e->E(), n = e->n();
     switch (mode) {
     case kGradUser: {
+        if (e->cfg.likelihood == SMCMC_LLH_HARD) {
+            kHardGradient<<<ceilDiv((long long)E * n, 256), 256, 0, e->stream>>>(h.qProp.get(), h.grad.get(),
+                                                                                h.leapSteps.get(), k, E, n);
+            e->launched();
+            break;
+        }
         if (e->errDim != n) throw Error(SMCMC_ERR_LOGIC, "error matrix not set (smcmc_dummy_set_error)");
         if (e->dummyMode == SMCMC_DUMMY_TENSOR) {
             dim3 grid(ceilDiv(n, kDmmaBN), ceilDiv(E, kDmmaBM));
@@ -191,8 +198,8 @@ int smcmc_hmc_set(smcmc_engine* e, int setting, double v) {
         switch (setting) {
         case SMCMC_HMC_ALPHA: h.alpha = v; return;
         case SMCMC_HMC_USER_GRADIENT:
-            if (v != 0.0 && e->cfg.likelihood != SMCMC_LLH_DUMMY)
-                throw Error(SMCMC_ERR_INVALID_ARGUMENT, "only TDummyLogLikelihood provides a gradient functor");
+            if (v != 0.0 && e->cfg.likelihood != SMCMC_LLH_DUMMY && e->cfg.likelihood != SMCMC_LLH_HARD)
+                throw Error(SMCMC_ERR_INVALID_ARGUMENT, "only TDummyLogLikelihood and THardLogLikelihood provide a gradient functor");
             h.userGradient = (v != 0.0);
             return;
         case SMCMC_HMC_KEEP_ERROR_MATRIX:

@@ -53,6 +53,43 @@ __device__ __forceinline__ double llhAsym(const double* x, int n) {
     return s;
 }
 
+// THardLogLikelihood.H:57-69 (ROSEN_B = 100).
+__device__ __forceinline__ double llhHard(const double* x, int n) {
+    double s = 0.0;
+    for (int i = 0; i + 1 < n; ++i) {
+        const double a = __dsub_rn(1.0, x[i]);
+        const double b = __dsub_rn(x[i + 1], __dmul_rn(x[i], x[i]));
+        s = __dsub_rn(s, __dadd_rn(__dmul_rn(a, a), __dmul_rn(__dmul_rn(100.0, b), b)));
+    }
+    return s;
+}
+
+// The gradient functor of THardLogLikelihood (:72-91) followed by the sign flip
+// of TSimpleHMC::PotentialGradient (TSimpleHMC.H:478-487): two exact negations of
+// the Rosenbrock gradient r.  One thread per (chain, dimension).
+// leapSteps / k as kDummyGradient.
+__global__ void kHardGradient(const double* __restrict__ x, double* __restrict__ grad,
+                              const int* __restrict__ leapSteps, int k, int chains, int n) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)chains * n) return;
+    const int c = (int)(idx / n), i = (int)(idx - (size_t)c * n);
+    const int steps = leapSteps[c];
+    if (steps < 1 || k > steps) return;
+    const double* p = x + (size_t)c * n;
+    double g;
+    if (i == 0) {
+        g = __dsub_rn(-__dmul_rn(2.0, __dsub_rn(1.0, p[0])),
+                      __dmul_rn(__dmul_rn(400.0, p[0]), __dsub_rn(p[1], __dmul_rn(p[0], p[0]))));
+    } else if (i < n - 1) {
+        g = __dmul_rn(200.0, __dsub_rn(p[i], __dmul_rn(p[i - 1], p[i - 1])));
+        g = __dadd_rn(g, -__dmul_rn(2.0, __dsub_rn(1.0, p[i])));
+        g = __dadd_rn(g, __dmul_rn(__dmul_rn(-400.0, p[i]), __dsub_rn(p[i + 1], __dmul_rn(p[i], p[i]))));
+    } else {
+        g = __dmul_rn(200.0, __dsub_rn(p[i], __dmul_rn(p[i - 1], p[i - 1])));
+    }
+    grad[idx] = -(-g);
+}
+
 // TDummyLogLikelihood for many points: one THREAD per point, the block's points
 // transposed into shared memory (xs[j][point], lane = point: conflict-free).  The
 // error matrix is read through its transpose errT[i][j] = Error(j,i), one row per
@@ -117,6 +154,7 @@ __global__ void kSimpleLikelihood(int kind, const double* __restrict__ x, int m,
     case SMCMC_LLH_UNIT_GAUSS: v = llhUnitGauss(p, n); break;
     case SMCMC_LLH_DUMMY: v = llhDummy(p, n, err); break;
     case SMCMC_LLH_HORRIFIC: v = llhHorrific(p, n); break;
+    case SMCMC_LLH_HARD: v = llhHard(p, n); break;
     default: v = llhAsym(p, n); break;
     }
     out[c] = v;

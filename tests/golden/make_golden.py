@@ -137,6 +137,8 @@ def make_chains():
                 c.set_correlation(i, j, float(rng.uniform(-0.2, 0.2)))
         c.set_correlation(2, 3, 2.0)     # clamped to the maximum correlation
     put("unit6_clamped", run_chain(cc.LLH_UNIT_GAUSS, 6, 3, 4, 1500, nasty))
+    # SimpleMCMC.C -DUSE_HARD_LIKELIHOOD: the 6-dimensional Rosenbrock valley
+    put("hard6", run_chain(cc.LLH_HARD, 6, 13, 2, 2500, x0=np.full(6, 0.5)))
     # checkpoint / resume: 250 unsaved + 50 saved steps, SaveStep(), then a NEW
     # sampler is started, Restore()d from that tree and run on (TSimpleMCMC.H:282-352)
     a = cc.CpuChain("ref", cc.LLH_UNIT_GAUSS, 7, 31, 2)

@@ -44,6 +44,7 @@ GOLDEN_CHAINS = {
     "asym100": (3, 100, 4, 12, 1500, 0.01),
     "dummy100": (1, 100, 9, 0, 1200, None),
     "unit6_clamped": (0, 6, 3, 4, 1500, None),
+    "hard6": (6, 6, 13, 2, 2500, 0.5),
 }
 
 
@@ -76,6 +77,9 @@ HMC_GOLDEN = {
     "unit5_flat": dict(kind=0, dim=5, grad=False, seed=26, chain=4, nsteps=200, gtype=5, x0=0.1),
     "unit5_forced": dict(kind=0, dim=5, grad=False, seed=27, chain=6, nsteps=200, gtype=0, x0=0.1,
                          pre=(("leapfrog", 0),)),
+    # SimpleHMC.C -DUSE_HARD_LIKELIHOOD: the Rosenbrock valley with its gradient functor
+    "hard6_user": dict(kind=6, dim=6, grad=True, seed=41, chain=3, nsteps=400, gtype=0, x0=0.8),
+    "hard6_finite": dict(kind=6, dim=6, grad=False, seed=42, chain=0, nsteps=150, gtype=0, x0=0.8),
 }
 
 # Chains the reference build cannot run (its TDummyLogLikelihood is hard-wired to

@@ -29,7 +29,7 @@ def device_hmc(cfg, error, chains=4):
         eng.set_error_matrix(error)
     # THorrificLogLikelihood's gradient functor exists but declines (:41-43):
     # the same as having none
-    eng.hmc_set(b.HMC_USER_GRADIENT, 1 if (cfg["grad"] and cfg["kind"] == 1) else 0)
+    eng.hmc_set(b.HMC_USER_GRADIENT, 1 if (cfg["grad"] and cfg["kind"] in (1, 6)) else 0)
     if cfg["gtype"] == 2:
         eng.hmc_set(b.HMC_KEEP_ERROR_MATRIX, 1)
     fields = {"alpha": b.HMC_ALPHA, "mean_epsilon": b.HMC_MEAN_EPSILON, "leapfrog": b.HMC_LEAPFROG}
