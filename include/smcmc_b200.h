@@ -373,6 +373,12 @@ int smcmc_measure_fp64_peak(int device, double* tflops);
  * every SM).  The roofline denominator of the event-pair kernel, which needs two
  * exponentials per (chain, event) pair. */
 int smcmc_measure_sfu_peak(int device, double* gops);
+/* Device self-test of the shared-divisor division of the staged covariance
+ * update (csrc/proposal_staged.cuh, replacing the per-entry division of
+ * TSimpleMCMC.H:1811): `count` random numerators and divisors are divided both
+ * ways; *mismatches receives the number of quotients that differ in any bit
+ * from the correctly rounded IEEE quotient. */
+int smcmc_selftest_division(int device, int64_t count, uint64_t seed, int64_t* mismatches);
 
 #ifdef __cplusplus
 }

@@ -18,6 +18,7 @@
 #include "nccl_dyn.h"
 #include "pooled.cuh"
 #include "proposal.cuh"
+#include "proposal_staged.cuh"
 #include "simple_likelihoods.cuh"
 #include "unbinned_likelihood.cuh"
 
@@ -88,7 +89,10 @@ struct smcmc_engine {
     DeviceBuffer<double> dParam1, dParam2, dCorrValue;
 
     // ---- per-chain state ---------------------------------------------------
-    DeviceBuffer<double> xAcc, xProp, lastPoint, center, cov, decomp, llhProp;
+    DeviceBuffer<double> xAcc, xProp, lastPoint, center, cov, decomp, upk, llhProp;
+    DeviceBuffer<uint32_t> ijTab;
+    int covStride = 0, upkStride = 0;   // doubles per chain (whole 128-byte lines)
+    bool staged = false;                // kProposeStaged (one CTA per chain) instead of kPropose
     DeviceBuffer<ChainScalars> sc;
     DeviceBuffer<int32_t> okDev;
     DeviceBuffer<double> eigScratch;
@@ -219,6 +223,7 @@ struct smcmc_engine {
         a.center = center.get();
         a.cov = cov.get();
         a.decomp = decomp.get();
+        a.upk = upk.get();
         a.sc = sc.get();
         a.eigScratch = eigScratch.get();
         a.eigLocks = eigLocks.get();
@@ -251,6 +256,9 @@ struct smcmc_engine {
         PropSettings ps;
         ps.n = n();
         ps.tri = tri();
+        ps.covStride = covStride;
+        ps.upkStride = upkStride;
+        ps.ijTab = ijTab.get();
         ps.covFrozen = covFrozen;
         ps.stepRMSWindow = stepRMSWindow;
         ps.ncorr = (int)corrValue.size();
@@ -526,6 +534,9 @@ struct smcmc_engine {
         } else if (pooledEvery > 0)
             kProposePooled<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a, ps, pooled(), E(), cfg.seed,
                                                                           cfg.chain_offset, stepIndex, nullptr);
+        else if (staged)
+            kProposeStaged<<<E(), kStagedThreads, stagedChainBytes(n(), covStride, upkStride), stream>>>(
+                a, ps, E(), cfg.seed, cfg.chain_offset, stepIndex);
         else
             kPropose<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a, ps, E(), cfg.seed, cfg.chain_offset, stepIndex);
         launched();
@@ -612,8 +623,27 @@ int smcmc_create(const smcmc_config* cfg, smcmc_engine** out) {
         e->xProp.reserve(E * n);
         e->lastPoint.reserve(E * n);
         e->center.reserve(E * n);
-        e->cov.reserve(E * (n * (n + 1) / 2));
+        const size_t tri = n * (n + 1) / 2;
+        e->covStride = (int)((tri + 15) / 16 * 16);
+        e->upkStride = (upkTotal((int)n) + 15) / 16 * 16;
+        e->cov.reserve(E * e->covStride);
         e->decomp.reserve(E * n * n);
+        e->upk.reserve(E * e->upkStride);
+        {
+            std::vector<uint32_t> tab(tri);
+            for (size_t i = 0, k = 0; i < n; ++i)
+                for (size_t j = 0; j <= i; ++j) tab[k++] = (uint32_t)(i * 8) | ((uint32_t)(j * 8) << 16);
+            e->ijTab.reserve(tri);
+            CUDA_CHECK(cudaMemcpy(e->ijTab.get(), tab.data(), tri * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
+        // kProposeStaged (one CTA per chain) when at least four chains fit an SM (227 KB)
+        {
+            const size_t cb = stagedChainBytes((int)n, e->covStride, e->upkStride);
+            if ((227 * 1024) / (cb + 1024) >= 4 && n < 8192 && !std::getenv("SMCMC_PROPOSE_GENERIC")) {
+                e->staged = true;
+                CUDA_CHECK(cudaFuncSetAttribute(kProposeStaged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cb));
+            }
+        }
         e->llhProp.reserve(E);
         e->sc.reserve(E);
         e->okDev.reserve(E);
@@ -625,6 +655,7 @@ int smcmc_create(const smcmc_config* cfg, smcmc_engine** out) {
         CUDA_CHECK(cudaMemset(e->sc.get(), 0, e->sc.bytes()));
         CUDA_CHECK(cudaMemset(e->cov.get(), 0, e->cov.bytes()));
         CUDA_CHECK(cudaMemset(e->decomp.get(), 0, e->decomp.bytes()));
+        CUDA_CHECK(cudaMemset(e->upk.get(), 0, e->upk.bytes()));
         CUDA_CHECK(cudaMemset(e->center.get(), 0, e->center.bytes()));
         CUDA_CHECK(cudaMemset(e->lastPoint.get(), 0, e->lastPoint.bytes()));
         // TProposeAdaptiveStep constructor defaults, TSimpleMCMC.H:642-655
@@ -1133,7 +1164,9 @@ int smcmc_save_state(smcmc_engine* e, const smcmc_saved_state* out) {
         CUDA_CHECK(cudaMemcpy(h.data(), e->sc.get(), sizeof(ChainScalars) * E, cudaMemcpyDeviceToHost));
         if (out->accepted) CUDA_CHECK(cudaMemcpy(out->accepted, e->xAcc.get(), E * n * 8, cudaMemcpyDeviceToHost));
         if (out->central_point) CUDA_CHECK(cudaMemcpy(out->central_point, e->center.get(), E * n * 8, cudaMemcpyDeviceToHost));
-        if (out->covariance) CUDA_CHECK(cudaMemcpy(out->covariance, e->cov.get(), E * tri * 8, cudaMemcpyDeviceToHost));
+        if (out->covariance)
+            CUDA_CHECK(cudaMemcpy2D(out->covariance, tri * 8, e->cov.get(), (size_t)e->covStride * 8, tri * 8, E,
+                                    cudaMemcpyDeviceToHost));
         for (size_t c = 0; c < E; ++c) {
             if (out->log_likelihood) out->log_likelihood[c] = h[c].accLlh;
             if (out->total_steps) out->total_steps[c] = h[c].totalSteps;
@@ -1174,7 +1207,8 @@ int smcmc_restore_state(smcmc_engine* e, const smcmc_saved_state* in, int32_t* m
         };
         CUDA_CHECK(cudaMemcpyAsync(e->xAcc.get(), in->accepted, E * n * 8, cudaMemcpyHostToDevice, e->stream));
         CUDA_CHECK(cudaMemcpyAsync(e->center.get(), in->central_point, E * n * 8, cudaMemcpyHostToDevice, e->stream));
-        CUDA_CHECK(cudaMemcpyAsync(e->cov.get(), in->covariance, E * tri * 8, cudaMemcpyHostToDevice, e->stream));
+        CUDA_CHECK(cudaMemcpy2DAsync(e->cov.get(), (size_t)e->covStride * 8, in->covariance, tri * 8, tri * 8, E,
+                                     cudaMemcpyHostToDevice, e->stream));
         RestoreScalars r;
         r.savedLlh = upD(d[0], in->log_likelihood);
         r.stepRMS = upD(d[1], in->step_rms);
@@ -1226,7 +1260,12 @@ int smcmc_get(smcmc_engine* e, int field, void* dst, size_t bytes) {
         case SMCMC_F_ACCEPTED: copyArray(e->xAcc.get(), E * n * 8); return;
         case SMCMC_F_PROPOSED: copyArray(e->xProp.get(), E * n * 8); return;
         case SMCMC_F_CENTER: copyArray(e->center.get(), E * n * 8); return;
-        case SMCMC_F_COVARIANCE: copyArray(e->cov.get(), E * e->tri() * 8); return;
+        case SMCMC_F_COVARIANCE:
+            need(E * e->tri() * 8);
+            CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)e->tri() * 8, e->cov.get(), (size_t)e->covStride * 8,
+                                         (size_t)e->tri() * 8, E, cudaMemcpyDeviceToHost, e->stream));
+            CUDA_CHECK(cudaStreamSynchronize(e->stream));
+            return;
         case SMCMC_F_DECOMPOSITION: copyArray(e->decomp.get(), E * n * n * 8); return;
         case SMCMC_F_COVARIANCE_WINDOW: need(8); *(double*)dst = e->covWindow; return;
         case SMCMC_F_ACCEPTANCE_WINDOW: need(8); *(double*)dst = e->accWindow; return;
@@ -1276,7 +1315,8 @@ int smcmc_get(smcmc_engine* e, int field, void* dst, size_t bytes) {
         case SMCMC_F_COVARIANCE_TRACE: {
             need(E * 8);
             std::vector<double> covHost(E * e->tri());
-            CUDA_CHECK(cudaMemcpyAsync(covHost.data(), e->cov.get(), covHost.size() * 8, cudaMemcpyDeviceToHost, e->stream));
+            CUDA_CHECK(cudaMemcpy2DAsync(covHost.data(), (size_t)e->tri() * 8, e->cov.get(), (size_t)e->covStride * 8,
+                                         (size_t)e->tri() * 8, E, cudaMemcpyDeviceToHost, e->stream));
             CUDA_CHECK(cudaStreamSynchronize(e->stream));
             for (size_t c = 0; c < E; ++c) {
                 double t = 0.0;                                             // :961-967
@@ -1357,6 +1397,26 @@ __global__ void __launch_bounds__(256) kSfuPeak(float* out, float a, int iters) 
     if (s == 12345.678f) out[0] = s;     // never true: keeps the chains alive
 }
 }  // namespace smcmc
+
+int smcmc_selftest_division(int device, int64_t count, uint64_t seed, int64_t* mismatches) {
+    return guarded(nullptr, [&]() {
+        if (!mismatches || count < 0) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "bad arguments");
+        int devices = 0;
+        if (cudaGetDeviceCount(&devices) != cudaSuccess || device < 0 || device >= devices) {
+            cudaGetLastError();
+            throw Error(SMCMC_ERR_NO_DEVICE, "no CUDA device");
+        }
+        CUDA_CHECK(cudaSetDevice(device));
+        DeviceBuffer<unsigned long long> bad;
+        bad.reserve(1);
+        CUDA_CHECK(cudaMemset(bad.get(), 0, sizeof(unsigned long long)));
+        kSelftestDivision<<<148 * 8, 256>>>(seed, (long long)count, bad.get());
+        CUDA_CHECK(cudaGetLastError());
+        unsigned long long h = 0;
+        CUDA_CHECK(cudaMemcpy(&h, bad.get(), sizeof h, cudaMemcpyDeviceToHost));
+        *mismatches = (int64_t)h;
+    });
+}
 
 int smcmc_measure_sfu_peak(int device, double* gops) {
     return guarded(nullptr, [&]() {

@@ -32,6 +32,7 @@
 
 #include "seqsum.h"
 #include "smcmc_b200.h"
+#include "tma.cuh"
 
 namespace smcmc {
 
@@ -416,42 +417,6 @@ static_assert(kPairRowBytes == 512, "row stride of the counter table");
 
 __device__ __forceinline__ void redShared(unsigned addr, unsigned value) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(value) : "memory");
-}
-
-// ---------------------------------------------------------------------------
-// TMA bulk copy + mbarrier helpers (sm_90+ PTX; SASS: UBLKCP / SYNCS).
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smemAddr(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(smemAddr(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tmaLoad1D(void* dstSmem, const void* srcGlobal, uint32_t bytes,
-                                          uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smemAddr(dstSmem)),
-        "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar))
-        : "memory");
 }
 
 // ---------------------------------------------------------------------------

@@ -161,6 +161,7 @@ def load_library():
         "smcmc_enable_kernel_timing": (ci, [vp, ci]),
         "smcmc_measure_fp64_peak": (ci, [ci, ctypes.POINTER(cd)]),
         "smcmc_measure_sfu_peak": (ci, [ci, ctypes.POINTER(cd)]),
+        "smcmc_selftest_division": (ci, [ci, ctypes.c_int64, ctypes.c_uint64, ctypes.POINTER(ctypes.c_int64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -183,7 +184,7 @@ EXPORTED_SYMBOLS = [
     "smcmc_hmc_set", "smcmc_hmc_start", "smcmc_hmc_set_position", "smcmc_hmc_step",
     "smcmc_hmc_step_trace", "smcmc_hmc_get",
     "smcmc_pair_kernel_stats", "smcmc_enable_kernel_timing",
-    "smcmc_measure_fp64_peak", "smcmc_measure_sfu_peak",
+    "smcmc_measure_fp64_peak", "smcmc_measure_sfu_peak", "smcmc_selftest_division",
 ]
 
 
@@ -212,6 +213,17 @@ def measure_sfu_peak(device=0):
     lib = load_library()
     out = ctypes.c_double()
     rc = lib.smcmc_measure_sfu_peak(device, ctypes.byref(out))
+    if rc != 0:
+        raise SmcmcError(rc, lib.smcmc_last_error(None).decode())
+    return out.value
+
+
+def selftest_division(count, seed=1, device=0):
+    """Number of quotients of the staged covariance update's shared-divisor division
+    that differ from the IEEE quotient, over `count` random cases (must be 0)."""
+    lib = load_library()
+    out = ctypes.c_int64()
+    rc = lib.smcmc_selftest_division(device, count, seed, ctypes.byref(out))
     if rc != 0:
         raise SmcmcError(rc, lib.smcmc_last_error(None).decode())
     return out.value

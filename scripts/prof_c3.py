@@ -6,5 +6,5 @@ sys.path.insert(0, os.path.join(ROOT, "root-simple-mcmc_b200")); sys.path.insert
 import smcmc_b200
 eng = smcmc_b200.Engine(smcmc_b200.LLH_HORRIFIC, 50, 65536, seed=4)
 eng.start(np.zeros(50))
-eng.step(6); eng.sync()
+eng.step(int(os.environ.get("C3_STEPS", "40"))); eng.sync()
 print("done", eng.get("acceptance").mean())
