@@ -56,7 +56,7 @@ struct HmcHost {
     double alpha = 0.0;              // fAlpha                 TSimpleHMC.H:133
     int userGradient = 0;            // TSimpleHMC<L, L> instead of TSimpleHMC<L>
     int keepError = 0;               // keep fEstimatedError per chain
-    DeviceBuffer<double> qAcc, pAcc, qProp, pProp, p0, grad, central, average, exxt, estErr, repairedDiag;
+    DeviceBuffer<double> qAcc, pAcc, qProp, pProp, p0, grad, central, average, exxt, exxtT, estErr, repairedDiag;
     DeviceBuffer<double> llh, fdWork, fdLlh, avgPts, avgLlh;
     DeviceBuffer<HmcScalars> sc;
     DeviceBuffer<int> leapSteps, counters, updateList;

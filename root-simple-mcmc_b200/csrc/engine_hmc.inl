@@ -19,6 +19,8 @@ void hmcAllocate(smcmc_engine* e) {
     h.average.reserve(E * n);
     h.repairedDiag.reserve(E * n);
     h.exxt.reserve(E * tri);
+    h.exxtT.reserve(E);
+    CUDA_CHECK(cudaMemset(h.exxtT.get(), 0xFF, E * sizeof(double)));
     h.llh.reserve(E);
     h.sc.reserve(E);
     h.leapSteps.reserve(E);
@@ -48,6 +50,7 @@ HmcArrays hmcArrays(smcmc_engine* e) {
     a.central = h.central.get();
     a.average = h.average.get();
     a.exxt = h.exxt.get();
+    a.exxtT = h.exxtT.get();
     a.estErr = h.keepError ? h.estErr.get() : nullptr;
     a.repairedDiag = h.repairedDiag.get();
     a.sc = h.sc.get();
@@ -171,6 +174,13 @@ void hmcStepOnce(smcmc_engine* e, int type, const HmcTraceDev& tr, int traceStep
     e->evaluate(h.qProp.get(), E, h.llh.get(), nullptr);                  // :327
     kHmcPost<<<blocks, threads, smem, e->stream>>>(a, n, E, h.llh.get(), 1000000.0 /* fCovarianceWindow :134 */);
     e->launched();
+    {
+        const long long tri = (long long)n * (n + 1) / 2;
+        const int perZ = std::min(E, 32768);
+        dim3 grid(ceilDiv(tri, kExxtPerBlock), perZ, ceilDiv(E, perZ));
+        kHmcExxtUpdate<<<grid, kExxtThreads, (size_t)n * sizeof(double), e->stream>>>(a, n, E);   // :678-686
+        e->launched();
+    }
     const int updates = hmcReadCounter(e, 1);
     if (updates > 0) {
         h.avgPts.reserve((size_t)updates * n);

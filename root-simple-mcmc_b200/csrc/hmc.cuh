@@ -85,6 +85,7 @@ struct HmcArrays {
     double* central;    // fCentralPoint
     double* average;    // fAveragePoint
     double* exxt;       // fEXXT, packed lower triangle
+    double* exxtT;      // per chain: fCovarianceTrials before this step's UpdateCovariance, NaN = no update
     double* estErr;     // fEstimatedError or nullptr
     double* repairedDiag;
     HmcScalars* sc;
@@ -427,6 +428,7 @@ kHmcPost(HmcArrays a, int n, int chains, const double* __restrict__ llhProp, dou
     const size_t row = (size_t)c * n;
     const size_t tri = (size_t)n * (n + 1) / 2;
     s.needUpdate = 0;
+    if (lane == 0) a.exxtT[c] = __longlong_as_double(-1ll);                // NaN: no UpdateCovariance this step
 
     if (s.leapFrogSteps > 0) {                                            // :302-323
         if (s.okLeap != 2) {
@@ -470,33 +472,11 @@ kHmcPost(HmcArrays a, int n, int chains, const double* __restrict__ llhProp, dou
         }
         for (int i = lane; i < n; i += 32) buf[i] = a.qAcc[row + i];
         __syncwarp();
-        {
-            const double t = s.covTrials, t1 = __dadd_rn(t, 1.0);
-            double* ex = a.exxt + (size_t)c * tri;
-            for (int i = 0; i < n; ++i) {         // row i of the packed lower triangle: lanes across j <= i
-                double* exRow = ex + triIndex(i, 0);
-                const double xi = buf[i];
-                int j = lane;
-                for (; j + 96 <= i; j += 128) {   // four independent loads in flight per lane
-                    double v[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) v[u] = exRow[j + 32 * u];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        double w = __dmul_rn(v[u], t);
-                        w = __dadd_rn(w, __dmul_rn(xi, buf[j + 32 * u]));
-                        exRow[j + 32 * u] = __ddiv_rn(w, t1);
-                    }
-                }
-                for (; j <= i; j += 32) {
-                    double v = __dmul_rn(exRow[j], t);
-                    v = __dadd_rn(v, __dmul_rn(xi, buf[j]));
-                    v = __ddiv_rn(v, t1);
-                    exRow[j] = v;
-                }
-            }
-            s.covTrials = fmin(covWindow, t1);
-        }
+        // fEXXT itself (n(n+1)/2 entries per chain) is updated by kHmcExxtUpdate,
+        // launched right after this kernel; only the diagonal is needed here.
+        const double exxtT = s.covTrials, exxtT1 = __dadd_rn(exxtT, 1.0);
+        if (lane == 0) a.exxtT[c] = exxtT;
+        s.covTrials = fmin(covWindow, exxtT1);
         s.repaired = 0;          // fEstimatedCovariance is again fEXXT - mean mean^T
         __syncwarp();
         // ---- UpdateErrorMatrix up to its trigger, :703-719 ---------------
@@ -504,7 +484,11 @@ kHmcPost(HmcArrays a, int n, int chains, const double* __restrict__ llhProp, dou
             const double* ex = a.exxt + (size_t)c * tri;
             for (int i = lane; i < n; i += 32) {
                 const double m = a.average[row + i];
-                buf[i] = fabs(__dsub_rn(ex[triIndex(i, i)], __dmul_rn(m, m)));
+                const double xi = buf[i];
+                double d = __dmul_rn(ex[triIndex(i, i)], exxtT);          // the updated diagonal entry, :683
+                d = __dadd_rn(d, __dmul_rn(xi, xi));
+                d = __ddiv_rn(d, exxtT1);
+                buf[i] = fabs(__dsub_rn(d, __dmul_rn(m, m)));
             }
             __syncwarp();
             s.curCovTrace = warpSeqSum(buf, n);
@@ -525,6 +509,64 @@ kHmcPost(HmcArrays a, int n, int chains, const double* __restrict__ llhProp, dou
         if (s.meanEpsilon > 0) s.meanEpsilon = __dmul_rn(0.3, s.meanEpsilon);   // :343
     }
     if (lane == 0) a.sc[c] = s;
+}
+
+// UpdateCovariance's fEXXT(i,j) = (fEXXT(i,j) T + x_i x_j) / (T + 1), TSimpleHMC.H:678-686,
+// for the chains kHmcPost marked (exxtT[c] = T): a flat streaming kernel, one CTA
+// per 4096 consecutive entries of one chain's packed triangle (HBM-bound: 16 bytes
+// of traffic per entry).  (i, j) is decoded once per thread and advanced with the
+// packed index.
+constexpr int kExxtThreads = 256;
+constexpr int kExxtPerBlock = 4096;
+__global__ void __launch_bounds__(kExxtThreads)
+kHmcExxtUpdate(HmcArrays a, int n, int chains) {
+    extern __shared__ double smemD[];
+    const int c = blockIdx.y + gridDim.y * blockIdx.z;
+    if (c >= chains) return;
+    const double t = a.exxtT[c];
+    if (!(t >= 0.0)) return;
+    const double t1 = __dadd_rn(t, 1.0);
+    const bool fast = t1 >= 1.0 && t1 <= 1152921504606846976.0;
+    const double y = __ddiv_rn(1.0, t1);
+    const long long tri = (long long)n * (n + 1) / 2;
+    const long long k0 = (long long)blockIdx.x * kExxtPerBlock;
+    const long long kEnd = min(tri, k0 + kExxtPerBlock);
+    const double* x = a.qAcc + (size_t)c * n;
+    // the rows this CTA touches end at row iMax: only x[0..iMax] is needed
+    int iMax = (int)((sqrt(8.0 * (double)(kEnd - 1) + 1.0) - 1.0) * 0.5) + 1;
+    if (iMax > n - 1) iMax = n - 1;
+    for (int i = threadIdx.x; i <= iMax; i += kExxtThreads) smemD[i] = x[i];
+    __syncthreads();
+    double* ex = a.exxt + (size_t)c * tri;
+    long long k = k0 + threadIdx.x;
+    if (k >= kEnd) return;
+    int i = (int)((sqrt(8.0 * (double)k + 1.0) - 1.0) * 0.5);
+    while ((long long)i * (i + 1) / 2 > k) --i;
+    while ((long long)(i + 1) * (i + 2) / 2 <= k) ++i;
+    int j = (int)(k - (long long)i * (i + 1) / 2);
+    constexpr int kUnroll = 4;
+    for (; k < kEnd; k += (long long)kUnroll * kExxtThreads) {
+        double v[kUnroll], r[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long ku = k + (long long)u * kExxtThreads;
+            v[u] = ku < kEnd ? ex[ku] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            r[u] = (k + (long long)u * kExxtThreads < kEnd) ? __dmul_rn(smemD[i], smemD[j]) : 0.0;
+            j += kExxtThreads;
+            while (j > i) { j -= i + 1; ++i; }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long ku = k + (long long)u * kExxtThreads;
+            if (ku < kEnd) {
+                const double w = __dadd_rn(__dmul_rn(v[u], t), r[u]);
+                ex[ku] = fast ? divideByShared(w, t1, y) : __ddiv_rn(w, t1);
+            }
+        }
+    }
 }
 
 // Copy the average points of the chains in the update list to a dense array.
