@@ -49,8 +49,14 @@ typedef enum smcmc_likelihood {
     SMCMC_LLH_UNBINNED = 5,   /* NOT in the reference: unbinned mixture likelihood over
                                  events (BASELINE.json configs[4]); see
                                  smcmc_unbinned_set_events                        */
-    SMCMC_LLH_HARD = 6        /* Rosenbrock valley   THardLogLikelihood.H:57-91 (with its
+    SMCMC_LLH_HARD = 6,       /* Rosenbrock valley   THardLogLikelihood.H:57-91 (with its
                                  gradient functor for TSimpleHMC), dim >= 2       */
+    SMCMC_LLH_FAKE2 = 7       /* example2/FakeLikelihood.H:58-118,222-289: the same event
+                                 corrections and cuts, signal and background filled into
+                                 separate histograms, each renormalised to the event
+                                 counts x[0], x[1] by its integral, plus the penalty terms
+                                 (:91-115).  Events and data histograms are set with the
+                                 smcmc_fake_* calls; the exposure argument is not used  */
 } smcmc_likelihood;
 
 typedef struct smcmc_config {

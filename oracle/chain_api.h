@@ -28,6 +28,8 @@ enum {
     ORC_LLH_ASYM = 3,       /* TAsymLogLikelihood.H:20-31                       */
     ORC_LLH_FAKE = 4,       /* example/FakeLikelihood.H:47-81                   */
     ORC_LLH_HARD = 6,       /* THardLogLikelihood.H:57-91 (Rosenbrock, with gradient) */
+    ORC_LLH_FAKE2 = 7,      /* example2/FakeLikelihood.H:58-118, 222-289 (events and data
+                               set with *_chain_set_fake; the exposure is not used)   */
     ORC_LLH_UNBINNED = 5    /* NOT in the reference: the unbinned
                                mixture likelihood of BASELINE.json configs[4], defined in
                                include/smcmc_b200.h; events set with *_chain_set_fake */

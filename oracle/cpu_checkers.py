@@ -18,7 +18,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-LLH_UNIT_GAUSS, LLH_DUMMY, LLH_HORRIFIC, LLH_ASYM, LLH_FAKE, LLH_UNBINNED, LLH_HARD = range(7)
+LLH_UNIT_GAUSS, LLH_DUMMY, LLH_HORRIFIC, LLH_ASYM, LLH_FAKE, LLH_UNBINNED, LLH_HARD, LLH_FAKE2 = range(8)
 
 (SET_SIGMA, SET_TARGET_ACCEPTANCE, SET_ACCEPTANCE_WINDOW,
  SET_ACCEPTANCE_RIGIDITY, SET_ACCEPTANCE_DEWEIGHT, SET_COVARIANCE_WINDOW,
@@ -116,6 +116,8 @@ def load(which):
                                           ctypes.c_long, vp, vp]
         lib.ref_dummy_matrices.restype = ci
         lib.ref_dummy_matrices.argtypes = [vp, vp]
+        lib.ref_ex2_generate.restype = ctypes.c_long
+        lib.ref_ex2_generate.argtypes = [ctypes.c_ulong, ci, ci, cd, vp, ctypes.c_long, vp]
     _LIBS[which] = lib
     return lib
 
@@ -313,6 +315,18 @@ def ref_generate(seed, data_signal, data_background, oversample):
     got = lib.ref_fake_generate(seed, data_signal, data_background, float(oversample),
                                 _ptr(ev), n, _ptr(data), _ptr(expo))
     return ev[:got], data, float(expo[0])
+
+
+def ref2_generate(seed, data_signal, data_background, oversample):
+    """Run example2's own FakeLikelihood::Init() (example2/FakeLikelihood.H:123-199)
+    under a seeded shim generator: (events, data150)."""
+    lib = load("ref")
+    cap = 8 * (int(oversample * max(data_signal, 1000)) + int(2 * oversample * max(data_background, 1000))) + 4096
+    ev = np.zeros(cap, EVENT_DTYPE)
+    data = np.zeros(150)
+    got = lib.ref_ex2_generate(seed, data_signal, data_background, float(oversample), _ptr(ev), cap, _ptr(data))
+    assert got <= cap
+    return ev[:got], data
 
 
 def ref_dummy_matrices():

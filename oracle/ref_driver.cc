@@ -54,9 +54,29 @@ using namespace sMCMC;  // example/ predates the namespace
 #undef private
 #undef protected
 
+// oracle/ref_ex2.cc: the reference's example2 likelihood (own translation unit)
+extern "C" {
+void* ref_ex2_create(void);
+void ref_ex2_destroy(void* h);
+int ref_ex2_set(void* h, const orc_event* ev, long n, const double* data150);
+double ref_ex2_llh(void* h, const double* x, int n);
+int ref_ex2_hist(void* h, const double* x, int n, double* out150);
+}
+
 namespace {
 
 std::string gLastError;
+
+// example2's FakeLikelihood behind the likelihood-functor contract
+// (TSimpleMCMC.H:59-106): TSimpleMCMC holds it by value and calls operator().
+class Example2Likelihood {
+public:
+    Example2Likelihood() : impl(ref_ex2_create()) {}
+    ~Example2Likelihood() { ref_ex2_destroy(impl); }
+    Example2Likelihood(const Example2Likelihood&) = delete;
+    double operator()(const Vector& point) { return ref_ex2_llh(impl, point.data(), (int)point.size()); }
+    void* impl;
+};
 
 // gRandom replacement: call k of step s of chain c returns slot k.
 class InjectedRandom : public TRandom {
@@ -109,6 +129,7 @@ struct ChainBase {
     virtual void SaveStep() = 0;
     virtual void Restore(TTree* tree) = 0;
     virtual FakeLikelihood* Fake() { return 0; }
+    virtual void* Fake2() { return 0; }
     TTree tree;      // every chain writes to its own in-memory tree
 };
 
@@ -141,6 +162,11 @@ struct FakeChain : public Chain<FakeLikelihood> {
         like.SimulatedClose = like.SimulatedSeparated = like.SimulatedDecayTag = 0;
     }
     FakeLikelihood* Fake() { return &mcmc.GetLogLikelihood(); }
+};
+
+struct Fake2Chain : public Chain<Example2Likelihood> {
+    Fake2Chain(uint64_t seed, uint32_t chain, int d) : Chain<Example2Likelihood>(seed, chain, d) {}
+    void* Fake2() { return mcmc.GetLogLikelihood().impl; }
 };
 
 ChainBase* H(void* h) { return static_cast<ChainBase*>(h); }
@@ -193,6 +219,10 @@ void* ref_chain_create(int kind, int dim, uint64_t seed, uint32_t chain) {
         if (dim != (int)SystematicCorrection::kParamSize) { gLastError = "FakeLikelihood is 9-dim"; return 0; }
         c = new FakeChain(seed, chain, dim);
         break;
+    case ORC_LLH_FAKE2:
+        if (dim != 9) { gLastError = "example2 FakeLikelihood is 9-dim"; return 0; }
+        c = new Fake2Chain(seed, chain, dim);
+        break;
     default:
         gLastError = "unknown likelihood kind";
         return 0;
@@ -205,6 +235,7 @@ void ref_chain_destroy(void* h) { delete H(h); }
 
 int ref_chain_set_fake(void* h, const orc_event* ev, long n,
                        const double* data150, double exposure) {
+    if (H(h)->Fake2()) return ref_ex2_set(H(h)->Fake2(), ev, n, data150);
     FakeLikelihood* like = H(h)->Fake();
     if (!like) { gLastError = "not a FakeLikelihood chain"; return -1; }
     static_assert(sizeof(Simulated::Event) == sizeof(orc_event), "event layout");
@@ -382,6 +413,7 @@ double ref_chain_llh(void* h, const double* x) {
 }
 
 int ref_chain_fake_hist(void* h, const double* x, double* out150) {
+    if (H(h)->Fake2()) return ref_ex2_hist(H(h)->Fake2(), x, H(h)->dim, out150);
     FakeLikelihood* like = H(h)->Fake();
     if (!like) { gLastError = "not a FakeLikelihood chain"; return -1; }
     std::vector<double> p(x, x + H(h)->dim);

@@ -237,6 +237,96 @@ struct Likelihood {
         return logLikelihood;
     }
 
+    // ---- example2 ---------------------------------------------------------
+    // example2/SystematicCorrection.H:75-117: no event-count factor, no exposure
+    static double EventWeight2(const orc_event& e, const double* p) {
+        double weight = 1.0;
+        if (e.Type < 0) return weight;
+        const double trueFakes = 0.05;
+        double fakes = std::tan(M_PI * (trueFakes - 0.5));
+        fakes += p[7];
+        fakes = std::atan(fakes) / M_PI + 0.5;
+        if (e.Type == 0) {
+            if (e.MuDk > 0) weight *= fakes / trueFakes;
+            else weight *= (1.0 - fakes) / (1.0 - trueFakes);
+        }
+        const double trueEff = 0.5;
+        double eff = std::tan(M_PI * (trueEff - 0.5));
+        eff += p[8];
+        eff = std::atan(eff) / M_PI + 0.5;
+        if (e.Type > 0) {
+            if (e.MuDk > 0) weight *= eff / trueEff;
+            else weight *= (1.0 - eff) / (1.0 - trueEff);
+        }
+        return weight;
+    }
+    // example2/FakeLikelihood.H:222-289: six histograms (signal | background x
+    // Close, Separated, DecayTag), their integrals, and the renormalised
+    // expectation left in sim[h][1..50].  Mass, separation and the cuts are
+    // those of example/ (identical functions, example2/SystematicCorrection.H:30-73).
+    void FillFake2(const double* p) {
+        double part[2][3][52];
+        std::memset(part, 0, sizeof(part));
+        for (size_t i = 0; i < events.size(); ++i) {
+            const orc_event& e = events[i];
+            double mass = InvariantMass(e, p);
+            double sep = Separation(e, p);
+            double w = EventWeight2(e, p);
+            if (mass > 500.0) continue;
+            if (mass < 0.0) continue;
+            if (sep < 0.0) continue;
+            int h = 1;
+            if (e.MuDk > 0) h = 2;
+            else if (sep < 100.0) h = 0;
+            part[e.Type == 0 ? 0 : 1][h][FindBin50(mass)] += w;      // IsSignal: Type == 0
+        }
+        double norm[2];
+        for (int k = 0; k < 2; ++k) {
+            double integral[3];
+            for (int h = 0; h < 3; ++h) {                           // TH1::Integral: bins 1..50
+                double t = 0.0;
+                for (int b = 1; b <= 50; ++b) t += part[k][h][b];
+                integral[h] = t;
+            }
+            double t = integral[2];                                 // DecayTag, Close, Separated :266-275
+            t += integral[0];
+            t += integral[1];
+            norm[k] = p[k] / t;
+        }
+        std::memset(sim, 0, sizeof(sim));
+        for (int h = 0; h < 3; ++h)
+            for (int b = 0; b < 52; ++b) {                          // TH1::Add, every cell :280-287
+                sim[h][b] += norm[0] * part[0][h][b];
+                sim[h][b] += norm[1] * part[1][h][b];
+            }
+    }
+    // example2/FakeLikelihood.H:58-118
+    double EvalFake2(const double* p) {
+        FillFake2(p);
+        double logLikelihood = 0.0;
+        for (int h = 0; h < 3; ++h) {
+            for (int b = 1; b <= 50; ++b) {
+                double d = data[h * 50 + b - 1];
+                double mc = sim[h][b];
+                if (mc < 0.001) mc = 0.001;
+                double v = d - mc;
+                if (d > 0.0) v += d * std::log(mc / d);
+                logLikelihood += v;
+            }
+        }
+        double v = p[0];
+        if (v < 0.0) logLikelihood -= 10.0 + std::abs(logLikelihood);
+        v = p[1];
+        if (v < 0.0) logLikelihood -= 10.0 + std::abs(logLikelihood);
+        v = p[6] / 5.0;
+        logLikelihood -= 0.5 * v * v;
+        v = p[7] / 1.0;
+        logLikelihood -= 0.5 * v * v;
+        v = p[8] / 1.0;
+        logLikelihood -= 0.5 * v * v;
+        return logLikelihood;
+    }
+
     double operator()(const double* x) {
         switch (kind) {
         case ORC_LLH_UNIT_GAUSS: {           // TSimpleMCMC.H:113-119
@@ -275,6 +365,8 @@ struct Likelihood {
         }
         case ORC_LLH_FAKE:
             return EvalFake(x);
+        case ORC_LLH_FAKE2:
+            return EvalFake2(x);
         case ORC_LLH_UNBINNED:
             return EvalUnbinned(x);
         case ORC_LLH_HARD: {                 // THardLogLikelihood.H:57-69
@@ -756,11 +848,11 @@ extern "C" {
 const char* orc_last_error(void) { return gLastError.c_str(); }
 
 void* orc_chain_create(int kind, int dim, uint64_t seed, uint32_t chain) {
-    if (kind < ORC_LLH_UNIT_GAUSS || kind > ORC_LLH_HARD || dim < 1 || (kind == ORC_LLH_HARD && dim < 2)) {
+    if (kind < ORC_LLH_UNIT_GAUSS || kind > ORC_LLH_FAKE2 || dim < 1 || (kind == ORC_LLH_HARD && dim < 2)) {
         gLastError = "bad likelihood kind or dimension";
         return 0;
     }
-    if ((kind == ORC_LLH_FAKE || kind == ORC_LLH_UNBINNED) && dim != 9) { gLastError = "FakeLikelihood is 9-dim"; return 0; }
+    if ((kind == ORC_LLH_FAKE || kind == ORC_LLH_FAKE2 || kind == ORC_LLH_UNBINNED) && dim != 9) { gLastError = "FakeLikelihood is 9-dim"; return 0; }
     OrcChain* c = new OrcChain;
     c->n = dim;
     c->like.kind = kind;
@@ -776,7 +868,7 @@ void orc_chain_destroy(void* h) { delete H(h); }
 
 int orc_chain_set_fake(void* h, const orc_event* ev, long n, const double* data150, double exposure) {
     Likelihood& l = H(h)->like;
-    if (l.kind != ORC_LLH_FAKE && l.kind != ORC_LLH_UNBINNED) { gLastError = "not a FakeLikelihood chain"; return -1; }
+    if (l.kind != ORC_LLH_FAKE && l.kind != ORC_LLH_FAKE2 && l.kind != ORC_LLH_UNBINNED) { gLastError = "not a FakeLikelihood chain"; return -1; }
     l.events.assign(ev, ev + n);
     if (data150) std::copy(data150, data150 + 150, l.data);
     l.exposure = exposure;
@@ -890,8 +982,9 @@ double orc_chain_llh(void* h, const double* x) { return H(h)->like(x); }
 
 int orc_chain_fake_hist(void* h, const double* x, double* out150) {
     Likelihood& l = H(h)->like;
-    if (l.kind != ORC_LLH_FAKE) { gLastError = "not a FakeLikelihood chain"; return -1; }
-    l.FillFake(x);
+    if (l.kind != ORC_LLH_FAKE && l.kind != ORC_LLH_FAKE2) { gLastError = "not a FakeLikelihood chain"; return -1; }
+    if (l.kind == ORC_LLH_FAKE2) l.FillFake2(x);
+    else l.FillFake(x);
     for (int hh = 0; hh < 3; ++hh)
         for (int b = 0; b < 50; ++b) out150[hh * 50 + b] = l.sim[hh][b + 1];
     return 0;
@@ -914,7 +1007,7 @@ int orc_chain_step_saved(void* h, int nsteps, int32_t* accepted) {
 
 int orc_chain_fake_counts(void* h, const double* x, uint32_t* out450) {
     Likelihood& l = H(h)->like;
-    if (l.kind != ORC_LLH_FAKE) { gLastError = "not a FakeLikelihood chain"; return -1; }
+    if (l.kind != ORC_LLH_FAKE && l.kind != ORC_LLH_FAKE2) { gLastError = "not a FakeLikelihood chain"; return -1; }
     l.CountFake(x, out450);
     return 0;
 }

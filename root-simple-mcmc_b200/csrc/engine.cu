@@ -304,6 +304,7 @@ struct smcmc_engine {
     void evaluate(const double* xDev, int m, double* llhDev, double* histDev) {
         switch (cfg.likelihood) {
         case SMCMC_LLH_FAKE:
+        case SMCMC_LLH_FAKE2:
             evaluateFake(xDev, m, llhDev, histDev);
             break;
         case SMCMC_LLH_UNBINNED:
@@ -404,7 +405,8 @@ struct smcmc_engine {
         fakeCountStride = stride;
         CUDA_CHECK(cudaMemsetAsync(fakeCounts.get(), 0, (size_t)kFakeSlots * stride * sizeof(uint32_t), stream));
         kFakePrepareChains<<<ceilDiv(m, 128), 128, 0, stream>>>(xDev, m, n(), fakeExposure, fakeChains.get(),
-                                                                fakeFilterChains.get(), exactOnly ? 1 : 0);
+                                                                fakeFilterChains.get(), exactOnly ? 1 : 0,
+                                                                cfg.likelihood == SMCMC_LLH_FAKE2 ? 1 : 0);
         launched();
 
         PairLaunch L = pairLaunch(m, stride);
@@ -438,8 +440,12 @@ struct smcmc_engine {
             nccl.check(nccl.AllReduce(fakeCounts.get(), fakeCounts.get(), (size_t)kFakeSlots * stride, ncclUint32,
                                       ncclSum, eventComm, stream), "all-reduce of event counts");
         }
-        kFakeFinish<<<ceilDiv(m, 32), 32 * kFinishWarps, 0, stream>>>(fakeCounts.get(), stride, m, fakeChains.get(),
-                                                                      fakeData.get(), llhDev, histDev);
+        if (cfg.likelihood == SMCMC_LLH_FAKE2)
+            kFake2Finish<<<ceilDiv(m, 32), 32 * kFinishWarps, kFinish2SmemBytes, stream>>>(
+                fakeCounts.get(), stride, m, fakeChains.get(), fakeData.get(), xDev, n(), llhDev, histDev);
+        else
+            kFakeFinish<<<ceilDiv(m, 32), 32 * kFinishWarps, 0, stream>>>(fakeCounts.get(), stride, m, fakeChains.get(),
+                                                                          fakeData.get(), llhDev, histDev);
         launched();
     }
 
@@ -594,11 +600,12 @@ int smcmc_create(const smcmc_config* cfg, smcmc_engine** out) {
         if (!cfg || !out) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null argument");
         if (cfg->struct_size != sizeof(smcmc_config)) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "smcmc_config size mismatch");
         if (cfg->dim < 1 || cfg->chains < 1) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "dim and chains must be positive");
-        if (cfg->likelihood < SMCMC_LLH_UNIT_GAUSS || cfg->likelihood > SMCMC_LLH_HARD)
+        if (cfg->likelihood < SMCMC_LLH_UNIT_GAUSS || cfg->likelihood > SMCMC_LLH_FAKE2)
             throw Error(SMCMC_ERR_INVALID_ARGUMENT, "unknown likelihood");
         if (cfg->likelihood == SMCMC_LLH_HARD && cfg->dim < 2)
             throw Error(SMCMC_ERR_INVALID_ARGUMENT, "THardLogLikelihood needs two or more dimensions");
-        if ((cfg->likelihood == SMCMC_LLH_FAKE || cfg->likelihood == SMCMC_LLH_UNBINNED) && cfg->dim != 9)
+        if ((cfg->likelihood == SMCMC_LLH_FAKE || cfg->likelihood == SMCMC_LLH_FAKE2 ||
+             cfg->likelihood == SMCMC_LLH_UNBINNED) && cfg->dim != 9)
             throw Error(SMCMC_ERR_INVALID_ARGUMENT, "the event likelihood functors have 9 parameters");
         int count = 0;
         cudaError_t ce = cudaGetDeviceCount(&count);
@@ -675,7 +682,8 @@ int smcmc_create(const smcmc_config* cfg, smcmc_engine** out) {
             double consts[4] = {std::tan(M_PI * (0.05 - 0.5)), std::tan(M_PI * (0.5 - 0.5)), M_PI, 0.0};
             CUDA_CHECK(cudaMemcpyToSymbol(gFakeConst, consts, sizeof(consts)));
         }
-        if (cfg->likelihood == SMCMC_LLH_FAKE) {
+        if (cfg->likelihood == SMCMC_LLH_FAKE || cfg->likelihood == SMCMC_LLH_FAKE2) {
+            CUDA_CHECK(cudaFuncSetAttribute(kFake2Finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinish2SmemBytes));
             // Pre-images of the TH1 bin edges under this host's exp: bin(exp(l)).
             double edges[52];
             edges[0] = -std::numeric_limits<double>::infinity();
@@ -868,7 +876,8 @@ int smcmc_prop_reset(smcmc_engine* e) {
 
 int smcmc_fake_set_events(smcmc_engine* e, const smcmc_event* events, int64_t count) {
     return guarded(e, [&]() {
-        if (e->cfg.likelihood != SMCMC_LLH_FAKE) throw Error(SMCMC_ERR_LOGIC, "engine was not created with SMCMC_LLH_FAKE");
+        if (e->cfg.likelihood != SMCMC_LLH_FAKE && e->cfg.likelihood != SMCMC_LLH_FAKE2)
+            throw Error(SMCMC_ERR_LOGIC, "engine was not created with SMCMC_LLH_FAKE or SMCMC_LLH_FAKE2");
         if (count < 0 || (count > 0 && !events)) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "bad event array");
         if (count > 0xffffffffLL) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "more than 2^32 events per engine");
         // One arena for everything that only lives during the re-layout (raw
@@ -999,7 +1008,8 @@ int smcmc_unbinned_set_events(smcmc_engine* e, const smcmc_event* events, int64_
 
 int smcmc_fake_set_data(smcmc_engine* e, const double* data150, double exposure) {
     return guarded(e, [&]() {
-        if (e->cfg.likelihood != SMCMC_LLH_FAKE) throw Error(SMCMC_ERR_LOGIC, "engine was not created with SMCMC_LLH_FAKE");
+        if (e->cfg.likelihood != SMCMC_LLH_FAKE && e->cfg.likelihood != SMCMC_LLH_FAKE2)
+            throw Error(SMCMC_ERR_LOGIC, "engine was not created with SMCMC_LLH_FAKE or SMCMC_LLH_FAKE2");
         if (!data150) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null data histograms");
         CUDA_CHECK(cudaMemcpyAsync(e->fakeData.get(), data150, 150 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
         CUDA_CHECK(cudaStreamSynchronize(e->stream));
@@ -1047,7 +1057,8 @@ static void evalHost(smcmc_engine* e, const double* x, int m, double* llh, doubl
 
 int smcmc_fake_histograms(smcmc_engine* e, const double* x, int m, double* out) {
     return guarded(e, [&]() {
-        if (e->cfg.likelihood != SMCMC_LLH_FAKE) throw Error(SMCMC_ERR_LOGIC, "engine was not created with SMCMC_LLH_FAKE");
+        if (e->cfg.likelihood != SMCMC_LLH_FAKE && e->cfg.likelihood != SMCMC_LLH_FAKE2)
+            throw Error(SMCMC_ERR_LOGIC, "engine was not created with SMCMC_LLH_FAKE or SMCMC_LLH_FAKE2");
         if (!out) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null output");
         evalHost(e, x, m, nullptr, out);
     });
@@ -1055,7 +1066,8 @@ int smcmc_fake_histograms(smcmc_engine* e, const double* x, int m, double* out) 
 
 int smcmc_fake_counts(smcmc_engine* e, const double* x, int m, uint32_t* out) {
     return guarded(e, [&]() {
-        if (e->cfg.likelihood != SMCMC_LLH_FAKE) throw Error(SMCMC_ERR_LOGIC, "engine was not created with SMCMC_LLH_FAKE");
+        if (e->cfg.likelihood != SMCMC_LLH_FAKE && e->cfg.likelihood != SMCMC_LLH_FAKE2)
+            throw Error(SMCMC_ERR_LOGIC, "engine was not created with SMCMC_LLH_FAKE or SMCMC_LLH_FAKE2");
         if (!out) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null output");
         evalHost(e, x, m, nullptr, nullptr);
         const int stride = e->fakeCountStride;
@@ -1069,7 +1081,8 @@ int smcmc_fake_counts(smcmc_engine* e, const double* x, int m, uint32_t* out) {
 
 int smcmc_fake_filter_check(smcmc_engine* e, const double* x, int m, uint64_t* out3) {
     return guarded(e, [&]() {
-        if (e->cfg.likelihood != SMCMC_LLH_FAKE) throw Error(SMCMC_ERR_LOGIC, "engine was not created with SMCMC_LLH_FAKE");
+        if (e->cfg.likelihood != SMCMC_LLH_FAKE && e->cfg.likelihood != SMCMC_LLH_FAKE2)
+            throw Error(SMCMC_ERR_LOGIC, "engine was not created with SMCMC_LLH_FAKE or SMCMC_LLH_FAKE2");
         if (!out3) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null output");
         evalHost(e, x, m, nullptr, nullptr);         // fills the per-chain constants for these points
         PairLaunch L = e->pairLaunch(m, e->fakeCountStride);

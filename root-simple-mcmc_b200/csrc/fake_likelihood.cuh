@@ -175,9 +175,12 @@ __global__ void kFakeGather(const smcmc_event* __restrict__ ev, int64_t n, const
 struct FilterChain;
 __device__ __forceinline__ void storeFilterChain(FilterChain* dst, int c, const FakeChainParams& cp, int exactOnly);
 
+// variant 0: example/SystematicCorrection.H; variant 1: example2/SystematicCorrection.H
+// (:75-117), whose EventWeight has neither the exp(p/10) event-count factors nor
+// the exposure ratio (the counts are applied by the renormalisation in kFake2Finish).
 __global__ void kFakePrepareChains(const double* __restrict__ x, int m, int dim,
                                    double exposure, FakeChainParams* out, FilterChain* fout,
-                                   int exactOnly) {
+                                   int exactOnly, int variant) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= m) return;
     const double* p = x + (size_t)c * dim;
@@ -200,10 +203,18 @@ __global__ void kFakePrepareChains(const double* __restrict__ x, int m, int dim,
     double sigNo = __dmul_rn(wSig, __ddiv_rn(__dsub_rn(1.0, fakes), __dsub_rn(1.0, trueFakes)));    // :101
     double bkgTag = __dmul_rn(wBkg, __ddiv_rn(eff, trueEff));                                       // :112
     double bkgNo = __dmul_rn(wBkg, __ddiv_rn(__dsub_rn(1.0, eff), __dsub_rn(1.0, trueEff)));        // :113
-    cp.weight[0] = __dmul_rn(sigNo, exposure);                         // :116
-    cp.weight[1] = __dmul_rn(sigTag, exposure);
-    cp.weight[2] = __dmul_rn(bkgNo, exposure);
-    cp.weight[3] = __dmul_rn(bkgTag, exposure);
+    if (variant == 0) {
+        cp.weight[0] = __dmul_rn(sigNo, exposure);                     // :116
+        cp.weight[1] = __dmul_rn(sigTag, exposure);
+        cp.weight[2] = __dmul_rn(bkgNo, exposure);
+        cp.weight[3] = __dmul_rn(bkgTag, exposure);
+    } else {
+        // weight = 1.0; weight *= ratio  (example2/SystematicCorrection.H:76,98-99,110-111)
+        cp.weight[0] = __dmul_rn(1.0, __ddiv_rn(__dsub_rn(1.0, fakes), __dsub_rn(1.0, trueFakes)));
+        cp.weight[1] = __dmul_rn(1.0, __ddiv_rn(fakes, trueFakes));
+        cp.weight[2] = __dmul_rn(1.0, __ddiv_rn(__dsub_rn(1.0, eff), __dsub_rn(1.0, trueEff)));
+        cp.weight[3] = __dmul_rn(1.0, __ddiv_rn(eff, trueEff));
+    }
     out[c] = cp;
     storeFilterChain(fout, c, cp, exactOnly);
 }
@@ -884,6 +895,110 @@ kFakeFinish(const uint32_t* __restrict__ counts, int pointStride, int m,
         double s = 0.0;                                                 // :51,59 in bin order
         for (int hb = 0; hb < 150; ++hb) s = __dadd_rn(s, term[hb][lane]);
         llhOut[point] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// example2/FakeLikelihood.H: counts -> the six signal / background histograms ->
+// their integrals -> renormalised expectation (:266-288) -> log-likelihood and
+// penalty terms (:58-118).  Block = 32 points (lane = point) x kFinishWarps warps
+// striding the 150 bins; dynamic shared memory 2 x 150 x 33 doubles.
+// Event order as in kFakeFinish: background events, then data-typed ones (which
+// IsSignal() sends to the background histograms with weight 1).
+// ---------------------------------------------------------------------------
+constexpr size_t kFinish2SmemBytes = (size_t)2 * 150 * 33 * sizeof(double);
+
+__global__ void __launch_bounds__(32 * kFinishWarps)
+kFake2Finish(const uint32_t* __restrict__ counts, int pointStride, int m,
+             const FakeChainParams* __restrict__ chains, const double* __restrict__ data150,
+             const double* __restrict__ x, int dim, double* llhOut, double* histOut) {
+    extern __shared__ double fin2[];
+    double (*sig)[33] = reinterpret_cast<double (*)[33]>(fin2);              // later: the bin terms
+    double (*bkg)[33] = reinterpret_cast<double (*)[33]>(fin2 + 150 * 33);
+    __shared__ double norm[2][32];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int point = blockIdx.x * 32 + lane;
+    const bool live = point < m;
+    double w[4] = {0, 0, 0, 0};
+    if (live) {
+        for (int k = 0; k < 4; ++k) w[k] = chains[point].weight[k];
+    }
+    for (int hb = warp; hb < 150; hb += kFinishWarps) {
+        const int h = hb / 50, b = hb - h * 50;
+        double s = 0.0, g = 0.0;
+        if (live) {
+            uint32_t nSig, nBkg;
+            double wSig, wBkg;
+            if (h < 2) {
+                nSig = counts[(size_t)(0 + h * 50 + b) * pointStride + point];
+                nBkg = counts[(size_t)(150 + h * 50 + b) * pointStride + point];
+                wSig = w[0];
+                wBkg = w[2];
+            } else {
+                nSig = counts[(size_t)(100 + b) * pointStride + point];
+                nBkg = counts[(size_t)(250 + b) * pointStride + point];
+                wSig = w[1];
+                wBkg = w[3];
+            }
+            const uint32_t nDat = counts[(size_t)(300 + hb) * pointStride + point];
+            s = smcmc_seq_add(0.0, wSig, nSig);                          // Simulated*Signal      :244-262
+            g = smcmc_seq_add(0.0, wBkg, nBkg);                          // Simulated*Background
+            g = smcmc_seq_add(g, 1.0, nDat);
+        }
+        sig[hb][lane] = s;
+        bkg[hb][lane] = g;
+    }
+    __syncthreads();
+    if (warp == 0 && live) {
+        // TH1::Integral: bins 1..50 in order; DecayTag, Close, Separated (:266-277)
+        const double* p = x + (size_t)point * dim;
+        double tot[2];
+        for (int k = 0; k < 2; ++k) {
+            double (*hst)[33] = k ? bkg : sig;
+            double part[3];
+            for (int h = 0; h < 3; ++h) {
+                double t = 0.0;
+                for (int b = 0; b < 50; ++b) t = __dadd_rn(t, hst[h * 50 + b][lane]);
+                part[h] = t;
+            }
+            double t = part[2];
+            t = __dadd_rn(t, part[0]);
+            t = __dadd_rn(t, part[1]);
+            tot[k] = __ddiv_rn(p[k], t);                                 // :269-270, :276-277
+        }
+        norm[0][lane] = tot[0];
+        norm[1][lane] = tot[1];
+    }
+    __syncthreads();
+    for (int hb = warp; hb < 150; hb += kFinishWarps) {
+        double v = 0.0;
+        if (live) {
+            // TH1::Add on the reset histogram: (0 + sW s) + bW b              :280-287
+            double mc = __dadd_rn(0.0, __dmul_rn(norm[0][lane], sig[hb][lane]));
+            mc = __dadd_rn(mc, __dmul_rn(norm[1][lane], bkg[hb][lane]));
+            if (histOut) histOut[(size_t)point * 150 + hb] = mc;
+            const double d = data150[hb];
+            if (mc < 0.001) mc = 0.001;                                  // :66
+            v = __dsub_rn(d, mc);
+            if (d > 0.0) v = __dadd_rn(v, __dmul_rn(d, log(__ddiv_rn(mc, d))));
+        }
+        sig[hb][lane] = v;
+    }
+    __syncthreads();
+    if (warp == 0 && live && llhOut) {
+        const double* p = x + (size_t)point * dim;
+        double L = 0.0;
+        for (int hb = 0; hb < 150; ++hb) L = __dadd_rn(L, sig[hb][lane]);
+        if (p[0] < 0.0) L = __dsub_rn(L, __dadd_rn(10.0, fabs(L)));       // :95-96
+        if (p[1] < 0.0) L = __dsub_rn(L, __dadd_rn(10.0, fabs(L)));       // :99-100
+        double v = __ddiv_rn(p[6], 5.0);                                   // :104-105
+        L = __dsub_rn(L, __dmul_rn(__dmul_rn(0.5, v), v));
+        v = __ddiv_rn(p[7], 1.0);                                          // :109-110
+        L = __dsub_rn(L, __dmul_rn(__dmul_rn(0.5, v), v));
+        v = __ddiv_rn(p[8], 1.0);                                          // :114-115
+        L = __dsub_rn(L, __dmul_rn(__dmul_rn(0.5, v), v));
+        llhOut[point] = L;
     }
 }
 

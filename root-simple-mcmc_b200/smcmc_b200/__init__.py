@@ -6,10 +6,10 @@ built library, or creating one without a GPU, fails loudly: there is no CPU
 fallback.
 """
 from .binding import (Engine, EVENT_DTYPE, LLH_ASYM, LLH_DUMMY, LLH_FAKE,
-                      LLH_HARD, LLH_HORRIFIC, LLH_UNBINNED, LLH_UNIT_GAUSS, SmcmcError,
+                      LLH_FAKE2, LLH_HARD, LLH_HORRIFIC, LLH_UNBINNED, LLH_UNIT_GAUSS, SmcmcError,
                       build_library, library_path, load_library)
 from . import shard, synth
 
 __all__ = ["Engine", "EVENT_DTYPE", "SmcmcError", "build_library",
            "library_path", "load_library", "shard", "synth", "LLH_UNIT_GAUSS",
-           "LLH_DUMMY", "LLH_HORRIFIC", "LLH_ASYM", "LLH_FAKE", "LLH_UNBINNED", "LLH_HARD"]
+           "LLH_DUMMY", "LLH_HORRIFIC", "LLH_ASYM", "LLH_FAKE", "LLH_UNBINNED", "LLH_HARD", "LLH_FAKE2"]

@@ -1,13 +1,19 @@
 // The reference's documentation example (reference TSimpleMCMC.H:122-156),
 // written against include/TSimpleMCMC.H.  Prints per-step records that
 // tests/test_gpu_cpp_facade.py compares with the oracle.
-//   argv[1] = "unit" | "fake" ; argv[2] = chains ; argv[3] = steps
+//   argv[1] = "unit" | "fake" | "fake2" ; argv[2] = chains ; argv[3] = steps
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
 #include "TSimpleMCMC.H"
 #include "smcmc_likelihoods.H"
+
+// Starting point: the origin, or the true event counts for example2
+// (example2/FakeMCMC.C starts the chain at MCTrueValues).
+template <class L>
+static void StartingPoint(const L&, sMCMC::Vector&) {}
+static void StartingPoint(const FakeLikelihood2& like, sMCMC::Vector& p) { p = like.MCTrueValues; }
 
 template <class L>
 static int Run(int chains, int steps, bool hints) {
@@ -24,6 +30,7 @@ static int Run(int chains, int steps, bool hints) {
         mcmc.GetProposeStep().SetCorrelation(3, 4, 0.3);
     }
     sMCMC::Vector point(like.GetDim());
+    StartingPoint(like, point);
     if (!mcmc.Start(point, false)) { std::printf("start failed\n"); return 2; }
     std::printf("start llh %.17g direct %.17g\n", mcmc.GetAcceptedLogLikelihood(), like(point));
     int accepted = 0;
@@ -56,5 +63,6 @@ int main(int argc, char** argv) {
     int chains = argc > 2 ? std::atoi(argv[2]) : 1;
     int steps = argc > 3 ? std::atoi(argv[3]) : 100;
     if (!std::strcmp(kind, "fake")) return Run<FakeLikelihood>(chains, steps, false);
+    if (!std::strcmp(kind, "fake2")) return Run<FakeLikelihood2>(chains, steps, false);
     return Run<TUnitGaussLogLikelihood>(chains, steps, true);
 }

@@ -83,6 +83,64 @@ def make_fake():
     print("fake_likelihood.npz: %d events, %d points" % (len(events), len(points)))
 
 
+def make_fake2():
+    """example2/FakeLikelihood.H through the reference build: the parameter
+    excursions of example2/TestLikelihood.C around the true event counts, random
+    points (negative event counts and empty histograms included), and a chain
+    with the example2/FakeMCMC.C schedule in miniature."""
+    events, data = synth.fake2_inputs(150, 150, 10, seed=29)     # ~7 000 events
+    extra = np.zeros(3, cc.EVENT_DTYPE)                          # data-typed records: background histograms, weight 1
+    extra["Mass"] = [120.0, 250.0, 40.0]
+    extra["Type"] = [-1, -2, -1]
+    extra["Separation"] = [30.0, 150.0, 80.0]
+    extra["MuDk"] = [0, 1, 0]
+    extra["TrueMass"] = [135.0, 200.0, 135.0]
+    extra["TrueMassSigma"] = [40.5, 60.0, 40.5]
+    events_irregular = np.concatenate([events, extra])
+    nominal = np.zeros(9)
+    nominal[0], nominal[1] = 150.0, 150.0
+    pts = [nominal.copy()]
+    for i, d in enumerate([15.0, 15.0, 1.0, 1.0, 5.0, 5.0, 5.0, 2.0, 2.0]):
+        for sgn in (+1.0, -1.0):
+            q = nominal.copy()
+            q[i] += sgn * d
+            pts.append(q)
+    rng = np.random.default_rng(31)
+    rnd = rng.normal(0, 3, (14, 9))
+    rnd[:, 0] = rng.uniform(-100, 900, 14)
+    rnd[:, 1] = rng.uniform(-100, 900, 14)
+    far = rng.normal(0, 40, (3, 9))
+    far[0, 2] = 100.0                      # every event cut: empty histograms, x/0 normalisation
+    points = np.concatenate([np.array(pts), rnd, far])
+    out = {"events": events, "events_irregular": events_irregular, "data": data, "points": points}
+    for tag, ev in (("", events), ("_irregular", events_irregular)):
+        c = cc.CpuChain("ref", cc.LLH_FAKE2, 9, 1, 0)
+        c.set_fake(ev, data, 1.0)
+        out["llh" + tag] = np.array([c.llh(q) for q in points])
+        out["hist" + tag] = np.array([c.fake_hist(q) for q in points])
+    for chain in (0, 5):
+        x0 = nominal + np.random.default_rng(200 + chain).uniform(-1, 1, 9)
+        c = cc.CpuChain("ref", cc.LLH_FAKE2, 9, 777, chain)
+        c.set_fake(events, data, 1.0)
+        c.set_gaussian(0, 15.0)            # the event counts move on their own scale
+        c.set_gaussian(1, 15.0)
+        c.start(x0)
+        parts = [c.step(80)]
+        c.reset_proposal()
+        parts.append(c.step(80))
+        c.update_proposal()
+        parts.append(c.step(140))
+        for k in ("accepted", "llh_accepted", "llh_proposed", "x", "sigma"):
+            out["chain%d_%s" % (chain, k)] = np.concatenate([q[k] for q in parts])
+        out["chain%d_x0" % chain] = x0
+        st = c.state()
+        out["chain%d_cov" % chain] = st["cov"]
+        out["chain%d_decomp" % chain] = st["decomp"]
+    np.savez_compressed(os.path.join(HERE, "fake2_likelihood.npz"), **out)
+    print("fake2_likelihood.npz: %d events, %d points, accepted %s" % (
+        len(events), len(points), [int(out["chain%d_accepted" % c].sum()) for c in (0, 5)]))
+
+
 def run_chain(kind, dim, seed, chain, nsteps, configure=None, x0=None):
     c = cc.CpuChain("ref", kind, dim, seed, chain)
     if configure:
@@ -192,9 +250,11 @@ def make_hmc():
 
 if __name__ == "__main__":
     cc.build()
-    which = sys.argv[1:] or ["fake", "chains", "hmc"]
+    which = sys.argv[1:] or ["fake", "fake2", "chains", "hmc"]
     if "fake" in which:
         make_fake()
+    if "fake2" in which:
+        make_fake2()
     if "chains" in which:
         make_chains()
     if "hmc" in which:

@@ -119,3 +119,15 @@ def test_fake_likelihood_ensemble_through_the_cpp_api(program):
     assert m and m.group(1) == m.group(2) == str(8 * 41)
     s = re.search(r"start llh (\S+) direct (\S+)", r.stdout)
     assert s and s.group(1) == s.group(2) and np.isfinite(float(s.group(1)))
+
+
+@pytest.mark.gpu
+def test_example2_likelihood_ensemble_through_the_cpp_api(program):
+    """example2's FakeLikelihood (include/smcmc_likelihoods.H::FakeLikelihood2) started at the
+    true event counts, 8 chains."""
+    r = subprocess.run([program, "fake2", "8", "40"], capture_output=True, text=True, check=True)
+    m = re.search(r"entries (\d+) expected (\d+) accepted (\d+) calls (\d+)", r.stdout)
+    assert m and m.group(1) == m.group(2) == str(8 * 41)
+    s = re.search(r"start llh (\S+) direct (\S+)", r.stdout)
+    assert s and s.group(1) == s.group(2) and np.isfinite(float(s.group(1)))
+    assert float(s.group(1)) > -2000.0          # near the truth the fit is good

@@ -245,3 +245,73 @@ def test_unbinned_port_matches_its_definition(checkers):
     b.set_fake(events[900:], np.zeros(150), 1.0)
     p = rng.uniform(-1, 1, 9)
     assert abs((a.llh(p) + b.llh(p)) / c.llh(p) - 1.0) < 1e-13
+
+
+# ---------------------------------------------------------------------------
+# example2/FakeLikelihood.H
+# ---------------------------------------------------------------------------
+def _fake2_schedule(c, g, chain):
+    c.set_fake(g["events"], g["data"], 1.0)
+    c.set_gaussian(0, 15.0)
+    c.set_gaussian(1, 15.0)
+    c.start(g["chain%d_x0" % chain])
+    parts = [c.step(80)]
+    c.reset_proposal()
+    parts.append(c.step(80))
+    c.update_proposal()
+    parts.append(c.step(140))
+    return parts
+
+
+@pytest.mark.parametrize("which", ["orc", "ref"])
+def test_fake2_likelihood_matches_golden(checkers, have_ref, which):
+    """Signal / background histograms renormalised by their integrals and the
+    penalty terms (example2/FakeLikelihood.H:58-118, 222-289): bit for bit."""
+    if which == "ref" and not have_ref:
+        pytest.skip("reference-backed checker not built here")
+    g = golden("fake2_likelihood.npz")
+    for tag in ("", "_irregular"):
+        c = checkers.CpuChain(which, checkers.LLH_FAKE2, 9, 1, 0)
+        c.set_fake(g["events" + tag], g["data"], 1.0)
+        for p, llh, hist in zip(g["points"], g["llh" + tag], g["hist" + tag]):
+            assert c.llh(p) == llh
+            assert np.array_equal(c.fake_hist(p), hist)
+
+
+@pytest.mark.parametrize("which", ["orc", "ref"])
+def test_fake2_schedule_matches_golden(checkers, have_ref, which):
+    if which == "ref" and not have_ref:
+        pytest.skip("reference-backed checker not built here")
+    g = golden("fake2_likelihood.npz")
+    for chain in (0, 5):
+        c = checkers.CpuChain(which, checkers.LLH_FAKE2, 9, 777, chain)
+        parts = _fake2_schedule(c, g, chain)
+        for k in ("accepted", "llh_accepted", "llh_proposed", "x", "sigma"):
+            got = np.concatenate([p[k] for p in parts])
+            assert np.array_equal(got, g["chain%d_%s" % (chain, k)]), k
+        st = c.state()
+        assert np.array_equal(st["cov"], g["chain%d_cov" % chain])
+        assert np.array_equal(st["decomp"], g["chain%d_decomp" % chain])
+
+
+def test_fake2_port_equals_reference_on_fresh_inputs(checkers, have_ref):
+    """New events and points, including negative event counts (the penalty
+    branches) and a point where every event is cut (x / 0 normalisation)."""
+    if not have_ref:
+        pytest.skip("reference-backed checker not built here")
+    from smcmc_b200 import synth
+    events, data = synth.fake2_inputs(120, 90, 10, seed=77)
+    a = checkers.CpuChain("orc", checkers.LLH_FAKE2, 9, 1, 0)
+    b = checkers.CpuChain("ref", checkers.LLH_FAKE2, 9, 1, 0)
+    a.set_fake(events, data, 1.0)
+    b.set_fake(events, data, 1.0)
+    rng = np.random.default_rng(5)
+    pts = rng.normal(0, 2, (30, 9))
+    pts[:, 0] = rng.uniform(-60, 400, 30)
+    pts[:, 1] = rng.uniform(-60, 400, 30)
+    pts[0, 2] = 2000.0      # exp overflows: every mass is inf, every event cut
+    for p in pts:
+        la, lb = a.llh(p), b.llh(p)
+        assert la == lb or (np.isnan(la) and np.isnan(lb))
+        assert np.array_equal(a.fake_hist(p), b.fake_hist(p), equal_nan=True)
+    assert np.isnan(a.llh(pts[0]))

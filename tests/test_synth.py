@@ -40,3 +40,32 @@ def test_against_reference_generators(checkers, have_ref):
             assert abs(a.std() - b.std()) < 0.05 * scale + 1e-12, f
     assert data_ref.sum() == 6000
     assert 0.03 < expo_ref < 0.3
+
+
+def test_example2_generators_against_reference(checkers, have_ref):
+    """example2/Simulated.H:17-63 and example2/FakeData.H:32-120."""
+    if not have_ref:
+        pytest.skip("reference-backed checker not built here")
+    from smcmc_b200 import synth
+    ev_ref, data_ref = checkers.ref2_generate(13, 2000, 2000, 10.0)
+    ev, data = synth.fake2_inputs(2000, 2000, 10.0, seed=8)
+    ns_ref, ns = int((ev_ref["Type"] == 0).sum()), int((ev["Type"] == 0).sum())
+    assert ns_ref == ns == 20000
+    # background events are drawn until 40000 of them lie below 500
+    for sample in (ev_ref, ev):
+        b = sample[sample["Type"] == 1]
+        assert int((b["Mass"] < 500.0).sum()) == 40000
+        assert np.all(sample["Type"][:20000] == 0) and np.all(sample["Type"][20000:] == 1)
+    assert abs(len(ev_ref) - len(ev)) < 0.03 * len(ev)
+    for typ in (0, 1):
+        a, b = ev_ref[ev_ref["Type"] == typ], ev[ev["Type"] == typ]
+        for f in ("Mass", "Separation", "TrueMass", "TrueMassSigma"):
+            x, y = a[f].astype(float), b[f].astype(float)
+            scale = max(abs(x.mean()), x.std(), 1e-9)
+            assert abs(x.mean() - y.mean()) < 0.03 * scale, (typ, f)
+            assert abs(x.std() - y.std()) < 0.05 * scale + 1e-12, (typ, f)
+        want = 0.05 if typ == 0 else 0.5                  # Bernoulli tag probabilities (:48, :60)
+        assert abs(a["MuDk"].mean() - want) < 0.012 and abs(b["MuDk"].mean() - want) < 0.012
+    assert data_ref.sum() == data.sum() == 4000
+    for h in range(3):       # the split over Close / Separated / DecayTag
+        assert abs(data_ref[h * 50:(h + 1) * 50].sum() - data[h * 50:(h + 1) * 50].sum()) < 200
