@@ -379,6 +379,33 @@ int smcmc_measure_fp64_peak(int device, double* tflops);
  * every SM).  The roofline denominator of the event-pair kernel, which needs two
  * exponentials per (chain, event) pair. */
 int smcmc_measure_sfu_peak(int device, double* gops);
+/* ---- ensemble diagnostics ------------------------------
+ * The reference derives these offline from the output TTree, one chain at a
+ * time: MakeCovariance.C:63-89 (mean and covariance of the accepted points),
+ * MakeAutocorrelation.C:96-148 (autocorrelation on a subset of lags).  Here the
+ * sums are accumulated on the device for every chain after every smcmc_step,
+ * so the points of a large ensemble never have to be written out.  R-hat is
+ * Gelman-Rubin's potential scale reduction across the chains of the engine. */
+typedef struct smcmc_diag_result {
+    int64_t* samples;         /* [1] chains x steps accumulated                                  */
+    int64_t* steps;           /* [1] steps accumulated                                           */
+    double* mean;             /* [n]   sum x / N                         MakeCovariance.C:76     */
+    double* covariance;       /* [n*n] sum x_i x_j / N - mean_i mean_j   MakeCovariance.C:79-83  */
+    double* rhat;             /* [n]   sqrt(((N-1)/N W + B/N) / W) over the chains               */
+    int32_t* lags;            /* [nlags] the sampled lags 1,2,3,4,6,8,12,... <= max_lag          */
+    double* autocorrelation;  /* [nlags*n] (<x(t) x(t-lag)> - mean^2) / var, lag-major
+                                                                     MakeAutocorrelation.C:131-136 */
+    double* tau;              /* [n] integrated autocorrelation time 1 + 2 sum rho(k)             */
+    double* ess;              /* [n] samples / tau                                                */
+} smcmc_diag_result;          /* any pointer may be NULL                                          */
+/* Start accumulating (MH engines, smcmc_step / smcmc_step_trace).  max_lag = 0:
+ * no autocorrelation; otherwise a ring buffer of max_lag points per chain is kept
+ * on the device (max_lag x chains x dim doubles). */
+int smcmc_diag_enable(smcmc_engine* e, int max_lag);
+int smcmc_diag_reset(smcmc_engine* e);
+int smcmc_diag_lag_count(smcmc_engine* e, int32_t* nlags);
+int smcmc_diag_get(smcmc_engine* e, const smcmc_diag_result* out);
+
 /* Device self-test of the shared-divisor division of the staged covariance
  * update (csrc/proposal_staged.cuh, replacing the per-entry division of
  * TSimpleMCMC.H:1811): `count` random numerators and divisors are divided both

@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "contraction.cuh"
+#include "diagnostics.cuh"
 #include "fake_likelihood.cuh"
 #include "hmc.cuh"
 #include "nccl_dyn.h"
@@ -129,6 +130,58 @@ struct smcmc_engine {
     DeviceBuffer<double> unbPartial;
     int64_t unbClassCount[2] = {0, 0};
     int64_t unbEventCount = -1;
+
+    // ---- ensemble diagnostics (diagnostics.cuh) ------------------------------------
+    bool diagOn = false;
+    int diagDepth = 0;
+    long long diagFills = 0;
+    std::vector<int> diagLags;
+    DeviceBuffer<double> diagPooled, diagS1, diagS2, diagRing, diagLagProd, diagLagCount;
+    DeviceBuffer<int> diagLagsDev;
+
+    DiagArrays diagArrays() {
+        DiagArrays d;
+        d.pooled = diagPooled.get();
+        d.s1 = diagS1.get();
+        d.s2 = diagS2.get();
+        d.ring = diagRing.get();
+        d.lagProd = diagLagProd.get();
+        d.lagCount = diagLagCount.get();
+        d.lags = diagLagsDev.get();
+        d.nlags = (int)diagLags.size();
+        d.depth = diagDepth;
+        return d;
+    }
+    void diagReset() {
+        const size_t En = (size_t)E() * n();
+        CUDA_CHECK(cudaMemsetAsync(diagPooled.get(), 0, poolStatCount() * sizeof(double), stream));
+        CUDA_CHECK(cudaMemsetAsync(diagS1.get(), 0, En * sizeof(double), stream));
+        CUDA_CHECK(cudaMemsetAsync(diagS2.get(), 0, En * sizeof(double), stream));
+        if (!diagLags.empty()) {
+            CUDA_CHECK(cudaMemsetAsync(diagLagProd.get(), 0, diagLags.size() * n() * sizeof(double), stream));
+            CUDA_CHECK(cudaMemsetAsync(diagLagCount.get(), 0, diagLags.size() * sizeof(double), stream));
+        }
+        diagFills = 0;
+    }
+    // the accepted points of this step join the sums (after kAccept)
+    void diagAccumulate() {
+        const size_t En = (size_t)E() * n();
+        DiagArrays d = diagArrays();
+        const int slot = diagDepth > 0 ? (int)(diagFills % diagDepth) : 0;
+        ++diagFills;
+        if (d.nlags > 0) {
+            const int blocksX = (int)std::min<size_t>((En + 255) / 256, (size_t)smCount * 4);
+            dim3 grid(blocksX, d.nlags);
+            kDiagLags<<<grid, 256, (n() + 1) * sizeof(double), stream>>>(xAcc.get(), E(), n(), d, slot, diagFills);
+            launched();
+        }
+        kDiagChains<<<ceilDiv((long long)En, 256), 256, 0, stream>>>(xAcc.get(), sc.get(), E(), n(), d, slot);
+        launched();
+        const int poolBlocks = std::min(smCount * 2, ceilDiv(E(), 32));
+        kPoolAccumulate<<<poolBlocks, 256, 32 * n() * sizeof(double), stream>>>(xAcc.get(), sc.get(), E(), n(),
+                                                                                diagPooled.get());
+        launched();
+    }
 
     // ---- pooled adaptation (pooled.cuh) -----------------------------------------
     int pooledEvery = 0;                            // 0 = per-chain adaptation (the reference)
@@ -551,6 +604,7 @@ struct smcmc_engine {
                                                             stepIndex, metropolis, tr, traceStep);
         launched();
         ++stepIndex;
+        if (diagOn) diagAccumulate();
         if (pooledEvery > 0) {
             const int poolBlocks = std::min(smCount * 2, ceilDiv(E(), 32));
             kPoolAccumulate<<<poolBlocks, 256, 32 * n() * sizeof(double), stream>>>(xAcc.get(), sc.get(), E(), n(),
@@ -1469,6 +1523,143 @@ int64_t smcmc_launch_count(const smcmc_engine* e) { return e ? e->launches : 0; 
 
 int smcmc_enable_kernel_timing(smcmc_engine* e, int on) {
     return guarded(e, [&]() { e->timing = on != 0; });
+}
+
+int smcmc_diag_enable(smcmc_engine* e, int max_lag) {
+    return guarded(e, [&]() {
+        if (max_lag < 0) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "max_lag must not be negative");
+        const size_t En = (size_t)e->E() * e->n();
+        if ((size_t)max_lag * En * sizeof(double) > ((size_t)48 << 30))
+            throw Error(SMCMC_ERR_INVALID_ARGUMENT, "the ring buffer of max_lag points per chain would exceed 48 GiB");
+        // lags 1, 2, 3, 4, 6, 8, 12, 16, ... up to max_lag (MakeAutocorrelation.C:99-101 also samples the lags)
+        e->diagLags.clear();
+        for (int lag = 1; lag <= max_lag;) {
+            e->diagLags.push_back(lag);
+            if (lag < 4) ++lag;
+            else if ((lag & (lag - 1)) == 0) lag += lag / 2;
+            else lag = (lag / 3) * 4;
+        }
+        e->diagDepth = max_lag;
+        if ((size_t)32 * e->n() * sizeof(double) > 48 * 1024)
+            CUDA_CHECK(cudaFuncSetAttribute(kPoolAccumulate, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)((size_t)32 * e->n() * sizeof(double))));
+        e->diagPooled.reserve(e->poolStatCount());
+        e->diagS1.reserve(En);
+        e->diagS2.reserve(En);
+        if (max_lag > 0) {
+            e->diagRing.reserve((size_t)max_lag * En);
+            e->diagLagProd.reserve(e->diagLags.size() * e->n());
+            e->diagLagCount.reserve(e->diagLags.size());
+            e->diagLagsDev.reserve(e->diagLags.size());
+            CUDA_CHECK(cudaMemcpy(e->diagLagsDev.get(), e->diagLags.data(), e->diagLags.size() * sizeof(int),
+                                  cudaMemcpyHostToDevice));
+        }
+        e->diagReset();
+        e->diagOn = true;
+    });
+}
+
+int smcmc_diag_reset(smcmc_engine* e) {
+    return guarded(e, [&]() {
+        if (!e->diagOn) throw Error(SMCMC_ERR_LOGIC, "diagnostics are not enabled (smcmc_diag_enable)");
+        e->diagReset();
+    });
+}
+
+int smcmc_diag_lag_count(smcmc_engine* e, int32_t* nlags) {
+    return guarded(e, [&]() {
+        if (!nlags) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null output");
+        *nlags = (int32_t)e->diagLags.size();
+    });
+}
+
+int smcmc_diag_get(smcmc_engine* e, const smcmc_diag_result* out) {
+    return guarded(e, [&]() {
+        if (!e->diagOn) throw Error(SMCMC_ERR_LOGIC, "diagnostics are not enabled (smcmc_diag_enable)");
+        if (!out) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null result");
+        const size_t E = e->E(), n = e->n(), nl = e->diagLags.size();
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        std::vector<double> pooled(e->poolStatCount()), s1(E * n), s2(E * n), lp(nl * n), lc(nl);
+        CUDA_CHECK(cudaMemcpy(pooled.data(), e->diagPooled.get(), pooled.size() * 8, cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(s1.data(), e->diagS1.get(), s1.size() * 8, cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(s2.data(), e->diagS2.get(), s2.size() * 8, cudaMemcpyDeviceToHost));
+        if (nl) {
+            CUDA_CHECK(cudaMemcpy(lp.data(), e->diagLagProd.get(), lp.size() * 8, cudaMemcpyDeviceToHost));
+            CUDA_CHECK(cudaMemcpy(lc.data(), e->diagLagCount.get(), lc.size() * 8, cudaMemcpyDeviceToHost));
+        }
+        const double count = pooled[0];
+        if (out->samples) *out->samples = (int64_t)count;
+        if (out->steps) *out->steps = (int64_t)e->diagFills;
+        std::vector<double> mean(n, 0.0), var(n, 0.0);
+        for (size_t i = 0; i < n; ++i) {                                   // MakeCovariance.C:76-83
+            mean[i] = pooled[1 + i] / count;
+            var[i] = pooled[1 + n + i * (i + 1) / 2 + i] / count - mean[i] * mean[i];
+        }
+        if (out->mean) std::copy(mean.begin(), mean.end(), out->mean);
+        if (out->covariance) {
+            for (size_t i = 0; i < n; ++i)
+                for (size_t j = 0; j < n; ++j) {
+                    const size_t hi = std::max(i, j), lo = std::min(i, j);
+                    out->covariance[i * n + j] = pooled[1 + n + hi * (hi + 1) / 2 + lo] / count - mean[i] * mean[j];
+                }
+        }
+        if (out->rhat) {
+            // Gelman-Rubin: W = mean within-chain variance, B/N = variance of the chain means
+            const double N = (double)e->diagFills;
+            for (size_t i = 0; i < n; ++i) {
+                double W = 0.0, m1 = 0.0, m2 = 0.0;
+                size_t M = 0;
+                for (size_t c = 0; c < E; ++c) {
+                    const double a = s1[c * n + i], b = s2[c * n + i];
+                    if (a == 0.0 && b == 0.0) continue;                    // chain not running
+                    const double cm = a / N;
+                    W += (b - N * cm * cm) / (N - 1.0);
+                    m1 += cm;
+                    m2 += cm * cm;
+                    ++M;
+                }
+                double r = std::numeric_limits<double>::quiet_NaN();
+                if (M > 1 && N > 1.0) {
+                    W /= (double)M;
+                    const double grand = m1 / (double)M;
+                    const double BoverN = (m2 - (double)M * grand * grand) / ((double)M - 1.0);
+                    r = std::sqrt(((N - 1.0) / N * W + BoverN) / W);
+                }
+                out->rhat[i] = r;
+            }
+        }
+        if (out->lags) std::copy(e->diagLags.begin(), e->diagLags.end(), out->lags);
+        std::vector<double> rho(nl * n, 0.0);
+        for (size_t l = 0; l < nl; ++l)
+            for (size_t i = 0; i < n; ++i)                                 // MakeAutocorrelation.C:131-136
+                rho[l * n + i] = (lp[l * n + i] / lc[l] - mean[i] * mean[i]) / var[i];
+        if (out->autocorrelation) std::copy(rho.begin(), rho.end(), out->autocorrelation);
+        if (out->tau || out->ess) {
+            // integrated autocorrelation time tau = 1 + 2 sum_{k>=1} rho(k): rho is taken
+            // piecewise linear between the sampled lags (rho(0) = 1) and the sum stops at
+            // the first zero crossing
+            for (size_t i = 0; i < n; ++i) {
+                double S = 0.0, prevLag = 0.0, prevRho = 1.0;
+                for (size_t l = 0; l < nl; ++l) {
+                    if (!(lc[l] > 0.0)) break;
+                    const double r = rho[l * n + i], lag = (double)e->diagLags[l];
+                    const double w = lag - prevLag, m = (r - prevRho) / w;
+                    if (r > 0.0) {
+                        S += w * prevRho + m * w * (w + 1.0) / 2.0;
+                        prevLag = lag;
+                        prevRho = r;
+                    } else {
+                        const double k = std::floor(prevRho / (-m));
+                        S += k * prevRho + m * k * (k + 1.0) / 2.0;
+                        break;
+                    }
+                }
+                const double tau = 1.0 + 2.0 * S;
+                if (out->tau) out->tau[i] = tau;
+                if (out->ess) out->ess[i] = count / tau;
+            }
+        }
+    });
 }
 
 int smcmc_pair_kernel_stats(smcmc_engine* e, double* totalMs, int64_t* launches, int reset) {

@@ -103,6 +103,12 @@ def build_library(verbose=False):
                    stdout=None if verbose else subprocess.DEVNULL)
 
 
+class _DiagResult(ctypes.Structure):
+    """smcmc_diag_result"""
+    _fields_ = [(name, ctypes.c_void_p) for name in
+                ("samples", "steps", "mean", "covariance", "rhat", "lags", "autocorrelation", "tau", "ess")]
+
+
 _LIB = None
 
 
@@ -162,6 +168,10 @@ def load_library():
         "smcmc_measure_fp64_peak": (ci, [ci, ctypes.POINTER(cd)]),
         "smcmc_measure_sfu_peak": (ci, [ci, ctypes.POINTER(cd)]),
         "smcmc_selftest_division": (ci, [ci, ctypes.c_int64, ctypes.c_uint64, ctypes.POINTER(ctypes.c_int64)]),
+        "smcmc_diag_enable": (ci, [vp, ci]),
+        "smcmc_diag_reset": (ci, [vp]),
+        "smcmc_diag_lag_count": (ci, [vp, ctypes.POINTER(ctypes.c_int32)]),
+        "smcmc_diag_get": (ci, [vp, ctypes.POINTER(_DiagResult)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -185,6 +195,7 @@ EXPORTED_SYMBOLS = [
     "smcmc_hmc_step_trace", "smcmc_hmc_get",
     "smcmc_pair_kernel_stats", "smcmc_enable_kernel_timing",
     "smcmc_measure_fp64_peak", "smcmc_measure_sfu_peak", "smcmc_selftest_division",
+    "smcmc_diag_enable", "smcmc_diag_reset", "smcmc_diag_lag_count", "smcmc_diag_get",
 ]
 
 
@@ -456,6 +467,31 @@ class Engine:
         return {k: s[:, i] for i, k in enumerate(HMC_SCALARS)}
 
     # -- instrumentation -----------------------------------------------------------
+    # -- ensemble diagnostics --------------------------------------------------------
+    def diag_enable(self, max_lag=0):
+        """Accumulate mean / covariance / R-hat / autocorrelation of the accepted points on
+        the device after every step (MakeCovariance.C, MakeAutocorrelation.C)."""
+        self._check(self.lib.smcmc_diag_enable(self.h, max_lag))
+
+    def diag_reset(self):
+        self._check(self.lib.smcmc_diag_reset(self.h))
+
+    def diag_get(self):
+        n = self.dim
+        nl = ctypes.c_int32()
+        self._check(self.lib.smcmc_diag_lag_count(self.h, ctypes.byref(nl)))
+        nl = nl.value
+        out = {"samples": np.zeros(1, np.int64), "steps": np.zeros(1, np.int64), "mean": np.zeros(n),
+               "covariance": np.zeros((n, n)), "rhat": np.zeros(n), "lags": np.zeros(nl, np.int32),
+               "autocorrelation": np.zeros((nl, n)), "tau": np.zeros(n), "ess": np.zeros(n)}
+        res = _DiagResult()
+        for k, v in out.items():
+            setattr(res, k, v.ctypes.data)
+        self._check(self.lib.smcmc_diag_get(self.h, ctypes.byref(res)))
+        out["samples"] = int(out["samples"][0])
+        out["steps"] = int(out["steps"][0])
+        return out
+
     def launch_count(self):
         return int(self.lib.smcmc_launch_count(self.h))
 

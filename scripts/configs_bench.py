@@ -138,6 +138,43 @@ def c4():
             eng.close()
 
 
+def ex2():
+    """example2's likelihood on the shape of C2 (4096 chains x 1M events),
+    next to the reference's own example2 code on one host core."""
+    from oracle import cpu_checkers as cc
+    E, steps = 4096, 20
+    signal = 333334
+    events = synth.make_mc_sample(signal, 1000000 - signal, seed=2)        # the C2 event set
+    data = synth.make_data_histograms(33334, 33334, seed=2, variant=2)
+    eng = smcmc_b200.Engine(smcmc_b200.LLH_FAKE2, 9, E, seed=3)
+    eng.set_fake_events(events)
+    eng.set_fake_data(data, 1.0)
+    x0 = np.zeros((E, 9))
+    for c in range(E):
+        x0[c] = np.random.default_rng([3, c]).uniform(-1.0, 1.0, 9)
+    x0[:, 0] += 33334.0
+    x0[:, 1] += 33334.0
+    eng.set_gaussian(0, 300.0)
+    eng.set_gaussian(1, 300.0)
+    eng.start(x0)
+    eng.step(3)
+    dt = timed(lambda: eng.step(steps), eng.sync)
+    rec = {"config": "example2 (8f rank 2)", "target": "example2/FakeLikelihood.H on the C2 shape", "chains": E,
+           "events": len(events), "ms_per_step": 1e3 * dt / steps, "chain_steps_per_s": E * steps / dt,
+           "pair_evals_per_s": E * steps * float(len(events)) / dt, "acceptance": float(eng.get("acceptance").mean())}
+    which = "ref" if cc.available("ref") else "orc"
+    c = cc.CpuChain(which, cc.LLH_FAKE2, 9, 3, 0)
+    c.set_fake(events, data, 1.0)
+    c.set_gaussian(0, 300.0)
+    c.set_gaussian(1, 300.0)
+    c.start(x0[0])
+    t = time.perf_counter()
+    c.step(6)
+    rec["cpu_steps_per_s_one_core"] = 6 / (time.perf_counter() - t)
+    rec["cpu_kind"] = "reference" if which == "ref" else "port"
+    emit(rec)
+
+
 def c5(args):
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", 0))
@@ -212,5 +249,7 @@ if __name__ == "__main__":
     for w in a.which:
         if w == "c5":
             c5(a)
+        elif w == "ex2":
+            ex2()
         else:
             {"c1": c1, "c3": c3, "c4": c4}[w]()
