@@ -101,6 +101,8 @@ typedef enum smcmc_prop_field {
     SMCMC_PROP_POOLED_EVERY = 13,        /* NEW (not in the reference): K > 0 pools the
                                             covariance adaptation over all chains and
                                             GPUs, exchanging statistics every K steps   */
+    SMCMC_PROP_KIND = 15,                /* which proposal functor the sampler is instantiated with
+                                            (smcmc_proposal_kind); before smcmc_start          */
     SMCMC_PROP_POOLED_TENSOR = 14        /* pooled mode: evaluate x' = x + (sigma z).U of all
                                             chains as one GEMM on the FP64 tensor cores;
                                             -1 automatic (dim >= 128, default), 0 off, 1 on */
@@ -140,8 +142,26 @@ typedef enum smcmc_field {
     SMCMC_F_POOLED_MEAN = 25,       /* double[dim]       pooled mode: ensemble mean        */
     SMCMC_F_POOLED_COVARIANCE = 26, /* double[dim*(dim+1)/2] pooled mode: packed covariance */
     SMCMC_F_POOLED_DECOMPOSITION = 27, /* double[dim*dim] pooled mode: the shared U         */
-    SMCMC_F_POOLED_COUNT = 28       /* double[1]         points behind the pooled estimate */
+    SMCMC_F_POOLED_COUNT = 28,      /* double[1]         points behind the pooled estimate */
+    /* TProposeVAATStep (SMCMC_PROPOSAL_VAAT); with it SMCMC_F_SIGMA and SMCMC_F_ACCEPTANCE are
+     * its GetSigma / GetAcceptance: the means over the dimensions (TProposeVAATStep.H:155-173) */
+    SMCMC_F_VAAT_SIGMA = 29,        /* double[chains*dim] fSigma            :299 */
+    SMCMC_F_VAAT_ACCEPTANCE = 30,   /* double[chains*dim] fAcceptance       :290 */
+    SMCMC_F_VAAT_ACCEPTANCE_TRIALS = 31, /* int32[chains*dim] fAcceptanceTrials :293 */
+    SMCMC_F_VAAT_LAST_INDEX = 32,   /* int32[chains]      fLastIndex        :275 */
+    SMCMC_F_VAAT_QUEUE = 33         /* int32[chains]      indices left in fNextIndex :272 */
 } smcmc_field;
+
+/* The proposal functor of the sampler (SMCMC_PROP_KIND). */
+typedef enum smcmc_proposal_kind {
+    SMCMC_PROPOSAL_ADAPTIVE = 0,    /* sMCMC::TProposeAdaptiveStep, TSimpleMCMC.H:640-1977 (default;
+                                       TProposeSimpleStep is this one with its adaptation frozen)   */
+    SMCMC_PROPOSAL_VAAT = 1         /* sMCMC::TProposeVAATStep, TProposeVAATStep.H:22-307: adaptive
+                                       variable-at-a-time.  Settings that exist for it: SetGaussian
+                                       (sigma itself), SetUniform, SetAcceptanceWindow (reset to 100
+                                       by the first Start, as in the reference), SetAcceptanceRigidity;
+                                       no save / restore (the reference's returns false)            */
+} smcmc_proposal_kind;
 
 /* Optional per-step trace of smcmc_step_trace(); any pointer may be NULL.
  * Step-major: entry (s, c) at [s*chains + c], points at [(s*chains+c)*dim]. */

@@ -77,6 +77,13 @@ typedef struct orc_event {
 
 #define ORC_DECLARE(P)                                                        \
     void* P##chain_create(int kind, int dim, uint64_t seed, uint32_t chain);  \
+    /* TSimpleMCMC<L, TProposeVAATStep> (TProposeVAATStep.H:22-307); settings:  \
+     * chain_set(ACCEPTANCE_WINDOW | ACCEPTANCE_RIGIDITY), set_gaussian (sigma  \
+     * itself, :121-133), set_uniform.  misc = trials, successes, last index,   \
+     * indices left in the queue. */                                            \
+    void* P##chain_create_vaat(int kind, int dim, uint64_t seed, uint32_t chain); \
+    int P##chain_get_vaat(void* h, double* sigma, double* acceptance,         \
+                          int32_t* acceptance_trials, int32_t* misc);         \
     void P##chain_destroy(void* h);                                           \
     int P##chain_set_fake(void* h, const orc_event* ev, long n,               \
                           const double* data150, double exposure);            \

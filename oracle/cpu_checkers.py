@@ -71,6 +71,8 @@ def load(which):
     vp, ci, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
     sig = {
         "chain_create": (vp, [ci, ci, ctypes.c_uint64, ctypes.c_uint32]),
+        "chain_create_vaat": (vp, [ci, ci, ctypes.c_uint64, ctypes.c_uint32]),
+        "chain_get_vaat": (ci, [vp, vp, vp, vp, vp]),
         "chain_destroy": (None, [vp]),
         "chain_set_fake": (ci, [vp, vp, ctypes.c_long, vp, cd]),
         "chain_set_error_matrix": (ci, [vp, vp, ci]),
@@ -129,11 +131,13 @@ def _ptr(a):
 class CpuChain:
     """One chain of one checker (``which`` = "ref" or "orc")."""
 
-    def __init__(self, which, kind, dim, seed, chain):
+    def __init__(self, which, kind, dim, seed, chain, vaat=False):
+        """vaat=True: TSimpleMCMC<L, TProposeVAATStep> (TProposeVAATStep.H)."""
         self.lib = load(which)
         self.p = which + "_"
         self.dim = dim
-        self.h = self._f("chain_create")(kind, dim, seed, chain)
+        self.vaat = vaat
+        self.h = self._f("chain_create_vaat" if vaat else "chain_create")(kind, dim, seed, chain)
         if not self.h:
             raise RuntimeError(self._f("last_error")().decode())
         self._keep = []
@@ -221,6 +225,16 @@ class CpuChain:
         out = dict(zip(STATE_FIELDS, s))
         out.update(accepted=acc, center=cen, cov=cov, decomp=dec)
         return out
+
+    def vaat_state(self):
+        """The proposal's own state: per-dimension step size, acceptance, trial
+        counts; trials, successes, last index, indices left in the queue."""
+        n = self.dim
+        sigma, acc = np.zeros(n), np.zeros(n)
+        trials, misc = np.zeros(n, np.int32), np.zeros(4, np.int32)
+        self._check(self._f("chain_get_vaat")(self.h, _ptr(sigma), _ptr(acc), _ptr(trials), _ptr(misc)))
+        return {"sigma": sigma, "acceptance": acc, "acceptance_trials": trials, "trials": int(misc[0]),
+                "successes": int(misc[1]), "last_index": int(misc[2]), "queue": int(misc[3])}
 
     def llh(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -21,6 +21,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include <TDecompChol.h>
@@ -41,6 +42,7 @@
 #define protected public
 #include "TSimpleMCMC.H"
 using namespace sMCMC;  // example/ predates the namespace
+#include "TProposeVAATStep.H"
 #include "TDummyLogLikelihood.H"
 #include "THorrificLogLikelihood.H"
 #include "TAsymLogLikelihood.H"
@@ -130,18 +132,33 @@ struct ChainBase {
     virtual void Restore(TTree* tree) = 0;
     virtual FakeLikelihood* Fake() { return 0; }
     virtual void* Fake2() { return 0; }
+    virtual TProposeVAATStep* Vaat() { return 0; }
     TTree tree;      // every chain writes to its own in-memory tree
 };
 
-template <class L>
+template <class L, class P = TProposeAdaptiveStep>
 struct Chain : public ChainBase {
-    TSimpleMCMC<L> mcmc;
+    static const bool kAdaptive = std::is_same<P, TProposeAdaptiveStep>::value;
+    TSimpleMCMC<L, P> mcmc;
     Chain(uint64_t seed, uint32_t chain, int d)
         : ChainBase(seed, chain, d), mcmc(&tree, false) {}
     void SaveStep() { mcmc.SaveStep(); }
-    void Restore(TTree* t) { mcmc.Restore(t); }
+    // TProposeVAATStep::RestoreState does not match the call in
+    // TSimpleMCMC::Restore (TProposeVAATStep.H:33 vs TSimpleMCMC.H:351): Restore
+    // can only be instantiated for the adaptive proposal.
+    void Restore(TTree* t) {
+        if constexpr (kAdaptive) mcmc.Restore(t);
+        else throw std::logic_error("Restore needs TProposeAdaptiveStep");
+    }
     bool StepSaved(int metropolis) { return mcmc.Step(true, metropolis); }
-    TProposeAdaptiveStep& Prop() { return mcmc.GetProposeStep(); }
+    TProposeAdaptiveStep& Prop() {
+        if constexpr (kAdaptive) return mcmc.GetProposeStep();
+        else throw std::logic_error("not a TProposeAdaptiveStep chain");
+    }
+    TProposeVAATStep* Vaat() {
+        if constexpr (kAdaptive) return 0;
+        else return &mcmc.GetProposeStep();
+    }
     bool Start(const Vector& x) { return mcmc.Start(x, false); }
     bool Step(int metropolis) { return mcmc.Step(false, metropolis); }
     double Llh(const Vector& x) { return mcmc.GetLogLikelihood()(x); }
@@ -157,6 +174,16 @@ struct Chain : public ChainBase {
 struct FakeChain : public Chain<FakeLikelihood> {
     FakeChain(uint64_t seed, uint32_t chain, int d)
         : Chain<FakeLikelihood>(seed, chain, d) {
+        FakeLikelihood& like = mcmc.GetLogLikelihood();
+        like.DataClose = like.DataSeparated = like.DataDecayTag = 0;
+        like.SimulatedClose = like.SimulatedSeparated = like.SimulatedDecayTag = 0;
+    }
+    FakeLikelihood* Fake() { return &mcmc.GetLogLikelihood(); }
+};
+
+struct FakeVaatChain : public Chain<FakeLikelihood, TProposeVAATStep> {
+    FakeVaatChain(uint64_t seed, uint32_t chain, int d)
+        : Chain<FakeLikelihood, TProposeVAATStep>(seed, chain, d) {
         FakeLikelihood& like = mcmc.GetLogLikelihood();
         like.DataClose = like.DataSeparated = like.DataDecayTag = 0;
         like.SimulatedClose = like.SimulatedSeparated = like.SimulatedDecayTag = 0;
@@ -231,6 +258,48 @@ void* ref_chain_create(int kind, int dim, uint64_t seed, uint32_t chain) {
     return c;
 }
 
+// TSimpleMCMC<L, TProposeVAATStep>, the pairing of SimpleVAAT.C:31.
+void* ref_chain_create_vaat(int kind, int dim, uint64_t seed, uint32_t chain) {
+    ChainBase* c = 0;
+    switch (kind) {
+    case ORC_LLH_UNIT_GAUSS:
+        c = new Chain<UnitGaussLikelihood, TProposeVAATStep>(seed, chain, dim);
+        break;
+    case ORC_LLH_HORRIFIC:
+        if (dim != 75) { gLastError = "reference THorrificLogLikelihood is 75-dim"; return 0; }
+        c = new Chain<THorrificLogLikelihood, TProposeVAATStep>(seed, chain, 75);
+        break;
+    case ORC_LLH_ASYM:
+        if (dim != 100) { gLastError = "reference TASymLogLikelihood is 100-dim"; return 0; }
+        c = new Chain<TASymLogLikelihood, TProposeVAATStep>(seed, chain, 100);
+        break;
+    case ORC_LLH_FAKE:
+        if (dim != 9) { gLastError = "FakeLikelihood is 9-dim"; return 0; }
+        c = new FakeVaatChain(seed, chain, dim);
+        break;
+    default:
+        gLastError = "likelihood kind not offered with TProposeVAATStep";
+        return 0;
+    }
+    c->Vaat()->SetDim(c->dim);
+    return c;
+}
+
+int ref_chain_get_vaat(void* h, double* sigma, double* acceptance, int32_t* acceptanceTrials, int32_t* misc) {
+    TProposeVAATStep* p = H(h)->Vaat();
+    if (!p) { gLastError = "not a TProposeVAATStep chain"; return -1; }
+    if (sigma) std::copy(p->fSigma.begin(), p->fSigma.end(), sigma);
+    if (acceptance) std::copy(p->fAcceptance.begin(), p->fAcceptance.end(), acceptance);
+    if (acceptanceTrials) std::copy(p->fAcceptanceTrials.begin(), p->fAcceptanceTrials.end(), acceptanceTrials);
+    if (misc) {
+        misc[0] = p->GetTrials();
+        misc[1] = p->GetSuccesses();
+        misc[2] = p->fLastIndex;
+        misc[3] = (int32_t)p->fNextIndex.size();
+    }
+    return 0;
+}
+
 void ref_chain_destroy(void* h) { delete H(h); }
 
 int ref_chain_set_fake(void* h, const orc_event* ev, long n,
@@ -266,6 +335,13 @@ int ref_chain_set_error_matrix(void*, const double*, int) {
 }
 
 int ref_chain_set(void* h, int field, double v) {
+    if (H(h)->Vaat() && field != ORC_SET_STEP_RMS_WINDOW) {
+        if (field == ORC_SET_ACCEPTANCE_WINDOW) H(h)->Vaat()->SetAcceptanceWindow(v);
+        else if (field == ORC_SET_ACCEPTANCE_RIGIDITY) H(h)->Vaat()->SetAcceptanceRigidity(v);
+        else { gLastError = "TProposeVAATStep has no such setting"; return -1; }
+        return 0;
+    }
+    if (H(h)->Vaat()) { H(h)->SetStepRMSWindow((int)v); return 0; }
     TProposeAdaptiveStep& p = H(h)->Prop();
     switch (field) {
     case ORC_SET_SIGMA: p.SetSigma(v); break;
@@ -287,11 +363,13 @@ int ref_chain_set(void* h, int field, double v) {
 }
 
 int ref_chain_set_gaussian(void* h, int d, double sigma) {
+    if (H(h)->Vaat()) { H(h)->Vaat()->SetGaussian(d, sigma); return 0; }
     H(h)->Prop().SetGaussian(d, sigma);
     return 0;
 }
 
 int ref_chain_set_uniform(void* h, int d, double lo, double hi) {
+    if (H(h)->Vaat()) { H(h)->Vaat()->SetUniform(d, lo, hi); return 0; }
     H(h)->Prop().SetUniform(d, lo, hi);
     return 0;
 }
@@ -322,7 +400,7 @@ int ref_chain_step(void* h, int nsteps, int metropolis, int32_t* accepted,
             if (accepted) accepted[s] = ok ? 1 : 0;
             if (llhAccepted) llhAccepted[s] = c->AcceptedLlh();
             if (llhProposed) llhProposed[s] = c->ProposedLlh();
-            if (sigma) sigma[s] = c->Prop().GetSigma();
+            if (sigma) sigma[s] = c->Vaat() ? c->Vaat()->GetSigma() : c->Prop().GetSigma();
             if (x) std::copy(c->Accepted().begin(), c->Accepted().end(),
                              x + (size_t)s * c->dim);
         }
@@ -373,6 +451,25 @@ int ref_chain_reset_proposal(void* h) {
 int ref_chain_get_state(void* h, double* s, double* accepted, double* center,
                         double* cov, double* decomp) {
     ChainBase* c = H(h);
+    if (c->Vaat()) {
+        // the sampler-level scalars; the proposal's own state comes from ref_chain_get_vaat
+        if (s) {
+            for (int k = 0; k < ORC_ST_COUNT; ++k) s[k] = 0.0;
+            s[ORC_ST_SIGMA] = c->Vaat()->GetSigma();
+            s[ORC_ST_ACCEPTANCE] = c->Vaat()->GetAcceptance();
+            s[ORC_ST_ACCEPTANCE_WINDOW] = c->Vaat()->GetAcceptanceWindow();
+            s[ORC_ST_ACCEPTANCE_RIGIDITY] = c->Vaat()->GetAcceptanceRigidity();
+            s[ORC_ST_TRIALS] = c->Vaat()->GetTrials();
+            s[ORC_ST_SUCCESSES] = c->Vaat()->GetSuccesses();
+            s[ORC_ST_STEP_RMS] = c->StepRMS();
+            s[ORC_ST_ACCEPTED_LLH] = c->AcceptedLlh();
+            s[ORC_ST_PROPOSED_LLH] = c->ProposedLlh();
+            s[ORC_ST_TOTAL_STEPS] = c->TotalSteps();
+            s[ORC_ST_LLH_CALLS] = c->LlhCalls();
+        }
+        if (accepted) std::copy(c->Accepted().begin(), c->Accepted().end(), accepted);
+        return 0;
+    }
     TProposeAdaptiveStep& p = c->Prop();
     const int n = c->dim;
     if (s) {

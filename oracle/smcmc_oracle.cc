@@ -711,11 +711,107 @@ struct Proposal {
 };
 
 // ---------------------------------------------------------------------------
+// TProposeVAATStep (TProposeVAATStep.H:22-307): adaptive variable-at-a-time
+// proposal.  Draws of a step, in the order the reference calls gRandom: when
+// the index queue is empty n uniforms for the shuffle (:186-189), then one draw
+// for the proposed coordinate (:60-78); TSimpleMCMC's accept uniform follows.
+// ---------------------------------------------------------------------------
+struct VaatProposal {
+    int n = 0;
+    uint64_t seed = 0;
+    uint32_t chain = 0;
+    std::vector<int> type;
+    std::vector<double> param1, param2;
+    std::vector<int> nextIndex;
+    std::vector<double> acceptance, sigma;
+    std::vector<int> acceptanceTrials;
+    double lastValue = 0.0;
+    int trials = 0, successes = 0;
+    int acceptanceWindow = -1;                 // an int in the reference (:281)
+    int lastIndex = -1;
+    double rigidity = 2.0, target = 0.44;
+    bool initialized = false;
+    uint32_t slot = 0;                         // draws consumed by the current step
+
+    void SetDim(int d) {                       // :82-96
+        n = d;
+        type.assign(d, 0);
+        param1.assign(d, 0.0);
+        param2.assign(d, 0.0);
+        acceptance.assign(d, 0.0);
+        acceptanceTrials.assign(d, 0);
+        sigma.assign(d, 2.34);
+    }
+    void InitializeState(double value) {       // :193-209
+        if (initialized) return;
+        initialized = true;
+        lastValue = value;
+        acceptanceWindow = 100;
+    }
+    void UpdateState(double value) {           // :216-254
+        InitializeState(value);
+        ++trials;
+        bool accepted = false;
+        if (value != lastValue) accepted = true;
+        if (accepted) ++successes;
+        lastValue = value;
+        if (lastIndex < 0) return;
+        ++acceptanceTrials[lastIndex];
+        acceptance[lastIndex] *= 1.0 * std::min(acceptanceWindow, acceptanceTrials[lastIndex]);
+        if (accepted) acceptance[lastIndex] += 1.0;
+        acceptance[lastIndex] /= 1.0 + 1.0 * std::min(acceptanceWindow, acceptanceTrials[lastIndex]);
+        if (acceptanceTrials[lastIndex] > 0.1 * acceptanceWindow && rigidity > 0 && rigidity < 100.0) {
+            double v = sigma[lastIndex];
+            v *= std::pow(acceptance[lastIndex] / target,
+                          std::min(1.0 / 500.0, 1.0 / (rigidity * acceptanceWindow)));
+            sigma[lastIndex] = std::max(v, 1.0E-4);
+        }
+    }
+    void UpdateProposal(uint32_t step) {       // :176-190
+        if (!nextIndex.empty()) return;
+        nextIndex.resize(n);
+        lastIndex = -1;
+        for (int i = 0; i < n; ++i) nextIndex[i] = i;
+        for (int i = 0; i < n; ++i) {
+            double u = 1.0 * smcmc_uniform(seed, chain, step, slot++, SMCMC_STREAM_STEP);   // TRandom::Uniform()
+            std::size_t sw = (std::size_t)(nextIndex.size() * u);
+            if (sw >= nextIndex.size()) sw = nextIndex.size() - 1;     // u < 1, but n*u can round up to n
+            std::swap(nextIndex[i], nextIndex[sw]);
+        }
+    }
+    void Propose(double* proposal, const double* current, double value, uint32_t step) {   // :40-80
+        slot = 0;
+        UpdateState(value);
+        std::copy(current, current + n, proposal);
+        UpdateProposal(step);
+        lastIndex = nextIndex.back();
+        nextIndex.pop_back();
+        if (type[lastIndex] == 1) {
+            double u = smcmc_uniform(seed, chain, step, slot++, SMCMC_STREAM_STEP);
+            proposal[lastIndex] = param1[lastIndex] + (param2[lastIndex] - param1[lastIndex]) * u;
+            return;
+        }
+        double expectedVariance = 1.0;
+        if (type[lastIndex] == 0 && param1[lastIndex] > 0) expectedVariance = param1[lastIndex];
+        double g = smcmc_normal(seed, chain, step, slot++, SMCMC_STREAM_STEP);
+        double r = 0.0 + expectedVariance * g;                                   // TRandom::Gaus(0, expectedVariance)
+        proposal[lastIndex] = current[lastIndex] + sigma[lastIndex] * r;
+    }
+    double MeanSigma() const {                 // GetSigma :166-173
+        double t = 0.0;
+        for (int i = 0; i < n; ++i) t += sigma[i];
+        return n ? t / n : 0.0;
+    }
+};
+
+// ---------------------------------------------------------------------------
 // TSimpleMCMC (TSimpleMCMC.H:185-590)
 // ---------------------------------------------------------------------------
 struct OrcChain {
     Likelihood like;
     Proposal prop;
+    VaatProposal vprop;
+    bool vaat = false;      // TSimpleMCMC<L, TProposeVAATStep>
     int n = 0;
     uint32_t step = 0;
     std::vector<double> accepted, proposed, trial;
@@ -733,6 +829,10 @@ struct OrcChain {
         proposedLlh = Eval(proposed.data());
         if (!std::isfinite(proposedLlh) || proposedLlh < -0.999999E+10) return 0;
         acceptedLlh = proposedLlh;
+        if (vaat) {
+            vprop.InitializeState(acceptedLlh);
+            return 1;
+        }
         if (!prop.InitializeState(accepted.data(), acceptedLlh)) return -1;
         return 1;
     }
@@ -741,7 +841,11 @@ struct OrcChain {
     int Step(int metropolis) {
         if (proposed.empty() || accepted.empty()) { gLastError = "Uninitialized starting point"; return -1; }
         ++totalSteps;
-        if (!prop.Propose(proposed.data(), accepted.data(), acceptedLlh, step++)) return -1;
+        uint32_t acceptSlot = (uint32_t)n;
+        if (vaat) {
+            vprop.Propose(proposed.data(), accepted.data(), acceptedLlh, step++);
+            acceptSlot = vprop.slot;
+        } else if (!prop.Propose(proposed.data(), accepted.data(), acceptedLlh, step++)) return -1;
         if (stepRMSWindow > 0) {                                       // :391-406
             double sqr = 0.0;
             for (int i = 0; i < n; ++i) {
@@ -765,7 +869,7 @@ struct OrcChain {
         double delta = proposedLlh - acceptedLlh;                      // :441-463
         if (delta < 0.0) {
             if (metropolis == 1) return 0;
-            double u = 1.0 * smcmc_uniform(prop.seed, prop.chain, step - 1, (uint32_t)n, SMCMC_STREAM_STEP);
+            double u = 1.0 * smcmc_uniform(prop.seed, prop.chain, step - 1, acceptSlot, SMCMC_STREAM_STEP);
             double t = std::log(u);
             if (delta < t) return 0;
         }
@@ -864,6 +968,32 @@ void* orc_chain_create(int kind, int dim, uint64_t seed, uint32_t chain) {
     return c;
 }
 
+void* orc_chain_create_vaat(int kind, int dim, uint64_t seed, uint32_t chain) {
+    OrcChain* c = static_cast<OrcChain*>(orc_chain_create(kind, dim, seed, chain));
+    if (!c) return 0;
+    c->vaat = true;
+    c->vprop.seed = seed;
+    c->vprop.chain = chain;
+    c->vprop.SetDim(dim);
+    return c;
+}
+
+int orc_chain_get_vaat(void* h, double* sigma, double* acceptance, int32_t* acceptanceTrials, int32_t* misc) {
+    OrcChain* c = H(h);
+    if (!c->vaat) { gLastError = "not a TProposeVAATStep chain"; return -1; }
+    VaatProposal& p = c->vprop;
+    if (sigma) std::copy(p.sigma.begin(), p.sigma.end(), sigma);
+    if (acceptance) std::copy(p.acceptance.begin(), p.acceptance.end(), acceptance);
+    if (acceptanceTrials) std::copy(p.acceptanceTrials.begin(), p.acceptanceTrials.end(), acceptanceTrials);
+    if (misc) {
+        misc[0] = p.trials;
+        misc[1] = p.successes;
+        misc[2] = p.lastIndex;
+        misc[3] = (int32_t)p.nextIndex.size();
+    }
+    return 0;
+}
+
 void orc_chain_destroy(void* h) { delete H(h); }
 
 int orc_chain_set_fake(void* h, const orc_event* ev, long n, const double* data150, double exposure) {
@@ -883,6 +1013,13 @@ int orc_chain_set_error_matrix(void* h, const double* e, int n) {
 }
 
 int orc_chain_set(void* h, int field, double v) {
+    if (H(h)->vaat && field != ORC_SET_STEP_RMS_WINDOW) {
+        VaatProposal& q = H(h)->vprop;
+        if (field == ORC_SET_ACCEPTANCE_WINDOW) q.acceptanceWindow = (int)v;        // :136
+        else if (field == ORC_SET_ACCEPTANCE_RIGIDITY) q.rigidity = v;              // :146
+        else { gLastError = "TProposeVAATStep has no such setting"; return -1; }
+        return 0;
+    }
     Proposal& p = H(h)->prop;
     switch (field) {
     case ORC_SET_SIGMA: p.sigma = v; break;
@@ -906,6 +1043,11 @@ int orc_chain_set(void* h, int field, double v) {
 int orc_chain_set_gaussian(void* h, int d, double sigma) {            // :855-867
     Proposal& p = H(h)->prop;
     if (d < 0 || d >= p.n) return -1;
+    if (H(h)->vaat) {                                                 // TProposeVAATStep.H:121-133: sigma itself
+        H(h)->vprop.type[d] = 0;
+        H(h)->vprop.param1[d] = sigma;
+        return 0;
+    }
     p.type[d] = 0;
     p.param1[d] = sigma * sigma;
     return 0;
@@ -914,6 +1056,12 @@ int orc_chain_set_gaussian(void* h, int d, double sigma) {            // :855-86
 int orc_chain_set_uniform(void* h, int d, double lo, double hi) {     // :833-848
     Proposal& p = H(h)->prop;
     if (d < 0 || d >= p.n) return -1;
+    if (H(h)->vaat) {                                                 // TProposeVAATStep.H:99-115
+        H(h)->vprop.type[d] = 1;
+        H(h)->vprop.param1[d] = lo;
+        H(h)->vprop.param2[d] = hi;
+        return 0;
+    }
     p.type[d] = 1;
     p.param1[d] = lo;
     p.param2[d] = hi;
@@ -936,7 +1084,7 @@ int orc_chain_step(void* h, int nsteps, int metropolis, int32_t* accepted,
         if (accepted) accepted[s] = r;
         if (llhAccepted) llhAccepted[s] = c->acceptedLlh;
         if (llhProposed) llhProposed[s] = c->proposedLlh;
-        if (sigma) sigma[s] = c->prop.sigma;
+        if (sigma) sigma[s] = c->vaat ? c->vprop.MeanSigma() : c->prop.sigma;
         if (x) std::copy(c->accepted.begin(), c->accepted.end(), x + (size_t)s * c->n);
     }
     return 0;
@@ -948,6 +1096,27 @@ int orc_chain_reset_proposal(void* h) { return H(h)->prop.ResetProposal() ? 0 : 
 int orc_chain_get_state(void* h, double* s, double* accepted, double* center,
                         double* cov, double* decomp) {
     OrcChain* c = H(h);
+    if (c->vaat) {
+        VaatProposal& q = c->vprop;
+        if (s) {
+            for (int k = 0; k < ORC_ST_COUNT; ++k) s[k] = 0.0;
+            double acc = 0.0;                                   // GetAcceptance :155-163
+            for (int i = 0; i < q.n; ++i) acc += q.acceptance[i];
+            s[ORC_ST_SIGMA] = q.MeanSigma();
+            s[ORC_ST_ACCEPTANCE] = q.n ? acc / q.n : 0.0;
+            s[ORC_ST_ACCEPTANCE_WINDOW] = q.acceptanceWindow;
+            s[ORC_ST_ACCEPTANCE_RIGIDITY] = q.rigidity;
+            s[ORC_ST_TRIALS] = q.trials;
+            s[ORC_ST_SUCCESSES] = q.successes;
+            s[ORC_ST_STEP_RMS] = c->stepRMS;
+            s[ORC_ST_ACCEPTED_LLH] = c->acceptedLlh;
+            s[ORC_ST_PROPOSED_LLH] = c->proposedLlh;
+            s[ORC_ST_TOTAL_STEPS] = c->totalSteps;
+            s[ORC_ST_LLH_CALLS] = c->llhCalls;
+        }
+        if (accepted) std::copy(c->accepted.begin(), c->accepted.end(), accepted);
+        return 0;
+    }
     Proposal& p = c->prop;
     const size_t nn = (size_t)c->n * c->n;
     if (s) {

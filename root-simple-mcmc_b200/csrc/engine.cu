@@ -22,6 +22,7 @@
 #include "proposal_staged.cuh"
 #include "simple_likelihoods.cuh"
 #include "unbinned_likelihood.cuh"
+#include "vaat.cuh"
 
 namespace smcmc {
 
@@ -94,6 +95,41 @@ struct smcmc_engine {
     DeviceBuffer<uint32_t> ijTab;
     int covStride = 0, upkStride = 0;   // doubles per chain (whole 128-byte lines)
     bool staged = false;                // kProposeStaged (one CTA per chain) instead of kPropose
+
+    // ---- TProposeVAATStep (vaat.cuh) ---------------------------------------
+    int propKind = SMCMC_PROPOSAL_ADAPTIVE;
+    std::vector<double> gaussSigma;     // SetGaussian's argument as given (TProposeVAATStep keeps sigma, not sigma^2)
+    int vaatWindow = -1;                // fAcceptanceWindow (int; InitializeState forces 100, TProposeVAATStep.H:208)
+    DeviceBuffer<double> vSigma, vAcceptance;
+    DeviceBuffer<int> vAccTrials, vQueue;
+    DeviceBuffer<VaatState> vState;
+    VaatArrays vaatArrays() {
+        VaatArrays v;
+        v.sigma = vSigma.get();
+        v.acceptance = vAcceptance.get();
+        v.acceptanceTrials = vAccTrials.get();
+        v.queue = vQueue.get();
+        v.st = vState.get();
+        v.window = vaatWindow;
+        v.target = 0.44;                // :30
+        return v;
+    }
+    void vaatAllocate() {
+        const size_t En = (size_t)E() * n();
+        vSigma.reserve(En);
+        vAcceptance.reserve(En);
+        vAccTrials.reserve(En);
+        vQueue.reserve(En);
+        vState.reserve(E());
+        std::vector<double> sig(En, 2.34);                                  // SetDim, :95
+        CUDA_CHECK(cudaMemcpy(vSigma.get(), sig.data(), En * sizeof(double), cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemset(vAcceptance.get(), 0, En * sizeof(double)));
+        CUDA_CHECK(cudaMemset(vAccTrials.get(), 0, En * sizeof(int)));
+        CUDA_CHECK(cudaMemset(vQueue.get(), 0, En * sizeof(int)));
+        std::vector<VaatState> st(E());
+        for (auto& q : st) { q.lastIndex = -1; q.queueSize = 0; q.acceptSlot = 0; q.pad_ = 0; }
+        CUDA_CHECK(cudaMemcpy(vState.get(), st.data(), st.size() * sizeof(VaatState), cudaMemcpyHostToDevice));
+    }
     DeviceBuffer<ChainScalars> sc;
     DeviceBuffer<int32_t> okDev;
     DeviceBuffer<double> eigScratch;
@@ -291,7 +327,12 @@ struct smcmc_engine {
             dParam1.reserve(nn);
             dParam2.reserve(nn);
             CUDA_CHECK(cudaMemcpyAsync(dType.get(), type.data(), nn * sizeof(int), cudaMemcpyHostToDevice, stream));
-            CUDA_CHECK(cudaMemcpyAsync(dParam1.get(), param1.data(), nn * sizeof(double), cudaMemcpyHostToDevice, stream));
+            // SetGaussian keeps sigma^2 in the adaptive proposal (TSimpleMCMC.H:865-866) and sigma
+            // itself in TProposeVAATStep (TProposeVAATStep.H:132)
+            std::vector<double> p1(param1);
+            for (int i = 0; i < nn; ++i)
+                if (type[i] == 0 && propKind == SMCMC_PROPOSAL_VAAT) p1[i] = gaussSigma[i];
+            CUDA_CHECK(cudaMemcpyAsync(dParam1.get(), p1.data(), nn * sizeof(double), cudaMemcpyHostToDevice, stream));
             CUDA_CHECK(cudaMemcpyAsync(dParam2.get(), param2.data(), nn * sizeof(double), cudaMemcpyHostToDevice, stream));
             const size_t nc = corrValue.size();
             if (nc) {
@@ -593,7 +634,10 @@ struct smcmc_engine {
         } else if (pooledEvery > 0)
             kProposePooled<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a, ps, pooled(), E(), cfg.seed,
                                                                           cfg.chain_offset, stepIndex, nullptr);
-        else if (staged)
+        else if (propKind == SMCMC_PROPOSAL_VAAT) {
+            CUDA_CHECK(cudaMemcpyAsync(xProp.get(), xAcc.get(), sizeof(double) * E() * n(), cudaMemcpyDeviceToDevice, stream));   // :52
+            kVaatPropose<<<ceilDiv(E(), 128), 128, 0, stream>>>(a, vaatArrays(), ps, E(), cfg.seed, cfg.chain_offset, stepIndex);
+        } else if (staged)
             kProposeStaged<<<E(), kStagedThreads, stagedChainBytes(n(), covStride, upkStride), stream>>>(
                 a, ps, E(), cfg.seed, cfg.chain_offset, stepIndex);
         else
@@ -601,7 +645,8 @@ struct smcmc_engine {
         launched();
         evaluate(xProp.get(), E(), llhProp.get(), nullptr);
         kAccept<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(a, ps, E(), llhProp.get(), cfg.seed, cfg.chain_offset,
-                                                            stepIndex, metropolis, tr, traceStep);
+                                                            stepIndex, metropolis, tr, traceStep,
+                                                            propKind == SMCMC_PROPOSAL_VAAT ? (const int*)vState.get() : nullptr);
         launched();
         ++stepIndex;
         if (diagOn) diagAccumulate();
@@ -680,6 +725,7 @@ int smcmc_create(const smcmc_config* cfg, smcmc_engine** out) {
         e->type.assign(n, 0);
         e->param1.assign(n, 0.0);
         e->param2.assign(n, 0.0);
+        e->gaussSigma.assign(n, 0.0);
         e->xAcc.reserve(E * n);
         e->xProp.reserve(E * n);
         e->lastPoint.reserve(E * n);
@@ -832,7 +878,17 @@ int smcmc_prop_set(smcmc_engine* e, int field, double v) {
         switch (field) {
         case SMCMC_PROP_SIGMA: perChain = true; break;
         case SMCMC_PROP_TARGET_ACCEPTANCE: e->target = v; break;
-        case SMCMC_PROP_ACCEPTANCE_WINDOW: e->accWindow = v; break;
+        case SMCMC_PROP_ACCEPTANCE_WINDOW:
+            e->accWindow = v;
+            e->vaatWindow = (int)v;                                            // TProposeVAATStep.H:136 (int member)
+            break;
+        case SMCMC_PROP_KIND:
+            if (e->started) throw Error(SMCMC_ERR_LOGIC, "the proposal kind is chosen before Start()");
+            if (v != SMCMC_PROPOSAL_ADAPTIVE && v != SMCMC_PROPOSAL_VAAT)
+                throw Error(SMCMC_ERR_INVALID_ARGUMENT, "unknown proposal kind");
+            e->propKind = (int)v;
+            e->settingsDirty = true;
+            break;
         case SMCMC_PROP_ACCEPTANCE_RIGIDITY: perChain = true; break;
         case SMCMC_PROP_ACCEPTANCE_DEWEIGHT: e->accDeweight = v; break;
         case SMCMC_PROP_COVARIANCE_WINDOW: e->covWindow = (int)v; break;      // SetCovarianceWindow(int)
@@ -866,6 +922,7 @@ int smcmc_prop_set_gaussian(smcmc_engine* e, int d, double sigma) {
         if (d < 0 || d >= e->n()) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "dimension out of range");   // :856-860
         e->type[d] = 0;
         e->param1[d] = sigma * sigma;                                                                  // :865-866
+        e->gaussSigma[d] = sigma;
         e->settingsDirty = true;
     });
 }
@@ -921,11 +978,19 @@ static void userUpdate(smcmc_engine* e, int reset) {
 }
 
 int smcmc_prop_update(smcmc_engine* e) {
-    return guarded(e, [&]() { userUpdate(e, 0); });
+    return guarded(e, [&]() {
+        if (e->propKind == SMCMC_PROPOSAL_VAAT)
+            throw Error(SMCMC_ERR_LOGIC, "TProposeVAATStep has no UpdateProposal / ResetProposal to call");
+        userUpdate(e, 0);
+    });
 }
 
 int smcmc_prop_reset(smcmc_engine* e) {
-    return guarded(e, [&]() { userUpdate(e, 1); });
+    return guarded(e, [&]() {
+        if (e->propKind == SMCMC_PROPOSAL_VAAT)
+            throw Error(SMCMC_ERR_LOGIC, "TProposeVAATStep has no UpdateProposal / ResetProposal to call");
+        userUpdate(e, 1);
+    });
 }
 
 int smcmc_fake_set_events(smcmc_engine* e, const smcmc_event* events, int64_t count) {
@@ -1165,6 +1230,23 @@ int smcmc_start(smcmc_engine* e, const double* x0, int32_t* ok) {
         CUDA_CHECK(cudaMemcpyAsync(e->xAcc.get(), x0, bytes, cudaMemcpyHostToDevice, e->stream));   // :247-256
         CUDA_CHECK(cudaMemcpyAsync(e->xProp.get(), e->xAcc.get(), bytes, cudaMemcpyDeviceToDevice, e->stream));
         e->evaluate(e->xProp.get(), e->E(), e->llhProp.get(), nullptr);                             // :258
+        if (e->propKind == SMCMC_PROPOSAL_VAAT) {
+            if (e->pooledEvery > 0) throw Error(SMCMC_ERR_LOGIC, "pooled adaptation belongs to the adaptive proposal");
+            PropSettings psv = e->settings();
+            if (!e->started) e->vaatAllocate();
+            e->vaatWindow = 100;                                                                    // InitializeState, TProposeVAATStep.H:208
+            kStoreStartLlh<<<ceilDiv(e->E(), 128), 128, 0, e->stream>>>(e->sc.get(), e->llhProp.get(), e->E());
+            e->launched();
+            kVaatInit<<<ceilDiv(e->E(), 128), 128, 0, e->stream>>>(e->arrays(), e->vaatArrays(), e->E(), e->n(), e->okDev.get());
+            e->launched();
+            (void)psv;
+            std::vector<int32_t> okv(e->E());
+            CUDA_CHECK(cudaMemcpyAsync(okv.data(), e->okDev.get(), sizeof(int32_t) * e->E(), cudaMemcpyDeviceToHost, e->stream));
+            CUDA_CHECK(cudaStreamSynchronize(e->stream));
+            if (ok) std::memcpy(ok, okv.data(), sizeof(int32_t) * e->E());
+            e->started = true;
+            return;
+        }
         e->resolveInitDefaults();
         e->resolveResetDefaults();
         PropSettings ps = e->settings();
@@ -1224,6 +1306,8 @@ int smcmc_step_trace(smcmc_engine* e, int nsteps, int metropolis, const smcmc_tr
 int smcmc_save_state(smcmc_engine* e, const smcmc_saved_state* out) {
     return guarded(e, [&]() {
         requireStarted(e);
+        if (e->propKind == SMCMC_PROPOSAL_VAAT)
+            throw Error(SMCMC_ERR_LOGIC, "TProposeVAATStep does not save or restore its state (TProposeVAATStep.H:33-36)");
         if (!out) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null state");
         const size_t E = e->E(), n = e->n(), tri = e->tri();
         CUDA_CHECK(cudaStreamSynchronize(e->stream));
@@ -1253,6 +1337,8 @@ int smcmc_save_state(smcmc_engine* e, const smcmc_saved_state* out) {
 int smcmc_restore_state(smcmc_engine* e, const smcmc_saved_state* in, int32_t* mismatch) {
     return guarded(e, [&]() {
         requireStarted(e);
+        if (e->propKind == SMCMC_PROPOSAL_VAAT)
+            throw Error(SMCMC_ERR_LOGIC, "TProposeVAATStep does not save or restore its state (TProposeVAATStep.H:33-36)");
         if (!in || !in->accepted || !in->log_likelihood || !in->total_steps || !in->step_rms || !in->trials ||
             !in->successes || !in->next_update || !in->acceptance || !in->acceptance_trials || !in->sigma ||
             !in->central_point || !in->central_point_trials || !in->covariance || !in->covariance_trials)
@@ -1323,6 +1409,39 @@ int smcmc_get(smcmc_engine* e, int field, void* dst, size_t bytes) {
             CUDA_CHECK(cudaMemcpyAsync(dst, src, want, cudaMemcpyDeviceToHost, e->stream));
             CUDA_CHECK(cudaStreamSynchronize(e->stream));
         };
+        const bool vaat = e->propKind == SMCMC_PROPOSAL_VAAT;
+        if (field >= SMCMC_F_VAAT_SIGMA && field <= SMCMC_F_VAAT_QUEUE && (!vaat || !e->started))
+            throw Error(SMCMC_ERR_LOGIC, "the sampler was not started with SMCMC_PROPOSAL_VAAT");
+        if (vaat && e->started && (field == SMCMC_F_ACCEPTANCE || field == SMCMC_F_VAAT_LAST_INDEX || field == SMCMC_F_VAAT_QUEUE)) {
+            if (field == SMCMC_F_ACCEPTANCE) {                                // GetAcceptance, TProposeVAATStep.H:155-163
+                need(E * 8);
+                std::vector<double> acc(E * n);
+                CUDA_CHECK(cudaMemcpyAsync(acc.data(), e->vAcceptance.get(), acc.size() * 8, cudaMemcpyDeviceToHost, e->stream));
+                CUDA_CHECK(cudaStreamSynchronize(e->stream));
+                for (size_t c = 0; c < E; ++c) {
+                    double t = 0.0;
+                    for (size_t i = 0; i < n; ++i) t += acc[c * n + i];
+                    ((double*)dst)[c] = t / (double)n;
+                }
+                return;
+            }
+            need(E * 4);
+            std::vector<VaatState> st(E);
+            CUDA_CHECK(cudaMemcpyAsync(st.data(), e->vState.get(), E * sizeof(VaatState), cudaMemcpyDeviceToHost, e->stream));
+            CUDA_CHECK(cudaStreamSynchronize(e->stream));
+            for (size_t c = 0; c < E; ++c)
+                ((int32_t*)dst)[c] = field == SMCMC_F_VAAT_LAST_INDEX ? st[c].lastIndex : st[c].queueSize;
+            return;
+        }
+        switch (field) {
+        case SMCMC_F_VAAT_SIGMA: copyArray(e->vSigma.get(), E * n * 8); return;
+        case SMCMC_F_VAAT_ACCEPTANCE: copyArray(e->vAcceptance.get(), E * n * 8); return;
+        case SMCMC_F_VAAT_ACCEPTANCE_TRIALS: copyArray(e->vAccTrials.get(), E * n * 4); return;
+        case SMCMC_F_ACCEPTANCE_WINDOW:
+            if (vaat) { need(8); *(double*)dst = e->vaatWindow; return; }
+            break;
+        default: break;
+        }
         switch (field) {
         case SMCMC_F_ACCEPTED: copyArray(e->xAcc.get(), E * n * 8); return;
         case SMCMC_F_PROPOSED: copyArray(e->xProp.get(), E * n * 8); return;

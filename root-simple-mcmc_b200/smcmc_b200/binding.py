@@ -17,6 +17,8 @@ DUMMY_EXACT, DUMMY_TENSOR = 0, 1
  PROP_COVARIANCE_DEWEIGHT, PROP_COVARIANCE_FROZEN, PROP_COVARIANCE_TRIALS,
  PROP_CENTER_TRIALS, PROP_NEXT_UPDATE, PROP_MAX_CORRELATION,
  PROP_STEP_RMS_WINDOW, PROP_POOLED_EVERY, PROP_POOLED_TENSOR) = range(15)
+PROP_KIND = 15
+PROPOSAL_ADAPTIVE, PROPOSAL_VAAT = 0, 1
 
 # smcmc_field: name -> (id, dtype, shape code)
 _FIELDS = {
@@ -35,6 +37,9 @@ _FIELDS = {
     "target_acceptance": (24, np.float64, "1"),
     "pooled_mean": (25, np.float64, "n"), "pooled_covariance": (26, np.float64, "t"),
     "pooled_decomposition": (27, np.float64, "nn"), "pooled_count": (28, np.float64, "1"),
+    "vaat_sigma": (29, np.float64, "En"), "vaat_acceptance": (30, np.float64, "En"),
+    "vaat_acceptance_trials": (31, np.int32, "En"), "vaat_last_index": (32, np.int32, "E"),
+    "vaat_queue": (33, np.int32, "E"),
 }
 
 # The reference's MC event record (example/Simulated.H:7-14), 48 bytes.
@@ -252,7 +257,8 @@ class Engine:
     to every chain of the ensemble.
     """
 
-    def __init__(self, likelihood, dim, chains, seed=1, device=0, chain_offset=0):
+    def __init__(self, likelihood, dim, chains, seed=1, device=0, chain_offset=0, proposal=PROPOSAL_ADAPTIVE):
+        """proposal=PROPOSAL_VAAT: sMCMC::TSimpleMCMC<L, TProposeVAATStep> (TProposeVAATStep.H)."""
         self.lib = load_library()
         self.dim, self.chains = int(dim), int(chains)
         cfg = _Config(ctypes.sizeof(_Config), device, dim, chains, chain_offset,
@@ -262,6 +268,8 @@ class Engine:
         if rc != 0:
             raise SmcmcError(rc, self.lib.smcmc_last_error(None).decode())
         self.h = h
+        if proposal != PROPOSAL_ADAPTIVE:
+            self.prop_set(PROP_KIND, proposal)
 
     def close(self):
         if getattr(self, "h", None):

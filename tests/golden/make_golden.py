@@ -141,6 +141,42 @@ def make_fake2():
         len(events), len(points), [int(out["chain%d_accepted" % c].sum()) for c in (0, 5)]))
 
 
+# TSimpleMCMC<L, TProposeVAATStep> (SimpleVAAT.C:31): name -> (kind, dim, seed, chain, steps, configure)
+def _vaat_hints(c):
+    c.set_uniform(2, -1.5, 2.0)
+    c.set_gaussian(4, 0.5)
+    c.set(cc.SET_ACCEPTANCE_RIGIDITY, 1.5)
+
+
+VAAT_CHAINS = {
+    "vaat_unit5": (cc.LLH_UNIT_GAUSS, 5, 7, 3, 1500, None),
+    "vaat_unit9_hints": (cc.LLH_UNIT_GAUSS, 9, 11, 0, 1200, _vaat_hints),
+    "vaat_horrific75": (cc.LLH_HORRIFIC, 75, 5, 9, 900, None),
+}
+
+
+def make_vaat():
+    out = {}
+    for name, (kind, dim, seed, chain, nsteps, configure) in VAAT_CHAINS.items():
+        c = cc.CpuChain("ref", kind, dim, seed, chain, vaat=True)
+        if configure:
+            configure(c)
+        out[name + "/ok"] = np.array([c.start(np.zeros(dim))])
+        first = c.step(nsteps - 300)
+        c.set(cc.SET_ACCEPTANCE_WINDOW, 37.0)        # honoured after Start (before, InitializeState overrides it)
+        second = c.step(300)
+        for k in ("accepted", "llh_accepted", "llh_proposed", "x", "sigma"):
+            out[name + "/" + k] = np.concatenate([first[k], second[k]])
+        v = c.vaat_state()
+        for k in ("sigma", "acceptance", "acceptance_trials"):
+            out[name + "/final_" + k] = np.asarray(v[k])
+        out[name + "/final_misc"] = np.array([v["trials"], v["successes"], v["last_index"], v["queue"]])
+        st = c.state()
+        out[name + "/final_step_rms"] = np.array([st["step_rms"]])
+        print(name, "accepted", int(out[name + "/accepted"].sum()), "of", nsteps)
+    np.savez_compressed(os.path.join(HERE, "vaat.npz"), **out)
+
+
 def run_chain(kind, dim, seed, chain, nsteps, configure=None, x0=None):
     c = cc.CpuChain("ref", kind, dim, seed, chain)
     if configure:
@@ -250,7 +286,9 @@ def make_hmc():
 
 if __name__ == "__main__":
     cc.build()
-    which = sys.argv[1:] or ["fake", "fake2", "chains", "hmc"]
+    which = sys.argv[1:] or ["fake", "fake2", "chains", "hmc", "vaat"]
+    if "vaat" in which:
+        make_vaat()
     if "fake" in which:
         make_fake()
     if "fake2" in which:

@@ -315,3 +315,38 @@ def test_fake2_port_equals_reference_on_fresh_inputs(checkers, have_ref):
         assert la == lb or (np.isnan(la) and np.isnan(lb))
         assert np.array_equal(a.fake_hist(p), b.fake_hist(p), equal_nan=True)
     assert np.isnan(a.llh(pts[0]))
+
+
+# ---------------------------------------------------------------------------
+# TProposeVAATStep
+# ---------------------------------------------------------------------------
+def _vaat_run(checkers, which, name):
+    from golden.make_golden import VAAT_CHAINS
+    kind, dim, seed, chain, nsteps, configure = VAAT_CHAINS[name]
+    c = checkers.CpuChain(which, kind, dim, seed, chain, vaat=True)
+    if configure:
+        configure(c)
+    ok = c.start(np.zeros(dim))
+    first = c.step(nsteps - 300)
+    c.set(checkers.SET_ACCEPTANCE_WINDOW, 37.0)
+    second = c.step(300)
+    return ok, first, second, c
+
+
+@pytest.mark.parametrize("which", ["orc", "ref"])
+@pytest.mark.parametrize("name", ["vaat_unit5", "vaat_unit9_hints", "vaat_horrific75"])
+def test_vaat_chain_matches_golden(checkers, have_ref, which, name):
+    """TSimpleMCMC<L, TProposeVAATStep>: shuffled index queue, per-dimension step
+    size and acceptance (TProposeVAATStep.H:40-80, 176-190, 216-254), bit for bit."""
+    if which == "ref" and not have_ref:
+        pytest.skip("reference-backed checker not built here")
+    g = golden("vaat.npz")
+    ok, first, second, c = _vaat_run(checkers, which, name)
+    assert ok == int(g[name + "/ok"][0])
+    for k in ("accepted", "llh_accepted", "llh_proposed", "x", "sigma"):
+        assert np.array_equal(np.concatenate([first[k], second[k]]), g[name + "/" + k]), k
+    v = c.vaat_state()
+    for k in ("sigma", "acceptance", "acceptance_trials"):
+        assert np.array_equal(np.asarray(v[k]), g[name + "/final_" + k]), k
+    assert [v["trials"], v["successes"], v["last_index"], v["queue"]] == list(g[name + "/final_misc"])
+    assert c.state()["step_rms"] == g[name + "/final_step_rms"][0]
