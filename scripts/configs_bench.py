@@ -138,6 +138,25 @@ def c4():
             eng.close()
 
 
+def vaat():
+    """TProposeVAATStep on the C3 shape (65 536 chains x 50 dimensions)."""
+    E, n, steps = 65536, 50, 200
+    for name, kind in (("THorrificLogLikelihood", 2), ("TASymLogLikelihood", 3)):
+        eng = smcmc_b200.Engine(kind, n, E, seed=4, proposal=smcmc_b200.PROPOSAL_VAAT)
+        eng.start(np.zeros(n) if kind == 2 else np.full(n, 0.01))
+        eng.step(50)
+        dt = timed(lambda: eng.step(steps), eng.sync)
+        # per chain-step: the point is copied (2 n doubles), the likelihood reads it (n), the accept
+        # writes it back on acceptance (<= 2 n); the proposal itself touches O(1) entries
+        bytes_per = 5 * n * 8
+        rate = E * steps / dt
+        emit({"config": "VAAT (8f rank 4)", "target": name, "chains": E, "dim": n, "proposal": "TProposeVAATStep",
+              "ms_per_step": 1e3 * dt / steps, "chain_steps_per_s": rate, "algorithmic_bytes_per_chain_step": bytes_per,
+              "hbm_gbs": rate * bytes_per / 1e9, "hbm_peak_gbs": HBM, "frac": rate * bytes_per / 1e9 / HBM,
+              "acceptance": float(eng.get("acceptance").mean())})
+        eng.close()
+
+
 def ex2():
     """example2's likelihood on the shape of C2 (4096 chains x 1M events),
     next to the reference's own example2 code on one host core."""
@@ -251,5 +270,7 @@ if __name__ == "__main__":
             c5(a)
         elif w == "ex2":
             ex2()
+        elif w == "vaat":
+            vaat()
         else:
             {"c1": c1, "c3": c3, "c4": c4}[w]()

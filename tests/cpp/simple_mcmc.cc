@@ -7,6 +7,7 @@
 #include <cstring>
 
 #include "TSimpleMCMC.H"
+#include "TProposeVAATStep.H"
 #include "smcmc_likelihoods.H"
 
 // Starting point: the origin, or the true event counts for example2
@@ -58,11 +59,37 @@ static int Run(int chains, int steps, bool hints) {
     return 0;
 }
 
+// SimpleVAAT.C:31-66 written against the mirror: the variable-at-a-time proposal.
+// Chain `chain` of seed 7 is the golden chain "vaat_unit5" of the reference build.
+static int RunVaat(int chains, int steps) {
+    TTree tree("SimpleMCMC", "Tree of accepted points");
+    sMCMC::TSimpleMCMC<TUnitGaussLogLikelihood, sMCMC::TProposeVAATStep> mcmc(&tree, false);
+    mcmc.SetChains(chains);
+    mcmc.SetSeed(7);
+    mcmc.SetDevice(0, 3);
+    TUnitGaussLogLikelihood& like = mcmc.GetLogLikelihood();
+    mcmc.GetProposeStep().SetDim(like.GetDim());
+    sMCMC::Vector point(like.GetDim());
+    if (!mcmc.Start(point, false)) { std::printf("start failed\n"); return 2; }
+    int accepted = 0;
+    for (int i = 0; i < steps; ++i) {
+        bool ok = mcmc.Step();
+        accepted += ok;
+        std::printf("step %d acc %d llh %.17g x0 %.17g sigma %.17g\n", i, (int)ok, mcmc.GetAcceptedLogLikelihood(),
+                    mcmc.GetAccepted()[0], mcmc.GetProposeStep().GetSigma());
+    }
+    std::printf("entries %ld accepted %d trials %d successes %d window %g\n", tree.GetEntries(), accepted,
+                mcmc.GetProposeStep().GetTrials(), mcmc.GetProposeStep().GetSuccesses(),
+                mcmc.GetProposeStep().GetAcceptanceWindow());
+    return 0;
+}
+
 int main(int argc, char** argv) {
     const char* kind = argc > 1 ? argv[1] : "unit";
     int chains = argc > 2 ? std::atoi(argv[2]) : 1;
     int steps = argc > 3 ? std::atoi(argv[3]) : 100;
     if (!std::strcmp(kind, "fake")) return Run<FakeLikelihood>(chains, steps, false);
     if (!std::strcmp(kind, "fake2")) return Run<FakeLikelihood2>(chains, steps, false);
+    if (!std::strcmp(kind, "vaat")) return RunVaat(chains, steps);
     return Run<TUnitGaussLogLikelihood>(chains, steps, true);
 }

@@ -131,3 +131,22 @@ def test_example2_likelihood_ensemble_through_the_cpp_api(program):
     s = re.search(r"start llh (\S+) direct (\S+)", r.stdout)
     assert s and s.group(1) == s.group(2) and np.isfinite(float(s.group(1)))
     assert float(s.group(1)) > -2000.0          # near the truth the fit is good
+
+
+@pytest.mark.gpu
+def test_vaat_proposal_through_the_cpp_api(program):
+    """SimpleVAAT.C's pairing TSimpleMCMC<L, TProposeVAATStep> through include/TProposeVAATStep.H:
+    chain 0 of the program is chain 3 of seed 7, the golden chain "vaat_unit5" of the reference build."""
+    r = subprocess.run([program, "vaat", "2", "400"], capture_output=True, text=True, check=True)
+    want = golden("vaat.npz")
+    rows = re.findall(r"step (\d+) acc (\d) llh (\S+) x0 (\S+) sigma (\S+)", r.stdout)
+    assert len(rows) == 400
+    acc = np.array([int(x[1]) for x in rows])
+    x0 = np.array([float(x[3]) for x in rows])
+    sigma = np.array([float(x[4]) for x in rows])
+    assert np.array_equal(acc, want["vaat_unit5/accepted"][:400])
+    assert np.allclose(x0, want["vaat_unit5/x"][:400, 0], rtol=1e-12, atol=1e-13)
+    assert np.allclose(sigma, want["vaat_unit5/sigma"][:400], rtol=1e-12)
+    m = re.search(r"entries (\d+) accepted (\d+) trials (\d+) successes (\d+) window (\S+)", r.stdout)
+    assert m and int(m.group(1)) == 2 * 400 and int(m.group(3)) == 400 and float(m.group(5)) == 100.0
+    assert int(m.group(2)) == int(acc.sum())
