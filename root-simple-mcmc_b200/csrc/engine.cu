@@ -213,8 +213,8 @@ struct smcmc_engine {
         }
         kDiagChains<<<ceilDiv((long long)En, 256), 256, 0, stream>>>(xAcc.get(), sc.get(), E(), n(), d, slot);
         launched();
-        const int poolBlocks = std::min(smCount * 2, ceilDiv(E(), 32));
-        kPoolAccumulate<<<poolBlocks, 256, 32 * n() * sizeof(double), stream>>>(xAcc.get(), sc.get(), E(), n(),
+        const int poolBlocks = std::min(smCount * 8, ceilDiv(E(), kPoolTile));
+        kPoolAccumulate<<<poolBlocks, 256, poolAccSmem(n()), stream>>>(xAcc.get(), sc.get(), E(), n(),
                                                                                 diagPooled.get());
         launched();
     }
@@ -251,11 +251,17 @@ struct smcmc_engine {
         return p;
     }
     int poolStatCount() const { return 1 + n() + tri(); }
+    static size_t poolAccSmem(int n) { return (size_t)kPoolTile * (n + 2) * sizeof(double); }
+    // the tile kernel keeps the shared U and 32 chains in shared memory: four CTAs per SM
+    bool usePooledTile() const { return !std::getenv("SMCMC_POOLED_WARP") && pooledTileSmem(n()) <= 56 * 1024; }
     void poolInit() {
         const size_t nn = (size_t)n() * n();
-        if ((size_t)32 * n() * sizeof(double) > 48 * 1024)
+        if (poolAccSmem(n()) > 48 * 1024)
             CUDA_CHECK(cudaFuncSetAttribute(kPoolAccumulate, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)((size_t)32 * n() * sizeof(double))));
+                                            (int)poolAccSmem(n())));
+        if (usePooledTile() && pooledTileSmem(n()) > 48 * 1024)
+            CUDA_CHECK(cudaFuncSetAttribute(kProposePooledTile, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)pooledTileSmem(n())));
         poolStats.reserve(poolStatCount());
         poolStatsAll.reserve(poolStatCount());
         poolCov.reserve(tri());
@@ -631,7 +637,10 @@ struct smcmc_engine {
             launched();
             kProposePooledFinish<<<blocks, kWarpsPerBlock * 32, (size_t)kWarpsPerBlock * n() * sizeof(double), stream>>>(
                 a, ps, E(), poolY.get());
-        } else if (pooledEvery > 0)
+        } else if (pooledEvery > 0 && usePooledTile())
+            kProposePooledTile<<<ceilDiv(E(), kPooledTileChains), kPooledTileThreads, pooledTileSmem(n()), stream>>>(
+                a, ps, pooled(), E(), cfg.seed, cfg.chain_offset, stepIndex);
+        else if (pooledEvery > 0)
             kProposePooled<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a, ps, pooled(), E(), cfg.seed,
                                                                           cfg.chain_offset, stepIndex, nullptr);
         else if (propKind == SMCMC_PROPOSAL_VAAT) {
@@ -651,8 +660,8 @@ struct smcmc_engine {
         ++stepIndex;
         if (diagOn) diagAccumulate();
         if (pooledEvery > 0) {
-            const int poolBlocks = std::min(smCount * 2, ceilDiv(E(), 32));
-            kPoolAccumulate<<<poolBlocks, 256, 32 * n() * sizeof(double), stream>>>(xAcc.get(), sc.get(), E(), n(),
+            const int poolBlocks = std::min(smCount * 8, ceilDiv(E(), kPoolTile));
+            kPoolAccumulate<<<poolBlocks, 256, poolAccSmem(n()), stream>>>(xAcc.get(), sc.get(), E(), n(),
                                                                                     poolStats.get());
             launched();
             if (stepIndex % (uint32_t)pooledEvery == 0) poolExchange();
@@ -1659,9 +1668,9 @@ int smcmc_diag_enable(smcmc_engine* e, int max_lag) {
             else lag = (lag / 3) * 4;
         }
         e->diagDepth = max_lag;
-        if ((size_t)32 * e->n() * sizeof(double) > 48 * 1024)
+        if (smcmc_engine::poolAccSmem(e->n()) > 48 * 1024)
             CUDA_CHECK(cudaFuncSetAttribute(kPoolAccumulate, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)((size_t)32 * e->n() * sizeof(double))));
+                                            (int)smcmc_engine::poolAccSmem(e->n())));
         e->diagPooled.reserve(e->poolStatCount());
         e->diagS1.reserve(En);
         e->diagS2.reserve(En);

@@ -29,59 +29,64 @@ struct PooledState {
     double* trace;      // [0] trace of the pooled covariance behind `decomp`
 };
 
-// S += sum over local chains.  Block = 256 threads; thread t owns packed
-// entries t, t+256, ...; a block walks a slice of the chains with the points
-// staged through shared memory.
+// S += sum over local chains.  Block = 256 threads; thread t owns statistics
+// t, t+256, ...; a block walks a slice of the chains with the points staged
+// through shared memory as y = (1, x_0 .. x_{n-1}): every statistic is a product
+// y_a y_b (count = y_0 y_0, sum x_i = y_{i+1} y_0, sum x_i x_j = y_{i+1} y_{j+1}),
+// so the inner loop is branch-free: two LDS, one multiply, one add per statistic
+// and chain.  A chain that is not running is staged as y = 0.
+constexpr int kPoolOwn = 6;                 // statistics per thread and pass
+constexpr int kPoolTile = 32;               // chains per staged tile
 __global__ void __launch_bounds__(256)
 kPoolAccumulate(const double* __restrict__ xAcc, const ChainScalars* __restrict__ sc, int chains, int n,
                 double* stats) {
-    extern __shared__ double tile[];          // 32 chains x n
+    extern __shared__ double tile[];          // kPoolTile x (n + 2): y, then a zero for unused slots
     const int tri = n * (n + 1) / 2;
     const int nstat = 1 + n + tri;
-    constexpr int kMaxOwn = 8;                // entries per thread handled per pass
+    const int row = n + 2;
     const int perBlock = (chains + gridDim.x - 1) / gridDim.x;
     const int first = blockIdx.x * perBlock;
     const int last = min(chains, first + perBlock);
-    for (int pass = 0; pass * 256 * kMaxOwn < nstat; ++pass) {
-        double acc[kMaxOwn];
-        int ei[kMaxOwn], ej[kMaxOwn];
+    for (int pass = 0; pass * 256 * kPoolOwn < nstat; ++pass) {
+        double acc[kPoolOwn];
+        int ea[kPoolOwn], eb[kPoolOwn];
 #pragma unroll
-        for (int o = 0; o < kMaxOwn; ++o) {
+        for (int o = 0; o < kPoolOwn; ++o) {
             acc[o] = 0.0;
-            const int k = (pass * kMaxOwn + o) * 256 + threadIdx.x;      // 0: count, 1..n: sum x, then packed x x^T
-            ei[o] = -2; ej[o] = 0;
-            if (k == 0) ei[o] = -1;
-            else if (k <= n) { ei[o] = k - 1; ej[o] = -1; }
+            const int k = (pass * kPoolOwn + o) * 256 + threadIdx.x;      // 0: count, 1..n: sum x, then packed x x^T
+            ea[o] = eb[o] = n + 1;                                        // the zero slot
+            if (k == 0) ea[o] = eb[o] = 0;
+            else if (k <= n) { ea[o] = k; eb[o] = 0; }
             else if (k < nstat) {
                 const int p = k - 1 - n;
                 int i = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
                 while (i * (i + 1) / 2 > p) --i;
                 while ((i + 1) * (i + 2) / 2 <= p) ++i;
-                ei[o] = i; ej[o] = p - i * (i + 1) / 2;
+                ea[o] = i + 1;
+                eb[o] = p - i * (i + 1) / 2 + 1;
             }
         }
-        for (int c0 = first; c0 < last; c0 += 32) {
-            const int nc = min(32, last - c0);
+        for (int c0 = first; c0 < last; c0 += kPoolTile) {
+            const int nc = min(kPoolTile, last - c0);
             __syncthreads();
-            for (int k = threadIdx.x; k < nc * n; k += 256) {
-                const int c = k / n;
-                tile[k] = sc[c0 + c].started ? xAcc[(size_t)(c0 + c) * n + (k - c * n)] : nan("");
+            for (int k = threadIdx.x; k < nc * row; k += 256) {
+                const int c = k / row, i = k - c * row;
+                const bool live = sc[c0 + c].started != 0;
+                double v = 0.0;
+                if (live && i == 0) v = 1.0;
+                else if (live && i <= n) v = xAcc[(size_t)(c0 + c) * n + (i - 1)];
+                tile[k] = v;
             }
             __syncthreads();
             for (int c = 0; c < nc; ++c) {
-                const double* x = tile + c * n;
-                if (isnan(x[0])) continue;               // chain not started
+                const double* y = tile + c * row;
 #pragma unroll
-                for (int o = 0; o < kMaxOwn; ++o) {
-                    if (ei[o] == -1) acc[o] += 1.0;
-                    else if (ei[o] >= 0 && ej[o] < 0) acc[o] += x[ei[o]];
-                    else if (ei[o] >= 0) acc[o] += x[ei[o]] * x[ej[o]];
-                }
+                for (int o = 0; o < kPoolOwn; ++o) acc[o] += y[ea[o]] * y[eb[o]];
             }
         }
 #pragma unroll
-        for (int o = 0; o < kMaxOwn; ++o) {
-            const int k = (pass * kMaxOwn + o) * 256 + threadIdx.x;
+        for (int o = 0; o < kPoolOwn; ++o) {
+            const int k = (pass * kPoolOwn + o) * 256 + threadIdx.x;
             if (k < nstat && acc[o] != 0.0) atomicAdd(&stats[k], acc[o]);
         }
     }
@@ -269,6 +274,121 @@ kProposePooledFinish(ChainArrays a, PropSettings ps, int chains, const double* _
         s.stepRMSTrials = min(ps.stepRMSWindow, s.stepRMSTrials + 1);
         s.stepRMS = __dsqrt_rn(ms);
         if (lane == 0) a.sc[c] = s;
+    }
+}
+
+// kProposePooled for small dimensions (the shared U fits shared memory next to a
+// tile of chains): one CTA of 256 threads owns kPooledTileChains chains.  The
+// scalar part of UpdateState runs one THREAD per chain, the draws one thread per
+// (chain, dimension), the contraction with the shared U one thread per (chain,
+// column) -- instead of one warp per chain with 31 lanes idle through the scalars.
+constexpr int kPooledTileChains = 32;
+constexpr int kPooledTileThreads = 256;
+__host__ __device__ inline size_t pooledTileSmem(int n) {
+    return ((size_t)n * n + (size_t)2 * kPooledTileChains * (n + 1) + kPooledTileChains) * sizeof(double);
+}
+
+__global__ void __launch_bounds__(kPooledTileThreads)
+kProposePooledTile(ChainArrays a, PropSettings ps, PooledState pool, int chains, uint64_t seed,
+                   uint32_t chainOffset, uint32_t step) {
+    extern __shared__ double smemD[];
+    const int n = ps.n;
+    const int ld = n + 1;                                    // padded rows: conflict-free column walks
+    double* uS = smemD;                                      // n x n, the shared U
+    double* cur = uS + (size_t)n * n;                        // [chain][n+1] accepted points
+    double* zr = cur + (size_t)kPooledTileChains * ld;       // draws, then sigma * r
+    double* dif = cur;                                       // squared step per dimension: entry (c, j) replaces
+                                                             // x_j of chain c once its only reader has used it
+    double* sig = zr + (size_t)kPooledTileChains * ld;       // [chain] fSigma, or NaN for a chain that does not run
+    const int tid = threadIdx.x;
+    const int c0 = blockIdx.x * kPooledTileChains;
+    const int nc = min(kPooledTileChains, chains - c0);
+
+    for (int k = tid; k < n * n; k += kPooledTileThreads) uS[k] = pool.decomp[k];
+    for (int k = tid; k < nc * n; k += kPooledTileThreads) {
+        const int c = k / n, i = k - c * n;
+        cur[c * ld + i] = a.xAcc[(size_t)c0 * n + k];
+    }
+    ChainScalars s;
+    bool live = false;
+    if (tid < nc) {
+        // ---- one thread per chain: the scalars of UpdateState, :1723-1776 ----
+        const int c = c0 + tid;
+        s = a.sc[c];
+        live = s.started && s.status == 0;
+        if (live) {
+            s.totalSteps += 1;
+            const double value = s.accLlh;
+            const bool accepted = updateStateScalars(s, ps, value, a.xAcc[(size_t)c * n], a.lastPoint[(size_t)c * n]);
+            (void)accepted;
+            // the shared covariance changed since this chain last looked: keep the
+            // step length in units of the new trace (UpdateProposal :1042-1043)
+            const double poolTrace = pool.trace[0];
+            if (poolTrace > 0.0 && poolTrace != s.sigmaTrace) {
+                s.sigma = __dmul_rn(s.sigma, __dsqrt_rn(__ddiv_rn(s.sigmaTrace, poolTrace)));
+                s.sigmaTrace = poolTrace;
+            }
+            s.lastValue = value;
+        }
+        sig[tid] = live ? s.sigma : nan("");
+    }
+    // ---- one thread per (chain, dimension): the draws, :709-719 -------------------
+    for (int k = tid; k < nc * n; k += kPooledTileThreads) {
+        const int c = k / n, i = k - c * n;
+        const uint32_t gchain = chainOffset + (uint32_t)(c0 + c);
+        double v;
+        if (ps.anyUniform && ps.type[i] == 1) {
+            const double uu = smcmc_uniform(seed, gchain, step, (uint32_t)i, SMCMC_STREAM_STEP);
+            v = __dadd_rn(ps.param1[i], __dmul_rn(__dsub_rn(ps.param2[i], ps.param1[i]), uu));
+        } else {
+            const double g = smcmc_normal(seed, gchain, step, (uint32_t)i, SMCMC_STREAM_STEP);
+            v = __dadd_rn(0.0, __dmul_rn(1.0, g));
+        }
+        zr[c * ld + i] = v;
+    }
+    __syncthreads();
+    for (int k = tid; k < nc * n; k += kPooledTileThreads) {
+        const int c = k / n, i = k - c * n;
+        if (!(ps.anyUniform && ps.type[i] == 1)) zr[c * ld + i] = __dmul_rn(sig[c], zr[c * ld + i]);   // fSigma*r
+    }
+    __syncthreads();
+    // ---- one thread per (chain, column): x'_j = x_j + sum_{i<=j} (fSigma r_i) U(i,j) ----
+    for (int k = tid; k < nc * n; k += kPooledTileThreads) {
+        const int c = k / n, j = k - c * n;
+        const double* z = zr + c * ld;
+        const double x = cur[c * ld + j];
+        double p = x;
+        if (ps.anyUniform && ps.type[j] == 1) {
+            p = z[j];
+        } else if (!ps.anyUniform) {
+#pragma unroll 4
+            for (int i = 0; i <= j; ++i) p = __dadd_rn(p, __dmul_rn(z[i], uS[i * n + j]));
+        } else {
+            for (int i = 0; i <= j; ++i)
+                if (ps.type[i] != 1) p = __dadd_rn(p, __dmul_rn(z[i], uS[i * n + j]));
+        }
+        const bool run = !isnan(sig[c]);
+        if (run) {
+            a.xProp[(size_t)c0 * n + k] = p;
+            a.lastPoint[(size_t)c0 * n + k] = x;                          // :1829-1830
+        }
+        const double d = __dsub_rn(p, x);
+        dif[c * ld + j] = __dmul_rn(d, d);
+    }
+    __syncthreads();
+    if (tid < nc && live) {
+        if (ps.stepRMSWindow > 0) {                                       // :391-406
+            const double* q = dif + tid * ld;
+            double sqr = 0.0;
+            for (int i = 0; i < n; ++i) sqr = __dadd_rn(sqr, q[i]);
+            double ms = __dmul_rn(s.stepRMS, s.stepRMS);
+            ms = __dmul_rn(ms, (double)s.stepRMSTrials);
+            ms = __dadd_rn(ms, sqr);
+            ms = __ddiv_rn(ms, __dadd_rn((double)s.stepRMSTrials, 1.0));
+            s.stepRMSTrials = min(ps.stepRMSWindow, s.stepRMSTrials + 1);
+            s.stepRMS = __dsqrt_rn(ms);
+        }
+        a.sc[c0 + tid] = s;
     }
 }
 
