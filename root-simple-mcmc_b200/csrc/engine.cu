@@ -519,7 +519,14 @@ struct smcmc_engine {
                 CUDA_CHECK(cudaEventCreate(&e1));
                 CUDA_CHECK(cudaEventRecord(e0, stream));
             }
-            kFakePairs<<<(unsigned)chunks * (unsigned)pointTiles, kPairThreads, kPairSmemBytes, stream>>>(L);
+            if (m <= kStreamMaxChains && !std::getenv("SMCMC_FAKE_NO_STREAM")) {
+                // few chains: events streamed once, chains looped per event (fake_likelihood.cuh)
+                int64_t tiles = 0;
+                for (int c = 0; c < kFakeClasses; ++c) tiles += fakeClassCount[c] / kPairTile;
+                const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)smCount * 8, (tiles + 7) / 8));
+                kFakeStream<<<blocks, kStreamThreads, 0, stream>>>(L);
+            } else
+                kFakePairs<<<(unsigned)chunks * (unsigned)pointTiles, kPairThreads, kPairSmemBytes, stream>>>(L);
             launched();
             if (timing) {
                 CUDA_CHECK(cudaEventRecord(e1, stream));

@@ -760,6 +760,95 @@ kFakePairs(const __grid_constant__ PairLaunch L) {
     else pairChunk<false>(L, cls, first, count, pointBase, tiles, bars, counters, queue);
 }
 
+// ---------------------------------------------------------------------------
+// The streaming kernel: FEW chains (<= kStreamMaxChains) over many events.
+//
+// kFakePairs maps one chain to one thread and reuses every event tile for 256
+// chains: with a handful of chains (the reference's own use: ONE chain) 255 of
+// its 256 threads idle.  Here the roles are swapped: a warp takes one tile of
+// 128 events (four per lane, the tile's 2 KB read with four coalesced 16-byte
+// loads per lane), every lane evaluates its four events for each of the E chains
+// (parameters in shared memory) with the same FP32 interval filter and the same
+// FP64 fallback, and counts into a per-CTA shared-memory table that is flushed
+// to the global count table at the end.  Each event is read ONCE: 16 bytes per
+// event per evaluation, HBM-bound for E <= ~4 (SURVEY.md 8d "streaming regime").
+// The counts are the same integers kFakePairs produces.
+// ---------------------------------------------------------------------------
+constexpr int kStreamMaxChains = 8;
+constexpr int kStreamThreads = 256;
+constexpr int kStreamRows = 300;             // slots of the four weight classes
+
+template <bool TAGGED>
+__device__ __forceinline__ void streamCount(const FilterDecision& dec, int cls, int chain, int64_t event,
+                                            const PairLaunch& L, const FakeChainParams* cps, uint32_t* table) {
+    int row;
+    if (dec.sure) {
+        if (!dec.counted) return;
+        row = (int)(dec.bits - kFloorMagicBits);
+        if (!TAGGED && dec.far) row += 50;
+    } else {
+        row = exactDecide(L.events[event], cps[chain], cls);             // FP64, the reference's arithmetic
+        if (row < 0) return;
+    }
+    atomicAdd(&table[chain * kStreamRows + fakeClassSlotBase(cls) + row], 1u);
+}
+
+template <bool TAGGED>
+__device__ __forceinline__ void streamTile(const PairLaunch& L, int cls, int64_t tileIndex, int lane,
+                                           const FilterChain* fcs, const FakeChainParams* cps, uint32_t* table) {
+    const FilterTile& tile = L.filterTiles[tileIndex];
+    const float4 ls = reinterpret_cast<const float4*>(tile.ls)[lane];
+    const float4 d = reinterpret_cast<const float4*>(tile.d)[lane];
+    const float4 nl = reinterpret_cast<const float4*>(tile.nl2)[lane];
+    float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!TAGGED) sp = reinterpret_cast<const float4*>(tile.sep)[lane];
+    const int64_t event0 = tileIndex * kPairTile + 4 * lane;
+    for (int c = 0; c < L.numPoints; ++c) {
+        const FilterChain fc = fcs[c];
+        const float thr = fc.thr[cls >> 1], thrEps = fc.thrEps[cls >> 1];
+        const FilterPair a = filterCore2<TAGGED>(make_float2(ls.x, ls.y), make_float2(d.x, d.y), make_float2(nl.x, nl.y),
+                                                 make_float2(sp.x, sp.y), fc, thr);
+        const FilterPair b = filterCore2<TAGGED>(make_float2(ls.z, ls.w), make_float2(d.z, d.w), make_float2(nl.z, nl.w),
+                                                 make_float2(sp.z, sp.w), fc, thr);
+        streamCount<TAGGED>(filterDecide<TAGGED>(a.lo.x, a.hi.x, a.ds.x, thrEps), cls, c, event0 + 0, L, cps, table);
+        streamCount<TAGGED>(filterDecide<TAGGED>(a.lo.y, a.hi.y, a.ds.y, thrEps), cls, c, event0 + 1, L, cps, table);
+        streamCount<TAGGED>(filterDecide<TAGGED>(b.lo.x, b.hi.x, b.ds.x, thrEps), cls, c, event0 + 2, L, cps, table);
+        streamCount<TAGGED>(filterDecide<TAGGED>(b.lo.y, b.hi.y, b.ds.y, thrEps), cls, c, event0 + 3, L, cps, table);
+    }
+}
+
+__global__ void __launch_bounds__(kStreamThreads)
+kFakeStream(const __grid_constant__ PairLaunch L) {
+    __shared__ uint32_t table[kStreamMaxChains * kStreamRows];
+    __shared__ FilterChain fcs[kStreamMaxChains];
+    __shared__ FakeChainParams cps[kStreamMaxChains];
+    for (int k = threadIdx.x; k < L.numPoints * kStreamRows; k += kStreamThreads) table[k] = 0u;
+    if (threadIdx.x < L.numPoints) {
+        fcs[threadIdx.x] = L.filterChains[threadIdx.x];
+        cps[threadIdx.x] = L.chains[threadIdx.x];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (kStreamThreads / 32) + (threadIdx.x >> 5);
+    const int64_t warps = (int64_t)gridDim.x * (kStreamThreads / 32);
+    for (int cls = 0; cls < kFakeClasses; ++cls) {
+        const int64_t firstTile = L.classBase[cls] / kPairTile;
+        const int64_t tiles = L.classCount[cls] / kPairTile;             // padded to whole tiles
+        for (int64_t t = warp; t < tiles; t += warps) {
+            if (cls & 1) streamTile<true>(L, cls, firstTile + t, lane, fcs, cps, table);
+            else streamTile<false>(L, cls, firstTile + t, lane, fcs, cps, table);
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < L.numPoints * kStreamRows; k += kStreamThreads) {
+        const uint32_t v = table[k];
+        if (v) {
+            const int c = k / kStreamRows, slot = k - c * kStreamRows;
+            atomicAdd(&L.counts[(size_t)slot * L.pointStride + c], v);
+        }
+    }
+}
+
 // Test kernel: run the filter AND the FP64 arithmetic on every pair and count
 // the pairs where a filter decision differs from the FP64 decision (must be
 // zero).  stats[0] = pairs, [1] = unsure, [2] = mismatches.

@@ -157,6 +157,37 @@ def vaat():
         eng.close()
 
 
+def stream():
+    """The streaming regime of the event likelihood: few chains over 16.8 M events, every
+    event read once per evaluation (16 bytes in the FP32 tile layout) => HBM-bound for E <= ~4."""
+    N = 16777216
+    signal = N // 3 + 1
+    events = synth.make_mc_sample(signal, N - signal, seed=2)
+    data = synth.make_data_histograms(33334, 33334, seed=2)
+    for E in (1, 2, 4, 8):
+        eng = smcmc_b200.Engine(smcmc_b200.LLH_FAKE, 9, E, seed=3)
+        eng.set_fake_events(events)
+        eng.set_fake_data(data, 0.006)
+        x0 = np.zeros((E, 9))
+        for c in range(E):
+            x0[c] = np.random.default_rng([3, c]).uniform(-1.0, 1.0, 9)
+        eng.start(x0)
+        eng.step(3)
+        eng.enable_kernel_timing(True)
+        eng.pair_kernel_stats(reset=True)
+        steps = 30
+        dt = timed(lambda: eng.step(steps), eng.sync)
+        ms, launches = eng.pair_kernel_stats()
+        kernel_s = ms / max(launches, 1) / 1e3
+        bytes_alg = N * 16.0
+        emit({"config": "event likelihood, streaming regime", "chains": E, "events": N, "kernel": "kFakeStream",
+              "ms_per_step": 1e3 * dt / steps, "kernel_ms": 1e3 * kernel_s, "launches_timed": launches,
+              "algorithmic_bytes_per_launch": bytes_alg, "hbm_gbs": bytes_alg / kernel_s / 1e9, "hbm_peak_gbs": HBM,
+              "frac": bytes_alg / kernel_s / 1e9 / HBM, "pair_evals_per_s": E * float(N) / kernel_s,
+              "chain_steps_per_s": E * steps / dt})
+        eng.close()
+
+
 def ex2():
     """example2's likelihood on the shape of C2 (4096 chains x 1M events),
     next to the reference's own example2 code on one host core."""
@@ -272,5 +303,7 @@ if __name__ == "__main__":
             ex2()
         elif w == "vaat":
             vaat()
+        elif w == "stream":
+            stream()
         else:
             {"c1": c1, "c3": c3, "c4": c4}[w]()

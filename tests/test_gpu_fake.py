@@ -204,3 +204,27 @@ def test_missing_inputs_fail_loudly():
     with pytest.raises(smcmc_b200.SmcmcError) as err:
         eng.step(1)
     assert err.value.status == -1          # Step before Start: std::invalid_argument (:371-374)
+
+
+@pytest.mark.parametrize("chains", [1, 3, 8])
+def test_streaming_kernel_counts_equal_the_pair_kernel(chains, monkeypatch):
+    """Up to 8 chains the events are streamed once with the chains looped per event (kFakeStream);
+    more chains use the chain-per-thread pair kernel.  Same filter, same FP64 fallback: the integer
+    counts, and therefore the histograms and likelihoods, are identical."""
+    import smcmc_b200
+    events, data = smcmc_b200.synth.fake_inputs(700, 900, 10, seed=13)        # 25 000 events, ragged tiles
+    rng = np.random.default_rng(4)
+    pts = np.concatenate([rng.uniform(-1, 1, (4, 9)), rng.normal(0, 6, (4, 9))])[:chains]
+    stream = make_engine(events, data, 0.1, chains=chains)
+    c_stream, l_stream = stream.fake_counts(pts), stream.eval(pts)
+    monkeypatch.setenv("SMCMC_FAKE_NO_STREAM", "1")
+    pair = make_engine(events, data, 0.1, chains=chains)
+    c_pair, l_pair = pair.fake_counts(pts), pair.eval(pts)
+    monkeypatch.delenv("SMCMC_FAKE_NO_STREAM")
+    assert np.array_equal(c_stream, c_pair)
+    assert np.array_equal(l_stream, l_pair)
+    assert c_stream.sum() > 1000 * chains
+    # and the exact (all-FP64) evaluation agrees as well
+    monkeypatch.setenv("SMCMC_FAKE_EXACT", "1")
+    exact = make_engine(events, data, 0.1, chains=chains)
+    assert np.array_equal(exact.fake_counts(pts), c_stream)
