@@ -387,6 +387,36 @@ def run_b200(args):
             "peak_source": "measured in this run (DFMA chain micro-benchmark)"},
     }
 
+    # ---- the same likelihood in its streaming regime: ONE chain, every event
+    # read once per evaluation by kFakeStream -- the HBM-bound face of the event likelihood.
+    # 16.8 M events = 268 MB of FP32 tile records: larger than the 126 MB L2.
+    if world == 1 and not args.no_streaming:
+        n_stream = 16777216
+        sig = n_stream // 3 + 1
+        ev_stream = synth.make_mc_sample(sig, n_stream - sig, seed=2)
+        eng_s = smcmc_b200.Engine(smcmc_b200.LLH_FAKE, DIM, 1, seed=SEED, device=local)
+        eng_s.set_stream(stream)
+        eng_s.set_fake_events(ev_stream)
+        eng_s.set_fake_data(data, exposure * len(events) / float(n_stream))
+        eng_s.start(start_points(1, 0))
+        eng_s.step(3)
+        eng_s.enable_kernel_timing(True)
+        eng_s.pair_kernel_stats(reset=True)
+        eng_s.step(20)
+        eng_s.sync()
+        s_ms, s_n = eng_s.pair_kernel_stats()
+        s_sec = s_ms / max(s_n, 1) * 1e-3
+        roofline["hbm_streaming"] = {
+            "kernel": "smcmc::kFakeStream (the same likelihood with 1 chain: every event is read once per evaluation)",
+            "bound": "hbm", "achieved": 16.0 * n_stream / s_sec / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "frac": 16.0 * n_stream / s_sec / 1e9 / hbm_peak, "peak_source": hbm_src,
+            "algorithmic": "16 B per event (FP32 tile record: logSigma, dLog, nomLog, separation) x %d events per launch"
+                           % n_stream,
+            "launch_ms": s_ms / max(s_n, 1), "launches_timed": int(s_n), "chains": 1, "events": n_stream,
+            "inputs": "larger than L2 (268 MB)"}
+        eng_s.close()
+        del ev_stream
+
     cpu_value, cpu_desc = (None, None)
     if world == 1 and not args.no_cpu_baseline:
         cpu_value, cpu_desc = cpu_arm(events, data, exposure, args.cpu_steps, 1)
@@ -425,6 +455,8 @@ def main():
     ap.add_argument("--events", type=int, default=EVENTS)
     ap.add_argument("--cpu-steps", type=int, default=12, help="steps of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-streaming", action="store_true",
+                    help="skip the 1-chain x 16.8M-event streaming measurement (roofline.hbm_streaming)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
