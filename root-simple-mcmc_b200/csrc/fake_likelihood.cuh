@@ -596,6 +596,7 @@ __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t 
     const int tid = threadIdx.x;
     const int point = pointBase + tid;
     const bool live = point < L.numPoints;
+    const bool warpLive = __any_sync(0xffffffffu, live);
     FilterChain fc;
     if (live) fc = L.filterChains[point];
     else {
@@ -674,7 +675,10 @@ __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t 
         if (TAGGED) mode = 1;
         else if (tile->sep[kPairTile - 1] < sepLow) mode = 1;
         else if (tile->sep[0] > sepHigh) mode = 2;
-        if (mode == 0) mask = tileLoop<false>(tile, fc, thr, thrEps, mineAdj, mineDummy, mineAdd);
+        // a warp without a live chain (ensembles that do not fill the 256-chain tile) only
+        // keeps the buffer protocol going
+        if (!warpLive) mask = 0;
+        else if (mode == 0) mask = tileLoop<false>(tile, fc, thr, thrEps, mineAdj, mineDummy, mineAdd);
         else mask = tileLoop<true>(tile, fc, thr, thrEps, mode == 2 ? mineAdj + kFilterCutRow * kPairRowBytes : mineAdj,
                                    mineDummy, mineAdd);
         if (!live) mask = 0;
@@ -774,7 +778,7 @@ kFakePairs(const __grid_constant__ PairLaunch L) {
 // event per evaluation, HBM-bound for E <= ~4 (SURVEY.md 8d "streaming regime").
 // The counts are the same integers kFakePairs produces.
 // ---------------------------------------------------------------------------
-constexpr int kStreamMaxChains = 8;
+constexpr int kStreamMaxChains = 16;
 constexpr int kStreamThreads = 256;
 constexpr int kStreamRows = 300;             // slots of the four weight classes
 

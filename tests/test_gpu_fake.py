@@ -206,15 +206,15 @@ def test_missing_inputs_fail_loudly():
     assert err.value.status == -1          # Step before Start: std::invalid_argument (:371-374)
 
 
-@pytest.mark.parametrize("chains", [1, 3, 8])
+@pytest.mark.parametrize("chains", [1, 3, 8, 16])
 def test_streaming_kernel_counts_equal_the_pair_kernel(chains, monkeypatch):
-    """Up to 8 chains the events are streamed once with the chains looped per event (kFakeStream);
+    """Up to 16 chains the events are streamed once with the chains looped per event (kFakeStream);
     more chains use the chain-per-thread pair kernel.  Same filter, same FP64 fallback: the integer
     counts, and therefore the histograms and likelihoods, are identical."""
     import smcmc_b200
     events, data = smcmc_b200.synth.fake_inputs(700, 900, 10, seed=13)        # 25 000 events, ragged tiles
     rng = np.random.default_rng(4)
-    pts = np.concatenate([rng.uniform(-1, 1, (4, 9)), rng.normal(0, 6, (4, 9))])[:chains]
+    pts = np.concatenate([rng.uniform(-1, 1, (4, 9)), rng.normal(0, 6, (4, 9)), rng.normal(0, 2, (24, 9))])[:chains]
     stream = make_engine(events, data, 0.1, chains=chains)
     c_stream, l_stream = stream.fake_counts(pts), stream.eval(pts)
     monkeypatch.setenv("SMCMC_FAKE_NO_STREAM", "1")
