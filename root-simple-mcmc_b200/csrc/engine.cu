@@ -660,7 +660,7 @@ struct smcmc_engine {
             kPropose<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a, ps, E(), cfg.seed, cfg.chain_offset, stepIndex);
         launched();
         evaluate(xProp.get(), E(), llhProp.get(), nullptr);
-        kAccept<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(a, ps, E(), llhProp.get(), cfg.seed, cfg.chain_offset,
+        kAccept<<<ceilDiv(E(), kAcceptThreads), kAcceptThreads, 0, stream>>>(a, ps, E(), llhProp.get(), cfg.seed, cfg.chain_offset,
                                                             stepIndex, metropolis, tr, traceStep,
                                                             propKind == SMCMC_PROPOSAL_VAAT ? (const int*)vState.get() : nullptr);
         launched();
