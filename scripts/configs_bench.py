@@ -188,6 +188,38 @@ def stream():
         eng.close()
 
 
+def ess():
+    """Effective samples per second on C2 (the metric a user cares about):
+    the FakeMCMC.C schedule (100 + reset + 100 + update + production, FakeMCMC.C:93-165), then the
+    on-device diagnostics over the production steps."""
+    E, prod, lag = 4096, 1000, 96
+    signal = 333334
+    events = synth.make_mc_sample(signal, 1000000 - signal, seed=2)
+    data = synth.make_data_histograms(33334, 33334, seed=2)
+    eng = smcmc_b200.Engine(smcmc_b200.LLH_FAKE, 9, E, seed=3)
+    eng.set_fake_events(events)
+    expo = synth.exposure_ratio(eng, data)
+    eng.set_fake_data(data, expo)
+    x0 = np.zeros((E, 9))
+    for c in range(E):
+        x0[c] = np.random.default_rng([3, c]).uniform(-1.0, 1.0, 9)
+    eng.start(x0)
+    eng.step(100)
+    eng.reset_proposal()
+    eng.step(100)
+    eng.update_proposal()
+    eng.step(500)
+    eng.diag_enable(lag)
+    dt = timed(lambda: eng.step(prod), eng.sync)
+    d = eng.diag_get()
+    emit({"config": "C2 effective samples", "chains": E, "events": len(events), "production_steps": prod,
+          "ms_per_step_with_diagnostics": 1e3 * dt / prod, "chain_steps_per_s": E * prod / dt,
+          "acceptance": float(eng.get("acceptance").mean()), "rhat_max": float(np.max(d["rhat"])),
+          "tau": [float(v) for v in d["tau"]], "ess_per_s_min_dim": float(np.min(d["ess"]) / dt),
+          "ess_per_s_median_dim": float(np.median(d["ess"]) / dt), "lag1_autocorrelation": [float(v) for v in d["autocorrelation"][0]],
+          "posterior_mean": [float(v) for v in d["mean"]]})
+
+
 def ex2():
     """example2's likelihood on the shape of C2 (4096 chains x 1M events),
     next to the reference's own example2 code on one host core."""
@@ -305,5 +337,7 @@ if __name__ == "__main__":
             vaat()
         elif w == "stream":
             stream()
+        elif w == "ess":
+            ess()
         else:
             {"c1": c1, "c3": c3, "c4": c4}[w]()
