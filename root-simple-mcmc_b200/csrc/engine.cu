@@ -20,6 +20,7 @@
 #include "pooled.cuh"
 #include "proposal.cuh"
 #include "proposal_staged.cuh"
+#include "proposal_resident.cuh"
 #include "simple_likelihoods.cuh"
 #include "unbinned_likelihood.cuh"
 #include "vaat.cuh"
@@ -76,6 +77,18 @@ struct smcmc_engine {
     int smCount = 148;
     uint32_t stepIndex = 0;
     bool started = false;
+    // the step loop as a CUDA graph (stepMany): the step counter moves to a device word
+    bool graphMode = false;
+    DeviceBuffer<uint32_t> dStep;
+    cudaStream_t graphStream = nullptr;
+    cudaEvent_t graphEvent = nullptr;
+    cudaGraphExec_t graphExec = nullptr;
+    StepRef stepRef() {
+        StepRef r;
+        r.value = stepIndex;
+        r.ptr = graphMode ? dStep.get() : nullptr;
+        return r;
+    }
 
     // ---- proposal settings (host mirror of the reference's members) -------
     std::vector<int> type;
@@ -95,6 +108,8 @@ struct smcmc_engine {
     DeviceBuffer<uint32_t> ijTab;
     int covStride = 0, upkStride = 0;   // doubles per chain (whole 128-byte lines)
     bool staged = false;                // kProposeStaged (one CTA per chain) instead of kPropose
+    bool resident = false;              // kStepsResident fits (whole steps out of shared memory)
+    int64_t residentLaunches = 0;
 
     // ---- TProposeVAATStep (vaat.cuh) ---------------------------------------
     int propKind = SMCMC_PROPOSAL_ADAPTIVE;
@@ -637,7 +652,7 @@ struct smcmc_engine {
             poolZ.reserve((size_t)E() * n());
             poolY.reserve((size_t)E() * n());
             kProposePooled<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a, ps, pooled(), E(), cfg.seed,
-                                                                          cfg.chain_offset, stepIndex, poolZ.get());
+                                                                          cfg.chain_offset, stepRef(), poolZ.get());
             launched();
             dim3 grid(ceilDiv(n(), kDmmaBN), ceilDiv(E(), kDmmaBM));
             kDummyContractDmma<<<grid, 128, 0, stream>>>(poolZ.get(), poolDecompT.get(), poolY.get(), nullptr, 0, E(), n(), 0);
@@ -646,24 +661,28 @@ struct smcmc_engine {
                 a, ps, E(), poolY.get());
         } else if (pooledEvery > 0 && usePooledTile())
             kProposePooledTile<<<ceilDiv(E(), kPooledTileChains), kPooledTileThreads, pooledTileSmem(n()), stream>>>(
-                a, ps, pooled(), E(), cfg.seed, cfg.chain_offset, stepIndex);
+                a, ps, pooled(), E(), cfg.seed, cfg.chain_offset, stepRef());
         else if (pooledEvery > 0)
             kProposePooled<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a, ps, pooled(), E(), cfg.seed,
-                                                                          cfg.chain_offset, stepIndex, nullptr);
+                                                                          cfg.chain_offset, stepRef(), nullptr);
         else if (propKind == SMCMC_PROPOSAL_VAAT) {
             CUDA_CHECK(cudaMemcpyAsync(xProp.get(), xAcc.get(), sizeof(double) * E() * n(), cudaMemcpyDeviceToDevice, stream));   // :52
-            kVaatPropose<<<ceilDiv(E(), 128), 128, 0, stream>>>(a, vaatArrays(), ps, E(), cfg.seed, cfg.chain_offset, stepIndex);
+            kVaatPropose<<<ceilDiv(E(), 128), 128, 0, stream>>>(a, vaatArrays(), ps, E(), cfg.seed, cfg.chain_offset, stepRef());
         } else if (staged)
             kProposeStaged<<<E(), kStagedThreads, stagedChainBytes(n(), covStride, upkStride), stream>>>(
-                a, ps, E(), cfg.seed, cfg.chain_offset, stepIndex);
+                a, ps, E(), cfg.seed, cfg.chain_offset, stepRef());
         else
-            kPropose<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a, ps, E(), cfg.seed, cfg.chain_offset, stepIndex);
+            kPropose<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a, ps, E(), cfg.seed, cfg.chain_offset, stepRef());
         launched();
         evaluate(xProp.get(), E(), llhProp.get(), nullptr);
         kAccept<<<ceilDiv(E(), kAcceptThreads), kAcceptThreads, 0, stream>>>(a, ps, E(), llhProp.get(), cfg.seed, cfg.chain_offset,
-                                                            stepIndex, metropolis, tr, traceStep,
+                                                            stepRef(), metropolis, tr, traceStep,
                                                             propKind == SMCMC_PROPOSAL_VAAT ? (const int*)vState.get() : nullptr);
         launched();
+        if (graphMode) {
+            kBumpStep<<<1, 1, 0, stream>>>(dStep.get());
+            launched();
+        }
         ++stepIndex;
         if (diagOn) diagAccumulate();
         if (pooledEvery > 0) {
@@ -673,6 +692,114 @@ struct smcmc_engine {
             launched();
             if (stepIndex % (uint32_t)pooledEvery == 0) poolExchange();
         }
+    }
+
+    // nsteps Metropolis steps without a trace.  A step is 3 to 8 small launches; for
+    // small ensembles the host launch path, not the GPU, sets the pace.  When nothing in
+    // the step needs the host (no exchange, no timing, no diagnostics) the loop is
+    // captured ONCE as a CUDA graph -- after a plain first step that sizes every buffer --
+    // and replayed; the kernels read the step counter from a device word that the graph's
+    // last node increments.  Opt-in (SMCMC_GRAPH=1): measured on B200 it gains 2-5 % for
+    // 8-256 chains x 4M events and LOSES for one chain (gpurun_out/mid_ensemble.txt);
+    // the launch-bound chain-local case is served by kStepsResident instead.
+    static constexpr int kGraphMinSteps = 8;
+    bool graphable() const {
+        const char* g = std::getenv("SMCMC_GRAPH");
+        return g && g[0] == '1' && pooledEvery == 0 && !eventComm && !timing && !diagOn;
+    }
+    // The likelihood needs only the chain's own point and the proposal is the per-chain
+    // adaptive one: all nsteps steps run in ONE launch with the chain's state resident in
+    // shared memory (proposal_resident.cuh).  SMCMC_NO_RESIDENT=1 keeps the step-by-step path.
+    bool residentable() const {
+        if (!resident || !staged || pooledEvery > 0 || propKind != SMCMC_PROPOSAL_ADAPTIVE || timing || diagOn) return false;
+        if (std::getenv("SMCMC_NO_RESIDENT")) return false;
+        switch (cfg.likelihood) {
+        case SMCMC_LLH_UNIT_GAUSS:
+        case SMCMC_LLH_HORRIFIC:
+        case SMCMC_LLH_ASYM:
+        case SMCMC_LLH_HARD:
+            return true;
+        case SMCMC_LLH_DUMMY:
+            return dummyMode != SMCMC_DUMMY_TENSOR && errDim == n();
+        default:
+            return false;
+        }
+    }
+    void stepMany(int nsteps, int metropolis) {
+        TraceDev none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        int done = 0;
+        if (nsteps >= 2 && residentable()) {
+            PropSettings ps = settings();
+            ChainArrays a = arrays();
+            kStepsResident<<<E(), kStagedThreads, residentChainBytes(n(), covStride, upkStride), stream>>>(
+                a, ps, E(), cfg.seed, cfg.chain_offset, stepIndex, nsteps, metropolis, cfg.likelihood,
+                cfg.likelihood == SMCMC_LLH_DUMMY ? errMatrixT.get() : nullptr);
+            launched();
+            ++residentLaunches;
+            stepIndex += (uint32_t)nsteps;
+            return;
+        }
+        if (nsteps >= kGraphMinSteps && graphable()) {
+            stepOnce(metropolis, none, -1);           // sizes the buffers, uploads dirty settings
+            done = 1;
+            if (!graphStream) {
+                CUDA_CHECK(cudaStreamCreateWithFlags(&graphStream, cudaStreamNonBlocking));
+                CUDA_CHECK(cudaEventCreateWithFlags(&graphEvent, cudaEventDisableTiming));
+            }
+            dStep.reserve(1);
+            cudaStream_t user = stream;
+            kSetStep<<<1, 1, 0, user>>>(dStep.get(), stepIndex);
+            CUDA_CHECK(cudaEventRecord(graphEvent, user));
+            CUDA_CHECK(cudaStreamWaitEvent(graphStream, graphEvent, 0));
+            cudaGraph_t graph = nullptr;
+            const int64_t launchesBefore = launches;
+            const uint32_t stepBefore = stepIndex;
+            bool captured = false;
+            stream = graphStream;
+            graphMode = true;
+            if (cudaStreamBeginCapture(graphStream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                try {
+                    stepOnce(metropolis, none, -1);
+                    captured = cudaStreamEndCapture(graphStream, &graph) == cudaSuccess && graph != nullptr;
+                } catch (...) {
+                    cudaStreamEndCapture(graphStream, &graph);
+                    captured = false;
+                }
+            }
+            graphMode = false;
+            stream = user;
+            stepIndex = stepBefore;                   // the captured step has not run
+            const int64_t nodes = launches - launchesBefore;
+            launches = launchesBefore;
+            // the executable graph is kept between calls: a fresh capture of the same
+            // topology only updates its node parameters (settings, pointers), which is
+            // much cheaper than instantiating it again
+            if (captured && graphExec) {
+                cudaGraphExecUpdateResultInfo info;
+                if (cudaGraphExecUpdate(graphExec, graph, &info) != cudaSuccess) {
+                    cudaGetLastError();
+                    cudaGraphExecDestroy(graphExec);
+                    graphExec = nullptr;
+                }
+            }
+            if (captured && !graphExec && cudaGraphInstantiate(&graphExec, graph, 0) != cudaSuccess) {
+                cudaGetLastError();
+                graphExec = nullptr;
+            }
+            if (captured && graphExec) {
+                for (; done < nsteps; ++done) {
+                    CUDA_CHECK(cudaGraphLaunch(graphExec, graphStream));
+                    ++stepIndex;
+                    launches += nodes;
+                }
+                CUDA_CHECK(cudaEventRecord(graphEvent, graphStream));
+                CUDA_CHECK(cudaStreamWaitEvent(user, graphEvent, 0));
+            } else {
+                cudaGetLastError();                   // capture is an optimisation: fall through to the plain loop
+            }
+            if (graph) cudaGraphDestroy(graph);
+        }
+        for (; done < nsteps; ++done) stepOnce(metropolis, none, -1);
     }
 };
 
@@ -765,6 +892,11 @@ int smcmc_create(const smcmc_config* cfg, smcmc_engine** out) {
             if ((227 * 1024) / (cb + 1024) >= 4 && n < 8192 && !std::getenv("SMCMC_PROPOSE_GENERIC")) {
                 e->staged = true;
                 CUDA_CHECK(cudaFuncSetAttribute(kProposeStaged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cb));
+                const size_t rb = residentChainBytes((int)n, e->covStride, e->upkStride);
+                if (rb <= 200u * 1024u) {
+                    e->resident = true;
+                    CUDA_CHECK(cudaFuncSetAttribute(kStepsResident, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rb));
+                }
             }
         }
         e->llhProp.reserve(E);
@@ -864,6 +996,9 @@ int smcmc_destroy(smcmc_engine* e) {
     if (!e) return SMCMC_OK;
     cudaSetDevice(e->cfg.device);
     cudaDeviceSynchronize();
+    if (e->graphExec) cudaGraphExecDestroy(e->graphExec);
+    if (e->graphStream) cudaStreamDestroy(e->graphStream);
+    if (e->graphEvent) cudaEventDestroy(e->graphEvent);
     if (e->eventComm) NcclApi::get().CommDestroy(e->eventComm);
     if (e->worldComm) NcclApi::get().CommDestroy(e->worldComm);
     for (auto& pr : e->pairEvents) {
@@ -1284,8 +1419,7 @@ int smcmc_start(smcmc_engine* e, const double* x0, int32_t* ok) {
 int smcmc_step(smcmc_engine* e, int nsteps, int metropolis) {
     return guarded(e, [&]() {
         requireStarted(e);
-        TraceDev none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-        for (int s = 0; s < nsteps; ++s) e->stepOnce(metropolis, none, -1);
+        e->stepMany(nsteps, metropolis);
     });
 }
 

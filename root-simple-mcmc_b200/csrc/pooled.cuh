@@ -125,8 +125,9 @@ __global__ void kPoolFactor(PooledState ps, int n, int* ok) {
 // (:1723-1776) per chain, then the draw (:709-724) with the SHARED U.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 8)
 kProposePooled(ChainArrays a, PropSettings ps, PooledState pool, int chains, uint64_t seed,
-               uint32_t chainOffset, uint32_t step, double* zOut) {
+               uint32_t chainOffset, StepRef stepRef, double* zOut) {
     extern __shared__ double smemD[];
+    const uint32_t step = stepRef.get();
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int c = blockIdx.x * kWarpsPerBlock + warp;
@@ -290,8 +291,9 @@ __host__ __device__ inline size_t pooledTileSmem(int n) {
 
 __global__ void __launch_bounds__(kPooledTileThreads)
 kProposePooledTile(ChainArrays a, PropSettings ps, PooledState pool, int chains, uint64_t seed,
-                   uint32_t chainOffset, uint32_t step) {
+                   uint32_t chainOffset, StepRef stepRef) {
     extern __shared__ double smemD[];
+    const uint32_t step = stepRef.get();
     const int n = ps.n;
     const int ld = n + 1;                                    // padded rows: conflict-free column walks
     double* uS = smemD;                                      // n x n, the shared U

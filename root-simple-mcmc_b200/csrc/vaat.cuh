@@ -58,7 +58,8 @@ __global__ void kVaatInit(ChainArrays a, VaatArrays v, int chains, int n, int32_
 // (:40-80).  xProp already holds a copy of xAcc (device-to-device copy).
 __global__ void __launch_bounds__(128)
 kVaatPropose(ChainArrays a, VaatArrays v, PropSettings ps, int chains, uint64_t seed, uint32_t chainOffset,
-             uint32_t step) {
+             StepRef stepRef) {
+    const uint32_t step = stepRef.get();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= chains) return;
     const int n = ps.n;

@@ -67,9 +67,14 @@ def c1():
         eng.start(np.zeros(dim))
         eng.step(500)
         steps = 5000
+        os.environ["SMCMC_NO_RESIDENT"] = "1"
+        dt3 = timed(lambda: eng.step(steps), eng.sync)
+        del os.environ["SMCMC_NO_RESIDENT"]
         dt = timed(lambda: eng.step(steps), eng.sync)
         rec = {"config": "C1", "target": name, "chains": 1, "dim": dim, "steps_per_s": steps / dt,
-               "us_per_step": 1e6 * dt / steps, "bound": "latency (one chain)"}
+               "us_per_step": 1e6 * dt / steps, "bound": "latency (one chain)",
+               "kernel": "kStepsResident (all steps of the call in one launch)",
+               "steps_per_s_three_launch_step": steps / dt3}
         which = "ref" if have_ref else "orc"
         c = cc.CpuChain(which, kind, dim, 1, 0)
         if kind == 1 and which == "orc":
@@ -87,13 +92,32 @@ def c3():
     E, n, steps = 65536, 50, 100
     tri = n * (n + 1) // 2
     for name, kind in (("THorrificLogLikelihood", 2), ("TASymLogLikelihood", 3)):
+        # the reference-exact per-chain adaptation with the chain state resident in shared
+        # memory over the steps of one call (kStepsResident): not HBM-bound any more
+        for call in (100, 1000):
+            eng = smcmc_b200.Engine(kind, n, E, seed=4)
+            eng.start(np.zeros(n) if kind == 2 else np.full(n, 0.01))
+            eng.step(20)
+            dt = timed(lambda: eng.step(call), eng.sync)
+            rate = E * call / dt
+            per = ((3 * tri + 10 * n) * 8 + 256) / call
+            emit({"config": "C3", "target": name, "chains": E, "dim": n, "mode": "per-chain, resident (%d steps per launch)" % call,
+                  "kernel": "kStepsResident", "ms_per_step": 1e3 * dt / call, "chain_steps_per_s": rate,
+                  "hbm_bytes_per_chain_step": per, "hbm_gbs": rate * per / 1e9,
+                  "three_launch_algorithmic_bytes_per_chain_step": (3 * tri + 6 * n) * 8,
+                  "equivalent_hbm_frac_of_three_launch_algorithm": rate * (3 * tri + 6 * n) * 8 / 1e9 / HBM,
+                  "acceptance": float(eng.get("acceptance").mean())})
+            eng.close()
         for pooled in (0, 16):
             eng = smcmc_b200.Engine(kind, n, E, seed=4)
             if pooled:
                 eng.prop_set(b.PROP_POOLED_EVERY, pooled)
+            else:
+                os.environ["SMCMC_NO_RESIDENT"] = "1"
             eng.start(np.zeros(n) if kind == 2 else np.full(n, 0.01))
             eng.step(20)
             dt = timed(lambda: eng.step(steps), eng.sync)
+            os.environ.pop("SMCMC_NO_RESIDENT", None)
             # per chain-step 3 n(n+1)/2 doubles (covariance read + write, U read)
             # + 6n doubles; pooled mode (4n + 8) doubles
             bytes_per = (3 * tri + 6 * n) * 8 if not pooled else (4 * n + 8) * 8

@@ -13,3 +13,10 @@ for E in (1, 8, 16, 17, 64, 256):
     eng.start(x0); eng.step(3); eng.sync()
     t = time.perf_counter(); eng.step(20); eng.sync(); dt = (time.perf_counter() - t) / 20
     print("E %4d  %.3f ms/step  %.3e pairs/s" % (E, dt * 1e3, E * N / dt), flush=True)
+    os.environ["SMCMC_GRAPH"] = "1"
+    eng.step(20); eng.sync()
+    t = time.perf_counter(); eng.step(200); eng.sync(); dt = (time.perf_counter() - t) / 200
+    del os.environ["SMCMC_GRAPH"]
+    print("        %.3f ms/step replayed from a CUDA graph (SMCMC_GRAPH=1, 200 steps, graph cached)" % (dt * 1e3), flush=True)
+    t = time.perf_counter(); eng.step(200); eng.sync(); dt = (time.perf_counter() - t) / 200
+    print("        %.3f ms/step plain loop, 200 steps" % (dt * 1e3), flush=True)
