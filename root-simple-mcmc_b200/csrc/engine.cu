@@ -709,10 +709,13 @@ struct smcmc_engine {
     }
     // The likelihood needs only the chain's own point and the proposal is the per-chain
     // adaptive one: all nsteps steps run in ONE launch with the chain's state resident in
-    // shared memory (proposal_resident.cuh).  SMCMC_NO_RESIDENT=1 keeps the step-by-step path.
+    // shared memory (proposal_resident.cuh).  SMCMC_NO_RESIDENT=1 keeps the three-launch step.
     bool residentable() const {
         if (!resident || !staged || pooledEvery > 0 || propKind != SMCMC_PROPOSAL_ADAPTIVE || timing || diagOn) return false;
         if (std::getenv("SMCMC_NO_RESIDENT")) return false;
+        // up to one wave of CTAs; a larger ensemble is served as well by the three-launch
+        // step (measured, proposal_resident.cuh).  SMCMC_RESIDENT=1 lifts the limit.
+        if (E() > 6 * smCount && !std::getenv("SMCMC_RESIDENT")) return false;
         switch (cfg.likelihood) {
         case SMCMC_LLH_UNIT_GAUSS:
         case SMCMC_LLH_HORRIFIC:
@@ -731,9 +734,9 @@ struct smcmc_engine {
         if (nsteps >= 2 && residentable()) {
             PropSettings ps = settings();
             ChainArrays a = arrays();
+            const double* errT = cfg.likelihood == SMCMC_LLH_DUMMY ? errMatrixT.get() : nullptr;
             kStepsResident<<<E(), kStagedThreads, residentChainBytes(n(), covStride, upkStride), stream>>>(
-                a, ps, E(), cfg.seed, cfg.chain_offset, stepIndex, nsteps, metropolis, cfg.likelihood,
-                cfg.likelihood == SMCMC_LLH_DUMMY ? errMatrixT.get() : nullptr);
+                a, ps, E(), cfg.seed, cfg.chain_offset, stepIndex, nsteps, metropolis, cfg.likelihood, errT);
             launched();
             ++residentLaunches;
             stepIndex += (uint32_t)nsteps;

@@ -12,8 +12,17 @@
 // bulk copies as kProposeStaged), runs the steps back to back out of shared
 // memory -- proposal, likelihood, accept, UpdateState -- and writes the state
 // back once.  HBM traffic per chain-step falls from 3 n(n+1)/2 doubles to
-// (3 n(n+1)/2 + 5 n) / nsteps doubles; the step becomes bound by the FP64 pipe
-// and by the dependent chain of the scalars.
+// (3 n(n+1)/2 + 5 n) / nsteps doubles; the step becomes bound by instruction issue
+// (about 4.5 k warp-instructions per chain-step at n = 50, a third of them the
+// 51 Philox / Box-Muller draws) and by the dependent chain of the scalars.
+//
+// Measured on B200 (profiles/r01_configs.jsonl): one chain, n = 5: 14.3 -> 2.9 us
+// per step.  For an ensemble that fills the GPU several times over the gain is
+// gone -- 65536 chains x 50 dims: 0.54 ms per step here, 0.50 ms for the
+// three-launch step, both at about half of the issue slots -- so the engine uses
+// this kernel for ensembles of up to one wave of CTAs (6 per SM) and the
+// three-launch step beyond.  A one-warp-per-chain variant (no CTA barriers, 9
+// chains per SM) was measured too: 0.57 ms, dropped.
 //
 // The arithmetic is kProposeStaged's, kSimpleLikelihood's and kAccept's,
 // operation for operation and draw for draw (same Philox slots), so a chain

@@ -95,6 +95,7 @@ def c3():
         # the reference-exact per-chain adaptation with the chain state resident in shared
         # memory over the steps of one call (kStepsResident): not HBM-bound any more
         for call in (100, 1000):
+            os.environ["SMCMC_RESIDENT"] = "1"       # beyond one wave of CTAs the engine would not choose it
             eng = smcmc_b200.Engine(kind, n, E, seed=4)
             eng.start(np.zeros(n) if kind == 2 else np.full(n, 0.01))
             eng.step(20)
@@ -108,6 +109,7 @@ def c3():
                   "equivalent_hbm_frac_of_three_launch_algorithm": rate * (3 * tri + 6 * n) * 8 / 1e9 / HBM,
                   "acceptance": float(eng.get("acceptance").mean())})
             eng.close()
+            del os.environ["SMCMC_RESIDENT"]
         for pooled in (0, 16):
             eng = smcmc_b200.Engine(kind, n, E, seed=4)
             if pooled:
