@@ -566,7 +566,7 @@ struct smcmc_engine {
             kFake2Finish<<<ceilDiv(m, 32), 32 * kFinishWarps, kFinish2SmemBytes, stream>>>(
                 fakeCounts.get(), stride, m, fakeChains.get(), fakeData.get(), xDev, n(), llhDev, histDev);
         else
-            kFakeFinish<<<ceilDiv(m, 32), 32 * kFinishWarps, 0, stream>>>(fakeCounts.get(), stride, m, fakeChains.get(),
+            kFakeFinish<<<ceilDiv(m, kFinishPoints), 32 * kFinishBinWarps, 0, stream>>>(fakeCounts.get(), stride, m, fakeChains.get(),
                                                                           fakeData.get(), llhDev, histDev);
         launched();
     }

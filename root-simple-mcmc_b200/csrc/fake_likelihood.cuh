@@ -935,24 +935,33 @@ __global__ void kFakePairsGeneric(const smcmc_event* __restrict__ ev, int64_t ne
 
 // ---------------------------------------------------------------------------
 // Counts -> bin contents -> log-likelihood (FakeLikelihood.H:51-80).
-// Block = 32 points (lane = point) x kFinishWarps warps striding the 150 bins.
+// The work is 150 x m independent (point, bin) items, each three emulated running
+// sums (seqsum.h: data-dependent loops with an FP64 division per binade) and a
+// log: latency-bound, so the kernel wants as many warps as the SMs hold.  Block =
+// kFinishPoints points x kFinishBinWarps warps; a warp covers two bins for 16
+// points (lane & 15 = point, lane >> 4 = bin parity).  4096 points: 256 CTAs x 15
+// warps (0.15 -> see DESIGN.md 4.2 for the measured time).
 // ---------------------------------------------------------------------------
-constexpr int kFinishWarps = 10;
+constexpr int kFinishWarps = 10;            // kFake2Finish
+constexpr int kFinishPoints = 16;
+constexpr int kFinishBinWarps = 15;
 
-__global__ void __launch_bounds__(32 * kFinishWarps)
+__global__ void __launch_bounds__(32 * kFinishBinWarps)
 kFakeFinish(const uint32_t* __restrict__ counts, int pointStride, int m,
             const FakeChainParams* __restrict__ chains, const double* __restrict__ data150,
             double* llhOut, double* histOut) {
-    __shared__ double term[150][33];
+    __shared__ double term[150][kFinishPoints + 1];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int point = blockIdx.x * 32 + lane;
+    const int p = lane & (kFinishPoints - 1);
+    const int sub = lane / kFinishPoints;                   // 0 or 1
+    const int point = blockIdx.x * kFinishPoints + p;
     const bool live = point < m;
     double w[4] = {0, 0, 0, 0};
     if (live) {
         for (int k = 0; k < 4; ++k) w[k] = chains[point].weight[k];
     }
-    for (int hb = warp; hb < 150; hb += kFinishWarps) {
+    for (int hb = 2 * warp + sub; hb < 150; hb += 2 * kFinishBinWarps) {
         const int h = hb / 50, b = hb - h * 50;
         double v = 0.0;
         if (live) {
@@ -981,12 +990,13 @@ kFakeFinish(const uint32_t* __restrict__ counts, int pointStride, int m,
             v = __dsub_rn(d, mc);                                       // :57
             if (d > 0.0) v = __dadd_rn(v, __dmul_rn(d, log(__ddiv_rn(mc, d))));   // :58
         }
-        term[hb][lane] = v;
+        term[hb][p] = v;
     }
     __syncthreads();
-    if (warp == 0 && live && llhOut) {
+    if (warp == 0 && sub == 0 && live && llhOut) {
         double s = 0.0;                                                 // :51,59 in bin order
-        for (int hb = 0; hb < 150; ++hb) s = __dadd_rn(s, term[hb][lane]);
+#pragma unroll 6
+        for (int hb = 0; hb < 150; ++hb) s = __dadd_rn(s, term[hb][p]);
         llhOut[point] = s;
     }
 }
