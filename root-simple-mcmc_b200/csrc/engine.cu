@@ -109,6 +109,7 @@ struct smcmc_engine {
     int covStride = 0, upkStride = 0;   // doubles per chain (whole 128-byte lines)
     bool staged = false;                // kProposeStaged (one CTA per chain) instead of kPropose
     bool resident = false;              // kStepsResident fits (whole steps out of shared memory)
+    int residentPerSm = 0;              // its CTAs per SM
     int64_t residentLaunches = 0;
 
     // ---- TProposeVAATStep (vaat.cuh) ---------------------------------------
@@ -711,11 +712,11 @@ struct smcmc_engine {
     // adaptive one: all nsteps steps run in ONE launch with the chain's state resident in
     // shared memory (proposal_resident.cuh).  SMCMC_NO_RESIDENT=1 keeps the three-launch step.
     bool residentable() const {
-        if (!resident || !staged || pooledEvery > 0 || propKind != SMCMC_PROPOSAL_ADAPTIVE || timing || diagOn) return false;
+        if (!resident || pooledEvery > 0 || propKind != SMCMC_PROPOSAL_ADAPTIVE || timing || diagOn) return false;
         if (std::getenv("SMCMC_NO_RESIDENT")) return false;
         // up to one wave of CTAs; a larger ensemble is served as well by the three-launch
         // step (measured, proposal_resident.cuh).  SMCMC_RESIDENT=1 lifts the limit.
-        if (E() > 6 * smCount && !std::getenv("SMCMC_RESIDENT")) return false;
+        if (E() > residentPerSm * smCount && !std::getenv("SMCMC_RESIDENT")) return false;
         switch (cfg.likelihood) {
         case SMCMC_LLH_UNIT_GAUSS:
         case SMCMC_LLH_HORRIFIC:
@@ -723,7 +724,9 @@ struct smcmc_engine {
         case SMCMC_LLH_HARD:
             return true;
         case SMCMC_LLH_DUMMY:
-            return dummyMode != SMCMC_DUMMY_TENSOR && errDim == n();
+            // the n^2 ordered terms are summed by one warp here: beyond n = 20 the tiled
+            // kDummyLikelihood of the three-launch step is faster (n = 100: 213 vs 461 us per step)
+            return dummyMode != SMCMC_DUMMY_TENSOR && errDim == n() && n() <= 20;
         default:
             return false;
         }
@@ -895,11 +898,13 @@ int smcmc_create(const smcmc_config* cfg, smcmc_engine** out) {
             if ((227 * 1024) / (cb + 1024) >= 4 && n < 8192 && !std::getenv("SMCMC_PROPOSE_GENERIC")) {
                 e->staged = true;
                 CUDA_CHECK(cudaFuncSetAttribute(kProposeStaged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cb));
-                const size_t rb = residentChainBytes((int)n, e->covStride, e->upkStride);
-                if (rb <= 200u * 1024u) {
-                    e->resident = true;
-                    CUDA_CHECK(cudaFuncSetAttribute(kStepsResident, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rb));
-                }
+            }
+            // kStepsResident (whole steps out of shared memory) when one chain fits an SM
+            const size_t rb = residentChainBytes((int)n, e->covStride, e->upkStride);
+            if (rb <= 200u * 1024u && n < 8192) {
+                e->resident = true;
+                e->residentPerSm = (int)std::min<size_t>(6, (227 * 1024) / (rb + 1024));
+                CUDA_CHECK(cudaFuncSetAttribute(kStepsResident, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rb));
             }
         }
         e->llhProp.reserve(E);

@@ -78,7 +78,35 @@ def _dummy(sm):
     return eng
 
 
+def _frozen(sm):
+    from smcmc_b200 import binding
+    eng = sm.Engine(sm.LLH_ASYM, 24, 50, seed=11)
+    eng.prop_set(binding.PROP_ACCEPTANCE_WINDOW, 12.0)       # UpdateProposal after 12 accepted steps
+    eng.prop_set(binding.PROP_COVARIANCE_FROZEN, 1.0)
+    eng.start(np.random.default_rng(5).uniform(-0.01, 0.01, (50, 24)))
+    return eng
+
+
+def _deweighted(sm):
+    from smcmc_b200 import binding
+    eng = sm.Engine(sm.LLH_HORRIFIC, 24, 50, seed=11)
+    eng.prop_set(binding.PROP_ACCEPTANCE_WINDOW, 12.0)
+    eng.prop_set(binding.PROP_COVARIANCE_DEWEIGHT, 0.37)     # fractional trial counts
+    eng.prop_set(binding.PROP_COVARIANCE_WINDOW, 150.0)
+    eng.start(np.random.default_rng(5).uniform(-0.01, 0.01, (50, 24)))
+    return eng
+
+
+def _asym100(sm):
+    eng = sm.Engine(sm.LLH_ASYM, 100, 6, seed=4, chain_offset=10)   # one chain per CTA, two CTAs per SM
+    eng.start(np.full(100, 0.01))
+    return eng
+
+
 @pytest.mark.parametrize("make,steps", [
+    (_frozen, (300, 60)),
+    (_deweighted, (500,)),
+    (_asym100, (900, 1)),
     (_horrific, (1500, 3, 1, 200)),       # several UpdateProposal passes per chain
     (_asym50, (400, 100)),
     (_unit_hints, (2500, 700)),           # a uniform dimension: the generic proposal loop
