@@ -940,7 +940,7 @@ __global__ void kFakePairsGeneric(const smcmc_event* __restrict__ ev, int64_t ne
 // log: latency-bound, so the kernel wants as many warps as the SMs hold.  Block =
 // kFinishPoints points x kFinishBinWarps warps; a warp covers two bins for 16
 // points (lane & 15 = point, lane >> 4 = bin parity).  4096 points: 256 CTAs x 15
-// warps (0.15 -> see DESIGN.md 4.2 for the measured time).
+// warps: 0.151 -> 0.058 ms per launch.
 // ---------------------------------------------------------------------------
 constexpr int kFinishWarps = 10;            // kFake2Finish
 constexpr int kFinishPoints = 16;
