@@ -107,6 +107,8 @@ struct smcmc_engine {
     DeviceBuffer<double> xAcc, xProp, lastPoint, center, cov, decomp, upk, llhProp;
     DeviceBuffer<uint32_t> ijTab;
     int covStride = 0, upkStride = 0;   // doubles per chain (whole 128-byte lines)
+    DeviceBuffer<double> fakeTerms;     // kFakeFinish with few points: the 150 bin terms per point
+    DeviceBuffer<unsigned int> fakeTickets;
     bool staged = false;                // kProposeStaged (one CTA per chain) instead of kPropose
     bool resident = false;              // kStepsResident fits (whole steps out of shared memory)
     int residentPerSm = 0;              // its CTAs per SM
@@ -566,9 +568,21 @@ struct smcmc_engine {
         if (cfg.likelihood == SMCMC_LLH_FAKE2)
             kFake2Finish<<<ceilDiv(m, 32), 32 * kFinishWarps, kFinish2SmemBytes, stream>>>(
                 fakeCounts.get(), stride, m, fakeChains.get(), fakeData.get(), xDev, n(), llhDev, histDev);
-        else
-            kFakeFinish<<<ceilDiv(m, kFinishPoints), 32 * kFinishBinWarps, 0, stream>>>(fakeCounts.get(), stride, m, fakeChains.get(),
-                                                                          fakeData.get(), llhDev, histDev);
+        else {
+            // few points: the bins of a point group are split over kFinishGroups CTAs
+            const int pointGroups = ceilDiv(m, kFinishPoints);
+            const bool split = pointGroups * 2 <= smCount;
+            if (split) {
+                fakeTerms.reserve((size_t)m * 150);
+                if ((size_t)pointGroups > fakeTickets.count()) {
+                    fakeTickets.reserve(smCount);
+                    CUDA_CHECK(cudaMemsetAsync(fakeTickets.get(), 0, fakeTickets.bytes(), stream));
+                }
+            }
+            kFakeFinish<<<dim3(pointGroups, split ? kFinishGroups : 1), 32 * kFinishBinWarps, 0, stream>>>(
+                fakeCounts.get(), stride, m, fakeChains.get(), fakeData.get(), llhDev, histDev,
+                split ? fakeTerms.get() : nullptr, split ? fakeTickets.get() : nullptr);
+        }
         launched();
     }
 

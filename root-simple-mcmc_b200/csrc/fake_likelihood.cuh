@@ -946,22 +946,32 @@ constexpr int kFinishWarps = 10;            // kFake2Finish
 constexpr int kFinishPoints = 16;
 constexpr int kFinishBinWarps = 15;
 
+// With few points the grid's y dimension splits the 150 bins over kFinishGroups
+// CTAs (one item per thread: the latency of ONE item instead of five); the terms
+// go through global memory and the last CTA of a point group to arrive (ticket
+// counter, reset by that CTA) adds them in bin order.
+constexpr int kFinishGroups = 5;
+
 __global__ void __launch_bounds__(32 * kFinishBinWarps)
 kFakeFinish(const uint32_t* __restrict__ counts, int pointStride, int m,
             const FakeChainParams* __restrict__ chains, const double* __restrict__ data150,
-            double* llhOut, double* histOut) {
+            double* llhOut, double* histOut, double* termScratch, unsigned int* tickets) {
     __shared__ double term[150][kFinishPoints + 1];
+    __shared__ int lastArriver;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int p = lane & (kFinishPoints - 1);
     const int sub = lane / kFinishPoints;                   // 0 or 1
     const int point = blockIdx.x * kFinishPoints + p;
     const bool live = point < m;
+    const int groups = gridDim.y;
+    const int binsPerGroup = 150 / groups;
+    const int binBase = blockIdx.y * binsPerGroup;
     double w[4] = {0, 0, 0, 0};
     if (live) {
         for (int k = 0; k < 4; ++k) w[k] = chains[point].weight[k];
     }
-    for (int hb = 2 * warp + sub; hb < 150; hb += 2 * kFinishBinWarps) {
+    for (int hb = binBase + 2 * warp + sub; hb < binBase + binsPerGroup; hb += 2 * kFinishBinWarps) {
         const int h = hb / 50, b = hb - h * 50;
         double v = 0.0;
         if (live) {
@@ -990,7 +1000,28 @@ kFakeFinish(const uint32_t* __restrict__ counts, int pointStride, int m,
             v = __dsub_rn(d, mc);                                       // :57
             if (d > 0.0) v = __dadd_rn(v, __dmul_rn(d, log(__ddiv_rn(mc, d))));   // :58
         }
-        term[hb][p] = v;
+        if (groups == 1) term[hb][p] = v;
+        else if (live) termScratch[(size_t)point * 150 + hb] = v;
+    }
+    if (groups > 1) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int ticket = atomicAdd(tickets + blockIdx.x, 1u);
+            lastArriver = ticket == (unsigned int)(groups - 1);
+            if (lastArriver) tickets[blockIdx.x] = 0;                   // ready for the next evaluation
+        }
+        __syncthreads();
+        if (!lastArriver) return;
+        __threadfence();
+        if (warp == 0 && sub == 0 && live && llhOut) {
+            const double* t = termScratch + (size_t)point * 150;
+            double s = 0.0;
+#pragma unroll 6
+            for (int hb = 0; hb < 150; ++hb) s = __dadd_rn(s, __ldcg(t + hb));
+            llhOut[point] = s;
+        }
+        return;
     }
     __syncthreads();
     if (warp == 0 && sub == 0 && live && llhOut) {
