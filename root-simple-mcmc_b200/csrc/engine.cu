@@ -231,10 +231,7 @@ struct smcmc_engine {
         }
         kDiagChains<<<ceilDiv((long long)En, 256), 256, 0, stream>>>(xAcc.get(), sc.get(), E(), n(), d, slot);
         launched();
-        const int poolBlocks = std::min(smCount * 8, ceilDiv(E(), kPoolTile));
-        kPoolAccumulate<<<poolBlocks, 256, poolAccSmem(n()), stream>>>(xAcc.get(), sc.get(), E(), n(),
-                                                                                diagPooled.get());
-        launched();
+        poolAccumulate(diagPooled.get());
     }
 
     // ---- pooled adaptation (pooled.cuh) -----------------------------------------
@@ -269,6 +266,27 @@ struct smcmc_engine {
         return p;
     }
     int poolStatCount() const { return 1 + n() + tri(); }
+    // S += the accepted points of the local chains (count, sum x, sum x x^T): Y^T Y on the
+    // FP64 tensor cores; SMCMC_POOL_ACC_SCALAR=1 keeps the scalar kernel
+    void poolAccumulate(double* stats) {
+        if (std::getenv("SMCMC_POOL_ACC_SCALAR")) {
+            const int poolBlocks = std::min(smCount * 8, ceilDiv(E(), kPoolTile));
+            kPoolAccumulate<<<poolBlocks, 256, poolAccSmem(n()), stream>>>(xAcc.get(), sc.get(), E(), n(), stats);
+        } else {
+            const int blocks = ceilDiv(n() + 1, kPaBlock);
+            const int pairs = blocks * (blocks + 1) / 2;
+            int slices = std::max(1, std::min(ceilDiv(E(), 16), ceilDiv(2 * smCount, pairs)));
+            const int perCta = ceilDiv(ceilDiv(E(), slices), 16) * 16;
+            slices = ceilDiv(E(), perCta);
+            kPoolAccumulateDmma<true><<<dim3(blocks, slices), 128, 0, stream>>>(xAcc.get(), sc.get(), E(), n(), stats, perCta);
+            if (blocks > 1) {
+                launched();
+                kPoolAccumulateDmma<false><<<dim3(pairs - blocks, slices), 128, 0, stream>>>(xAcc.get(), sc.get(), E(), n(),
+                                                                                         stats, perCta);
+            }
+        }
+        launched();
+    }
     static size_t poolAccSmem(int n) { return (size_t)kPoolTile * (n + 2) * sizeof(double); }
     // the tile kernel keeps the shared U and 32 chains in shared memory: four CTAs per SM
     bool usePooledTile() const { return !std::getenv("SMCMC_POOLED_WARP") && pooledTileSmem(n()) <= 56 * 1024; }
@@ -701,10 +719,7 @@ struct smcmc_engine {
         ++stepIndex;
         if (diagOn) diagAccumulate();
         if (pooledEvery > 0) {
-            const int poolBlocks = std::min(smCount * 8, ceilDiv(E(), kPoolTile));
-            kPoolAccumulate<<<poolBlocks, 256, poolAccSmem(n()), stream>>>(xAcc.get(), sc.get(), E(), n(),
-                                                                                    poolStats.get());
-            launched();
+            poolAccumulate(poolStats.get());
             if (stepIndex % (uint32_t)pooledEvery == 0) poolExchange();
         }
     }

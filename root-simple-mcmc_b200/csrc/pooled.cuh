@@ -92,6 +92,137 @@ kPoolAccumulate(const double* __restrict__ xAcc, const ChainScalars* __restrict_
     }
 }
 
+// The same accumulation on the FP64 tensor cores.  With y = (1, x_0 .. x_{n-1}) per
+// chain (y = 0 for a chain that is not running) the statistics are the lower
+// triangle of S = Y^T Y, a (n+1) x (n+1) x E GEMM whose long dimension is the
+// chains: 3.4e8 flop for C3 (65536 chains x 50 dims), nothing for the DMMA pipe.
+// mma.sync.m8n8k4.f64 takes A(row g, k q) and B(k q, column g) from lane 4g+q:
+// with k = chain and row/column = statistic BOTH fragments are y[chain q][8t + g],
+// so a warp feeds the tensor cores straight from global memory -- no shared
+// memory, no CTA barrier in the loop: per group of 4 chains a lane loads 7 values
+// (a block of 56 statistics; 4 x 64 contiguous bytes per load instruction), the
+// next group's loads are in flight while the 28 (diagonal block: lower triangle)
+// or 49 DMMAs of this group issue.  Blocks of 56 statistics, block pairs
+// (bi >= bj) on blockIdx.x, chain slices on blockIdx.y, the four warps of a CTA on
+// quarter slices; their fragments are summed through shared memory and go to
+// `stats` with one FP64 atomic per entry and CTA (packing as kPoolAccumulate).
+// The count S[0][0] is a sum of ones: exact.
+constexpr int kPaBlock = 56;                // statistics per block = 7 DMMA tiles
+
+__device__ __forceinline__ void poolDmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// y[chain][y0 + 8 t + g], t = 0..6, for this lane's chain (c = group + q)
+__device__ __forceinline__ void poolLoadFragment(double (&f)[7], const double* __restrict__ xAcc,
+                                                 const ChainScalars* __restrict__ sc, int n, int c, int cLast,
+                                                 int y0, int g) {
+    const bool live = c < cLast && sc[c].started != 0;
+    const double* xr = xAcc + (size_t)c * n;
+#pragma unroll
+    for (int t = 0; t < 7; ++t) {
+        const int y = y0 + 8 * t + g;
+        f[t] = (!live || y > n) ? 0.0 : (y == 0 ? 1.0 : xr[y - 1]);
+    }
+}
+
+template <bool kDiag>
+__device__ __forceinline__ void poolWarpTiles(const double* __restrict__ xAcc, const ChainScalars* __restrict__ sc,
+                                              int n, int a0, int b0, int cFirst, int cLast, int lane,
+                                              double* red, int warp) {
+    constexpr int kTiles = kDiag ? 28 : 49;
+    const int g = lane >> 2, q = lane & 3;
+    double acc[kTiles][2];
+#pragma unroll
+    for (int t = 0; t < kTiles; ++t) acc[t][0] = acc[t][1] = 0.0;
+    double af[7], bf[7], an[7], bn[7];
+    if (cFirst < cLast) {
+        poolLoadFragment(af, xAcc, sc, n, cFirst + q, cLast, a0, g);
+        if (!kDiag) poolLoadFragment(bf, xAcc, sc, n, cFirst + q, cLast, b0, g);
+    }
+    for (int c0 = cFirst; c0 < cLast; c0 += 4) {
+        if (c0 + 4 < cLast) {
+            poolLoadFragment(an, xAcc, sc, n, c0 + 4 + q, cLast, a0, g);
+            if (!kDiag) poolLoadFragment(bn, xAcc, sc, n, c0 + 4 + q, cLast, b0, g);
+        }
+#pragma unroll
+        for (int ta = 0; ta < 7; ++ta)
+#pragma unroll
+            for (int tb = 0; tb < 7; ++tb) {
+                if (kDiag && tb > ta) continue;
+                const int idx = kDiag ? ta * (ta + 1) / 2 + tb : ta * 7 + tb;
+                poolDmma(acc[idx][0], acc[idx][1], af[ta], kDiag ? af[tb] : bf[tb]);
+            }
+#pragma unroll
+        for (int t = 0; t < 7; ++t) {
+            af[t] = an[t];
+            if (!kDiag) bf[t] = bn[t];
+        }
+    }
+    // the warps of the CTA take turns adding their fragments (same lane, same slot)
+    for (int w = 0; w < 4; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int t = 0; t < kTiles; ++t) {
+                double* r = red + (t * 32 + lane) * 2;
+                if (w == 0) { r[0] = acc[t][0]; r[1] = acc[t][1]; }
+                else { r[0] += acc[t][0]; r[1] += acc[t][1]; }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// kDiag: blockIdx.x = diagonal block (bi = bj); otherwise blockIdx.x enumerates the
+// pairs bi > bj row by row.  Two kernels so that the diagonal one (the only one
+// for n < 56) keeps its 28 accumulator tiles in registers.
+template <bool kDiag>
+__global__ void __launch_bounds__(128, kDiag ? 3 : 2)
+kPoolAccumulateDmma(const double* __restrict__ xAcc, const ChainScalars* __restrict__ sc, int chains, int n,
+                    double* stats, int chainsPerCta) {
+    __shared__ double red[(kDiag ? 28 : 49) * 64];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int bi = blockIdx.x, bj = blockIdx.x;
+    if (!kDiag) {
+        bi = 1;
+        int rest = blockIdx.x;
+        while (rest >= bi) { rest -= bi; ++bi; }
+        bj = rest;
+    }
+    const int a0 = bi * kPaBlock, b0 = bj * kPaBlock;
+    constexpr bool diagonal = kDiag;
+    const int first = blockIdx.y * chainsPerCta;
+    const int last = min(chains, first + chainsPerCta);
+    const int perWarp = ((chainsPerCta + 15) / 16) * 4;                 // a multiple of 4 chains
+    const int wFirst = min(last, first + warp * perWarp), wLast = min(last, wFirst + perWarp);
+    poolWarpTiles<kDiag>(xAcc, sc, n, a0, b0, wFirst, wLast, lane, red, warp);
+    // C fragment of tile (ta, tb): row g, columns 2q and 2q+1; the lower triangle goes out
+    const int tiles = diagonal ? 28 : 49;
+    for (int e = tid; e < tiles * 64; e += 128) {
+        const int t = e >> 6, l = (e >> 1) & 31, h = e & 1;
+        int ta, tb;
+        if (diagonal) {
+            ta = 0;
+            int r = t;
+            while (r > ta) { r -= ta + 1; ++ta; }
+            tb = r;
+        } else {
+            ta = t / 7;
+            tb = t - ta * 7;
+        }
+        const int ya = a0 + ta * 8 + (l >> 2), yb = b0 + tb * 8 + 2 * (l & 3) + h;
+        const double v = red[e];
+        if (ya > n || yb > ya || v == 0.0) continue;
+        int k;
+        if (ya == 0) k = 0;                                     // count
+        else if (yb == 0) k = ya;                               // sum x_{ya-1}
+        else k = 1 + n + (ya - 1) * ya / 2 + (yb - 1);          // sum x_i x_j, j <= i
+        atomicAdd(&stats[k], v);
+    }
+}
+
 // One warp: S -> mean, covariance, trace, U.  Keeps the previous U when the
 // pooled covariance is not (yet) positive definite.  ok[0] = 1 on success.
 __global__ void kPoolFactor(PooledState ps, int n, int* ok) {

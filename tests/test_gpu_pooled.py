@@ -88,3 +88,34 @@ def test_pooled_tensor_path_matches_the_warp_path():
     assert np.allclose(runs[0]["points"], runs[1]["points"], rtol=1e-10, atol=1e-12)
     assert np.allclose(runs[0]["step_rms"], runs[1]["step_rms"], rtol=1e-10)
     assert runs[0]["accepted"].mean() > 0.02
+
+
+@pytest.mark.parametrize("n,E", [(8, 2048), (50, 5001), (130, 384)])
+def test_tensor_core_accumulation_matches_the_scalar_kernel(monkeypatch, n, E):
+    """kPoolAccumulateDmma (S = Y^T Y on the FP64 tensor cores, lower-triangular
+    64 x 64 tile pairs, chains sliced over CTAs) against kPoolAccumulate
+    (SMCMC_POOL_ACC_SCALAR=1) and against numpy on the traced points.  One exchange
+    at the last step: the chains are the same in both runs."""
+    import smcmc_b200
+    from smcmc_b200 import binding
+    steps = 24
+    runs = {}
+    for scalar in (0, 1):
+        if scalar:
+            monkeypatch.setenv("SMCMC_POOL_ACC_SCALAR", "1")
+        else:
+            monkeypatch.delenv("SMCMC_POOL_ACC_SCALAR", raising=False)
+        eng = smcmc_b200.Engine(smcmc_b200.LLH_UNIT_GAUSS, n, E, seed=17)
+        eng.prop_set(binding.PROP_POOLED_EVERY, steps)
+        x0 = np.random.default_rng(3).normal(0, 1, (E, n))
+        assert eng.start(x0).all()
+        tr = eng.step_trace(steps, want=("accepted", "points"))
+        runs[scalar] = {"points": tr["points"], "count": eng.get("pooled_count")[0], "mean": eng.get("pooled_mean"),
+                        "cov": eng.get("pooled_covariance")}
+    assert np.array_equal(runs[0]["points"], runs[1]["points"])
+    assert runs[0]["count"] == runs[1]["count"] == E * steps
+    pts = runs[0]["points"].reshape(-1, n)
+    assert np.allclose(runs[0]["mean"], pts.mean(axis=0), rtol=1e-11, atol=1e-13)
+    assert np.allclose(runs[0]["mean"], runs[1]["mean"], rtol=1e-11, atol=1e-13)
+    scale = np.abs(runs[1]["cov"]).max()
+    assert np.allclose(runs[0]["cov"], runs[1]["cov"], rtol=1e-9, atol=1e-11 * scale)
