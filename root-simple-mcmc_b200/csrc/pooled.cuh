@@ -483,28 +483,31 @@ kProposePooledTile(ChainArrays a, PropSettings ps, PooledState pool, int chains,
     for (int k = tid; k < nc * n; k += kPooledTileThreads) {
         const int c = k / n, i = k - c * n;
         if (!(ps.anyUniform && ps.type[i] == 1)) zr[c * ld + i] = __dmul_rn(sig[c], zr[c * ld + i]);   // fSigma*r
+        if (!isnan(sig[c])) a.lastPoint[(size_t)c0 * n + k] = cur[c * ld + i];                         // :1829-1830
     }
     __syncthreads();
-    // ---- one thread per (chain, column): x'_j = x_j + sum_{i<=j} (fSigma r_i) U(i,j) ----
-    for (int k = tid; k < nc * n; k += kPooledTileThreads) {
-        const int c = k / n, j = k - c * n;
+    // ---- one thread per (chain, column): x'_j = x_j + sum_{i<=j} (fSigma r_i) U(i,j), i ascending.
+    // Column-major over the tile: the 32 lanes of a warp hold the SAME column j of 32 chains,
+    // so a warp runs exactly j+1 terms (with consecutive columns in a warp it waited for its
+    // longest column, twice the average), U(i,j) is one broadcast read and the chains' draws
+    // sit in different banks (row stride n+1).
+    for (int k = tid; k < kPooledTileChains * n; k += kPooledTileThreads) {
+        const int j = k / kPooledTileChains, c = k - j * kPooledTileChains;
+        if (c >= nc) continue;
         const double* z = zr + c * ld;
         const double x = cur[c * ld + j];
         double p = x;
         if (ps.anyUniform && ps.type[j] == 1) {
             p = z[j];
         } else if (!ps.anyUniform) {
+            const double* u = uS + j;
 #pragma unroll 4
-            for (int i = 0; i <= j; ++i) p = __dadd_rn(p, __dmul_rn(z[i], uS[i * n + j]));
+            for (int i = 0; i <= j; ++i) p = __dadd_rn(p, __dmul_rn(z[i], u[i * n]));
         } else {
             for (int i = 0; i <= j; ++i)
                 if (ps.type[i] != 1) p = __dadd_rn(p, __dmul_rn(z[i], uS[i * n + j]));
         }
-        const bool run = !isnan(sig[c]);
-        if (run) {
-            a.xProp[(size_t)c0 * n + k] = p;
-            a.lastPoint[(size_t)c0 * n + k] = x;                          // :1829-1830
-        }
+        if (!isnan(sig[c])) a.xProp[(size_t)(c0 + c) * n + j] = p;
         const double d = __dsub_rn(p, x);
         dif[c * ld + j] = __dmul_rn(d, d);
     }
