@@ -21,6 +21,7 @@
 #include "proposal.cuh"
 #include "proposal_staged.cuh"
 #include "proposal_resident.cuh"
+#include "accept_local.cuh"
 #include "simple_likelihoods.cuh"
 #include "unbinned_likelihood.cuh"
 #include "vaat.cuh"
@@ -707,10 +708,17 @@ struct smcmc_engine {
         else
             kPropose<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a, ps, E(), cfg.seed, cfg.chain_offset, stepRef());
         launched();
-        evaluate(xProp.get(), E(), llhProp.get(), nullptr);
-        kAccept<<<ceilDiv(E(), kAcceptThreads), kAcceptThreads, 0, stream>>>(a, ps, E(), llhProp.get(), cfg.seed, cfg.chain_offset,
-                                                            stepRef(), metropolis, tr, traceStep,
-                                                            propKind == SMCMC_PROPOSAL_VAAT ? (const int*)vState.get() : nullptr);
+        const int* acceptSlot = propKind == SMCMC_PROPOSAL_VAAT ? (const int*)vState.get() : nullptr;
+        if (traceStep < 0 && acceptLocal()) {
+            // chain-local likelihood, no trace: likelihood + Metropolis rule in one launch (accept_local.cuh)
+            kAcceptLocal<<<ceilDiv(E(), 32 * kAcceptLocalWarps), 32 * kAcceptLocalWarps, acceptLocalSmem(n()), stream>>>(
+                a, ps, E(), cfg.likelihood, cfg.seed, cfg.chain_offset, stepRef(), metropolis, acceptSlot);
+        } else {
+            evaluate(xProp.get(), E(), llhProp.get(), nullptr);
+            kAccept<<<ceilDiv(E(), kAcceptThreads), kAcceptThreads, 0, stream>>>(a, ps, E(), llhProp.get(), cfg.seed,
+                                                                                 cfg.chain_offset, stepRef(), metropolis, tr,
+                                                                                 traceStep, acceptSlot);
+        }
         launched();
         if (graphMode) {
             kBumpStep<<<1, 1, 0, stream>>>(dStep.get());
@@ -736,6 +744,26 @@ struct smcmc_engine {
     bool graphable() const {
         const char* g = std::getenv("SMCMC_GRAPH");
         return g && g[0] == '1' && pooledEvery == 0 && !eventComm && !timing && !diagOn;
+    }
+    // kAcceptLocal instead of likelihood kernel + kAccept (SMCMC_NO_ACCEPT_LOCAL=1: the two launches)
+    bool acceptLocalReady = false;
+    bool acceptLocal() {
+        switch (cfg.likelihood) {
+        case SMCMC_LLH_UNIT_GAUSS:
+        case SMCMC_LLH_HORRIFIC:
+        case SMCMC_LLH_ASYM:
+        case SMCMC_LLH_HARD:
+            break;
+        default:
+            return false;
+        }
+        if (timing || acceptLocalSmem(n()) > 160u * 1024u || std::getenv("SMCMC_NO_ACCEPT_LOCAL")) return false;
+        if (!acceptLocalReady) {
+            CUDA_CHECK(cudaFuncSetAttribute(kAcceptLocal, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)acceptLocalSmem(n())));
+            acceptLocalReady = true;
+        }
+        return true;
     }
     // The likelihood needs only the chain's own point and the proposal is the per-chain
     // adaptive one: all nsteps steps run in ONE launch with the chain's state resident in
