@@ -202,7 +202,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_b200(args):
@@ -440,9 +440,18 @@ def run_b200(args):
     }
     if cpu_desc:
         line["cpu_baseline"] = dict(cpu_desc, value=cpu_value, unit="steps/s")
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_RESULT_OUT = None
+
+
+def emit(line):
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -458,6 +467,13 @@ def main():
     ap.add_argument("--no-streaming", action="store_true",
                     help="skip the 1-chain x 16.8M-event streaming measurement (roofline.hbm_streaming)")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result: anything else that writes to file
+    # descriptor 1 (NCCL prints its version banner there when the first communicator is
+    # made, child processes inherit it) is sent to stderr; emit() writes to the saved descriptor
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
