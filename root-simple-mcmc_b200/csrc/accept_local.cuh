@@ -37,6 +37,9 @@ kAcceptLocal(ChainArrays a, PropSettings ps, int chains, int llhKind, uint64_t s
     if (c0 >= chains) return;
     const int nc = min(32, chains - c0);
     const double* src = a.xProp + (size_t)c0 * n;
+    // (row, column) by division: an incremental walk would chain the iterations and leave
+    // one load in flight at a time (measured: 26 -> 39 us per launch on C3)
+#pragma unroll 4
     for (int k = lane; k < nc * n; k += 32) {
         const int r = k / n, i = k - r * n;
         tile[r * ld + i] = src[k];

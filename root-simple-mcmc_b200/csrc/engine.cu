@@ -276,7 +276,8 @@ struct smcmc_engine {
         } else {
             const int blocks = ceilDiv(n() + 1, kPaBlock);
             const int pairs = blocks * (blocks + 1) / 2;
-            int slices = std::max(1, std::min(ceilDiv(E(), 16), ceilDiv(2 * smCount, pairs)));
+            // three CTAs per SM (168 registers): the loop is bound by load and DMMA latency
+            int slices = std::max(1, std::min(ceilDiv(E(), 16), ceilDiv(3 * smCount, pairs)));
             const int perCta = ceilDiv(ceilDiv(E(), slices), 16) * 16;
             slices = ceilDiv(E(), perCta);
             kPoolAccumulateDmma<true><<<dim3(blocks, slices), 128, 0, stream>>>(xAcc.get(), sc.get(), E(), n(), stats, perCta);
