@@ -117,6 +117,7 @@ struct smcmc_engine {
 
     // ---- TProposeVAATStep (vaat.cuh) ---------------------------------------
     int propKind = SMCMC_PROPOSAL_ADAPTIVE;
+    bool vaatSynced = false;            // xProp equals xAcc except in the last moved coordinate (vaat.cuh)
     std::vector<double> gaussSigma;     // SetGaussian's argument as given (TProposeVAATStep keeps sigma, not sigma^2)
     int vaatWindow = -1;                // fAcceptanceWindow (int; InitializeState forces 100, TProposeVAATStep.H:208)
     DeviceBuffer<double> vSigma, vAcceptance;
@@ -701,7 +702,10 @@ struct smcmc_engine {
             kProposePooled<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a, ps, pooled(), E(), cfg.seed,
                                                                           cfg.chain_offset, stepRef(), nullptr);
         else if (propKind == SMCMC_PROPOSAL_VAAT) {
-            CUDA_CHECK(cudaMemcpyAsync(xProp.get(), xAcc.get(), sizeof(double) * E() * n(), cudaMemcpyDeviceToDevice, stream));   // :52
+            if (!vaatSynced) {   // :52 -- once; afterwards kVaatPropose restores the one coordinate that moved
+                CUDA_CHECK(cudaMemcpyAsync(xProp.get(), xAcc.get(), sizeof(double) * E() * n(), cudaMemcpyDeviceToDevice, stream));
+                vaatSynced = true;
+            }
             kVaatPropose<<<ceilDiv(E(), 128), 128, 0, stream>>>(a, vaatArrays(), ps, E(), cfg.seed, cfg.chain_offset, stepRef());
         } else if (staged)
             kProposeStaged<<<E(), kStagedThreads, stagedChainBytes(n(), covStride, upkStride), stream>>>(
@@ -1444,6 +1448,7 @@ int smcmc_start(smcmc_engine* e, const double* x0, int32_t* ok) {
     return guarded(e, [&]() {
         if (!x0) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null starting points");
         const size_t bytes = sizeof(double) * e->E() * e->n();
+        e->vaatSynced = false;
         CUDA_CHECK(cudaMemcpyAsync(e->xAcc.get(), x0, bytes, cudaMemcpyHostToDevice, e->stream));   // :247-256
         CUDA_CHECK(cudaMemcpyAsync(e->xProp.get(), e->xAcc.get(), bytes, cudaMemcpyDeviceToDevice, e->stream));
         e->evaluate(e->xProp.get(), e->E(), e->llhProp.get(), nullptr);                             // :258
@@ -1574,6 +1579,7 @@ int smcmc_restore_state(smcmc_engine* e, const smcmc_saved_state* in, int32_t* m
             CUDA_CHECK(cudaMemcpyAsync(b.get(), src, E * 4, cudaMemcpyHostToDevice, e->stream));
             return b.get();
         };
+        e->vaatSynced = false;
         CUDA_CHECK(cudaMemcpyAsync(e->xAcc.get(), in->accepted, E * n * 8, cudaMemcpyHostToDevice, e->stream));
         CUDA_CHECK(cudaMemcpyAsync(e->center.get(), in->central_point, E * n * 8, cudaMemcpyHostToDevice, e->stream));
         CUDA_CHECK(cudaMemcpy2DAsync(e->cov.get(), (size_t)e->covStride * 8, in->covariance, tri * 8, tri * 8, E,

@@ -55,7 +55,11 @@ __global__ void kVaatInit(ChainArrays a, VaatArrays v, int chains, int n, int32_
 }
 
 // The head of TSimpleMCMC::Step (:376-406) with TProposeVAATStep::operator()
-// (:40-80).  xProp already holds a copy of xAcc (device-to-device copy).
+// (:40-80).  The functor starts from a copy of the accepted point (:52) and moves
+// ONE coordinate.  The engine copies xAcc into xProp once (Start / Restore); from
+// then on xProp differs from xAcc at most in the coordinate of the previous step
+// (when that step was rejected), which this kernel puts back before it moves the
+// next one -- 8 bytes per chain instead of a copy of the whole ensemble per step.
 __global__ void __launch_bounds__(128)
 kVaatPropose(ChainArrays a, VaatArrays v, PropSettings ps, int chains, uint64_t seed, uint32_t chainOffset,
              StepRef stepRef) {
@@ -74,6 +78,8 @@ kVaatPropose(ChainArrays a, VaatArrays v, PropSettings ps, int chains, uint64_t 
     uint32_t slot = 0;
 
     s.totalSteps += 1;                                                     // :376
+    if (st.lastIndex >= 0)                                                 // :52, see above
+        a.xProp[(size_t)c * n + st.lastIndex] = a.xAcc[(size_t)c * n + st.lastIndex];
 
     // ---- UpdateState, TProposeVAATStep.H:216-254 ---------------------------
     const double value = s.accLlh;

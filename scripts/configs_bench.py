@@ -172,9 +172,10 @@ def vaat():
         eng.start(np.zeros(n) if kind == 2 else np.full(n, 0.01))
         eng.step(50)
         dt = timed(lambda: eng.step(steps), eng.sync)
-        # per chain-step: the point is copied (2 n doubles), the likelihood reads it (n), the accept
-        # writes it back on acceptance (<= 2 n); the proposal itself touches O(1) entries
-        bytes_per = 5 * n * 8
+        # per chain-step: the likelihood reads the proposed point (n doubles), the 128-byte scalar
+        # record is read and written twice, the proposal touches O(1) entries; accepted rows
+        # (a few per cent here) are copied back (2 n)
+        bytes_per = n * 8 + 4 * 128
         rate = E * steps / dt
         emit({"config": "VAAT (8f rank 4)", "target": name, "chains": E, "dim": n, "proposal": "TProposeVAATStep",
               "ms_per_step": 1e3 * dt / steps, "chain_steps_per_s": rate, "algorithmic_bytes_per_chain_step": bytes_per,
