@@ -64,6 +64,10 @@ struct HmcHost {
     DeviceBuffer<double> llh, fdWork, fdLlh, avgPts, avgLlh;
     DeviceBuffer<HmcScalars> sc;
     DeviceBuffer<int> leapSteps, counters, updateList;
+    // deferred fEXXT update (hmc.cuh, kHmcExxtFlush): 0 = every step
+    DeviceBuffer<double> ring, ringT, exxtDiag;
+    DeviceBuffer<int> pending;
+    int deferK = 0, sinceFlush = 0;
     int* hostCounters = nullptr;     // pinned
     ~HmcHost() {
         if (hostCounters) cudaFreeHost(hostCounters);

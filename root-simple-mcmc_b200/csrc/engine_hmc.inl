@@ -21,6 +21,21 @@ void hmcAllocate(smcmc_engine* e) {
     h.exxt.reserve(E * tri);
     h.exxtT.reserve(E);
     CUDA_CHECK(cudaMemset(h.exxtT.get(), 0xFF, E * sizeof(double)));
+    // fEXXT is rewritten once per deferK steps instead of every step when the triangles of the
+    // ensemble are larger than the L2 can hold (SMCMC_HMC_DEFER=k forces k, 0 = every step)
+    h.deferK = (E * tri * sizeof(double) >= (256u << 20)) ? 16 : 0;
+    if (const char* k = std::getenv("SMCMC_HMC_DEFER")) h.deferK = std::max(0, std::min(64, atoi(k)));
+    if (h.deferK > 0) {
+        h.ring.reserve(E * h.deferK * n);
+        h.ringT.reserve(E * h.deferK);
+        h.pending.reserve(E);
+        h.exxtDiag.reserve(E * n);
+        CUDA_CHECK(cudaMemset(h.pending.get(), 0, h.pending.bytes()));
+        CUDA_CHECK(cudaMemset(h.exxtDiag.get(), 0, h.exxtDiag.bytes()));
+        const size_t flushSmem = (size_t)h.deferK * (n + 3) * sizeof(double);
+        if (flushSmem > 48 * 1024)
+            CUDA_CHECK(cudaFuncSetAttribute(kHmcExxtFlush, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)flushSmem));
+    }
     h.llh.reserve(E);
     h.sc.reserve(E);
     h.leapSteps.reserve(E);
@@ -51,6 +66,11 @@ HmcArrays hmcArrays(smcmc_engine* e) {
     a.average = h.average.get();
     a.exxt = h.exxt.get();
     a.exxtT = h.exxtT.get();
+    a.ring = h.ring.get();
+    a.ringT = h.ringT.get();
+    a.pending = h.pending.get();
+    a.exxtDiag = h.exxtDiag.get();
+    a.deferK = h.deferK;
     a.estErr = h.keepError ? h.estErr.get() : nullptr;
     a.repairedDiag = h.repairedDiag.get();
     a.sc = h.sc.get();
@@ -151,6 +171,23 @@ int hmcReadCounter(smcmc_engine* e, int which) {
     return h.hostCounters[which];
 }
 
+// apply the recorded UpdateCovariance calls to fEXXT: of every chain (list == nullptr) or of
+// the `count` chains of `list` (hmc.cuh, kHmcExxtFlush)
+void hmcFlushExxt(smcmc_engine* e, const int* list, int count) {
+    HmcHost& h = e->hmc;
+    if (h.deferK <= 0 || count <= 0) return;
+    HmcArrays a = hmcArrays(e);
+    const int n = e->n();
+    const long long tri = (long long)n * (n + 1) / 2;
+    const int perZ = std::min(count, 32768);
+    dim3 grid(ceilDiv(tri, kExxtPerBlock), perZ, ceilDiv(count, perZ));
+    kHmcExxtFlush<<<grid, kExxtThreads, (size_t)h.deferK * (n + 3) * sizeof(double), e->stream>>>(a, n, count, list);
+    e->launched();
+    kHmcExxtFlushDone<<<ceilDiv(count, 256), 256, 0, e->stream>>>(a, count, list);
+    e->launched();
+    if (!list) h.sinceFlush = 0;
+}
+
 void hmcStepOnce(smcmc_engine* e, int type, const HmcTraceDev& tr, int traceStep) {
     HmcHost& h = e->hmc;
     const HmcGradientMode mode = hmcResolveGradient(e, type);
@@ -174,7 +211,9 @@ void hmcStepOnce(smcmc_engine* e, int type, const HmcTraceDev& tr, int traceStep
     e->evaluate(h.qProp.get(), E, h.llh.get(), nullptr);                  // :327
     kHmcPost<<<blocks, threads, smem, e->stream>>>(a, n, E, h.llh.get(), 1000000.0 /* fCovarianceWindow :134 */);
     e->launched();
-    {
+    if (h.deferK > 0) {
+        if (++h.sinceFlush >= h.deferK) hmcFlushExxt(e, nullptr, E);     // :678-686, deferK steps at once
+    } else {
         const long long tri = (long long)n * (n + 1) / 2;
         const int perZ = std::min(E, 32768);
         dim3 grid(ceilDiv(tri, kExxtPerBlock), perZ, ceilDiv(E, perZ));
@@ -183,6 +222,7 @@ void hmcStepOnce(smcmc_engine* e, int type, const HmcTraceDev& tr, int traceStep
     }
     const int updates = hmcReadCounter(e, 1);
     if (updates > 0) {
+        hmcFlushExxt(e, h.updateList.get(), updates);                     // UpdateErrorMatrix reads fEXXT
         h.avgPts.reserve((size_t)updates * n);
         h.avgLlh.reserve(updates);
         kHmcGatherAverage<<<ceilDiv((long long)updates * n, 256), 256, 0, e->stream>>>(a, n, updates, h.avgPts.get());
@@ -237,6 +277,7 @@ int smcmc_hmc_start(smcmc_engine* e, const double* x0) {
         // scratch for UpdateErrorMatrix: eigenvalues and the inverse share the engine's slots
         CUDA_CHECK(cudaMemcpyAsync(h.qAcc.get(), x0, E * n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
         e->evaluate(h.qAcc.get(), (int)E, h.llh.get(), nullptr);           // SetPosition, :221
+        h.sinceFlush = 0;                                                  // kHmcStart empties the rings
         kHmcStart<<<ceilDiv((long long)E, kWarpsPerBlock), kWarpsPerBlock * 32, 0, e->stream>>>(
             hmcArrays(e), (int)n, (int)E, h.llh.get(), h.firstStart ? 1 : 0);
         e->launched();
@@ -363,6 +404,8 @@ int smcmc_hmc_get(smcmc_engine* e, int field, void* dst, size_t bytes) {
             // the first step (:254-260).
             need(E * n * n * 8);
             std::vector<double> ex(E * tri), avg(E * n), diag(E * n);
+            hmcFlushExxt(e, nullptr, (int)E);
+            CUDA_CHECK(cudaStreamSynchronize(e->stream));
             CUDA_CHECK(cudaMemcpy(ex.data(), h.exxt.get(), ex.size() * 8, cudaMemcpyDeviceToHost));
             CUDA_CHECK(cudaMemcpy(avg.data(), h.average.get(), avg.size() * 8, cudaMemcpyDeviceToHost));
             CUDA_CHECK(cudaMemcpy(diag.data(), h.repairedDiag.get(), diag.size() * 8, cudaMemcpyDeviceToHost));

@@ -58,10 +58,14 @@ def check_against(eng, tr, c, want_tr, want_scalars, want_arrays, keep_error):
         assert np.array_equal(eng.hmc_get("error_matrix")[c], want_arrays["error"], equal_nan=True)
 
 
+@pytest.mark.parametrize("defer", ["0", "5", "16"])
 @pytest.mark.parametrize("name", sorted(HMC_GOLDEN))
-def test_hmc_golden_chain(name):
+def test_hmc_golden_chain(monkeypatch, name, defer):
     """Chain `id` of a 4-chain ensemble equals the golden run of the reference
-    build for that chain id."""
+    build for that chain id -- with fEXXT rewritten every step (defer 0) and with
+    the recorded UpdateCovariance calls applied 5 or 16 at a time (kHmcExxtFlush;
+    large ensembles use 16 by default)."""
+    monkeypatch.setenv("SMCMC_HMC_DEFER", defer)
     g = golden("hmc.npz")
     want = golden_chain(g, name)
     cfg = HMC_GOLDEN[name]
