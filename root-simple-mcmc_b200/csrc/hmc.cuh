@@ -286,8 +286,26 @@ kHmcKickDrift(HmcArrays a, int n, int chains, int k, int countPotentials) {
     __syncwarp();
     bool reversed = false;
     if (!half) {
-        const double inner = warpSeqSum(buf, n);
-        reversed = !(inner >= 0.0);                                       // :637-638
+        // :637-638 needs only the SIGN of the reference's ordered sum of the n products.  A
+        // lane-parallel sum S and A = sum |t_i| settle it whenever |S| > 2 n u A (u = 2^-53):
+        // both summation orders are within (n-1) u A of the exact sum, so they share its sign.
+        // Otherwise (a knife edge, or a NaN) the ordered sum itself is formed.
+        double sPar = 0.0, aPar = 0.0;
+        for (int i = lane; i < n; i += 32) {
+            const double t = buf[i];
+            sPar += t;
+            aPar += fabs(t);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sPar += __shfl_xor_sync(0xffffffffu, sPar, o);
+            aPar += __shfl_xor_sync(0xffffffffu, aPar, o);
+        }
+        if (fabs(sPar) > (double)n * 2.33e-16 * aPar) reversed = sPar < 0.0;
+        else {
+            const double inner = warpSeqSum(buf, n);
+            reversed = !(inner >= 0.0);
+        }
     }
     if (lane == 0) {
         sp->gradientCount += 1;                                           // :469
@@ -649,18 +667,38 @@ kHmcExxtFlush(HmcArrays a, int n, int count, const int* __restrict__ list) {
     while ((long long)i * (i + 1) / 2 > k) --i;
     while ((long long)(i + 1) * (i + 2) / 2 <= k) ++i;
     int j = (int)(k - (long long)i * (i + 1) / 2);
-    for (; k < kEnd; k += kExxtThreads) {
-        double v = ex[k];
+    // four entries per thread and pass: four independent chains of dependent updates, and the
+    // three per-update scalars (T, T + 1, 1 / (T + 1)) are read once for the four
+    constexpr int kUnroll = 4;
+    for (; k < kEnd; k += (long long)kUnroll * kExxtThreads) {
+        double v[kUnroll];
+        int ei[kUnroll], ej[kUnroll];
+#pragma unroll
+        for (int q = 0; q < kUnroll; ++q) {
+            const long long kq = k + (long long)q * kExxtThreads;
+            v[q] = kq < kEnd ? ex[kq] : 0.0;
+            ei[q] = i;
+            ej[q] = j;
+            j += kExxtThreads;
+            while (j > i) { j -= i + 1; ++i; }
+            if (kq >= kEnd) ei[q] = ej[q] = 0;      // a staged column: the value is not stored
+        }
         for (int u = 0; u < p; ++u) {
             const double t = ts[u], t1 = ts[K + u], y = ts[2 * K + u];
-            const double r = __dmul_rn(xs[(size_t)u * n + i], xs[(size_t)u * n + j]);
-            const double w = __dadd_rn(__dmul_rn(v, t), r);
             const bool fast = t1 >= 1.0 && t1 <= 1152921504606846976.0;
-            v = fast ? divideByShared(w, t1, y) : __ddiv_rn(w, t1);
+            const double* xu = xs + (size_t)u * n;
+#pragma unroll
+            for (int q = 0; q < kUnroll; ++q) {
+                const double r = __dmul_rn(xu[ei[q]], xu[ej[q]]);
+                const double w = __dadd_rn(__dmul_rn(v[q], t), r);
+                v[q] = fast ? divideByShared(w, t1, y) : __ddiv_rn(w, t1);
+            }
         }
-        ex[k] = v;
-        j += kExxtThreads;
-        while (j > i) { j -= i + 1; ++i; }
+#pragma unroll
+        for (int q = 0; q < kUnroll; ++q) {
+            const long long kq = k + (long long)q * kExxtThreads;
+            if (kq < kEnd) ex[kq] = v[q];
+        }
     }
 }
 

@@ -13,5 +13,5 @@ eng.set_error_matrix(precision(n))
 eng.set_dummy_mode(b.DUMMY_TENSOR)
 eng.hmc_set(b.HMC_USER_GRADIENT, 1)
 eng.hmc_start(np.ones(n))
-eng.hmc_step(2); eng.sync()
+eng.hmc_step(int(os.environ.get("HMC_STEPS", "2"))); eng.sync()
 print("done")
