@@ -7,4 +7,3 @@ python scripts/prof_c3.py > /dev/null 2>&1 || exit 1
 for k in kProposePooledTile kPoolAccumulateDmma kAcceptLocal; do
   timeout 600 $NCU -k regex:$k --launch-skip 8 -o gpurun_out/prof_$k python scripts/prof_c3.py > gpurun_out/ncu_$k.log 2>&1; tail -1 gpurun_out/ncu_$k.log
 done
-T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
