@@ -275,13 +275,31 @@ kHmcKickDrift(HmcArrays a, int n, int chains, int k, int countPotentials) {
     HmcScalars* sp = a.sc + c;
     const double eps = sp->epsilon;
     const bool half = (k == 0) || (k == steps);
-    for (int i = lane; i < n; i += 32) {
-        double kick = __dmul_rn(eps, a.grad[row + i]);
-        if (half) kick = __ddiv_rn(kick, 2.0);
-        const double p = __dsub_rn(a.pProp[row + i], kick);
-        a.pProp[row + i] = p;
-        if (!half) buf[i] = __dmul_rn(p, a.p0[row + i]);                  // :635
-        if (k < steps) a.qProp[row + i] = __dadd_rn(a.qProp[row + i], __dmul_rn(eps, p));
+    // four elements per lane are loaded before any of them is stored: the arrays of HmcArrays
+    // may alias as far as the compiler knows, and a load behind a store would wait for it
+    const bool drift = k < steps;
+    for (int i0 = lane; i0 < n; i0 += 128) {
+        double g[4], pp[4], p0v[4], q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 32 * u;
+            const bool in = i < n;
+            g[u] = in ? a.grad[row + i] : 0.0;
+            pp[u] = in ? a.pProp[row + i] : 0.0;
+            p0v[u] = (in && !half) ? a.p0[row + i] : 0.0;
+            q[u] = (in && drift) ? a.qProp[row + i] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 32 * u;
+            if (i >= n) continue;
+            double kick = __dmul_rn(eps, g[u]);
+            if (half) kick = __ddiv_rn(kick, 2.0);
+            const double p = __dsub_rn(pp[u], kick);
+            a.pProp[row + i] = p;
+            if (!half) buf[i] = __dmul_rn(p, p0v[u]);                     // :635
+            if (drift) a.qProp[row + i] = __dadd_rn(q[u], __dmul_rn(eps, p));
+        }
     }
     __syncwarp();
     bool reversed = false;
