@@ -1,0 +1,24 @@
+"""bench.py's output contract, on the arm that runs without a GPU: `--impl reference`
+prints exactly ONE line on stdout, a JSON object with the keys the driver reads."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line():
+    from oracle import cpu_checkers as cc
+    assert cc.available("ref") or cc.available("orc")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--events", "20000"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["metric"].startswith("MH steps/sec") and d["unit"] == "steps/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["steps"] == 1 and d["warmup"] == 0 and d["data"] == "synthetic" and d["dtype"] == "f64"
