@@ -880,6 +880,9 @@ namespace {
 template <class F>
 int guarded(smcmc_engine* e, F f) {
     try {
+        // every entry point works on the engine's device whatever the caller's current one is
+        // (allocations come from that device's pool, launches go to a stream of that device)
+        if (e) CUDA_CHECK(cudaSetDevice(e->cfg.device));
         f();
         return SMCMC_OK;
     } catch (const Error& err) {
