@@ -942,7 +942,7 @@ __global__ void kFakePairsGeneric(const smcmc_event* __restrict__ ev, int64_t ne
 // points (lane & 15 = point, lane >> 4 = bin parity).  4096 points: 256 CTAs x 15
 // warps: 0.151 -> 0.058 ms per launch.
 // ---------------------------------------------------------------------------
-constexpr int kFinishWarps = 10;            // kFake2Finish
+constexpr int kFinishWarps = 30;            // kFake2Finish: 32 points x 30 warps over the 150 bins (was 10: 9 warps per SM)
 constexpr int kFinishPoints = 16;
 constexpr int kFinishBinWarps = 15;
 
