@@ -32,7 +32,7 @@ void hmcAllocate(smcmc_engine* e) {
         h.exxtDiag.reserve(E * n);
         CUDA_CHECK(cudaMemset(h.pending.get(), 0, h.pending.bytes()));
         CUDA_CHECK(cudaMemset(h.exxtDiag.get(), 0, h.exxtDiag.bytes()));
-        const size_t flushSmem = (size_t)h.deferK * (n + 3) * sizeof(double);
+        const size_t flushSmem = exxtFlushSmem((int)n, h.deferK);
         if (flushSmem > 48 * 1024)
             CUDA_CHECK(cudaFuncSetAttribute(kHmcExxtFlush, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)flushSmem));
     }
@@ -181,7 +181,7 @@ void hmcFlushExxt(smcmc_engine* e, const int* list, int count) {
     const long long tri = (long long)n * (n + 1) / 2;
     const int perZ = std::min(count, 32768);
     dim3 grid(ceilDiv(tri, kExxtPerBlock), perZ, ceilDiv(count, perZ));
-    kHmcExxtFlush<<<grid, kExxtThreads, (size_t)h.deferK * (n + 3) * sizeof(double), e->stream>>>(a, n, count, list);
+    kHmcExxtFlush<<<grid, kExxtThreads, exxtFlushSmem(n, h.deferK), e->stream>>>(a, n, count, list);
     e->launched();
     kHmcExxtFlushDone<<<ceilDiv(count, 256), 256, 0, e->stream>>>(a, count, list);
     e->launched();

@@ -648,18 +648,34 @@ kHmcExxtUpdate(HmcArrays a, int n, int chains) {
 // all chains every deferK steps and for the chains of the update list before
 // kHmcErrorMatrix, and before anything else reads fEXXT.  list == nullptr: chain =
 // blockIdx.y + gridDim.y * blockIdx.z; otherwise chain = list[that index].
-// Dynamic shared memory: deferK * (n + 3) doubles.
+// Dynamic shared memory: exxtFlushSmem(n, deferK).
+// one recorded update of one entry: v <- (v T + x_i x_j) / (T + 1)
+__device__ __forceinline__ double exxtApply(double v, double xi, double xj, double t, double t1, double y, bool fast) {
+    const double r = __dmul_rn(xi, xj);
+    const double w = __dadd_rn(__dmul_rn(v, t), r);
+    return fast ? divideByShared(w, t1, y) : __ddiv_rn(w, t1);
+}
+
+// Shared memory: the recorded points TRANSPOSED, xsT[i][u] with a row of deferK + 2 doubles per
+// dimension (the 16 values an entry needs from dimension i are contiguous: with a full ring of
+// 16 they are read two at a time with LDS.128 at immediate offsets, no address arithmetic per
+// update; rows of 144 bytes keep a quarter warp on different banks), then T, T + 1, 1 / (T + 1).
+__host__ __device__ inline size_t exxtFlushSmem(int n, int deferK) {
+    return ((size_t)n * (deferK + 2) + 3 * (size_t)deferK) * sizeof(double);
+}
+
 __global__ void __launch_bounds__(kExxtThreads)
 kHmcExxtFlush(HmcArrays a, int n, int count, const int* __restrict__ list) {
-    extern __shared__ double smemD[];
+    extern __shared__ __align__(16) double smemD[];
     const int idx = blockIdx.y + gridDim.y * blockIdx.z;
     if (idx >= count) return;
     const int c = list ? list[idx] : idx;
     const int p = a.pending[c];
     if (p <= 0) return;
     const int K = a.deferK;
-    double* xs = smemD;                 // [p][n]
-    double* ts = smemD + (size_t)K * n; // [K] T, [K] T + 1, [K] 1 / (T + 1)
+    const int KS = K + 2;
+    double* xsT = smemD;                        // [n][KS]
+    double* ts = smemD + (size_t)n * KS;        // [K] T, [K] T + 1, [K] 1 / (T + 1)
     const long long tri = (long long)n * (n + 1) / 2;
     const long long k0 = (long long)blockIdx.x * kExxtPerBlock;
     const long long kEnd = min(tri, k0 + kExxtPerBlock);
@@ -668,7 +684,7 @@ kHmcExxtFlush(HmcArrays a, int n, int count, const int* __restrict__ list) {
     const double* ring = a.ring + (size_t)c * K * n;
     for (int e = threadIdx.x; e < p * (iMax + 1); e += kExxtThreads) {
         const int u = e / (iMax + 1), i = e - u * (iMax + 1);
-        xs[(size_t)u * n + i] = ring[(size_t)u * n + i];
+        xsT[i * KS + u] = ring[(size_t)u * n + i];
     }
     if (threadIdx.x < p) {
         const double t = a.ringT[(size_t)c * K + threadIdx.x];
@@ -686,30 +702,44 @@ kHmcExxtFlush(HmcArrays a, int n, int count, const int* __restrict__ list) {
     while ((long long)(i + 1) * (i + 2) / 2 <= k) ++i;
     int j = (int)(k - (long long)i * (i + 1) / 2);
     // four entries per thread and pass: four independent chains of dependent updates, and the
-    // three per-update scalars (T, T + 1, 1 / (T + 1)) are read once for the four
+    // three per-update scalars are read once for the four.  (Eight per thread at two CTAs per SM
+    // measured slower, 51.6 against 40.2 ms per flush of C4: resident warps count for more.)
     constexpr int kUnroll = 4;
+    const bool fullRing = (K == 16 && p == 16);
     for (; k < kEnd; k += (long long)kUnroll * kExxtThreads) {
         double v[kUnroll];
-        int ei[kUnroll], ej[kUnroll];
+        int ri[kUnroll], rj[kUnroll];        // element offsets of the rows of x_i and x_j in xsT
 #pragma unroll
         for (int q = 0; q < kUnroll; ++q) {
             const long long kq = k + (long long)q * kExxtThreads;
-            v[q] = kq < kEnd ? ex[kq] : 0.0;
-            ei[q] = i;
-            ej[q] = j;
+            const bool in = kq < kEnd;
+            v[q] = in ? ex[kq] : 0.0;
+            ri[q] = (in ? i : 0) * KS;              // out of range: a staged row, the value is not stored
+            rj[q] = (in ? j : 0) * KS;
             j += kExxtThreads;
             while (j > i) { j -= i + 1; ++i; }
-            if (kq >= kEnd) ei[q] = ej[q] = 0;      // a staged column: the value is not stored
         }
-        for (int u = 0; u < p; ++u) {
-            const double t = ts[u], t1 = ts[K + u], y = ts[2 * K + u];
-            const bool fast = t1 >= 1.0 && t1 <= 1152921504606846976.0;
-            const double* xu = xs + (size_t)u * n;
+        if (fullRing) {
 #pragma unroll
-            for (int q = 0; q < kUnroll; ++q) {
-                const double r = __dmul_rn(xu[ei[q]], xu[ej[q]]);
-                const double w = __dadd_rn(__dmul_rn(v[q], t), r);
-                v[q] = fast ? divideByShared(w, t1, y) : __ddiv_rn(w, t1);
+            for (int u = 0; u < 16; u += 2) {
+                const double ta = ts[u], ta1 = ts[16 + u], ya = ts[32 + u];
+                const double tb = ts[u + 1], tb1 = ts[16 + u + 1], yb = ts[32 + u + 1];
+                const bool fa = ta1 >= 1.0 && ta1 <= 1152921504606846976.0;
+                const bool fb = tb1 >= 1.0 && tb1 <= 1152921504606846976.0;
+#pragma unroll
+                for (int q = 0; q < kUnroll; ++q) {
+                    const double2 xi = *reinterpret_cast<const double2*>(xsT + ri[q] + u);
+                    const double2 xj = *reinterpret_cast<const double2*>(xsT + rj[q] + u);
+                    v[q] = exxtApply(v[q], xi.x, xj.x, ta, ta1, ya, fa);
+                    v[q] = exxtApply(v[q], xi.y, xj.y, tb, tb1, yb, fb);
+                }
+            }
+        } else {
+            for (int u = 0; u < p; ++u) {
+                const double t = ts[u], t1 = ts[K + u], y = ts[2 * K + u];
+                const bool fast = t1 >= 1.0 && t1 <= 1152921504606846976.0;
+#pragma unroll
+                for (int q = 0; q < kUnroll; ++q) v[q] = exxtApply(v[q], xsT[ri[q] + u], xsT[rj[q] + u], t, t1, y, fast);
             }
         }
 #pragma unroll

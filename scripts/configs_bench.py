@@ -142,7 +142,8 @@ def c4():
     n = 500
     fp64 = b.measure_fp64_peak(0)
     prec = precision(n)
-    for E, steps, burn in ((1, 20, 5), (1024, 20, 5), (16384, 10, 3)):
+    # 32 timed steps: a whole number of deferred-fEXXT periods (16 steps) lies inside the timed region
+    for E, steps, burn in ((1, 32, 5), (1024, 32, 5), (16384, 32, 3)):
         for mode in (b.DUMMY_EXACT, b.DUMMY_TENSOR):
             eng = smcmc_b200.Engine(smcmc_b200.LLH_DUMMY, n, E, seed=5)
             eng.set_error_matrix(prec)
