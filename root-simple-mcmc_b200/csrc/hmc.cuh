@@ -705,7 +705,7 @@ kHmcExxtFlush(HmcArrays a, int n, int count, const int* __restrict__ list) {
     // three per-update scalars are read once for the four.  (Eight per thread at two CTAs per SM
     // measured slower, 51.6 against 40.2 ms per flush of C4: resident warps count for more.)
     constexpr int kUnroll = 4;
-    const bool fullRing = (K == 16 && p == 16);
+    const bool fullRing = p == K && (K == 16 || K == 8);
     for (; k < kEnd; k += (long long)kUnroll * kExxtThreads) {
         double v[kUnroll];
         int ri[kUnroll], rj[kUnroll];        // element offsets of the rows of x_i and x_j in xsT
@@ -722,8 +722,9 @@ kHmcExxtFlush(HmcArrays a, int n, int count, const int* __restrict__ list) {
         if (fullRing) {
 #pragma unroll
             for (int u = 0; u < 16; u += 2) {
-                const double ta = ts[u], ta1 = ts[16 + u], ya = ts[32 + u];
-                const double tb = ts[u + 1], tb1 = ts[16 + u + 1], yb = ts[32 + u + 1];
+                if (u >= K) break;
+                const double ta = ts[u], ta1 = ts[K + u], ya = ts[2 * K + u];
+                const double tb = ts[u + 1], tb1 = ts[K + u + 1], yb = ts[2 * K + u + 1];
                 const bool fa = ta1 >= 1.0 && ta1 <= 1152921504606846976.0;
                 const bool fb = tb1 >= 1.0 && tb1 <= 1152921504606846976.0;
 #pragma unroll
