@@ -10,7 +10,12 @@
  *   - Philox4x32-10 (Salmon et al., SC'11) keyed by the 64-bit run seed,
  *     counter = (chain, step, slot, stream);
  *   - Rndm() in the open interval (0,1) like TRandom3 (never 0, never 1);
- *   - Gaus(0,1) by Box-Muller where log / sin / cos are evaluated with
+ *   - Gaus(0,1) by Box-Muller, TWO normals per Philox block: draw slots 2k and
+ *     2k+1 are the cosine and the sine branch of the same 128 bits (one log,
+ *     one sqrt, one argument reduction for both), taken from a sub-stream of
+ *     their own (SMCMC_STREAM_NORMAL_PAIR) so that a uniform draw of slot 2k
+ *     never shares bits with the normal of slot 2k+1; log / sin / cos are
+ *     evaluated with
  *     polynomial kernels that use ONLY +,-,*,/ and sqrt, i.e. operations IEEE
  *     754 rounds identically on x86 and on sm_100a.  Every operation goes
  *     through the SMCMC_ADD/SUB/MUL/DIV macros, which on the device are the
@@ -56,6 +61,9 @@ enum {
     SMCMC_STREAM_HMC = 1,       /* momentum / epsilon / accept draws of HMC */
     SMCMC_STREAM_INPUT = 2      /* synthetic-input generators               */
 };
+/* OR-ed into the stream word of the Philox blocks that feed normal PAIRS: block
+ * `pair` of that sub-stream yields the normals of draw slots 2*pair, 2*pair+1. */
+#define SMCMC_STREAM_NORMAL_PAIR 0x100u
 
 typedef struct smcmc_u32x4 {
     uint32_t v[4];
@@ -98,11 +106,13 @@ SMCMC_HD smcmc_u32x4 smcmc_draw_bits(uint64_t seed, uint32_t chain,
                                (uint32_t)(seed >> 32));
 }
 
-/* 53 random bits -> double in the open interval (0,1):  (k + 1/2) * 2^-53.
- * Both the conversion and the scaling are exact. */
+/* 52 random bits -> double in the open interval (0,1):  (k + 1/2) * 2^-52,
+ * k < 2^52.  k + 1/2 has at most 53 significant bits, so the conversion, the
+ * sum and the scaling are all exact: the smallest value is 2^-53, the largest
+ * 1 - 2^-53, never 0 and never 1. */
 SMCMC_HD double smcmc_bits_to_open01(uint32_t hi, uint32_t lo) {
-    uint64_t k = (((uint64_t)hi << 32) | (uint64_t)lo) >> 11;
-    return SMCMC_MUL(SMCMC_ADD((double)k, 0.5), 1.1102230246251565404e-16);
+    uint64_t k = (((uint64_t)hi << 32) | (uint64_t)lo) >> 12;
+    return SMCMC_MUL(SMCMC_ADD((double)k, 0.5), 2.2204460492503130808e-16);
 }
 
 /* log(x) for finite x > 0, fdlibm-style reduction x = 2^e * m with
@@ -178,21 +188,44 @@ SMCMC_HD double smcmc_det_kcos(double x) {
     return SMCMC_ADD(w, SMCMC_ADD(SMCMC_SUB(SMCMC_SUB(1.0, w), hz), SMCMC_MUL(z, r)));
 }
 
-/* cos(2*pi*u) for u in (0,1) on the 2^-53 grid: exact octant reduction. */
-SMCMC_HD double smcmc_det_cos2pi(double u) {
+/* cos(2*pi*u) and sin(2*pi*u) for u in (0,1) on the 2^-53 grid: exact octant
+ * reduction.  `which`: 1 cosine only, 2 sine only, 3 both.
+ * octant:  0     1     2      3      4      5     6     7     (a: reduced angle)
+ * cos  :  cos a sin a -sin a -cos a -cos a -sin a sin a cos a
+ * sin  :  sin a cos a  cos a  sin a -sin a -cos a -cos a -sin a */
+SMCMC_HD void smcmc_det_sincos2pi(double u, int which, double* c, double* s) {
     const double quarter_pi = 7.85398163397448278999e-01;
     double t = SMCMC_MUL(u, 8.0);               /* exact */
     int oct = (int)t;                           /* 0..7 */
     double r = SMCMC_SUB(t, (double)oct);       /* exact, in [0,1) */
-    double c;
     if (oct & 1) r = SMCMC_SUB(1.0, r);         /* exact */
     double a = SMCMC_MUL(r, quarter_pi);        /* angle in [0, pi/4] */
-    /* octant:  0     1     2      3      4      5     6     7
-     * cos  :  cos a sin a -sin a -cos a -cos a -sin a sin a cos a */
-    if (((oct + 1) >> 1) & 1) c = smcmc_det_ksin(a);
-    else c = smcmc_det_kcos(a);
-    if (oct >= 2 && oct <= 5) c = -c;
+    const int swap = ((oct + 1) >> 1) & 1;      /* octants 1, 2, 5, 6 */
+    double ks = 0.0, kc = 0.0;
+    if (which == 3 || (which == 1) == (swap != 0)) ks = smcmc_det_ksin(a);
+    if (which == 3 || (which == 1) != (swap != 0)) kc = smcmc_det_kcos(a);
+    if (which & 1) {
+        double v = swap ? ks : kc;
+        if (oct >= 2 && oct <= 5) v = -v;
+        *c = v;
+    }
+    if (which & 2) {
+        double v = swap ? kc : ks;
+        if (oct >= 4) v = -v;
+        *s = v;
+    }
+}
+
+SMCMC_HD double smcmc_det_cos2pi(double u) {
+    double c = 0.0, s = 0.0;
+    smcmc_det_sincos2pi(u, 1, &c, &s);
     return c;
+}
+
+SMCMC_HD double smcmc_det_sin2pi(double u) {
+    double c = 0.0, s = 0.0;
+    smcmc_det_sincos2pi(u, 2, &c, &s);
+    return s;
 }
 
 /* Rndm() of draw (chain, step, slot). */
@@ -202,18 +235,37 @@ SMCMC_HD double smcmc_uniform(uint64_t seed, uint32_t chain, uint32_t step,
     return smcmc_bits_to_open01(b.v[0], b.v[1]);
 }
 
-/* Gaus(0,1) of draw (chain, step, slot): Box-Muller on the same 128 bits. */
-SMCMC_HD double smcmc_normal_from_bits(smcmc_u32x4 b) {
+/* Box-Muller on one 128-bit block: z0 = rad cos(2 pi u2), z1 = rad sin(2 pi u2),
+ * rad = sqrt(-2 log u1).  `which` as smcmc_det_sincos2pi. */
+SMCMC_HD void smcmc_normal_pair_from_bits(smcmc_u32x4 b, int which, double* z0, double* z1) {
     double u1 = smcmc_bits_to_open01(b.v[0], b.v[1]);
     double u2 = smcmc_bits_to_open01(b.v[2], b.v[3]);
     double rad = SMCMC_SQRT(SMCMC_MUL(-2.0, smcmc_det_log(u1)));
-    return SMCMC_MUL(rad, smcmc_det_cos2pi(u2));
+    double c = 0.0, s = 0.0;
+    smcmc_det_sincos2pi(u2, which, &c, &s);
+    if (which & 1) *z0 = SMCMC_MUL(rad, c);
+    if (which & 2) *z1 = SMCMC_MUL(rad, s);
 }
 
+/* The Philox block behind the normals of draw slots 2*pair and 2*pair+1. */
+SMCMC_HD smcmc_u32x4 smcmc_normal_pair_bits(uint64_t seed, uint32_t chain, uint32_t step,
+                                            uint32_t pair, uint32_t stream) {
+    return smcmc_draw_bits(seed, chain, step, pair, stream | SMCMC_STREAM_NORMAL_PAIR);
+}
+
+/* Gaus(0,1) of draw slots 2*pair (z0) and 2*pair+1 (z1) of (chain, step). */
+SMCMC_HD void smcmc_normal_pair(uint64_t seed, uint32_t chain, uint32_t step,
+                                uint32_t pair, uint32_t stream, double* z0, double* z1) {
+    smcmc_normal_pair_from_bits(smcmc_normal_pair_bits(seed, chain, step, pair, stream), 3, z0, z1);
+}
+
+/* Gaus(0,1) of draw (chain, step, slot): one branch of its pair. */
 SMCMC_HD double smcmc_normal(uint64_t seed, uint32_t chain, uint32_t step,
                              uint32_t slot, uint32_t stream) {
-    return smcmc_normal_from_bits(
-        smcmc_draw_bits(seed, chain, step, slot, stream));
+    double z0 = 0.0, z1 = 0.0;
+    smcmc_normal_pair_from_bits(smcmc_normal_pair_bits(seed, chain, step, slot >> 1, stream),
+                                (slot & 1u) ? 2 : 1, &z0, &z1);
+    return (slot & 1u) ? z1 : z0;
 }
 
 #endif

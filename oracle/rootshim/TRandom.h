@@ -20,7 +20,7 @@ public:
         if (seed == 0) { std::random_device rd; seed = rd(); }
         fEngine.seed(seed);
     }
-    // Uniform deviate in the open interval (0,1), 53 bits.
+    // Uniform deviate in the open interval (0,1), 52 bits.
     virtual double Rndm() {
         uint64_t k = fEngine();
         return smcmc_bits_to_open01((uint32_t)(k >> 32), (uint32_t)k);
@@ -32,7 +32,9 @@ public:
         smcmc_u32x4 bits;
         bits.v[0] = (uint32_t)(a >> 32); bits.v[1] = (uint32_t)a;
         bits.v[2] = (uint32_t)(b >> 32); bits.v[3] = (uint32_t)b;
-        return smcmc_normal_from_bits(bits);
+        double z0 = 0.0, z1 = 0.0;
+        smcmc_normal_pair_from_bits(bits, 1, &z0, &z1);
+        return z0;
     }
     double Uniform(double x1 = 1.0) { return x1 * Rndm(); }
     double Uniform(double x1, double x2) { return x1 + (x2 - x1) * Rndm(); }

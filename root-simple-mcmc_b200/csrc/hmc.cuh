@@ -219,12 +219,18 @@ kHmcBegin(HmcArrays a, int n, int chains, double alpha, uint64_t seed, uint32_t 
         }
     } else {
         const double w = __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(alpha, alpha)));
-        for (int i = lane; i < n; i += 32) {
-            const double g = __dadd_rn(0.0, __dmul_rn(1.0, smcmc_normal(seed, gchain, step, (uint32_t)i,
-                                                                       SMCMC_STREAM_STEP)));   // Gaus(0,1)
-            const double p = __dadd_rn(__dmul_rn(alpha, a.pAcc[row + i]), __dmul_rn(w, g));
-            a.pProp[row + i] = p;
-            a.p0[row + i] = p;                                            // :587
+        for (int pr = lane; 2 * pr < n; pr += 32) {
+            // slots 2 pr and 2 pr + 1: the two branches of one Box-Muller block (smcmc_rng.h)
+            double z0 = 0.0, z1 = 0.0;
+            smcmc_normal_pair(seed, gchain, step, (uint32_t)pr, SMCMC_STREAM_STEP, &z0, &z1);
+            for (int h = 0; h < 2; ++h) {
+                const int i = 2 * pr + h;
+                if (i >= n) break;
+                const double g = __dadd_rn(0.0, __dmul_rn(1.0, h ? z1 : z0));   // Gaus(0,1)
+                const double p = __dadd_rn(__dmul_rn(alpha, a.pAcc[row + i]), __dmul_rn(w, g));
+                a.pProp[row + i] = p;
+                a.p0[row + i] = p;                                        // :587
+            }
         }
         slot = (uint32_t)n;
     }

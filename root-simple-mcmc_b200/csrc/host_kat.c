@@ -26,6 +26,11 @@ void smcmc_kat_normals(uint64_t seed, uint32_t chain, uint32_t step0, uint32_t n
 }
 double smcmc_kat_det_log(double x) { return smcmc_det_log(x); }
 double smcmc_kat_det_cos2pi(double u) { return smcmc_det_cos2pi(u); }
+double smcmc_kat_det_sin2pi(double u) { return smcmc_det_sin2pi(u); }
+void smcmc_kat_normal_pair(uint64_t seed, uint32_t chain, uint32_t step, uint32_t pair, uint32_t stream, double* out2) {
+    smcmc_normal_pair(seed, chain, step, pair, stream, out2, out2 + 1);
+}
+double smcmc_kat_bits_to_open01(uint32_t hi, uint32_t lo) { return smcmc_bits_to_open01(hi, lo); }
 double smcmc_kat_seq_add(double s, double w, uint32_t n) { return smcmc_seq_add(s, w, n); }
 double smcmc_kat_seq_add_naive(double s, double w, uint32_t n) {
     for (uint32_t i = 0; i < n; ++i) s = s + w;

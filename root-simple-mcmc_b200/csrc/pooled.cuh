@@ -311,14 +311,12 @@ kProposePooled(ChainArrays a, PropSettings ps, PooledState pool, int chains, uin
     for (int i = lane; i < n; i += 32) last[i] = cur[i];
 
     const uint32_t gchain = chainOffset + (uint32_t)c;
-    for (int i = lane; i < n; i += 32) {
-        if (ps.type[i] == 1) {
-            const double uu = smcmc_uniform(seed, gchain, step, (uint32_t)i, SMCMC_STREAM_STEP);
-            zr[i] = __dadd_rn(ps.param1[i], __dmul_rn(__dsub_rn(ps.param2[i], ps.param1[i]), uu));
-        } else {
-            const double g = smcmc_normal(seed, gchain, step, (uint32_t)i, SMCMC_STREAM_STEP);
-            zr[i] = __dmul_rn(s.sigma, __dadd_rn(0.0, __dmul_rn(1.0, g)));
-        }
+    for (int pr = lane; 2 * pr < n; pr += 32) {
+        double v0, v1;
+        drawPair(ps, seed, gchain, step, pr, v0, v1);
+        const int i = 2 * pr;
+        zr[i] = ps.type[i] == 1 ? v0 : __dmul_rn(s.sigma, v0);
+        if (i + 1 < n) zr[i + 1] = ps.type[i + 1] == 1 ? v1 : __dmul_rn(s.sigma, v1);
     }
     __syncwarp();
     if (zOut) {
@@ -466,18 +464,15 @@ kProposePooledTile(ChainArrays a, PropSettings ps, PooledState pool, int chains,
         sig[tid] = live ? s.sigma : nan("");
     }
     // ---- one thread per (chain, dimension): the draws, :709-719 -------------------
-    for (int k = tid; k < nc * n; k += kPooledTileThreads) {
-        const int c = k / n, i = k - c * n;
+    // (one thread per chain and PAIR of dimensions: both normals from one Philox block)
+    const int npairs = (n + 1) >> 1;
+    for (int k = tid; k < nc * npairs; k += kPooledTileThreads) {
+        const int c = k / npairs, pr = k - c * npairs;
         const uint32_t gchain = chainOffset + (uint32_t)(c0 + c);
-        double v;
-        if (ps.anyUniform && ps.type[i] == 1) {
-            const double uu = smcmc_uniform(seed, gchain, step, (uint32_t)i, SMCMC_STREAM_STEP);
-            v = __dadd_rn(ps.param1[i], __dmul_rn(__dsub_rn(ps.param2[i], ps.param1[i]), uu));
-        } else {
-            const double g = smcmc_normal(seed, gchain, step, (uint32_t)i, SMCMC_STREAM_STEP);
-            v = __dadd_rn(0.0, __dmul_rn(1.0, g));
-        }
-        zr[c * ld + i] = v;
+        double v0, v1;
+        drawPair(ps, seed, gchain, step, pr, v0, v1);
+        zr[c * ld + 2 * pr] = v0;
+        if (2 * pr + 1 < n) zr[c * ld + 2 * pr + 1] = v1;
     }
     __syncthreads();
     for (int k = tid; k < nc * n; k += kPooledTileThreads) {

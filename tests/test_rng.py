@@ -26,6 +26,11 @@ def kat():
     lib.smcmc_kat_det_log.argtypes = [d]
     lib.smcmc_kat_det_cos2pi.restype = d
     lib.smcmc_kat_det_cos2pi.argtypes = [d]
+    lib.smcmc_kat_det_sin2pi.restype = d
+    lib.smcmc_kat_det_sin2pi.argtypes = [d]
+    lib.smcmc_kat_normal_pair.argtypes = [u64, u32, u32, u32, u32, ctypes.c_void_p]
+    lib.smcmc_kat_bits_to_open01.restype = d
+    lib.smcmc_kat_bits_to_open01.argtypes = [u32, u32]
     lib.smcmc_kat_seq_add.restype = d
     lib.smcmc_kat_seq_add.argtypes = [d, d, u32]
     lib.smcmc_kat_seq_add_naive.restype = d
@@ -57,6 +62,39 @@ def test_uniform_open_interval_and_addressing(kat):
     assert kat.smcmc_kat_uniform(7, 1, 2, 3, 0) != kat.smcmc_kat_uniform(7, 1, 2, 3, 1)
 
 
+def test_uniform_end_points_are_exact(kat):
+    # 52 random bits k -> (k + 1/2) 2^-52: the all-ones word must stay below 1, the zero word above 0
+    assert kat.smcmc_kat_bits_to_open01(0xffffffff, 0xffffffff) == 1.0 - 2.0 ** -53
+    assert kat.smcmc_kat_bits_to_open01(0, 0) == 2.0 ** -53
+    assert kat.smcmc_kat_bits_to_open01(0x80000000, 0) == 0.5 + 2.0 ** -53
+    assert kat.smcmc_kat_bits_to_open01(0, 0xfff) == 2.0 ** -53          # the low 12 bits are not used
+    assert kat.smcmc_kat_bits_to_open01(0, 0x1000) == 1.5 * 2.0 ** -52
+
+
+def test_normals_come_in_pairs(kat):
+    # slots 2k and 2k+1 are the cosine and the sine branch of one Box-Muller block
+    out = np.zeros(2)
+    for chain, step, pair in [(0, 0, 0), (3, 17, 4), (4095, 1999, 24), (7, 1, 249)]:
+        kat.smcmc_kat_normal_pair(11, chain, step, pair, 0, out.ctypes.data)
+        assert out[0] == kat.smcmc_kat_normal(11, chain, step, 2 * pair, 0)
+        assert out[1] == kat.smcmc_kat_normal(11, chain, step, 2 * pair + 1, 0)
+        assert out[0] != out[1]
+    # the pair is uncorrelated and each branch is a unit normal
+    n_steps = 20000
+    g = np.zeros(n_steps * 2)
+    kat.smcmc_kat_normals(5, 1, 0, n_steps, 2, g.ctypes.data)
+    g = g.reshape(n_steps, 2)
+    assert abs(np.mean(g[:, 0] * g[:, 1])) < 0.02
+    assert abs(g[:, 1].var() - 1.0) < 0.03 and abs(g[:, 0].var() - 1.0) < 0.03
+    r2 = (g ** 2).sum(axis=1)                          # chi-square with 2 dof: mean 2
+    assert abs(r2.mean() - 2.0) < 0.05
+    # a uniform draw of slot 2k does not share its bits with the normals of the pair (own sub-stream)
+    u = kat.smcmc_kat_uniform(5, 1, 0, 0, 0)
+    kat.smcmc_kat_normal_pair(5, 1, 0, 0, 0, out.ctypes.data)
+    rad2 = out[0] ** 2 + out[1] ** 2
+    assert abs(math.exp(-0.5 * rad2) - u) > 1e-9
+
+
 def test_normal_moments(kat):
     n_steps, n_slots = 4000, 50
     g = np.zeros(n_steps * n_slots)
@@ -78,6 +116,11 @@ def test_deterministic_log_and_cos_accuracy(kat):
         assert abs(kat.smcmc_kat_det_log(x) - math.log(x)) <= 4e-16 * abs(math.log(x))
     for x in rng.uniform(0, 1, 20000):
         assert abs(kat.smcmc_kat_det_cos2pi(float(x)) - math.cos(2 * math.pi * x)) < 1.5e-15
+        assert abs(kat.smcmc_kat_det_sin2pi(float(x)) - math.sin(2 * math.pi * x)) < 1.5e-15
+    for k in range(8):                                  # octant boundaries
+        for x in (k / 8.0 + 2.0 ** -53, (k + 1) / 8.0 - 2.0 ** -53, k / 8.0 + 0.0625):
+            assert abs(kat.smcmc_kat_det_cos2pi(x) - math.cos(2 * math.pi * x)) < 1.5e-15
+            assert abs(kat.smcmc_kat_det_sin2pi(x) - math.sin(2 * math.pi * x)) < 1.5e-15
 
 
 def test_sequential_sum_emulation_is_exact(kat):
