@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SMCMC_B200_ABI_VERSION 1
+#define SMCMC_B200_ABI_VERSION 2
 
 typedef struct smcmc_engine smcmc_engine;
 
@@ -51,13 +51,39 @@ typedef enum smcmc_likelihood {
                                  smcmc_unbinned_set_events                        */
     SMCMC_LLH_HARD = 6,       /* Rosenbrock valley   THardLogLikelihood.H:57-91 (with its
                                  gradient functor for TSimpleHMC), dim >= 2       */
-    SMCMC_LLH_FAKE2 = 7       /* example2/FakeLikelihood.H:58-118,222-289: the same event
+    SMCMC_LLH_FAKE2 = 7,      /* example2/FakeLikelihood.H:58-118,222-289: the same event
                                  corrections and cuts, signal and background filled into
                                  separate histograms, each renormalised to the event
                                  counts x[0], x[1] by its integral, plus the penalty terms
                                  (:91-115).  Events and data histograms are set with the
                                  smcmc_fake_* calls; the exposure argument is not used  */
+    SMCMC_LLH_USER = 8        /* a USER-WRITTEN device functor: the reference's plugin contract
+                                 (TSimpleMCMC.H:48-106: "hand TSimpleMCMC your own functor",
+                                 used that way in example/FakeMCMC.C:28-30 and
+                                 example4/Constrained.C:17-25).  The functor is compiled by nvcc
+                                 in the user's translation unit together with the kernel
+                                 templates of include/smcmc_device_functor.cuh and registered
+                                 with smcmc_user_set_ops; any dimension                        */
 } smcmc_likelihood;
+
+/* The table entry of a user device functor (SMCMC_LLH_USER).  Both entries are HOST
+ * functions of the user's translation unit that queue a kernel on `cuda_stream`
+ * (include/smcmc_device_functor.cuh instantiates them from the functor's type);
+ * pointers ending in _dev are device pointers.  They return 0 or a cudaError_t. */
+typedef struct smcmc_user_ops {
+    uint32_t struct_size;   /* sizeof(smcmc_user_ops)                                          */
+    uint32_t reserved_;
+    void* ctx;              /* passed back to the two functions                                */
+    /* UserLikelihood::operator() (TSimpleMCMC.H:59-69) at m points: x_dev[m*dim] -> llh_dev[m] */
+    int (*likelihood)(void* ctx, const double* x_dev, int m, int dim, double* llh_dev, void* cuda_stream);
+    /* UserGradient::operator() (TSimpleHMC.H:38-60, called at :478-487): the gradient of
+     * log L at the m points, NEGATED into grad_dev[m*dim] (the potential's gradient, :486).
+     * Chain c takes part when steps_dev == NULL or 1 <= steps_dev[c] and k <= steps_dev[c]
+     * (chains of an ensemble carry their own trajectory length).  NULL: the functor has no
+     * gradient (TSimpleHMC<L>: finite differences, :417-444).                                 */
+    int (*gradient)(void* ctx, const double* x_dev, int m, int dim, double* grad_dev,
+                    const int32_t* steps_dev, int k, void* cuda_stream);
+} smcmc_user_ops;
 
 typedef struct smcmc_config {
     uint32_t struct_size;   /* sizeof(smcmc_config), for ABI growth            */
@@ -211,7 +237,20 @@ int smcmc_prop_reset_correlations(smcmc_engine* e);                       /* :87
 int smcmc_prop_update(smcmc_engine* e);   /* UpdateProposal() on every chain :1009 */
 int smcmc_prop_reset(smcmc_engine* e);    /* ResetProposal()  on every chain :1396 */
 
+/* Debugging modes of the proposal functor (TSimpleMCMC.H:671-704).
+ * ForceStep (:811-818): the NEXT step proposes the given point (x[dim] for every chain,
+ * or x[chains*dim] with per_chain != 0) without touching the adaptive state; combine
+ * with metropolis = 2 to move the chains there (the idiom of :797-808). */
+int smcmc_prop_force_step(smcmc_engine* e, const double* x, int per_chain);
+/* SetScanDimension (:820-830): while dim is a valid dimension every step only redraws
+ * that coordinate around the estimated centre (one draw); -1 (or out of range) = off. */
+int smcmc_prop_set_scan_dimension(smcmc_engine* e, int dim);
+/* SetEstimatedCenter (:733-739): v[dim] for every chain, or v[chains*dim]. */
+int smcmc_prop_set_center(smcmc_engine* e, const double* v, int per_chain);
+
 /* ---- likelihood inputs --------------------------------------------------- */
+/* SMCMC_LLH_USER: register the functor's launch table; before smcmc_start. */
+int smcmc_user_set_ops(smcmc_engine* e, const smcmc_user_ops* ops);
 /* FakeLikelihood::SimulatedSample (example/FakeLikelihood.H:30); events are
  * copied to the device and re-laid-out there.  Replaces the sample. */
 int smcmc_fake_set_events(smcmc_engine* e, const smcmc_event* events, int64_t n);
@@ -293,6 +332,8 @@ typedef struct smcmc_saved_state {
     double* central_point_trials;/* [chains]      AdaptiveCentralPointTrials  */
     double* covariance;          /* [chains*dim*(dim+1)/2] AdaptiveCovariance */
     double* covariance_trials;   /* [chains]      AdaptiveCovarianceTrials    */
+    double* covariance_trace;    /* [chains]      AdaptiveCovarianceTrace (GetCovarianceTrace :961-967);
+                                    written by smcmc_save_state, not read by smcmc_restore_state */
 } smcmc_saved_state;
 /* SaveStep(true): copy the state of every chain into the caller's arrays. */
 int smcmc_save_state(smcmc_engine* e, const smcmc_saved_state* out);
@@ -319,7 +360,8 @@ typedef enum smcmc_hmc_setting {
     SMCMC_HMC_MEAN_EPSILON = 1,     /* SetMeanEpsilon  :181 (Start() resets it to 0.05, :229) */
     SMCMC_HMC_LEAPFROG = 2,         /* SetLeapFrog     :190 (stored negated = fixed)          */
     SMCMC_HMC_USER_GRADIENT = 3,    /* 1: TSimpleHMC<L, L> (the likelihood's own gradient functor,
-                                       TDummyLogLikelihood.H:34-42); 0: TSimpleHMC<L>, finite
+                                       TDummyLogLikelihood.H:34-42, THardLogLikelihood.H:72-91, or
+                                       smcmc_user_ops::gradient); 0: TSimpleHMC<L>, finite
                                        differences (:417-444).  Set before smcmc_hmc_start.   */
     SMCMC_HMC_KEEP_ERROR_MATRIX = 4 /* 1: keep fEstimatedError per chain (dim*dim doubles), which
                                        gradient type 2 (:447-454) reads.  Set before start.   */

@@ -16,6 +16,9 @@
 
 #ifdef SMCMC_HAVE_ROOT_TTREE
 #include <TTree.h>
+namespace sMCMC { namespace detail {
+inline bool TreeHasBranch(TTree* t, const char* name) { return t->GetBranch(name) != NULL; }
+} }
 #else
 #include <map>
 #include <string>
@@ -80,5 +83,8 @@ private:
     std::map<std::string, Column<int> > fI;
     std::map<std::string, Column<std::vector<double>, std::vector<double>**> > fV;
 };
+namespace sMCMC { namespace detail {
+inline bool TreeHasBranch(TTree* t, const char* name) { return t->HasBranch(name); }
+} }
 #endif
 #endif

@@ -30,6 +30,8 @@ enum {
     ORC_LLH_HARD = 6,       /* THardLogLikelihood.H:57-91 (Rosenbrock, with gradient) */
     ORC_LLH_FAKE2 = 7,      /* example2/FakeLikelihood.H:58-118, 222-289 (events and data
                                set with *_chain_set_fake; the exposure is not used)   */
+    ORC_LLH_CONSTRAINED = 8, /* example4/TConstrainedLikelihood.H:26-46 with the priors of its
+                               Init() (:55-110): 25 dimensions, a constraint on the sum        */
     ORC_LLH_UNBINNED = 5    /* NOT in the reference: the unbinned
                                mixture likelihood of BASELINE.json configs[4], defined in
                                include/smcmc_b200.h; events set with *_chain_set_fake */
@@ -102,6 +104,11 @@ typedef struct orc_event {
                            double* center, double* cov, double* decomp);      \
     double P##chain_llh(void* h, const double* x);                            \
     int P##chain_fake_hist(void* h, const double* x, double* out150);         \
+    /* the debugging modes of TProposeAdaptiveStep::operator() (:671-704) and        \
+     * SetEstimatedCenter (:733-739) */                                             \
+    int P##chain_force_step(void* h, const double* x);                            \
+    int P##chain_set_scan(void* h, int dim);                                      \
+    int P##chain_set_center(void* h, const double* v);                            \
     const char* P##last_error(void);
 
 ORC_DECLARE(ref_)
@@ -124,6 +131,10 @@ enum {
     ORC_HS_AVERAGE_TRIALS, ORC_HS_EST_COV_TRACE, ORC_HS_CUR_COV_TRACE, ORC_HS_ORBIT_LENGTH,
     ORC_HS_STEPS_REMAINING, ORC_HS_STEPS_SINCE_UPDATE, ORC_HS_COUNT
 };
+/* Reference build only: Restore(tree, randomize = true) (TSimpleMCMC.H:309-316) from the
+ * tree of `source`; the uniforms of the walk are draws k = 0, 1, ... of (seed, chain,
+ * step 0xffffffff).  out[0] = TotalSteps of the entry that was adopted. */
+int ref_chain_restore_random(void* h, void* source, int32_t* out);
 #define ORC_DECLARE_HMC(P)                                                            \
     void* P##hmc_create(int kind, int dim, int with_gradient, uint64_t seed, uint32_t chain); \
     void P##hmc_destroy(void* h);                                                     \

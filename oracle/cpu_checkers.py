@@ -18,7 +18,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-LLH_UNIT_GAUSS, LLH_DUMMY, LLH_HORRIFIC, LLH_ASYM, LLH_FAKE, LLH_UNBINNED, LLH_HARD, LLH_FAKE2 = range(8)
+LLH_UNIT_GAUSS, LLH_DUMMY, LLH_HORRIFIC, LLH_ASYM, LLH_FAKE, LLH_UNBINNED, LLH_HARD, LLH_FAKE2, LLH_CONSTRAINED = range(9)
 
 (SET_SIGMA, SET_TARGET_ACCEPTANCE, SET_ACCEPTANCE_WINDOW,
  SET_ACCEPTANCE_RIGIDITY, SET_ACCEPTANCE_DEWEIGHT, SET_COVARIANCE_WINDOW,
@@ -91,6 +91,9 @@ def load(which):
         "chain_step_saved": (ci, [vp, ci, vp]),
         "chain_save_step": (ci, [vp]),
         "chain_restore": (ci, [vp, vp]),
+        "chain_force_step": (ci, [vp, vp]),
+        "chain_set_scan": (ci, [vp, ci]),
+        "chain_set_center": (ci, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, p + name)
@@ -120,6 +123,8 @@ def load(which):
         lib.ref_dummy_matrices.argtypes = [vp, vp]
         lib.ref_ex2_generate.restype = ctypes.c_long
         lib.ref_ex2_generate.argtypes = [ctypes.c_ulong, ci, ci, cd, vp, ctypes.c_long, vp]
+        lib.ref_chain_restore_random.restype = ci
+        lib.ref_chain_restore_random.argtypes = [vp, vp, vp]
     _LIBS[which] = lib
     return lib
 
@@ -207,6 +212,27 @@ class CpuChain:
     def restore(self, source):
         """Restore() from the tree of `source` (call after start())."""
         self._check(self._f("chain_restore")(self.h, source.h))
+
+    def restore_random(self, source):
+        """Reference build only: Restore(tree, randomize=true); returns the
+        TotalSteps of the adopted entry."""
+        out = np.zeros(1, np.int32)
+        self._check(self.lib.ref_chain_restore_random(self.h, source.h, _ptr(out)))
+        return int(out[0])
+
+    def force_step(self, x):
+        """ForceStep (TSimpleMCMC.H:811-818): the next proposal is x."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        self._check(self._f("chain_force_step")(self.h, _ptr(x)))
+
+    def set_scan(self, dim):
+        """SetScanDimension (:820-830)."""
+        self._check(self._f("chain_set_scan")(self.h, int(dim)))
+
+    def set_center(self, v):
+        """SetEstimatedCenter (:733-739)."""
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        self._check(self._f("chain_set_center")(self.h, _ptr(v)))
 
     def update_proposal(self):
         self._check(self._f("chain_update_proposal")(self.h))

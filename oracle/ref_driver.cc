@@ -51,6 +51,7 @@ using namespace sMCMC;  // example/ predates the namespace
 #undef THardLogLikelihood_H_seen
 #include "THardLogLikelihood.H"
 #include "example/FakeLikelihood.H"
+#include "example4/TConstrainedLikelihood.H"
 #define HMC_DEBUG_LEVEL -1
 #include "TSimpleHMC.H"
 #undef private
@@ -130,6 +131,7 @@ struct ChainBase {
     virtual void SetStepRMSWindow(int n) = 0;
     virtual void SaveStep() = 0;
     virtual void Restore(TTree* tree) = 0;
+    virtual void RestoreRandom(TTree* tree) = 0;
     virtual FakeLikelihood* Fake() { return 0; }
     virtual void* Fake2() { return 0; }
     virtual TProposeVAATStep* Vaat() { return 0; }
@@ -148,6 +150,10 @@ struct Chain : public ChainBase {
     // can only be instantiated for the adaptive proposal.
     void Restore(TTree* t) {
         if constexpr (kAdaptive) mcmc.Restore(t);
+        else throw std::logic_error("Restore needs TProposeAdaptiveStep");
+    }
+    void RestoreRandom(TTree* t) {
+        if constexpr (kAdaptive) mcmc.Restore(t, true);
         else throw std::logic_error("Restore needs TProposeAdaptiveStep");
     }
     bool StepSaved(int metropolis) { return mcmc.Step(true, metropolis); }
@@ -250,6 +256,13 @@ void* ref_chain_create(int kind, int dim, uint64_t seed, uint32_t chain) {
         if (dim != 9) { gLastError = "example2 FakeLikelihood is 9-dim"; return 0; }
         c = new Fake2Chain(seed, chain, dim);
         break;
+    case ORC_LLH_CONSTRAINED: {
+        Chain<TConstrainedLikelihood>* k = new Chain<TConstrainedLikelihood>(seed, chain, 25);
+        k->mcmc.GetLogLikelihood().Init();                       // example4/Constrained.C:21-22
+        if (dim != (int)k->mcmc.GetLogLikelihood().GetDim()) { delete k; gLastError = "TConstrainedLikelihood is 25-dim"; return 0; }
+        c = k;
+        break;
+    }
     default:
         gLastError = "unknown likelihood kind";
         return 0;
@@ -437,6 +450,40 @@ int ref_chain_restore(void* h, void* source) {
         c->Restore(&src->tree);
         c->step = src->step;
         return 0;
+    });
+}
+
+int ref_chain_restore_random(void* h, void* source, int32_t* out) {
+    ChainBase* c = H(h);
+    ChainBase* src = H(source);
+    return Guard([&]() {
+        gRandom = &c->rng;
+        c->rng.Begin(0xffffffffu);
+        c->RestoreRandom(&src->tree);
+        c->step = src->step;
+        if (out) out[0] = c->TotalSteps();
+        return 0;
+    });
+}
+
+int ref_chain_force_step(void* h, const double* x) {
+    ChainBase* c = H(h);
+    return Guard([&]() {
+        Vector v(x, x + c->dim);
+        c->Prop().ForceStep(v);
+        return 0;
+    });
+}
+
+int ref_chain_set_scan(void* h, int dim) {
+    return Guard([&]() { H(h)->Prop().SetScanDimension(dim); return 0; });
+}
+
+int ref_chain_set_center(void* h, const double* v) {
+    ChainBase* c = H(h);
+    return Guard([&]() {
+        Vector p(v, v + c->dim);
+        return c->Prop().SetEstimatedCenter(p) ? 0 : -1;
     });
 }
 

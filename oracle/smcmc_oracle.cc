@@ -369,6 +369,21 @@ struct Likelihood {
             return EvalFake2(x);
         case ORC_LLH_UNBINNED:
             return EvalUnbinned(x);
+        case ORC_LLH_CONSTRAINED: {          // example4/TConstrainedLikelihood.H:26-46, priors of Init() :55-110
+            double logLikelihood = 0.0;
+            double sum = 0.0;
+            for (int i = 0; i < dim; ++i) sum += x[i];
+            sum = (sum - 1902.0) / 16.0;
+            logLikelihood -= 0.5 * sum * sum;
+            for (int i = 0; i < dim; ++i) {
+                const double expected = (i < 24) ? 76.0 : 80.0;
+                const double prior = (i < 24) ? 76.0 * 0.08 : 2.0;
+                double v = x[i] - expected;
+                v /= prior;
+                logLikelihood -= 0.5 * v * v;
+            }
+            return logLikelihood;
+        }
         case ORC_LLH_HARD: {                 // THardLogLikelihood.H:57-69
             double s = 0.0;
             for (int i = 0; i < dim - 1; ++i) {
@@ -689,8 +704,34 @@ struct Proposal {
         return true;
     }
 
-    // operator(), :659-725 (forced-step and scan debug modes not restated)
+    std::vector<double> forcedStep;          // fForcedStep  :811-818
+    int scanDimension = -1;                  // fScanDimension :820-830
+    uint32_t drawsUsed = 0;                  // gRandom calls of the last operator()
+
+    // operator(), :659-725
     bool Propose(double* proposal, const double* current, double value, uint32_t step) {
+        if (!forcedStep.empty()) {                                           // :671-678
+            std::copy(forcedStep.begin(), forcedStep.end(), proposal);
+            forcedStep.clear();
+            drawsUsed = 0;
+            return true;
+        }
+        const int scan = scanDimension;
+        if (scan >= 0 && scan < n) {                                         // :685-704
+            std::copy(current, current + n, proposal);
+            drawsUsed = 1;
+            if (type[scan] == 1) {
+                double u = smcmc_uniform(seed, chain, step, 0u, SMCMC_STREAM_STEP);
+                proposal[scan] = param1[scan] + (param2[scan] - param1[scan]) * u;
+                return true;
+            }
+            double sig = 1.0;
+            if (param1[scan] > 0) sig = std::sqrt(param1[scan]);
+            double g = smcmc_normal(seed, chain, step, 0u, SMCMC_STREAM_STEP);
+            proposal[scan] = center[scan] + sig * g;                         // TRandom::Gaus(mean, sigma)
+            return true;
+        }
+        drawsUsed = (uint32_t)n;
         if (!UpdateState(current, value)) return false;
         std::copy(current, current + n, proposal);
         for (int i = 0; i < n; ++i) {
@@ -845,7 +886,10 @@ struct OrcChain {
         if (vaat) {
             vprop.Propose(proposed.data(), accepted.data(), acceptedLlh, step++);
             acceptSlot = vprop.slot;
-        } else if (!prop.Propose(proposed.data(), accepted.data(), acceptedLlh, step++)) return -1;
+        } else {
+            if (!prop.Propose(proposed.data(), accepted.data(), acceptedLlh, step++)) return -1;
+            acceptSlot = prop.drawsUsed;                               // the accept draw is the next gRandom call
+        }
         if (stepRMSWindow > 0) {                                       // :391-406
             double sqr = 0.0;
             for (int i = 0; i < n; ++i) {
@@ -952,7 +996,8 @@ extern "C" {
 const char* orc_last_error(void) { return gLastError.c_str(); }
 
 void* orc_chain_create(int kind, int dim, uint64_t seed, uint32_t chain) {
-    if (kind < ORC_LLH_UNIT_GAUSS || kind > ORC_LLH_FAKE2 || dim < 1 || (kind == ORC_LLH_HARD && dim < 2)) {
+    if (kind < ORC_LLH_UNIT_GAUSS || kind > ORC_LLH_CONSTRAINED || dim < 1 || (kind == ORC_LLH_HARD && dim < 2) ||
+        (kind == ORC_LLH_CONSTRAINED && dim != 25)) {
         gLastError = "bad likelihood kind or dimension";
         return 0;
     }
@@ -1156,6 +1201,24 @@ int orc_chain_fake_hist(void* h, const double* x, double* out150) {
     else l.FillFake(x);
     for (int hh = 0; hh < 3; ++hh)
         for (int b = 0; b < 50; ++b) out150[hh * 50 + b] = l.sim[hh][b + 1];
+    return 0;
+}
+
+int orc_chain_force_step(void* h, const double* x) {
+    OrcChain* c = H(h);
+    c->prop.forcedStep.assign(x, x + c->n);
+    return 0;
+}
+int orc_chain_set_scan(void* h, int dim) {
+    OrcChain* c = H(h);
+    if (c->prop.lastPoint.empty()) return 0;
+    c->prop.scanDimension = (dim < 0 || dim >= c->n) ? -1 : dim;
+    return 0;
+}
+int orc_chain_set_center(void* h, const double* v) {
+    OrcChain* c = H(h);
+    if ((int)c->prop.center.size() != c->n) return -1;
+    std::copy(v, v + c->n, c->prop.center.begin());
     return 0;
 }
 

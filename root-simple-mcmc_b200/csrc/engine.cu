@@ -82,6 +82,11 @@ struct smcmc_engine {
     int smCount = 148;
     uint32_t stepIndex = 0;
     bool started = false;
+    // debugging modes of the proposal (TSimpleMCMC.H:671-704)
+    DeviceBuffer<double> forcedStep;    // ForceStep: the next proposal of every chain
+    bool forcedPending = false;
+    int scanDim = -1;                   // SetScanDimension
+    bool vaatInitialized = false;       // TProposeVAATStep::InitializeState ran (it runs once, :197-198)
     // the step loop as a CUDA graph (stepMany): the step counter moves to a device word
     bool graphMode = false;
     DeviceBuffer<uint32_t> dStep;
@@ -161,6 +166,7 @@ struct smcmc_engine {
     int eigSlots = 0;
 
     // ---- likelihood data ---------------------------------------------------
+    smcmc_user_ops userOps = {0, 0, nullptr, nullptr, nullptr};   // USER: the functor's launch table
     DeviceBuffer<double> errMatrix, errMatrixT;     // DUMMY: Error(i,j) row-major, and its transpose
     int errDim = 0;
     int dummyMode = SMCMC_DUMMY_EXACT;              // SMCMC_DUMMY_EXACT | SMCMC_DUMMY_TENSOR
@@ -453,6 +459,15 @@ struct smcmc_engine {
         case SMCMC_LLH_UNBINNED:
             evaluateUnbinned(xDev, m, llhDev);
             break;
+        case SMCMC_LLH_USER: {
+            // the user's functor: its kernel lives in the user's translation unit
+            if (!userOps.likelihood) throw Error(SMCMC_ERR_LOGIC, "user functor not registered (smcmc_user_set_ops)");
+            const int rc = userOps.likelihood(userOps.ctx, xDev, m, n(), llhDev, (void*)stream);
+            if (rc != 0) throw Error(SMCMC_ERR_CUDA, std::string("user likelihood launch failed: ") +
+                                                     cudaGetErrorString((cudaError_t)rc));
+            launched();
+            break;
+        }
         case SMCMC_LLH_DUMMY: {
             if (errDim != n()) throw Error(SMCMC_ERR_LOGIC, "error matrix not set (smcmc_dummy_set_error)");
             if (dummyMode == SMCMC_DUMMY_TENSOR) {
@@ -687,6 +702,24 @@ struct smcmc_engine {
         ChainArrays a = arrays();
         const int blocks = ceilDiv(E(), kWarpsPerBlock);
         const size_t smem = (size_t)kWarpsPerBlock * 3 * n() * sizeof(double);
+        if (debugStep()) {
+            // forced or scan step (:671-704): no UpdateState, the accept draw is the next
+            // gRandom call of the step (slot 0 after a forced point, 1 after the scan draw)
+            const bool forced = forcedPending;
+            kProposeDebug<<<ceilDiv(E(), 128), 128, 0, stream>>>(a, ps, E(), forced ? forcedStep.get() : nullptr, scanDim,
+                                                                 cfg.seed, cfg.chain_offset, stepRef());
+            launched();
+            forcedPending = false;                                       // fForcedStep.clear(), :677
+            vaatSynced = false;
+            evaluate(xProp.get(), E(), llhProp.get(), nullptr);
+            kAccept<<<ceilDiv(E(), kAcceptThreads), kAcceptThreads, 0, stream>>>(a, ps, E(), llhProp.get(), cfg.seed,
+                                                                                 cfg.chain_offset, stepRef(), metropolis, tr,
+                                                                                 traceStep, nullptr, forced ? 0 : 1);
+            launched();
+            ++stepIndex;
+            if (diagOn) diagAccumulate();
+            return;
+        }
         if (pooledEvery > 0 && usePooledTensor()) {
             // x' = x + (sigma z) . U for all chains as one GEMM on the FP64 tensor cores
             poolZ.reserve((size_t)E() * n());
@@ -750,9 +783,10 @@ struct smcmc_engine {
     // 8-256 chains x 4M events and LOSES for one chain (gpurun_out/mid_ensemble.txt);
     // the launch-bound chain-local case is served by kStepsResident instead.
     static constexpr int kGraphMinSteps = 8;
+    bool debugStep() const { return propKind == SMCMC_PROPOSAL_ADAPTIVE && (forcedPending || scanDim >= 0); }
     bool graphable() const {
         const char* g = std::getenv("SMCMC_GRAPH");
-        return g && g[0] == '1' && pooledEvery == 0 && !eventComm && !timing && !diagOn;
+        return g && g[0] == '1' && pooledEvery == 0 && !eventComm && !timing && !diagOn && !debugStep();
     }
     // kAcceptLocal instead of likelihood kernel + kAccept (SMCMC_NO_ACCEPT_LOCAL=1: the two launches)
     bool acceptLocalReady = false;
@@ -778,7 +812,7 @@ struct smcmc_engine {
     // adaptive one: all nsteps steps run in ONE launch with the chain's state resident in
     // shared memory (proposal_resident.cuh).  SMCMC_NO_RESIDENT=1 keeps the three-launch step.
     bool residentable() const {
-        if (!resident || pooledEvery > 0 || propKind != SMCMC_PROPOSAL_ADAPTIVE || timing || diagOn) return false;
+        if (!resident || pooledEvery > 0 || propKind != SMCMC_PROPOSAL_ADAPTIVE || timing || diagOn || debugStep()) return false;
         if (std::getenv("SMCMC_NO_RESIDENT")) return false;
         // up to one wave of CTAs; a larger ensemble is served as well by the three-launch
         // step (measured, proposal_resident.cuh).  SMCMC_RESIDENT=1 lifts the limit.
@@ -800,20 +834,25 @@ struct smcmc_engine {
     void stepMany(int nsteps, int metropolis) {
         TraceDev none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
         int done = 0;
-        if (nsteps >= 2 && residentable()) {
+        if (forcedPending && nsteps > 0) {            // the forced point is the proposal of the first step only
+            stepOnce(metropolis, none, -1);
+            done = 1;
+            if (nsteps == 1) return;
+        }
+        if (nsteps - done >= 2 && residentable()) {
             PropSettings ps = settings();
             ChainArrays a = arrays();
             const double* errT = cfg.likelihood == SMCMC_LLH_DUMMY ? errMatrixT.get() : nullptr;
             kStepsResident<<<E(), kStagedThreads, residentChainBytes(n(), covStride, upkStride), stream>>>(
-                a, ps, E(), cfg.seed, cfg.chain_offset, stepIndex, nsteps, metropolis, cfg.likelihood, errT);
+                a, ps, E(), cfg.seed, cfg.chain_offset, stepIndex, nsteps - done, metropolis, cfg.likelihood, errT);
             launched();
             ++residentLaunches;
-            stepIndex += (uint32_t)nsteps;
+            stepIndex += (uint32_t)(nsteps - done);
             return;
         }
-        if (nsteps >= kGraphMinSteps && graphable()) {
+        if (nsteps - done >= kGraphMinSteps && graphable()) {
             stepOnce(metropolis, none, -1);           // sizes the buffers, uploads dirty settings
-            done = 1;
+            ++done;
             if (!graphStream) {
                 CUDA_CHECK(cudaStreamCreateWithFlags(&graphStream, cudaStreamNonBlocking));
                 CUDA_CHECK(cudaEventCreateWithFlags(&graphEvent, cudaEventDisableTiming));
@@ -917,7 +956,7 @@ int smcmc_create(const smcmc_config* cfg, smcmc_engine** out) {
         if (!cfg || !out) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null argument");
         if (cfg->struct_size != sizeof(smcmc_config)) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "smcmc_config size mismatch");
         if (cfg->dim < 1 || cfg->chains < 1) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "dim and chains must be positive");
-        if (cfg->likelihood < SMCMC_LLH_UNIT_GAUSS || cfg->likelihood > SMCMC_LLH_FAKE2)
+        if (cfg->likelihood < SMCMC_LLH_UNIT_GAUSS || cfg->likelihood > SMCMC_LLH_USER)
             throw Error(SMCMC_ERR_INVALID_ARGUMENT, "unknown likelihood");
         if (cfg->likelihood == SMCMC_LLH_HARD && cfg->dim < 2)
             throw Error(SMCMC_ERR_INVALID_ARGUMENT, "THardLogLikelihood needs two or more dimensions");
@@ -1221,6 +1260,53 @@ int smcmc_prop_reset(smcmc_engine* e) {
     });
 }
 
+int smcmc_user_set_ops(smcmc_engine* e, const smcmc_user_ops* ops) {
+    return guarded(e, [&]() {
+        if (e->cfg.likelihood != SMCMC_LLH_USER) throw Error(SMCMC_ERR_LOGIC, "engine was not created with SMCMC_LLH_USER");
+        if (!ops || ops->struct_size != sizeof(smcmc_user_ops) || !ops->likelihood)
+            throw Error(SMCMC_ERR_INVALID_ARGUMENT, "bad smcmc_user_ops");
+        e->userOps = *ops;
+    });
+}
+
+int smcmc_prop_force_step(smcmc_engine* e, const double* x, int per_chain) {
+    return guarded(e, [&]() {
+        if (e->propKind != SMCMC_PROPOSAL_ADAPTIVE) throw Error(SMCMC_ERR_LOGIC, "ForceStep belongs to TProposeAdaptiveStep");
+        if (!x) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "Invalid forced step point.");          // :812-814
+        const size_t E = e->E(), n = e->n();
+        e->forcedStep.reserve(E * n);
+        if (per_chain) {
+            CUDA_CHECK(cudaMemcpyAsync(e->forcedStep.get(), x, E * n * 8, cudaMemcpyHostToDevice, e->stream));
+        } else {
+            std::vector<double> all(E * n);
+            for (size_t c = 0; c < E; ++c) std::copy(x, x + n, all.begin() + c * n);
+            CUDA_CHECK(cudaMemcpyAsync(e->forcedStep.get(), all.data(), E * n * 8, cudaMemcpyHostToDevice, e->stream));
+        }
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        e->forcedPending = true;
+    });
+}
+
+int smcmc_prop_set_scan_dimension(smcmc_engine* e, int dim) {
+    return guarded(e, [&]() {
+        if (e->propKind != SMCMC_PROPOSAL_ADAPTIVE) throw Error(SMCMC_ERR_LOGIC, "SetScanDimension belongs to TProposeAdaptiveStep");
+        e->scanDim = (dim < 0 || dim >= e->n()) ? -1 : dim;                                     // :827-829
+    });
+}
+
+int smcmc_prop_set_center(smcmc_engine* e, const double* v, int per_chain) {
+    return guarded(e, [&]() {
+        if (!v) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null centre");
+        const size_t E = e->E(), n = e->n();
+        DeviceBuffer<double> tmp;
+        tmp.reserve(per_chain ? E * n : n);
+        CUDA_CHECK(cudaMemcpyAsync(tmp.get(), v, (per_chain ? E * n : n) * 8, cudaMemcpyHostToDevice, e->stream));
+        kSetCenter<<<ceilDiv((long long)(E * n), 256), 256, 0, e->stream>>>(e->center.get(), tmp.get(), (int)E, (int)n, per_chain ? 1 : 0);
+        e->launched();
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    });
+}
+
 int smcmc_fake_set_events(smcmc_engine* e, const smcmc_event* events, int64_t count) {
     return guarded(e, [&]() {
         if (e->cfg.likelihood != SMCMC_LLH_FAKE && e->cfg.likelihood != SMCMC_LLH_FAKE2)
@@ -1463,7 +1549,8 @@ int smcmc_start(smcmc_engine* e, const double* x0, int32_t* ok) {
             if (e->pooledEvery > 0) throw Error(SMCMC_ERR_LOGIC, "pooled adaptation belongs to the adaptive proposal");
             PropSettings psv = e->settings();
             if (!e->started) e->vaatAllocate();
-            e->vaatWindow = 100;                                                                    // InitializeState, TProposeVAATStep.H:208
+            if (!e->vaatInitialized) e->vaatWindow = 100;                                           // InitializeState (first Start only), TProposeVAATStep.H:197-208
+            e->vaatInitialized = true;
             kStoreStartLlh<<<ceilDiv(e->E(), 128), 128, 0, e->stream>>>(e->sc.get(), e->llhProp.get(), e->E());
             e->launched();
             kVaatInit<<<ceilDiv(e->E(), 128), 128, 0, e->stream>>>(e->arrays(), e->vaatArrays(), e->E(), e->n(), e->okDev.get());
@@ -1490,7 +1577,7 @@ int smcmc_start(smcmc_engine* e, const double* x0, int32_t* ok) {
         if (ok) std::memcpy(ok, okHost.data(), sizeof(int32_t) * e->E());
         e->started = true;
         e->checkChainStatus();
-        if (e->pooledEvery > 0) e->poolInit();
+        if (e->pooledEvery > 0 && e->poolStats.count() == 0) e->poolInit();
     });
 }
 
@@ -1546,6 +1633,14 @@ int smcmc_save_state(smcmc_engine* e, const smcmc_saved_state* out) {
         if (out->covariance)
             CUDA_CHECK(cudaMemcpy2D(out->covariance, tri * 8, e->cov.get(), (size_t)e->covStride * 8, tri * 8, E,
                                     cudaMemcpyDeviceToHost));
+        if (out->covariance_trace) {
+            DeviceBuffer<double> tr;
+            tr.reserve(E);
+            kCovarianceTrace<<<ceilDiv((long long)E, 128), 128, 0, e->stream>>>(e->cov.get(), e->covStride, (int)E, (int)n, tr.get());
+            e->launched();
+            CUDA_CHECK(cudaMemcpyAsync(out->covariance_trace, tr.get(), E * 8, cudaMemcpyDeviceToHost, e->stream));
+            CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        }
         for (size_t c = 0; c < E; ++c) {
             if (out->log_likelihood) out->log_likelihood[c] = h[c].accLlh;
             if (out->total_steps) out->total_steps[c] = h[c].totalSteps;
@@ -1727,17 +1822,14 @@ int smcmc_get(smcmc_engine* e, int field, void* dst, size_t bytes) {
         case SMCMC_F_TOTAL_STEPS: putI(&ChainScalars::totalSteps); break;
         case SMCMC_F_LLH_CALLS: putI(&ChainScalars::llhCalls); break;
         case SMCMC_F_STATUS: putI(&ChainScalars::status); break;
-        case SMCMC_F_COVARIANCE_TRACE: {
+        case SMCMC_F_COVARIANCE_TRACE: {                                    // :961-967
             need(E * 8);
-            std::vector<double> covHost(E * e->tri());
-            CUDA_CHECK(cudaMemcpy2DAsync(covHost.data(), (size_t)e->tri() * 8, e->cov.get(), (size_t)e->covStride * 8,
-                                         (size_t)e->tri() * 8, E, cudaMemcpyDeviceToHost, e->stream));
+            DeviceBuffer<double> tr;
+            tr.reserve(E);
+            kCovarianceTrace<<<ceilDiv((long long)E, 128), 128, 0, e->stream>>>(e->cov.get(), e->covStride, (int)E, (int)n, tr.get());
+            e->launched();
+            CUDA_CHECK(cudaMemcpyAsync(dst, tr.get(), E * 8, cudaMemcpyDeviceToHost, e->stream));
             CUDA_CHECK(cudaStreamSynchronize(e->stream));
-            for (size_t c = 0; c < E; ++c) {
-                double t = 0.0;                                             // :961-967
-                for (size_t i = 0; i < n; ++i) t += covHost[c * e->tri() + i * (i + 1) / 2 + i];
-                ((double*)dst)[c] = t;
-            }
             break;
         }
         default: throw Error(SMCMC_ERR_INVALID_ARGUMENT, "unknown field");

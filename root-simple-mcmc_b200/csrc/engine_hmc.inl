@@ -92,7 +92,8 @@ enum HmcGradientMode { kGradUser, kGradFinite, kGradCovariant, kGradZero };
 
 HmcGradientMode hmcResolveGradient(smcmc_engine* e, int type) {
     const bool haveUser = e->hmc.userGradient &&
-                          (e->cfg.likelihood == SMCMC_LLH_DUMMY || e->cfg.likelihood == SMCMC_LLH_HARD);
+                          (e->cfg.likelihood == SMCMC_LLH_DUMMY || e->cfg.likelihood == SMCMC_LLH_HARD ||
+                           (e->cfg.likelihood == SMCMC_LLH_USER && e->userOps.gradient));
     switch (type) {
     case 2:
         if (!e->hmc.keepError)
@@ -113,6 +114,14 @@ void hmcGradient(smcmc_engine* e, HmcGradientMode mode, int k) {
     const int E = e->E(), n = e->n();
     switch (mode) {
     case kGradUser: {
+        if (e->cfg.likelihood == SMCMC_LLH_USER) {
+            const int rc = e->userOps.gradient(e->userOps.ctx, h.qProp.get(), E, n, h.grad.get(), h.leapSteps.get(), k,
+                                               (void*)e->stream);
+            if (rc != 0) throw Error(SMCMC_ERR_CUDA, std::string("user gradient launch failed: ") +
+                                                     cudaGetErrorString((cudaError_t)rc));
+            e->launched();
+            break;
+        }
         if (e->cfg.likelihood == SMCMC_LLH_HARD) {
             kHardGradient<<<ceilDiv((long long)E * n, 256), 256, 0, e->stream>>>(h.qProp.get(), h.grad.get(),
                                                                                 h.leapSteps.get(), k, E, n);
@@ -248,8 +257,10 @@ int smcmc_hmc_set(smcmc_engine* e, int setting, double v) {
         switch (setting) {
         case SMCMC_HMC_ALPHA: h.alpha = v; return;
         case SMCMC_HMC_USER_GRADIENT:
-            if (v != 0.0 && e->cfg.likelihood != SMCMC_LLH_DUMMY && e->cfg.likelihood != SMCMC_LLH_HARD)
-                throw Error(SMCMC_ERR_INVALID_ARGUMENT, "only TDummyLogLikelihood and THardLogLikelihood provide a gradient functor");
+            if (v != 0.0 && e->cfg.likelihood != SMCMC_LLH_DUMMY && e->cfg.likelihood != SMCMC_LLH_HARD &&
+                !(e->cfg.likelihood == SMCMC_LLH_USER && e->userOps.gradient))
+                throw Error(SMCMC_ERR_INVALID_ARGUMENT, "only TDummyLogLikelihood, THardLogLikelihood and user functors with a "
+                                                        "gradient entry provide a gradient functor");
             h.userGradient = (v != 0.0);
             return;
         case SMCMC_HMC_KEEP_ERROR_MATRIX:

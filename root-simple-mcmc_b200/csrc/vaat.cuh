@@ -46,7 +46,8 @@ __global__ void kVaatInit(ChainArrays a, VaatArrays v, int chains, int n, int32_
     s.started = good ? 1 : 0;
     if (good) {
         s.accLlh = s.propLlh;                                              // :270
-        s.lastValue = s.accLlh;                                            // TProposeVAATStep.H:204
+        if (!s.initialized) s.lastValue = s.accLlh;                        // TProposeVAATStep.H:197-204 (first Start only)
+        s.initialized = 1;
         double t = 0.0;
         for (int i = 0; i < n; ++i) t = __dadd_rn(t, v.sigma[(size_t)c * n + i]);
         s.sigma = __ddiv_rn(t, (double)n);

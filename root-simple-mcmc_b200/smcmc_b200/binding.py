@@ -8,7 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 
-LLH_UNIT_GAUSS, LLH_DUMMY, LLH_HORRIFIC, LLH_ASYM, LLH_FAKE, LLH_UNBINNED, LLH_HARD, LLH_FAKE2 = range(8)
+LLH_UNIT_GAUSS, LLH_DUMMY, LLH_HORRIFIC, LLH_ASYM, LLH_FAKE, LLH_UNBINNED, LLH_HARD, LLH_FAKE2, LLH_USER = range(9)
 DUMMY_EXACT, DUMMY_TENSOR = 0, 1
 
 # smcmc_prop_field
@@ -69,7 +69,8 @@ _SAVED_FIELDS = [("accepted", np.float64, "En"), ("log_likelihood", np.float64, 
                  ("next_update", np.int32, "E"), ("acceptance", np.float64, "E"),
                  ("acceptance_trials", np.float64, "E"), ("sigma", np.float64, "E"),
                  ("central_point", np.float64, "En"), ("central_point_trials", np.float64, "E"),
-                 ("covariance", np.float64, "Et"), ("covariance_trials", np.float64, "E")]
+                 ("covariance", np.float64, "Et"), ("covariance_trials", np.float64, "E"),
+                 ("covariance_trace", np.float64, "E")]
 
 
 class _SavedState(ctypes.Structure):
@@ -144,6 +145,10 @@ def load_library():
         "smcmc_prop_reset_correlations": (ci, [vp]),
         "smcmc_prop_update": (ci, [vp]),
         "smcmc_prop_reset": (ci, [vp]),
+        "smcmc_prop_force_step": (ci, [vp, vp, ci]),
+        "smcmc_prop_set_scan_dimension": (ci, [vp, ci]),
+        "smcmc_prop_set_center": (ci, [vp, vp, ci]),
+        "smcmc_user_set_ops": (ci, [vp, vp]),
         "smcmc_fake_set_events": (ci, [vp, vp, ctypes.c_int64]),
         "smcmc_fake_set_data": (ci, [vp, vp, cd]),
         "smcmc_unbinned_set_events": (ci, [vp, vp, ctypes.c_int64]),
@@ -191,6 +196,7 @@ EXPORTED_SYMBOLS = [
     "smcmc_set_stream", "smcmc_sync", "smcmc_comm_unique_id", "smcmc_comm_init", "smcmc_prop_set", "smcmc_prop_set_gaussian",
     "smcmc_prop_set_uniform", "smcmc_prop_set_correlation",
     "smcmc_prop_reset_correlations", "smcmc_prop_update", "smcmc_prop_reset",
+    "smcmc_prop_force_step", "smcmc_prop_set_scan_dimension", "smcmc_prop_set_center", "smcmc_user_set_ops",
     "smcmc_fake_set_events", "smcmc_fake_set_data", "smcmc_unbinned_set_events", "smcmc_fake_histograms",
     "smcmc_fake_counts", "smcmc_fake_filter_check",
     "smcmc_dummy_set_error", "smcmc_dummy_set_mode", "smcmc_eval", "smcmc_start", "smcmc_step",
@@ -316,6 +322,32 @@ class Engine:
     def reset_proposal(self):
         self._check(self.lib.smcmc_prop_reset(self.h))
 
+    def force_step(self, x):
+        """ForceStep (TSimpleMCMC.H:811-818): x[dim] for every chain or x[chains, dim]."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        per_chain = 1 if x.ndim == 2 else 0
+        if x.size != (self.chains * self.dim if per_chain else self.dim):
+            raise SmcmcError(-1, "Invalid forced step point.")
+        self._check(self.lib.smcmc_prop_force_step(self.h, _ptr(x), per_chain))
+
+    def set_scan(self, dim):
+        """SetScanDimension (:820-830); -1 = off."""
+        self._check(self.lib.smcmc_prop_set_scan_dimension(self.h, int(dim)))
+
+    def set_center(self, v):
+        """SetEstimatedCenter (:733-739): v[dim] for every chain or v[chains, dim]."""
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        self._check(self.lib.smcmc_prop_set_center(self.h, _ptr(v), 1 if v.ndim == 2 else 0))
+
+    def bind_user_library(self, lib, symbol):
+        """SMCMC_LLH_USER: `symbol(engine)` of a user library compiled by nvcc with
+        include/smcmc_device_functor.cuh registers the functor's launch table."""
+        fn = getattr(lib, symbol)
+        fn.restype = ctypes.c_int
+        fn.argtypes = [ctypes.c_void_p]
+        if fn(self.h) != 0:
+            raise SmcmcError(-3, "%s failed: %s" % (symbol, self.lib.smcmc_last_error(self.h).decode()))
+
     # -- likelihood inputs ---------------------------------------------------
     def set_fake_events(self, events):
         ev = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
@@ -421,7 +453,8 @@ class Engine:
         """Restore() + RestoreState() for every chain (call after start())."""
         arrays = self._saved_arrays()
         for k in arrays:
-            arrays[k][...] = np.asarray(saved[k]).reshape(arrays[k].shape)
+            if k in saved:          # (the covariance trace is written by save_state only)
+                arrays[k][...] = np.asarray(saved[k]).reshape(arrays[k].shape)
         st = _SavedState(**{k: v.ctypes.data for k, v in arrays.items()})
         mismatch = np.zeros(self.chains, np.int32)
         self._check(self.lib.smcmc_restore_state(self.h, ctypes.byref(st), _ptr(mismatch)))

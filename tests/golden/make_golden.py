@@ -233,6 +233,32 @@ def make_chains():
     put("unit6_clamped", run_chain(cc.LLH_UNIT_GAUSS, 6, 3, 4, 1500, nasty))
     # SimpleMCMC.C -DUSE_HARD_LIKELIHOOD: the 6-dimensional Rosenbrock valley
     put("hard6", run_chain(cc.LLH_HARD, 6, 13, 2, 2500, x0=np.full(6, 0.5)))
+    # example4: the constrained 25-dimensional Gaussian, started near its priors
+    put("constrained25", run_chain(cc.LLH_CONSTRAINED, 25, 51, 3, 3000, x0=np.full(25, 70.0)))
+    # the debugging modes of the proposal: ForceStep, SetScanDimension, SetEstimatedCenter
+    sys.path.insert(0, os.path.dirname(HERE))
+    from helpers import configure_debug_modes, run_debug_modes
+    d = cc.CpuChain("ref", cc.LLH_UNIT_GAUSS, 9, 61, 5)
+    configure_debug_modes(d)
+    d.start(np.full(9, 0.2))
+    rec = run_debug_modes(d)
+    sd = d.state()
+    rec["final_scalars"] = np.array([sd[k] for k in cc.STATE_FIELDS])
+    rec["final_center"] = sd["center"]
+    rec["final_cov"] = sd["cov"]
+    put("debug9", rec)
+    # Restore(tree, randomize = true): which entry of a 400-entry tree each of 6 chains adopts
+    picks = []
+    for chain in range(6):
+        a = cc.CpuChain("ref", cc.LLH_UNIT_GAUSS, 4, 71, chain)
+        a.start(np.full(4, 0.1))
+        a.step_saved(400)
+        a.save_step()
+        b = cc.CpuChain("ref", cc.LLH_UNIT_GAUSS, 4, 71, chain)
+        b.start(np.zeros(4))
+        total = b.restore_random(a)
+        picks.append(np.concatenate([[total], b.state()["accepted"], [b.state()["accepted_llh"]]]))
+    out["restore_random__picks"] = np.array(picks)
     # checkpoint / resume: 250 unsaved + 50 saved steps, SaveStep(), then a NEW
     # sampler is started, Restore()d from that tree and run on (TSimpleMCMC.H:282-352)
     a = cc.CpuChain("ref", cc.LLH_UNIT_GAUSS, 7, 31, 2)

@@ -45,7 +45,76 @@ GOLDEN_CHAINS = {
     "dummy100": (1, 100, 9, 0, 1200, None),
     "unit6_clamped": (0, 6, 3, 4, 1500, None),
     "hard6": (6, 6, 13, 2, 2500, 0.5),
+    # example4/Constrained.C: TConstrainedLikelihood (25 dimensions, a constraint on the sum) -- on
+    # the device a USER functor (tests/cpp/constrained_functor.cuh), not a built-in kernel
+    "constrained25": (8, 25, 51, 3, 3000, 70.0),
 }
+
+
+_USER_LIB = None
+
+
+def user_functor_library():
+    """tests/cpp/user_functor_lib.cu compiled by nvcc (once per session) into
+    tests/cpp/_build/libuser_functor.so: the USER's translation unit, with the
+    kernels of include/smcmc_device_functor.cuh instantiated for example4's
+    TConstrainedLikelihood written as a device functor."""
+    global _USER_LIB
+    if _USER_LIB is not None:
+        return _USER_LIB
+    import ctypes
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "root-simple-mcmc_b200", "smcmc_b200")
+    out = os.path.join(root, "tests", "cpp", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libuser_functor.so")
+    src = [os.path.join(root, "tests", "cpp", f) for f in ("user_functor_lib.cu", "constrained_functor.cuh")]
+    src.append(os.path.join(root, "include", "smcmc_device_functor.cuh"))
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in src):
+        subprocess.run(["nvcc", "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+                        "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(root, "include"),
+                        "-I", os.path.join(root, "tests", "cpp"), "-o", so, src[0],
+                        "-L", libdir, "-lsmcmc_b200", "-Xlinker", "-rpath," + libdir], check=True)
+    _USER_LIB = ctypes.CDLL(so)
+    return _USER_LIB
+
+
+def bind_likelihood_inputs(eng, kind, g=None):
+    """What a golden chain's likelihood needs before Start(): the error matrix of
+    TDummyLogLikelihood, or -- kind 8 -- the user functor registered with the engine."""
+    if kind == 1 and g is not None:
+        eng.set_error_matrix(g["dummy100_error"])
+    if kind == 8:
+        eng.bind_user_library(user_functor_library(), "user_constrained_bind")
+
+
+def run_debug_modes(c):
+    """The call sequence of the golden run "debug9" (tests/golden/make_golden.py):
+    regular steps, a forced step taken with metropolis = 2 (the idiom of
+    TSimpleMCMC.H:797-808), SetEstimatedCenter, scans of a Gaussian and of a uniform
+    dimension (:685-704), a forced step under the normal Metropolis rule, regular
+    steps again.  `c` has the methods of oracle.cpu_checkers.CpuChain; returns the
+    concatenated trace."""
+    parts = [c.step(60)]
+    c.force_step(np.linspace(-0.4, 0.4, 9))
+    parts.append(c.step(1, 2))
+    parts.append(c.step(5))
+    c.set_center(np.linspace(0.3, -0.3, 9))
+    c.set_scan(3)
+    parts.append(c.step(25))
+    c.set_scan(6)                       # a SetUniform dimension
+    parts.append(c.step(15))
+    c.set_scan(-1)
+    c.force_step(np.full(9, 0.05))
+    parts.append(c.step(1))
+    parts.append(c.step(80))
+    return {k: np.concatenate([p[k] for p in parts]) for k in ("accepted", "llh_accepted", "llh_proposed", "x", "sigma")}
+
+
+def configure_debug_modes(c):
+    c.set_gaussian(3, 0.7)
+    c.set_uniform(6, -1.5, 2.0)
 
 
 # ---------------------------------------------------------------------------

@@ -27,7 +27,7 @@ def test_header_symbols_are_exported():
     for name in names:
         assert hasattr(lib, name), "missing export " + name
     assert sorted(binding.EXPORTED_SYMBOLS) == names
-    assert lib.smcmc_abi_version() == 1
+    assert lib.smcmc_abi_version() == 2
 
 
 def test_struct_layouts_match_reference_event():

@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import GOLDEN_CHAINS, configure_golden, golden, golden_chain
+from helpers import GOLDEN_CHAINS, bind_likelihood_inputs, configure_golden, golden, golden_chain
 
 pytestmark = pytest.mark.gpu
 
@@ -42,8 +42,7 @@ def test_golden_chain(name):
     want = golden_chain(g, name)
     lo = max(0, chain - 2)
     eng = smcmc_b200.Engine(kind, dim, 4, seed=seed, chain_offset=lo)
-    if kind == smcmc_b200.LLH_DUMMY:
-        eng.set_error_matrix(g["dummy100_error"])
+    bind_likelihood_inputs(eng, kind, g)
     configure_golden(name, eng, _set_field)
     x0 = np.zeros(dim) if start is None else np.full(dim, start)
     ok = eng.start(x0)

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import GOLDEN_CHAINS, configure_golden, golden, golden_chain
+from helpers import GOLDEN_CHAINS, bind_likelihood_inputs, configure_golden, golden, golden_chain
 from test_gpu_chains import _set_field, close
 
 pytestmark = pytest.mark.gpu
@@ -135,8 +135,7 @@ def test_resident_reaches_the_golden_end_state(name):
     want = golden_chain(g, name)
     lo = max(0, chain - 2)
     eng = smcmc_b200.Engine(kind, dim, 4, seed=seed, chain_offset=lo)
-    if kind == smcmc_b200.LLH_DUMMY:
-        eng.set_error_matrix(g["dummy100_error"])
+    bind_likelihood_inputs(eng, kind, g)
     configure_golden(name, eng, _set_field)
     x0 = np.zeros(dim) if start is None else np.full(dim, start)
     eng.start(x0)

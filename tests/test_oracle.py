@@ -147,6 +147,49 @@ def test_restore_matches_golden(checkers, have_ref, which):
     assert np.array_equal(np.array([b.state()[k] for k in cc.STATE_FIELDS]), want["final_scalars"])
 
 
+@pytest.mark.parametrize("which", ["orc", "ref"])
+def test_debug_modes_match_golden(checkers, have_ref, which):
+    """ForceStep, SetScanDimension, SetEstimatedCenter (TSimpleMCMC.H:671-704,
+    :733-739, :811-830): the port and the reference build reproduce the golden run."""
+    if which == "ref" and not have_ref:
+        pytest.skip("reference-backed checker not built here")
+    from helpers import configure_debug_modes, run_debug_modes
+    want = golden_chain(golden("chains.npz"), "debug9")
+    cc = checkers
+    c = cc.CpuChain(which, cc.LLH_UNIT_GAUSS, 9, 61, 5)
+    configure_debug_modes(c)
+    c.start(np.full(9, 0.2))
+    got = run_debug_modes(c)
+    for k in got:
+        assert np.array_equal(got[k], want[k]), k
+    st = c.state()
+    assert np.array_equal(np.array([st[k] for k in cc.STATE_FIELDS]), want["final_scalars"])
+    assert np.array_equal(st["center"], want["final_center"])
+    assert np.array_equal(st["cov"], want["final_cov"])
+    # the forced point was taken (metropolis = 2), and scans only move their dimension
+    assert np.array_equal(want["x"][60], np.linspace(-0.4, 0.4, 9))
+    scan = want["x"][66:91]
+    assert np.all(scan[:, [0, 1, 2, 4, 5, 6, 7, 8]] == scan[0, [0, 1, 2, 4, 5, 6, 7, 8]])
+
+
+def test_constrained_posterior_closed_form(checkers):
+    """example4's likelihood has a closed-form posterior: precision
+    diag(1/s_i^2) + 1 1^T / 16^2.  The restated likelihood must be that quadratic form."""
+    cc = checkers
+    c = cc.CpuChain("orc", cc.LLH_CONSTRAINED, 25, 1, 0)
+    mu = np.array([76.0] * 24 + [80.0])
+    sg = np.array([76.0 * 0.08] * 24 + [2.0])
+    prec = np.diag(1.0 / sg ** 2) + np.ones((25, 25)) / 16.0 ** 2
+    b = mu / sg ** 2 + 1902.0 / 16.0 ** 2
+    mean = np.linalg.solve(prec, b)
+    rng = np.random.default_rng(5)
+    l0 = c.llh(mean)
+    for _ in range(50):
+        d = rng.normal(0, 3, 25)
+        want = l0 - 0.5 * d @ prec @ d
+        assert abs(c.llh(mean + d) - want) < 1e-9 * abs(want)
+
+
 # ---------------------------------------------------------------------------
 # TSimpleHMC (TSimpleHMC.H:119-973)
 # ---------------------------------------------------------------------------
