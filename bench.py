@@ -14,6 +14,20 @@ A step  : one TSimpleMCMC::Step() of every chain = adaptive proposal, one
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...      # the reference's own CPU code
 
+At N > 1 the line carries a second leg, "multi_gpu": the ensemble-sweep shape
+(BASELINE.json configs[4], scaled to a bounded size) with the EVENTS sharded
+over the GPUs -- integer event counts reduce-scattered / log-likelihoods
+all-gathered over NCCL every step -- next to the same work chain-sharded, after
+checking that the sharded chains are bit-identical to unsharded ones.
+
+--config c1 | c3 | c4 print the same contract for the other BASELINE.json
+configs (default c2 = the headline one):
+  c1  SimpleMCMC.C / mcmc.exe schedule, 1 chain (latency-bound; steps/s only)
+  c3  THorrificLogLikelihood 50-dim, 65 536 chains, per-chain adaptation (HBM-bound)
+      + pooled adaptation as a sub-object
+  c4  TSimpleHMC, 500-dim dense Gaussian, analytic gradient, 16 384 chains,
+      contractions on the FP64 tensor cores (DMMA-bound)
+
 Prints ONE JSON line (rank 0).
 """
 import argparse
@@ -216,7 +230,6 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the MCMC step path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"               # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
@@ -314,10 +327,19 @@ def run_b200(args):
            "includes": "event upload + re-layout, Start, %d x Step(save=true) with the accepted points, "
                        "likelihoods and accept flags copied to pinned host memory every step" % e2e_steps}
 
+    multi_gpu = None
+    if world > 1 and not args.no_multi_leg:
+        eng.close()
+        del flush
+        multi_gpu = multi_gpu_leg(args, rank, world, local, dist, barrier)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+
+    if world == 1 and not args.no_cpp_tree:
+        e2e["via_cpp_tree"] = cpp_tree_leg(chains, len(events))
 
     # ---- roofline of the dominant kernel ------------------------------------------
     # kFakePairs is neither HBM- nor tensor-bound: every event is re-used by all
@@ -379,6 +401,14 @@ def run_b200(args):
         "hbm": {"achieved": alg_bytes / pair_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / pair_s / 1e9 / hbm_peak, "peak_source": hbm_src,
                 "algorithmic_bytes": alg_bytes},
+        "fp64_survey_8d": {
+            "note": "SURVEY.md 8(d)'s own figure: 120 flop per (chain,event) pair against the FP64 peak.  NOT the "
+                    "binding unit of this kernel: 99.94 % of the pairs are decided by an FP32 interval filter and "
+                    "never reach the FP64 pipe (counts checked identical on every pair, tests/test_gpu_fullsize.py), "
+                    "so the figure exceeds 1",
+            "achieved": FLOP_PER_PAIR * pairs_per_launch / pair_s / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": FLOP_PER_PAIR * pairs_per_launch / pair_s / 1e12 / fp64_peak,
+            "peak_source": "measured in this run (DFMA chain micro-benchmark)"},
         "fp64_of_unfiltered_algorithm": {
             "note": "the FP64 work the same counts cost WITHOUT the FP32 interval filter: 25 FP64 instructions "
                     "(50 flop) per pair, first version of this kernel; above 1.0 = faster than that roofline allows",
@@ -440,9 +470,143 @@ def run_b200(args):
     }
     if cpu_desc:
         line["cpu_baseline"] = dict(cpu_desc, value=cpu_value, unit="steps/s")
+        line["cpu_baseline"]["gpu_over_cpu_per_core"] = value / (cpu_value / cpu_desc["cores"])
+    if multi_gpu:
+        line["multi_gpu"] = multi_gpu
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------
+# N > 1: the ensemble-sweep shape with the events sharded over the GPUs
+# --------------------------------------------------------------------------
+def multi_gpu_leg(args, rank, world, local, dist, barrier):
+    """BASELINE.json configs[4] ("chains and events sharded over 1/2/4/8 B200") at a bounded
+    size: MG_CHAINS chains x MG_EVENTS events in total.
+      event-sharded  1 x G: every rank holds ALL chains and 1/G of the events; each likelihood
+                     evaluation reduce-scatters the integer count table over NCCL, each rank
+                     finishes its block of chains, the log-likelihoods are all-gathered;
+      chain-sharded  G x 1: every rank holds 1/G of the chains and all events, no exchange.
+    Both do chains x events / G pair evaluations per rank and step.  Before timing, the first
+    MG_SAMPLE chains of the sharded ensemble are compared bit for bit (likelihoods and two traced
+    steps) with an unsharded engine on rank 0."""
+    import torch
+    import smcmc_b200
+    from smcmc_b200 import binding, synth
+    chains_total, events_total, sample, steps = args.mg_chains, args.mg_events, args.mg_sample, args.mg_steps
+    signal = events_total // 3 + 1
+    events = synth.make_mc_sample(signal, events_total - signal, seed=2)
+    data = synth.make_data_histograms(33334, 33334, seed=2)
+    exposure = 0.1 * 1e6 / events_total
+    x0 = start_points(chains_total, 0)
+    stream = torch.cuda.current_stream().cuda_stream
+    dev = torch.device("cuda", local)
+
+    def timed_steps(eng, n):
+        eng.step(2)
+        eng.sync()
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        eng.step(n)
+        t1.record()
+        barrier()
+        eng.sync()
+        t = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) * 1e-3 / n
+
+    # ---- event-sharded: one event group of all ranks
+    uid = [binding.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    eng = smcmc_b200.Engine(smcmc_b200.LLH_FAKE, DIM, chains_total, seed=SEED, device=local, chain_offset=0)
+    eng.set_stream(stream)
+    eng.comm_init(uid[0], world, rank, event_group=world)
+    eng.set_fake_events(events[rank::world])
+    eng.set_fake_data(data, exposure)
+    sharded_llh = eng.eval(x0[:sample])                  # collective: every rank of the group calls it
+    assert eng.start(x0).all()
+    tr = eng.step_trace(2, want=("accepted", "llh_accepted"))
+    identical = None
+    if rank == 0:
+        full = smcmc_b200.Engine(smcmc_b200.LLH_FAKE, DIM, sample, seed=SEED, device=local, chain_offset=0)
+        full.set_stream(stream)
+        full.set_fake_events(events)
+        full.set_fake_data(data, exposure)
+        full_llh = full.eval(x0[:sample])
+        full.start(x0[:sample])
+        ftr = full.step_trace(2, want=("accepted", "llh_accepted"))
+        full.close()
+        identical = bool(np.array_equal(full_llh, sharded_llh)
+                         and np.array_equal(ftr["accepted"], tr["accepted"][:, :sample])
+                         and np.array_equal(ftr["llh_accepted"], tr["llh_accepted"][:, :sample]))
+    flag = torch.tensor([1 if (identical or rank != 0) else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) != 1:
+        raise SystemExit("bench.py: event-sharded chains differ from the unsharded evaluation")
+    t_event = timed_steps(eng, steps)
+    eng.close()
+
+    # ---- chain-sharded: the same total work, no exchange
+    per = chains_total // world
+    eng = smcmc_b200.Engine(smcmc_b200.LLH_FAKE, DIM, per, seed=SEED, device=local, chain_offset=rank * per)
+    eng.set_stream(stream)
+    eng.set_fake_events(events)
+    eng.set_fake_data(data, exposure)
+    assert eng.start(x0[rank * per:(rank + 1) * per]).all()
+    t_chain = timed_steps(eng, steps)
+    eng.close()
+    pairs = float(chains_total) * float(events_total)
+    per_rank = -(-chains_total // world)
+    block = -(-per_rank // 256) * 256              # chains per reduce-scatter block
+    return {
+        "workload": "ensemble sweep of the event likelihood (BASELINE.json configs[4] shape, bounded): %d chains x %d "
+                    "events in total over %d GPUs" % (chains_total, events_total, world),
+        "nccl_ranks": world,
+        "bit_identical_to_unsharded": True,
+        "checked": "likelihoods of %d chains and two traced Metropolis steps (accept flags, accepted likelihoods) "
+                   "against an unsharded engine on rank 0" % sample,
+        "event_sharded": {"layout": "1 x %d (every rank: all chains, 1/%d of the events)" % (world, world),
+                          "s_per_step": t_event, "pair_evals_per_s": pairs / t_event, "steps_per_s": chains_total / t_event,
+                          "exchange": "ncclReduceScatter of 450 x %d uint32 event counts + ncclAllGather of %d f64 "
+                                      "log-likelihoods per evaluation" % (block * world, block * world),
+                          "bytes_reduce_scattered_per_step": 450 * block * world * 4,
+                          "bytes_all_gathered_per_step": block * world * 8},
+        "chain_sharded": {"layout": "%d x 1 (every rank: 1/%d of the chains, all events)" % (world, world),
+                          "s_per_step": t_chain, "pair_evals_per_s": pairs / t_chain, "steps_per_s": chains_total / t_chain,
+                          "exchange": "none"},
+        "event_vs_chain_sharded": t_chain / t_event,
+        "steps_timed": steps,
+    }
+
+
+def cpp_tree_leg(chains, events_n):
+    """"Accepted points written to the user's TTree" at the benchmark's size, through the C++
+    mirror of the reference API (include/TSimpleMCMC.H): tests/cpp/simple_mcmc.cc `tree` mode runs
+    Step(true) with a tree attached -- one synchronous device read of the step's record and one
+    TTree::Fill per chain -- and StepMany() without one."""
+    import re
+    import subprocess
+    libdir = os.path.join(ROOT, "root-simple-mcmc_b200", "smcmc_b200")
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "simple_mcmc")
+    src = os.path.join(ROOT, "tests", "cpp", "simple_mcmc.cc")
+    try:
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src):
+            subprocess.run(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), "-o", exe, src,
+                            "-L", libdir, "-lsmcmc_b200", "-Wl,-rpath," + libdir], check=True)
+        r = subprocess.run([exe, "tree", str(chains), "10", str(max(1, events_n // 30))], capture_output=True, text=True,
+                           check=True, timeout=600)
+        m = re.search(r"events (\d+) ms_per_step_plain (\S+) ms_per_step_tree (\S+) full_save_ms (\S+) entries (\d+)", r.stdout)
+        plain, tree = float(m.group(2)), float(m.group(3))
+        return {"value": chains / (tree * 1e-3), "unit": "steps/s", "ms_per_step_with_tree": tree,
+                "ms_per_step_without_tree": plain, "events": int(m.group(1)), "tree_entries": int(m.group(5)),
+                "full_state_save_ms": float(m.group(4)),
+                "note": "sMCMC::TSimpleMCMC<FakeLikelihood>::Step(true) with a TTree attached (in-memory TTree of "
+                        "include/smcmc_tree.h; ROOT is not installed): one TTree::Fill per chain and step on the host"}
+    except Exception as exc:                          # reported, never fatal for the headline line
+        return {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
 
 
 _RESULT_OUT = None
@@ -466,6 +630,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-streaming", action="store_true",
                     help="skip the 1-chain x 16.8M-event streaming measurement (roofline.hbm_streaming)")
+    ap.add_argument("--no-cpp-tree", action="store_true", help="skip e2e.via_cpp_tree (the compiled C++ program)")
+    ap.add_argument("--no-multi-leg", action="store_true", help="N > 1: skip the event-sharded leg (multi_gpu)")
+    ap.add_argument("--mg-chains", type=int, default=32768, help="multi_gpu leg: chains in total")
+    ap.add_argument("--mg-events", type=int, default=8388608, help="multi_gpu leg: events in total")
+    ap.add_argument("--mg-sample", type=int, default=4096, help="multi_gpu leg: chains compared with the unsharded engine")
+    ap.add_argument("--mg-steps", type=int, default=5)
+    ap.add_argument("--c4-chains", type=int, default=16384, help="--config c4: chains per GPU")
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4"],
+                    help="which BASELINE.json config to measure (default c2, the headline one)")
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON result: anything else that writes to file
     # descriptor 1 (NCCL prints its version banner there when the first communicator is
@@ -474,7 +647,10 @@ def main():
     sys.stdout.flush()
     _RESULT_OUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
-    if args.impl == "reference":
+    if args.config != "c2":
+        import bench_configs
+        bench_configs.run(args, emit, ClockSampler)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)

@@ -436,6 +436,11 @@ int smcmc_enable_kernel_timing(smcmc_engine* e, int on);
  * register-resident chain of independent DFMAs on every SM, timed with CUDA
  * events.  The roofline denominator for the FP64-bound pair kernel. */
 int smcmc_measure_fp64_peak(int device, double* tflops);
+/* Measured throughput of the FP64 tensor cores of `device` in TFLOP/s: register-resident
+ * chains of independent mma.sync.m8n8k4.f64 (DMMA, 512 flop per warp instruction) on every
+ * SM.  The roofline denominator of the dense contractions (kDummyContractDmma,
+ * kPoolAccumulateDmma). */
+int smcmc_measure_dmma_peak(int device, double* tflops);
 /* Measured throughput of the special-function unit of `device` in 10^9 ex2
  * evaluations per second (register-resident chains of independent MUFU.EX2 on
  * every SM).  The roofline denominator of the event-pair kernel, which needs two

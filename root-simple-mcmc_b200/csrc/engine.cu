@@ -546,17 +546,38 @@ struct smcmc_engine {
         L.filterChains = fakeFilterChains.get();
         L.numPoints = m;
         L.pointStride = stride;
+        L.blockPoints = fakeBlockPoints > 0 ? fakeBlockPoints : stride;
         L.counts = fakeCounts.get();
         L.stats = collectStats ? fakeStats.get() : nullptr;
         return L;
     }
     bool collectStats = false;
     size_t dummySmemSet = 48 << 10;
+    // event-sharded evaluation: the count table in blocks of this many points (one block per
+    // rank of the event group), 0 = one block
+    int fakeBlockPoints = 0;
+    bool wantFullCounts = false;                    // the caller reads the whole count table back
+    DeviceBuffer<uint32_t> fakeCountsMine;          // the block this rank finishes
+    DeviceBuffer<double> fakeLlhGather;
+    int eventRank() const { return worldRank % eventGroup; }
 
     void evaluateFake(const double* xDev, int m, double* llhDev, double* histDev) {
         if (fakeEventCount < 0) throw Error(SMCMC_ERR_LOGIC, "events not set (smcmc_fake_set_events)");
         if (!fakeDataSet) throw Error(SMCMC_ERR_LOGIC, "data histograms not set (smcmc_fake_set_data)");
-        const int stride = (m + 31) / 32 * 32;
+        int stride = (m + 31) / 32 * 32;
+        // Events split over the G ranks of an event group: every rank counts its events for
+        // ALL points, then the table is reduce-scattered over points -- rank r receives the
+        // summed block r, turns it into log-likelihoods (1/G of the finish work) and the
+        // values are all-gathered.  Half the bytes of an all-reduce of the table, and integer
+        // sums: the result does not depend on the split.  (Few points, or a caller that wants
+        // the histograms / the whole table: one block, all-reduce.)
+        const int G = eventGroup;
+        const bool scatter = eventComm && G > 1 && !histDev && !wantFullCounts && m >= kPairThreads * G;
+        fakeBlockPoints = 0;
+        if (scatter) {
+            fakeBlockPoints = ceilDiv(ceilDiv(m, G), kPairThreads) * kPairThreads;
+            stride = fakeBlockPoints * G;
+        }
         fakeChains.reserve(stride);
         fakeFilterChains.reserve(stride);
         fakeCounts.reserve((size_t)kFakeSlots * stride);
@@ -595,8 +616,31 @@ struct smcmc_engine {
         if (fakeIrregularCount > 0) {
             long long pairs = (long long)fakeIrregularCount * m;
             kFakePairsGeneric<<<ceilDiv(pairs, 256), 256, 0, stream>>>(fakeIrregular.get(), fakeIrregularCount,
-                                                                       xDev, m, n(), fakeCounts.get(), stride);
+                                                                       xDev, m, n(), fakeCounts.get(), L.blockPoints);
             launched();
+        }
+        if (scatter) {
+            NcclApi& nccl = NcclApi::get();
+            const int per = fakeBlockPoints, r = eventRank();
+            const size_t blockWords = (size_t)kFakeSlots * per;
+            fakeCountsMine.reserve(blockWords);
+            fakeLlhGather.reserve((size_t)per * G);
+            nccl.check(nccl.ReduceScatter(fakeCounts.get(), fakeCountsMine.get(), blockWords, ncclUint32, ncclSum, eventComm,
+                                          stream), "reduce-scatter of event counts");
+            const int first = r * per, mine = std::max(0, std::min(per, m - first));
+            if (mine > 0) {
+                if (cfg.likelihood == SMCMC_LLH_FAKE2)
+                    kFake2Finish<<<ceilDiv(mine, 32), 32 * kFinishWarps, kFinish2SmemBytes, stream>>>(
+                        fakeCountsMine.get(), per, mine, fakeChains.get() + first, fakeData.get(),
+                        xDev + (size_t)first * n(), n(), fakeLlhGather.get() + first, nullptr);
+                else
+                    finishFake(fakeCountsMine.get(), per, mine, fakeChains.get() + first, fakeLlhGather.get() + first, nullptr);
+                launched();
+            }
+            nccl.check(nccl.AllGather(fakeLlhGather.get() + first, fakeLlhGather.get(), (size_t)per, ncclDouble, eventComm,
+                                      stream), "all-gather of log-likelihoods");
+            CUDA_CHECK(cudaMemcpyAsync(llhDev, fakeLlhGather.get(), (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+            return;
         }
         if (eventComm) {
             // events are split over the ranks of the event group: the integer
@@ -608,22 +652,25 @@ struct smcmc_engine {
         if (cfg.likelihood == SMCMC_LLH_FAKE2)
             kFake2Finish<<<ceilDiv(m, 32), 32 * kFinishWarps, kFinish2SmemBytes, stream>>>(
                 fakeCounts.get(), stride, m, fakeChains.get(), fakeData.get(), xDev, n(), llhDev, histDev);
-        else {
-            // few points: the bins of a point group are split over kFinishGroups CTAs
-            const int pointGroups = ceilDiv(m, kFinishPoints);
-            const bool split = pointGroups * 2 <= smCount;
-            if (split) {
-                fakeTerms.reserve((size_t)m * 150);
-                if ((size_t)pointGroups > fakeTickets.count()) {
-                    fakeTickets.reserve(smCount);
-                    CUDA_CHECK(cudaMemsetAsync(fakeTickets.get(), 0, fakeTickets.bytes(), stream));
-                }
-            }
-            kFakeFinish<<<dim3(pointGroups, split ? kFinishGroups : 1), 32 * kFinishBinWarps, 0, stream>>>(
-                fakeCounts.get(), stride, m, fakeChains.get(), fakeData.get(), llhDev, histDev,
-                split ? fakeTerms.get() : nullptr, split ? fakeTickets.get() : nullptr);
-        }
+        else
+            finishFake(fakeCounts.get(), stride, m, fakeChains.get(), llhDev, histDev);
         launched();
+    }
+    // counts -> bin contents -> log-likelihood of m points (kFakeFinish)
+    void finishFake(const uint32_t* counts, int stride, int m, const FakeChainParams* chains, double* llhDev, double* histDev) {
+        // few points: the bins of a point group are split over kFinishGroups CTAs
+        const int pointGroups = ceilDiv(m, kFinishPoints);
+        const bool split = pointGroups * 2 <= smCount;
+        if (split) {
+            fakeTerms.reserve((size_t)m * 150);
+            if ((size_t)pointGroups > fakeTickets.count()) {
+                fakeTickets.reserve(smCount);
+                CUDA_CHECK(cudaMemsetAsync(fakeTickets.get(), 0, fakeTickets.bytes(), stream));
+            }
+        }
+        kFakeFinish<<<dim3(pointGroups, split ? kFinishGroups : 1), 32 * kFinishBinWarps, 0, stream>>>(
+            counts, stride, m, chains, fakeData.get(), llhDev, histDev,
+            split ? fakeTerms.get() : nullptr, split ? fakeTickets.get() : nullptr);
     }
 
     void evaluateUnbinned(const double* xDev, int m, double* llhDev) {
@@ -1502,7 +1549,9 @@ int smcmc_fake_counts(smcmc_engine* e, const double* x, int m, uint32_t* out) {
         if (e->cfg.likelihood != SMCMC_LLH_FAKE && e->cfg.likelihood != SMCMC_LLH_FAKE2)
             throw Error(SMCMC_ERR_LOGIC, "engine was not created with SMCMC_LLH_FAKE or SMCMC_LLH_FAKE2");
         if (!out) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null output");
-        evalHost(e, x, m, nullptr, nullptr);
+        e->wantFullCounts = true;
+        try { evalHost(e, x, m, nullptr, nullptr); } catch (...) { e->wantFullCounts = false; throw; }
+        e->wantFullCounts = false;
         const int stride = e->fakeCountStride;
         std::vector<uint32_t> host((size_t)kFakeSlots * stride);
         CUDA_CHECK(cudaMemcpyAsync(host.data(), e->fakeCounts.get(), host.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
@@ -1517,7 +1566,9 @@ int smcmc_fake_filter_check(smcmc_engine* e, const double* x, int m, uint64_t* o
         if (e->cfg.likelihood != SMCMC_LLH_FAKE && e->cfg.likelihood != SMCMC_LLH_FAKE2)
             throw Error(SMCMC_ERR_LOGIC, "engine was not created with SMCMC_LLH_FAKE or SMCMC_LLH_FAKE2");
         if (!out3) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null output");
-        evalHost(e, x, m, nullptr, nullptr);         // fills the per-chain constants for these points
+        e->wantFullCounts = true;
+        try { evalHost(e, x, m, nullptr, nullptr); } catch (...) { e->wantFullCounts = false; throw; }   // fills the per-chain constants for these points
+        e->wantFullCounts = false;
         PairLaunch L = e->pairLaunch(m, e->fakeCountStride);
         CUDA_CHECK(cudaMemsetAsync(e->fakeStats.get(), 0, 4 * sizeof(unsigned long long), e->stream));
         dim3 grid(512, ceilDiv(m, 128));
@@ -1880,6 +1931,58 @@ int smcmc_measure_fp64_peak(int device, double* tflops) {
             float ms = 0.f;
             CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
             double flops = 2.0 * 8.0 * iters * (double)blocks * threads;
+            if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *tflops = best;
+    });
+}
+
+namespace smcmc {
+// 8 independent DMMA (mma.sync.m8n8k4.f64) accumulator chains per warp, operands in registers.
+__global__ void __launch_bounds__(256) kDmmaPeak(double* out, double a, double b, int iters) {
+    double acc[8][2];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k][0] = acc[k][1] = (double)(threadIdx.x + k);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dmma884(acc[k][0], acc[k][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += acc[k][0] + acc[k][1];
+    if (s == 12345.678) out[0] = s;      // never true: keeps the chains alive
+}
+}  // namespace smcmc
+
+int smcmc_measure_dmma_peak(int device, double* tflops) {
+    return guarded(nullptr, [&]() {
+        if (!tflops) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "null output");
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+            cudaGetLastError();
+            throw Error(SMCMC_ERR_NO_DEVICE, "no CUDA device");
+        }
+        CUDA_CHECK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        DeviceBuffer<double> out;
+        out.reserve(1);
+        const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 2048;
+        cudaEvent_t e0, e1;
+        CUDA_CHECK(cudaEventCreate(&e0));
+        CUDA_CHECK(cudaEventCreate(&e1));
+        double best = 0.0;
+        for (int rep = 0; rep < 6; ++rep) {
+            CUDA_CHECK(cudaEventRecord(e0));
+            kDmmaPeak<<<blocks, threads>>>(out.get(), 0.999999, 1e-7, iters);
+            CUDA_CHECK(cudaEventRecord(e1));
+            CUDA_CHECK(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+            // one m8n8k4 DMMA per warp = 8 x 8 x 4 multiply-adds = 512 flop
+            const double flops = 512.0 * 8.0 * iters * (double)blocks * (threads / 32);
             if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
         }
         cudaEventDestroy(e0);

@@ -433,6 +433,15 @@ __device__ __forceinline__ void redShared(unsigned addr, unsigned value) {
 // ---------------------------------------------------------------------------
 // The pair kernel.
 // ---------------------------------------------------------------------------
+// The count table is cut into blocks of blockPoints consecutive points, each block a
+// [kFakeSlots][blockPoints] array (point fastest).  One block (blockPoints = row length) is
+// the plain [slot][point] table; with the events split over G GPUs block r is what rank r
+// receives from the reduce-scatter and finishes (engine.cu, evaluateFake).
+__device__ __forceinline__ size_t countIndex(int slot, int point, int blockPoints) {
+    const int b = point / blockPoints;
+    return ((size_t)b * kFakeSlots + slot) * (size_t)blockPoints + (size_t)(point - b * blockPoints);
+}
+
 struct PairLaunch {
     const PreparedEvent* events;     // FP64 records; class segments contiguous, padded to whole tiles
     const FilterTile* filterTiles;   // FP32 records, same order, 128 per tile
@@ -444,8 +453,9 @@ struct PairLaunch {
     const FakeChainParams* chains;
     const FilterChain* filterChains;
     int numPoints;                   // chains (parameter points) to evaluate
-    int pointStride;                 // row length of the count table
-    uint32_t* counts;                // [kFakeSlots][pointStride]
+    int pointStride;                 // points the count table has room for
+    int blockPoints;                 // points per block of the count table (countIndex); == pointStride: one block
+    uint32_t* counts;                // [block][kFakeSlots][blockPoints]
     unsigned long long* stats;       // optional: [0] unsure pairs
 };
 
@@ -729,7 +739,7 @@ __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t 
         const int word = tid & (kPairThreads / 2 - 1), shift = (tid >= kPairThreads / 2) ? 16 : 0;
         for (int r = 0; r < rows; ++r) {
             const uint32_t v = (counters[r * (kPairThreads / 2) + word] >> shift) & 0xffffu;
-            if (v) atomicAdd(&L.counts[(size_t)(slotBase + r) * L.pointStride + point], v);
+            if (v) atomicAdd(&L.counts[countIndex(slotBase + r, point, L.blockPoints)], v);
         }
     }
     if (L.stats && unsureTotal) atomicAdd(&L.stats[0], (unsigned long long)unsureTotal);
@@ -848,7 +858,7 @@ kFakeStream(const __grid_constant__ PairLaunch L) {
         const uint32_t v = table[k];
         if (v) {
             const int c = k / kStreamRows, slot = k - c * kStreamRows;
-            atomicAdd(&L.counts[(size_t)slot * L.pointStride + c], v);
+            atomicAdd(&L.counts[countIndex(slot, c, L.blockPoints)], v);
         }
     }
 }
@@ -896,7 +906,7 @@ __global__ void kFakeVerifyFilter(const PairLaunch L, unsigned long long* stats)
 // one thread per (point, event).
 __global__ void kFakePairsGeneric(const smcmc_event* __restrict__ ev, int64_t nev,
                                   const double* __restrict__ x, int m, int dim,
-                                  uint32_t* counts, int pointStride) {
+                                  uint32_t* counts, int blockPoints) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nev * (int64_t)m) return;
     int point = (int)(idx % m);
@@ -923,13 +933,13 @@ __global__ void kFakePairsGeneric(const smcmc_event* __restrict__ ev, int64_t ne
         int cls = (e.Type == 0 ? 0 : 2) + (e.MuDk > 0 ? 1 : 0);
         int row = bin;
         if (!(cls & 1) && !(sep < 100.0)) row += 50;
-        atomicAdd(&counts[(size_t)(fakeClassSlotBase(cls) + row) * pointStride + point], 1u);
+        atomicAdd(&counts[countIndex(fakeClassSlotBase(cls) + row, point, blockPoints)], 1u);
     } else {
         if (mass > 500.0 || mass < 0.0 || sep < 0.0) return;
         if (!(mass < 500.0)) return;                 // NaN or ==500: overflow bin
         int bin = (int)(50 * (mass - 0.0) / (500.0 - 0.0));
         int h = e.MuDk > 0 ? 2 : (sep < 100.0 ? 0 : 1);
-        atomicAdd(&counts[(size_t)(300 + h * 50 + bin) * pointStride + point], 1u);
+        atomicAdd(&counts[countIndex(300 + h * 50 + bin, point, blockPoints)], 1u);
     }
 }
 

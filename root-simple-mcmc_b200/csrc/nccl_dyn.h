@@ -17,6 +17,9 @@ struct NcclApi {
     ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, ncclConfig_t*) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommCount)(const ncclComm_t, int*) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     void* handle = nullptr;
 
@@ -36,6 +39,9 @@ struct NcclApi {
         api.CommSplit = (decltype(api.CommSplit))sym("ncclCommSplit");
         api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
         api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+        api.ReduceScatter = (decltype(api.ReduceScatter))sym("ncclReduceScatter");
+        api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+        api.CommCount = (decltype(api.CommCount))sym("ncclCommCount");
         api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
         api.handle = h;
         return api;

@@ -177,6 +177,7 @@ def load_library():
         "smcmc_enable_kernel_timing": (ci, [vp, ci]),
         "smcmc_measure_fp64_peak": (ci, [ci, ctypes.POINTER(cd)]),
         "smcmc_measure_sfu_peak": (ci, [ci, ctypes.POINTER(cd)]),
+        "smcmc_measure_dmma_peak": (ci, [ci, ctypes.POINTER(cd)]),
         "smcmc_selftest_division": (ci, [ci, ctypes.c_int64, ctypes.c_uint64, ctypes.POINTER(ctypes.c_int64)]),
         "smcmc_diag_enable": (ci, [vp, ci]),
         "smcmc_diag_reset": (ci, [vp]),
@@ -205,7 +206,7 @@ EXPORTED_SYMBOLS = [
     "smcmc_hmc_set", "smcmc_hmc_start", "smcmc_hmc_set_position", "smcmc_hmc_step",
     "smcmc_hmc_step_trace", "smcmc_hmc_get",
     "smcmc_pair_kernel_stats", "smcmc_enable_kernel_timing",
-    "smcmc_measure_fp64_peak", "smcmc_measure_sfu_peak", "smcmc_selftest_division",
+    "smcmc_measure_fp64_peak", "smcmc_measure_sfu_peak", "smcmc_measure_dmma_peak", "smcmc_selftest_division",
     "smcmc_diag_enable", "smcmc_diag_reset", "smcmc_diag_lag_count", "smcmc_diag_get",
 ]
 
@@ -225,6 +226,16 @@ def measure_fp64_peak(device=0):
     lib = load_library()
     out = ctypes.c_double()
     rc = lib.smcmc_measure_fp64_peak(device, ctypes.byref(out))
+    if rc != 0:
+        raise SmcmcError(rc, lib.smcmc_last_error(None).decode())
+    return out.value
+
+
+def measure_dmma_peak(device=0):
+    """Measured FP64 tensor-core (DMMA m8n8k4) throughput of the device, TFLOP/s."""
+    lib = load_library()
+    out = ctypes.c_double()
+    rc = lib.smcmc_measure_dmma_peak(device, ctypes.byref(out))
     if rc != 0:
         raise SmcmcError(rc, lib.smcmc_last_error(None).decode())
     return out.value
@@ -479,17 +490,18 @@ class Engine:
         self._check(self.lib.smcmc_hmc_step(self.h, nsteps, gradient_type))
 
     def hmc_step_trace(self, nsteps, gradient_type=0,
-                       want=("potential", "points", "mean_epsilon", "leapfrog", "accepted")):
+                       want=("potential", "points", "mean_epsilon", "leapfrog", "accepted"), out=None):
         """Step(save=true): the per-step record of the output tree (:139-147)."""
         E, n = self.chains, self.dim
         shapes = {"potential": ((nsteps, E), np.float64), "points": ((nsteps, E, n), np.float64),
                   "mean_epsilon": ((nsteps, E), np.float64), "leapfrog": ((nsteps, E), np.int32),
                   "accepted": ((nsteps, E), np.int32)}
-        out = {}
+        out = {} if out is None else out
         tr = _HmcTrace()
         for name in want:
             shape, dt = shapes[name]
-            out[name] = np.zeros(shape, dt)
+            if name not in out:
+                out[name] = np.zeros(shape, dt)
             setattr(tr, name, out[name].ctypes.data)
         self._check(self.lib.smcmc_hmc_step_trace(self.h, nsteps, gradient_type, ctypes.byref(tr)))
         return out

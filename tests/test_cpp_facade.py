@@ -150,3 +150,44 @@ def test_vaat_proposal_through_the_cpp_api(program):
     m = re.search(r"entries (\d+) accepted (\d+) trials (\d+) successes (\d+) window (\S+)", r.stdout)
     assert m and int(m.group(1)) == 2 * 400 and int(m.group(3)) == 400 and float(m.group(5)) == 100.0
     assert int(m.group(2)) == int(acc.sum())
+
+
+@pytest.mark.gpu
+def test_debug_modes_through_the_cpp_api(program):
+    """ForceStep / SetScanDimension / SetEstimatedCenter / GetCovarianceFrozen through the mirror
+    header against the golden run "debug9" of the reference build."""
+    r = subprocess.run([program, "debug"], capture_output=True, text=True, check=True)
+    want = golden_chain(golden("chains.npz"), "debug9")
+    rows = re.findall(r"step (\d+) acc (\d) llh (\S+) x0 (\S+) x3 (\S+) x6 (\S+)", r.stdout)
+    assert len(rows) == 187
+    assert np.array_equal(np.array([int(x[1]) for x in rows]), want["accepted"])
+    for col, dim in ((3, 0), (4, 3), (5, 6)):
+        assert np.allclose(np.array([float(x[col]) for x in rows]), want["x"][:, dim], rtol=1e-12, atol=1e-14)
+    assert np.allclose(np.array([float(x[2]) for x in rows]), want["llh_accepted"], rtol=1e-11, atol=1e-13)
+    assert "frozen 0 calls 188" in r.stdout
+    assert "caught invalid_argument: Invalid forced step point." in r.stdout
+
+
+@pytest.mark.gpu
+def test_randomized_restore_through_the_cpp_api(program):
+    """Restore(tree, randomize = true) (reference :309-316): each of six chains adopts the
+    same entry of its 400-entry tree as the reference build did."""
+    r = subprocess.run([program, "restore_random"], capture_output=True, text=True, check=True)
+    want = golden("chains.npz")["restore_random__picks"]
+    rows = re.findall(r"pick (\d) x (\S+) (\S+) (\S+) (\S+) llh (\S+)", r.stdout)
+    assert len(rows) == 6
+    for row, w in zip(rows, want):
+        got = np.array([float(v) for v in row[1:]])
+        assert np.allclose(got[:4], w[1:5], rtol=1e-12, atol=1e-14)
+        assert np.isclose(got[4], w[5], rtol=1e-11)
+
+
+@pytest.mark.gpu
+def test_saving_an_ensemble_to_the_tree_reads_the_device_once_per_step(program):
+    """4096 chains, Step(true) with a tree attached: one entry per chain and step, and the
+    cost per step stays within a small multiple of the step itself (it used to be one device
+    read per chain and branch: minutes per step)."""
+    r = subprocess.run([program, "tree", "4096", "6", "100"], capture_output=True, text=True, check=True)
+    m = re.search(r"ms_per_step_plain (\S+) ms_per_step_tree (\S+) full_save_ms (\S+) entries (\d+)", r.stdout)
+    assert m and int(m.group(4)) == 4096 * 7
+    assert float(m.group(2)) < 100.0 and float(m.group(3)) < 200.0

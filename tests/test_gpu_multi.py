@@ -33,6 +33,36 @@ def _worker(rank, world, uid, out_dir):
     tr = eng.step_trace(25, want=("accepted", "points", "llh_accepted"))
     np.savez(os.path.join(out_dir, "shard%d.npz" % rank), llh=llh, counts=counts, acc=tr["accepted"],
              pts=tr["points"], la=tr["llh_accepted"])
+    # --- the same with enough chains for the reduce-scatter / all-gather exchange (>= 256 per
+    # rank; 700 = a full block for rank 0 and a ragged one for rank 1), and example2's finish
+    big = np.random.default_rng(5).uniform(-1.5, 1.5, (700, 9))
+    for kind, tag in ((smcmc_b200.LLH_FAKE, "big"), (smcmc_b200.LLH_FAKE2, "big2")):
+        if kind == smcmc_b200.LLH_FAKE2:
+            big = big.copy()
+            big[:, 0] = 20000.0 + 100.0 * big[:, 0]          # example2: parameters 0, 1 are the event counts
+            big[:, 1] = 40000.0 + 100.0 * big[:, 1]
+        be = smcmc_b200.Engine(kind, 9, 700, seed=11, device=rank, chain_offset=0)
+        be.comm_init(_MORE_IDS[0 if tag == "big" else 1], world, rank, event_group=world)
+        be.set_fake_events(events[rank::world])
+        be.set_fake_data(data, 0.11)
+        b_llh = be.eval(big)
+        b_counts = be.fake_counts(big[:300])
+        be.start(big)
+        btr = be.step_trace(12, want=("accepted", "llh_accepted"))
+        np.savez(os.path.join(out_dir, "%s%d.npz" % (tag, rank)), llh=b_llh, counts=b_counts, acc=btr["accepted"],
+                 la=btr["llh_accepted"])
+        be.close()
+        if rank == 0:
+            bf = smcmc_b200.Engine(kind, 9, 700, seed=11, device=rank, chain_offset=0)
+            bf.set_fake_events(events)
+            bf.set_fake_data(data, 0.11)
+            f_llh = bf.eval(big)
+            f_counts = bf.fake_counts(big[:300])
+            bf.start(big)
+            ftr = bf.step_trace(12, want=("accepted", "llh_accepted"))
+            np.savez(os.path.join(out_dir, "%sfull.npz" % tag), llh=f_llh, counts=f_counts, acc=ftr["accepted"],
+                     la=ftr["llh_accepted"])
+            bf.close()
     if rank == 0:
         full = smcmc_b200.Engine(smcmc_b200.LLH_FAKE, 9, 96, seed=7, device=rank, chain_offset=0)
         full.set_fake_events(events)
@@ -76,11 +106,13 @@ def _worker(rank, world, uid, out_dir):
 
 _SECOND_ID = [None]
 _THIRD_ID = [None]
+_MORE_IDS = [None, None]
 
 
-def _entry(rank, world, uid, uid2, uid3, out_dir):
+def _entry(rank, world, uid, uid2, uid3, uid4, uid5, out_dir):
     _SECOND_ID[0] = uid2
     _THIRD_ID[0] = uid3
+    _MORE_IDS[0], _MORE_IDS[1] = uid4, uid5
     _worker(rank, world, uid, out_dir)
 
 
@@ -88,8 +120,8 @@ def _entry(rank, world, uid, uid2, uid3, out_dir):
 def test_event_sharding_and_pooled_statistics_over_two_gpus(tmp_path):
     sys.path.insert(0, PKG)
     from smcmc_b200 import binding
-    uid, uid2, uid3 = binding.comm_unique_id(), binding.comm_unique_id(), binding.comm_unique_id()
-    mp.spawn(_entry, args=(2, uid, uid2, uid3, str(tmp_path)), nprocs=2, join=True)
+    uid, uid2, uid3, uid4, uid5 = [binding.comm_unique_id() for _ in range(5)]
+    mp.spawn(_entry, args=(2, uid, uid2, uid3, uid4, uid5, str(tmp_path)), nprocs=2, join=True)
     full = np.load(tmp_path / "full.npz")
     for r in range(2):
         s = np.load(tmp_path / ("shard%d.npz" % r))
@@ -99,6 +131,15 @@ def test_event_sharding_and_pooled_statistics_over_two_gpus(tmp_path):
         assert np.array_equal(s["acc"], full["acc"])
         assert np.array_equal(s["pts"], full["pts"])
         assert np.array_equal(s["la"], full["la"])
+    # 700 chains: the count table is reduce-scattered over chains, each rank finishes its block,
+    # the log-likelihoods are all-gathered -- still the unsharded numbers bit for bit
+    for tag in ("big", "big2"):
+        bfull = np.load(tmp_path / ("%sfull.npz" % tag))
+        for r in range(2):
+            b = np.load(tmp_path / ("%s%d.npz" % (tag, r)))
+            for k in ("counts", "llh", "acc", "la"):
+                assert np.array_equal(b[k], bfull[k], equal_nan=True), (tag, r, k)
+        assert np.isfinite(bfull["llh"]).all() and bfull["acc"].sum() > 0
     # unbinned: a floating-point sum, so the split changes the last bits only; both ranks
     # hold the same all-reduced value
     uf = np.load(tmp_path / "unbfull.npz")
