@@ -363,8 +363,14 @@ typedef enum smcmc_hmc_setting {
                                        TDummyLogLikelihood.H:34-42, THardLogLikelihood.H:72-91, or
                                        smcmc_user_ops::gradient); 0: TSimpleHMC<L>, finite
                                        differences (:417-444).  Set before smcmc_hmc_start.   */
-    SMCMC_HMC_KEEP_ERROR_MATRIX = 4 /* 1: keep fEstimatedError per chain (dim*dim doubles), which
+    SMCMC_HMC_KEEP_ERROR_MATRIX = 4,/* 1: keep fEstimatedError per chain (dim*dim doubles), which
                                        gradient type 2 (:447-454) reads.  Set before start.   */
+    SMCMC_HMC_POOLED_COVARIANCE = 5 /* NEW (not in the reference): UpdateCovariance / UpdateErrorMatrix
+                                       (:665-858) on ONE estimate pooled over every chain of the engine
+                                       instead of one per chain -- the estimate only feeds the step-size
+                                       and trajectory-length tuning (:833-847) unless gradient type 2 is
+                                       used.  0 per chain (the reference), 1 pooled, -1 (default) pooled
+                                       when the per-chain triangles would take >= 256 MB.  Before start. */
 } smcmc_hmc_setting;
 
 /* Per-chain quantities readable with smcmc_hmc_get(); arrays chain-major. */
@@ -376,8 +382,24 @@ typedef enum smcmc_hmc_field {
     SMCMC_HMC_F_AVERAGE = 4,       /* double[chains*dim]      fAveragePoint                  */
     SMCMC_HMC_F_COVARIANCE = 5,    /* double[chains*dim*dim]  GetEstimatedCovariance :197    */
     SMCMC_HMC_F_ERROR_MATRIX = 6,  /* double[chains*dim*dim]  fEstimatedError                */
-    SMCMC_HMC_F_SCALARS = 7        /* double[chains*SMCMC_HMC_SCALAR_COUNT], columns below   */
+    SMCMC_HMC_F_SCALARS = 7,       /* double[chains*SMCMC_HMC_SCALAR_COUNT], columns below   */
+    /* pooled covariance (SMCMC_HMC_POOLED_COVARIANCE) */
+    SMCMC_HMC_F_POOLED_COVARIANCE = 8, /* double[dim*dim]  the ensemble's fEstimatedCovariance      */
+    SMCMC_HMC_F_POOLED_AVERAGE = 9,    /* double[dim]      the ensemble's fAveragePoint             */
+    SMCMC_HMC_F_POOLED_SCALARS = 10    /* double[SMCMC_HMC_POOLED_SCALAR_COUNT], columns below      */
 } smcmc_hmc_field;
+enum {
+    SMCMC_HMC_PS_TRIALS = 0,         /* samples (chain-steps) behind the estimate                */
+    SMCMC_HMC_PS_EST_COV_TRACE,      /* fEstimatedCovarianceTrace                                */
+    SMCMC_HMC_PS_CUR_COV_TRACE,      /* fCurrentCovarianceTrace                                  */
+    SMCMC_HMC_PS_ORBIT_LENGTH,       /* fEstimatedOrbitLength                                    */
+    SMCMC_HMC_PS_MAX_SCALE,          /* sqrt(largest |eigenvalue|), clamped (:820-825)           */
+    SMCMC_HMC_PS_MIN_SCALE,          /* sqrt(smallest |eigenvalue|), clamped                     */
+    SMCMC_HMC_PS_STEP_COUNT,         /* steps that contributed                                   */
+    SMCMC_HMC_PS_UPDATES,            /* UpdateErrorMatrix bodies run so far                      */
+    SMCMC_HMC_PS_REPAIRED,           /* the last update found the estimate not positive definite */
+    SMCMC_HMC_POOLED_SCALAR_COUNT
+};
 enum {
     SMCMC_HMC_S_ACCEPTANCE = 0,      /* GetAcceptanceRate :160 */
     SMCMC_HMC_S_MEAN_EPSILON,        /* GetMeanEpsilon    :184 */

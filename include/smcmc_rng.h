@@ -235,14 +235,24 @@ SMCMC_HD double smcmc_uniform(uint64_t seed, uint32_t chain, uint32_t step,
     return smcmc_bits_to_open01(b.v[0], b.v[1]);
 }
 
+/* The two halves of Box-Muller on one 128-bit block, separately callable (a kernel may
+ * give them to two threads): the radius sqrt(-2 log u1) from words 0-1, the direction
+ * (cos, sin)(2 pi u2) from words 2-3. */
+SMCMC_HD double smcmc_normal_pair_radius(smcmc_u32x4 b) {
+    double u1 = smcmc_bits_to_open01(b.v[0], b.v[1]);
+    return SMCMC_SQRT(SMCMC_MUL(-2.0, smcmc_det_log(u1)));
+}
+SMCMC_HD void smcmc_normal_pair_direction(smcmc_u32x4 b, int which, double* c, double* s) {
+    double u2 = smcmc_bits_to_open01(b.v[2], b.v[3]);
+    smcmc_det_sincos2pi(u2, which, c, s);
+}
+
 /* Box-Muller on one 128-bit block: z0 = rad cos(2 pi u2), z1 = rad sin(2 pi u2),
  * rad = sqrt(-2 log u1).  `which` as smcmc_det_sincos2pi. */
 SMCMC_HD void smcmc_normal_pair_from_bits(smcmc_u32x4 b, int which, double* z0, double* z1) {
-    double u1 = smcmc_bits_to_open01(b.v[0], b.v[1]);
-    double u2 = smcmc_bits_to_open01(b.v[2], b.v[3]);
-    double rad = SMCMC_SQRT(SMCMC_MUL(-2.0, smcmc_det_log(u1)));
+    double rad = smcmc_normal_pair_radius(b);
     double c = 0.0, s = 0.0;
-    smcmc_det_sincos2pi(u2, which, &c, &s);
+    smcmc_normal_pair_direction(b, which, &c, &s);
     if (which & 1) *z0 = SMCMC_MUL(rad, c);
     if (which & 2) *z1 = SMCMC_MUL(rad, s);
 }

@@ -92,6 +92,10 @@ public:
         CUDA_CHECK(deviceAlloc((void**)&ptr_, n * sizeof(T)));
         count_ = n;
     }
+    void swap(DeviceBuffer& o) {
+        T* p = ptr_; ptr_ = o.ptr_; o.ptr_ = p;
+        size_t c = count_; count_ = o.count_; o.count_ = c;
+    }
     T* get() const { return ptr_; }
     size_t count() const { return count_; }
     size_t bytes() const { return count_ * sizeof(T); }

@@ -33,70 +33,114 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 // One 64 x 16 tile of a K-contiguous matrix (rows x n) into shared memory
-// [64][16 + pad]; rows past `rows` and columns past `n` are zero.
+// [64][16 + pad]; rows past `rows` and columns past `n` are zero.  Rows start on
+// 16-byte boundaries when n is even (VEC16: 16-byte cp.async, 4 per thread);
+// otherwise 8-byte copies.
+template <bool VEC16>
 __device__ __forceinline__ void dmmaLoadTile(double (*dst)[kDmmaBK + kDmmaPad], const double* __restrict__ src,
                                              int row0, int rows, int k0, int n, int tid) {
-    // 64 rows x 16 doubles = 1024 doubles, 128 threads: 8 each (one row, 8 consecutive k, as 8-byte copies:
-    // rows of X are only 8-byte aligned when n is odd)
+    if (VEC16) {
+        // 64 rows x 8 pairs = 512 16-byte pieces, 128 threads: 4 each
 #pragma unroll
-    for (int p = 0; p < 8; ++p) {
-        const int idx = p * 128 + tid;               // 0..1023
-        const int r = idx >> 4, k = idx & 15;
-        double* d = &dst[r][k];
-        if (row0 + r < rows && k0 + k < n) {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(d)),
-                         "l"(src + (size_t)(row0 + r) * n + k0 + k) : "memory");
-        } else {
-            *d = 0.0;
+        for (int p = 0; p < 4; ++p) {
+            const int idx = p * 128 + tid;               // 0..511
+            const int r = idx >> 3, k = (idx & 7) * 2;
+            double* d = &dst[r][k];
+            if (row0 + r < rows && k0 + k + 1 < n) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(d)),
+                             "l"(src + (size_t)(row0 + r) * n + k0 + k) : "memory");
+            } else {
+                d[0] = (row0 + r < rows && k0 + k < n) ? src[(size_t)(row0 + r) * n + k0 + k] : 0.0;
+                d[1] = 0.0;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            const int idx = p * 128 + tid;               // 0..1023
+            const int r = idx >> 4, k = idx & 15;
+            double* d = &dst[r][k];
+            if (row0 + r < rows && k0 + k < n) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(d)),
+                             "l"(src + (size_t)(row0 + r) * n + k0 + k) : "memory");
+            } else {
+                *d = 0.0;
+            }
         }
     }
 }
 
-// mode 0: y[c][i] = sum_j err[i][j] x[c][j]                      (gradient of the potential)
-// mode 1: partial[c][blockIdx.x] = sum_{i in this block} x[c][i] * Y[c][i]   (for the likelihood)
-// leapSteps / k: as kDummyGradient (chains whose trajectory is complete are not written); may be null.
-__global__ void __launch_bounds__(128)
-kDummyContractDmma(const double* __restrict__ x, const double* __restrict__ err, double* __restrict__ out,
-                   const int* __restrict__ leapSteps, int k, int chains, int n, int mode) {
-    __shared__ __align__(16) double As[2][kDmmaBM][kDmmaBK + kDmmaPad];
-    __shared__ __align__(16) double Bs[2][kDmmaBN][kDmmaBK + kDmmaPad];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;     // warp tile origin inside the CTA tile
-    const int c0 = blockIdx.y * kDmmaBM, i0 = blockIdx.x * kDmmaBN;
-    const int g = lane >> 2, q = lane & 3;                     // fragment coordinates
-    double acc[4][4][2];
+// The K loop of the 64 x 64 CTA tile: kDmmaStages-deep cp.async pipeline over K steps of 16,
+// 4 x 4 DMMA tiles per warp.  smem: [stages][2][64][20] doubles (dynamic).  acc is the C
+// fragment of the warp tile: tile (a, b) holds row g, columns 2q and 2q+1.
+constexpr int kDmmaStages = 3;
+constexpr int kDmmaStageDoubles = 2 * kDmmaBM * (kDmmaBK + kDmmaPad);
+constexpr size_t kDmmaSmemBytes = (size_t)kDmmaStages * kDmmaStageDoubles * sizeof(double);
+
+template <bool VEC16>
+__device__ __forceinline__ void dmmaMainloop(double (&acc)[4][4][2], double* smem, const double* __restrict__ x,
+                                             const double* __restrict__ err, int c0, int chains, int i0, int n, int tid) {
+    typedef double (*Tile)[kDmmaBK + kDmmaPad];
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    const int g = lane >> 2, q = lane & 3;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-
     const int steps = (n + kDmmaBK - 1) / kDmmaBK;
-    dmmaLoadTile(As[0], x, c0, chains, 0, n, tid);
-    dmmaLoadTile(Bs[0], err, i0, n, 0, n, tid);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    for (int s = 0; s < steps; ++s) {
-        const int cur = s & 1;
-        if (s + 1 < steps) {
-            dmmaLoadTile(As[cur ^ 1], x, c0, chains, (s + 1) * kDmmaBK, n, tid);
-            dmmaLoadTile(Bs[cur ^ 1], err, i0, n, (s + 1) * kDmmaBK, n, tid);
+#pragma unroll
+    for (int st = 0; st < kDmmaStages - 1; ++st) {
+        if (st < steps) {
+            dmmaLoadTile<VEC16>((Tile)(smem + st * kDmmaStageDoubles), x, c0, chains, st * kDmmaBK, n, tid);
+            dmmaLoadTile<VEC16>((Tile)(smem + st * kDmmaStageDoubles + kDmmaBM * (kDmmaBK + kDmmaPad)), err, i0, n, st * kDmmaBK, n, tid);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        __syncthreads();
+    }
+    for (int s = 0; s < steps; ++s) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kDmmaStages - 2) : "memory");
+        __syncthreads();                                   // stage s landed; everybody is done with stage s-1
+        const int nxt = s + kDmmaStages - 1;
+        if (nxt < steps) {
+            double* base = smem + (nxt % kDmmaStages) * kDmmaStageDoubles;
+            dmmaLoadTile<VEC16>((Tile)base, x, c0, chains, nxt * kDmmaBK, n, tid);
+            dmmaLoadTile<VEC16>((Tile)(base + kDmmaBM * (kDmmaBK + kDmmaPad)), err, i0, n, nxt * kDmmaBK, n, tid);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        Tile As = (Tile)(smem + (s % kDmmaStages) * kDmmaStageDoubles);
+        Tile Bs = (Tile)(smem + (s % kDmmaStages) * kDmmaStageDoubles + kDmmaBM * (kDmmaBK + kDmmaPad));
 #pragma unroll
         for (int kk = 0; kk < kDmmaBK; kk += 4) {
             double af[4], bf[4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) af[a] = As[cur][wm + a * 8 + g][kk + q];      // A(row g, col q)
+            for (int a = 0; a < 4; ++a) af[a] = As[wm + a * 8 + g][kk + q];      // A(row g, col q)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) bf[b] = Bs[cur][wn + b * 8 + g][kk + q];      // B(k q, col g) = err[i][k]
+            for (int b = 0; b < 4; ++b) bf[b] = Bs[wn + b * 8 + g][kk + q];      // B(k q, col g) = err[i][k]
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
         }
-        __syncthreads();
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+}
+
+// mode 0: y[c][i] = sum_j err[i][j] x[c][j]                      (gradient of the potential)
+// mode 1: partial[c][blockIdx.x] = sum_{i in this block} x[c][i] * Y[c][i]   (for the likelihood)
+// leapSteps / k: as kDummyGradient (chains whose trajectory is complete are not written); may be null.
+// Dynamic shared memory: kDmmaSmemBytes.
+template <bool VEC16>
+__global__ void __launch_bounds__(128, 3)
+kDummyContractDmma(const double* __restrict__ x, const double* __restrict__ err, double* __restrict__ out,
+                   const int* __restrict__ leapSteps, int k, int chains, int n, int mode) {
+    extern __shared__ __align__(16) double dmmaSmem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;     // warp tile origin inside the CTA tile
+    const int c0 = blockIdx.y * kDmmaBM, i0 = blockIdx.x * kDmmaBN;
+    const int g = lane >> 2, q = lane & 3;                     // fragment coordinates
+    double acc[4][4][2];
+    dmmaMainloop<VEC16>(acc, dmmaSmem, x, err, c0, chains, i0, n, tid);
     // C fragment: row g, columns 2q and 2q+1 of each 8 x 8 tile
     if (mode == 0) {
 #pragma unroll
@@ -135,6 +179,125 @@ kDummyContractDmma(const double* __restrict__ x, const double* __restrict__ err,
         __syncthreads();
         if (tid < kDmmaBM && c0 + tid < chains) out[(size_t)(c0 + tid) * gridDim.x + blockIdx.x] = part[tid][0] + part[tid][1];
     }
+}
+
+// Host side: launch with the copy width the operands allow.
+inline void launchDummyContractDmma(cudaStream_t stream, const double* x, const double* err, double* out,
+                                    const int* leapSteps, int k, int chains, int n, int mode) {
+    static bool ready = false;
+    if (!ready) {
+        cudaFuncSetAttribute(kDummyContractDmma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+        cudaFuncSetAttribute(kDummyContractDmma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+        ready = true;
+    }
+    dim3 grid((n + kDmmaBN - 1) / kDmmaBN, (chains + kDmmaBM - 1) / kDmmaBM);
+    if ((n & 1) == 0)
+        kDummyContractDmma<true><<<grid, 128, kDmmaSmemBytes, stream>>>(x, err, out, leapSteps, k, chains, n, mode);
+    else
+        kDummyContractDmma<false><<<grid, 128, kDmmaSmemBytes, stream>>>(x, err, out, leapSteps, k, chains, n, mode);
+}
+
+// ---------------------------------------------------------------------------
+// One leap-frog stage of TSimpleHMC::LeapFrog (TSimpleHMC.H:612-648) for the dense
+// Gaussian, FUSED with its gradient: the CTA that holds the 64 x 64 tile of
+// grad = X . Error^T in its accumulators applies, element by element,
+//     p  <- p - eps g          (/ 2 for the first and the last gradient, :618-620, :646-648)
+//     q' <- q + eps p          (when another gradient follows, :624-626, :641-643)
+// and the per-chain partial sums of p . p0 over its 64 dimensions for the U-turn test
+// (:633-638).  Nothing of the gradient goes to HBM and the kick / drift pass over four
+// E x n arrays (kHmcKickDrift) disappears.  q is double buffered (qIn -> qOut): other CTAs
+// of the same launch still read qIn as their GEMM operand.  Chains that do not take part
+// in gradient k (trajectory complete) copy q through, so both buffers stay current.
+// The U-turn partials of gradient k are summed (fixed order over the column blocks) by the
+// blockIdx.x = 0 CTAs of the NEXT launch, which exists for every chain that needs it
+// (the test is made for k = 1 .. steps-1).  TENSOR mode is specified to 1e-12 of the
+// reference, not bit for bit, so the sign of that sum is taken as it is.
+// ---------------------------------------------------------------------------
+struct LeapFused {
+    const double* qIn;
+    double* qOut;
+    double* p;               // fProposedMomentum, updated in place
+    const double* p0;        // the momentum the trajectory started with
+    const double* epsilon;   // per chain: &sc[c].epsilon, stride `scalarStride` doubles
+    int* okLeap;             // per chain: &sc[c].okLeap, stride `scalarStride` doubles
+    int scalarStride;        // sizeof(HmcScalars) / 8
+    const int* leapSteps;
+    double* uturn;           // [2][chains][blocks]: sum of p p0 over each column block, gradients k (parity k & 1)
+    int blocks;              // column blocks = gridDim.x
+};
+
+template <bool VEC16>
+__global__ void __launch_bounds__(128, 3)
+kHmcLeapDmma(const double* __restrict__ err, LeapFused f, int k, int chains, int n) {
+    extern __shared__ __align__(16) double dmmaSmem[];
+    __shared__ double part[kDmmaBM][2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    const int c0 = blockIdx.y * kDmmaBM, i0 = blockIdx.x * kDmmaBN;
+    const int g = lane >> 2, q = lane & 3;
+    // the U-turn test of the PREVIOUS gradient (k - 1 >= 1), one thread per chain of this row of CTAs
+    if (blockIdx.x == 0 && k >= 2 && tid < kDmmaBM && c0 + tid < chains) {
+        const int c = c0 + tid;
+        const int st = f.leapSteps[c];
+        if (st >= 1 && k - 1 <= st - 1) {
+            const double* u = f.uturn + ((size_t)((k - 1) & 1) * chains + c) * f.blocks;
+            double sum = 0.0;
+            for (int b = 0; b < f.blocks; ++b) sum += u[b];
+            if (!(sum >= 0.0)) f.okLeap[(size_t)c * f.scalarStride * 2] = 2;       // :637-638 (int index: two ints per double)
+        }
+    }
+    double acc[4][4][2];
+    dmmaMainloop<VEC16>(acc, dmmaSmem, f.qIn, err, c0, chains, i0, n, tid);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int c = c0 + wm + a * 8 + g;
+        double dot = 0.0;
+        if (c < chains) {
+            const int st = f.leapSteps[c];
+            const bool live = st >= 1 && k <= st;
+            const bool half = (k == 0) || (k == st);
+            const bool drift = live && k < st;
+            const double eps = live ? f.epsilon[(size_t)c * f.scalarStride] : 0.0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int i = i0 + wn + b * 8 + 2 * q + h;
+                    if (i >= n) continue;
+                    const size_t at = (size_t)c * n + i;
+                    const double qv = f.qIn[at];
+                    if (!live) {
+                        f.qOut[at] = qv;
+                        continue;
+                    }
+                    double kick = __dmul_rn(eps, acc[a][b][h]);
+                    if (half) kick = __ddiv_rn(kick, 2.0);
+                    const double pv = __dsub_rn(f.p[at], kick);
+                    f.p[at] = pv;
+                    if (!half) dot += __dmul_rn(pv, f.p0[at]);
+                    f.qOut[at] = drift ? __dadd_rn(qv, __dmul_rn(eps, pv)) : qv;
+                }
+            }
+        }
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+        if (q == 0) part[wm + a * 8 + g][warp & 1] = dot;
+    }
+    __syncthreads();
+    if (tid < kDmmaBM && c0 + tid < chains)
+        f.uturn[((size_t)(k & 1) * chains + c0 + tid) * f.blocks + blockIdx.x] = part[tid][0] + part[tid][1];
+}
+
+inline void launchHmcLeapDmma(cudaStream_t stream, const double* err, const LeapFused& f, int k, int chains, int n) {
+    static bool ready = false;
+    if (!ready) {
+        cudaFuncSetAttribute(kHmcLeapDmma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+        cudaFuncSetAttribute(kHmcLeapDmma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+        ready = true;
+    }
+    dim3 grid((n + kDmmaBN - 1) / kDmmaBN, (chains + kDmmaBM - 1) / kDmmaBM);
+    if ((n & 1) == 0) kHmcLeapDmma<true><<<grid, 128, kDmmaSmemBytes, stream>>>(err, f, k, chains, n);
+    else kHmcLeapDmma<false><<<grid, 128, kDmmaSmemBytes, stream>>>(err, f, k, chains, n);
 }
 
 // L[c] = -1/2 sum over the column blocks of the partial sums.

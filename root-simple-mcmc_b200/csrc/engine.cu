@@ -62,12 +62,19 @@ struct HmcHost {
     int keepError = 0;               // keep fEstimatedError per chain
     DeviceBuffer<double> qAcc, pAcc, qProp, pProp, p0, grad, central, average, exxt, exxtT, estErr, repairedDiag;
     DeviceBuffer<double> llh, fdWork, fdLlh, avgPts, avgLlh;
+    DeviceBuffer<double> qAlt, uturn;    // fused leap-frog stage (kHmcLeapDmma): the second q buffer, the U-turn partials
     DeviceBuffer<HmcScalars> sc;
     DeviceBuffer<int> leapSteps, counters, updateList;
     // deferred fEXXT update (hmc.cuh, kHmcExxtFlush): 0 = every step
     DeviceBuffer<double> ring, ringT, exxtDiag;
     DeviceBuffer<int> pending;
     int deferK = 0, sinceFlush = 0;
+    // ensemble-pooled covariance (hmc.cuh, kHmcPooled*): -1 automatic, 0 per chain, 1 pooled
+    int pooledSetting = -1;
+    bool pooled = false;
+    DeviceBuffer<int> poolMask;
+    DeviceBuffer<double> poolStats, poolExxt, poolAverage, poolDiag, poolScratch, poolLlh;
+    DeviceBuffer<HmcPooled> pool;
     int* hostCounters = nullptr;     // pinned
     ~HmcHost() {
         if (hostCounters) cudaFreeHost(hostCounters);
@@ -120,6 +127,7 @@ struct smcmc_engine {
     DeviceBuffer<double> fakeTerms;     // kFakeFinish with few points: the 150 bin terms per point
     DeviceBuffer<unsigned int> fakeTickets;
     bool staged = false;                // kProposeStaged (one CTA per chain) instead of kPropose
+    int stagedDraw = 0;                 // its DRAW variant
     bool resident = false;              // kStepsResident fits (whole steps out of shared memory)
     int residentPerSm = 0;              // its CTAs per SM
     int64_t residentLaunches = 0;
@@ -280,8 +288,10 @@ struct smcmc_engine {
     int poolStatCount() const { return 1 + n() + tri(); }
     // S += the accepted points of the local chains (count, sum x, sum x x^T): Y^T Y on the
     // FP64 tensor cores; SMCMC_POOL_ACC_SCALAR=1 keeps the scalar kernel
-    void poolAccumulate(double* stats) {
-        if (std::getenv("SMCMC_POOL_ACC_SCALAR")) {
+    void poolAccumulate(double* stats) { poolAccumulateOn(xAcc.get(), sc.get(), nullptr, stats); }
+    // ... of the rows of `x` whose chain is running (scalars) or marked (mask)
+    void poolAccumulateOn(const double* x, const ChainScalars* scalars, const int* mask, double* stats) {
+        if (!mask && std::getenv("SMCMC_POOL_ACC_SCALAR")) {
             const int poolBlocks = std::min(smCount * 8, ceilDiv(E(), kPoolTile));
             kPoolAccumulate<<<poolBlocks, 256, poolAccSmem(n()), stream>>>(xAcc.get(), sc.get(), E(), n(), stats);
         } else {
@@ -291,11 +301,11 @@ struct smcmc_engine {
             int slices = std::max(1, std::min(ceilDiv(E(), 16), ceilDiv(3 * smCount, pairs)));
             const int perCta = ceilDiv(ceilDiv(E(), slices), 16) * 16;
             slices = ceilDiv(E(), perCta);
-            kPoolAccumulateDmma<true><<<dim3(blocks, slices), 128, 0, stream>>>(xAcc.get(), sc.get(), E(), n(), stats, perCta);
+            kPoolAccumulateDmma<true><<<dim3(blocks, slices), 128, 0, stream>>>(x, scalars, E(), n(), stats, perCta, mask);
             if (blocks > 1) {
                 launched();
-                kPoolAccumulateDmma<false><<<dim3(pairs - blocks, slices), 128, 0, stream>>>(xAcc.get(), sc.get(), E(), n(),
-                                                                                         stats, perCta);
+                kPoolAccumulateDmma<false><<<dim3(pairs - blocks, slices), 128, 0, stream>>>(x, scalars, E(), n(), stats,
+                                                                                         perCta, mask);
             }
         }
         launched();
@@ -474,7 +484,7 @@ struct smcmc_engine {
                 // L = -1/2 x . (Error^T x): the contraction on the FP64 tensor cores
                 dim3 grid(ceilDiv(n(), kDmmaBN), ceilDiv(m, kDmmaBM));
                 dummyPartials.reserve((size_t)m * grid.x);
-                kDummyContractDmma<<<grid, 128, 0, stream>>>(xDev, errMatrixT.get(), dummyPartials.get(), nullptr, 0, m, n(), 1);
+                launchDummyContractDmma(stream, xDev, errMatrixT.get(), dummyPartials.get(), nullptr, 0, m, n(), 1);
                 launched();
                 kDummyLlhFromPartials<<<ceilDiv(m, 128), 128, 0, stream>>>(dummyPartials.get(), (int)grid.x, m, llhDev);
                 launched();
@@ -774,8 +784,7 @@ struct smcmc_engine {
             kProposePooled<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a, ps, pooled(), E(), cfg.seed,
                                                                           cfg.chain_offset, stepRef(), poolZ.get());
             launched();
-            dim3 grid(ceilDiv(n(), kDmmaBN), ceilDiv(E(), kDmmaBM));
-            kDummyContractDmma<<<grid, 128, 0, stream>>>(poolZ.get(), poolDecompT.get(), poolY.get(), nullptr, 0, E(), n(), 0);
+            launchDummyContractDmma(stream, poolZ.get(), poolDecompT.get(), poolY.get(), nullptr, 0, E(), n(), 0);
             launched();
             kProposePooledFinish<<<blocks, kWarpsPerBlock * 32, (size_t)kWarpsPerBlock * n() * sizeof(double), stream>>>(
                 a, ps, E(), poolY.get());
@@ -792,7 +801,8 @@ struct smcmc_engine {
             }
             kVaatPropose<<<ceilDiv(E(), 128), 128, 0, stream>>>(a, vaatArrays(), ps, E(), cfg.seed, cfg.chain_offset, stepRef());
         } else if (staged)
-            kProposeStaged<<<E(), kStagedThreads, stagedChainBytes(n(), covStride, upkStride), stream>>>(
+            (stagedDraw == 1 ? kProposeStaged<1> : stagedDraw == 2 ? kProposeStaged<2> : kProposeStaged<0>)
+                <<<E(), kStagedThreads, stagedChainBytes(n(), covStride, upkStride), stream>>>(
                 a, ps, E(), cfg.seed, cfg.chain_offset, stepRef());
         else
             kPropose<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a, ps, E(), cfg.seed, cfg.chain_offset, stepRef());
@@ -1052,7 +1062,10 @@ int smcmc_create(const smcmc_config* cfg, smcmc_engine** out) {
             const size_t cb = stagedChainBytes((int)n, e->covStride, e->upkStride);
             if ((227 * 1024) / (cb + 1024) >= 4 && n < 8192 && !std::getenv("SMCMC_PROPOSE_GENERIC")) {
                 e->staged = true;
-                CUDA_CHECK(cudaFuncSetAttribute(kProposeStaged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cb));
+                if (const char* d = std::getenv("SMCMC_STAGED_DRAW")) e->stagedDraw = atoi(d);
+                CUDA_CHECK(cudaFuncSetAttribute(kProposeStaged<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cb));
+                CUDA_CHECK(cudaFuncSetAttribute(kProposeStaged<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cb));
+                CUDA_CHECK(cudaFuncSetAttribute(kProposeStaged<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cb));
             }
             // kStepsResident (whole steps out of shared memory) when one chain fits an SM
             const size_t rb = residentChainBytes((int)n, e->covStride, e->upkStride);

@@ -18,13 +18,34 @@ void hmcAllocate(smcmc_engine* e) {
     h.central.reserve(E * n);
     h.average.reserve(E * n);
     h.repairedDiag.reserve(E * n);
-    h.exxt.reserve(E * tri);
+    // One covariance estimate per chain (the reference, TSimpleHMC.H:665-695) or one for the ensemble
+    // (hmc.cuh, kHmcPooled*).  Automatic: pooled when the per-chain triangles would take 256 MB or more
+    // (n = 500: from 269 chains on) and nothing needs a private estimate (the covariant gradient reads
+    // the chain's own error matrix).  SMCMC_HMC_POOLED_COVARIANCE / SMCMC_HMC_POOLED=0|1 decide otherwise.
+    h.pooled = h.pooledSetting < 0 ? (E * tri * sizeof(double) >= (256u << 20) && !h.keepError) : h.pooledSetting != 0;
+    if (const char* k = std::getenv("SMCMC_HMC_POOLED")) h.pooled = atoi(k) != 0;
+    if (h.pooled && h.keepError)
+        throw Error(SMCMC_ERR_LOGIC, "the covariant gradient (SMCMC_HMC_KEEP_ERROR_MATRIX) needs the per-chain covariance");
     h.exxtT.reserve(E);
     CUDA_CHECK(cudaMemset(h.exxtT.get(), 0xFF, E * sizeof(double)));
-    // fEXXT is rewritten once per deferK steps instead of every step when the triangles of the
-    // ensemble are larger than the L2 can hold (SMCMC_HMC_DEFER=k forces k, 0 = every step)
-    h.deferK = (E * tri * sizeof(double) >= (256u << 20)) ? 16 : 0;
-    if (const char* k = std::getenv("SMCMC_HMC_DEFER")) h.deferK = std::max(0, std::min(64, atoi(k)));
+    if (h.pooled) {
+        h.poolMask.reserve(E);
+        h.poolStats.reserve(1 + n + tri);
+        h.poolExxt.reserve(tri);
+        h.poolAverage.reserve(n);
+        h.poolDiag.reserve(n);
+        h.poolScratch.reserve(2 * n * n + 4 * n);
+        h.poolLlh.reserve(1);
+        h.pool.reserve(1);
+        CUDA_CHECK(cudaMemset(h.poolMask.get(), 0, h.poolMask.bytes()));
+        h.deferK = 0;
+    } else {
+        h.exxt.reserve(E * tri);
+        // fEXXT is rewritten once per deferK steps instead of every step when the triangles of the
+        // ensemble are larger than the L2 can hold (SMCMC_HMC_DEFER=k forces k, 0 = every step)
+        h.deferK = (E * tri * sizeof(double) >= (256u << 20)) ? 16 : 0;
+        if (const char* k = std::getenv("SMCMC_HMC_DEFER")) h.deferK = std::max(0, std::min(64, atoi(k)));
+    }
     if (h.deferK > 0) {
         h.ring.reserve(E * h.deferK * n);
         h.ringT.reserve(E * h.deferK);
@@ -71,6 +92,13 @@ HmcArrays hmcArrays(smcmc_engine* e) {
     a.pending = h.pending.get();
     a.exxtDiag = h.exxtDiag.get();
     a.deferK = h.deferK;
+    a.pooled = h.pooled ? 1 : 0;
+    a.poolMask = h.poolMask.get();
+    a.poolStats = h.poolStats.get();
+    a.poolExxt = h.poolExxt.get();
+    a.poolAverage = h.poolAverage.get();
+    a.poolDiag = h.poolDiag.get();
+    a.pool = h.pool.get();
     a.estErr = h.keepError ? h.estErr.get() : nullptr;
     a.repairedDiag = h.repairedDiag.get();
     a.sc = h.sc.get();
@@ -130,9 +158,7 @@ void hmcGradient(smcmc_engine* e, HmcGradientMode mode, int k) {
         }
         if (e->errDim != n) throw Error(SMCMC_ERR_LOGIC, "error matrix not set (smcmc_dummy_set_error)");
         if (e->dummyMode == SMCMC_DUMMY_TENSOR) {
-            dim3 grid(ceilDiv(n, kDmmaBN), ceilDiv(E, kDmmaBM));
-            kDummyContractDmma<<<grid, 128, 0, e->stream>>>(h.qProp.get(), e->errMatrix.get(), h.grad.get(),
-                                                           h.leapSteps.get(), k, E, n, 0);
+            launchDummyContractDmma(e->stream, h.qProp.get(), e->errMatrix.get(), h.grad.get(), h.leapSteps.get(), k, E, n, 0);
         } else {
             dim3 grid(ceilDiv(n, kGemmBN), ceilDiv(E, kGemmBM));
             kDummyGradient<<<grid, 256, 0, e->stream>>>(h.qProp.get(), e->errMatrix.get(), h.grad.get(),
@@ -210,7 +236,32 @@ void hmcStepOnce(smcmc_engine* e, int type, const HmcTraceDev& tr, int traceStep
     e->launched();
     const int maxSteps = hmcReadCounter(e, 0);
     const int countPotentials = (mode == kGradFinite) ? 2 * n : 0;
-    if (maxSteps >= 1) {
+    // dense Gaussian on the tensor cores: gradient, kick and drift of a leap-frog stage in ONE launch
+    // (contraction.cuh, kHmcLeapDmma); SMCMC_HMC_NO_FUSE=1 keeps gradient kernel + kHmcKickDrift
+    const bool fused = mode == kGradUser && e->cfg.likelihood == SMCMC_LLH_DUMMY && e->dummyMode == SMCMC_DUMMY_TENSOR &&
+                       e->errDim == n && !std::getenv("SMCMC_HMC_NO_FUSE");
+    if (maxSteps >= 1 && fused) {
+        const int colBlocks = ceilDiv(n, kDmmaBN);
+        h.qAlt.reserve((size_t)E * n);
+        h.uturn.reserve((size_t)2 * E * colBlocks);
+        LeapFused f;
+        f.p = h.pProp.get();
+        f.p0 = h.p0.get();
+        f.epsilon = &h.sc.get()->epsilon;
+        f.okLeap = &h.sc.get()->okLeap;
+        f.scalarStride = (int)(sizeof(HmcScalars) / sizeof(double));
+        f.leapSteps = h.leapSteps.get();
+        f.uturn = h.uturn.get();
+        f.blocks = colBlocks;
+        for (int k = 0; k <= maxSteps; ++k) {
+            f.qIn = h.qProp.get();
+            f.qOut = h.qAlt.get();
+            launchHmcLeapDmma(e->stream, e->errMatrix.get(), f, k, E, n);
+            e->launched();
+            h.qProp.swap(h.qAlt);                                        // the proposed positions are in the buffer just written
+        }
+        a = hmcArrays(e);
+    } else if (maxSteps >= 1) {
         for (int k = 0; k <= maxSteps; ++k) {
             hmcGradient(e, mode, k);
             kHmcKickDrift<<<blocks, threads, smem, e->stream>>>(a, n, E, k, countPotentials);
@@ -218,9 +269,20 @@ void hmcStepOnce(smcmc_engine* e, int type, const HmcTraceDev& tr, int traceStep
         }
     }
     e->evaluate(h.qProp.get(), E, h.llh.get(), nullptr);                  // :327
-    kHmcPost<<<blocks, threads, smem, e->stream>>>(a, n, E, h.llh.get(), 1000000.0 /* fCovarianceWindow :134 */);
+    kHmcPost<<<blocks, threads, smem, e->stream>>>(a, n, E, h.llh.get(), 1000000.0 /* fCovarianceWindow :134 */,
+                                                   fused && maxSteps >= 1 ? 1 : 0);
     e->launched();
-    if (h.deferK > 0) {
+    if (h.pooled) {
+        // UpdateCovariance on the pooled estimate: this step's sums over the marked chains, folded
+        // into the running averages; then the trigger of UpdateErrorMatrix
+        const long long tri = (long long)n * (n + 1) / 2;
+        CUDA_CHECK(cudaMemsetAsync(h.poolStats.get(), 0, (size_t)(1 + n + tri) * sizeof(double), e->stream));
+        e->poolAccumulateOn(h.qAcc.get(), nullptr, h.poolMask.get(), h.poolStats.get());
+        kHmcPooledFold<<<ceilDiv(n + tri, 256), 256, 0, e->stream>>>(a, n);
+        e->launched();
+        kHmcPooledTrigger<<<1, 256, 0, e->stream>>>(a, n, 1000000.0 * (double)E);
+        e->launched();
+    } else if (h.deferK > 0) {
         if (++h.sinceFlush >= h.deferK) hmcFlushExxt(e, nullptr, E);     // :678-686, deferK steps at once
     } else {
         const long long tri = (long long)n * (n + 1) / 2;
@@ -230,7 +292,13 @@ void hmcStepOnce(smcmc_engine* e, int type, const HmcTraceDev& tr, int traceStep
         e->launched();
     }
     const int updates = hmcReadCounter(e, 1);
-    if (updates > 0) {
+    if (updates > 0 && h.pooled) {
+        e->evaluate(h.poolAverage.get(), 1, h.poolLlh.get(), nullptr);    // :729, once for the ensemble
+        kHmcPooledSpectrum<<<1, kHmcSpectrumThreads, 0, e->stream>>>(a, n, h.poolLlh.get(), h.poolScratch.get());
+        e->launched();
+        kHmcPooledApply<<<ceilDiv(E, 128), 128, 0, e->stream>>>(a, n, E);
+        e->launched();
+    } else if (updates > 0) {
         hmcFlushExxt(e, h.updateList.get(), updates);                     // UpdateErrorMatrix reads fEXXT
         h.avgPts.reserve((size_t)updates * n);
         h.avgLlh.reserve(updates);
@@ -263,6 +331,10 @@ int smcmc_hmc_set(smcmc_engine* e, int setting, double v) {
                                                         "gradient entry provide a gradient functor");
             h.userGradient = (v != 0.0);
             return;
+        case SMCMC_HMC_POOLED_COVARIANCE:
+            if (h.allocated) throw Error(SMCMC_ERR_LOGIC, "set SMCMC_HMC_POOLED_COVARIANCE before the first HMC call that allocates state");
+            h.pooledSetting = v < 0 ? -1 : (v != 0.0);
+            return;
         case SMCMC_HMC_KEEP_ERROR_MATRIX:
             if (h.started) throw Error(SMCMC_ERR_LOGIC, "set SMCMC_HMC_KEEP_ERROR_MATRIX before smcmc_hmc_start");
             h.keepError = (v != 0.0);
@@ -289,6 +361,15 @@ int smcmc_hmc_start(smcmc_engine* e, const double* x0) {
         CUDA_CHECK(cudaMemcpyAsync(h.qAcc.get(), x0, E * n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
         e->evaluate(h.qAcc.get(), (int)E, h.llh.get(), nullptr);           // SetPosition, :221
         h.sinceFlush = 0;                                                  // kHmcStart empties the rings
+        if (h.pooled) {
+            HmcPooled init;
+            std::memset(&init, 0, sizeof init);
+            init.estCovTrace = (double)n;                                  // :263
+            CUDA_CHECK(cudaMemcpyAsync(h.pool.get(), &init, sizeof init, cudaMemcpyHostToDevice, e->stream));
+            CUDA_CHECK(cudaMemsetAsync(h.poolExxt.get(), 0, h.poolExxt.bytes(), e->stream));
+            CUDA_CHECK(cudaMemsetAsync(h.poolAverage.get(), 0, h.poolAverage.bytes(), e->stream));
+            CUDA_CHECK(cudaStreamSynchronize(e->stream));                  // `init` leaves scope
+        }
         kHmcStart<<<ceilDiv((long long)E, kWarpsPerBlock), kWarpsPerBlock * 32, 0, e->stream>>>(
             hmcArrays(e), (int)n, (int)E, h.llh.get(), h.firstStart ? 1 : 0);
         e->launched();
@@ -368,6 +449,37 @@ int smcmc_hmc_get(smcmc_engine* e, int field, void* dst, size_t bytes) {
             CUDA_CHECK(cudaMemcpyAsync(dst, src, want, cudaMemcpyDeviceToHost, e->stream));
             CUDA_CHECK(cudaStreamSynchronize(e->stream));
         };
+        if (field == SMCMC_HMC_F_POOLED_COVARIANCE || field == SMCMC_HMC_F_POOLED_AVERAGE || field == SMCMC_HMC_F_POOLED_SCALARS) {
+            if (!h.pooled) throw Error(SMCMC_ERR_LOGIC, "the covariance is kept per chain (SMCMC_HMC_POOLED_COVARIANCE)");
+            std::vector<double> ex(tri), avg(n);
+            HmcPooled hp;
+            CUDA_CHECK(cudaStreamSynchronize(e->stream));
+            CUDA_CHECK(cudaMemcpy(ex.data(), h.poolExxt.get(), tri * 8, cudaMemcpyDeviceToHost));
+            CUDA_CHECK(cudaMemcpy(avg.data(), h.poolAverage.get(), n * 8, cudaMemcpyDeviceToHost));
+            CUDA_CHECK(cudaMemcpy(&hp, h.pool.get(), sizeof hp, cudaMemcpyDeviceToHost));
+            double* out = (double*)dst;
+            if (field == SMCMC_HMC_F_POOLED_AVERAGE) {
+                need(n * 8);
+                std::copy(avg.begin(), avg.end(), out);
+            } else if (field == SMCMC_HMC_F_POOLED_COVARIANCE) {
+                need(n * n * 8);
+                for (size_t i = 0; i < n; ++i)
+                    for (size_t j = 0; j <= i; ++j)
+                        out[i * n + j] = out[j * n + i] = ex[i * (i + 1) / 2 + j] - avg[i] * avg[j];      // :688-689
+            } else {
+                need(SMCMC_HMC_POOLED_SCALAR_COUNT * 8);
+                out[SMCMC_HMC_PS_TRIALS] = hp.trials;
+                out[SMCMC_HMC_PS_EST_COV_TRACE] = hp.estCovTrace;
+                out[SMCMC_HMC_PS_CUR_COV_TRACE] = hp.curCovTrace;
+                out[SMCMC_HMC_PS_ORBIT_LENGTH] = hp.orbitLength;
+                out[SMCMC_HMC_PS_MAX_SCALE] = hp.maxScale;
+                out[SMCMC_HMC_PS_MIN_SCALE] = hp.minScale;
+                out[SMCMC_HMC_PS_STEP_COUNT] = hp.stepCount;
+                out[SMCMC_HMC_PS_UPDATES] = hp.updates;
+                out[SMCMC_HMC_PS_REPAIRED] = hp.repaired;
+            }
+            return;
+        }
         switch (field) {
         case SMCMC_HMC_F_ACCEPTED: copyArray(h.qAcc.get(), E * n * 8); return;
         case SMCMC_HMC_F_MOMENTUM: copyArray(h.pAcc.get(), E * n * 8); return;
@@ -409,6 +521,8 @@ int smcmc_hmc_get(smcmc_engine* e, int field, void* dst, size_t bytes) {
             }
             return;
         }
+        if (field == SMCMC_HMC_F_COVARIANCE && h.pooled)
+            throw Error(SMCMC_ERR_LOGIC, "the covariance is pooled over the ensemble: read SMCMC_HMC_F_POOLED_COVARIANCE");
         if (field == SMCMC_HMC_F_COVARIANCE) {
             // fEstimatedCovariance = fEXXT - mean mean^T (:688-689), or what a
             // positive-definiteness repair left (:792-806); the identity before

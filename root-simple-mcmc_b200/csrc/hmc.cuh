@@ -75,6 +75,19 @@ struct __align__(16) HmcScalars {
 };
 static_assert(sizeof(HmcScalars) == 160, "HmcScalars layout");
 
+// Shared state of the pooled covariance estimate: what fCovarianceTrials, fEstimatedCovarianceTrace,
+// fCurrentCovarianceTrace, fEstimatedOrbitLength, fStepsRemaining, fStepsSinceUpdate are for one
+// chain (TSimpleHMC.H:665-858), kept once for the ensemble.
+struct HmcPooled {
+    double trials;            // samples (chain-steps) behind poolAverage / poolExxt
+    double estCovTrace;
+    double curCovTrace;
+    double orbitLength;
+    double maxScale, minScale;        // sqrt of the largest / smallest |eigenvalue| of the pooled covariance, clamped (:820-825)
+    double averagePotential;          // Potential(average point) at the last update (:729)
+    int stepsRemaining, stepsSinceUpdate, stepCount, needUpdate, repaired, updates;
+};
+
 struct HmcArrays {
     double* qAcc;       // fAccepted
     double* pAcc;       // fAcceptedMomentum
@@ -95,6 +108,14 @@ struct HmcArrays {
     int deferK;
     double* estErr;     // fEstimatedError or nullptr
     double* repairedDiag;
+    // ensemble-pooled covariance (kHmcPooled*, below): one running mean / E[x x^T] for all chains
+    int pooled;         // 1: UpdateCovariance / UpdateErrorMatrix run on the pooled estimate
+    int* poolMask;      // [E] chains whose UpdateCovariance call happens this step
+    double* poolStats;  // [1 + n + n(n+1)/2] this step's (count, sum x, sum x x^T) over the marked chains
+    double* poolExxt;   // [n(n+1)/2] pooled fEXXT
+    double* poolAverage;// [n]        pooled fAveragePoint
+    double* poolDiag;   // [n]        the repaired diagonal (:792-806)
+    struct HmcPooled* pool;
     HmcScalars* sc;
     int* leapSteps;     // copy of sc.steps for the gradient kernels
     int* counters;      // [0] max steps of this transition, [1] chains that need UpdateErrorMatrix
@@ -159,7 +180,8 @@ kHmcStart(HmcArrays a, int n, int chains, const double* __restrict__ llh, int fi
             a.pProp[row + i] = 0.0;
         }
     }
-    for (size_t k = lane; k < tri; k += 32) a.exxt[(size_t)c * tri + k] = 0.0;        // :258
+    if (!a.pooled)
+        for (size_t k = lane; k < tri; k += 32) a.exxt[(size_t)c * tri + k] = 0.0;    // :258
     if (a.deferK > 0) {
         for (int i = lane; i < n; i += 32) a.exxtDiag[row + i] = 0.0;
         if (lane == 0) a.pending[c] = 0;
@@ -469,7 +491,8 @@ __global__ void kHmcFdGradient(const double* __restrict__ llh, double* __restric
 // After the trajectory and the likelihood of the proposed point: :302-344.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-kHmcPost(HmcArrays a, int n, int chains, const double* __restrict__ llhProp, double covWindow) {
+kHmcPost(HmcArrays a, int n, int chains, const double* __restrict__ llhProp, double covWindow,
+         int countGradients /* the fused leap-frog launches do not count: steps + 1 gradients were made (:469) */) {
     extern __shared__ double smemD[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -481,6 +504,7 @@ kHmcPost(HmcArrays a, int n, int chains, const double* __restrict__ llhProp, dou
     const size_t row = (size_t)c * n;
     const size_t tri = (size_t)n * (n + 1) / 2;
     s.needUpdate = 0;
+    if (countGradients && s.steps >= 1) s.gradientCount += s.steps + 1;
     if (lane == 0) a.exxtT[c] = __longlong_as_double(-1ll);                // NaN: no UpdateCovariance this step
 
     if (s.leapFrogSteps > 0) {                                            // :302-323
@@ -509,6 +533,16 @@ kHmcPost(HmcArrays a, int n, int chains, const double* __restrict__ llhProp, dou
     const double acceptedH = __dadd_rn(s.accPotential, s.initialKinetic);
     s.deltaH = __dsub_rn(proposedH, acceptedH);                           // :346
 
+    if (a.pooled) {
+        // UpdateCovariance / UpdateErrorMatrix act on the estimate pooled over the ensemble: this
+        // chain only says whether its call happens (:336) -- kPoolAccumulateDmma adds the marked
+        // chains' accepted points, kHmcPooledFold / kHmcPooledTrigger do the rest once per step
+        const bool call = s.okLeap && isfinite(s.propPotential);
+        if (lane == 0) a.poolMask[c] = call ? 1 : 0;
+        if (!call && s.meanEpsilon > 0) s.meanEpsilon = __dmul_rn(0.3, s.meanEpsilon);     // :343
+        if (lane == 0) a.sc[c] = s;
+        return;
+    }
     if (s.okLeap && isfinite(s.propPotential)) {                          // :336
         // ---- UpdateCovariance, :665-695 ----------------------------------
         s.stepsSinceUpdate += 1;
@@ -976,6 +1010,271 @@ kHmcErrorMatrix(HmcArrays a, int n, int count, const double* __restrict__ avgLlh
         atomicExch(&a.eigLocks[slot], 0);
         a.sc[c] = s;
     }
+}
+
+// ===========================================================================
+// Ensemble-pooled UpdateCovariance / UpdateErrorMatrix (NOT in the reference, which keeps
+// one estimate per chain; SURVEY.md K11 "pooled option").  For gradient types 0 / 1 / 3 / 4 / 5
+// the covariance estimate only feeds the step-size and trajectory-length tuning of
+// UpdateErrorMatrix (:833-847); with thousands of chains one estimate from all of them is
+// better than E private ones and costs E times less memory (n = 500, 16 384 chains: 1 MB
+// instead of 16 GB) and bandwidth.  Per step: (count, sum x, sum x x^T) over the chains whose
+// UpdateCovariance call happens (kPoolAccumulateDmma: Y^T Y on the FP64 tensor cores), folded
+// into the running averages with the reference's update rule, weights = samples:
+//     v <- (v T + sum) / (T + count),   T <- min(window, T + count).
+// The trigger of UpdateErrorMatrix (:705-719) is the reference's, on the pooled quantities.
+// Its body needs the largest and smallest |eigenvalue| of the covariance and whether it is
+// positive definite (:762-825): a CTA-wide Cholesky factorisation decides the latter, power
+// iteration on the matrix gives the largest eigenvalue and inverse iteration through the
+// factor the smallest -- no full eigen-decomposition of a 500 x 500 matrix on one warp.
+// ===========================================================================
+constexpr int kHmcPooledMinSteps = 32;      // pooled steps before the first UpdateErrorMatrix: the chains of an
+                                            // ensemble start from common points, their first samples are not a cloud
+
+// running averages: entry k < n of the mean, then the packed second moments
+__global__ void kHmcPooledFold(HmcArrays a, int n) {
+    const long long tri = (long long)n * (n + 1) / 2;
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n + tri) return;
+    const double count = a.poolStats[0];
+    if (!(count > 0.0)) return;
+    const double t = a.pool->trials, t1 = __dadd_rn(t, count);
+    double* dst = k < n ? a.poolAverage + k : a.poolExxt + (k - n);
+    const double sum = a.poolStats[1 + k];
+    *dst = __ddiv_rn(__dadd_rn(__dmul_rn(*dst, t), sum), t1);
+}
+
+// the scalar part of UpdateCovariance (:668-669, :675, :690) and UpdateErrorMatrix up to its trigger (:703-719)
+__global__ void __launch_bounds__(256) kHmcPooledTrigger(HmcArrays a, int n, double window) {
+    __shared__ double part[256];
+    HmcPooled* p = a.pool;
+    const double count = a.poolStats[0];
+    double t = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const double m = a.poolAverage[i];
+        t += fabs(__dsub_rn(a.poolExxt[triIndex(i, i)], __dmul_rn(m, m)));
+    }
+    part[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    p->needUpdate = 0;
+    if (!(count > 0.0)) return;
+    p->stepsSinceUpdate += 1;
+    p->stepsRemaining -= 1;
+    p->stepCount += 1;
+    p->trials = fmin(window, __dadd_rn(p->trials, count));
+    p->repaired = 0;
+    if (p->trials < (double)(2 * n) || p->stepCount < kHmcPooledMinSteps) return;         // :705
+    p->curCovTrace = part[0];
+    const double change = fabs(__dsub_rn(p->curCovTrace, p->estCovTrace));
+    bool doIt = false;
+    if (p->stepsRemaining < 0) doIt = true;
+    if ((double)p->stepsSinceUpdate > __dmul_rn(2.0, (double)n) && change > __dmul_rn(0.01, p->estCovTrace)) doIt = true;
+    if (doIt) {
+        p->needUpdate = 1;
+        a.counters[1] = 1;
+    }
+}
+
+// The body of UpdateErrorMatrix on the pooled estimate (:727-828), one CTA.  scratch: 2 n^2 + 4 n doubles.
+constexpr int kHmcSpectrumThreads = 512;
+__global__ void __launch_bounds__(kHmcSpectrumThreads)
+kHmcPooledSpectrum(HmcArrays a, int n, const double* __restrict__ avgLlh, double* __restrict__ scratch) {
+    __shared__ double red[kHmcSpectrumThreads];
+    __shared__ double bcast;
+    __shared__ int flag;
+    const int tid = threadIdx.x;
+    HmcPooled* p = a.pool;
+    double* m = scratch;                         // the covariance, row-major
+    double* L = m + (size_t)n * n;               // its Cholesky factor (lower triangle)
+    double* x = L + (size_t)n * n;               // iteration vectors
+    double* y = x + n;
+    double* z = y + n;
+    auto blockSum = [&](double v) {
+        red[tid] = v;
+        __syncthreads();
+        for (int o = kHmcSpectrumThreads / 2; o > 0; o >>= 1) {
+            if (tid < o) red[tid] += red[tid + o];
+            __syncthreads();
+        }
+        const double r = red[0];
+        __syncthreads();
+        return r;
+    };
+    for (int k = tid; k < n * n; k += kHmcSpectrumThreads) {                  // :688-689
+        const int i = k / n, j = k - i * n;
+        const int hi = max(i, j), lo = min(i, j);
+        const double v = __dsub_rn(a.poolExxt[triIndex(hi, lo)], __dmul_rn(a.poolAverage[hi], a.poolAverage[lo]));
+        m[k] = v;
+        L[k] = v;
+    }
+    if (tid == 0) flag = 1;
+    __syncthreads();
+    // ---- positive definite?  right-looking Cholesky, L L^T = m
+    for (int c = 0; c < n; ++c) {
+        if (tid == 0) {
+            const double d = L[(size_t)c * n + c];
+            if (!(d > 0.0)) flag = 0;
+            bcast = flag ? sqrt(d) : 1.0;
+        }
+        __syncthreads();
+        if (!flag) break;
+        const double piv = bcast;
+        for (int i = c + tid; i < n; i += kHmcSpectrumThreads) L[(size_t)i * n + c] = L[(size_t)i * n + c] / piv;
+        __syncthreads();
+        const int rem = n - c - 1;
+        for (long long k = tid; k < (long long)rem * rem; k += kHmcSpectrumThreads) {
+            const int i = c + 1 + (int)(k / rem), j = c + 1 + (int)(k % rem);
+            if (j <= i) L[(size_t)i * n + j] -= L[(size_t)i * n + c] * L[(size_t)j * n + c];
+        }
+        __syncthreads();
+    }
+    const bool positiveDefinite = flag != 0;
+    double maxEig = 0.0, minEig = 1e20;
+    if (positiveDefinite) {
+        // ---- largest eigenvalue: power iteration on m (Rayleigh quotient of the last iterate)
+        for (int i = tid; i < n; i += kHmcSpectrumThreads) x[i] = 1.0 + 0.37 * (double)((i * 7) % 11);
+        __syncthreads();
+        for (int it = 0; it < 200; ++it) {
+            for (int i = tid; i < n; i += kHmcSpectrumThreads) {
+                double sum = 0.0;
+                const double* row = m + (size_t)i * n;
+                for (int j = 0; j < n; ++j) sum += row[j] * x[j];
+                y[i] = sum;
+            }
+            __syncthreads();
+            double xx = 0.0, xy = 0.0;
+            for (int i = tid; i < n; i += kHmcSpectrumThreads) {
+                xx += x[i] * x[i];
+                xy += x[i] * y[i];
+            }
+            xx = blockSum(xx);
+            xy = blockSum(xy);
+            const double lambda = xy / xx;
+            const bool done = fabs(lambda - maxEig) <= 1e-10 * fabs(lambda);
+            maxEig = lambda;
+            double yy = 0.0;
+            for (int i = tid; i < n; i += kHmcSpectrumThreads) yy += y[i] * y[i];
+            yy = sqrt(blockSum(yy));
+            for (int i = tid; i < n; i += kHmcSpectrumThreads) x[i] = y[i] / yy;
+            __syncthreads();
+            if (done) break;
+        }
+        // ---- smallest eigenvalue: inverse iteration, m^-1 x through the factor (L z = x, L^T y = z)
+        for (int i = tid; i < n; i += kHmcSpectrumThreads) x[i] = 1.0 + 0.29 * (double)((i * 5) % 13);
+        __syncthreads();
+        double mu = 0.0;
+        for (int it = 0; it < 100; ++it) {
+            for (int i = tid; i < n; i += kHmcSpectrumThreads) z[i] = x[i];
+            __syncthreads();
+            for (int c = 0; c < n; ++c) {                                     // forward substitution, column oriented
+                if (tid == 0) z[c] = z[c] / L[(size_t)c * n + c];
+                __syncthreads();
+                const double zc = z[c];
+                for (int i = c + 1 + tid; i < n; i += kHmcSpectrumThreads) z[i] -= L[(size_t)i * n + c] * zc;
+                __syncthreads();
+            }
+            for (int i = tid; i < n; i += kHmcSpectrumThreads) y[i] = z[i];
+            __syncthreads();
+            for (int c = n - 1; c >= 0; --c) {                                // back substitution with L^T
+                if (tid == 0) y[c] = y[c] / L[(size_t)c * n + c];
+                __syncthreads();
+                const double yc = y[c];
+                for (int i = tid; i < c; i += kHmcSpectrumThreads) y[i] -= L[(size_t)c * n + i] * yc;
+                __syncthreads();
+            }
+            double xx = 0.0, xy = 0.0, yy = 0.0;
+            for (int i = tid; i < n; i += kHmcSpectrumThreads) {
+                xx += x[i] * x[i];
+                xy += x[i] * y[i];
+                yy += y[i] * y[i];
+            }
+            xx = blockSum(xx);
+            xy = blockSum(xy);
+            yy = sqrt(blockSum(yy));
+            const double lambda = xy / xx;                                    // -> 1 / smallest eigenvalue
+            const bool done = fabs(lambda - mu) <= 1e-8 * fabs(lambda);
+            mu = lambda;
+            for (int i = tid; i < n; i += kHmcSpectrumThreads) x[i] = y[i] / yy;
+            __syncthreads();
+            if (done) break;
+        }
+        minEig = 1.0 / mu;
+    } else {
+        // :792-806 -- floor the variances, drop every correlation: the matrix is diagonal from here on
+        double r = fabs(__ddiv_rn(__dmul_rn(p->estCovTrace, 1E-6), (double)n));
+        for (int i = tid; i < n; i += kHmcSpectrumThreads) {
+            double v = m[(size_t)i * n + i];
+            if (v < r) v = r;
+            a.poolDiag[i] = v;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double hi = 0.0, lo = 1e20;
+            for (int i = 0; i < n; ++i) {
+                hi = fmax(hi, fabs(a.poolDiag[i]));
+                lo = fmin(lo, fabs(a.poolDiag[i]));
+            }
+            red[0] = hi;
+            red[1] = lo;
+        }
+        __syncthreads();
+        maxEig = red[0];
+        minEig = red[1];
+        __syncthreads();
+    }
+    double tr = 0.0;                                                          // :813-817
+    for (int i = tid; i < n; i += kHmcSpectrumThreads) tr += fabs(positiveDefinite ? m[(size_t)i * n + i] : a.poolDiag[i]);
+    tr = blockSum(tr);
+    if (tid == 0) {
+        p->repaired = positiveDefinite ? 0 : 1;
+        p->curCovTrace = tr;
+        p->estCovTrace = tr;
+        double maxScale = sqrt(fabs(maxEig)), minScale = sqrt(fabs(minEig));   // :820-825
+        if (maxScale < 0.1) maxScale = 0.1;
+        if (minScale < 0.01) minScale = 0.01;
+        p->maxScale = maxScale;
+        p->minScale = minScale;
+        p->orbitLength = 2.0 * 3.14 * maxScale;                               // :828
+        p->averagePotential = -avgLlh[0];                                     // :729
+        p->stepsRemaining = 2 * n + p->stepCount;                             // :758-759
+        p->stepsSinceUpdate = 0;
+        p->updates += 1;
+    }
+}
+
+// ... and what each chain takes from it: the central point (:734-738), the step size and the
+// trajectory length (:833-847).  One thread per chain.
+__global__ void kHmcPooledApply(HmcArrays a, int n, int chains) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= chains) return;
+    HmcScalars s = a.sc[c];
+    if (!s.started || s.status != 0 || s.leapFrogSteps == 0) return;          // :704
+    const HmcPooled p = *a.pool;
+    if (p.averagePotential < s.centralPotential) {
+        for (int i = 0; i < n; ++i) a.central[(size_t)c * n + i] = a.poolAverage[i];
+        s.centralPotential = p.averagePotential;
+    }
+    s.estCovTrace = p.estCovTrace;
+    s.curCovTrace = p.curCovTrace;
+    s.orbitLength = p.orbitLength;
+    if (s.meanEpsilon > 0) {                                                  // :833-837
+        s.meanEpsilon = __dmul_rn(0.2, p.maxScale);
+        if (s.meanEpsilon > __dmul_rn(0.5, p.minScale)) s.meanEpsilon = __dmul_rn(0.5, p.minScale);
+        if (s.meanEpsilon < __dmul_rn(0.05, p.maxScale)) s.meanEpsilon = __dmul_rn(0.05, p.maxScale);
+    }
+    if (s.leapFrogSteps > 0) {                                                // :839-847
+        const double targetLength = __dmul_rn(0.4, s.orbitLength);
+        s.leapFrogSteps = (int)__ddiv_rn(targetLength, fabs(s.meanEpsilon));
+        s.leapFrogSteps = 2 * (s.leapFrogSteps / 2 + 1);
+        if (s.leapFrogSteps > 3 * n) s.leapFrogSteps = 3 * n;
+        if (s.meanEpsilon > 0) s.meanEpsilon = __ddiv_rn(targetLength, (double)s.leapFrogSteps);
+    }
+    a.sc[c] = s;
 }
 
 struct HmcTraceDev {

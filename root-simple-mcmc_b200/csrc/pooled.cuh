@@ -117,9 +117,11 @@ __device__ __forceinline__ void poolDmma(double& c0, double& c1, double a, doubl
 
 // y[chain][y0 + 8 t + g], t = 0..6, for this lane's chain (c = group + q)
 __device__ __forceinline__ void poolLoadFragment(double (&f)[7], const double* __restrict__ xAcc,
-                                                 const ChainScalars* __restrict__ sc, int n, int c, int cLast,
-                                                 int y0, int g) {
-    const bool live = c < cLast && sc[c].started != 0;
+                                                 const ChainScalars* __restrict__ sc, const int* __restrict__ mask,
+                                                 int n, int c, int cLast, int y0, int g) {
+    // which chains take part: the running ones (sc), or -- TSimpleHMC's pooled covariance -- the
+    // chains marked in `mask`
+    const bool live = c < cLast && (mask ? mask[c] != 0 : sc[c].started != 0);
     const double* xr = xAcc + (size_t)c * n;
 #pragma unroll
     for (int t = 0; t < 7; ++t) {
@@ -130,8 +132,8 @@ __device__ __forceinline__ void poolLoadFragment(double (&f)[7], const double* _
 
 template <bool kDiag>
 __device__ __forceinline__ void poolWarpTiles(const double* __restrict__ xAcc, const ChainScalars* __restrict__ sc,
-                                              int n, int a0, int b0, int cFirst, int cLast, int lane,
-                                              double* red, int warp) {
+                                              const int* __restrict__ mask, int n, int a0, int b0, int cFirst, int cLast,
+                                              int lane, double* red, int warp) {
     constexpr int kTiles = kDiag ? 28 : 49;
     const int g = lane >> 2, q = lane & 3;
     double acc[kTiles][2];
@@ -139,13 +141,13 @@ __device__ __forceinline__ void poolWarpTiles(const double* __restrict__ xAcc, c
     for (int t = 0; t < kTiles; ++t) acc[t][0] = acc[t][1] = 0.0;
     double af[7], bf[7], an[7], bn[7];
     if (cFirst < cLast) {
-        poolLoadFragment(af, xAcc, sc, n, cFirst + q, cLast, a0, g);
-        if (!kDiag) poolLoadFragment(bf, xAcc, sc, n, cFirst + q, cLast, b0, g);
+        poolLoadFragment(af, xAcc, sc, mask, n, cFirst + q, cLast, a0, g);
+        if (!kDiag) poolLoadFragment(bf, xAcc, sc, mask, n, cFirst + q, cLast, b0, g);
     }
     for (int c0 = cFirst; c0 < cLast; c0 += 4) {
         if (c0 + 4 < cLast) {
-            poolLoadFragment(an, xAcc, sc, n, c0 + 4 + q, cLast, a0, g);
-            if (!kDiag) poolLoadFragment(bn, xAcc, sc, n, c0 + 4 + q, cLast, b0, g);
+            poolLoadFragment(an, xAcc, sc, mask, n, c0 + 4 + q, cLast, a0, g);
+            if (!kDiag) poolLoadFragment(bn, xAcc, sc, mask, n, c0 + 4 + q, cLast, b0, g);
         }
 #pragma unroll
         for (int ta = 0; ta < 7; ++ta)
@@ -181,7 +183,7 @@ __device__ __forceinline__ void poolWarpTiles(const double* __restrict__ xAcc, c
 template <bool kDiag>
 __global__ void __launch_bounds__(128, kDiag ? 3 : 2)
 kPoolAccumulateDmma(const double* __restrict__ xAcc, const ChainScalars* __restrict__ sc, int chains, int n,
-                    double* stats, int chainsPerCta) {
+                    double* stats, int chainsPerCta, const int* __restrict__ mask = nullptr) {
     __shared__ double red[(kDiag ? 28 : 49) * 64];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int bi = blockIdx.x, bj = blockIdx.x;
@@ -197,7 +199,7 @@ kPoolAccumulateDmma(const double* __restrict__ xAcc, const ChainScalars* __restr
     const int last = min(chains, first + chainsPerCta);
     const int perWarp = ((chainsPerCta + 15) / 16) * 4;                 // a multiple of 4 chains
     const int wFirst = min(last, first + warp * perWarp), wLast = min(last, wFirst + perWarp);
-    poolWarpTiles<kDiag>(xAcc, sc, n, a0, b0, wFirst, wLast, lane, red, warp);
+    poolWarpTiles<kDiag>(xAcc, sc, mask, n, a0, b0, wFirst, wLast, lane, red, warp);
     // C fragment of tile (ta, tb): row g, columns 2q and 2q+1; the lower triangle goes out
     const int tiles = diagonal ? 28 : 49;
     for (int e = tid; e < tiles * 64; e += 128) {

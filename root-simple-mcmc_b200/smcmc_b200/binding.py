@@ -78,9 +78,12 @@ class _SavedState(ctypes.Structure):
 
 
 # smcmc_hmc_setting / smcmc_hmc_field / scalar columns of SMCMC_HMC_F_SCALARS
-HMC_ALPHA, HMC_MEAN_EPSILON, HMC_LEAPFROG, HMC_USER_GRADIENT, HMC_KEEP_ERROR_MATRIX = range(5)
+HMC_ALPHA, HMC_MEAN_EPSILON, HMC_LEAPFROG, HMC_USER_GRADIENT, HMC_KEEP_ERROR_MATRIX, HMC_POOLED_COVARIANCE = range(6)
 _HMC_FIELDS = {"accepted": (0, "En"), "momentum": (1, "En"), "proposed": (2, "En"), "central": (3, "En"),
-               "average": (4, "En"), "covariance": (5, "Enn"), "error_matrix": (6, "Enn"), "scalars": (7, "Es")}
+               "average": (4, "En"), "covariance": (5, "Enn"), "error_matrix": (6, "Enn"), "scalars": (7, "Es"),
+               "pooled_covariance": (8, "nn"), "pooled_average": (9, "n"), "pooled_scalars": (10, "ps")}
+HMC_POOLED_SCALARS = ["trials", "est_cov_trace", "cur_cov_trace", "orbit_length", "max_scale", "min_scale",
+                      "step_count", "updates", "repaired"]
 HMC_SCALARS = ["acceptance", "mean_epsilon", "leapfrog", "reversal_len", "accepted_potential",
                "proposed_potential", "central_potential", "potential_count", "gradient_count", "step_count",
                "cov_trials", "average_trials", "est_cov_trace", "cur_cov_trace", "orbit_length",
@@ -509,7 +512,8 @@ class Engine:
     def hmc_get(self, name):
         fid, code = _HMC_FIELDS[name]
         E, n = self.chains, self.dim
-        shape = {"En": (E, n), "Enn": (E, n, n), "Es": (E, len(HMC_SCALARS))}[code]
+        shape = {"En": (E, n), "Enn": (E, n, n), "Es": (E, len(HMC_SCALARS)), "nn": (n, n), "n": (n,),
+                 "ps": (len(HMC_POOLED_SCALARS),)}[code]
         out = np.zeros(shape)
         self._check(self.lib.smcmc_hmc_get(self.h, fid, _ptr(out), out.nbytes))
         return out

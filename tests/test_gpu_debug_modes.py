@@ -110,14 +110,14 @@ def test_trace_rows_of_chains_that_are_not_running():
     """A chain whose Start() failed does not step; its trace rows repeat its standing
     state instead of holding whatever the buffer contained."""
     import smcmc_b200
-    eng = smcmc_b200.Engine(smcmc_b200.LLH_HORRIFIC, 6, 4, seed=2)
+    eng = smcmc_b200.Engine(smcmc_b200.LLH_UNIT_GAUSS, 6, 4, seed=2)
     x0 = np.zeros((4, 6))
-    x0[2] = 5.0                                    # outside the box: -1e30 -> Start fails (:265-268)
+    x0[2] = 1e200                                  # likelihood -inf: Start fails for this chain (:265-268)
     ok = eng.start(x0)
     assert list(ok) == [1, 1, 0, 1]
     tr = eng.step_trace(12)
     assert np.all(tr["accepted"][:, 2] == 0)
-    assert np.all(tr["points"][:, 2] == 5.0)
-    assert np.all(tr["llh_proposed"][:, 2] == -1e30)
+    assert np.all(tr["points"][:, 2] == 1e200)
+    assert np.all(tr["llh_proposed"][:, 2] == -np.inf)
     assert np.all(np.isfinite(tr["step_rms"])) and np.all(np.isfinite(tr["sigma"]))
     assert tr["accepted"][:, [0, 1, 3]].sum() > 0

@@ -170,3 +170,106 @@ def test_tensor_mode_matches_exact_mode():
         assert np.array_equal(runs[0]["leapfrog"], runs[1]["leapfrog"])
         assert np.array_equal(runs[0]["accepted"], runs[1]["accepted"])
         assert np.allclose(runs[0]["potential"], runs[1]["potential"], rtol=1e-9)
+
+
+def test_pooled_covariance_mode():
+    """SMCMC_HMC_POOLED_COVARIANCE: one running mean / covariance for the ensemble instead of
+    one per chain (not in the reference).  2048 chains on a correlated 24-dimensional Gaussian:
+    the pooled estimate converges to the target covariance, UpdateErrorMatrix runs on it (largest
+    and smallest eigenvalue from power / inverse iteration through a Cholesky factor: compared
+    with numpy's eigenvalues of the same matrix), every chain takes its step size and trajectory
+    length from it, and the ensemble still samples the target."""
+    import smcmc_b200
+    from smcmc_b200 import binding as b
+    n, E = 24, 2048
+    prec = hmc_error_matrix("spd24")
+    cov = np.linalg.inv(prec)
+    eng = smcmc_b200.Engine(smcmc_b200.LLH_DUMMY, n, E, seed=5)
+    eng.set_error_matrix(prec)
+    eng.hmc_set(b.HMC_USER_GRADIENT, 1)
+    eng.hmc_set(b.HMC_POOLED_COVARIANCE, 1)
+    eng.hmc_start(np.zeros(n))
+    eng.hmc_step(31)
+    ps = dict(zip(b.HMC_POOLED_SCALARS, eng.hmc_get("pooled_scalars")))
+    assert ps["updates"] == 0 and ps["step_count"] == 31 and ps["trials"] == 31 * E
+    eng.hmc_step(1)                                     # step 32: the first UpdateErrorMatrix on the pooled estimate
+    ps = dict(zip(b.HMC_POOLED_SCALARS, eng.hmc_get("pooled_scalars")))
+    got = eng.hmc_get("pooled_covariance")
+    assert ps["updates"] == 1 and ps["repaired"] == 0
+    lam = np.linalg.eigvalsh(got)
+    assert abs(ps["max_scale"] / max(0.1, np.sqrt(lam[-1])) - 1.0) < 1e-6
+    assert abs(ps["min_scale"] / max(0.01, np.sqrt(lam[0])) - 1.0) < 1e-5
+    assert abs(ps["est_cov_trace"] / np.trace(got) - 1.0) < 1e-12
+    assert abs(ps["orbit_length"] - 2.0 * 3.14 * ps["max_scale"]) < 1e-12
+    sc = eng.hmc_scalars()
+    target = 0.4 * ps["orbit_length"]
+    assert np.all(sc["leapfrog"] >= 2) and np.all(sc["leapfrog"] % 2 == 0)       # :841-842
+    assert np.allclose(sc["mean_epsilon"] * sc["leapfrog"], target, rtol=1e-12)  # :847
+    with pytest.raises(smcmc_b200.SmcmcError):
+        eng.hmc_get("covariance")
+    eng.hmc_step(150)
+    pts = []
+    for _ in range(10):
+        eng.hmc_step(10)
+        pts.append(eng.hmc_get("accepted"))
+    x = np.concatenate(pts)
+    assert np.all(np.abs(x.mean(0)) < 0.05)
+    assert np.max(np.abs(np.cov(x.T) - cov)) < 0.08 * np.max(np.diag(cov))
+    pooled = eng.hmc_get("pooled_covariance")
+    assert np.max(np.abs(pooled - cov)) < 0.1 * np.max(np.diag(cov))
+    assert np.all(np.abs(eng.hmc_get("pooled_average")) < 0.05)
+    sc = eng.hmc_scalars()
+    assert np.all(sc["step_count"] == 282) and 0.3 < np.mean(sc["acceptance"]) < 1.0
+
+
+def test_pooled_covariance_is_the_default_for_large_ensembles_only():
+    """n = 500: 300 chains (300 MB of per-chain triangles) pool automatically, 48 chains keep the
+    reference's per-chain estimate."""
+    import smcmc_b200
+    from smcmc_b200 import binding as b
+    prec = hmc_error_matrix("spd500")
+    for E, pooled in ((48, False), (300, True)):
+        eng = smcmc_b200.Engine(smcmc_b200.LLH_DUMMY, 500, E, seed=5)
+        eng.set_error_matrix(prec)
+        eng.set_dummy_mode(b.DUMMY_TENSOR)
+        eng.hmc_set(b.HMC_USER_GRADIENT, 1)
+        eng.hmc_start(np.ones(500))
+        eng.hmc_step(3)
+        if pooled:
+            assert eng.hmc_get("pooled_scalars")[0] == 3 * E
+        else:
+            with pytest.raises(smcmc_b200.SmcmcError):
+                eng.hmc_get("pooled_scalars")
+
+
+@pytest.mark.parametrize("n,E", [(130, 70), (37, 130), (500, 96)])
+def test_fused_leapfrog_stage_equals_gradient_plus_kick_drift(monkeypatch, n, E):
+    """TENSOR mode runs a leap-frog stage as ONE launch (kHmcLeapDmma: the gradient GEMM with the
+    kick, the drift and the U-turn partial sums in its epilogue).  Against the same mode with the
+    gradient kernel and kHmcKickDrift as separate launches (SMCMC_HMC_NO_FUSE=1): the same
+    arithmetic per element, so positions, potentials, step sizes, trajectory lengths and the
+    gradient counters are identical (ragged chain and column tiles, odd and even dimensions)."""
+    import smcmc_b200
+    from smcmc_b200 import binding as b
+    prec = hmc_error_matrix("spd%d" % n)
+    runs = {}
+    for fused in (1, 0):
+        if fused:
+            monkeypatch.delenv("SMCMC_HMC_NO_FUSE", raising=False)
+        else:
+            monkeypatch.setenv("SMCMC_HMC_NO_FUSE", "1")
+        h = smcmc_b200.Engine(smcmc_b200.LLH_DUMMY, n, E, seed=6)
+        h.set_error_matrix(prec)
+        h.set_dummy_mode(b.DUMMY_TENSOR)
+        h.hmc_set(b.HMC_USER_GRADIENT, 1)
+        h.hmc_start(np.full(n, 0.5))
+        before = h.launch_count()
+        tr = h.hmc_step_trace(30 if n < 500 else 12, 0)
+        tr["launches"] = h.launch_count() - before
+        tr["scalars"] = h.hmc_get("scalars")
+        tr["momentum"] = h.hmc_get("momentum")
+        runs[fused] = tr
+    for k in ("potential", "points", "mean_epsilon", "leapfrog", "accepted", "scalars", "momentum"):
+        assert np.array_equal(runs[1][k], runs[0][k]), k
+    assert runs[1]["launches"] < 0.62 * runs[0]["launches"]       # one launch per stage instead of two
+    assert np.abs(runs[1]["leapfrog"]).max() > 10 and runs[1]["accepted"].sum() > 0

@@ -126,7 +126,8 @@ def test_resident_equals_the_three_launch_step(monkeypatch, make, steps):
     assert a["launches"] < b["launches"] / 50     # one launch per call instead of three per step
 
 
-@pytest.mark.parametrize("name", sorted(GOLDEN_CHAINS))
+# (a user functor -- kind 8 -- has no code inside the resident kernel: it steps through its own launches)
+@pytest.mark.parametrize("name", sorted(k for k in GOLDEN_CHAINS if GOLDEN_CHAINS[k][0] != 8))
 def test_resident_reaches_the_golden_end_state(name):
     import smcmc_b200
     from oracle.cpu_checkers import STATE_FIELDS
