@@ -230,7 +230,6 @@ template <bool VEC16>
 __global__ void __launch_bounds__(128, 3)
 kHmcLeapDmma(const double* __restrict__ err, LeapFused f, int k, int chains, int n) {
     extern __shared__ __align__(16) double dmmaSmem[];
-    __shared__ double part[kDmmaBM][2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
     const int c0 = blockIdx.y * kDmmaBM, i0 = blockIdx.x * kDmmaBN;
@@ -248,44 +247,124 @@ kHmcLeapDmma(const double* __restrict__ err, LeapFused f, int k, int chains, int
     }
     double acc[4][4][2];
     dmmaMainloop<VEC16>(acc, dmmaSmem, f.qIn, err, c0, chains, i0, n, tid);
+    // The gradient tile goes through shared memory (the pipeline buffers are free now) so that the
+    // element-wise part reads and writes WHOLE ROWS: a warp takes a chain's 64 dimensions of this
+    // column block as one 512-byte piece of q, p, p0 (16 bytes per lane), instead of the 8 x 64-byte
+    // pieces of the accumulator layout.
+    constexpr int kLd = kDmmaBN + 2;
+    double* tile = dmmaSmem;                                   // [64][66]
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const int c = c0 + wm + a * 8 + g;
-        double dot = 0.0;
-        if (c < chains) {
-            const int st = f.leapSteps[c];
-            const bool live = st >= 1 && k <= st;
-            const bool half = (k == 0) || (k == st);
-            const bool drift = live && k < st;
-            const double eps = live ? f.epsilon[(size_t)c * f.scalarStride] : 0.0;
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
+        for (int b = 0; b < 4; ++b) {
+            double2 v;
+            v.x = acc[a][b][0];
+            v.y = acc[a][b][1];
+            *reinterpret_cast<double2*>(tile + (wm + a * 8 + g) * kLd + wn + b * 8 + 2 * q) = v;
+        }
+    __syncthreads();
+    // rows in batches of kBatch: every load of a batch is issued before the first store (the row
+    // loop would otherwise wait for one round trip to L2 per row: 16 in a row per warp)
+    constexpr int kBatch = 4;
+    int col[2];
+    bool in[2];
+    if (VEC16) {
+        col[0] = 2 * lane;
+        col[1] = 2 * lane + 1;
+    } else {
+        col[0] = lane;
+        col[1] = lane + 32;
+    }
+    in[0] = i0 + col[0] < n;
+    in[1] = i0 + col[1] < n;
+    for (int r0 = warp * (kDmmaBM / 4); r0 < (warp + 1) * (kDmmaBM / 4); r0 += kBatch) {
+        double gv[kBatch][2], qv[kBatch][2], pv[kBatch][2], p0v[kBatch][2], eps[kBatch];
+        int st[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const int c = c0 + r0 + u;
+            st[u] = c < chains ? f.leapSteps[c] : -1;
+            const bool live = st[u] >= 1 && k <= st[u];
+            eps[u] = live ? f.epsilon[(size_t)c * f.scalarStride] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const int c = c0 + r0 + u;
+            if (c >= chains) continue;
+            const bool live = st[u] >= 1 && k <= st[u];
+            const bool half = (k == 0) || (k == st[u]);
+            const size_t base = (size_t)c * n + i0;
+            if (VEC16) {                                       // n even: both columns of a lane are in range or neither
+                if (in[0]) {
+                    const double2 t2 = *reinterpret_cast<const double2*>(tile + (r0 + u) * kLd + col[0]);
+                    const double2 q2 = *reinterpret_cast<const double2*>(f.qIn + base + col[0]);
+                    gv[u][0] = t2.x; gv[u][1] = t2.y; qv[u][0] = q2.x; qv[u][1] = q2.y;
+                    if (live) {
+                        const double2 p2 = *reinterpret_cast<const double2*>(f.p + base + col[0]);
+                        pv[u][0] = p2.x; pv[u][1] = p2.y;
+                        if (!half) {
+                            const double2 z2 = *reinterpret_cast<const double2*>(f.p0 + base + col[0]);
+                            p0v[u][0] = z2.x; p0v[u][1] = z2.y;
+                        }
+                    }
+                }
+            } else {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const int i = i0 + wn + b * 8 + 2 * q + h;
-                    if (i >= n) continue;
-                    const size_t at = (size_t)c * n + i;
-                    const double qv = f.qIn[at];
-                    if (!live) {
-                        f.qOut[at] = qv;
-                        continue;
+                    if (!in[h]) continue;
+                    gv[u][h] = tile[(r0 + u) * kLd + col[h]];
+                    qv[u][h] = f.qIn[base + col[h]];
+                    if (live) {
+                        pv[u][h] = f.p[base + col[h]];
+                        if (!half) p0v[u][h] = f.p0[base + col[h]];
                     }
-                    double kick = __dmul_rn(eps, acc[a][b][h]);
-                    if (half) kick = __ddiv_rn(kick, 2.0);
-                    const double pv = __dsub_rn(f.p[at], kick);
-                    f.p[at] = pv;
-                    if (!half) dot += __dmul_rn(pv, f.p0[at]);
-                    f.qOut[at] = drift ? __dadd_rn(qv, __dmul_rn(eps, pv)) : qv;
                 }
             }
         }
-        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-        if (q == 0) part[wm + a * 8 + g][warp & 1] = dot;
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const int c = c0 + r0 + u;
+            if (c >= chains) continue;
+            const bool live = st[u] >= 1 && k <= st[u];
+            const bool half = (k == 0) || (k == st[u]);
+            const bool drift = live && k < st[u];
+            const size_t base = (size_t)c * n + i0;
+            double dot = 0.0;
+            double qo[2] = {0.0, 0.0}, po[2] = {0.0, 0.0};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (!in[h]) continue;
+                qo[h] = qv[u][h];
+                if (!live) continue;
+                double kick = __dmul_rn(eps[u], gv[u][h]);
+                if (half) kick = __ddiv_rn(kick, 2.0);
+                po[h] = __dsub_rn(pv[u][h], kick);
+                if (!half) dot += __dmul_rn(po[h], p0v[u][h]);
+                if (drift) qo[h] = __dadd_rn(qv[u][h], __dmul_rn(eps[u], po[h]));
+            }
+            if (VEC16) {
+                if (in[0]) {
+                    double2 o;
+                    o.x = qo[0]; o.y = qo[1];
+                    *reinterpret_cast<double2*>(f.qOut + base + col[0]) = o;
+                    if (live) {
+                        o.x = po[0]; o.y = po[1];
+                        *reinterpret_cast<double2*>(f.p + base + col[0]) = o;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (!in[h]) continue;
+                    f.qOut[base + col[h]] = qo[h];
+                    if (live) f.p[base + col[h]] = po[h];
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            if (lane == 0) f.uturn[((size_t)(k & 1) * chains + c) * f.blocks + blockIdx.x] = dot;
+        }
     }
-    __syncthreads();
-    if (tid < kDmmaBM && c0 + tid < chains)
-        f.uturn[((size_t)(k & 1) * chains + c0 + tid) * f.blocks + blockIdx.x] = part[tid][0] + part[tid][1];
 }
 
 inline void launchHmcLeapDmma(cudaStream_t stream, const double* err, const LeapFused& f, int k, int chains, int n) {

@@ -127,7 +127,7 @@ struct smcmc_engine {
     DeviceBuffer<double> fakeTerms;     // kFakeFinish with few points: the 150 bin terms per point
     DeviceBuffer<unsigned int> fakeTickets;
     bool staged = false;                // kProposeStaged (one CTA per chain) instead of kPropose
-    int stagedDraw = 0;                 // its DRAW variant
+    int stagedDraw = 1;                 // its DRAW variant (1 measured fastest on C3, 0.536 vs 0.540 / 0.550 ms per step)
     bool resident = false;              // kStepsResident fits (whole steps out of shared memory)
     int residentPerSm = 0;              // its CTAs per SM
     int64_t residentLaunches = 0;
@@ -342,7 +342,8 @@ struct smcmc_engine {
             nccl.check(nccl.AllReduce(poolStatsAll.get(), poolStatsAll.get(), poolStatCount(), ncclDouble, ncclSum,
                                       worldComm, stream), "all-reduce of pooled statistics");
         }
-        kPoolFactor<<<1, 32, 0, stream>>>(pooled(), n(), poolOk.get());
+        if (std::getenv("SMCMC_POOL_FACTOR_WARP")) kPoolFactor<<<1, 32, 0, stream>>>(pooled(), n(), poolOk.get());
+        else kPoolFactorCta<<<1, kPoolFactorThreads, 0, stream>>>(pooled(), n(), poolOk.get());
         launched();
         poolTranspose();
         ++poolExchanges;
@@ -613,7 +614,8 @@ struct smcmc_engine {
                 int64_t tiles = 0;
                 for (int c = 0; c < kFakeClasses; ++c) tiles += fakeClassCount[c] / kPairTile;
                 const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)smCount * 8, (tiles + 7) / 8));
-                kFakeStream<<<blocks, kStreamThreads, 0, stream>>>(L);
+                if (std::getenv("SMCMC_STREAM_PREFETCH")) kFakeStream<true><<<blocks, kStreamThreads, 0, stream>>>(L);
+                else kFakeStream<false><<<blocks, kStreamThreads, 0, stream>>>(L);
             } else
                 kFakePairs<<<(unsigned)chunks * (unsigned)pointTiles, kPairThreads, kPairSmemBytes, stream>>>(L);
             launched();

@@ -807,15 +807,26 @@ __device__ __forceinline__ void streamCount(const FilterDecision& dec, int cls, 
     atomicAdd(&table[chain * kStreamRows + fakeClassSlotBase(cls) + row], 1u);
 }
 
+// a lane's four events of one tile (four coalesced 16-byte loads; the separation only for the untagged classes)
+struct StreamRegs {
+    float4 ls, d, nl, sp;
+};
 template <bool TAGGED>
-__device__ __forceinline__ void streamTile(const PairLaunch& L, int cls, int64_t tileIndex, int lane,
-                                           const FilterChain* fcs, const FakeChainParams* cps, uint32_t* table) {
+__device__ __forceinline__ StreamRegs streamLoad(const PairLaunch& L, int64_t tileIndex, int lane) {
     const FilterTile& tile = L.filterTiles[tileIndex];
-    const float4 ls = reinterpret_cast<const float4*>(tile.ls)[lane];
-    const float4 d = reinterpret_cast<const float4*>(tile.d)[lane];
-    const float4 nl = reinterpret_cast<const float4*>(tile.nl2)[lane];
-    float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!TAGGED) sp = reinterpret_cast<const float4*>(tile.sep)[lane];
+    StreamRegs r;
+    r.ls = __ldcs(reinterpret_cast<const float4*>(tile.ls) + lane);      // read once: streaming loads
+    r.d = __ldcs(reinterpret_cast<const float4*>(tile.d) + lane);
+    r.nl = __ldcs(reinterpret_cast<const float4*>(tile.nl2) + lane);
+    r.sp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!TAGGED) r.sp = __ldcs(reinterpret_cast<const float4*>(tile.sep) + lane);
+    return r;
+}
+
+template <bool TAGGED>
+__device__ __forceinline__ void streamTile(const PairLaunch& L, int cls, int64_t tileIndex, int lane, const StreamRegs& regs,
+                                           const FilterChain* fcs, const FakeChainParams* cps, uint32_t* table) {
+    const float4 ls = regs.ls, d = regs.d, nl = regs.nl, sp = regs.sp;
     const int64_t event0 = tileIndex * kPairTile + 4 * lane;
     for (int c = 0; c < L.numPoints; ++c) {
         const FilterChain fc = fcs[c];
@@ -831,7 +842,10 @@ __device__ __forceinline__ void streamTile(const PairLaunch& L, int cls, int64_t
     }
 }
 
-__global__ void __launch_bounds__(kStreamThreads)
+// PREFETCH: the loads of a warp's next tile are in flight while the current one is evaluated
+// (80 registers, three CTAs per SM) or not (54 registers, four CTAs per SM)
+template <bool PREFETCH>
+__global__ void __launch_bounds__(kStreamThreads, PREFETCH ? 3 : 4)
 kFakeStream(const __grid_constant__ PairLaunch L) {
     __shared__ uint32_t table[kStreamMaxChains * kStreamRows];
     __shared__ FilterChain fcs[kStreamMaxChains];
@@ -848,9 +862,27 @@ kFakeStream(const __grid_constant__ PairLaunch L) {
     for (int cls = 0; cls < kFakeClasses; ++cls) {
         const int64_t firstTile = L.classBase[cls] / kPairTile;
         const int64_t tiles = L.classCount[cls] / kPairTile;             // padded to whole tiles
-        for (int64_t t = warp; t < tiles; t += warps) {
-            if (cls & 1) streamTile<true>(L, cls, firstTile + t, lane, fcs, cps, table);
-            else streamTile<false>(L, cls, firstTile + t, lane, fcs, cps, table);
+        if (!PREFETCH) {
+            for (int64_t t = warp; t < tiles; t += warps) {
+                if (cls & 1) streamTile<true>(L, cls, firstTile + t, lane, streamLoad<true>(L, firstTile + t, lane), fcs, cps, table);
+                else streamTile<false>(L, cls, firstTile + t, lane, streamLoad<false>(L, firstTile + t, lane), fcs, cps, table);
+            }
+        } else if (cls & 1) {
+            StreamRegs nxt;
+            if (warp < tiles) nxt = streamLoad<true>(L, firstTile + warp, lane);
+            for (int64_t t = warp; t < tiles; t += warps) {
+                const StreamRegs cur = nxt;
+                if (t + warps < tiles) nxt = streamLoad<true>(L, firstTile + t + warps, lane);
+                streamTile<true>(L, cls, firstTile + t, lane, cur, fcs, cps, table);
+            }
+        } else {
+            StreamRegs nxt;
+            if (warp < tiles) nxt = streamLoad<false>(L, firstTile + warp, lane);
+            for (int64_t t = warp; t < tiles; t += warps) {
+                const StreamRegs cur = nxt;
+                if (t + warps < tiles) nxt = streamLoad<false>(L, firstTile + t + warps, lane);
+                streamTile<false>(L, cls, firstTile + t, lane, cur, fcs, cps, table);
+            }
         }
     }
     __syncthreads();

