@@ -294,6 +294,23 @@ struct smcmc_engine {
         if (!mask && std::getenv("SMCMC_POOL_ACC_SCALAR")) {
             const int poolBlocks = std::min(smCount * 8, ceilDiv(E(), kPoolTile));
             kPoolAccumulate<<<poolBlocks, 256, poolAccSmem(n()), stream>>>(xAcc.get(), sc.get(), E(), n(), stats);
+        } else if (n() >= 64 && !std::getenv("SMCMC_POOL_ACC_DIRECT")) {
+            // large dimension: shared-memory tiled Y^T Y (kPoolGramDmma)
+            const int nb = ceilDiv(n() + 1, kGramB), pairs = nb * (nb + 1) / 2;
+            int slices = std::max(1, std::min(ceilDiv(E(), 4 * kGramK), ceilDiv(3 * smCount, pairs)));
+            slices = std::max(slices, ceilDiv(E(), 4096));                 // the liveness flags of a slice sit in shared memory
+            const int perCta = ceilDiv(ceilDiv(E(), slices), kGramK) * kGramK;
+            slices = ceilDiv(E(), perCta);
+            const size_t smem = kGramSmemBytes + (size_t)((perCta + 15) & ~15);
+            if (smem > gramSmemSet) {
+                CUDA_CHECK(cudaFuncSetAttribute(kPoolGramDmma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CUDA_CHECK(cudaFuncSetAttribute(kPoolGramDmma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                gramSmemSet = smem;
+            }
+            if ((n() & 1) == 0)
+                kPoolGramDmma<true><<<dim3(pairs, slices), 128, smem, stream>>>(x, scalars, mask, E(), n(), stats, perCta);
+            else
+                kPoolGramDmma<false><<<dim3(pairs, slices), 128, smem, stream>>>(x, scalars, mask, E(), n(), stats, perCta);
         } else {
             const int blocks = ceilDiv(n() + 1, kPaBlock);
             const int pairs = blocks * (blocks + 1) / 2;
@@ -564,6 +581,7 @@ struct smcmc_engine {
     }
     bool collectStats = false;
     size_t dummySmemSet = 48 << 10;
+    size_t gramSmemSet = 0;
     // event-sharded evaluation: the count table in blocks of this many points (one block per
     // rank of the event group), 0 = one block
     int fakeBlockPoints = 0;

@@ -225,6 +225,124 @@ kPoolAccumulateDmma(const double* __restrict__ xAcc, const ChainScalars* __restr
     }
 }
 
+// ---------------------------------------------------------------------------
+// The same statistics for LARGE dimensions (n >= 64): S = Y^T Y as a shared-memory tiled
+// DMMA GEMM, 64 x 64 statistics per CTA, the chains as the K dimension in steps of 16 through a
+// three-stage cp.async pipeline.  (kPoolAccumulateDmma above feeds the tensor cores straight from
+// global memory: right for n = 50, but at n = 500 its 7-tile blocks re-read every chain row 9 times
+// with 56-byte pieces -- 0.58 ms per step at 16 384 chains, 8 TFLOP/s.)  Here the statistics are
+// ordered (x_0 .. x_{n-1}, 1): the x part of a chain's row starts on a 16-byte boundary when n is
+// even, the column of ones is made in shared memory.  Tile pairs bi >= bj on blockIdx.x, chain
+// slices on blockIdx.y; shared-memory tiles are [chain][statistic] with row stride 68, which puts
+// the 16 lanes of a half warp (4 chains x 4 statistics) on 16 different bank pairs.
+// ---------------------------------------------------------------------------
+constexpr int kGramB = 64, kGramK = 16, kGramLd = 68, kGramStages = 3;
+constexpr int kGramStageDoubles = 2 * kGramK * kGramLd;
+constexpr size_t kGramSmemBytes = (size_t)kGramStages * kGramStageDoubles * sizeof(double);
+
+template <bool VEC16>
+__device__ __forceinline__ void gramLoadTile(double* dst, const double* __restrict__ x, const unsigned char* __restrict__ liveS,
+                                             int n, int s0, int c0, int cFirst, int cLast, int tid) {
+    constexpr int kPieces = VEC16 ? kGramK * kGramB / 2 : kGramK * kGramB;
+#pragma unroll
+    for (int p = 0; p < kPieces / 128; ++p) {
+        const int idx = p * 128 + tid;
+        const int r = VEC16 ? idx >> 5 : idx >> 6;
+        const int sl = VEC16 ? (idx & 31) * 2 : (idx & 63);
+        const int c = c0 + r, st = s0 + sl;
+        const bool live = c < cLast && liveS[c - cFirst] != 0;
+        double* d = dst + r * kGramLd + sl;
+        if (VEC16) {
+            if (live && st + 1 < n) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(d)),
+                             "l"(x + (size_t)c * n + st) : "memory");
+            } else {
+                d[0] = !live ? 0.0 : (st < n ? x[(size_t)c * n + st] : (st == n ? 1.0 : 0.0));
+                d[1] = !live ? 0.0 : (st + 1 < n ? x[(size_t)c * n + st + 1] : (st + 1 == n ? 1.0 : 0.0));
+            }
+        } else {
+            if (live && st < n) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(d)),
+                             "l"(x + (size_t)c * n + st) : "memory");
+            } else {
+                d[0] = (live && st == n) ? 1.0 : 0.0;
+            }
+        }
+    }
+}
+
+template <bool VEC16>
+__global__ void __launch_bounds__(128, 3)
+kPoolGramDmma(const double* __restrict__ x, const ChainScalars* __restrict__ sc, const int* __restrict__ mask, int chains,
+              int n, double* stats, int chainsPerCta) {
+    extern __shared__ __align__(16) double gramSmem[];
+    // which chains of this CTA's slice take part (running, or marked): read once, not per copy
+    unsigned char* liveS = reinterpret_cast<unsigned char*>(gramSmem + kGramStages * kGramStageDoubles);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    const int g = lane >> 2, q = lane & 3;
+    int bi = 0, rest = blockIdx.x;                              // block pair (bi >= bj), row by row
+    while (rest > bi) { rest -= bi + 1; ++bi; }
+    const int bj = rest;
+    const bool diag = bi == bj;
+    const int a0 = bi * kGramB, b0 = bj * kGramB;
+    const int first = blockIdx.y * chainsPerCta, last = min(chains, first + chainsPerCta);
+    for (int c = first + tid; c < last; c += 128) liveS[c - first] = (mask ? mask[c] != 0 : sc[c].started != 0) ? 1 : 0;
+    __syncthreads();
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    const int steps = (last - first + kGramK - 1) / kGramK;
+    auto load = [&](int st) {
+        double* base = gramSmem + (st % kGramStages) * kGramStageDoubles;
+        gramLoadTile<VEC16>(base, x, liveS, n, a0, first + st * kGramK, first, last, tid);
+        if (!diag) gramLoadTile<VEC16>(base + kGramK * kGramLd, x, liveS, n, b0, first + st * kGramK, first, last, tid);
+    };
+#pragma unroll
+    for (int st = 0; st < kGramStages - 1; ++st) {
+        if (st < steps) load(st);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int s = 0; s < steps; ++s) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kGramStages - 2) : "memory");
+        __syncthreads();
+        if (s + kGramStages - 1 < steps) load(s + kGramStages - 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const double* As = gramSmem + (s % kGramStages) * kGramStageDoubles;
+        const double* Bs = diag ? As : As + kGramK * kGramLd;
+#pragma unroll
+        for (int kk = 0; kk < kGramK; kk += 4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) af[a] = As[(kk + q) * kGramLd + wm + a * 8 + g];     // A(statistic g, chain q)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) bf[b] = Bs[(kk + q) * kGramLd + wn + b * 8 + g];     // B(chain q, statistic g)
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) poolDmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // C fragment of tile (a, b): row g, columns 2q and 2q+1; statistics in the order (x, 1)
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int sa = a0 + wm + a * 8 + g, sb = b0 + wn + b * 8 + 2 * q + h;
+                const double v = acc[a][b][h];
+                if (sa > n || sb > sa || v == 0.0) continue;
+                int k;
+                if (sa == n) k = (sb == n) ? 0 : 1 + sb;                       // count, sum x_sb
+                else k = 1 + n + sa * (sa + 1) / 2 + sb;                       // sum x_sa x_sb, sb <= sa
+                atomicAdd(&stats[k], v);
+            }
+}
+
 // One CTA: S -> mean, covariance, trace, U.  Keeps the previous U when the pooled covariance is
 // not (yet) positive definite.  ok[0] = 1 on success.  The factorisation is the column-ordered
 // U^T U = A of the per-chain path (warpCholesky: every entry the same operations in the same
@@ -255,6 +373,7 @@ __global__ void __launch_bounds__(kPoolFactorThreads) kPoolFactorCta(PooledState
         // entries (c, j), j >= c: v = A(c,j) - sum_{r<c} U(r,j) U(r,c), r ascending
         for (int j = c + tid; j < n; j += kPoolFactorThreads) {
             double v = ps.cov[triIndex(j, c)];
+#pragma unroll 8
             for (int r = 0; r < c; ++r) v = __dsub_rn(v, __dmul_rn(u[(size_t)r * n + j], u[(size_t)r * n + c]));
             if (j == c) {
                 if (v <= 0.0) goodS = 0;

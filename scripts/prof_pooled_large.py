@@ -10,5 +10,5 @@ eng = smcmc_b200.Engine(smcmc_b200.LLH_UNIT_GAUSS, n, E, seed=4)
 eng.prop_set(b.PROP_POOLED_EVERY, 16)
 eng.prop_set(b.PROP_POOLED_TENSOR, 1)
 eng.start(np.zeros(n))
-eng.step(8); eng.sync()
+eng.step(int(os.environ.get("POOLED_STEPS", "8"))); eng.sync()
 print("done")

@@ -124,8 +124,8 @@ def test_tensor_core_accumulation_matches_the_scalar_kernel(monkeypatch, n, E):
 @pytest.mark.parametrize("n,E", [(8, 512), (50, 2048), (130, 384)])
 def test_cta_wide_factorisation_equals_the_warp_one(monkeypatch, n, E):
     """kPoolFactorCta (one thread per column) against kPoolFactor (one warp, SMCMC_POOL_FACTOR_WARP=1):
-    the same operations in the same order per entry, so the shared factor -- and with it every chain --
-    is bit-identical."""
+    the same operations in the same order per entry: the shared factor and every chain agree to the
+    rounding of the (atomically summed) statistics."""
     import smcmc_b200
     from smcmc_b200 import binding
     runs = {}
@@ -140,7 +140,8 @@ def test_cta_wide_factorisation_equals_the_warp_one(monkeypatch, n, E):
         assert eng.start(x0).all()
         tr = eng.step_trace(30, want=("accepted", "points"))
         runs[warp] = {"points": tr["points"], "u": eng.get("pooled_decomposition"), "cov": eng.get("pooled_covariance")}
-    assert np.array_equal(runs[0]["u"], runs[1]["u"])
-    assert np.array_equal(runs[0]["points"], runs[1]["points"])
+    # (the statistics themselves are sums of FP64 atomics: equal to rounding from run to run)
+    assert np.allclose(runs[0]["u"], runs[1]["u"], rtol=1e-9, atol=1e-12)
+    assert np.allclose(runs[0]["points"], runs[1]["points"], rtol=1e-9, atol=1e-11)
     u = runs[0]["u"]
     assert np.abs(np.triu(u, 1)).max() > 0 and np.allclose(np.tril(u, -1), 0)
