@@ -577,6 +577,10 @@ struct smcmc_engine {
         L.blockPoints = fakeBlockPoints > 0 ? fakeBlockPoints : stride;
         L.counts = fakeCounts.get();
         L.stats = collectStats ? fakeStats.get() : nullptr;
+        L.irregular = fakeIrregular.get();
+        L.irregularCount = fakeIrregularCount;
+        L.points = nullptr;
+        L.dim = n();
         return L;
     }
     bool collectStats = false;
@@ -611,13 +615,18 @@ struct smcmc_engine {
         fakeFilterChains.reserve(stride);
         fakeCounts.reserve((size_t)kFakeSlots * stride);
         fakeCountStride = stride;
-        CUDA_CHECK(cudaMemsetAsync(fakeCounts.get(), 0, (size_t)kFakeSlots * stride * sizeof(uint32_t), stream));
+        const bool streaming = m <= kStreamMaxChains && !std::getenv("SMCMC_FAKE_NO_STREAM");
+        // few points: the (small) count table is cleared by the prepare kernel, no memset node
+        if (!streaming) CUDA_CHECK(cudaMemsetAsync(fakeCounts.get(), 0, (size_t)kFakeSlots * stride * sizeof(uint32_t), stream));
         kFakePrepareChains<<<ceilDiv(m, 128), 128, 0, stream>>>(xDev, m, n(), fakeExposure, fakeChains.get(),
                                                                 fakeFilterChains.get(), exactOnly ? 1 : 0,
-                                                                cfg.likelihood == SMCMC_LLH_FAKE2 ? 1 : 0);
+                                                                cfg.likelihood == SMCMC_LLH_FAKE2 ? 1 : 0,
+                                                                streaming ? fakeCounts.get() : nullptr,
+                                                                streaming ? kFakeSlots * stride : 0);
         launched();
 
         PairLaunch L = pairLaunch(m, stride);
+        L.points = xDev;
         const int chunks = L.chunkBase[kFakeClasses];
         if (chunks > 0) {
             const int pointTiles = ceilDiv(m, kPairThreads);
@@ -627,7 +636,7 @@ struct smcmc_engine {
                 CUDA_CHECK(cudaEventCreate(&e1));
                 CUDA_CHECK(cudaEventRecord(e0, stream));
             }
-            if (m <= kStreamMaxChains && !std::getenv("SMCMC_FAKE_NO_STREAM")) {
+            if (streaming) {
                 // few chains: events streamed once, chains looped per event (fake_likelihood.cuh)
                 int64_t tiles = 0;
                 for (int c = 0; c < kFakeClasses; ++c) tiles += fakeClassCount[c] / kPairTile;
@@ -643,7 +652,7 @@ struct smcmc_engine {
             }
             ++pairLaunches;
         }
-        if (fakeIrregularCount > 0) {
+        if (fakeIrregularCount > 0 && !(streaming && chunks > 0)) {       // (kFakeStream takes them along)
             long long pairs = (long long)fakeIrregularCount * m;
             kFakePairsGeneric<<<ceilDiv(pairs, 256), 256, 0, stream>>>(fakeIrregular.get(), fakeIrregularCount,
                                                                        xDev, m, n(), fakeCounts.get(), L.blockPoints);
@@ -789,7 +798,7 @@ struct smcmc_engine {
             forcedPending = false;                                       // fForcedStep.clear(), :677
             vaatSynced = false;
             evaluate(xProp.get(), E(), llhProp.get(), nullptr);
-            kAccept<<<ceilDiv(E(), kAcceptThreads), kAcceptThreads, 0, stream>>>(a, ps, E(), llhProp.get(), cfg.seed,
+            kAccept<<<ceilDiv(E(), acceptThreads()), acceptThreads(), 0, stream>>>(a, ps, E(), llhProp.get(), cfg.seed,
                                                                                  cfg.chain_offset, stepRef(), metropolis, tr,
                                                                                  traceStep, nullptr, forced ? 0 : 1);
             launched();
@@ -834,7 +843,7 @@ struct smcmc_engine {
                 a, ps, E(), cfg.likelihood, cfg.seed, cfg.chain_offset, stepRef(), metropolis, acceptSlot);
         } else {
             evaluate(xProp.get(), E(), llhProp.get(), nullptr);
-            kAccept<<<ceilDiv(E(), kAcceptThreads), kAcceptThreads, 0, stream>>>(a, ps, E(), llhProp.get(), cfg.seed,
+            kAccept<<<ceilDiv(E(), acceptThreads()), acceptThreads(), 0, stream>>>(a, ps, E(), llhProp.get(), cfg.seed,
                                                                                  cfg.chain_offset, stepRef(), metropolis, tr,
                                                                                  traceStep, acceptSlot);
         }
@@ -860,6 +869,9 @@ struct smcmc_engine {
     // 8-256 chains x 4M events and LOSES for one chain (gpurun_out/mid_ensemble.txt);
     // the launch-bound chain-local case is served by kStepsResident instead.
     static constexpr int kGraphMinSteps = 8;
+    // kAccept: one thread per chain decides, the warp then copies the rows of its chains that accepted.
+    // With few chains per SM the copies of 128-thread blocks leave most SMs idle: one warp per block then.
+    int acceptThreads() const { return E() < 2 * smCount * kAcceptThreads ? 32 : kAcceptThreads; }
     bool debugStep() const { return propKind == SMCMC_PROPOSAL_ADAPTIVE && (forcedPending || scanDim >= 0); }
     bool graphable() const {
         const char* g = std::getenv("SMCMC_GRAPH");

@@ -180,7 +180,9 @@ __device__ __forceinline__ void storeFilterChain(FilterChain* dst, int c, const 
 // the exposure ratio (the counts are applied by the renormalisation in kFake2Finish).
 __global__ void kFakePrepareChains(const double* __restrict__ x, int m, int dim,
                                    double exposure, FakeChainParams* out, FilterChain* fout,
-                                   int exactOnly, int variant) {
+                                   int exactOnly, int variant, uint32_t* zero = nullptr, int zeroWords = 0) {
+    // with few points the count table is small: cleared here instead of by a memset node of its own
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < zeroWords; k += gridDim.x * blockDim.x) zero[k] = 0u;
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= m) return;
     const double* p = x + (size_t)c * dim;
@@ -457,6 +459,11 @@ struct PairLaunch {
     int blockPoints;                 // points per block of the count table (countIndex); == pointStride: one block
     uint32_t* counts;                // [block][kFakeSlots][blockPoints]
     unsigned long long* stats;       // optional: [0] unsure pairs
+    // the events the tiles cannot hold (kFakePairsGeneric); kFakeStream evaluates them itself
+    const smcmc_event* irregular;
+    int64_t irregularCount;
+    const double* points;            // [numPoints][dim] the parameter points
+    int dim;
 };
 
 // Undecided pairs are not evaluated where they are found (one lane in FP64
@@ -788,6 +795,8 @@ kFakePairs(const __grid_constant__ PairLaunch L) {
 // event per evaluation, HBM-bound for E <= ~4 (SURVEY.md 8d "streaming regime").
 // The counts are the same integers kFakePairs produces.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ void fakePairGeneric(const smcmc_event& e, const double* __restrict__ p, int point,
+                                                uint32_t* counts, int blockPoints);
 constexpr int kStreamMaxChains = 16;
 constexpr int kStreamThreads = 256;
 constexpr int kStreamRows = 300;             // slots of the four weight classes
@@ -885,6 +894,15 @@ kFakeStream(const __grid_constant__ PairLaunch L) {
             }
         }
     }
+    // the few events outside the tiles (data-typed, non-finite ...): per-pair transcription of the
+    // reference formula, straight into the global table
+    {
+        const int64_t pairs = L.irregularCount * L.numPoints;
+        for (int64_t idx = (int64_t)blockIdx.x * kStreamThreads + threadIdx.x; idx < pairs; idx += (int64_t)gridDim.x * kStreamThreads) {
+            const int point = (int)(idx % L.numPoints);
+            fakePairGeneric(L.irregular[idx / L.numPoints], L.points + (size_t)point * L.dim, point, L.counts, L.blockPoints);
+        }
+    }
     __syncthreads();
     for (int k = threadIdx.x; k < L.numPoints * kStreamRows; k += kStreamThreads) {
         const uint32_t v = table[k];
@@ -936,14 +954,20 @@ __global__ void kFakeVerifyFilter(const PairLaunch L, unsigned long long* stats)
 // Straight transcription of the per-event formula for the events the fast
 // path cannot take (data-typed, negative separation, non-finite fields):
 // one thread per (point, event).
+__device__ __forceinline__ void fakePairGeneric(const smcmc_event& e, const double* __restrict__ p, int point,
+                                                uint32_t* counts, int blockPoints);
+
 __global__ void kFakePairsGeneric(const smcmc_event* __restrict__ ev, int64_t nev,
                                   const double* __restrict__ x, int m, int dim,
                                   uint32_t* counts, int blockPoints) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nev * (int64_t)m) return;
     int point = (int)(idx % m);
-    smcmc_event e = ev[idx / m];
-    const double* p = x + (size_t)point * dim;
+    fakePairGeneric(ev[idx / m], x + (size_t)point * dim, point, counts, blockPoints);
+}
+
+__device__ __forceinline__ void fakePairGeneric(const smcmc_event& e, const double* __restrict__ p, int point,
+                                                uint32_t* counts, int blockPoints) {
     double mass = e.Mass, sep = e.Separation;
     if (e.Type >= 0) {
         double nomLog = log(e.TrueMass);

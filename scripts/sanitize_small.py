@@ -44,4 +44,34 @@ eng.hmc_start(np.full(n, 0.5)); eng.hmc_step(40, 3); eng.sync()
 cov = eng.hmc_get("covariance")
 assert np.all(np.isfinite(cov))
 eng.close()
+del os.environ["SMCMC_HMC_DEFER"]
+# round 2 kernels: fused leap-frog stage + 3-stage DMMA pipeline (even and odd n, ragged tiles), pooled HMC
+# covariance (kHmcPooledFold / Trigger / Spectrum / Apply past the 32-step threshold)
+def spd(n, seed):
+    rng = np.random.default_rng(seed)
+    a = rng.normal(size=(n, n))
+    m = a @ a.T / n + np.diag(rng.uniform(0.5, 2.0, n))
+    return 0.5 * (m + m.T)
+for n, E in ((70, 66), (37, 9)):
+    eng = sm.Engine(sm.LLH_DUMMY, n, E, seed=6)
+    eng.set_error_matrix(spd(n, n))
+    eng.set_dummy_mode(b.DUMMY_TENSOR)
+    eng.hmc_set(b.HMC_USER_GRADIENT, 1)
+    eng.hmc_set(b.HMC_POOLED_COVARIANCE, 1)
+    eng.hmc_start(np.full(n, 0.5)); eng.hmc_step(36, 0); eng.sync()
+    assert eng.hmc_get("pooled_scalars")[7] >= 1
+    eng.close()
+# pooled Metropolis at n >= 64: tiled Gram statistics (kPoolGramDmma), CTA-wide factorisation, DMMA proposal
+eng = sm.Engine(sm.LLH_UNIT_GAUSS, 130, 70, seed=5)
+eng.prop_set(b.PROP_POOLED_EVERY, 4); eng.prop_set(b.PROP_POOLED_TENSOR, 1)
+eng.start(np.random.default_rng(1).normal(0, 1, (70, 130))); eng.step(9); eng.sync(); eng.close()
+# debugging modes of the proposal, event-sharded layout of the count table is covered by the 2-GPU test
+eng = sm.Engine(sm.LLH_UNIT_GAUSS, 5, 37, seed=2)
+eng.start(np.zeros(5)); eng.force_step(np.full(5, 0.1)); eng.step(3, 2); eng.set_scan(2); eng.step(4); eng.set_scan(-1); eng.step(3); eng.sync(); eng.close()
+# streaming event likelihood with irregular records folded into kFakeStream
+ev2 = np.concatenate([events[:2000], events[:3]])
+ev2["Type"][-3:] = -1
+eng = sm.Engine(sm.LLH_FAKE, 9, 2, seed=8)
+eng.set_fake_events(ev2); eng.set_fake_data(data, 0.1)
+eng.start(np.random.default_rng(1).uniform(-1, 1, (2, 9))); eng.step(4); eng.sync(); eng.close()
 print("sanitize_small ok")
