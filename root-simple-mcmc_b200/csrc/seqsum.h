@@ -63,6 +63,17 @@ SMCMC_HD double smcmc_seq_add(double s, double w, uint32_t n) {
                     n -= 2 + m;
                     continue;
                 }
+                /* within a few steps of the top of the binade: plain additions (the
+                 * reference's own operation) up to the crossing, without the set-up above */
+                s = s2;
+                n -= 2;
+                while (n > 0 && smcmc_exponent_bits(s) == e0) {
+                    double t = SMCMC_ADD(s, w);
+                    if (t == s) return s;
+                    s = t;
+                    --n;
+                }
+                continue;
             }
         }
         s = s2;

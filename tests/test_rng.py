@@ -132,6 +132,11 @@ def test_sequential_sum_emulation_is_exact(kat):
         s = 0.0 if t % 2 else float(rng.uniform(0, 100))
         n = int(rng.integers(0, 100000))
         assert kat.smcmc_kat_seq_add(s, w, n) == kat.smcmc_kat_seq_add_naive(s, w, n)
+    # event counts of the size of the streaming benchmark (16.8 M events in a bin's class): many binades crossed
+    for w in (0.3141592653589793, 0.0958270088772365, 1.0, 0.75, 1e-3, 0.05 * 2.0 ** -3, 37.5):
+        for n in (16777216, 9999999):
+            assert kat.smcmc_kat_seq_add(0.0, w, n) == kat.smcmc_kat_seq_add_naive(0.0, w, n), (w, n)
+            assert kat.smcmc_kat_seq_add(123.456, w, n) == kat.smcmc_kat_seq_add_naive(123.456, w, n), (w, n)
     for s, w, n in [(0.0, 0.0, 10), (1.0, 1e-30, 1000), (0.0, 0.1, 0), (0.0, 0.1, 1), (0.0, 0.1, 3),
                     (0.0, float("inf"), 5), (0.0, -0.5, 7), (3.0, 0.09582700887723655, 1000020)]:
         a, b = kat.smcmc_kat_seq_add(s, w, n), kat.smcmc_kat_seq_add_naive(s, w, n)
