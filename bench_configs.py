@@ -284,7 +284,10 @@ def gpu_c4(args, emit, ctx):
         return e
     eng = make()
     eng.hmc_start(np.ones(n))
-    warm = max(args.warmup, 3)
+    # past the first UpdateErrorMatrix of the pooled estimate (step 32): the step size and the
+    # trajectory length of the timed steps are the tuned ones, as in a long run (SimpleHMC.C: 100 + n
+    # burn-in steps before the 1000 it keeps)
+    warm = max(args.warmup, 40)
     eng.hmc_step(warm)
     eng.sync()
     s0 = eng.hmc_scalars()
@@ -328,6 +331,7 @@ def gpu_c4(args, emit, ctx):
                    "l2": "inputs larger than L2: 16384 x 500 points, momenta and gradients (~0.4 GB) plus the "
                          "per-chain covariance accumulators stream through every step"},
         "likelihood_evals_per_s": world * evals / (ms * 1e-3),
+        "mean_trajectory_length": float(np.abs(s1["leapfrog"]).mean()), "acceptance": float(s1["acceptance"].mean()),
         "roofline": {"kernel": "smcmc::kDummyContractDmma (X . Error^T, mma.sync.m8n8k4.f64) over the whole HMC step",
                      "bound": "tensor", "achieved": flops, "peak": dmma, "unit": "TFLOP/s", "frac": flops / dmma,
                      "peak_source": "measured in this run: register-resident DMMA chains on every SM (FP64 tensor "

@@ -1080,11 +1080,18 @@ kFakeFinish(const uint32_t* __restrict__ counts, int pointStride, int m,
         __syncthreads();
         if (!lastArriver) return;
         __threadfence();
+        // the terms come back through shared memory, every thread fetching a few in parallel: the
+        // ordered sum below then waits for LDS, not for 150 round trips to L2 one after the other
+        for (int k = threadIdx.x; k < 150 * kFinishPoints; k += blockDim.x) {
+            const int hb = k / kFinishPoints, pp = k - hb * kFinishPoints;
+            const int pt = blockIdx.x * kFinishPoints + pp;
+            if (pt < m) term[hb][pp] = __ldcg(termScratch + (size_t)pt * 150 + hb);
+        }
+        __syncthreads();
         if (warp == 0 && sub == 0 && live && llhOut) {
-            const double* t = termScratch + (size_t)point * 150;
             double s = 0.0;
 #pragma unroll 6
-            for (int hb = 0; hb < 150; ++hb) s = __dadd_rn(s, __ldcg(t + hb));
+            for (int hb = 0; hb < 150; ++hb) s = __dadd_rn(s, term[hb][p]);
             llhOut[point] = s;
         }
         return;

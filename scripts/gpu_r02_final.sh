@@ -19,14 +19,17 @@ timeout 300 python scripts/hmc_ab.py > $O/${T}_hmc_ab.txt 2>&1; cat $O/${T}_hmc_
 timeout 300 python scripts/pooled_bench.py > $O/${T}_pooled_large.txt 2>&1; cat $O/${T}_pooled_large.txt
 timeout 300 python scripts/configs_bench.py stream > $O/${T}_stream.jsonl 2>&1; cut -c1-200 $O/${T}_stream.jsonl
 NCU="ncu --set full --import-source on --clock-control none --launch-count 1 -f"
-timeout 300 $NCU -k regex:kFakePairs --launch-skip 3 -o $O/${T}_kFakePairs python scripts/prof_pairs.py > $O/${T}_ncu_pairs.log 2>&1; tail -1 $O/${T}_ncu_pairs.log
+# gpurun brings back at most 64 MiB: every report is exported to its raw CSV page on the box and
+# removed, except the headline kernel's
+keep() { ncu -i $O/${T}_$1.ncu-rep --page raw --csv > $O/${T}_$1.raw.csv 2>/dev/null; [ "$1" = kFakePairs ] || rm -f $O/${T}_$1.ncu-rep; }
+timeout 300 $NCU -k regex:kFakePairs --launch-skip 3 -o $O/${T}_kFakePairs python scripts/prof_pairs.py > $O/${T}_ncu_pairs.log 2>&1; tail -1 $O/${T}_ncu_pairs.log; keep kFakePairs
 export HMC_STEPS=4
 for k in kHmcLeapDmma kDummyContractDmma kPoolGramDmma; do
-  timeout 400 $NCU -k regex:$k --launch-skip 3 -o $O/${T}_$k python scripts/prof_hmc.py > $O/${T}_ncu_$k.log 2>&1; tail -1 $O/${T}_ncu_$k.log
+  timeout 400 $NCU -k regex:$k --launch-skip 3 -o $O/${T}_$k python scripts/prof_hmc.py > $O/${T}_ncu_$k.log 2>&1; tail -1 $O/${T}_ncu_$k.log; keep $k
 done
-C3_STEPS=12 timeout 300 $NCU -k regex:kProposeStaged --launch-skip 6 -o $O/${T}_kProposeStaged python scripts/prof_c3.py > $O/${T}_ncu_staged.log 2>&1; tail -1 $O/${T}_ncu_staged.log
-C3_POOLED=16 C3_STEPS=12 timeout 300 $NCU -k regex:kProposePooledTile --launch-skip 6 -o $O/${T}_kProposePooledTile python scripts/prof_c3.py > $O/${T}_ncu_pooledtile.log 2>&1; tail -1 $O/${T}_ncu_pooledtile.log
-timeout 300 $NCU -k regex:kFakeStream --launch-skip 2 -o $O/${T}_kFakeStream python scripts/prof_stream.py > $O/${T}_ncu_stream.log 2>&1; tail -1 $O/${T}_ncu_stream.log
+C3_STEPS=12 timeout 300 $NCU -k regex:kProposeStaged --launch-skip 6 -o $O/${T}_kProposeStaged python scripts/prof_c3.py > $O/${T}_ncu_staged.log 2>&1; tail -1 $O/${T}_ncu_staged.log; keep kProposeStaged
+C3_POOLED=16 C3_STEPS=12 timeout 300 $NCU -k regex:kProposePooledTile --launch-skip 6 -o $O/${T}_kProposePooledTile python scripts/prof_c3.py > $O/${T}_ncu_pooledtile.log 2>&1; tail -1 $O/${T}_ncu_pooledtile.log; keep kProposePooledTile
+timeout 300 $NCU -k regex:kFakeStream --launch-skip 2 -o $O/${T}_kFakeStream python scripts/prof_stream.py > $O/${T}_ncu_stream.log 2>&1; tail -1 $O/${T}_ncu_stream.log; keep kFakeStream
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/${T}_launches_stream.csv python scripts/prof_stream.py > /dev/null 2>&1
 python scripts/summarize_launches.py $O/${T}_launches_stream.csv | grep -v "cub::\|Gather\|SortKeys\|CountClasses\|PadEvents\|InitState\|StoreStart" | head -10
 C3_POOLED=16 C3_STEPS=20 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/${T}_launches_c3_pooled.csv python scripts/prof_c3.py > /dev/null 2>&1
