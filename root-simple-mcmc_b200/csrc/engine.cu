@@ -297,7 +297,9 @@ struct smcmc_engine {
         } else if (n() >= 64 && !std::getenv("SMCMC_POOL_ACC_DIRECT")) {
             // large dimension: shared-memory tiled Y^T Y (kPoolGramDmma)
             const int nb = ceilDiv(n() + 1, kGramB), pairs = nb * (nb + 1) / 2;
-            int slices = std::max(1, std::min(ceilDiv(E(), 4 * kGramK), ceilDiv(3 * smCount, pairs)));
+            // chain slices so that the grid is ONE wave of 3 CTAs per SM (13 slices x 36 tile pairs = 468 CTAs
+            // on 444 slots ran as two waves: 0.26 ms instead of 0.14 at n = 500)
+            int slices = std::max(1, std::min(ceilDiv(E(), 4 * kGramK), (3 * smCount) / pairs));
             slices = std::max(slices, ceilDiv(E(), 4096));                 // the liveness flags of a slice sit in shared memory
             const int perCta = ceilDiv(ceilDiv(E(), slices), kGramK) * kGramK;
             slices = ceilDiv(E(), perCta);
@@ -577,10 +579,6 @@ struct smcmc_engine {
         L.blockPoints = fakeBlockPoints > 0 ? fakeBlockPoints : stride;
         L.counts = fakeCounts.get();
         L.stats = collectStats ? fakeStats.get() : nullptr;
-        L.irregular = fakeIrregular.get();
-        L.irregularCount = fakeIrregularCount;
-        L.points = nullptr;
-        L.dim = n();
         return L;
     }
     bool collectStats = false;
@@ -622,11 +620,11 @@ struct smcmc_engine {
                                                                 fakeFilterChains.get(), exactOnly ? 1 : 0,
                                                                 cfg.likelihood == SMCMC_LLH_FAKE2 ? 1 : 0,
                                                                 streaming ? fakeCounts.get() : nullptr,
-                                                                streaming ? kFakeSlots * stride : 0);
+                                                                streaming ? kFakeSlots * stride : 0,
+                                                                fakeIrregular.get(), streaming ? fakeIrregularCount : 0, stride);
         launched();
 
         PairLaunch L = pairLaunch(m, stride);
-        L.points = xDev;
         const int chunks = L.chunkBase[kFakeClasses];
         if (chunks > 0) {
             const int pointTiles = ceilDiv(m, kPairThreads);
@@ -652,7 +650,7 @@ struct smcmc_engine {
             }
             ++pairLaunches;
         }
-        if (fakeIrregularCount > 0 && !(streaming && chunks > 0)) {       // (kFakeStream takes them along)
+        if (fakeIrregularCount > 0 && !streaming) {                       // (few points: kFakePrepareChains took them along)
             long long pairs = (long long)fakeIrregularCount * m;
             kFakePairsGeneric<<<ceilDiv(pairs, 256), 256, 0, stream>>>(fakeIrregular.get(), fakeIrregularCount,
                                                                        xDev, m, n(), fakeCounts.get(), L.blockPoints);

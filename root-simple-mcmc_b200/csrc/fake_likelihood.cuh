@@ -178,11 +178,26 @@ __device__ __forceinline__ void storeFilterChain(FilterChain* dst, int c, const 
 // variant 0: example/SystematicCorrection.H; variant 1: example2/SystematicCorrection.H
 // (:75-117), whose EventWeight has neither the exp(p/10) event-count factors nor
 // the exposure ratio (the counts are applied by the renormalisation in kFake2Finish).
+__device__ __forceinline__ void fakePairGeneric(const smcmc_event& e, const double* __restrict__ p, int point,
+                                                uint32_t* counts, int blockPoints);
 __global__ void kFakePrepareChains(const double* __restrict__ x, int m, int dim,
                                    double exposure, FakeChainParams* out, FilterChain* fout,
-                                   int exactOnly, int variant, uint32_t* zero = nullptr, int zeroWords = 0) {
-    // with few points the count table is small: cleared here instead of by a memset node of its own
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < zeroWords; k += gridDim.x * blockDim.x) zero[k] = 0u;
+                                   int exactOnly, int variant, uint32_t* zero = nullptr, int zeroWords = 0,
+                                   const smcmc_event* __restrict__ irregular = nullptr, int64_t irregularCount = 0,
+                                   int blockPoints = 0) {
+    // Few points (the streaming regime, ONE block): the small count table is cleared here instead of
+    // by a memset node of its own, and the handful of events the tiles cannot hold (data-typed,
+    // non-finite ...) are counted by the threads that have no chain to prepare -- the per-pair
+    // transcription of the reference formula, concurrent with the chain constants below.
+    if (zero) {
+        for (int k = threadIdx.x; k < zeroWords; k += blockDim.x) zero[k] = 0u;
+        __syncthreads();
+        const int64_t pairs = irregularCount * m;
+        for (int64_t idx = (int64_t)blockDim.x - 1 - threadIdx.x; idx < pairs; idx += blockDim.x) {
+            const int point = (int)(idx % m);
+            fakePairGeneric(irregular[idx / m], x + (size_t)point * dim, point, zero, blockPoints);
+        }
+    }
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= m) return;
     const double* p = x + (size_t)c * dim;
@@ -459,11 +474,6 @@ struct PairLaunch {
     int blockPoints;                 // points per block of the count table (countIndex); == pointStride: one block
     uint32_t* counts;                // [block][kFakeSlots][blockPoints]
     unsigned long long* stats;       // optional: [0] unsure pairs
-    // the events the tiles cannot hold (kFakePairsGeneric); kFakeStream evaluates them itself
-    const smcmc_event* irregular;
-    int64_t irregularCount;
-    const double* points;            // [numPoints][dim] the parameter points
-    int dim;
 };
 
 // Undecided pairs are not evaluated where they are found (one lane in FP64
@@ -892,15 +902,6 @@ kFakeStream(const __grid_constant__ PairLaunch L) {
                 if (t + warps < tiles) nxt = streamLoad<false>(L, firstTile + t + warps, lane);
                 streamTile<false>(L, cls, firstTile + t, lane, cur, fcs, cps, table);
             }
-        }
-    }
-    // the few events outside the tiles (data-typed, non-finite ...): per-pair transcription of the
-    // reference formula, straight into the global table
-    {
-        const int64_t pairs = L.irregularCount * L.numPoints;
-        for (int64_t idx = (int64_t)blockIdx.x * kStreamThreads + threadIdx.x; idx < pairs; idx += (int64_t)gridDim.x * kStreamThreads) {
-            const int point = (int)(idx % L.numPoints);
-            fakePairGeneric(L.irregular[idx / L.numPoints], L.points + (size_t)point * L.dim, point, L.counts, L.blockPoints);
         }
     }
     __syncthreads();
