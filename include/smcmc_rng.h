@@ -269,13 +269,25 @@ SMCMC_HD void smcmc_normal_pair(uint64_t seed, uint32_t chain, uint32_t step,
     smcmc_normal_pair_from_bits(smcmc_normal_pair_bits(seed, chain, step, pair, stream), 3, z0, z1);
 }
 
-/* Gaus(0,1) of draw (chain, step, slot): one branch of its pair. */
+/* Gaus(0,1) of draw (chain, step, slot): one branch of its pair -- the cosine branch for an
+ * even slot, the sine branch for an odd one.  Same operations as the pair routine; written out
+ * so that a thread evaluates exactly one of the two polynomial kernels. */
 SMCMC_HD double smcmc_normal(uint64_t seed, uint32_t chain, uint32_t step,
                              uint32_t slot, uint32_t stream) {
-    double z0 = 0.0, z1 = 0.0;
-    smcmc_normal_pair_from_bits(smcmc_normal_pair_bits(seed, chain, step, slot >> 1, stream),
-                                (slot & 1u) ? 2 : 1, &z0, &z1);
-    return (slot & 1u) ? z1 : z0;
+    const double quarter_pi = 7.85398163397448278999e-01;
+    smcmc_u32x4 b = smcmc_normal_pair_bits(seed, chain, step, slot >> 1, stream);
+    double rad = smcmc_normal_pair_radius(b);
+    double u2 = smcmc_bits_to_open01(b.v[2], b.v[3]);
+    double t = SMCMC_MUL(u2, 8.0);
+    int oct = (int)t;
+    double r = SMCMC_SUB(t, (double)oct);
+    if (oct & 1) r = SMCMC_SUB(1.0, r);
+    double a = SMCMC_MUL(r, quarter_pi);
+    const int odd = (int)(slot & 1u);
+    const int swap = ((oct + 1) >> 1) & 1;
+    double v = (swap ^ odd) ? smcmc_det_ksin(a) : smcmc_det_kcos(a);
+    if (odd ? (oct >= 4) : (oct >= 2 && oct <= 5)) v = -v;
+    return SMCMC_MUL(rad, v);
 }
 
 #endif

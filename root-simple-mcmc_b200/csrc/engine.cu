@@ -127,7 +127,6 @@ struct smcmc_engine {
     DeviceBuffer<double> fakeTerms;     // kFakeFinish with few points: the 150 bin terms per point
     DeviceBuffer<unsigned int> fakeTickets;
     bool staged = false;                // kProposeStaged (one CTA per chain) instead of kPropose
-    int stagedDraw = 1;                 // its DRAW variant (1 measured fastest on C3, 0.536 vs 0.540 / 0.550 ms per step)
     bool resident = false;              // kStepsResident fits (whole steps out of shared memory)
     int residentPerSm = 0;              // its CTAs per SM
     int64_t residentLaunches = 0;
@@ -828,8 +827,7 @@ struct smcmc_engine {
             }
             kVaatPropose<<<ceilDiv(E(), 128), 128, 0, stream>>>(a, vaatArrays(), ps, E(), cfg.seed, cfg.chain_offset, stepRef());
         } else if (staged)
-            (stagedDraw == 1 ? kProposeStaged<1> : stagedDraw == 2 ? kProposeStaged<2> : kProposeStaged<0>)
-                <<<E(), kStagedThreads, stagedChainBytes(n(), covStride, upkStride), stream>>>(
+            kProposeStaged<<<E(), kStagedThreads, stagedChainBytes(n(), covStride, upkStride), stream>>>(
                 a, ps, E(), cfg.seed, cfg.chain_offset, stepRef());
         else
             kPropose<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a, ps, E(), cfg.seed, cfg.chain_offset, stepRef());
@@ -1092,10 +1090,7 @@ int smcmc_create(const smcmc_config* cfg, smcmc_engine** out) {
             const size_t cb = stagedChainBytes((int)n, e->covStride, e->upkStride);
             if ((227 * 1024) / (cb + 1024) >= 4 && n < 8192 && !std::getenv("SMCMC_PROPOSE_GENERIC")) {
                 e->staged = true;
-                if (const char* d = std::getenv("SMCMC_STAGED_DRAW")) e->stagedDraw = atoi(d);
-                CUDA_CHECK(cudaFuncSetAttribute(kProposeStaged<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cb));
-                CUDA_CHECK(cudaFuncSetAttribute(kProposeStaged<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cb));
-                CUDA_CHECK(cudaFuncSetAttribute(kProposeStaged<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cb));
+                CUDA_CHECK(cudaFuncSetAttribute(kProposeStaged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cb));
             }
             // kStepsResident (whole steps out of shared memory) when one chain fits an SM
             const size_t rb = residentChainBytes((int)n, e->covStride, e->upkStride);

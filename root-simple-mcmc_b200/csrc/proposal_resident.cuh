@@ -77,11 +77,17 @@ __device__ __forceinline__ double residentLikelihood(int kind, const double* x, 
 // point for the others
 __device__ __forceinline__ void residentDraw(const PropSettings& ps, double* zr, int n, uint64_t seed, uint32_t gchain,
                                              uint32_t step, int t, int workers) {
-    for (int pr = t; 2 * pr < n; pr += workers) {
-        double v0, v1;
-        drawPair(ps, seed, gchain, step, pr, v0, v1);
-        zr[2 * pr] = v0;
-        if (2 * pr + 1 < n) zr[2 * pr + 1] = v1;
+    // one draw per thread: the workers' draws of the next step run beside warp 0's likelihood, and for
+    // a short chain-local likelihood their latency is the critical path (a Box-Muller pair per thread is
+    // 1.5 x the latency of one branch)
+    for (int i = t; i < n; i += workers) {
+        if (ps.anyUniform && ps.type[i] == 1) {
+            const double uu = smcmc_uniform(seed, gchain, step, (uint32_t)i, SMCMC_STREAM_STEP);
+            zr[i] = __dadd_rn(ps.param1[i], __dmul_rn(__dsub_rn(ps.param2[i], ps.param1[i]), uu));
+        } else {
+            const double g = smcmc_normal(seed, gchain, step, (uint32_t)i, SMCMC_STREAM_STEP);
+            zr[i] = __dadd_rn(0.0, __dmul_rn(1.0, g));              // TRandom::Gaus(0,1)
+        }
     }
 }
 
