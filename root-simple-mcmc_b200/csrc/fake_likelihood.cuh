@@ -77,6 +77,9 @@ constexpr int kPairCounterRows = 100;
 #ifndef SMCMC_PAIR_CTAS
 #define SMCMC_PAIR_CTAS 4
 #endif
+#ifndef SMCMC_PAIR_EXPERIMENT
+#define SMCMC_PAIR_EXPERIMENT 0
+#endif
 #ifndef SMCMC_PAIR_UNROLL
 #define SMCMC_PAIR_UNROLL 2
 #endif
@@ -280,16 +283,30 @@ __device__ __forceinline__ int exactDecide(const PreparedEvent& ev, const FakeCh
 // exactDecide.  The filter therefore never changes a count; it only decides
 // which pairs need FP64.
 //
+// Arithmetic (log2 domain; K = 2^c2 with c2 = scale*log2(e) - log2(10) is a per-chain constant
+// that never meets the per-pair exponent: it multiplies the error-bound factors instead):
+//   x2 = ls*scl2;  t = d*ex2(x2);  z = fma(t, w2, nl2);  q' = ex2(z);      q = K q'
+//   A = fma(|t|, aT, a0) = K(1+m),  B = 2K - A = K(1-m)     (m = m0 + slopeT|t|, the bound below)
+//   hi = RZ(fma(q', A, 1.5*2^23)),  lo = RZ(fma(q', B, 1.5*2^23))
+// The products q'A and q'B are exact inside the FMAs and the round-toward-zero sum with 1.5*2^23
+// is their integer part on the float grid: hi = floor(q(1+m)), lo = floor(q(1-m)), one instruction
+// each, no second rounding.
+//
 // Error bound (u = 2^-24; inputs are correctly rounded to FP32):
 //   x2 = ls*scl2             rel. error <= 3u
 //   skew = ex2.approx(x2)    rel. error <= 4u + ln2*3u|x2|          (2 ulp unit)
 //   t = d*skew               rel. error <= (6 + 2.08|x2|)u
-//   z = t*w2 + nl2 + c2      abs. error <= u[(9+2.08|x2|)|t w2| + 4|nl2| + 4|c2|]
-//   q = ex2.approx(z)        rel. error <= 4u + ln2*abs.err(z)
+//   z = fma(t, w2, nl2)      abs. error <= u[(8+2.08|x2|)|t w2| + 2|nl2|]
+//   q' = ex2.approx(z)       rel. error <= 4u + ln2*abs.err(z)
+//   K, A as floats           rel. error <= u/2 (K), u (A: one FMA rounding on [K, 2K));
+//                            B = 2K - A is exact (Sterbenz) while m <= 3
 // |x2| <= 16 holds for every pair because |scl2| = |0.3 erf(.) log2 e| <= 0.4329
 // and events with |logSigma| > 36 are kept out of the fast path at upload;
 // |nl2| <= 16 is checked per event at upload as well.  With those guards the
-// bound is  <= u[48.4 + 2.78|c2| + 30.5|t w2|];  the code uses twice that.
+// bound is  <= u[48.4 + 30.5|t w2|] (the c2 terms of the round-1 formula went with the
+// addition); the code keeps m0 = 2u(48.4 + 2.78|c2|) and slopeT = 2u 30.5|w2|: more than twice it.
+// Chains whose constants leave the range this analysis covers (|c2| > 24, |w2| > 2^24, anything
+// non-finite) and SMCMC_FAKE_EXACT carry force = 1: every pair of theirs goes to FP64.
 //
 // Data layout.  Events of a class are stored in TILES of 128, structure of
 // arrays inside a tile (FilterTile, 2 KB, one TMA bulk copy), and every class
@@ -310,12 +327,13 @@ static_assert(sizeof(FilterTile) == 16 * kPairTile, "FilterTile is 16 bytes per 
 struct __align__(16) FilterChain {
     float scl2;      // skewc * log2(e)
     float w2;        // width * log2(e)
-    float c2;        // scale * log2(e) - log2(10)
-    float m0;        // relative error bound of q: constant part ...
-    float slopeT;    // ... plus slopeT * |d*skew|
+    float a0;        // K (1 + m0),  K = 2^(scale*log2(e) - log2(10)), m0 = constant part of the error bound of q
+    float aT;        // K slopeT: the bound grows by slopeT * |d*skew|
+    float twoK;      // 2 K
     float thr[2];    // 100 / separation scale: signal, background
     float thrEps[2]; // error bound of the comparison  sep <> thr
-    float pad_[3];
+    uint32_t force;  // 1: the filter is not used for this chain (every pair in FP64)
+    float pad_[2];
 };
 static_assert(sizeof(FilterChain) == 48, "FilterChain is 48 bytes");
 
@@ -362,18 +380,31 @@ __device__ __forceinline__ void storeFilterChain(FilterChain* dst, int c, const 
     const double u = 5.9604645e-8;
     FilterChain f;
     f.scl2 = __double2float_rn(cp.skewc * log2e);
-    f.w2 = __double2float_rn(cp.width * log2e);
+    const double w2 = cp.width * log2e;
+    f.w2 = __double2float_rn(w2);
     const double c2 = cp.scale * log2e - log2ten;
-    f.c2 = __double2float_rn(c2);
-    f.m0 = __double2float_ru(2.0 * u * (48.4 + 2.78 * fabs(c2)));
-    f.slopeT = __double2float_ru(2.0 * u * 30.5 * fabs(cp.width * log2e));
-    if (exactOnly) f.m0 = __int_as_float(0x7f800000);
+    const double K = exp2(c2);
+    const double m0 = 2.0 * u * (48.4 + 2.78 * fabs(c2));
+    const double slopeT = 2.0 * u * 30.5 * fabs(w2);
+    f.a0 = __double2float_ru(K * (1.0 + m0));
+    f.aT = __double2float_ru(K * slopeT);
+    f.twoK = __double2float_rn(2.0 * K);
+    const bool covered = isfinite(cp.skewc) && fabs(w2) <= 16777216.0 && fabs(c2) <= 24.0;   // false for NaN
+    f.force = (exactOnly || !covered) ? 1u : 0u;
+    if (f.force) {
+        // lo != hi (or NaN) for every pair: the kernels that decide pair by pair (kFakeStream,
+        // kFakeVerifyFilter) need no flag
+        f.a0 = __int_as_float(0x7f800000);
+        f.aT = 0.f;
+        f.twoK = 1.f;
+        if (!covered) f.scl2 = f.w2 = 0.f;
+    }
     for (int k = 0; k < 2; ++k) {
         const double thr = 100.0 / cp.sepScale[k];
         f.thr[k] = __double2float_rn(thr);
         f.thrEps[k] = __double2float_ru(8.0 * u * fabs(thr));
     }
-    f.pad_[0] = f.pad_[1] = f.pad_[2] = 0.f;
+    f.pad_[0] = f.pad_[1] = 0.f;
     dst[c] = f;
 }
 
@@ -402,13 +433,14 @@ __device__ __forceinline__ FilterPair filterCore2(float2 ls, float2 d, float2 nl
                                                   const FilterChain& fc, float thr) {
     const float2 x2 = __fmul2_rn(ls, make_float2(fc.scl2, fc.scl2));
     const float2 t = __fmul2_rn(d, make_float2(fastEx2(x2.x), fastEx2(x2.y)));
-    const float2 z = __fadd2_rn(__ffma2_rn(t, make_float2(fc.w2, fc.w2), nl2), make_float2(fc.c2, fc.c2));
-    const float2 q = make_float2(fastEx2(z.x), fastEx2(z.y));
-    const float2 m = make_float2(fmaf(fabsf(t.x), fc.slopeT, fc.m0), fmaf(fabsf(t.y), fc.slopeT, fc.m0));
+    const float2 z = __ffma2_rn(t, make_float2(fc.w2, fc.w2), nl2);
+    const float2 q = make_float2(fastEx2(z.x), fastEx2(z.y));                       // q' = q / K
+    const float2 a = make_float2(fmaf(fabsf(t.x), fc.aT, fc.a0), fmaf(fabsf(t.y), fc.aT, fc.a0));
+    const float2 b = __fadd2_rn(make_float2(fc.twoK, fc.twoK), make_float2(-a.x, -a.y));
     const float2 magic = make_float2(12582912.0f, 12582912.0f);
     FilterPair r;
-    r.hi = __fadd2_rz(__ffma2_rn(q, m, q), magic);
-    r.lo = __fadd2_rz(__ffma2_rn(q, make_float2(-m.x, -m.y), q), magic);
+    r.hi = __ffma2_rz(q, a, magic);
+    r.lo = __ffma2_rz(q, b, magic);
     r.ds = TAGGED ? make_float2(0.f, 0.f) : __fadd2_rn(sep, make_float2(-thr, -thr));
     return r;
 }
@@ -434,14 +466,25 @@ __device__ __forceinline__ FilterDecision filterDecide(float lo, float hi, float
     return r;
 }
 
-// Counters.  A CTA holds 100 rows x 256 chains of 16-bit counters, packed two
+// Counters.  A CTA holds 101 rows x 256 chains of 16-bit counters, packed two
 // per 32-bit word (chains c and c+128 -> word c), and EVERY update is a shared-memory
 // atomic add without a return value (RED): one instruction instead of a
 // load/add/store chain, and the deferred FP64 pass may update any chain's
 // column.  16 bits cannot overflow within a chunk (kPairChunk < 65536), so the
 // low half never carries into the high half.
+//
+// Row layout: bins of the Close histogram (tagged classes: DecayTag) in rows 0..49 ascending,
+// row 50 takes the events that are cut (mass >= 500), the Separated histogram in rows 100..51
+// DESCENDING (bin b -> row 100 - b).  Both histograms reach the cut row by clamping the bin
+// at 50: the address of an event is  min(bits, 0x4b400032) * (+-512) + constant,
+// with no comparison, no select and no branch.
 constexpr unsigned kPairRowBytes = (kPairThreads / 2) * sizeof(uint32_t);
 static_assert(kPairRowBytes == 512, "row stride of the counter table");
+constexpr int kPairCutRow = kFilterCutRow;
+constexpr int kPairFarRow0 = 2 * kFilterCutRow;                  // row of Separated bin 0
+__host__ __device__ constexpr int pairRowOfBin(int bin) {         // bin: 0..49 Close, 50..99 Separated
+    return bin < kFilterCutRow ? bin : kPairFarRow0 - (bin - kFilterCutRow);
+}
 
 __device__ __forceinline__ void redShared(unsigned addr, unsigned value) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(value) : "memory");
@@ -477,23 +520,26 @@ struct PairLaunch {
 };
 
 // Undecided pairs are not evaluated where they are found (one lane in FP64
-// while 31 wait): they are appended to a small shared-memory queue and the
-// whole CTA works the queue off, one pair per thread, every kPairDrainEvery
-// tiles (and at the end of the chunk); pairs that do not fit are evaluated in place.
-constexpr int kPairQueueCap = 240;
-constexpr int kPairDrainEvery = 8;       // tiles between two passes over the queue
+// while 31 wait): a lane appends them to its WARP's queue in shared memory, and the warp works
+// its queue off by itself, one pair per lane, at the end of a tile once kPairDrainAt pairs
+// have gathered (and at the end of the chunk).  No CTA-wide barrier is involved; pairs that do not
+// fit are evaluated in place.
+constexpr int kPairWarps = kPairThreads / 32;
+constexpr int kPairQueueCap = 30;        // per warp
+constexpr int kPairDrainAt = 16;
 struct PairQueue {
-    unsigned count;
-    unsigned done[2];                // warps that have finished the tile in each buffer
+    unsigned done[2];                    // warps that have finished the tile in each buffer
+    unsigned unsure;                     // pairs that went to FP64 (statistics)
+    int cls;                             // what exactCount needs, for the lanes that find their queue full
+    const PreparedEvent* chunkEvents;
+    const FakeChainParams* chains;       // of the CTA's first chain
+    unsigned countersAddr;
     unsigned pad_;
-    unsigned entry[kPairQueueCap];   // (event index in chunk) << 8 | chain index in CTA
+    unsigned count[kPairWarps];
+    unsigned entry[kPairWarps][kPairQueueCap];   // (event index in chunk) << 8 | chain index in CTA
 };
 
 constexpr size_t kPairSmemTiles = 2 * sizeof(FilterTile);
-// one more row than the histograms need: the row that takes the updates of pairs
-// that are not counted (cut or undecided), so that the update itself is
-// unconditional (no branch around the atomic)
-constexpr int kPairDummyRow = kPairCounterRows;
 constexpr size_t kPairSmemCounters = (size_t)(kPairCounterRows + 1) * kPairRowBytes;
 constexpr size_t kPairSmemBytes = kPairSmemTiles + 64 + kPairSmemCounters + sizeof(PairQueue);
 static_assert(kPairCtasPerSm * (kPairSmemBytes + 1024) <= 232448, "resident CTAs per SM");
@@ -501,119 +547,156 @@ static_assert(kPairCtasPerSm * (kPairSmemBytes + 1024) <= 232448, "resident CTAs
 // FP64 evaluation of one undecided pair and its count.
 __device__ __noinline__ void exactCount(const PreparedEvent* ev, const FakeChainParams* cp, int cls,
                                         unsigned countersAddr, int chain) {
-    const int row = exactDecide(*ev, *cp, cls);
-    if (row >= 0)
-        redShared(countersAddr + (unsigned)row * kPairRowBytes + (unsigned)(chain & (kPairThreads / 2 - 1)) * 4u,
+    const int bin = exactDecide(*ev, *cp, cls);
+    if (bin >= 0)
+        redShared(countersAddr + (unsigned)pairRowOfBin(bin) * kPairRowBytes + (unsigned)(chain & (kPairThreads / 2 - 1)) * 4u,
                   (chain >= kPairThreads / 2) ? 65536u : 1u);
 }
 
-// Decide and count one event: one unconditional shared-memory RED whose target
-// is the event's counter when the decision is sure and in range, and the
-// thread's dummy row otherwise; an undecided event sets the group's bit in
-// `mask`.  Written in PTX so that the sequence stays
-//   FSETP.EQ  [FSETP.GT.AND]  ISETP.LT.AND  SEL  ATOMS  @!p LOP3
-// (the compiler otherwise splits the select in two and re-evaluates compares).
-//   lo, hi, ds : from filterCore2;  rowAdj = (address of the thread's word in
-//   row 0) - 0x4b400000 * row bytes, so that bits(lo) * row bytes + rowAdj is
-//   the counter of floor(q).
-template <bool TAGGED>
-__device__ __forceinline__ void countOne(float lo, float hi, float ds, float thrEps, unsigned rowAdj,
-                                         unsigned dummyAddr, unsigned addValue, unsigned& mask, unsigned groupBit) {
-    const unsigned bits = __float_as_uint(lo);
-    unsigned addr = bits * kPairRowBytes + rowAdj;
-    if (TAGGED) {
-        asm volatile(
-            "{\n.reg .pred p, q;\n.reg .u32 a;\n"
-            "setp.eq.f32 p, %1, %2;\n"
-            "setp.lt.and.u32 q, %3, %4, p;\n"
-            "selp.u32 a, %5, %6, q;\n"
-            "red.shared.add.u32 [a], %7;\n"
-            "@!p or.b32 %0, %0, %8;\n}"
-            : "+r"(mask)
-            : "f"(lo), "f"(hi), "r"(bits), "r"(kFloorMagicBits + kFilterCutRow), "r"(addr), "r"(dummyAddr),
-              "r"(addValue), "r"(groupBit)
-            : "memory");
-    } else {
-        if (ds > 0.0f) addr += kFilterCutRow * kPairRowBytes;
-        asm volatile(
-            "{\n.reg .pred p, q;\n.reg .u32 a;\n.reg .f32 t;\n"
-            "setp.eq.f32 p, %1, %2;\n"
-            "abs.f32 t, %9;\n"
-            "setp.gt.and.f32 p, t, %10, p;\n"
-            "setp.lt.and.u32 q, %3, %4, p;\n"
-            "selp.u32 a, %5, %6, q;\n"
-            "red.shared.add.u32 [a], %7;\n"
-            "@!p or.b32 %0, %0, %8;\n}"
-            : "+r"(mask)
-            : "f"(lo), "f"(hi), "r"(bits), "r"(kFloorMagicBits + kFilterCutRow), "r"(addr), "r"(dummyAddr),
-              "r"(addValue), "r"(groupBit), "f"(ds), "f"(thrEps)
-            : "memory");
-    }
+// The address arithmetic of one tile for one thread: counter of bin b = b * mul + adj for the
+// bits b of a float on the 1.5*2^23 grid (0x4b400000 + integer part).
+struct PairRows {
+    unsigned mul, adj;         // the tile's histogram (Close / DecayTag ascending, or Separated descending)
+    unsigned farMul, farAdj;   // the Separated histogram (tiles that test every pair)
+};
+
+// acc |= a ^ b: one LOP3 (an explicit lop3.b32 here crashes ptxas 12.9 in this kernel; tileLoop keeps
+// the compiler from turning the accumulation into compares instead)
+__device__ __forceinline__ void orXor(unsigned& acc, unsigned a, unsigned b) {
+    acc |= a ^ b;
 }
 
-// The rare path: group g of the tile (four events) held at least one undecided
-// pair of this thread.  Find them again (the filter is cheap) and queue them
-// for the FP64 pass at the end of the tile.  Out of line.
-template <bool TAGGED>
-__device__ __noinline__ unsigned queueUnsure(const FilterTile* tile, int g, const FilterChain* fcp, float thr,
-                                             float thrEps, PairQueue* queue, int tileBase, const PreparedEvent* chunkEvents,
-                                             const FakeChainParams* chain, int cls, unsigned countersAddr) {
-    const FilterChain fc = *fcp;
-    const float4 ls = reinterpret_cast<const float4*>(tile->ls)[g], d = reinterpret_cast<const float4*>(tile->d)[g];
-    const float4 nl = reinterpret_cast<const float4*>(tile->nl2)[g], sp = reinterpret_cast<const float4*>(tile->sep)[g];
-    const FilterPair a = filterCore2<TAGGED>(make_float2(ls.x, ls.y), make_float2(d.x, d.y), make_float2(nl.x, nl.y),
-                                             make_float2(sp.x, sp.y), fc, thr);
-    const FilterPair b = filterCore2<TAGGED>(make_float2(ls.z, ls.w), make_float2(d.z, d.w), make_float2(nl.z, nl.w),
-                                             make_float2(sp.z, sp.w), fc, thr);
-    bool sure[4];
-    sure[0] = filterDecide<TAGGED>(a.lo.x, a.hi.x, a.ds.x, thrEps).sure;
-    sure[1] = filterDecide<TAGGED>(a.lo.y, a.hi.y, a.ds.y, thrEps).sure;
-    sure[2] = filterDecide<TAGGED>(b.lo.x, b.hi.x, b.ds.x, thrEps).sure;
-    sure[3] = filterDecide<TAGGED>(b.lo.y, b.hi.y, b.ds.y, thrEps).sure;
-    unsigned inPlace = 0;
+// Count one event PROVISIONALLY in the row of floor(q(1+m)): VIMNMX, IMAD, ATOMS.  Whether the
+// decision stands is not looked at here: `acc` collects hi ^ lo over a group of four events
+// (one LOP3 each), and a group with a non-zero acc is revisited by queueUnsure, which takes the
+// provisional count of the undecided events back and queues them for FP64.
+__device__ __forceinline__ void countFast(float lo, float hi, unsigned mul, unsigned adj, unsigned addValue, unsigned& acc) {
+    const unsigned h = __float_as_uint(hi);
+#if SMCMC_PAIR_EXPERIMENT == 1 || SMCMC_PAIR_EXPERIMENT == 3          // timing experiment (wrong counts): no atomic at all
+    acc += min(h, kFloorMagicBits + kFilterCutRow) * mul + adj == 12345u ? 2u : 0u;
+#elif SMCMC_PAIR_EXPERIMENT == 2        // timing experiment (wrong counts): the atomic predicated off
+    const unsigned a = min(h, kFloorMagicBits + kFilterCutRow) * mul + adj;
+    if (h == 0x4b400000u + 77u) redShared(a, addValue);
+#else
+    redShared(min(h, kFloorMagicBits + kFilterCutRow) * mul + adj, addValue);
+#endif
+    orXor(acc, h, __float_as_uint(lo));
+}
+// ... in a tile that straddles the separation cut of some chain: far events go to the Separated
+// rows, and a separation within its error bound of the cut makes the event undecided as well.
+__device__ __forceinline__ void countFastSep(float lo, float hi, float ds, float thrEps, const PairRows& rows,
+                                             unsigned addValue, unsigned& acc) {
+    const unsigned h = __float_as_uint(hi);
+    const unsigned b = min(h, kFloorMagicBits + kFilterCutRow);
+    const bool far = ds > 0.0f;
+    redShared(far ? b * rows.farMul + rows.farAdj : b * rows.mul + rows.adj, addValue);
+    orXor(acc, h, __float_as_uint(lo));
+    if (!(fabsf(ds) > thrEps)) acc |= 1u;
+}
+
+// The rare path, out of line: queue one undecided pair of this lane (or evaluate it on the spot
+// when the warp's queue is full).
+__device__ __noinline__ void pushUnsure(PairQueue* queue, int eventInChunk) {
+    const int tid = threadIdx.x;
+    atomicAdd(&queue->unsure, 1u);
+    const unsigned slot = atomicAdd(&queue->count[tid >> 5], 1u);
+    if (slot < (unsigned)kPairQueueCap) queue->entry[tid >> 5][slot] = ((unsigned)eventInChunk << 8) | (unsigned)tid;
+    else exactCount(queue->chunkEvents + eventInChunk, queue->chains + tid, queue->cls, queue->countersAddr, tid);
+}
+// One warp works its queue off: one pair per lane.
+__device__ __noinline__ void drainWarpQueue(PairQueue* queue) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncwarp();
+    const unsigned queued = min(queue->count[w], (unsigned)kPairQueueCap);
+    if ((unsigned)lane < queued) {
+        const unsigned e = queue->entry[w][lane];
+        const int chain = (int)(e & 255u);
+        exactCount(queue->chunkEvents + (e >> 8), queue->chains + chain, queue->cls, queue->countersAddr, chain);
+    }
+    __syncwarp();
+    if (lane == 0) queue->count[w] = 0;
+    __syncwarp();
+}
+
+// An iteration (eight events) of a tile held an undecided pair of this lane, or the lane's chain
+// does not use the filter: take the provisional counts of the undecided events back and queue
+// them for FP64.  The values are the ones the iteration has just computed -- nothing is
+// evaluated again.
+struct Settle8 {
+    float lo[8], hi[8], ds[8];
+};
+template <bool NOSEP>
+__device__ __forceinline__ void settleUnsure(const Settle8& v, float thrEps, const PairRows& rows,
+                                             unsigned addValue, unsigned forceBit, PairQueue* queue, int event0) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (sure[k]) continue;
-        const int e = tileBase + g * 4 + k;
-        const unsigned slot = atomicAdd(&queue->count, 1u);
-        if (slot < (unsigned)kPairQueueCap) queue->entry[slot] = ((unsigned)e << 8) | threadIdx.x;
-        else {                            // queue full: evaluate in place
-            exactCount(chunkEvents + e, chain, cls, countersAddr, (int)threadIdx.x);
-            ++inPlace;
+    for (int k = 0; k < 8; ++k) {
+        const unsigned h = __float_as_uint(v.hi[k]);
+        bool unsure = ((h ^ __float_as_uint(v.lo[k])) | forceBit) != 0u;
+        if (!NOSEP && !(fabsf(v.ds[k]) > thrEps)) unsure = true;
+        if (!unsure) continue;
+        if (h < kFloorMagicBits + kFilterCutRow) {            // it was counted: take that back
+            const bool far = !NOSEP && v.ds[k] > 0.0f;
+            redShared(far ? h * rows.farMul + rows.farAdj : h * rows.mul + rows.adj, 0u - addValue);
         }
+        pushUnsure(queue, event0 + k);
     }
-    return inPlace;
 }
 
-// One tile of 128 events for one chain: four events per iteration, two packed
-// pairs whose dependency chains (LDS -> MUFU -> MUFU -> RED) overlap.  Returns
-// the mask of the groups (of four events) that held an undecided pair.
+// One tile of 128 events for one chain: eight events per iteration, four packed
+// pairs whose dependency chains (LDS -> MUFU -> MUFU -> RED) overlap.
 // NOSEP: no separation test (tagged classes, and tiles of the untagged classes
 // that lie on one side of the cut for every chain of the CTA).
 template <bool NOSEP>
-__device__ __forceinline__ unsigned tileLoop(const FilterTile* tile, const FilterChain& fc, float thr, float thrEps,
-                                             unsigned rowAdj, unsigned dummyAddr, unsigned addValue) {
+__device__ __forceinline__ void tileLoop(const FilterTile* tile, const FilterChain& fc, float thr, float thrEps,
+                                         const PairRows& rows, unsigned addValue, unsigned forceBit,
+                                         PairQueue* queue, int tileBase) {
     const float4* ls4 = reinterpret_cast<const float4*>(tile->ls);
     const float4* d4 = reinterpret_cast<const float4*>(tile->d);
     const float4* nl4 = reinterpret_cast<const float4*>(tile->nl2);
     const float4* sp4 = reinterpret_cast<const float4*>(tile->sep);
-    unsigned mask = 0;
-#pragma unroll kPairUnroll
-    for (int g = 0; g < kPairTile / 4; ++g) {
-        const float4 ls = ls4[g], d = d4[g], nl = nl4[g];
-        float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!NOSEP) sp = sp4[g];
-        const FilterPair a = filterCore2<NOSEP>(make_float2(ls.x, ls.y), make_float2(d.x, d.y),
-                                                make_float2(nl.x, nl.y), make_float2(sp.x, sp.y), fc, thr);
-        const FilterPair b = filterCore2<NOSEP>(make_float2(ls.z, ls.w), make_float2(d.z, d.w),
-                                                make_float2(nl.z, nl.w), make_float2(sp.z, sp.w), fc, thr);
-        const unsigned bit = 1u << g;
-        countOne<NOSEP>(a.lo.x, a.hi.x, a.ds.x, thrEps, rowAdj, dummyAddr, addValue, mask, bit);
-        countOne<NOSEP>(a.lo.y, a.hi.y, a.ds.y, thrEps, rowAdj, dummyAddr, addValue, mask, bit);
-        countOne<NOSEP>(b.lo.x, b.hi.x, b.ds.x, thrEps, rowAdj, dummyAddr, addValue, mask, bit);
-        countOne<NOSEP>(b.lo.y, b.hi.y, b.ds.y, thrEps, rowAdj, dummyAddr, addValue, mask, bit);
+#pragma unroll 1
+    for (int g = 0; g < kPairTile / 4; g += 2) {
+        FilterPair f[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#if SMCMC_PAIR_EXPERIMENT == 3          // timing experiment (wrong counts): no shared-memory loads either
+            const float gf = __int_as_float(0x3f800000 + ((g + h) << 12));
+            const float4 ls = make_float4(gf, gf + 0.25f, gf + 0.5f, gf + 0.75f);
+            const float4 d = make_float4(gf - 1.f, gf - 1.25f, gf - 1.5f, gf - 1.75f);
+            const float4 nl = make_float4(gf + 1.f, gf + 1.25f, gf + 1.5f, gf + 1.75f);
+#else
+            const float4 ls = ls4[g + h], d = d4[g + h], nl = nl4[g + h];
+#endif
+            float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!NOSEP) sp = sp4[g + h];
+            f[2 * h] = filterCore2<NOSEP>(make_float2(ls.x, ls.y), make_float2(d.x, d.y),
+                                          make_float2(nl.x, nl.y), make_float2(sp.x, sp.y), fc, thr);
+            f[2 * h + 1] = filterCore2<NOSEP>(make_float2(ls.z, ls.w), make_float2(d.z, d.w),
+                                              make_float2(nl.z, nl.w), make_float2(sp.z, sp.w), fc, thr);
+        }
+        unsigned acc = forceBit;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (NOSEP) {
+                countFast(f[k].lo.x, f[k].hi.x, rows.mul, rows.adj, addValue, acc);
+                countFast(f[k].lo.y, f[k].hi.y, rows.mul, rows.adj, addValue, acc);
+            } else {
+                countFastSep(f[k].lo.x, f[k].hi.x, f[k].ds.x, thrEps, rows, addValue, acc);
+                countFastSep(f[k].lo.y, f[k].hi.y, f[k].ds.y, thrEps, rows, addValue, acc);
+            }
+        }
+        asm volatile("" : "+r"(acc));           // keep acc an integer (one LOP3 per event), not eight compares
+        if (acc != 0u) {
+            Settle8 v;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v.lo[2 * k] = f[k].lo.x; v.lo[2 * k + 1] = f[k].lo.y;
+                v.hi[2 * k] = f[k].hi.x; v.hi[2 * k + 1] = f[k].hi.y;
+                v.ds[2 * k] = f[k].ds.x; v.ds[2 * k + 1] = f[k].ds.y;
+            }
+            settleUnsure<NOSEP>(v, thrEps, rows, addValue, forceBit, queue, tileBase + g * 4);
+        }
     }
-    return mask;
 }
 
 template <bool TAGGED>
@@ -627,25 +710,35 @@ __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t 
     FilterChain fc;
     if (live) fc = L.filterChains[point];
     else {
-        fc.scl2 = 0.f; fc.w2 = 1.f; fc.c2 = 0.f; fc.m0 = 1e-4f; fc.slopeT = 0.f;
-        fc.thr[0] = fc.thr[1] = 100.f; fc.thrEps[0] = fc.thrEps[1] = 1e-3f;
+        // no chain here: A = B (hi == lo for every event) and a negative bound of the separation test --
+        // nothing this lane computes is ever "undecided", nothing is read from its counters
+        fc.scl2 = 0.f; fc.w2 = 1.f; fc.a0 = 1.f; fc.aT = 0.f; fc.twoK = 2.f; fc.force = 0u;
+        fc.thr[0] = fc.thr[1] = 100.f; fc.thrEps[0] = fc.thrEps[1] = -1.f;
     }
     const float thr = (cls >> 1) ? fc.thr[1] : fc.thr[0];
     const float thrEps = (cls >> 1) ? fc.thrEps[1] : fc.thrEps[0];
-    constexpr int rows = TAGGED ? 50 : 100;
+    constexpr int rows = TAGGED ? kPairCutRow : kPairCounterRows + 1;      // the cut row is cleared too, never read
     for (int w = tid; w < rows * (kPairThreads / 2); w += kPairThreads) counters[w] = 0;
-    if (tid == 0) {
-        queue->count = 0;
-        queue->done[0] = queue->done[1] = 0;
-    }
     const unsigned countersAddr = smemAddr(counters);
+    const int64_t classFirst = L.classBase[cls] + first;          // a multiple of kPairTile
+    if (tid == 0) {
+        queue->done[0] = queue->done[1] = 0;
+        queue->unsure = 0;
+        queue->cls = cls;
+        queue->chunkEvents = L.events + classFirst;
+        queue->chains = L.chains + pointBase;
+        queue->countersAddr = countersAddr;
+    }
+    if (tid < kPairWarps) queue->count[tid] = 0;
     // chains c and c+128 share a word: the 32 lanes of a warp always address 32
     // consecutive words, i.e. 32 different banks, whatever rows they hit
-    const unsigned mineWord = (unsigned)(tid & (kPairThreads / 2 - 1));
-    const unsigned mineAdj = countersAddr + mineWord * 4u - kFloorMagicBits * kPairRowBytes;
-    const unsigned mineDummy = countersAddr + mineWord * 4u + kPairDummyRow * kPairRowBytes;
+    const unsigned mineWord = countersAddr + (unsigned)(tid & (kPairThreads / 2 - 1)) * 4u;
+    PairRows nearRows, farRows;
+    nearRows.mul = kPairRowBytes;
+    nearRows.adj = mineWord - kFloorMagicBits * kPairRowBytes;
+    nearRows.farMul = farRows.mul = farRows.farMul = 0u - kPairRowBytes;
+    nearRows.farAdj = farRows.adj = farRows.farAdj = mineWord + kPairFarRow0 * kPairRowBytes + kFloorMagicBits * kPairRowBytes;
     const unsigned mineAdd = (tid >= kPairThreads / 2) ? 65536u : 1u;
-    unsigned int unsureTotal = 0;
     // Range of the separation cut over the chains of the CTA, widened by the
     // error bound of the FP32 comparison: a tile whose separations all lie below
     // sepLow (above sepHigh) is near (far) for every chain, decided.
@@ -660,7 +753,7 @@ __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t 
             lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
             hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
         }
-        float* red = reinterpret_cast<float*>(queue->entry);       // the queue is not in use yet
+        float* red = reinterpret_cast<float*>(&queue->entry[0][0]);   // the queues are not in use yet
         if ((tid & 31) == 0) {
             red[(tid >> 5) * 2] = lo;
             red[(tid >> 5) * 2 + 1] = hi;
@@ -676,7 +769,6 @@ __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t 
     }
     __syncthreads();
 
-    const int64_t classFirst = L.classBase[cls] + first;          // a multiple of kPairTile
     const FilterTile* src = L.filterTiles + classFirst / kPairTile;
     const int numTiles = count / kPairTile;
     // Two tile buffers.  There is no CTA-wide barrier per tile: a warp that has
@@ -697,25 +789,15 @@ __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t 
         // Untagged classes: the events are sorted by separation, so most tiles lie
         // on one side of the cut for every chain of the CTA and the per-pair
         // separation test (and the load of the separations) is skipped there.
-        unsigned mask;
         int mode = 0;                             // 0: test every pair, 1: all near, 2: all far
         if (TAGGED) mode = 1;
         else if (tile->sep[kPairTile - 1] < sepLow) mode = 1;
         else if (tile->sep[0] > sepHigh) mode = 2;
         // a warp without a live chain (ensembles that do not fill the 256-chain tile) only
         // keeps the buffer protocol going
-        if (!warpLive) mask = 0;
-        else if (mode == 0) mask = tileLoop<false>(tile, fc, thr, thrEps, mineAdj, mineDummy, mineAdd);
-        else mask = tileLoop<true>(tile, fc, thr, thrEps, mode == 2 ? mineAdj + kFilterCutRow * kPairRowBytes : mineAdj,
-                                   mineDummy, mineAdd);
-        if (!live) mask = 0;
-        while (mask) {                            // rare: queue the undecided pairs for FP64
-            const int g = __ffs(mask) - 1;
-            mask &= mask - 1;
-            // (the general variant is right for every tile mode: where the test
-            // was skipped it is passed with room to spare)
-            unsureTotal += queueUnsure<TAGGED>(tile, g, L.filterChains + point, thr, thrEps, queue, t * kPairTile,
-                                               L.events + classFirst, L.chains + point, cls, countersAddr);
+        if (warpLive) {
+            if (mode == 0) tileLoop<false>(tile, fc, thr, thrEps, nearRows, mineAdd, fc.force, queue, t * kPairTile);
+            else tileLoop<true>(tile, fc, thr, thrEps, mode == 2 ? farRows : nearRows, mineAdd, fc.force, queue, t * kPairTile);
         }
         // end of tile for this warp: release the buffer
         __syncwarp();
@@ -732,34 +814,24 @@ __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t 
                 }
             }
         }
-        // every kPairDrainEvery tiles (and at the end of the chunk) the CTA meets
-        // and works the queue of undecided pairs off
-        if ((t % kPairDrainEvery) == kPairDrainEvery - 1 || t + 1 == numTiles) {
-            __syncthreads();
-            unsigned queued = queue->count;       // stable: nobody pushes before the next barrier
-            if (queued > (unsigned)kPairQueueCap) queued = kPairQueueCap;
-            for (unsigned i = tid; i < queued; i += kPairThreads) {
-                const unsigned e = queue->entry[i];
-                const int chain = (int)(e & 255u);
-                if (pointBase + chain < L.numPoints) {
-                    exactCount(L.events + classFirst + (e >> 8), L.chains + pointBase + chain, cls, countersAddr, chain);
-                    ++unsureTotal;
-                }
-            }
-            __syncthreads();
-            if (tid == 0) queue->count = 0;
-            __syncthreads();
-        }
+        // the warp's queue of undecided pairs: worked off once enough lanes would be busy, and at the
+        // end of the chunk (the count is the same for the whole warp after the barrier above)
+        const unsigned queued = queue->count[tid >> 5];
+        if (queued >= (unsigned)kPairDrainAt || (queued && t + 1 == numTiles)) drainWarpQueue(queue);
     }
     if (live) {
         const int slotBase = fakeClassSlotBase(cls);
         const int word = tid & (kPairThreads / 2 - 1), shift = (tid >= kPairThreads / 2) ? 16 : 0;
-        for (int r = 0; r < rows; ++r) {
-            const uint32_t v = (counters[r * (kPairThreads / 2) + word] >> shift) & 0xffffu;
-            if (v) atomicAdd(&L.counts[countIndex(slotBase + r, point, L.blockPoints)], v);
+        constexpr int bins = TAGGED ? kFilterCutRow : 2 * kFilterCutRow;
+        for (int b = 0; b < bins; ++b) {
+            const uint32_t v = (counters[pairRowOfBin(b) * (kPairThreads / 2) + word] >> shift) & 0xffffu;
+            if (v) atomicAdd(&L.counts[countIndex(slotBase + b, point, L.blockPoints)], v);
         }
     }
-    if (L.stats && unsureTotal) atomicAdd(&L.stats[0], (unsigned long long)unsureTotal);
+    if (L.stats) {
+        __syncthreads();
+        if (tid == 0 && queue->unsure) atomicAdd(&L.stats[0], (unsigned long long)queue->unsure);
+    }
 }
 
 // grid.x = (#chunks over all classes) * (#point tiles); consecutive CTAs take
