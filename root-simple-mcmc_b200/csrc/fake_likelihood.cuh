@@ -302,9 +302,12 @@ __device__ __forceinline__ int exactDecide(const PreparedEvent& ev, const FakeCh
 //                            B = 2K - A is exact (Sterbenz) while m <= 3
 // |x2| <= 16 holds for every pair because |scl2| = |0.3 erf(.) log2 e| <= 0.4329
 // and events with |logSigma| > 36 are kept out of the fast path at upload;
-// |nl2| <= 16 is checked per event at upload as well.  With those guards the
-// bound is  <= u[48.4 + 30.5|t w2|] (the c2 terms of the round-1 formula went with the
-// addition); the code keeps m0 = 2u(48.4 + 2.78|c2|) and slopeT = 2u 30.5|w2|: more than twice it.
+// |nl2| <= 16 is checked per event at upload as well.  With those guards
+//   rel(q') <= u[4 + ln2 (2*16)] + u ln2 (8 + 2.08*16)|t w2| = u[26.2 + 28.6|t w2|],
+// and the interval [q'B, q'A] holds the exact q when m >= rel(q') + 3u (K, A and 2K as floats):
+//   m >= u[29.2 + 28.6|t w2|]  (first order; the second-order terms are below 1e-3 u).
+// The code uses kFilterSafety = 1.5 times that (round 1 used 2 x u[48.4 + 2.78|c2| + 30.5|t w2|]: the
+// c2 terms went with the addition, and every undecided pair costs an FP64 evaluation).
 // Chains whose constants leave the range this analysis covers (|c2| > 24, |w2| > 2^24, anything
 // non-finite) and SMCMC_FAKE_EXACT carry force = 1: every pair of theirs goes to FP64.
 //
@@ -324,6 +327,7 @@ struct __align__(16) FilterTile {
 };
 static_assert(sizeof(FilterTile) == 16 * kPairTile, "FilterTile is 16 bytes per event");
 
+constexpr double kFilterSafety = 1.5;
 struct __align__(16) FilterChain {
     float scl2;      // skewc * log2(e)
     float w2;        // width * log2(e)
@@ -384,8 +388,8 @@ __device__ __forceinline__ void storeFilterChain(FilterChain* dst, int c, const 
     f.w2 = __double2float_rn(w2);
     const double c2 = cp.scale * log2e - log2ten;
     const double K = exp2(c2);
-    const double m0 = 2.0 * u * (48.4 + 2.78 * fabs(c2));
-    const double slopeT = 2.0 * u * 30.5 * fabs(w2);
+    const double m0 = kFilterSafety * u * 29.2;
+    const double slopeT = kFilterSafety * u * 28.6 * fabs(w2);
     f.a0 = __double2float_ru(K * (1.0 + m0));
     f.aT = __double2float_ru(K * slopeT);
     f.twoK = __double2float_rn(2.0 * K);
@@ -733,11 +737,11 @@ __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t 
     // chains c and c+128 share a word: the 32 lanes of a warp always address 32
     // consecutive words, i.e. 32 different banks, whatever rows they hit
     const unsigned mineWord = countersAddr + (unsigned)(tid & (kPairThreads / 2 - 1)) * 4u;
-    PairRows nearRows, farRows;
+    PairRows nearRows;
     nearRows.mul = kPairRowBytes;
     nearRows.adj = mineWord - kFloorMagicBits * kPairRowBytes;
-    nearRows.farMul = farRows.mul = farRows.farMul = 0u - kPairRowBytes;
-    nearRows.farAdj = farRows.adj = farRows.farAdj = mineWord + kPairFarRow0 * kPairRowBytes + kFloorMagicBits * kPairRowBytes;
+    nearRows.farMul = 0u - kPairRowBytes;
+    nearRows.farAdj = mineWord + kPairFarRow0 * kPairRowBytes + kFloorMagicBits * kPairRowBytes;
     const unsigned mineAdd = (tid >= kPairThreads / 2) ? 65536u : 1u;
     // Range of the separation cut over the chains of the CTA, widened by the
     // error bound of the FP32 comparison: a tile whose separations all lie below
@@ -796,8 +800,13 @@ __device__ __forceinline__ void pairChunk(const PairLaunch& L, int cls, int64_t 
         // a warp without a live chain (ensembles that do not fill the 256-chain tile) only
         // keeps the buffer protocol going
         if (warpLive) {
-            if (mode == 0) tileLoop<false>(tile, fc, thr, thrEps, nearRows, mineAdd, fc.force, queue, t * kPairTile);
-            else tileLoop<true>(tile, fc, thr, thrEps, mode == 2 ? farRows : nearRows, mineAdd, fc.force, queue, t * kPairTile);
+            PairRows rows = nearRows;             // (by value: a pointer to one of two structs puts both on the stack)
+            if (mode == 2) {
+                rows.mul = nearRows.farMul;
+                rows.adj = nearRows.farAdj;
+            }
+            if (mode == 0) tileLoop<false>(tile, fc, thr, thrEps, rows, mineAdd, fc.force, queue, t * kPairTile);
+            else tileLoop<true>(tile, fc, thr, thrEps, rows, mineAdd, fc.force, queue, t * kPairTile);
         }
         // end of tile for this warp: release the buffer
         __syncwarp();
