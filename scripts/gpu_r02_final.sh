@@ -22,7 +22,7 @@ NCU="ncu --set full --import-source on --clock-control none --launch-count 1 -f"
 # gpurun brings back at most 64 MiB: every report is exported to its raw CSV page on the box and
 # removed, except the headline kernel's
 keep() { ncu -i $O/${T}_$1.ncu-rep --page raw --csv > $O/${T}_$1.raw.csv 2>/dev/null; [ "$1" = kFakePairs ] || rm -f $O/${T}_$1.ncu-rep; }
-timeout 300 $NCU -k regex:^kFakePairs$ --launch-skip 3 -o $O/${T}_kFakePairs python scripts/prof_pairs.py > $O/${T}_ncu_pairs.log 2>&1; tail -1 $O/${T}_ncu_pairs.log; keep kFakePairs
+timeout 300 $NCU -k regex:^kFakePairs$ --launch-skip 3 -o $O/${T}_kFakePairs env PAIRS_FILTER_CHECK=1 python scripts/prof_pairs.py > $O/${T}_ncu_pairs.log 2>&1; tail -1 $O/${T}_ncu_pairs.log; keep kFakePairs
 export HMC_STEPS=4
 for k in kHmcLeapDmma kDummyContractDmma kPoolGramDmma; do
   timeout 400 $NCU -k regex:$k --launch-skip 3 -o $O/${T}_$k python scripts/prof_hmc.py > $O/${T}_ncu_$k.log 2>&1; tail -1 $O/${T}_ncu_$k.log; keep $k

@@ -13,3 +13,6 @@ expo = smcmc_b200.synth.exposure_ratio(eng, data); eng.set_fake_data(data, expo)
 eng.start(np.random.default_rng(0).uniform(-1, 1, (E, 9)))
 eng.step(4); eng.sync()
 print("done", eng.get("acceptance").mean())
+if os.environ.get("PAIRS_FILTER_CHECK"):
+    pairs, unsure, bad = eng.fake_filter_check(eng.get("proposed"))
+    print("filter check: pairs %d, undecided %d (%.4f %%), disagreements %d" % (pairs, unsure, 100.0 * unsure / pairs, bad))
