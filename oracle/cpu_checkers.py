@@ -123,6 +123,8 @@ def load(which):
         lib.ref_dummy_matrices.argtypes = [vp, vp]
         lib.ref_ex2_generate.restype = ctypes.c_long
         lib.ref_ex2_generate.argtypes = [ctypes.c_ulong, ci, ci, cd, vp, ctypes.c_long, vp]
+        lib.ref_shim_linalg.restype = ci
+        lib.ref_shim_linalg.argtypes = [ci, ci, vp, vp, vp]
         lib.ref_chain_restore_random.restype = ci
         lib.ref_chain_restore_random.argtypes = [vp, vp, vp]
     _LIBS[which] = lib
@@ -377,3 +379,17 @@ def ref_dummy_matrices():
     err = np.zeros((100, 100))
     lib.ref_dummy_matrices(_ptr(cov), _ptr(err))
     return cov, err
+
+
+def ref_shim_linalg(which, a):
+    """The shim's TDecompChol (0), TMatrixD::Invert (1) or TMatrixDSymEigen (2) on a square matrix:
+    (matrix, values) as the reference's code receives them."""
+    lib = load("ref")
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    n = a.shape[0]
+    out = np.zeros((n, n))
+    values = np.zeros(n)
+    rc = lib.ref_shim_linalg(which, n, _ptr(a), _ptr(out), _ptr(values))
+    if rc < 0:
+        raise RuntimeError(lib.ref_last_error().decode())
+    return (out, values) if rc == 0 else (None, None)

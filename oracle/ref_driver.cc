@@ -586,6 +586,46 @@ int ref_dummy_matrices(double* covariance, double* error) {
     return 0;
 }
 
+// The ROOT linear algebra the reference calls, as restated in oracle/rootshim (ROOT itself is
+// absent): exposed so that tests/test_oracle.py can hold it against LAPACK (numpy) -- an
+// independent implementation -- on random symmetric positive definite matrices.
+//   which 0: TDecompChol::Decompose -> U (upper, U^T U = a)          TSimpleMCMC.H:1100-1118
+//   which 1: TMatrixD::Invert                                          TSimpleHMC.H:806-812
+//   which 2: TMatrixDSymEigen -> out = eigenvectors in columns, values = eigenvalues descending
+//            (TSimpleMCMC.H:1287-1301, TSimpleHMC.H:786-800)
+int ref_shim_linalg(int which, int n, const double* a, double* out, double* values) {
+    return Guard([&]() {
+        if (which == 2) {
+            TMatrixDSym m(n);
+            for (int i = 0; i < n; ++i)
+                for (int j = 0; j < n; ++j) m(i, j) = a[(size_t)i * n + j];
+            TMatrixDSymEigen eig(m);
+            const TMatrixD& v = eig.GetEigenVectors();
+            const TVectorD& w = eig.GetEigenValues();
+            for (int i = 0; i < n; ++i) {
+                values[i] = w(i);
+                for (int j = 0; j < n; ++j) out[(size_t)i * n + j] = v(i, j);
+            }
+            return 0;
+        }
+        TMatrixD m(n, n);
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) m(i, j) = a[(size_t)i * n + j];
+        if (which == 0) {
+            TDecompChol chol(m);
+            if (!chol.Decompose()) return 1;
+            const TMatrixD& u = chol.GetU();
+            for (int i = 0; i < n; ++i)
+                for (int j = 0; j < n; ++j) out[(size_t)i * n + j] = u(i, j);
+            return 0;
+        }
+        m.Invert();
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) out[(size_t)i * n + j] = m(i, j);
+        return 0;
+    });
+}
+
 // The reference's own toy-input generators (example/Simulated.H:17-53 and
 // example/FakeData.H:32-117) run under a seeded shim generator; used to check
 // that the product's synthetic-input builder follows the same distributions.

@@ -393,3 +393,43 @@ def test_vaat_chain_matches_golden(checkers, have_ref, which, name):
         assert np.array_equal(np.asarray(v[k]), g[name + "/final_" + k]), k
     assert [v["trials"], v["successes"], v["last_index"], v["queue"]] == list(g[name + "/final_misc"])
     assert c.state()["step_rms"] == g[name + "/final_step_rms"][0]
+
+
+@pytest.mark.parametrize("n", [2, 5, 50, 100])
+def test_shim_linear_algebra_against_lapack(checkers, have_ref, n):
+    """ROOT is absent, so `oracle/_ref` runs the reference's headers on a restatement of the ROOT
+    linear algebra they call (oracle/rootshim: TDecompChol, TMatrixD::Invert, TMatrixDSymEigen).
+    Held here against LAPACK (numpy), an independent implementation, on random symmetric positive
+    definite matrices of the sizes the golden chains use: the factor, the inverse and the spectrum
+    are unique, so agreement to rounding pins what the shim computes, not how."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(1000 + n)
+    for trial in range(4):
+        g = rng.normal(size=(n, 2 * n))
+        a = g @ g.T / (2 * n) + 0.05 * np.eye(n)
+        if trial == 3:                                   # strongly correlated, condition number ~1e6
+            d = np.logspace(0, 3, n)
+            a = d[:, None] * (0.98 + 0.02 * np.eye(n)) * d[None, :]
+        cond = np.linalg.cond(a)
+        u, _ = checkers.ref_shim_linalg(0, a)
+        assert np.array_equal(np.tril(u, -1), np.zeros((n, n)))
+        assert np.allclose(u, np.linalg.cholesky(a).T, rtol=1e-13 * cond, atol=1e-15 * np.abs(a).max())
+        inv, _ = checkers.ref_shim_linalg(1, a)
+        ref = np.linalg.inv(a)
+        assert np.abs(inv - ref).max() <= 1e-14 * cond * np.abs(ref).max()
+        vec, val = checkers.ref_shim_linalg(2, a)
+        w, v = np.linalg.eigh(a)
+        w, v = w[::-1], v[:, ::-1]                       # the reference relies on DESCENDING eigenvalues
+        assert np.all(np.diff(val) <= 0.0)
+        assert np.allclose(val, w, rtol=0, atol=1e-13 * w[0])
+        assert np.allclose(vec.T @ vec, np.eye(n), atol=1e-12)
+        assert np.abs(a @ vec - vec * val[None, :]).max() <= 1e-12 * w[0]
+        gap = np.min(np.abs(np.diff(w))) / w[0]
+        if gap > 1e-6:                                   # simple spectrum: the eigenvectors themselves, up to sign
+            sign = np.sign(np.sum(vec * v, axis=0))
+            assert np.abs(vec * sign[None, :] - v).max() <= 1e-12 / gap
+    # a matrix that is not positive definite: Decompose() fails (TSimpleMCMC.H:1100-1118 takes that branch)
+    bad = np.eye(n)
+    bad[n - 1, n - 1] = -1.0
+    assert checkers.ref_shim_linalg(0, bad)[0] is None
