@@ -34,3 +34,14 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --c
 python scripts/summarize_launches.py $O/${T}_launches_stream.csv | grep -v "cub::\|Gather\|SortKeys\|CountClasses\|PadEvents\|InitState\|StoreStart" | head -10
 C3_POOLED=16 C3_STEPS=20 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/${T}_launches_c3_pooled.csv python scripts/prof_c3.py > /dev/null 2>&1
 python scripts/summarize_launches.py $O/${T}_launches_c3_pooled.csv | head -8
+HMC_STEPS=6 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${T}_launches_hmc.csv python scripts/prof_hmc.py > /dev/null 2>&1
+python scripts/summarize_launches.py $O/${T}_launches_hmc.csv | head -14
+# same-box A/B against the round-1 tree (a git worktree at _r01, present only while measuring)
+if [ -d _r01 ]; then
+  for d in _r01 .; do
+    ( cd $d; timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); r=d['roofline']
+print('$d', 'C2 ms/step %.4f'%d['ms_per_step'], 'kFakePairs ms %.4f'%r['launch_ms'], 'sfu frac %.4f'%r['frac'], 'e2e %.4g'%d['e2e']['value'])" )
+  done > $O/${T}_ab_r01.txt 2>&1; cat $O/${T}_ab_r01.txt
+fi
