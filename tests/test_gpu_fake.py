@@ -158,15 +158,26 @@ def test_ragged_event_counts(checkers, nev):
     assert rel(llh, np.array([orc.llh(p) for p in pts])) < RTOL
 
 
-def test_extreme_parameters(checkers):
+@pytest.mark.parametrize("kernel", ["stream", "pairs"])
+def test_extreme_parameters(checkers, kernel):
     """Parameter points that push masses out of range, collapse the width, or
     are not finite: the cut / overflow handling must follow the reference
-    (FakeLikelihood.H:203-205 and TH1's under/overflow bins)."""
+    (FakeLikelihood.H:203-205 and TH1's under/overflow bins).  Twelve points go through the
+    streaming kernel (<= 16 chains); "pairs" evaluates them three times over in one call so that
+    kFakePairs takes them -- including the chains whose constants leave the range the FP32 filter's
+    error analysis covers (|c2| > 24, |w2| > 2^24, non-finite: every pair in FP64) and chains
+    just inside it, whose bound is so wide that most pairs are undecided."""
     g = golden("fake_likelihood.npz")
-    eng = make_engine(g["events"], g["data"], float(g["exposure"]))
+    eng = make_engine(g["events"], g["data"], float(g["exposure"]), chains=64)
     orc = checkers.CpuChain("orc", checkers.LLH_FAKE, 9, 1, 0)
     orc.set_fake(g["events"], g["data"], float(g["exposure"]))
-    pts = np.zeros((12, 9))
+    pts = np.zeros((18, 9))
+    pts[12, 2] = 200.0        # c2 = 25.5: outside the filter's range
+    pts[13, 2] = -250.0       # c2 = -39.4
+    pts[14, 3] = 200.0        # width e^20: w2 > 2^24
+    pts[15, 3] = 160.0        # w2 = 1.3e7 < 2^24: filter on, bound useless
+    pts[16, 2] = 160.0        # c2 = 19.8: filter on, K = 2^19.8
+    pts[17, 2], pts[17, 3] = -140.0, 100.0
     pts[0, 2] = 40.0          # mass scale e^4: everything above 500
     pts[1, 2] = -60.0         # everything in the first bin
     pts[2, 3] = -400.0        # width -> 0: all events at the nominal mass
@@ -179,10 +190,16 @@ def test_extreme_parameters(checkers):
     pts[9, 8] = -1e6
     pts[10, 2] = np.nan
     pts[11, 3] = np.inf
+    base = len(pts)
+    if kernel == "pairs":
+        pts = np.concatenate([pts, pts, pts])
     hist = eng.fake_histograms(pts)
     counts = eng.fake_counts(pts)
     llh = eng.eval(pts)
     for i in range(len(pts)):
+        if i >= base:                                  # the repeats: identical to the first copy
+            assert np.array_equal(counts[i], counts[i - base]) and np.array_equal(llh[i], llh[i - base], equal_nan=True), i
+            continue
         assert np.array_equal(counts[i], orc.fake_counts(pts[i])), i
         want_hist = orc.fake_hist(pts[i])
         ok = np.isfinite(want_hist)
@@ -228,3 +245,25 @@ def test_streaming_kernel_counts_equal_the_pair_kernel(chains, monkeypatch):
     monkeypatch.setenv("SMCMC_FAKE_EXACT", "1")
     exact = make_engine(events, data, 0.1, chains=chains)
     assert np.array_equal(exact.fake_counts(pts), c_stream)
+
+
+def test_pair_kernel_is_deterministic_under_repetition():
+    """compute-sanitizer is closed on this pool, so the barrier-free tile hand-over, the shared-memory
+    RED counters, the provisional count / take-back of undecided pairs and the per-warp FP64 queues of
+    kFakePairs are stressed the only way left: the same 700 points (a partly filled last CTA), 40
+    evaluations, on an event set with ragged class sizes -- every integer of every count table must come
+    out the same, and equal to the all-FP64 evaluation."""
+    import smcmc_b200
+    import os
+    events, data = smcmc_b200.synth.fake_inputs(9000, 7000, 6, seed=5)
+    eng = make_engine(events, data, 0.15, chains=700)
+    pts = np.random.default_rng(8).normal(0, 3, (700, 9))
+    first = eng.fake_counts(pts)
+    for _ in range(40):
+        assert np.array_equal(eng.fake_counts(pts), first)
+    os.environ["SMCMC_FAKE_EXACT"] = "1"
+    try:
+        exact = make_engine(events, data, 0.15, chains=700)
+    finally:
+        del os.environ["SMCMC_FAKE_EXACT"]
+    assert np.array_equal(exact.fake_counts(pts), first)
