@@ -285,6 +285,10 @@ struct smcmc_engine {
         return p;
     }
     int poolStatCount() const { return 1 + n() + tri(); }
+    static int poolGramMin() {
+        const char* v = std::getenv("SMCMC_POOL_GRAM_MIN");
+        return v ? std::atoi(v) : 64;
+    }
     // S += the accepted points of the local chains (count, sum x, sum x x^T): Y^T Y on the
     // FP64 tensor cores; SMCMC_POOL_ACC_SCALAR=1 keeps the scalar kernel
     void poolAccumulate(double* stats) { poolAccumulateOn(xAcc.get(), sc.get(), nullptr, stats); }
@@ -293,7 +297,7 @@ struct smcmc_engine {
         if (!mask && std::getenv("SMCMC_POOL_ACC_SCALAR")) {
             const int poolBlocks = std::min(smCount * 8, ceilDiv(E(), kPoolTile));
             kPoolAccumulate<<<poolBlocks, 256, poolAccSmem(n()), stream>>>(xAcc.get(), sc.get(), E(), n(), stats);
-        } else if (n() >= 64 && !std::getenv("SMCMC_POOL_ACC_DIRECT")) {
+        } else if (n() >= poolGramMin() && !std::getenv("SMCMC_POOL_ACC_DIRECT")) {
             // large dimension: shared-memory tiled Y^T Y (kPoolGramDmma)
             const int nb = ceilDiv(n() + 1, kGramB), pairs = nb * (nb + 1) / 2;
             // chain slices so that the grid is ONE wave of 3 CTAs per SM (13 slices x 36 tile pairs = 468 CTAs

@@ -121,13 +121,20 @@ __device__ __forceinline__ void poolLoadFragment(double (&f)[7], const double* _
                                                  int n, int c, int cLast, int y0, int g) {
     // which chains take part: the running ones (sc), or -- TSimpleHMC's pooled covariance -- the
     // chains marked in `mask`
-    const bool live = c < cLast && (mask ? mask[c] != 0 : sc[c].started != 0);
-    const double* xr = xAcc + (size_t)c * n;
+    // (the point is loaded NEXT TO the flag, not behind it: a chain outside the range reads, and
+    // discards, the last row inside it)
+    const bool inside = c < cLast;
+    const int cc = inside ? c : cLast - 1;
+    const int flag = mask ? mask[cc] : sc[cc].started;
+    const double* xr = xAcc + (size_t)cc * n;
 #pragma unroll
     for (int t = 0; t < 7; ++t) {
         const int y = y0 + 8 * t + g;
-        f[t] = (!live || y > n) ? 0.0 : (y == 0 ? 1.0 : xr[y - 1]);
+        f[t] = (y >= 1 && y <= n) ? xr[y - 1] : (y == 0 ? 1.0 : 0.0);
     }
+    const bool live = inside && flag != 0;
+#pragma unroll
+    for (int t = 0; t < 7; ++t) f[t] = live ? f[t] : 0.0;
 }
 
 template <bool kDiag>
@@ -644,8 +651,11 @@ kProposePooledTile(ChainArrays a, PropSettings ps, PooledState pool, int chains,
     }
     // ---- one thread per (chain, dimension): the draws, :709-719 -------------------
     // (one thread per chain and PAIR of dimensions: both normals from one Philox block)
+    // (warps 1..7: warp 0 is busy with the scalars above -- pow, divisions, a square root per chain --
+    // and the CTA would wait for it at the barrier if it took a share of the draws as well)
     const int npairs = (n + 1) >> 1;
-    for (int k = tid; k < nc * npairs; k += kPooledTileThreads) {
+    for (int k = tid - 32; k < nc * npairs; k += kPooledTileThreads - 32) {
+        if (k < 0) break;
         const int c = k / npairs, pr = k - c * npairs;
         const uint32_t gchain = chainOffset + (uint32_t)(c0 + c);
         double v0, v1;
