@@ -224,6 +224,8 @@ struct LeapFused {
     const int* leapSteps;
     double* uturn;           // [2][chains][blocks]: sum of p p0 over each column block, gradients k (parity k & 1)
     int blocks;              // column blocks = gridDim.x
+    double* endPartial;      // [chains][blocks] or null: x . (Error x) over each column block at the END point of a chain's
+                             // trajectory (its last gradient, k == steps) -- the potential there without another GEMM
 };
 
 template <bool VEC16>
@@ -247,6 +249,45 @@ kHmcLeapDmma(const double* __restrict__ err, LeapFused f, int k, int chains, int
     }
     double acc[4][4][2];
     dmmaMainloop<VEC16>(acc, dmmaSmem, f.qIn, err, c0, chains, i0, n, tid);
+    // The last gradient of a chain's trajectory is taken AT the proposed point (no drift follows,
+    // :646-648): x . (Error x) over this column block is the block's share of the potential there --
+    // the partial sum kDummyContractDmma (mode 1) would produce from the same accumulators, formed the
+    // same way (per lane over its columns, the quad by shuffle, the two warps of a row in shared memory).
+    if (f.endPartial) {
+        __shared__ double part[kDmmaBM][2];
+        bool mine = false;
+        int rowEnd[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int c = c0 + wm + a * 8 + g;
+            const int st = c < chains ? f.leapSteps[c] : -1;
+            rowEnd[a] = (st >= 1 && k == st) ? 1 : 0;
+            mine = mine || rowEnd[a];
+        }
+        if (__syncthreads_or(mine ? 1 : 0)) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int c = c0 + wm + a * 8 + g;
+                double sum = 0.0;
+                if (rowEnd[a]) {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int i = i0 + wn + b * 8 + 2 * q;
+                        if (i < n) sum = fma(f.qIn[(size_t)c * n + i], acc[a][b][0], sum);
+                        if (i + 1 < n) sum = fma(f.qIn[(size_t)c * n + i + 1], acc[a][b][1], sum);
+                    }
+                }
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                if (q == 0) part[wm + a * 8 + g][warp & 1] = sum;
+            }
+            __syncthreads();
+            if (tid < kDmmaBM && c0 + tid < chains) {
+                const int st = f.leapSteps[c0 + tid];
+                if (st >= 1 && k == st) f.endPartial[(size_t)(c0 + tid) * f.blocks + blockIdx.x] = part[tid][0] + part[tid][1];
+            }
+        }
+    }
     // The gradient tile goes through shared memory (the pipeline buffers are free now) so that the
     // element-wise part reads and writes WHOLE ROWS: a warp takes a chain's 64 dimensions of this
     // column block as one 512-byte piece of q, p, p0 (16 bytes per lane), instead of the 8 x 64-byte

@@ -61,8 +61,8 @@ void hmcAllocate(smcmc_engine* e) {
     h.sc.reserve(E);
     h.leapSteps.reserve(E);
     h.updateList.reserve(E);
-    h.counters.reserve(2);
-    CUDA_CHECK(cudaMallocHost((void**)&h.hostCounters, 2 * sizeof(int)));
+    h.counters.reserve(3);
+    CUDA_CHECK(cudaMallocHost((void**)&h.hostCounters, 3 * sizeof(int)));
     std::vector<HmcScalars> init(E);
     std::memset(init.data(), 0, sizeof(HmcScalars) * E);
     for (size_t c = 0; c < E; ++c) init[c].leapFrogSteps = 10;            // TSimpleHMC.H:133
@@ -200,7 +200,9 @@ void hmcGradient(smcmc_engine* e, HmcGradientMode mode, int k) {
 
 int hmcReadCounter(smcmc_engine* e, int which) {
     HmcHost& h = e->hmc;
-    CUDA_CHECK(cudaMemcpyAsync(h.hostCounters + which, h.counters.get() + which, sizeof(int),
+    // ([0] and [2] are written by the same kernel and read together)
+    const int first = which == 1 ? 1 : 0, count = which == 1 ? 1 : 3;
+    CUDA_CHECK(cudaMemcpyAsync(h.hostCounters + first, h.counters.get() + first, count * sizeof(int),
                                cudaMemcpyDeviceToHost, e->stream));
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
     return h.hostCounters[which];
@@ -231,7 +233,7 @@ void hmcStepOnce(smcmc_engine* e, int type, const HmcTraceDev& tr, int traceStep
     const int blocks = ceilDiv(E, kWarpsPerBlock), threads = kWarpsPerBlock * 32;
     const size_t smem = (size_t)kWarpsPerBlock * n * sizeof(double);
     if (h.alpha < 0.0) h.alpha = 0.0;                                     // :565
-    CUDA_CHECK(cudaMemsetAsync(h.counters.get(), 0, 2 * sizeof(int), e->stream));
+    CUDA_CHECK(cudaMemsetAsync(h.counters.get(), 0, 3 * sizeof(int), e->stream));
     kHmcBegin<<<blocks, threads, smem, e->stream>>>(a, n, E, h.alpha, e->cfg.seed, e->cfg.chain_offset, e->stepIndex);
     e->launched();
     const int maxSteps = hmcReadCounter(e, 0);
@@ -240,10 +242,15 @@ void hmcStepOnce(smcmc_engine* e, int type, const HmcTraceDev& tr, int traceStep
     // (contraction.cuh, kHmcLeapDmma); SMCMC_HMC_NO_FUSE=1 keeps gradient kernel + kHmcKickDrift
     const bool fused = mode == kGradUser && e->cfg.likelihood == SMCMC_LLH_DUMMY && e->dummyMode == SMCMC_DUMMY_TENSOR &&
                        e->errDim == n && !std::getenv("SMCMC_HMC_NO_FUSE");
+    // ... and when every running chain has a trajectory, the potential at its end comes out of the
+    // chain's last gradient launch (LeapFused::endPartial) instead of a GEMM of its own
+    bool potentialDone = false;
     if (maxSteps >= 1 && fused) {
         const int colBlocks = ceilDiv(n, kDmmaBN);
         h.qAlt.reserve((size_t)E * n);
         h.uturn.reserve((size_t)2 * E * colBlocks);
+        const bool endPotential = h.hostCounters[2] == 0 && !std::getenv("SMCMC_HMC_SEPARATE_POTENTIAL");
+        if (endPotential) e->dummyPartials.reserve((size_t)E * colBlocks);
         LeapFused f;
         f.p = h.pProp.get();
         f.p0 = h.p0.get();
@@ -253,6 +260,7 @@ void hmcStepOnce(smcmc_engine* e, int type, const HmcTraceDev& tr, int traceStep
         f.leapSteps = h.leapSteps.get();
         f.uturn = h.uturn.get();
         f.blocks = colBlocks;
+        f.endPartial = endPotential ? e->dummyPartials.get() : nullptr;
         for (int k = 0; k <= maxSteps; ++k) {
             f.qIn = h.qProp.get();
             f.qOut = h.qAlt.get();
@@ -261,6 +269,11 @@ void hmcStepOnce(smcmc_engine* e, int type, const HmcTraceDev& tr, int traceStep
             h.qProp.swap(h.qAlt);                                        // the proposed positions are in the buffer just written
         }
         a = hmcArrays(e);
+        if (endPotential) {
+            kDummyLlhFromPartials<<<ceilDiv(E, 128), 128, 0, e->stream>>>(e->dummyPartials.get(), colBlocks, E, h.llh.get());
+            e->launched();
+            potentialDone = true;
+        }
     } else if (maxSteps >= 1) {
         for (int k = 0; k <= maxSteps; ++k) {
             hmcGradient(e, mode, k);
@@ -268,7 +281,7 @@ void hmcStepOnce(smcmc_engine* e, int type, const HmcTraceDev& tr, int traceStep
             e->launched();
         }
     }
-    e->evaluate(h.qProp.get(), E, h.llh.get(), nullptr);                  // :327
+    if (!potentialDone) e->evaluate(h.qProp.get(), E, h.llh.get(), nullptr);   // :327
     kHmcPost<<<blocks, threads, smem, e->stream>>>(a, n, E, h.llh.get(), 1000000.0 /* fCovarianceWindow :134 */,
                                                    fused && maxSteps >= 1 ? 1 : 0);
     e->launched();

@@ -118,7 +118,8 @@ struct HmcArrays {
     struct HmcPooled* pool;
     HmcScalars* sc;
     int* leapSteps;     // copy of sc.steps for the gradient kernels
-    int* counters;      // [0] max steps of this transition, [1] chains that need UpdateErrorMatrix
+    int* counters;      // [0] max steps of this transition, [1] chains that need UpdateErrorMatrix,
+                        // [2] running chains WITHOUT a trajectory in this transition (steps < 1)
     int* updateList;
     double* eigScratch; // slots of 2*n*n doubles
     int* eigLocks;
@@ -279,6 +280,7 @@ kHmcBegin(HmcArrays a, int n, int chains, double alpha, uint64_t seed, uint32_t 
         a.sc[c] = s;
         a.leapSteps[c] = s.steps;
         atomicMax(&a.counters[0], s.steps);
+        if (s.steps < 1) atomicAdd(&a.counters[2], 1);
     }
 }
 
