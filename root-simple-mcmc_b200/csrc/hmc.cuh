@@ -133,6 +133,33 @@ __device__ __forceinline__ double warpSeqSum(const double* buf, int n) {
     return s;
 }
 
+// Row copies of one chain by its warp: 16 bytes per lane and four loads in flight before the
+// first store when the rows allow it (n even: every row starts 16-byte aligned), instead of one
+// 8-byte load per lane at a time -- the pointers of HmcArrays may alias as far as the compiler
+// knows, so it never hoists a load over a store by itself.  NEG: dst = -src (:364-366).
+template <bool NEG>
+__device__ __forceinline__ void warpCopyRow(double* dst, const double* src, int n, int lane) {
+    if ((n & 1) == 0) {
+        const int m = n >> 1;
+        const double2* s2 = reinterpret_cast<const double2*>(src);
+        double2* d2 = reinterpret_cast<double2*>(dst);
+        for (int i = lane; i < m; i += 128) {
+            double2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i + 32 * u < m) v[u] = s2[i + 32 * u];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i + 32 * u < m) {
+                    if (NEG) { v[u].x = -v[u].x; v[u].y = -v[u].y; }
+                    d2[i + 32 * u] = v[u];
+                }
+        }
+    } else {
+        for (int i = lane; i < n; i += 32) dst[i] = NEG ? -src[i] : src[i];
+    }
+}
+
 // KineticEnergy (:535-542): ke += p*p/2.0 in index order.  `buf` is the warp's
 // shared scratch of n doubles.
 __device__ __forceinline__ double warpKinetic(const double* __restrict__ p, double* buf, int n, int lane) {
@@ -274,7 +301,7 @@ kHmcBegin(HmcArrays a, int n, int chains, double alpha, uint64_t seed, uint32_t 
             a.qProp[row + i] = __dadd_rn(a.qAcc[row + i], mv);
         }
     } else {
-        for (int i = lane; i < n; i += 32) a.qProp[row + i] = a.qAcc[row + i];   // :586
+        warpCopyRow<false>(a.qProp + row, a.qAcc + row, n, lane);        // :586
     }
     if (lane == 0) {
         a.sc[c] = s;
@@ -1301,19 +1328,17 @@ kHmcAccept(HmcArrays a, int n, int chains, uint64_t seed, uint32_t chainOffset, 
     const double trial = -log(u);                                         // :347
     const bool reject = (s.deltaH > trial) || !isfinite(s.deltaH);        // :348
     if (reject) {
-        for (int i = lane; i < n; i += 32) a.pAcc[row + i] = -a.pAcc[row + i];            // :364-366
+        warpCopyRow<true>(a.pAcc + row, a.pAcc + row, n, lane);          // :364-366
         s.acceptance = __ddiv_rn(__dmul_rn(s.acceptance, 4999.0), 5000.0);               // :367
     } else {
-        for (int i = lane; i < n; i += 32) {                              // :380-383
-            a.qAcc[row + i] = a.qProp[row + i];
-            a.pAcc[row + i] = a.pProp[row + i];
-        }
+        warpCopyRow<false>(a.qAcc + row, a.qProp + row, n, lane);        // :380-383
+        warpCopyRow<false>(a.pAcc + row, a.pProp + row, n, lane);
         s.accPotential = s.propPotential;                                 // :384
         s.acceptance = __ddiv_rn(__dadd_rn(__dmul_rn(s.acceptance, 4999.0), 1.0), 5000.0);   // :386
     }
     __syncwarp();
     if (s.accPotential < s.centralPotential) {                            // :393-395
-        for (int i = lane; i < n; i += 32) a.central[row + i] = a.qAcc[row + i];
+        warpCopyRow<false>(a.central + row, a.qAcc + row, n, lane);
         s.centralPotential = s.accPotential;
     }
     if (lane == 0) a.sc[c] = s;
@@ -1325,8 +1350,7 @@ kHmcAccept(HmcArrays a, int n, int chains, uint64_t seed, uint32_t chainOffset, 
             if (tr.leapfrog) tr.leapfrog[r] = s.leapFrogSteps;
             if (tr.accepted) tr.accepted[r] = reject ? 0 : 1;
         }
-        if (tr.points)
-            for (int i = lane; i < n; i += 32) tr.points[r * n + i] = a.qAcc[row + i];
+        if (tr.points) warpCopyRow<false>(tr.points + r * n, a.qAcc + row, n, lane);
     }
 }
 
