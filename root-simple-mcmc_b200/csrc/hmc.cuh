@@ -245,47 +245,68 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 kHmcBegin(HmcArrays a, int n, int chains, double alpha, uint64_t seed, uint32_t chainOffset,
           uint32_t step) {
     extern __shared__ double smemD[];
+    __shared__ double kinetic[kWarpsPerBlock];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int c = blockIdx.x * kWarpsPerBlock + warp;
-    if (c >= chains) return;
     double* buf = smemD + (size_t)warp * n;
-    HmcScalars s = a.sc[c];
-    if (!s.started || s.status != 0) {
-        if (lane == 0) a.leapSteps[c] = -1;
-        return;
+    HmcScalars s;
+    bool run = c < chains;                                                // (the same for the whole warp)
+    if (run) {
+        s = a.sc[c];
+        run = s.started && s.status == 0;
+        if (!run && lane == 0) a.leapSteps[c] = -1;
     }
     const size_t row = (size_t)c * n;
     const uint32_t gchain = chainOffset + (uint32_t)c;
-    s.stepCount += 1;                                                     // :286
     // ProposeMomentum, :554-570.  alpha has been clamped on the host the way
-    // the reference clamps its member (:558, :565).
+    // the reference clamps its member (:558, :565).  The terms p*p/2.0 of KineticEnergy (:535-542)
+    // go to shared memory as the momenta are made.
     uint32_t slot = 0;
-    if (alpha >= 1.0) {
-        for (int i = lane; i < n; i += 32) {
-            const double p = __ddiv_rn(a.pAcc[row + i], alpha);
-            a.pProp[row + i] = p;
-            a.p0[row + i] = p;
-        }
-    } else {
-        const double w = __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(alpha, alpha)));
-        for (int pr = lane; 2 * pr < n; pr += 32) {
-            // slots 2 pr and 2 pr + 1: the two branches of one Box-Muller block (smcmc_rng.h)
-            double z0 = 0.0, z1 = 0.0;
-            smcmc_normal_pair(seed, gchain, step, (uint32_t)pr, SMCMC_STREAM_STEP, &z0, &z1);
-            for (int h = 0; h < 2; ++h) {
-                const int i = 2 * pr + h;
-                if (i >= n) break;
-                const double g = __dadd_rn(0.0, __dmul_rn(1.0, h ? z1 : z0));   // Gaus(0,1)
-                const double p = __dadd_rn(__dmul_rn(alpha, a.pAcc[row + i]), __dmul_rn(w, g));
+    if (run) {
+        s.stepCount += 1;                                                 // :286
+        if (alpha >= 1.0) {
+            for (int i = lane; i < n; i += 32) {
+                const double p = __ddiv_rn(a.pAcc[row + i], alpha);
                 a.pProp[row + i] = p;
-                a.p0[row + i] = p;                                        // :587
+                a.p0[row + i] = p;
+                buf[i] = __ddiv_rn(__dmul_rn(p, p), 2.0);
             }
+        } else {
+            const double w = __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(alpha, alpha)));
+            for (int pr = lane; 2 * pr < n; pr += 32) {
+                // the accepted momenta first: their load is under way while the normals are made
+                const int i0 = 2 * pr;
+                const bool two = i0 + 1 < n;
+                const double pa0 = a.pAcc[row + i0], pa1 = two ? a.pAcc[row + i0 + 1] : 0.0;
+                // slots 2 pr and 2 pr + 1: the two branches of one Box-Muller block (smcmc_rng.h)
+                double z0 = 0.0, z1 = 0.0;
+                smcmc_normal_pair(seed, gchain, step, (uint32_t)pr, SMCMC_STREAM_STEP, &z0, &z1);
+                const double g0 = __dadd_rn(0.0, __dmul_rn(1.0, z0));     // Gaus(0,1)
+                const double p0 = __dadd_rn(__dmul_rn(alpha, pa0), __dmul_rn(w, g0));
+                a.pProp[row + i0] = p0;
+                a.p0[row + i0] = p0;                                      // :587
+                buf[i0] = __ddiv_rn(__dmul_rn(p0, p0), 2.0);
+                if (two) {
+                    const double g1 = __dadd_rn(0.0, __dmul_rn(1.0, z1));
+                    const double p1 = __dadd_rn(__dmul_rn(alpha, pa1), __dmul_rn(w, g1));
+                    a.pProp[row + i0 + 1] = p1;
+                    a.p0[row + i0 + 1] = p1;
+                    buf[i0 + 1] = __ddiv_rn(__dmul_rn(p1, p1), 2.0);
+                }
+            }
+            slot = (uint32_t)n;
         }
-        slot = (uint32_t)n;
     }
-    __syncwarp();
-    s.initialKinetic = warpKinetic(a.pProp + row, buf, n, lane);          // :292
+    // KineticEnergy is a sum in index order: one dependent chain of n additions per chain.  The
+    // block's chains take one LANE each of warp 0 (rows n doubles apart: different banks) instead of
+    // every warp walking its own chain with all 32 lanes in step -- a quarter of the instructions,
+    // which were two fifths of this kernel's.
+    __syncthreads();
+    if (warp == 0 && lane < kWarpsPerBlock) kinetic[lane] = warpSeqSum(smemD + (size_t)lane * n, n);
+    __syncthreads();
+    if (!run) return;
+    s.initialKinetic = kinetic[warp];                                     // :292
     {                                                                     // :297-298
         const double lo = __dmul_rn(0.9, fabs(s.meanEpsilon));
         const double hi = __dmul_rn(1.1, fabs(s.meanEpsilon));
