@@ -160,16 +160,6 @@ __device__ __forceinline__ void warpCopyRow(double* dst, const double* src, int 
     }
 }
 
-// KineticEnergy (:535-542): ke += p*p/2.0 in index order.  `buf` is the warp's
-// shared scratch of n doubles.
-__device__ __forceinline__ double warpKinetic(const double* __restrict__ p, double* buf, int n, int lane) {
-    for (int i = lane; i < n; i += 32) buf[i] = __ddiv_rn(__dmul_rn(p[i], p[i]), 2.0);
-    __syncwarp();
-    const double ke = warpSeqSum(buf, n);
-    __syncwarp();
-    return ke;
-}
-
 // ---------------------------------------------------------------------------
 // Start (:210-269); the likelihood of the starting points is in llh[].
 // ---------------------------------------------------------------------------
@@ -544,15 +534,31 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 kHmcPost(HmcArrays a, int n, int chains, const double* __restrict__ llhProp, double covWindow,
          int countGradients /* the fused leap-frog launches do not count: steps + 1 gradients were made (:469) */) {
     extern __shared__ double smemD[];
+    __shared__ double kinetic[kWarpsPerBlock];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int c = blockIdx.x * kWarpsPerBlock + warp;
-    if (c >= chains) return;
     double* buf = smemD + (size_t)warp * n;
-    HmcScalars s = a.sc[c];
-    if (!s.started || s.status != 0) return;
     const size_t row = (size_t)c * n;
     const size_t tri = (size_t)n * (n + 1) / 2;
+    // the kinetic energy of the proposed momenta (:326): terms by the chain's warp, the ordered sums
+    // one lane per chain (as in kHmcBegin)
+    HmcScalars s;
+    bool run = c < chains;
+    if (run) {
+        s = a.sc[c];
+        run = s.started && s.status == 0;
+    }
+    if (run)
+        for (int i = lane; i < n; i += 32) {
+            const double p = a.pProp[row + i];
+            buf[i] = __ddiv_rn(__dmul_rn(p, p), 2.0);
+        }
+    __syncthreads();
+    if (warp == 0 && lane < kWarpsPerBlock) kinetic[lane] = warpSeqSum(smemD + (size_t)lane * n, n);
+    __syncthreads();
+    if (!run) return;
+    const double proposedKinetic = kinetic[warp];
     s.needUpdate = 0;
     if (countGradients && s.steps >= 1) s.gradientCount += s.steps + 1;
     if (lane == 0) a.exxtT[c] = __longlong_as_double(-1ll);                // NaN: no UpdateCovariance this step
@@ -576,7 +582,6 @@ kHmcPost(HmcArrays a, int n, int chains, const double* __restrict__ llhProp, dou
             if (s.meanEpsilon > 0) s.meanEpsilon = __dmul_rn(s.meanEpsilon, 0.99);
         }
     }
-    const double proposedKinetic = warpKinetic(a.pProp + row, buf, n, lane);   // :326
     s.potentialCount += 1;                                                // :327
     s.propPotential = -llhProp[c];
     const double proposedH = __dadd_rn(s.propPotential, proposedKinetic);  // :333-334
