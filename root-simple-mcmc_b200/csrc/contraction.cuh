@@ -36,9 +36,12 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // [64][16 + pad]; rows past `rows` and columns past `n` are zero.  Rows start on
 // 16-byte boundaries when n is even (VEC16: 16-byte cp.async, 4 per thread);
 // otherwise 8-byte copies.
+// rowMap (shared memory, 64 entries, or null): tile row r is row rowMap[r] of the matrix (-1: no row)
+// instead of row0 + r -- the rows of a tile need not be neighbours (kHmcLeapDmma, chains ordered by
+// trajectory length).
 template <bool VEC16>
 __device__ __forceinline__ void dmmaLoadTile(double (*dst)[kDmmaBK + kDmmaPad], const double* __restrict__ src,
-                                             int row0, int rows, int k0, int n, int tid) {
+                                             int row0, int rows, int k0, int n, int tid, const int* rowMap = nullptr) {
     if (VEC16) {
         // 64 rows x 8 pairs = 512 16-byte pieces, 128 threads: 4 each
 #pragma unroll
@@ -46,11 +49,12 @@ __device__ __forceinline__ void dmmaLoadTile(double (*dst)[kDmmaBK + kDmmaPad], 
             const int idx = p * 128 + tid;               // 0..511
             const int r = idx >> 3, k = (idx & 7) * 2;
             double* d = &dst[r][k];
-            if (row0 + r < rows && k0 + k + 1 < n) {
+            const int row = rowMap ? rowMap[r] : (row0 + r < rows ? row0 + r : -1);
+            if (row >= 0 && k0 + k + 1 < n) {
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(d)),
-                             "l"(src + (size_t)(row0 + r) * n + k0 + k) : "memory");
+                             "l"(src + (size_t)row * n + k0 + k) : "memory");
             } else {
-                d[0] = (row0 + r < rows && k0 + k < n) ? src[(size_t)(row0 + r) * n + k0 + k] : 0.0;
+                d[0] = (row >= 0 && k0 + k < n) ? src[(size_t)row * n + k0 + k] : 0.0;
                 d[1] = 0.0;
             }
         }
@@ -60,9 +64,10 @@ __device__ __forceinline__ void dmmaLoadTile(double (*dst)[kDmmaBK + kDmmaPad], 
             const int idx = p * 128 + tid;               // 0..1023
             const int r = idx >> 4, k = idx & 15;
             double* d = &dst[r][k];
-            if (row0 + r < rows && k0 + k < n) {
+            const int row = rowMap ? rowMap[r] : (row0 + r < rows ? row0 + r : -1);
+            if (row >= 0 && k0 + k < n) {
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(d)),
-                             "l"(src + (size_t)(row0 + r) * n + k0 + k) : "memory");
+                             "l"(src + (size_t)row * n + k0 + k) : "memory");
             } else {
                 *d = 0.0;
             }
@@ -79,7 +84,8 @@ constexpr size_t kDmmaSmemBytes = (size_t)kDmmaStages * kDmmaStageDoubles * size
 
 template <bool VEC16>
 __device__ __forceinline__ void dmmaMainloop(double (&acc)[4][4][2], double* smem, const double* __restrict__ x,
-                                             const double* __restrict__ err, int c0, int chains, int i0, int n, int tid) {
+                                             const double* __restrict__ err, int c0, int chains, int i0, int n, int tid,
+                                             const int* rowMap = nullptr) {
     typedef double (*Tile)[kDmmaBK + kDmmaPad];
     const int lane = tid & 31, warp = tid >> 5;
     const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
@@ -92,7 +98,7 @@ __device__ __forceinline__ void dmmaMainloop(double (&acc)[4][4][2], double* sme
 #pragma unroll
     for (int st = 0; st < kDmmaStages - 1; ++st) {
         if (st < steps) {
-            dmmaLoadTile<VEC16>((Tile)(smem + st * kDmmaStageDoubles), x, c0, chains, st * kDmmaBK, n, tid);
+            dmmaLoadTile<VEC16>((Tile)(smem + st * kDmmaStageDoubles), x, c0, chains, st * kDmmaBK, n, tid, rowMap);
             dmmaLoadTile<VEC16>((Tile)(smem + st * kDmmaStageDoubles + kDmmaBM * (kDmmaBK + kDmmaPad)), err, i0, n, st * kDmmaBK, n, tid);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -103,7 +109,7 @@ __device__ __forceinline__ void dmmaMainloop(double (&acc)[4][4][2], double* sme
         const int nxt = s + kDmmaStages - 1;
         if (nxt < steps) {
             double* base = smem + (nxt % kDmmaStages) * kDmmaStageDoubles;
-            dmmaLoadTile<VEC16>((Tile)base, x, c0, chains, nxt * kDmmaBK, n, tid);
+            dmmaLoadTile<VEC16>((Tile)base, x, c0, chains, nxt * kDmmaBK, n, tid, rowMap);
             dmmaLoadTile<VEC16>((Tile)(base + kDmmaBM * (kDmmaBK + kDmmaPad)), err, i0, n, nxt * kDmmaBK, n, tid);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -226,9 +232,13 @@ struct LeapFused {
     int blocks;              // column blocks = gridDim.x
     double* endPartial;      // [chains][blocks] or null: x . (Error x) over each column block at the END point of a chain's
                              // trajectory (its last gradient, k == steps) -- the potential there without another GEMM
+    const int* order;        // null, or the chains ordered by trajectory length, longest first: row r of the launch is
+                             // chain order[r]
+    int gemmTiles;           // with `order`: the first gemmTiles row tiles (blockIdx.y) hold every chain that still takes
+                             // part in gradient k; row tiles behind them (launched for k = 0 only) copy qIn to qOut
 };
 
-template <bool VEC16>
+template <bool VEC16, bool ORDERED>
 __global__ void __launch_bounds__(128, 3)
 kHmcLeapDmma(const double* __restrict__ err, LeapFused f, int k, int chains, int n) {
     extern __shared__ __align__(16) double dmmaSmem[];
@@ -236,9 +246,41 @@ kHmcLeapDmma(const double* __restrict__ err, LeapFused f, int k, int chains, int
     const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
     const int c0 = blockIdx.y * kDmmaBM, i0 = blockIdx.x * kDmmaBN;
     const int g = lane >> 2, q = lane & 3;
+    // ORDERED -- ragged trajectory lengths: the launch's rows are the chains in order of length
+    // (f.order), so the chains that still run fill the first row tiles, and only those are launched:
+    // the unordered launch runs the whole GEMM for rows that ignore its result.  A chain's last gradient
+    // is taken at its end point and copies it to the second position buffer (no drift), so both buffers
+    // hold it from then on and later launches need not touch the row; chains that never run are copied
+    // once, by the row tiles behind the running ones in the launch for k = 0.  A row's arithmetic does not
+    // depend on its neighbours: the chains come out bit for bit as without the ordering.
+    __shared__ int rowChain[ORDERED ? kDmmaBM : 1];
+    if (ORDERED) {
+        if (tid < kDmmaBM) {
+            const int r = c0 + tid;
+            rowChain[tid] = r < chains ? f.order[r] : -1;
+        }
+        __syncthreads();
+    }
+    // chain of tile row r, or -1
+    auto chainOf = [&](int r) -> int { return ORDERED ? rowChain[r] : (c0 + r < chains ? c0 + r : -1); };
+    if (ORDERED && (int)blockIdx.y >= f.gemmTiles) {
+        for (int r = warp * (kDmmaBM / 4); r < (warp + 1) * (kDmmaBM / 4); ++r) {
+            const int c = rowChain[r];
+            if (c < 0) continue;
+            const size_t base = (size_t)c * n + i0;
+            if (VEC16) {
+                if (i0 + 2 * lane < n)
+                    *reinterpret_cast<double2*>(f.qOut + base + 2 * lane) = *reinterpret_cast<const double2*>(f.qIn + base + 2 * lane);
+            } else {
+                if (i0 + lane < n) f.qOut[base + lane] = f.qIn[base + lane];
+                if (i0 + lane + 32 < n) f.qOut[base + lane + 32] = f.qIn[base + lane + 32];
+            }
+        }
+        return;
+    }
     // the U-turn test of the PREVIOUS gradient (k - 1 >= 1), one thread per chain of this row of CTAs
-    if (blockIdx.x == 0 && k >= 2 && tid < kDmmaBM && c0 + tid < chains) {
-        const int c = c0 + tid;
+    if (blockIdx.x == 0 && k >= 2 && tid < kDmmaBM && chainOf(tid) >= 0) {
+        const int c = chainOf(tid);
         const int st = f.leapSteps[c];
         if (st >= 1 && k - 1 <= st - 1) {
             const double* u = f.uturn + ((size_t)((k - 1) & 1) * chains + c) * f.blocks;
@@ -248,7 +290,7 @@ kHmcLeapDmma(const double* __restrict__ err, LeapFused f, int k, int chains, int
         }
     }
     double acc[4][4][2];
-    dmmaMainloop<VEC16>(acc, dmmaSmem, f.qIn, err, c0, chains, i0, n, tid);
+    dmmaMainloop<VEC16>(acc, dmmaSmem, f.qIn, err, c0, chains, i0, n, tid, ORDERED ? rowChain : nullptr);
     // The last gradient of a chain's trajectory is taken AT the proposed point (no drift follows,
     // :646-648): x . (Error x) over this column block is the block's share of the potential there --
     // the partial sum kDummyContractDmma (mode 1) would produce from the same accumulators, formed the
@@ -259,15 +301,15 @@ kHmcLeapDmma(const double* __restrict__ err, LeapFused f, int k, int chains, int
         int rowEnd[4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-            const int c = c0 + wm + a * 8 + g;
-            const int st = c < chains ? f.leapSteps[c] : -1;
+            const int c = chainOf(wm + a * 8 + g);
+            const int st = c >= 0 ? f.leapSteps[c] : -1;
             rowEnd[a] = (st >= 1 && k == st) ? 1 : 0;
             mine = mine || rowEnd[a];
         }
         if (__syncthreads_or(mine ? 1 : 0)) {
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
-                const int c = c0 + wm + a * 8 + g;
+                const int c = chainOf(wm + a * 8 + g);
                 double sum = 0.0;
                 if (rowEnd[a]) {
 #pragma unroll
@@ -282,9 +324,10 @@ kHmcLeapDmma(const double* __restrict__ err, LeapFused f, int k, int chains, int
                 if (q == 0) part[wm + a * 8 + g][warp & 1] = sum;
             }
             __syncthreads();
-            if (tid < kDmmaBM && c0 + tid < chains) {
-                const int st = f.leapSteps[c0 + tid];
-                if (st >= 1 && k == st) f.endPartial[(size_t)(c0 + tid) * f.blocks + blockIdx.x] = part[tid][0] + part[tid][1];
+            if (tid < kDmmaBM && chainOf(tid) >= 0) {
+                const int c = chainOf(tid);
+                const int st = f.leapSteps[c];
+                if (st >= 1 && k == st) f.endPartial[(size_t)c * f.blocks + blockIdx.x] = part[tid][0] + part[tid][1];
             }
         }
     }
@@ -323,15 +366,15 @@ kHmcLeapDmma(const double* __restrict__ err, LeapFused f, int k, int chains, int
         int st[kBatch];
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
-            const int c = c0 + r0 + u;
-            st[u] = c < chains ? f.leapSteps[c] : -1;
+            const int c = chainOf(r0 + u);
+            st[u] = c >= 0 ? f.leapSteps[c] : -1;
             const bool live = st[u] >= 1 && k <= st[u];
             eps[u] = live ? f.epsilon[(size_t)c * f.scalarStride] : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
-            const int c = c0 + r0 + u;
-            if (c >= chains) continue;
+            const int c = chainOf(r0 + u);
+            if (c < 0) continue;
             const bool live = st[u] >= 1 && k <= st[u];
             const bool half = (k == 0) || (k == st[u]);
             const size_t base = (size_t)c * n + i0;
@@ -364,8 +407,8 @@ kHmcLeapDmma(const double* __restrict__ err, LeapFused f, int k, int chains, int
         }
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
-            const int c = c0 + r0 + u;
-            if (c >= chains) continue;
+            const int c = chainOf(r0 + u);
+            if (c < 0) continue;
             const bool live = st[u] >= 1 && k <= st[u];
             const bool half = (k == 0) || (k == st[u]);
             const bool drift = live && k < st[u];
@@ -411,13 +454,23 @@ kHmcLeapDmma(const double* __restrict__ err, LeapFused f, int k, int chains, int
 inline void launchHmcLeapDmma(cudaStream_t stream, const double* err, const LeapFused& f, int k, int chains, int n) {
     static bool ready = false;
     if (!ready) {
-        cudaFuncSetAttribute(kHmcLeapDmma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
-        cudaFuncSetAttribute(kHmcLeapDmma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+        cudaFuncSetAttribute(kHmcLeapDmma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+        cudaFuncSetAttribute(kHmcLeapDmma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+        cudaFuncSetAttribute(kHmcLeapDmma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+        cudaFuncSetAttribute(kHmcLeapDmma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
         ready = true;
     }
-    dim3 grid((n + kDmmaBN - 1) / kDmmaBN, (chains + kDmmaBM - 1) / kDmmaBM);
-    if ((n & 1) == 0) kHmcLeapDmma<true><<<grid, 128, kDmmaSmemBytes, stream>>>(err, f, k, chains, n);
-    else kHmcLeapDmma<false><<<grid, 128, kDmmaSmemBytes, stream>>>(err, f, k, chains, n);
+    const int rowTiles = (chains + kDmmaBM - 1) / kDmmaBM;
+    // ordered: only the row tiles of the chains that still run (and, for k = 0, the copy of the others)
+    dim3 grid((n + kDmmaBN - 1) / kDmmaBN, f.order ? (k == 0 ? rowTiles : f.gemmTiles) : rowTiles);
+    if (grid.y == 0) return;
+    if (f.order) {
+        if ((n & 1) == 0) kHmcLeapDmma<true, true><<<grid, 128, kDmmaSmemBytes, stream>>>(err, f, k, chains, n);
+        else kHmcLeapDmma<false, true><<<grid, 128, kDmmaSmemBytes, stream>>>(err, f, k, chains, n);
+    } else {
+        if ((n & 1) == 0) kHmcLeapDmma<true, false><<<grid, 128, kDmmaSmemBytes, stream>>>(err, f, k, chains, n);
+        else kHmcLeapDmma<false, false><<<grid, 128, kDmmaSmemBytes, stream>>>(err, f, k, chains, n);
+    }
 }
 
 // L[c] = -1/2 sum over the column blocks of the partial sums.

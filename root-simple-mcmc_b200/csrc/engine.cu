@@ -63,6 +63,8 @@ struct HmcHost {
     DeviceBuffer<double> qAcc, pAcc, qProp, pProp, p0, grad, central, average, exxt, exxtT, estErr, repairedDiag;
     DeviceBuffer<double> llh, fdWork, fdLlh, avgPts, avgLlh;
     DeviceBuffer<double> qAlt, uturn;    // fused leap-frog stage (kHmcLeapDmma): the second q buffer, the U-turn partials
+    DeviceBuffer<int> order;             // ... and the chains ordered by trajectory length (ragged ensembles)
+    int* hostSteps = nullptr;            // pinned, 2 x chains: the trajectory lengths read back, the order sent
     DeviceBuffer<HmcScalars> sc;
     DeviceBuffer<int> leapSteps, counters, updateList;
     // deferred fEXXT update (hmc.cuh, kHmcExxtFlush): 0 = every step
@@ -78,6 +80,7 @@ struct HmcHost {
     int* hostCounters = nullptr;     // pinned
     ~HmcHost() {
         if (hostCounters) cudaFreeHost(hostCounters);
+        if (hostSteps) cudaFreeHost(hostSteps);
     }
 };
 

@@ -236,12 +236,18 @@ void hmcStepOnce(smcmc_engine* e, int type, const HmcTraceDev& tr, int traceStep
     CUDA_CHECK(cudaMemsetAsync(h.counters.get(), 0, 3 * sizeof(int), e->stream));
     kHmcBegin<<<blocks, threads, smem, e->stream>>>(a, n, E, h.alpha, e->cfg.seed, e->cfg.chain_offset, e->stepIndex);
     e->launched();
-    const int maxSteps = hmcReadCounter(e, 0);
-    const int countPotentials = (mode == kGradFinite) ? 2 * n : 0;
     // dense Gaussian on the tensor cores: gradient, kick and drift of a leap-frog stage in ONE launch
     // (contraction.cuh, kHmcLeapDmma); SMCMC_HMC_NO_FUSE=1 keeps gradient kernel + kHmcKickDrift
     const bool fused = mode == kGradUser && e->cfg.likelihood == SMCMC_LLH_DUMMY && e->dummyMode == SMCMC_DUMMY_TENSOR &&
                        e->errDim == n && !std::getenv("SMCMC_HMC_NO_FUSE");
+    // (the trajectory lengths come back with the counter: one synchronisation for both)
+    const bool wantOrder = fused && !std::getenv("SMCMC_HMC_NO_ORDER");
+    if (wantOrder) {
+        if (!h.hostSteps) CUDA_CHECK(cudaMallocHost((void**)&h.hostSteps, (size_t)2 * E * sizeof(int)));
+        CUDA_CHECK(cudaMemcpyAsync(h.hostSteps, h.leapSteps.get(), (size_t)E * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    }
+    const int maxSteps = hmcReadCounter(e, 0);
+    const int countPotentials = (mode == kGradFinite) ? 2 * n : 0;
     // ... and when every running chain has a trajectory, the potential at its end comes out of the
     // chain's last gradient launch (LeapFused::endPartial) instead of a GEMM of its own
     bool potentialDone = false;
@@ -261,9 +267,51 @@ void hmcStepOnce(smcmc_engine* e, int type, const HmcTraceDev& tr, int traceStep
         f.uturn = h.uturn.get();
         f.blocks = colBlocks;
         f.endPartial = endPotential ? e->dummyPartials.get() : nullptr;
+        // Ragged trajectory lengths (each chain tunes its own, :302-323): the launches take the chains in
+        // order of length, so that the row tiles behind the chains that still run skip the GEMM
+        // (kHmcLeapDmma).  The lengths are read back next to the counter above; ordering them is a
+        // counting sort on the host.  Not worth it when (nearly) all tiles stay busy to the end.
+        std::vector<int> gemmTiles;
+        f.order = nullptr;
+        f.gemmTiles = 0;
+        if (wantOrder) {
+            std::vector<int> atLeast(maxSteps + 2, 0);             // atLeast[k] = chains with length >= k
+            for (int c = 0; c < E; ++c) {
+                const int st = h.hostSteps[c];
+                if (st >= 1) atLeast[std::min(st, maxSteps)] += 1;
+            }
+            for (int k = maxSteps - 1; k >= 1; --k) atLeast[k] += atLeast[k + 1];
+            const long long allTiles = (long long)(maxSteps + 1) * ceilDiv(E, kDmmaBM);
+            long long busyTiles = 0;
+            gemmTiles.resize(maxSteps + 1);
+            for (int k = 0; k <= maxSteps; ++k) {
+                gemmTiles[k] = ceilDiv(atLeast[std::max(k, 1)], kDmmaBM);
+                busyTiles += gemmTiles[k];
+            }
+            if (busyTiles * 100 <= allTiles * 97 || std::getenv("SMCMC_HMC_ORDER_ALWAYS")) {
+                // longest first, equal lengths in chain order; chains without a trajectory last
+                int* order = h.hostSteps + E;
+                std::vector<int> next(maxSteps + 2, 0);            // first position of each length
+                int pos = 0;
+                for (int st = maxSteps; st >= 1; --st) {
+                    next[st] = pos;
+                    pos += atLeast[st] - atLeast[st + 1];
+                }
+                int tail = pos;
+                for (int c = 0; c < E; ++c) {
+                    const int st = h.hostSteps[c];
+                    if (st >= 1) order[next[std::min(st, maxSteps)]++] = c;
+                    else order[tail++] = c;
+                }
+                h.order.reserve(E);
+                CUDA_CHECK(cudaMemcpyAsync(h.order.get(), order, (size_t)E * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+                f.order = h.order.get();
+            }
+        }
         for (int k = 0; k <= maxSteps; ++k) {
             f.qIn = h.qProp.get();
             f.qOut = h.qAlt.get();
+            if (f.order) f.gemmTiles = gemmTiles[k];
             launchHmcLeapDmma(e->stream, e->errMatrix.get(), f, k, E, n);
             e->launched();
             h.qProp.swap(h.qAlt);                                        // the proposed positions are in the buffer just written

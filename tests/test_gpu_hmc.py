@@ -242,7 +242,7 @@ def test_pooled_covariance_is_the_default_for_large_ensembles_only():
                 eng.hmc_get("pooled_scalars")
 
 
-@pytest.mark.parametrize("n,E", [(130, 70), (37, 130), (500, 96)])
+@pytest.mark.parametrize("n,E", [(130, 70), (37, 130), (500, 96), (64, 700)])
 def test_fused_leapfrog_stage_equals_gradient_plus_kick_drift(monkeypatch, n, E):
     """TENSOR mode runs a leap-frog stage as ONE launch (kHmcLeapDmma: the gradient GEMM with the
     kick, the drift and the U-turn partial sums in its epilogue).  Against the same mode with the
@@ -253,9 +253,14 @@ def test_fused_leapfrog_stage_equals_gradient_plus_kick_drift(monkeypatch, n, E)
     from smcmc_b200 import binding as b
     prec = hmc_error_matrix("spd%d" % n)
     runs = {}
-    for fused in (1, 0):
+    # fused = 2: the fused launches take the chains in order of trajectory length (rows behind the
+    # chains that still run skip the GEMM) even where the engine would not bother
+    for fused in (1, 0, 2):
+        monkeypatch.delenv("SMCMC_HMC_ORDER_ALWAYS", raising=False)
         if fused:
             monkeypatch.delenv("SMCMC_HMC_NO_FUSE", raising=False)
+            if fused == 2:
+                monkeypatch.setenv("SMCMC_HMC_ORDER_ALWAYS", "1")
         else:
             monkeypatch.setenv("SMCMC_HMC_NO_FUSE", "1")
         h = smcmc_b200.Engine(smcmc_b200.LLH_DUMMY, n, E, seed=6)
@@ -271,5 +276,9 @@ def test_fused_leapfrog_stage_equals_gradient_plus_kick_drift(monkeypatch, n, E)
         runs[fused] = tr
     for k in ("potential", "points", "mean_epsilon", "leapfrog", "accepted", "scalars", "momentum"):
         assert np.array_equal(runs[1][k], runs[0][k]), k
+        assert np.array_equal(runs[2][k], runs[0][k]), k
     assert runs[1]["launches"] < 0.62 * runs[0]["launches"]       # one launch per stage instead of two
     assert np.abs(runs[1]["leapfrog"]).max() > 10 and runs[1]["accepted"].sum() > 0
+    if E >= 700:                                                  # the ordering has something to order
+        lf = np.abs(runs[1]["leapfrog"])
+        assert max(len(np.unique(lf[s])) for s in range(lf.shape[0])) > 1
