@@ -36,12 +36,9 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // [64][16 + pad]; rows past `rows` and columns past `n` are zero.  Rows start on
 // 16-byte boundaries when n is even (VEC16: 16-byte cp.async, 4 per thread);
 // otherwise 8-byte copies.
-// rowMap (shared memory, 64 entries, or null): tile row r is row rowMap[r] of the matrix (-1: no row)
-// instead of row0 + r -- the rows of a tile need not be neighbours (kHmcLeapDmma, chains ordered by
-// trajectory length).
 template <bool VEC16>
 __device__ __forceinline__ void dmmaLoadTile(double (*dst)[kDmmaBK + kDmmaPad], const double* __restrict__ src,
-                                             int row0, int rows, int k0, int n, int tid, const int* rowMap = nullptr) {
+                                             int row0, int rows, int k0, int n, int tid) {
     if (VEC16) {
         // 64 rows x 8 pairs = 512 16-byte pieces, 128 threads: 4 each
 #pragma unroll
@@ -49,7 +46,45 @@ __device__ __forceinline__ void dmmaLoadTile(double (*dst)[kDmmaBK + kDmmaPad], 
             const int idx = p * 128 + tid;               // 0..511
             const int r = idx >> 3, k = (idx & 7) * 2;
             double* d = &dst[r][k];
-            const int row = rowMap ? rowMap[r] : (row0 + r < rows ? row0 + r : -1);
+            if (row0 + r < rows && k0 + k + 1 < n) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(d)),
+                             "l"(src + (size_t)(row0 + r) * n + k0 + k) : "memory");
+            } else {
+                d[0] = (row0 + r < rows && k0 + k < n) ? src[(size_t)(row0 + r) * n + k0 + k] : 0.0;
+                d[1] = 0.0;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            const int idx = p * 128 + tid;               // 0..1023
+            const int r = idx >> 4, k = idx & 15;
+            double* d = &dst[r][k];
+            if (row0 + r < rows && k0 + k < n) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(d)),
+                             "l"(src + (size_t)(row0 + r) * n + k0 + k) : "memory");
+            } else {
+                *d = 0.0;
+            }
+        }
+    }
+}
+
+// The same tile with its rows GATHERED: tile row r is row rowMap[r] of the matrix (shared memory, 64
+// entries; -1: no row) -- the rows of a tile need not be neighbours (kHmcLeapDmma, chains ordered by
+// trajectory length).  A function of its own: with the row map as an optional argument of the loader
+// above the compiler no longer kept the contiguous rows' addresses in registers across the K loop
+// (156 -> 132 registers and a slower kernel for everybody).
+template <bool VEC16>
+__device__ __forceinline__ void dmmaLoadTileRows(double (*dst)[kDmmaBK + kDmmaPad], const double* __restrict__ src,
+                                                 const int* rowMap, int k0, int n, int tid) {
+    if (VEC16) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int idx = p * 128 + tid;
+            const int r = idx >> 3, k = (idx & 7) * 2;
+            double* d = &dst[r][k];
+            const int row = rowMap[r];
             if (row >= 0 && k0 + k + 1 < n) {
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(d)),
                              "l"(src + (size_t)row * n + k0 + k) : "memory");
@@ -61,10 +96,10 @@ __device__ __forceinline__ void dmmaLoadTile(double (*dst)[kDmmaBK + kDmmaPad], 
     } else {
 #pragma unroll
         for (int p = 0; p < 8; ++p) {
-            const int idx = p * 128 + tid;               // 0..1023
+            const int idx = p * 128 + tid;
             const int r = idx >> 4, k = idx & 15;
             double* d = &dst[r][k];
-            const int row = rowMap ? rowMap[r] : (row0 + r < rows ? row0 + r : -1);
+            const int row = rowMap[r];
             if (row >= 0 && k0 + k < n) {
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(d)),
                              "l"(src + (size_t)row * n + k0 + k) : "memory");
@@ -82,7 +117,7 @@ constexpr int kDmmaStages = 3;
 constexpr int kDmmaStageDoubles = 2 * kDmmaBM * (kDmmaBK + kDmmaPad);
 constexpr size_t kDmmaSmemBytes = (size_t)kDmmaStages * kDmmaStageDoubles * sizeof(double);
 
-template <bool VEC16>
+template <bool VEC16, bool GATHER = false>
 __device__ __forceinline__ void dmmaMainloop(double (&acc)[4][4][2], double* smem, const double* __restrict__ x,
                                              const double* __restrict__ err, int c0, int chains, int i0, int n, int tid,
                                              const int* rowMap = nullptr) {
@@ -98,7 +133,8 @@ __device__ __forceinline__ void dmmaMainloop(double (&acc)[4][4][2], double* sme
 #pragma unroll
     for (int st = 0; st < kDmmaStages - 1; ++st) {
         if (st < steps) {
-            dmmaLoadTile<VEC16>((Tile)(smem + st * kDmmaStageDoubles), x, c0, chains, st * kDmmaBK, n, tid, rowMap);
+            if (GATHER) dmmaLoadTileRows<VEC16>((Tile)(smem + st * kDmmaStageDoubles), x, rowMap, st * kDmmaBK, n, tid);
+            else dmmaLoadTile<VEC16>((Tile)(smem + st * kDmmaStageDoubles), x, c0, chains, st * kDmmaBK, n, tid);
             dmmaLoadTile<VEC16>((Tile)(smem + st * kDmmaStageDoubles + kDmmaBM * (kDmmaBK + kDmmaPad)), err, i0, n, st * kDmmaBK, n, tid);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -109,7 +145,8 @@ __device__ __forceinline__ void dmmaMainloop(double (&acc)[4][4][2], double* sme
         const int nxt = s + kDmmaStages - 1;
         if (nxt < steps) {
             double* base = smem + (nxt % kDmmaStages) * kDmmaStageDoubles;
-            dmmaLoadTile<VEC16>((Tile)base, x, c0, chains, nxt * kDmmaBK, n, tid, rowMap);
+            if (GATHER) dmmaLoadTileRows<VEC16>((Tile)base, x, rowMap, nxt * kDmmaBK, n, tid);
+            else dmmaLoadTile<VEC16>((Tile)base, x, c0, chains, nxt * kDmmaBK, n, tid);
             dmmaLoadTile<VEC16>((Tile)(base + kDmmaBM * (kDmmaBK + kDmmaPad)), err, i0, n, nxt * kDmmaBK, n, tid);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -262,7 +299,8 @@ kHmcLeapDmma(const double* __restrict__ err, LeapFused f, int k, int chains, int
         __syncthreads();
     }
     // chain of tile row r, or -1
-    auto chainOf = [&](int r) -> int { return ORDERED ? rowChain[r] : (c0 + r < chains ? c0 + r : -1); };
+    auto chainOf = [&](int r) -> int { return ORDERED ? rowChain[r] : c0 + r; };
+    auto valid = [&](int c) -> bool { return ORDERED ? c >= 0 : c < chains; };      // (unordered: exactly the tests this kernel had)
     if (ORDERED && (int)blockIdx.y >= f.gemmTiles) {
         for (int r = warp * (kDmmaBM / 4); r < (warp + 1) * (kDmmaBM / 4); ++r) {
             const int c = rowChain[r];
@@ -279,7 +317,7 @@ kHmcLeapDmma(const double* __restrict__ err, LeapFused f, int k, int chains, int
         return;
     }
     // the U-turn test of the PREVIOUS gradient (k - 1 >= 1), one thread per chain of this row of CTAs
-    if (blockIdx.x == 0 && k >= 2 && tid < kDmmaBM && chainOf(tid) >= 0) {
+    if (blockIdx.x == 0 && k >= 2 && tid < kDmmaBM && valid(chainOf(tid))) {
         const int c = chainOf(tid);
         const int st = f.leapSteps[c];
         if (st >= 1 && k - 1 <= st - 1) {
@@ -290,7 +328,7 @@ kHmcLeapDmma(const double* __restrict__ err, LeapFused f, int k, int chains, int
         }
     }
     double acc[4][4][2];
-    dmmaMainloop<VEC16>(acc, dmmaSmem, f.qIn, err, c0, chains, i0, n, tid, ORDERED ? rowChain : nullptr);
+    dmmaMainloop<VEC16, ORDERED>(acc, dmmaSmem, f.qIn, err, c0, chains, i0, n, tid, rowChain);
     // The last gradient of a chain's trajectory is taken AT the proposed point (no drift follows,
     // :646-648): x . (Error x) over this column block is the block's share of the potential there --
     // the partial sum kDummyContractDmma (mode 1) would produce from the same accumulators, formed the
@@ -302,7 +340,7 @@ kHmcLeapDmma(const double* __restrict__ err, LeapFused f, int k, int chains, int
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const int c = chainOf(wm + a * 8 + g);
-            const int st = c >= 0 ? f.leapSteps[c] : -1;
+            const int st = valid(c) ? f.leapSteps[c] : -1;
             rowEnd[a] = (st >= 1 && k == st) ? 1 : 0;
             mine = mine || rowEnd[a];
         }
@@ -324,7 +362,7 @@ kHmcLeapDmma(const double* __restrict__ err, LeapFused f, int k, int chains, int
                 if (q == 0) part[wm + a * 8 + g][warp & 1] = sum;
             }
             __syncthreads();
-            if (tid < kDmmaBM && chainOf(tid) >= 0) {
+            if (tid < kDmmaBM && valid(chainOf(tid))) {
                 const int c = chainOf(tid);
                 const int st = f.leapSteps[c];
                 if (st >= 1 && k == st) f.endPartial[(size_t)c * f.blocks + blockIdx.x] = part[tid][0] + part[tid][1];
@@ -367,14 +405,14 @@ kHmcLeapDmma(const double* __restrict__ err, LeapFused f, int k, int chains, int
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
             const int c = chainOf(r0 + u);
-            st[u] = c >= 0 ? f.leapSteps[c] : -1;
+            st[u] = valid(c) ? f.leapSteps[c] : -1;
             const bool live = st[u] >= 1 && k <= st[u];
             eps[u] = live ? f.epsilon[(size_t)c * f.scalarStride] : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
             const int c = chainOf(r0 + u);
-            if (c < 0) continue;
+            if (!valid(c)) continue;
             const bool live = st[u] >= 1 && k <= st[u];
             const bool half = (k == 0) || (k == st[u]);
             const size_t base = (size_t)c * n + i0;
@@ -408,7 +446,7 @@ kHmcLeapDmma(const double* __restrict__ err, LeapFused f, int k, int chains, int
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
             const int c = chainOf(r0 + u);
-            if (c < 0) continue;
+            if (!valid(c)) continue;
             const bool live = st[u] >= 1 && k <= st[u];
             const bool half = (k == 0) || (k == st[u]);
             const bool drift = live && k < st[u];

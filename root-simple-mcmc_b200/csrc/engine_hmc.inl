@@ -61,8 +61,8 @@ void hmcAllocate(smcmc_engine* e) {
     h.sc.reserve(E);
     h.leapSteps.reserve(E);
     h.updateList.reserve(E);
-    h.counters.reserve(3);
-    CUDA_CHECK(cudaMallocHost((void**)&h.hostCounters, 3 * sizeof(int)));
+    h.counters.reserve(4);
+    CUDA_CHECK(cudaMallocHost((void**)&h.hostCounters, 4 * sizeof(int)));
     std::vector<HmcScalars> init(E);
     std::memset(init.data(), 0, sizeof(HmcScalars) * E);
     for (size_t c = 0; c < E; ++c) init[c].leapFrogSteps = 10;            // TSimpleHMC.H:133
@@ -200,8 +200,8 @@ void hmcGradient(smcmc_engine* e, HmcGradientMode mode, int k) {
 
 int hmcReadCounter(smcmc_engine* e, int which) {
     HmcHost& h = e->hmc;
-    // ([0] and [2] are written by the same kernel and read together)
-    const int first = which == 1 ? 1 : 0, count = which == 1 ? 1 : 3;
+    // ([0], [2] and [3] are written by the same kernel and read together)
+    const int first = which == 1 ? 1 : 0, count = which == 1 ? 1 : 4;
     CUDA_CHECK(cudaMemcpyAsync(h.hostCounters + first, h.counters.get() + first, count * sizeof(int),
                                cudaMemcpyDeviceToHost, e->stream));
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
@@ -233,20 +233,23 @@ void hmcStepOnce(smcmc_engine* e, int type, const HmcTraceDev& tr, int traceStep
     const int blocks = ceilDiv(E, kWarpsPerBlock), threads = kWarpsPerBlock * 32;
     const size_t smem = (size_t)kWarpsPerBlock * n * sizeof(double);
     if (h.alpha < 0.0) h.alpha = 0.0;                                     // :565
-    CUDA_CHECK(cudaMemsetAsync(h.counters.get(), 0, 3 * sizeof(int), e->stream));
+    CUDA_CHECK(cudaMemsetAsync(h.counters.get(), 0, 4 * sizeof(int), e->stream));
     kHmcBegin<<<blocks, threads, smem, e->stream>>>(a, n, E, h.alpha, e->cfg.seed, e->cfg.chain_offset, e->stepIndex);
     e->launched();
     // dense Gaussian on the tensor cores: gradient, kick and drift of a leap-frog stage in ONE launch
     // (contraction.cuh, kHmcLeapDmma); SMCMC_HMC_NO_FUSE=1 keeps gradient kernel + kHmcKickDrift
     const bool fused = mode == kGradUser && e->cfg.likelihood == SMCMC_LLH_DUMMY && e->dummyMode == SMCMC_DUMMY_TENSOR &&
                        e->errDim == n && !std::getenv("SMCMC_HMC_NO_FUSE");
-    // (the trajectory lengths come back with the counter: one synchronisation for both)
-    const bool wantOrder = fused && !std::getenv("SMCMC_HMC_NO_ORDER");
-    if (wantOrder) {
+    const int maxSteps = hmcReadCounter(e, 0);
+    // the chains' trajectory lengths are fetched only when they differ (shortest < longest)
+    const int minSteps = h.hostCounters[3] > 0 ? (1 << 20) - h.hostCounters[3] : maxSteps;
+    const bool wantOrder = fused && !std::getenv("SMCMC_HMC_NO_ORDER") &&
+                           (minSteps < maxSteps || std::getenv("SMCMC_HMC_ORDER_ALWAYS"));
+    if (wantOrder && maxSteps >= 1) {
         if (!h.hostSteps) CUDA_CHECK(cudaMallocHost((void**)&h.hostSteps, (size_t)2 * E * sizeof(int)));
         CUDA_CHECK(cudaMemcpyAsync(h.hostSteps, h.leapSteps.get(), (size_t)E * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
     }
-    const int maxSteps = hmcReadCounter(e, 0);
     const int countPotentials = (mode == kGradFinite) ? 2 * n : 0;
     // ... and when every running chain has a trajectory, the potential at its end comes out of the
     // chain's last gradient launch (LeapFused::endPartial) instead of a GEMM of its own

@@ -119,7 +119,8 @@ struct HmcArrays {
     HmcScalars* sc;
     int* leapSteps;     // copy of sc.steps for the gradient kernels
     int* counters;      // [0] max steps of this transition, [1] chains that need UpdateErrorMatrix,
-                        // [2] running chains WITHOUT a trajectory in this transition (steps < 1)
+                        // [2] running chains WITHOUT a trajectory in this transition (steps < 1),
+                        // [3] 2^20 - (shortest trajectory of this transition), 0 when there is none
     int* updateList;
     double* eigScratch; // slots of 2*n*n doubles
     int* eigLocks;
@@ -319,6 +320,7 @@ kHmcBegin(HmcArrays a, int n, int chains, double alpha, uint64_t seed, uint32_t 
         a.leapSteps[c] = s.steps;
         atomicMax(&a.counters[0], s.steps);
         if (s.steps < 1) atomicAdd(&a.counters[2], 1);
+        else atomicMax(&a.counters[3], (1 << 20) - min(s.steps, 1 << 20));
     }
 }
 
