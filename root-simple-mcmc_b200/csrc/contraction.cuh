@@ -269,6 +269,9 @@ struct LeapFused {
     int blocks;              // column blocks = gridDim.x
     double* endPartial;      // [chains][blocks] or null: x . (Error x) over each column block at the END point of a chain's
                              // trajectory (its last gradient, k == steps) -- the potential there without another GEMM
+    double* gradStart;       // null, or [chains][n]: the gradient at the START point (k = 0) is kept ...
+    double* gradEnd;         // null, or [chains][n]: ... and the one at the END point (k == steps): the next step starts at one
+                             // of the two, and its first gradient is the one kept (kHmcLeapCached)
     const int* order;        // null, or the chains ordered by trajectory length, longest first: row r of the launch is
                              // chain order[r]
     int gemmTiles;           // with `order`: the first gemmTiles row tiles (blockIdx.y) hold every chain that still takes
@@ -464,6 +467,7 @@ kHmcLeapDmma(const double* __restrict__ err, LeapFused f, int k, int chains, int
                 if (!half) dot += __dmul_rn(po[h], p0v[u][h]);
                 if (drift) qo[h] = __dadd_rn(qv[u][h], __dmul_rn(eps[u], po[h]));
             }
+            double* keep = !live ? nullptr : (k == 0 ? f.gradStart : (k == st[u] ? f.gradEnd : nullptr));
             if (VEC16) {
                 if (in[0]) {
                     double2 o;
@@ -473,6 +477,10 @@ kHmcLeapDmma(const double* __restrict__ err, LeapFused f, int k, int chains, int
                         o.x = po[0]; o.y = po[1];
                         *reinterpret_cast<double2*>(f.p + base + col[0]) = o;
                     }
+                    if (keep) {
+                        o.x = gv[u][0]; o.y = gv[u][1];
+                        *reinterpret_cast<double2*>(keep + base + col[0]) = o;
+                    }
                 }
             } else {
 #pragma unroll
@@ -480,11 +488,70 @@ kHmcLeapDmma(const double* __restrict__ err, LeapFused f, int k, int chains, int
                     if (!in[h]) continue;
                     f.qOut[base + col[h]] = qo[h];
                     if (live) f.p[base + col[h]] = po[h];
+                    if (keep) keep[base + col[h]] = gv[u][h];
                 }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
             if (lane == 0) f.uturn[((size_t)(k & 1) * chains + c) * f.blocks + blockIdx.x] = dot;
+        }
+    }
+}
+
+// The first leap-frog stage (k = 0) when the gradient at the starting point is already known: a step
+// starts where the previous one started (rejected) or ended (accepted), and the previous step took
+// the gradient at both (LeapFused::gradStart / gradEnd; kHmcAccept keeps the right one in `grad`).
+// Element for element what kHmcLeapDmma's epilogue does for k = 0 -- half kick, drift, no U-turn
+// term -- without the GEMM: the same values, one gradient evaluation per step less.  One warp per
+// chain.
+__global__ void __launch_bounds__(128)
+kHmcLeapCached(LeapFused f, const double* __restrict__ grad, int chains, int n) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (c >= chains) return;
+    const int st = f.leapSteps[c];
+    const bool live = st >= 1;
+    const double eps = live ? f.epsilon[(size_t)c * f.scalarStride] : 0.0;
+    const size_t row = (size_t)c * n;
+    if ((n & 1) == 0) {
+        const int m = n >> 1;
+        const double2* q2 = reinterpret_cast<const double2*>(f.qIn + row);
+        const double2* g2 = reinterpret_cast<const double2*>(grad + row);
+        double2* p2 = reinterpret_cast<double2*>(f.p + row);
+        double2* o2 = reinterpret_cast<double2*>(f.qOut + row);
+        for (int i = lane; i < m; i += 64) {
+            const bool two = i + 32 < m;
+            double2 q[2], g[2], p[2];
+            q[0] = q2[i];
+            if (two) q[1] = q2[i + 32];
+            if (live) {
+                g[0] = g2[i]; p[0] = p2[i];
+                if (two) { g[1] = g2[i + 32]; p[1] = p2[i + 32]; }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (u == 1 && !two) break;
+                double2 qo = q[u];
+                if (live) {
+                    double2 po;
+                    po.x = __dsub_rn(p[u].x, __ddiv_rn(__dmul_rn(eps, g[u].x), 2.0));
+                    po.y = __dsub_rn(p[u].y, __ddiv_rn(__dmul_rn(eps, g[u].y), 2.0));
+                    qo.x = __dadd_rn(q[u].x, __dmul_rn(eps, po.x));
+                    qo.y = __dadd_rn(q[u].y, __dmul_rn(eps, po.y));
+                    p2[i + 32 * u] = po;
+                }
+                o2[i + 32 * u] = qo;
+            }
+        }
+    } else {
+        for (int i = lane; i < n; i += 32) {
+            double qo = f.qIn[row + i];
+            if (live) {
+                const double po = __dsub_rn(f.p[row + i], __ddiv_rn(__dmul_rn(eps, grad[row + i]), 2.0));
+                qo = __dadd_rn(qo, __dmul_rn(eps, po));
+                f.p[row + i] = po;
+            }
+            f.qOut[row + i] = qo;
         }
     }
 }

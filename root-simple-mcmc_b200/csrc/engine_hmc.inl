@@ -83,6 +83,8 @@ HmcArrays hmcArrays(smcmc_engine* e) {
     a.pProp = h.pProp.get();
     a.p0 = h.p0.get();
     a.grad = h.grad.get();
+    a.gradCur = nullptr;                 // set by hmcStepOnce for the steps that keep the gradients
+    a.gradEnd = nullptr;
     a.central = h.central.get();
     a.average = h.average.get();
     a.exxt = h.exxt.get();
@@ -254,12 +256,22 @@ void hmcStepOnce(smcmc_engine* e, int type, const HmcTraceDev& tr, int traceStep
     // ... and when every running chain has a trajectory, the potential at its end comes out of the
     // chain's last gradient launch (LeapFused::endPartial) instead of a GEMM of its own
     bool potentialDone = false;
+    bool keepGradients = false;
     if (maxSteps >= 1 && fused) {
         const int colBlocks = ceilDiv(n, kDmmaBN);
         h.qAlt.reserve((size_t)E * n);
         h.uturn.reserve((size_t)2 * E * colBlocks);
         const bool endPotential = h.hostCounters[2] == 0 && !std::getenv("SMCMC_HMC_SEPARATE_POTENTIAL");
         if (endPotential) e->dummyPartials.reserve((size_t)E * colBlocks);
+        // The gradient at the starting point is known from the previous step (kHmcLeapCached): every
+        // step keeps the gradients at its start and at its end point, kHmcAccept the one at the point
+        // the chain goes on from.  Needs every running chain to have a trajectory, this step and the last.
+        keepGradients = h.hostCounters[2] == 0 && !std::getenv("SMCMC_HMC_NO_GRADIENT_CACHE");
+        const bool cached = keepGradients && h.gradCacheReady;
+        if (keepGradients) {
+            h.gradCur.reserve((size_t)E * n);
+            h.gradEnd.reserve((size_t)E * n);
+        }
         LeapFused f;
         f.p = h.pProp.get();
         f.p0 = h.p0.get();
@@ -270,6 +282,8 @@ void hmcStepOnce(smcmc_engine* e, int type, const HmcTraceDev& tr, int traceStep
         f.uturn = h.uturn.get();
         f.blocks = colBlocks;
         f.endPartial = endPotential ? e->dummyPartials.get() : nullptr;
+        f.gradStart = keepGradients && !cached ? h.gradCur.get() : nullptr;
+        f.gradEnd = keepGradients ? h.gradEnd.get() : nullptr;
         // Ragged trajectory lengths (each chain tunes its own, :302-323): the launches take the chains in
         // order of length, so that the row tiles behind the chains that still run skip the GEMM
         // (kHmcLeapDmma).  The lengths are read back next to the counter above; ordering them is a
@@ -315,11 +329,16 @@ void hmcStepOnce(smcmc_engine* e, int type, const HmcTraceDev& tr, int traceStep
             f.qIn = h.qProp.get();
             f.qOut = h.qAlt.get();
             if (f.order) f.gemmTiles = gemmTiles[k];
-            launchHmcLeapDmma(e->stream, e->errMatrix.get(), f, k, E, n);
+            if (k == 0 && cached) kHmcLeapCached<<<ceilDiv(E, 4), 128, 0, e->stream>>>(f, h.gradCur.get(), E, n);
+            else launchHmcLeapDmma(e->stream, e->errMatrix.get(), f, k, E, n);
             e->launched();
             h.qProp.swap(h.qAlt);                                        // the proposed positions are in the buffer just written
         }
         a = hmcArrays(e);
+        if (keepGradients) {
+            a.gradCur = h.gradCur.get();
+            a.gradEnd = h.gradEnd.get();
+        }
         if (endPotential) {
             kDummyLlhFromPartials<<<ceilDiv(E, 128), 128, 0, e->stream>>>(e->dummyPartials.get(), colBlocks, E, h.llh.get());
             e->launched();
@@ -372,6 +391,7 @@ void hmcStepOnce(smcmc_engine* e, int type, const HmcTraceDev& tr, int traceStep
         kHmcErrorMatrix<<<ceilDiv(updates, kWarpsPerBlock), threads, 0, e->stream>>>(a, n, updates, h.avgLlh.get());
         e->launched();
     }
+    h.gradCacheReady = keepGradients;                                     // (kHmcAccept below completes it)
     const uint32_t acceptSlot = (h.alpha >= 1.0 ? 0u : (uint32_t)n) + 1u;
     kHmcAccept<<<blocks, threads, 0, e->stream>>>(a, n, E, e->cfg.seed, e->cfg.chain_offset, e->stepIndex,
                                                   acceptSlot, tr, traceStep);
@@ -423,6 +443,7 @@ int smcmc_hmc_start(smcmc_engine* e, const double* x0) {
         if (h.keepError) h.estErr.reserve(E * n * n);
         // scratch for UpdateErrorMatrix: eigenvalues and the inverse share the engine's slots
         CUDA_CHECK(cudaMemcpyAsync(h.qAcc.get(), x0, E * n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        h.gradCacheReady = false;                                          // new points: no gradient is known there
         e->evaluate(h.qAcc.get(), (int)E, h.llh.get(), nullptr);           // SetPosition, :221
         h.sinceFlush = 0;                                                  // kHmcStart empties the rings
         if (h.pooled) {
@@ -457,6 +478,7 @@ int smcmc_hmc_set_position(smcmc_engine* e, const double* x) {
         HmcHost& h = e->hmc;
         const size_t E = e->E(), n = e->n();
         CUDA_CHECK(cudaMemcpyAsync(h.qAcc.get(), x, E * n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        h.gradCacheReady = false;
         e->evaluate(h.qAcc.get(), (int)E, h.llh.get(), nullptr);
         kHmcSetPosition<<<ceilDiv((long long)E, 128), 128, 0, e->stream>>>(hmcArrays(e), (int)E, h.llh.get());
         e->launched();

@@ -95,6 +95,8 @@ struct HmcArrays {
     double* pProp;      // fProposedMomentum
     double* p0;         // LeapFrog's copy of the starting momentum (:587)
     double* grad;
+    double* gradCur;    // fused tensor path (kHmcLeapCached): the gradient at fAccepted, or nullptr ...
+    double* gradEnd;    // ... and the one at fProposed, which replaces it when the step is accepted
     double* central;    // fCentralPoint
     double* average;    // fAveragePoint
     double* exxt;       // fEXXT, packed lower triangle
@@ -1361,6 +1363,7 @@ kHmcAccept(HmcArrays a, int n, int chains, uint64_t seed, uint32_t chainOffset, 
     } else {
         warpCopyRow<false>(a.qAcc + row, a.qProp + row, n, lane);        // :380-383
         warpCopyRow<false>(a.pAcc + row, a.pProp + row, n, lane);
+        if (a.gradCur) warpCopyRow<false>(a.gradCur + row, a.gradEnd + row, n, lane);
         s.accPotential = s.propPotential;                                 // :384
         s.acceptance = __ddiv_rn(__dadd_rn(__dmul_rn(s.acceptance, 4999.0), 1.0), 5000.0);   // :386
     }

@@ -254,13 +254,19 @@ def test_fused_leapfrog_stage_equals_gradient_plus_kick_drift(monkeypatch, n, E)
     prec = hmc_error_matrix("spd%d" % n)
     runs = {}
     # fused = 2: the fused launches take the chains in order of trajectory length (rows behind the
-    # chains that still run skip the GEMM) even where the engine would not bother
-    for fused in (1, 0, 2):
-        monkeypatch.delenv("SMCMC_HMC_ORDER_ALWAYS", raising=False)
+    # chains that still run skip the GEMM) even where the engine would not bother;
+    # fused = 3: every step computes its first gradient instead of taking it from the previous step,
+    # and the likelihood of the proposed point by a contraction of its own
+    for fused in (1, 0, 2, 3):
+        for name in ("SMCMC_HMC_ORDER_ALWAYS", "SMCMC_HMC_NO_GRADIENT_CACHE", "SMCMC_HMC_SEPARATE_POTENTIAL"):
+            monkeypatch.delenv(name, raising=False)
         if fused:
             monkeypatch.delenv("SMCMC_HMC_NO_FUSE", raising=False)
             if fused == 2:
                 monkeypatch.setenv("SMCMC_HMC_ORDER_ALWAYS", "1")
+            if fused == 3:
+                monkeypatch.setenv("SMCMC_HMC_NO_GRADIENT_CACHE", "1")
+                monkeypatch.setenv("SMCMC_HMC_SEPARATE_POTENTIAL", "1")
         else:
             monkeypatch.setenv("SMCMC_HMC_NO_FUSE", "1")
         h = smcmc_b200.Engine(smcmc_b200.LLH_DUMMY, n, E, seed=6)
@@ -277,7 +283,9 @@ def test_fused_leapfrog_stage_equals_gradient_plus_kick_drift(monkeypatch, n, E)
     for k in ("potential", "points", "mean_epsilon", "leapfrog", "accepted", "scalars", "momentum"):
         assert np.array_equal(runs[1][k], runs[0][k]), k
         assert np.array_equal(runs[2][k], runs[0][k]), k
+        assert np.array_equal(runs[3][k], runs[0][k]), k
     assert runs[1]["launches"] < 0.62 * runs[0]["launches"]       # one launch per stage instead of two
+    assert runs[1]["launches"] < runs[3]["launches"]
     assert np.abs(runs[1]["leapfrog"]).max() > 10 and runs[1]["accepted"].sum() > 0
     if E >= 700:                                                  # the ordering has something to order
         lf = np.abs(runs[1]["leapfrog"])
