@@ -1550,6 +1550,7 @@ int smcmc_dummy_set_mode(smcmc_engine* e, int mode) {
         if (e->cfg.likelihood != SMCMC_LLH_DUMMY) throw Error(SMCMC_ERR_LOGIC, "engine was not created with SMCMC_LLH_DUMMY");
         if (mode != SMCMC_DUMMY_EXACT && mode != SMCMC_DUMMY_TENSOR) throw Error(SMCMC_ERR_INVALID_ARGUMENT, "unknown mode");
         e->dummyMode = mode;
+        e->hmc.gradCacheReady = false;                 // (kHmcLeapCached: gradients kept from the other mode's arithmetic)
     });
 }
 
@@ -1565,6 +1566,7 @@ int smcmc_dummy_set_error(smcmc_engine* e, const double* err, int nn) {
         CUDA_CHECK(cudaMemcpyAsync(e->errMatrix.get(), err, sizeof(double) * nn * nn, cudaMemcpyHostToDevice, e->stream));
         CUDA_CHECK(cudaMemcpyAsync(e->errMatrixT.get(), t.data(), sizeof(double) * nn * nn, cudaMemcpyHostToDevice, e->stream));
         CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        e->hmc.gradCacheReady = false;                 // the gradients kept belong to the old matrix
         e->errDim = nn;
     });
 }
