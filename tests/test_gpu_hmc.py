@@ -290,3 +290,38 @@ def test_fused_leapfrog_stage_equals_gradient_plus_kick_drift(monkeypatch, n, E)
     if E >= 700:                                                  # the ordering has something to order
         lf = np.abs(runs[1]["leapfrog"])
         assert max(len(np.unique(lf[s])) for s in range(lf.shape[0])) > 1
+
+
+def test_kept_gradients_are_dropped_when_the_points_or_the_matrix_change(monkeypatch):
+    """TENSOR mode takes the first gradient of a step from the previous step (kHmcLeapCached).  Moving
+    the chains (SetPosition), restarting them, changing the error matrix or running a step of another
+    kind in between must drop what was kept: the run equals the one that computes every gradient
+    (SMCMC_HMC_NO_GRADIENT_CACHE=1) bit for bit."""
+    import smcmc_b200
+    from smcmc_b200 import binding as b
+    n, E = 96, 150
+    prec, prec2 = hmc_error_matrix("spd%d" % n), hmc_error_matrix("spd%d" % n) * 1.25
+    runs = []
+    for cache in (1, 0):
+        if cache:
+            monkeypatch.delenv("SMCMC_HMC_NO_GRADIENT_CACHE", raising=False)
+        else:
+            monkeypatch.setenv("SMCMC_HMC_NO_GRADIENT_CACHE", "1")
+        h = smcmc_b200.Engine(smcmc_b200.LLH_DUMMY, n, E, seed=9)
+        h.set_error_matrix(prec)
+        h.set_dummy_mode(b.DUMMY_TENSOR)
+        h.hmc_set(b.HMC_USER_GRADIENT, 1)
+        h.hmc_start(np.full(n, 0.3))
+        out = [h.hmc_step_trace(6, 0)]
+        h.hmc_set_position(np.random.default_rng(3).normal(0, 0.4, (E, n)))
+        out.append(h.hmc_step_trace(5, 0))
+        h.set_error_matrix(prec2)
+        out.append(h.hmc_step_trace(5, 0))
+        h.hmc_step(2, 5)                                   # gradient type 5 (zero gradient): another kind of step
+        out.append(h.hmc_step_trace(5, 0))
+        h.hmc_start(np.full(n, -0.2))
+        out.append(h.hmc_step_trace(5, 0))
+        runs.append(out)
+    for a, c in zip(*runs):
+        for k in ("potential", "points", "mean_epsilon", "leapfrog", "accepted"):
+            assert np.array_equal(a[k], c[k]), k
