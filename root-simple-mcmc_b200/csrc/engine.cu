@@ -65,7 +65,8 @@ struct HmcHost {
     DeviceBuffer<double> qAlt, uturn;    // fused leap-frog stage (kHmcLeapDmma): the second q buffer, the U-turn partials
     DeviceBuffer<int> order;             // ... and the chains ordered by trajectory length (ragged ensembles)
     DeviceBuffer<double> gradCur, gradEnd;   // ... the gradients at the accepted and the proposed points (kHmcLeapCached)
-    bool gradCacheReady = false;         // gradCur holds the gradient at every running chain's accepted point
+    bool gradCacheReady = false;         // gradCur holds the gradient at every running chain's accepted point ...
+    int gradCacheMode = -1;              // ... as the path that kept it computes it (gradient kind; 100: fused tensor stage)
     int* hostSteps = nullptr;            // pinned, 2 x chains: the trajectory lengths read back, the order sent
     DeviceBuffer<HmcScalars> sc;
     DeviceBuffer<int> leapSteps, counters, updateList;

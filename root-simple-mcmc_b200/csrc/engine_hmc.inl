@@ -267,7 +267,7 @@ void hmcStepOnce(smcmc_engine* e, int type, const HmcTraceDev& tr, int traceStep
         // step keeps the gradients at its start and at its end point, kHmcAccept the one at the point
         // the chain goes on from.  Needs every running chain to have a trajectory, this step and the last.
         keepGradients = h.hostCounters[2] == 0 && !std::getenv("SMCMC_HMC_NO_GRADIENT_CACHE");
-        const bool cached = keepGradients && h.gradCacheReady;
+        const bool cached = keepGradients && h.gradCacheReady && h.gradCacheMode == 100;
         if (keepGradients) {
             h.gradCur.reserve((size_t)E * n);
             h.gradEnd.reserve((size_t)E * n);
@@ -338,6 +338,7 @@ void hmcStepOnce(smcmc_engine* e, int type, const HmcTraceDev& tr, int traceStep
         if (keepGradients) {
             a.gradCur = h.gradCur.get();
             a.gradEnd = h.gradEnd.get();
+            h.gradCacheMode = 100;                                       // the fused tensor path
         }
         if (endPotential) {
             kDummyLlhFromPartials<<<ceilDiv(E, 128), 128, 0, e->stream>>>(e->dummyPartials.get(), colBlocks, E, h.llh.get());
@@ -345,10 +346,30 @@ void hmcStepOnce(smcmc_engine* e, int type, const HmcTraceDev& tr, int traceStep
             potentialDone = true;
         }
     } else if (maxSteps >= 1) {
+        // The same in the general path, for the gradients that are functions of the point alone -- the
+        // built-in analytic ones and finite differences of a built-in likelihood (2n likelihoods per
+        // gradient): the gradient kernel of k = 0 is skipped when the previous step left the gradient at
+        // the chain's point.  (A user functor is called as often as the reference calls it.)
+        const bool pure = e->cfg.likelihood != SMCMC_LLH_USER && (mode == kGradUser || mode == kGradFinite);
+        keepGradients = pure && h.hostCounters[2] == 0 && !std::getenv("SMCMC_HMC_NO_GRADIENT_CACHE");
+        const bool cached = keepGradients && h.gradCacheReady && h.gradCacheMode == (int)mode;
+        if (keepGradients) {
+            h.gradCur.reserve((size_t)E * n);
+            h.gradEnd.reserve((size_t)E * n);
+        }
         for (int k = 0; k <= maxSteps; ++k) {
-            hmcGradient(e, mode, k);
-            kHmcKickDrift<<<blocks, threads, smem, e->stream>>>(a, n, E, k, countPotentials);
+            HmcArrays ak = a;
+            if (k == 0 && cached) ak.grad = h.gradCur.get();
+            else hmcGradient(e, mode, k);
+            kHmcKickDrift<<<blocks, threads, smem, e->stream>>>(ak, n, E, k, countPotentials,
+                                                                keepGradients && !cached ? h.gradCur.get() : nullptr,
+                                                                keepGradients ? h.gradEnd.get() : nullptr);
             e->launched();
+        }
+        if (keepGradients) {
+            a.gradCur = h.gradCur.get();
+            a.gradEnd = h.gradEnd.get();
+            h.gradCacheMode = (int)mode;
         }
     }
     if (!potentialDone) e->evaluate(h.qProp.get(), E, h.llh.get(), nullptr);   // :327

@@ -334,7 +334,8 @@ kHmcBegin(HmcArrays a, int n, int chains, double alpha, uint64_t seed, uint32_t 
 // differences, :436-438).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-kHmcKickDrift(HmcArrays a, int n, int chains, int k, int countPotentials) {
+kHmcKickDrift(HmcArrays a, int n, int chains, int k, int countPotentials,
+              double* keepStart = nullptr, double* keepEnd = nullptr /* the gradient of k = 0 / of k = steps is kept here */) {
     extern __shared__ double smemD[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -369,6 +370,8 @@ kHmcKickDrift(HmcArrays a, int n, int chains, int k, int countPotentials) {
             if (half) kick = __ddiv_rn(kick, 2.0);
             const double p = __dsub_rn(pp[u], kick);
             a.pProp[row + i] = p;
+            if (k == 0 && keepStart) keepStart[row + i] = g[u];
+            if (k == steps && keepEnd) keepEnd[row + i] = g[u];
             if (!half) buf[i] = __dmul_rn(p, p0v[u]);                     // :635
             if (drift) a.qProp[row + i] = __dadd_rn(q[u], __dmul_rn(eps, p));
         }
