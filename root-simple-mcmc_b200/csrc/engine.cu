@@ -16,6 +16,7 @@
 #include "diagnostics.cuh"
 #include "fake_likelihood.cuh"
 #include "hmc.cuh"
+#include "hmc_order.h"
 #include "nccl_dyn.h"
 #include "pooled.cuh"
 #include "proposal.cuh"

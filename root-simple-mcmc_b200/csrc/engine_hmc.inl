@@ -292,34 +292,15 @@ void hmcStepOnce(smcmc_engine* e, int type, const HmcTraceDev& tr, int traceStep
         f.order = nullptr;
         f.gemmTiles = 0;
         if (wantOrder) {
-            std::vector<int> atLeast(maxSteps + 2, 0);             // atLeast[k] = chains with length >= k
-            for (int c = 0; c < E; ++c) {
-                const int st = h.hostSteps[c];
-                if (st >= 1) atLeast[std::min(st, maxSteps)] += 1;
-            }
-            for (int k = maxSteps - 1; k >= 1; --k) atLeast[k] += atLeast[k + 1];
-            const long long allTiles = (long long)(maxSteps + 1) * ceilDiv(E, kDmmaBM);
-            long long busyTiles = 0;
+            // (hmc_order.h: counting sort -- longest first, equal lengths in chain order, chains without a
+            // trajectory last -- and the row tiles each launch needs; checked on the CPU by tests/test_rng.py)
+            std::vector<int> scratch(maxSteps + 2);
             gemmTiles.resize(maxSteps + 1);
-            for (int k = 0; k <= maxSteps; ++k) {
-                gemmTiles[k] = ceilDiv(atLeast[std::max(k, 1)], kDmmaBM);
-                busyTiles += gemmTiles[k];
-            }
+            const long long allTiles = (long long)(maxSteps + 1) * ceilDiv(E, kDmmaBM);
+            const long long busyTiles = smcmc_hmc_order(h.hostSteps, E, maxSteps, kDmmaBM, nullptr, gemmTiles.data(), scratch.data());
             if (busyTiles * 100 <= allTiles * 97 || std::getenv("SMCMC_HMC_ORDER_ALWAYS")) {
-                // longest first, equal lengths in chain order; chains without a trajectory last
                 int* order = h.hostSteps + E;
-                std::vector<int> next(maxSteps + 2, 0);            // first position of each length
-                int pos = 0;
-                for (int st = maxSteps; st >= 1; --st) {
-                    next[st] = pos;
-                    pos += atLeast[st] - atLeast[st + 1];
-                }
-                int tail = pos;
-                for (int c = 0; c < E; ++c) {
-                    const int st = h.hostSteps[c];
-                    if (st >= 1) order[next[std::min(st, maxSteps)]++] = c;
-                    else order[tail++] = c;
-                }
+                smcmc_hmc_order(h.hostSteps, E, maxSteps, kDmmaBM, order, gemmTiles.data(), scratch.data());
                 h.order.reserve(E);
                 CUDA_CHECK(cudaMemcpyAsync(h.order.get(), order, (size_t)E * sizeof(int), cudaMemcpyHostToDevice, e->stream));
                 f.order = h.order.get();

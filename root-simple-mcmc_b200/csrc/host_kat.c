@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include "smcmc_rng.h"
 #include "seqsum.h"
+#include "hmc_order.h"
 
 void smcmc_kat_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
     smcmc_u32x4 r = smcmc_philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
@@ -35,4 +36,9 @@ double smcmc_kat_seq_add(double s, double w, uint32_t n) { return smcmc_seq_add(
 double smcmc_kat_seq_add_naive(double s, double w, uint32_t n) {
     for (uint32_t i = 0; i < n; ++i) s = s + w;
     return s;
+}
+
+/* the chains of an HMC ensemble in order of trajectory length (hmc_order.h) */
+long long smcmc_kat_hmc_order(const int* steps, int chains, int maxSteps, int tile, int* order, int* tiles, int* scratch) {
+    return smcmc_hmc_order(steps, chains, maxSteps, tile, order, tiles, scratch);
 }

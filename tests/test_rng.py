@@ -141,3 +141,37 @@ def test_sequential_sum_emulation_is_exact(kat):
                     (0.0, float("inf"), 5), (0.0, -0.5, 7), (3.0, 0.09582700887723655, 1000020)]:
         a, b = kat.smcmc_kat_seq_add(s, w, n), kat.smcmc_kat_seq_add_naive(s, w, n)
         assert a == b or (math.isnan(a) and math.isnan(b))
+
+
+def test_hmc_chains_in_order_of_trajectory_length():
+    """csrc/hmc_order.h (host code of the fused HMC stage): chains sorted by trajectory length, longest
+    first, equal lengths in chain order, chains without a trajectory last; and per gradient k the row
+    tiles that hold every chain taking part in it."""
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(PKG, "smcmc_b200", "libsmcmc_hostkat.so"))
+    lib.smcmc_kat_hmc_order.restype = ctypes.c_longlong
+    lib.smcmc_kat_hmc_order.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_void_p]
+    rng = np.random.default_rng(11)
+    for chains, top, tile in [(1, 3, 64), (63, 5, 64), (700, 9, 64), (16384, 50, 64), (1000, 1, 64), (257, 1500, 16)]:
+        steps = rng.integers(-1, top + 1, chains).astype(np.int32)
+        steps[rng.integers(0, chains)] = top                       # the longest length is present
+        order = np.full(chains, -1, np.int32)
+        tiles = np.zeros(top + 1, np.int32)
+        scratch = np.zeros(top + 2, np.int32)
+        busy = lib.smcmc_kat_hmc_order(steps.ctypes.data, chains, top, tile, order.ctypes.data, tiles.ctypes.data,
+                                       scratch.ctypes.data)
+        assert sorted(order.tolist()) == list(range(chains))       # a permutation
+        running = steps[order] >= 1
+        assert not np.any(running[1:] & ~running[:-1])             # chains without a trajectory last ...
+        assert np.all(np.diff(order[~running]) > 0)                # ... in chain order
+        key = steps[order][running]
+        assert np.all(np.diff(key) <= 0)                           # lengths descending
+        same = np.diff(key) == 0
+        assert np.all(np.diff(order[running])[same] > 0)           # equal lengths in chain order
+        want = [-(-int(np.sum(steps >= max(k, 1))) // tile) for k in range(top + 1)]
+        assert tiles.tolist() == want and busy == sum(want)
+        # the first tiles[k] row tiles hold every chain of gradient k
+        for k in (0, 1, top // 2, top):
+            active = set(np.nonzero(steps >= max(k, 1))[0].tolist())
+            assert active <= set(order[: tiles[k] * tile].tolist())
